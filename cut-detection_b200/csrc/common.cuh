@@ -1,0 +1,41 @@
+// Shared helpers for libcutdet_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cutdet_b200.h"
+
+namespace cutdet {
+
+// Thread-local error text behind cutdet_last_error().
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define CUTDET_CUDA(expr)                                           \
+    do {                                                            \
+        cudaError_t _e = (expr);                                    \
+        if (_e != cudaSuccess) return ::cutdet::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define CUTDET_LAUNCH_CHECK(name)                                   \
+    do {                                                            \
+        cudaError_t _e = cudaGetLastError();                        \
+        if (_e != cudaSuccess) return ::cutdet::cuda_fail(_e, name); \
+    } while (0)
+
+#define CUTDET_REQUIRE(cond, ...)                                   \
+    do {                                                            \
+        if (!(cond)) return ::cutdet::fail(CUTDET_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+static inline cudaStream_t as_stream(cutdet_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int sm_count();
+
+}  // namespace cutdet

@@ -1,0 +1,49 @@
+// Internal layout of a cutdet_net and the launchers of its kernels.
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace cutdet {
+
+struct ConvLayer {
+    int cin = 0, cout = 0;
+    bool set = false;
+    std::vector<float> w;       // [cout][cin][3][3] as given
+    std::vector<float> bias;    // [cout]
+    std::vector<float> scale;   // gamma / sqrt(var + eps)
+    std::vector<float> shift;   // beta - mean * scale
+    // generic path (device, float32)
+    float *d_w_t = nullptr;     // [cin][9][cout_padded8]
+    float *d_bias = nullptr, *d_scale = nullptr, *d_shift = nullptr;
+};
+
+struct FcLayer {
+    int in = 0, out = 0;
+    bool set = false, has_bn = false;
+    std::vector<float> w, bias, scale, shift;
+    float *d_w = nullptr, *d_bias = nullptr, *d_scale = nullptr, *d_shift = nullptr;
+};
+
+struct LayerGeom {
+    int cin, cout, h, w, ph, pw;   // conv input h x w, pooled output ph x pw
+};
+
+// generic CUDA-core kernels (any architecture the reference's constructors can build)
+int launch_conv_block_generic(const float *in, float *out, const ConvLayer &L, int batch, int h, int w,
+                              cudaStream_t stream);
+int launch_avgpool_flatten(const float *in, float *out, int batch, int c, int h, int w, int pool,
+                           cudaStream_t stream);
+int launch_fc(const float *in, float *out, const FcLayer &L, int batch, bool relu, cudaStream_t stream);
+
+}  // namespace cutdet
+
+struct cutdet_net {
+    cutdet_net_config cfg;
+    std::vector<cutdet::ConvLayer> conv;
+    std::vector<cutdet::FcLayer> fc;
+    bool finalized = false;
+    std::vector<void *> dev_allocs;
+    struct TcState *tc = nullptr;   // tensor-core path (conv_tc.cu), null when not applicable
+};

@@ -1,0 +1,235 @@
+// K1: decoded uint8 BGR HWC frames -> resized / normalised model input.
+//
+// Stands in for VideoDataset.__next__ (reference frameID/data.py:218-228):
+//     cv2.resize(frame, (W2, H2), INTER_LINEAR) -> float -> permute(2,0,1) -> flip(BGR->RGB) -> /255
+// The resize arithmetic is OpenCV's 11-bit fixed point for uint8 images (see oracle/preprocess.py for the
+// restatement it is tested against, bit for bit):
+//     S   = a0 * p[x0] + a1 * p[x0 + 1]                                  (horizontal, int32)
+//     out = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2   (vertical)
+// with an exact 2x2 box mean when both scales are exactly 2, and a plain copy at scale 1.
+//
+// The tap tables are built on the host with the same float32 steps OpenCV takes and live in a
+// cutdet_resize_plan.  Taps whose weight is zero are never loaded: at 1280x720 -> 256x144 (scale 5) every
+// second tap has weight 0, so the kernel touches only source rows 5y+2 -- 144 of the 720 rows.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "preprocess.cuh"
+
+namespace cutdet {
+
+namespace {
+
+void linear_taps(int src, int dst, bool clamp_weights, std::vector<int> &i0, std::vector<int> &i1,
+                 std::vector<int> &w0, std::vector<int> &w1) {
+    i0.resize(dst); i1.resize(dst); w0.resize(dst); w1.resize(dst);
+    const double scale = 1.0 / ((double)dst / (double)src);
+    for (int d = 0; d < dst; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (clamp_weights) {
+            if (s < 0) { f = 0.f; s = 0; }
+            if (s >= src - 1) { f = 0.f; s = src - 1; }
+        }
+        w0[d] = (int)lrintf((1.f - f) * 2048.f);   // round half to even, like cvRound
+        w1[d] = (int)lrintf(f * 2048.f);
+        int a = s < 0 ? 0 : (s > src - 1 ? src - 1 : s);
+        int b = s + 1 < 0 ? 0 : (s + 1 > src - 1 ? src - 1 : s + 1);
+        i0[d] = a;
+        i1[d] = b;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------- kernels
+// One thread per output pixel, x fastest.  OUT: 0 = float32 NCHW RGB /255, 1 = uint8 HWC BGR.
+template <int OUT>
+__global__ void __launch_bounds__(256) preprocess_generic_kernel(ResizePlanDev plan, const uint8_t *__restrict__ frames,
+                                                                 int64_t frame_stride, int64_t row_pitch, int compact,
+                                                                 void *__restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x >= plan.dst_w || y >= plan.dst_h) return;
+    const uint8_t *frame = frames + (int64_t)b * frame_stride;
+    int v[3];
+    if (plan.mode == RESIZE_COPY) {
+        const int r = compact ? plan.row_slot[y] : y;
+        const uint8_t *p = frame + (int64_t)r * row_pitch + 3 * x;
+        v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+    } else if (plan.mode == RESIZE_AREA2) {
+        const int r0 = compact ? plan.row_slot[2 * y] : 2 * y;
+        const int r1 = compact ? plan.row_slot[2 * y + 1] : 2 * y + 1;
+        const uint8_t *p0 = frame + (int64_t)r0 * row_pitch + 6 * x;
+        const uint8_t *p1 = frame + (int64_t)r1 * row_pitch + 6 * x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = (p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2;
+    } else {
+        const int x0 = plan.x0[x], x1 = plan.x1[x], a0 = plan.a0[x], a1 = plan.a1[x];
+        const int y0 = plan.y0[y], y1 = plan.y1[y], b0 = plan.b0[y], b1 = plan.b1[y];
+        const int r0 = compact ? plan.row_slot[y0] : y0;
+        const uint8_t *p0 = frame + (int64_t)r0 * row_pitch;
+        int s0[3], s1[3] = {0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int s = a0 * p0[3 * x0 + c];
+            if (a1 != 0) s += a1 * p0[3 * x1 + c];
+            s0[c] = s;
+        }
+        if (b1 != 0) {
+            const int r1 = compact ? plan.row_slot[y1] : y1;
+            const uint8_t *p1 = frame + (int64_t)r1 * row_pitch;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                int s = a0 * p1[3 * x0 + c];
+                if (a1 != 0) s += a1 * p1[3 * x1 + c];
+                s1[c] = s;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int o = (((b0 * (s0[c] >> 4)) >> 16) + ((b1 * (s1[c] >> 4)) >> 16) + 2) >> 2;
+            v[c] = min(max(o, 0), 255);
+        }
+    }
+    if (OUT == 0) {
+        float *o = reinterpret_cast<float *>(out);
+        const int64_t plane = (int64_t)plan.dst_h * plan.dst_w;
+        const int64_t base = (int64_t)b * 3 * plane + (int64_t)y * plan.dst_w + x;
+        // BGR -> RGB: output channel 0 is source channel 2.  True float32 division, as the reference does.
+        o[base] = __fdiv_rn((float)v[2], 255.f);
+        o[base + plane] = __fdiv_rn((float)v[1], 255.f);
+        o[base + 2 * plane] = __fdiv_rn((float)v[0], 255.f);
+    } else {
+        uint8_t *o = reinterpret_cast<uint8_t *>(out) + ((int64_t)b * plan.dst_h * plan.dst_w + (int64_t)y * plan.dst_w + x) * 3;
+        o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
+    }
+}
+
+int check_frames(const cutdet_resize_plan *plan, const cutdet_frames *src) {
+    CUTDET_REQUIRE(plan && src && src->frames_dev, "preprocess: null plan/frames");
+    CUTDET_REQUIRE(src->batch >= 0, "preprocess: negative batch");
+    CUTDET_REQUIRE(src->row_pitch >= 3 * (int64_t)plan->host.src_w, "preprocess: row_pitch %lld < 3*width", (long long)src->row_pitch);
+    const int rows = src->row_map_compact ? plan->n_rows : plan->host.src_h;
+    CUTDET_REQUIRE(src->batch <= 1 || src->frame_stride >= src->row_pitch * (int64_t)(rows - 1) + 3 * (int64_t)plan->host.src_w,
+                   "preprocess: frame_stride too small");
+    return CUTDET_OK;
+}
+
+template <int OUT>
+static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *src, void *out, cutdet_stream_t stream) {
+    if (int rc = check_frames(plan, src)) return rc;
+    CUTDET_REQUIRE(out, "preprocess: null output");
+    if (src->batch == 0) return CUTDET_OK;
+    dim3 block(64, 4, 1);
+    for (int b0 = 0; b0 < src->batch; b0 += 65535) {
+        const int nb = src->batch - b0 < 65535 ? src->batch - b0 : 65535;
+        dim3 grid((unsigned)ceil_div(plan->host.dst_w, 64), (unsigned)ceil_div(plan->host.dst_h, 4), (unsigned)nb);
+        const int64_t out_frame = (int64_t)plan->host.dst_h * plan->host.dst_w * 3;
+        void *o = OUT == 0 ? (void *)((float *)out + b0 * out_frame) : (void *)((uint8_t *)out + b0 * out_frame);
+        preprocess_generic_kernel<OUT><<<grid, block, 0, as_stream(stream)>>>(
+            plan->host, src->frames_dev + (int64_t)b0 * src->frame_stride, src->frame_stride, src->row_pitch,
+            src->row_map_compact, o);
+        CUTDET_LAUNCH_CHECK("preprocess_generic_kernel");
+    }
+    return CUTDET_OK;
+}
+
+}  // namespace cutdet
+
+using namespace cutdet;
+
+extern "C" int cutdet_resize_plan_create(int src_h, int src_w, int dst_h, int dst_w, cutdet_resize_plan **out) {
+    CUTDET_REQUIRE(out, "resize_plan_create: null output");
+    CUTDET_REQUIRE(src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "resize_plan_create: bad geometry %dx%d -> %dx%d",
+                   src_w, src_h, dst_w, dst_h);
+    cutdet_resize_plan *plan = new cutdet_resize_plan();
+    ResizePlanDev &h = plan->host;
+    h.src_h = src_h; h.src_w = src_w; h.dst_h = dst_h; h.dst_w = dst_w;
+    std::vector<int> x0, x1, a0, a1, y0, y1, b0, b1;
+    std::vector<char> used(src_h, 0);
+    if (src_h == dst_h && src_w == dst_w) {
+        h.mode = RESIZE_COPY;
+        for (int y = 0; y < src_h; ++y) used[y] = 1;
+    } else if (src_w == 2 * dst_w && src_h == 2 * dst_h) {
+        h.mode = RESIZE_AREA2;
+        for (int y = 0; y < src_h; ++y) used[y] = 1;
+    } else {
+        h.mode = RESIZE_LINEAR;
+        linear_taps(src_w, dst_w, true, x0, x1, a0, a1);
+        linear_taps(src_h, dst_h, false, y0, y1, b0, b1);
+        for (int y = 0; y < dst_h; ++y) {
+            used[y0[y]] = 1;
+            if (b1[y] != 0) used[y1[y]] = 1;
+        }
+    }
+    h.all_a1_zero = 1; h.all_b1_zero = 1;
+    for (size_t i = 0; i < a1.size(); ++i) if (a1[i] != 0) h.all_a1_zero = 0;
+    for (size_t i = 0; i < b1.size(); ++i) if (b1[i] != 0) h.all_b1_zero = 0;
+    std::vector<int> slot(src_h, -1);
+    for (int y = 0; y < src_h; ++y)
+        if (used[y]) { slot[y] = (int)plan->rows.size(); plan->rows.push_back(y); }
+    // rows never read still need a defined slot (never dereferenced)
+    for (int y = 0; y < src_h; ++y) if (slot[y] < 0) slot[y] = 0;
+    plan->n_rows = (int)plan->rows.size();
+
+    // one device allocation for all tables
+    const size_t n_ints = 4 * (size_t)dst_w + 4 * (size_t)dst_h + (size_t)src_h;
+    std::vector<int> blob(n_ints, 0);
+    int *p = blob.data();
+    auto put = [&](const std::vector<int> &v, size_t n) { if (!v.empty()) memcpy(p, v.data(), n * sizeof(int)); int *r = p; p += n; return r; };
+    int *hx0 = put(x0, dst_w), *hx1 = put(x1, dst_w), *ha0 = put(a0, dst_w), *ha1 = put(a1, dst_w);
+    int *hy0 = put(y0, dst_h), *hy1 = put(y1, dst_h), *hb0 = put(b0, dst_h), *hb1 = put(b1, dst_h);
+    int *hslot = put(slot, src_h);
+    cudaError_t e = cudaMalloc(&plan->dev_blob, n_ints * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(plan->dev_blob, blob.data(), n_ints * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (plan->dev_blob) cudaFree(plan->dev_blob);
+        delete plan;
+        return cuda_fail(e, "resize_plan_create upload");
+    }
+    int *d = reinterpret_cast<int *>(plan->dev_blob);
+    h.x0 = d + (hx0 - blob.data()); h.x1 = d + (hx1 - blob.data());
+    h.a0 = d + (ha0 - blob.data()); h.a1 = d + (ha1 - blob.data());
+    h.y0 = d + (hy0 - blob.data()); h.y1 = d + (hy1 - blob.data());
+    h.b0 = d + (hb0 - blob.data()); h.b1 = d + (hb1 - blob.data());
+    h.row_slot = d + (hslot - blob.data());
+    // integer-scale gather fast path: every second tap has zero weight and taps are evenly spaced
+    h.gather_step_x = 0; h.gather_step_y = 0; h.gather_off_x = 0; h.gather_off_y = 0;
+    if (h.mode == RESIZE_LINEAR && h.all_a1_zero && h.all_b1_zero && dst_w > 1 && dst_h > 1) {
+        const int sx = x0[1] - x0[0], sy = y0[1] - y0[0];
+        bool ok = sx > 0 && sy > 0;
+        for (int x = 0; ok && x < dst_w; ++x) ok = (x0[x] == x0[0] + x * sx) && a0[x] == 2048;
+        for (int y = 0; ok && y < dst_h; ++y) ok = (y0[y] == y0[0] + y * sy) && b0[y] == 2048;
+        if (ok) { h.gather_step_x = sx; h.gather_step_y = sy; h.gather_off_x = x0[0]; h.gather_off_y = y0[0]; }
+    }
+    *out = plan;
+    return CUTDET_OK;
+}
+
+extern "C" void cutdet_resize_plan_destroy(cutdet_resize_plan *plan) {
+    if (!plan) return;
+    if (plan->dev_blob) cudaFree(plan->dev_blob);
+    delete plan;
+}
+
+extern "C" int cutdet_resize_plan_rows(const cutdet_resize_plan *plan, int *rows_host, int *n_rows_out) {
+    CUTDET_REQUIRE(plan && n_rows_out, "resize_plan_rows: null argument");
+    *n_rows_out = plan->n_rows;
+    if (rows_host) memcpy(rows_host, plan->rows.data(), plan->rows.size() * sizeof(int));
+    return CUTDET_OK;
+}
+
+extern "C" int cutdet_preprocess_f32(const cutdet_resize_plan *plan, const cutdet_frames *src, float *out_nchw_dev,
+                                     cutdet_stream_t stream) {
+    return launch_generic<0>(plan, src, out_nchw_dev, stream);
+}
+
+extern "C" int cutdet_preprocess_u8(const cutdet_resize_plan *plan, const cutdet_frames *src, uint8_t *out_hwc_dev,
+                                    cutdet_stream_t stream) {
+    return launch_generic<1>(plan, src, out_hwc_dev, stream);
+}

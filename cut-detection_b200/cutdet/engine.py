@@ -1,0 +1,344 @@
+"""Thin torch-facing wrappers over the C ABI: torch only supplies device memory and the stream.
+
+Every function here launches CUDA kernels from libcutdet_b200.so on the current torch stream and raises if the
+library is missing or the tensors are not on a CUDA device -- nothing is computed by PyTorch or on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+TABLE_COLUMNS = ("end_frames", "frame_types", "run_lengths", "start_frames", "score_means")  # Segmentation.te keys
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: this build has no CPU path (got device {t.device})")
+
+
+def device_check() -> dict:
+    sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+    _cabi.check(_cabi.lib().cutdet_device_check(C.byref(sm), C.byref(major), C.byref(minor)))
+    return {"sm_count": sm.value, "cc": (major.value, minor.value)}
+
+
+def target_size(width: int, height: int, resize: int = 256) -> tuple[int, int]:
+    """(new_width, new_height) per frameID/data.py:199-202."""
+    nw, nh = C.c_int(), C.c_int()
+    _cabi.check(_cabi.lib().cutdet_target_size(width, height, resize, C.byref(nw), C.byref(nh)))
+    return nw.value, nh.value
+
+
+# ----------------------------------------------------------------------------------------------- K1
+class ResizePlan:
+    """Tap tables of one cv2.resize(INTER_LINEAR) geometry, resident on the current device."""
+
+    def __init__(self, src_h: int, src_w: int, dst_h: int, dst_w: int):
+        self.src_h, self.src_w, self.dst_h, self.dst_w = src_h, src_w, dst_h, dst_w
+        handle = C.c_void_p()
+        _cabi.check(_cabi.lib().cutdet_resize_plan_create(src_h, src_w, dst_h, dst_w, C.byref(handle)))
+        self.handle = handle
+        n = C.c_int()
+        _cabi.check(_cabi.lib().cutdet_resize_plan_rows(self.handle, None, C.byref(n)))
+        rows = (C.c_int * n.value)()
+        _cabi.check(_cabi.lib().cutdet_resize_plan_rows(self.handle, rows, C.byref(n)))
+        self.rows = np.frombuffer(rows, dtype=np.int32).copy()   # source rows the resize reads
+
+    @classmethod
+    def for_video(cls, height: int, width: int, resize: int = 256) -> "ResizePlan":
+        nw, nh = target_size(width, height, resize)
+        return cls(height, width, nh, nw)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _cabi.lib().cutdet_resize_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _frames_struct(plan: ResizePlan, frames: torch.Tensor, compact: bool) -> _cabi.Frames:
+    _need_cuda(frames, "frames")
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
+        raise ValueError(f"frames must be uint8 [B, rows, width, 3], got {frames.dtype} {tuple(frames.shape)}")
+    rows = len(plan.rows) if compact else plan.src_h
+    if frames.shape[1] != rows or frames.shape[2] != plan.src_w:
+        raise ValueError(f"frames are {tuple(frames.shape[1:3])}, the plan expects ({rows}, {plan.src_w})")
+    if frames.stride(3) != 1 or frames.stride(2) != 3:
+        frames = frames.contiguous()
+    return _cabi.Frames(frames.data_ptr(), frames.stride(0), frames.stride(1), frames.shape[0], 1 if compact else 0), frames
+
+
+def preprocess_f32(plan: ResizePlan, frames: torch.Tensor, compact: bool = False, out: torch.Tensor | None = None):
+    """uint8 BGR HWC frames -> float32 RGB [B,3,H2,W2] in [0,1] (what VideoDataset yields, stacked)."""
+    fs, keep = _frames_struct(plan, frames, compact)
+    if out is None:
+        out = torch.empty((frames.shape[0], 3, plan.dst_h, plan.dst_w), dtype=torch.float32, device=frames.device)
+    _cabi.check(_cabi.lib().cutdet_preprocess_f32(plan.handle, C.byref(fs), out.data_ptr(), _stream()))
+    return out
+
+
+def preprocess_u8(plan: ResizePlan, frames: torch.Tensor, compact: bool = False):
+    """uint8 BGR HWC frames -> cv2.resize'd uint8 BGR HWC [B,H2,W2,3]."""
+    fs, keep = _frames_struct(plan, frames, compact)
+    out = torch.empty((frames.shape[0], plan.dst_h, plan.dst_w, 3), dtype=torch.uint8, device=frames.device)
+    _cabi.check(_cabi.lib().cutdet_preprocess_u8(plan.handle, C.byref(fs), out.data_ptr(), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- K2/K3
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+class NativeNet:
+    """A cutdet_net built from state_dict-style float32 arrays.
+
+    ``weights`` uses the reference's keys with the conv state_dict prefixed ``conv.`` and the linear one
+    ``linear.`` (the layout of oracle.net / prod_net_weights.npz); either part may be absent (a bare
+    FrameConvNet or FrameLinearNet)."""
+
+    def __init__(self, weights: dict, avg_pool_size: int, bn_eps: float = 1e-5, input_channels: int | None = None):
+        n_conv = 0
+        while f"conv.conv_layers.{n_conv}.conv.weight" in weights:
+            n_conv += 1
+        n_fc = 0
+        while f"linear.layers.{n_fc}.linear.weight" in weights:
+            n_fc += 1
+        if n_conv + n_fc == 0:
+            raise ValueError("no layers found in the weight dictionary")
+        cfg = _cabi.NetConfig()
+        if n_conv:
+            w0 = weights["conv.conv_layers.0.conv.weight"]
+            cfg.input_channels, cfg.hidden_channels = int(w0.shape[1]), int(w0.shape[0])
+            cfg.avg_pool_size = int(avg_pool_size)
+            cfg.fc_input_size = cfg.hidden_channels * cfg.avg_pool_size ** 2
+        else:
+            fin = int(weights["linear.layers.0.linear.weight"].shape[1])
+            cfg.input_channels, cfg.hidden_channels, cfg.avg_pool_size, cfg.fc_input_size = fin, fin, 1, fin
+        cfg.n_conv_layers, cfg.n_fc_layers = n_conv, n_fc
+        if n_fc:
+            cfg.fc_hidden_size = int(weights["linear.layers.0.linear.weight"].shape[0])
+            cfg.fc_output_size = int(weights[f"linear.layers.{n_fc - 1}.linear.weight"].shape[0])
+            if int(weights["linear.layers.0.linear.weight"].shape[1]) != cfg.fc_input_size:
+                raise ValueError("first FC layer does not match conv_channels * avg_pool_size^2")
+        else:
+            cfg.fc_hidden_size = cfg.fc_output_size = cfg.fc_input_size
+        self.cfg = cfg
+        self.out_features = cfg.fc_output_size if n_fc else cfg.fc_input_size
+        lib = _cabi.lib()
+        handle = C.c_void_p()
+        _cabi.check(lib.cutdet_net_create(C.byref(cfg), C.byref(handle)))
+        self.handle = handle
+        for i in range(n_conv):
+            p = f"conv.conv_layers.{i}"
+            arrs = [_f32(weights[p + s]) for s in (".conv.weight", ".conv.bias", ".bn.weight", ".bn.bias",
+                                                   ".bn.running_mean", ".bn.running_var")]
+            _cabi.check(lib.cutdet_net_set_conv_layer(self.handle, i, *[_cabi.fptr(a) for a in arrs], bn_eps))
+        for j in range(n_fc):
+            p = f"linear.layers.{j}"
+            arrs = [_f32(weights[p + ".linear.weight"]), _f32(weights[p + ".linear.bias"])]
+            if j < n_fc - 1:
+                arrs += [_f32(weights[p + s]) for s in (".bn.weight", ".bn.bias", ".bn.running_mean", ".bn.running_var")]
+            else:
+                arrs += [None] * 4
+            _cabi.check(lib.cutdet_net_set_fc_layer(self.handle, j, *[_cabi.fptr(a) for a in arrs], bn_eps))
+        _cabi.check(lib.cutdet_net_finalize(self.handle))
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _cabi.lib().cutdet_net_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def uses_tensor_cores(self, height: int, width: int) -> bool:
+        return bool(_cabi.lib().cutdet_net_uses_tensor_cores(self.handle, height, width))
+
+    def workspace(self, batch: int, height: int, width: int, device) -> torch.Tensor:
+        need = C.c_size_t()
+        _cabi.check(_cabi.lib().cutdet_net_workspace_bytes(self.handle, batch, height, width, C.byref(need)))
+        if self._ws is None or self._ws.numel() < need.value or self._ws.device != torch.device(device):
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def forward_f32(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """x float32 [B,C,H,W] -> float32 [B, out_features]."""
+        _need_cuda(x, "input")
+        if x.dim() == 2:
+            x = x[:, :, None, None]
+        if x.dtype != torch.float32 or x.dim() != 4:
+            raise ValueError(f"input must be float32 [B,C,H,W], got {x.dtype} {tuple(x.shape)}")
+        if x.shape[1] != self.cfg.input_channels:
+            raise ValueError(f"input has {x.shape[1]} channels, the net expects {self.cfg.input_channels}")
+        x = x.contiguous()
+        b, _, h, w = x.shape
+        if out is None:
+            out = torch.empty((b, self.out_features), dtype=torch.float32, device=x.device)
+        ws = self.workspace(b, h, w, x.device)
+        _cabi.check(_cabi.lib().cutdet_net_forward_f32(self.handle, x.data_ptr(), b, h, w, out.data_ptr(), ws.data_ptr(),
+                                                       ws.numel(), _stream()))
+        return out
+
+    def forward_frames(self, plan: ResizePlan, frames: torch.Tensor, compact: bool = False,
+                       out: torch.Tensor | None = None) -> torch.Tensor:
+        """Decoded uint8 BGR HWC frames -> logits, K1 fused in front of the conv stack."""
+        fs, keep = _frames_struct(plan, frames, compact)
+        b = frames.shape[0]
+        if out is None:
+            out = torch.empty((b, self.out_features), dtype=torch.float32, device=frames.device)
+        ws = self.workspace(b, plan.dst_h, plan.dst_w, frames.device)
+        _cabi.check(_cabi.lib().cutdet_net_forward_frames(self.handle, plan.handle, C.byref(fs), out.data_ptr(),
+                                                          ws.data_ptr(), ws.numel(), _stream()))
+        return out
+
+    def debug_conv_output(self, layer: int, batch: int, height: int, width: int) -> torch.Tensor:
+        """float32 NCHW output of conv layer ``layer`` from the last forward (test hook)."""
+        c = self.cfg.hidden_channels
+        h, w = height, width
+        for _ in range(layer + 1):
+            h, w = h // 3, w // 3
+        out = torch.empty((batch, c, h, w), dtype=torch.float32, device=self._ws.device)
+        _cabi.check(_cabi.lib().cutdet_net_debug_conv_output(self.handle, layer, batch, height, width,
+                                                             self._ws.data_ptr(), out.data_ptr(), _stream()))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- K4
+def argmax(scores: torch.Tensor):
+    """scores [N,C] float32 -> (labels uint8 [N], top float32 [N]): torch.max(scores, 1) with first-index ties."""
+    _need_cuda(scores, "scores")
+    if scores.dtype != torch.float32 or scores.dim() != 2:
+        raise ValueError(f"scores must be float32 [N,C], got {scores.dtype} {tuple(scores.shape)}")
+    scores = scores.contiguous()
+    n, c = scores.shape
+    labels = torch.empty(n, dtype=torch.uint8, device=scores.device)
+    top = torch.empty(n, dtype=torch.float32, device=scores.device)
+    _cabi.check(_cabi.lib().cutdet_argmax(scores.data_ptr(), n, c, labels.data_ptr(), top.data_ptr(), _stream()))
+    return labels, top
+
+
+# ----------------------------------------------------------------------------------------------- K5/K6
+class DeviceRunTable:
+    """A cutdet_run_table backed by torch tensors."""
+
+    def __init__(self, capacity: int, device):
+        capacity = max(int(capacity), 1)
+        self.capacity = capacity
+        self.device = torch.device(device)
+        self.end_frames = torch.empty(capacity, dtype=torch.int64, device=device)
+        self.start_frames = torch.empty(capacity, dtype=torch.int64, device=device)
+        self.run_lengths = torch.empty(capacity, dtype=torch.int64, device=device)
+        self.frame_types = torch.empty(capacity, dtype=torch.int32, device=device)
+        self.score_means = torch.empty(capacity, dtype=torch.float32, device=device)
+        self.score_sums = torch.empty(capacity, dtype=torch.float64, device=device)
+        self.n_runs = torch.zeros(1, dtype=torch.int64, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def struct(self) -> _cabi.RunTable:
+        return _cabi.RunTable(self.end_frames.data_ptr(), self.start_frames.data_ptr(), self.run_lengths.data_ptr(),
+                              self.frame_types.data_ptr(), self.score_means.data_ptr(), self.score_sums.data_ptr(),
+                              self.capacity)
+
+    @classmethod
+    def from_te(cls, te: dict, device, capacity: int | None = None) -> "DeviceRunTable":
+        """Upload the five Segmentation.te columns (sums are reconstructed as mean * length)."""
+        n = int(te["end_frames"].shape[0])
+        t = cls(capacity or n, device)
+        t.end_frames[:n] = te["end_frames"].to(device=device, dtype=torch.int64)
+        t.start_frames[:n] = te["start_frames"].to(device=device, dtype=torch.int64)
+        t.run_lengths[:n] = te["run_lengths"].to(device=device, dtype=torch.int64)
+        t.frame_types[:n] = te["frame_types"].to(device=device, dtype=torch.int32)
+        t.score_means[:n] = te["score_means"].to(device=device, dtype=torch.float32)
+        t.score_sums[:n] = t.score_means[:n].double() * t.run_lengths[:n].double()
+        t.n_runs.fill_(n)
+        return t
+
+    def count(self) -> int:
+        return int(self.n_runs.item())
+
+    def to_te(self) -> dict:
+        """The five columns as CPU tensors with the reference's dtypes (int64 / float32)."""
+        n = self.count()
+        if n > self.capacity:
+            raise RuntimeError(f"run table overflow: {n} runs, capacity {self.capacity}")
+        return {
+            "end_frames": self.end_frames[:n].cpu(),
+            "frame_types": self.frame_types[:n].to(torch.int64).cpu(),
+            "run_lengths": self.run_lengths[:n].cpu(),
+            "start_frames": self.start_frames[:n].cpu(),
+            "score_means": self.score_means[:n].cpu(),
+        }
+
+    def glue_orphans(self, real_threshold: int = 100, blank_threshold: int = 10) -> None:
+        ts = self.struct()
+        _cabi.check(_cabi.lib().cutdet_glue_orphans(C.byref(ts), self.n_runs.data_ptr(), int(real_threshold),
+                                                    int(blank_threshold), self.status.data_ptr(), _stream()))
+        _cabi.check(int(self.status.item()))      # ELONE_ORPHAN -> IndexError, like the reference
+
+    def combine_adjacent(self) -> None:
+        ts = self.struct()
+        _cabi.check(_cabi.lib().cutdet_combine_adjacent(C.byref(ts), self.n_runs.data_ptr(), _stream()))
+
+
+class RunLengthEncoder:
+    """Streaming K5: feed (labels, top) chunks in frame order, then ``finish()``."""
+
+    def __init__(self, capacity: int, device):
+        self.table = DeviceRunTable(capacity, device)
+        self.state = torch.empty(_cabi.lib().cutdet_rle_state_bytes(), dtype=torch.uint8, device=device)
+        self.reset()
+
+    def reset(self) -> None:
+        _cabi.check(_cabi.lib().cutdet_rle_reset(self.state.data_ptr(), _stream()))
+
+    def append(self, labels: torch.Tensor, top: torch.Tensor) -> None:
+        _need_cuda(labels, "labels")
+        if labels.dtype != torch.uint8 or top.dtype != torch.float32 or labels.shape != top.shape or labels.dim() != 1:
+            raise ValueError("labels must be uint8 [N] and top float32 [N]")
+        labels, top = labels.contiguous(), top.contiguous()
+        ts = self.table.struct()
+        _cabi.check(_cabi.lib().cutdet_rle_append(self.state.data_ptr(), labels.data_ptr(), top.data_ptr(),
+                                                  labels.shape[0], C.byref(ts), _stream()))
+
+    def finish(self) -> DeviceRunTable:
+        ts = self.table.struct()
+        _cabi.check(_cabi.lib().cutdet_rle_finish(self.state.data_ptr(), C.byref(ts), self.table.n_runs.data_ptr(),
+                                                  _stream()))
+        n = C.c_int64()
+        _cabi.check(_cabi.lib().cutdet_rle_count(self.state.data_ptr(), C.byref(n), _stream()))
+        return self.table
+
+
+def run_table_from_scores(scores: torch.Tensor, capacity: int | None = None) -> DeviceRunTable:
+    """K4 + K5 over a whole [N,C] score tensor."""
+    labels, top = argmax(scores)
+    enc = RunLengthEncoder(capacity or max(int(scores.shape[0]), 1), scores.device)
+    enc.append(labels, top)
+    return enc.finish()
+
+
+def stitch_shards(shards: "list[DeviceRunTable] | DeviceRunTable", n_runs: torch.Tensor, frame_offsets: torch.Tensor,
+                  shard_capacity: int) -> DeviceRunTable:
+    """Join per-shard run tables (local frame numbers) into one global table.
+
+    ``shards`` is ONE DeviceRunTable whose rows [i*shard_capacity, ...) hold shard i (e.g. the output of an
+    all_gather of equally sized tables)."""
+    src = shards
+    n_shards = int(n_runs.shape[0])
+    dst = DeviceRunTable(src.capacity, src.device)
+    s, d = src.struct(), dst.struct()
+    _cabi.check(_cabi.lib().cutdet_stitch_shards(C.byref(s), n_shards, int(shard_capacity), n_runs.data_ptr(),
+                                                 frame_offsets.data_ptr(), C.byref(d), dst.n_runs.data_ptr(), _stream()))
+    return dst

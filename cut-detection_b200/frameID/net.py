@@ -1,0 +1,197 @@
+"""frameID.net -- the reference's network API (reference frameID/net.py) over the B200 kernels.
+
+Same public names and constructor arguments as the reference:
+
+    CNNLayer, FCLayer                       net.py:11-68    (parameter containers here)
+    FrameConvNet(input_channels=3, hidden_channels=32, n_conv_layers=3, average_pool_size=1)     net.py:71-136
+    FrameLinearNet(n_layers=3, input_size=32, hidden_size=32, output_size=8)                     net.py:139-189
+    load_and_glue_nets(param_file, conv_file, linear_file) -> (net, params)                      net.py:193-217
+    load_default_net() -> (net, params)                                                          net.py:221-233
+
+The modules hold ordinary torch parameters under the reference's state_dict keys, so the reference's
+checkpoint files load with ``load_state_dict`` unchanged, ``.eval()``, ``.to(device)`` and ``num_params()``
+behave as before -- but ``forward`` does not run PyTorch operators: it hands the input to libcutdet_b200.so
+(hand-written sm_100a kernels) through the C ABI.  Inference only: a module left in training mode (batch-statistic
+BatchNorm) raises, as does a CPU input -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from cutdet import engine as _engine
+
+package_directory = os.path.dirname(os.path.abspath(__file__))
+
+
+class CNNLayer(nn.Module):
+    """conv3x3 -> activation -> max-pool -> batch-norm (in that order; reference net.py:33-40).
+    Parameter container: the fused kernel for the whole layer is launched by FrameConvNet."""
+
+    def __init__(self, conv_args: dict, max_pool_args: dict, activation=nn.ReLU, batch_norm=True):
+        super().__init__()
+        self.batch_norm = batch_norm
+        self.conv = nn.Conv2d(**conv_args)
+        self.activation = activation()
+        self.max_pool = nn.MaxPool2d(**max_pool_args)
+        self.bn = nn.BatchNorm2d(conv_args["out_channels"]) if batch_norm else nn.Identity()
+
+    def forward(self, x):
+        raise NotImplementedError("CNNLayer is a parameter container here; call the enclosing FrameConvNet")
+
+
+class FCLayer(nn.Module):
+    """linear -> activation -> batch-norm (reference net.py:62-68).  Parameter container."""
+
+    def __init__(self, linear_args: dict, activation=nn.ReLU, batch_norm=True):
+        super().__init__()
+        self.batch_norm = batch_norm
+        self.linear = nn.Linear(**linear_args)
+        self.activation = activation()
+        self.bn = nn.BatchNorm1d(linear_args["out_features"]) if batch_norm else nn.Identity()
+
+    def forward(self, x):
+        raise NotImplementedError("FCLayer is a parameter container here; call the enclosing FrameLinearNet")
+
+
+def _weights_of(module: nn.Module, prefix: str) -> dict:
+    return {prefix + k: v.detach().to("cpu", torch.float32).numpy()
+            for k, v in module.state_dict().items() if not k.endswith("num_batches_tracked")}
+
+
+class _NativeBacked(nn.Module):
+    """Builds (and caches) the native net for the module's current parameters."""
+
+    def _native_parts(self):   # -> (weights dict, avg_pool_size)
+        raise NotImplementedError
+
+    def _fingerprint(self):
+        return tuple((id(p), p._version, p.data_ptr()) for p in list(self.parameters()) + list(self.buffers()))
+
+    def _native(self) -> _engine.NativeNet:
+        if self.training:
+            raise RuntimeError("this build implements inference only (BatchNorm running statistics): call .eval() first")
+        fp = self._fingerprint()
+        cache = self.__dict__.get("_native_cache")
+        if cache is None or cache[0] != fp:
+            weights, pool = self._native_parts()
+            cache = (fp, _engine.NativeNet(weights, pool))
+            self.__dict__["_native_cache"] = cache
+        return cache[1]
+
+    def num_params(self):
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+
+class FrameConvNet(_NativeBacked):
+    """The convolutional trunk: n_conv_layers x CNNLayer(k3 p1 conv, k3 pool, BN) -> AdaptiveAvgPool2d -> flatten."""
+
+    def __init__(self, input_channels=3, hidden_channels=32, n_conv_layers=3, average_pool_size=1):
+        super().__init__()
+        self.input_channels = input_channels
+        self.hidden_channels = hidden_channels
+        self.n_conv_layers = n_conv_layers
+        self.average_pool_size = average_pool_size
+        self.conv_layers = nn.ModuleList()
+        self.average_pool = nn.AdaptiveAvgPool2d(average_pool_size)
+        channels = [input_channels] + [hidden_channels] * n_conv_layers
+        for cin, cout in zip(channels[:-1], channels[1:]):
+            self.conv_layers.append(CNNLayer(
+                conv_args={"in_channels": cin, "out_channels": cout, "kernel_size": 3, "padding": 1},
+                max_pool_args={"kernel_size": 3}, activation=nn.ReLU, batch_norm=True))
+
+    def _native_parts(self):
+        return _weights_of(self, "conv."), self.average_pool_size
+
+    def forward(self, x):
+        """float32 [B, Cin, H, W] on the GPU -> [B, hidden_channels * average_pool_size^2]."""
+        return self._native().forward_f32(x)
+
+
+class FrameLinearNet(_NativeBacked):
+    """The fully connected head: Linear -> ReLU -> BatchNorm1d on all but the last layer, which is Linear only."""
+
+    def __init__(self, n_layers: int = 3, input_size: int = 32, hidden_size: int = 32, output_size: int = 8):
+        super().__init__()
+        self.n_layers = n_layers
+        self.input_size = input_size
+        self.hidden_size = hidden_size
+        self.output_size = output_size
+        self.layers = nn.ModuleList()
+        widths = [input_size] + [hidden_size] * (n_layers - 1) + [output_size]
+        for j, (fin, fout) in enumerate(zip(widths[:-1], widths[1:])):
+            last = j == n_layers - 1
+            self.layers.append(FCLayer(linear_args={"in_features": fin, "out_features": fout},
+                                       activation=nn.Identity if last else nn.ReLU, batch_norm=not last))
+
+    def _native_parts(self):
+        return _weights_of(self, "linear."), 1
+
+    def forward(self, x):
+        """float32 [B, input_size] on the GPU -> [B, output_size] raw scores."""
+        return self._native().forward_f32(x)
+
+
+class GluedNet(nn.Sequential, _NativeBacked):
+    """nn.Sequential(conv_net, linear_net) whose forward is ONE native pipeline (trunk and head fused),
+    plus ``forward_frames`` which also fuses the frame preprocessing in front."""
+
+    def __init__(self, conv_net: FrameConvNet, linear_net: FrameLinearNet):
+        nn.Sequential.__init__(self, conv_net, linear_net)
+
+    def _native_parts(self):
+        weights = _weights_of(self[0], "conv.")
+        weights.update(_weights_of(self[1], "linear."))
+        return weights, self[0].average_pool_size
+
+    def forward(self, x):
+        """float32 [B, 3, H', W'] RGB in [0, 1] -> raw logits [B, output_size] (class order a22, ez, b)."""
+        return self._native().forward_f32(x)
+
+    def forward_frames(self, plan: _engine.ResizePlan, frames, compact: bool = False):
+        """Addition to the reference API: decoded uint8 BGR HWC frames [B, h, w, 3] on the GPU -> logits."""
+        return self._native().forward_frames(plan, frames, compact)
+
+
+def _build(model_params: dict):
+    conv_net = FrameConvNet(hidden_channels=model_params["conv_channels"], n_conv_layers=model_params["conv_layers"],
+                            average_pool_size=model_params["avg_pool_size"])
+    linear_net = FrameLinearNet(n_layers=model_params["linear_layers"],
+                                input_size=model_params["conv_channels"] * model_params["avg_pool_size"] ** 2,
+                                hidden_size=model_params["linear_size"], output_size=model_params["linear_output_size"])
+    return conv_net, linear_net
+
+
+def load_and_glue_nets(param_file, conv_file, linear_file):
+    """Read the reference's three-file checkpoint (JSON + two torch state_dicts) into one callable."""
+    with open(param_file, "r") as f:
+        model_params = json.load(f)
+    conv_net, linear_net = _build(model_params)
+    conv_net.load_state_dict(torch.load(conv_file, map_location="cpu"))
+    linear_net.load_state_dict(torch.load(linear_file, map_location="cpu"))
+    return GluedNet(conv_net, linear_net), model_params
+
+
+def _load_npz(path):
+    with np.load(path, allow_pickle=False) as z:
+        model_params = json.loads(bytes(z["__params_json__"]).decode("utf-8"))
+        arrays = {k: torch.from_numpy(z[k].copy()) for k in z.files if k != "__params_json__"}
+    conv_net, linear_net = _build(model_params)
+    conv_net.load_state_dict({k[len("conv."):]: v for k, v in arrays.items() if k.startswith("conv.")}, strict=False)
+    linear_net.load_state_dict({k[len("linear."):]: v for k, v in arrays.items() if k.startswith("linear.")}, strict=False)
+    return GluedNet(conv_net, linear_net), model_params
+
+
+def load_default_net():
+    """The classifier shipped with the package (prod_net/).  Uses the reference's own three files when they have been
+    dropped into prod_net/, else the re-encoded copy of the same parameters (prod_net_weights.npz)."""
+    d = os.path.join(package_directory, "prod_net")
+    three = [os.path.join(d, n) for n in ("init_model_model_params.json", "init_model_classifier_conv.pt",
+                                          "init_model_classifier_linear.pt")]
+    if all(os.path.isfile(p) for p in three):
+        return load_and_glue_nets(*three)
+    return _load_npz(os.path.join(d, "prod_net_weights.npz"))

@@ -1,0 +1,206 @@
+/*
+ * cutdet_b200.h -- C ABI of libcutdet_b200.so, the B200 (sm_100a) implementation of the
+ * per-frame hot path of play4honor/Cut-Detection:
+ *
+ *     decoded frames -> resize/normalise -> CNN -> (max logit, label) -> run table -> smoothed segments
+ *
+ * The reference has no FFI of its own (it is pure Python over PyTorch/OpenCV); every entry point
+ * below names the reference Python interface it stands in for (file:line under /root/reference).
+ * The Python side of this repo (cut-detection_b200/frameID, a mirror of the reference's `frameID`
+ * package) binds these symbols with ctypes; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a CUTDET_E* code; cutdet_last_error() gives the text
+ *     of the calling thread's last failure.  Nothing is ever computed on the CPU as a fallback.
+ *   - pointers named *_dev are device pointers on the current CUDA device, *_host are host pointers.
+ *     The caller owns every buffer it passes.  `stream` is a cudaStream_t (NULL = default stream);
+ *     calls are asynchronous with respect to the host unless stated otherwise.
+ *   - images are row-major; `frames` are uint8 BGR HWC exactly as cv2.VideoCapture.read() returns them.
+ *   - class ids follow frameID/data.py:116  {a22: 0, ez: 1, b: 2}.
+ */
+#ifndef CUTDET_B200_H
+#define CUTDET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUTDET_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CUTDET_API __attribute__((visibility("default")))
+#else
+#define CUTDET_API
+#endif
+
+enum {
+    CUTDET_OK = 0,
+    CUTDET_EINVAL = 1,        /* bad argument (shape, null pointer, ...)                        */
+    CUTDET_ECUDA = 2,         /* a CUDA runtime/driver call failed; see cutdet_last_error()     */
+    CUTDET_EUNSUPPORTED = 3,  /* configuration outside what the kernels implement               */
+    CUTDET_ECAPACITY = 4,     /* caller-provided table/workspace too small                      */
+    CUTDET_ELONE_ORPHAN = 5   /* glue_orphans on a single orphan run: the reference raises
+                                 IndexError here (frameID/segmentation.py:110-113)               */
+};
+
+typedef void *cutdet_stream_t;
+
+CUTDET_API int cutdet_abi_version(void);
+CUTDET_API const char *cutdet_last_error(void);
+/* Fails with CUTDET_EUNSUPPORTED unless the current device is compute capability 10.x. */
+CUTDET_API int cutdet_device_check(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  frame preprocessing            replaces VideoDataset.__init__/__next__, frameID/data.py:197-228
+ * ------------------------------------------------------------------------------------------------ */
+
+/* (new_width, new_height) = (resize, int(height * (resize / width)))       frameID/data.py:199-202 */
+CUTDET_API int cutdet_target_size(int width, int height, int resize, int *new_width, int *new_height);
+
+/* Geometry of one resize: the fixed-point tap tables cv2.resize(INTER_LINEAR) uses for uint8 images,
+ * built on the host and kept on the device.  Created once per (h, w, H2, W2); thread-safe to share. */
+typedef struct cutdet_resize_plan cutdet_resize_plan;
+CUTDET_API int cutdet_resize_plan_create(int src_h, int src_w, int dst_h, int dst_w, cutdet_resize_plan **plan);
+CUTDET_API void cutdet_resize_plan_destroy(cutdet_resize_plan *plan);
+/* Source rows the resize actually reads (sorted, unique).  n_rows_out receives the count; rows_host may
+ * be NULL to query it.  A host-side caller can copy just these rows to the device (row-compacted frames). */
+CUTDET_API int cutdet_resize_plan_rows(const cutdet_resize_plan *plan, int *rows_host, int *n_rows_out);
+
+/* Layout of a batch of source frames in device memory.  `row_map_compact` != 0 says the buffer holds only
+ * the rows listed by cutdet_resize_plan_rows(), in that order (row r of the list at row_pitch * r).      */
+typedef struct {
+    const uint8_t *frames_dev; /* [B] frames, each `frame_stride` bytes apart                             */
+    int64_t frame_stride;      /* bytes between consecutive frames                                        */
+    int64_t row_pitch;         /* bytes between consecutive stored rows (>= 3 * src_w)                    */
+    int batch;
+    int row_map_compact;
+} cutdet_frames;
+
+/* uint8 BGR HWC -> float32 RGB CHW in [0,1]: bit-exactly what VideoDataset yields (data.py:220-228),
+ * stacked to [B,3,H2,W2] as default_collate does (segment_video.py:29).                                  */
+CUTDET_API int cutdet_preprocess_f32(const cutdet_resize_plan *plan, const cutdet_frames *src, float *out_nchw_dev,
+                          cutdet_stream_t stream);
+/* uint8 BGR HWC -> resized uint8 BGR HWC [B,H2,W2,3]: bit-exactly cv2.resize(..., INTER_LINEAR).          */
+CUTDET_API int cutdet_preprocess_u8(const cutdet_resize_plan *plan, const cutdet_frames *src, uint8_t *out_hwc_dev,
+                         cutdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2/K3  the classifier             replaces FrameConvNet + FrameLinearNet, frameID/net.py:71-189,
+ *                                   and load_and_glue_nets, frameID/net.py:193-217
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cutdet_net cutdet_net;
+
+typedef struct {
+    int input_channels;    /* FrameConvNet(input_channels=3, ...)            net.py:77        */
+    int hidden_channels;   /* conv_channels                                  net.py:78        */
+    int n_conv_layers;     /*                                                net.py:78        */
+    int avg_pool_size;     /* AdaptiveAvgPool2d(average_pool_size)           net.py:79,88     */
+    int n_fc_layers;       /* FrameLinearNet(n_layers, ...)                  net.py:148-151   */
+    int fc_input_size;     /* must equal hidden_channels * avg_pool_size^2                   */
+    int fc_hidden_size;
+    int fc_output_size;
+} cutdet_net_config;
+
+CUTDET_API int cutdet_net_create(const cutdet_net_config *cfg, cutdet_net **net);
+CUTDET_API void cutdet_net_destroy(cutdet_net *net);
+/* Parameters come as host float32 arrays in PyTorch state_dict layout (eval-mode BatchNorm:
+ * running statistics).  conv weight [Cout,Cin,3,3]; fc weight [out,in]; bn_* are NULL for the last
+ * FC layer, which has no BatchNorm (net.py:164-167).                                                 */
+CUTDET_API int cutdet_net_set_conv_layer(cutdet_net *net, int layer, const float *weight_host, const float *bias_host,
+                              const float *bn_weight_host, const float *bn_bias_host,
+                              const float *bn_mean_host, const float *bn_var_host, float bn_eps);
+CUTDET_API int cutdet_net_set_fc_layer(cutdet_net *net, int layer, const float *weight_host, const float *bias_host,
+                            const float *bn_weight_host, const float *bn_bias_host,
+                            const float *bn_mean_host, const float *bn_var_host, float bn_eps);
+/* Packs the parameters into the kernels' layouts and uploads them.  Synchronous. */
+CUTDET_API int cutdet_net_finalize(cutdet_net *net);
+/* 1 if the tcgen05 tensor-core kernels cover this architecture and input size, else 0 (the generic
+ * CUDA-core kernels run instead).                                                                   */
+CUTDET_API int cutdet_net_uses_tensor_cores(const cutdet_net *net, int height, int width);
+
+/* Bytes of device scratch the forward pass needs for `batch` inputs of height x width. */
+CUTDET_API int cutdet_net_workspace_bytes(const cutdet_net *net, int batch, int height, int width, size_t *bytes);
+
+/* net(x): x float32 [B,Cin,H,W] (RGB in [0,1]) -> raw logits float32 [B,fc_output_size]
+ * (segment_video.py:45; no softmax anywhere in the reference).                                        */
+CUTDET_API int cutdet_net_forward_f32(cutdet_net *net, const float *x_nchw_dev, int batch, int height, int width,
+                           float *logits_dev, void *workspace_dev, size_t workspace_bytes,
+                           cutdet_stream_t stream);
+/* Fused entry: decoded frames in, logits out (K1 feeds the conv stack directly). */
+CUTDET_API int cutdet_net_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cutdet_frames *src,
+                              float *logits_dev, void *workspace_dev, size_t workspace_bytes,
+                              cutdet_stream_t stream);
+/* Intermediate activations of the last forward, converted to float32 NCHW (test hook):
+ * layer in [0, n_conv_layers) is the output of that CNNLayer.                                         */
+CUTDET_API int cutdet_net_debug_conv_output(cutdet_net *net, int layer, int batch, int height, int width,
+                                 const void *workspace_dev, float *out_nchw_dev, cutdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  per-frame decision            replaces torch.max(scores, dim=1), frameID/segmentation.py:37
+ * ------------------------------------------------------------------------------------------------ */
+/* scores [N,C] float32 -> top[N] (max logit), labels[N] (first index of the max, as torch does on CPU). */
+CUTDET_API int cutdet_argmax(const float *scores_dev, int64_t n_frames, int n_classes, uint8_t *labels_dev,
+                  float *top_dev, cutdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5  run-length encoding           replaces Segmentation.__init__, frameID/segmentation.py:39-60
+ * ------------------------------------------------------------------------------------------------ */
+/* A run table in device memory, struct-of-arrays, `capacity` rows.  Runs are appended in frame order.
+ * start_frames[s] = end_frames[s-1] + 1, run_lengths[s] = end - start + 1,
+ * score_means[s] = float32(sum of the run's max logits / run length).                                 */
+typedef struct {
+    int64_t *end_frames_dev;
+    int64_t *start_frames_dev;
+    int64_t *run_lengths_dev;
+    int32_t *frame_types_dev;
+    float *score_means_dev;
+    double *score_sums_dev;   /* exact-ish (float64) sums, so runs cut by a shard edge can be re-joined */
+    int64_t capacity;
+} cutdet_run_table;
+
+/* Streaming state (device memory, cutdet_rle_state_bytes() bytes, zero-initialised by cutdet_rle_reset):
+ * the still-open last run is carried from one call to the next, so a long video can be encoded chunk
+ * by chunk in frame order.                                                                            */
+CUTDET_API size_t cutdet_rle_state_bytes(void);
+CUTDET_API int cutdet_rle_reset(void *state_dev, cutdet_stream_t stream);
+/* Append `n_frames` more frames (labels + max logits). */
+CUTDET_API int cutdet_rle_append(void *state_dev, const uint8_t *labels_dev, const float *top_dev, int64_t n_frames,
+                      const cutdet_run_table *table, cutdet_stream_t stream);
+/* Close the open run; writes the number of runs to *n_runs_dev (device int64).  After this the table holds
+ * exactly the five columns of Segmentation.te.                                                         */
+CUTDET_API int cutdet_rle_finish(void *state_dev, const cutdet_run_table *table, int64_t *n_runs_dev,
+                      cutdet_stream_t stream);
+/* Synchronous helper: copies the run count (and the overflow flag) to the host after `stream` drains.
+ * Returns CUTDET_ECAPACITY if the table overflowed.                                                    */
+CUTDET_API int cutdet_rle_count(const void *state_dev, int64_t *n_runs_host, cutdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6  segment smoothing             replaces Segmentation.glue_orphans / combine_adjacent_segments,
+ *                                   frameID/segmentation.py:91-183 (incl. _find_orphans :12-17 and the
+ *                                   mean update of _update_neighbor :69-89, evaluated as written)
+ * ------------------------------------------------------------------------------------------------ */
+/* In place on the first *n_runs_dev rows of `table` (start/end/length/type/mean columns; sums untouched);
+ * *n_runs_dev is updated.  *status_dev (device int32) receives CUTDET_OK or CUTDET_ELONE_ORPHAN.
+ * Exact ties between orphan means are broken towards the lowest run index (the reference's
+ * torch.argsort is unstable, so its tie order is unspecified).                                         */
+CUTDET_API int cutdet_glue_orphans(const cutdet_run_table *table, int64_t *n_runs_dev, int real_threshold,
+                        int blank_threshold, int32_t *status_dev, cutdet_stream_t stream);
+CUTDET_API int cutdet_combine_adjacent(const cutdet_run_table *table, int64_t *n_runs_dev, cutdet_stream_t stream);
+
+/* Joins the run tables of consecutive shards (time ranges) into one: `src` holds `n_shards` tables
+ * back to back, shard i occupying rows [i * shard_capacity, i * shard_capacity + n_runs[i]) with frame
+ * numbers LOCAL to the shard; frame_offsets_dev[i] is the shard's first global frame.  Runs that touch
+ * across a shard edge with the same type are merged (sums and lengths add).  Output: global frame numbers;
+ * *n_runs_out_dev may exceed dst->capacity, in which case the surplus rows were dropped. */
+CUTDET_API int cutdet_stitch_shards(const cutdet_run_table *src, int n_shards, int64_t shard_capacity,
+                         const int64_t *n_runs_dev, const int64_t *frame_offsets_dev,
+                         const cutdet_run_table *dst, int64_t *n_runs_out_dev, cutdet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUTDET_B200_H */

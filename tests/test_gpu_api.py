@@ -1,0 +1,129 @@
+"""The reference-facing Python surface (frameID.*) end to end on the GPU, as segment_video.py uses it."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import kat_inputs
+from oracle import net as onet
+from oracle import segmentation as oseg
+
+pytestmark = pytest.mark.gpu
+
+
+def test_load_default_net_contract(prod_weights, golden_dir):
+    from frameID.net import load_default_net, FrameConvNet, FrameLinearNet
+    net, params = load_default_net()
+    assert params["conv_channels"] == 48 and params["linear_output_size"] == 3
+    assert isinstance(net, torch.nn.Sequential) and isinstance(net[0], FrameConvNet) and isinstance(net[1], FrameLinearNet)
+    assert net[0].num_params() == 43200 and net[1].num_params() == 24771
+    keys = set(net[0].state_dict().keys())
+    assert "conv_layers.0.conv.weight" in keys and "conv_layers.2.bn.running_var" in keys
+    assert "layers.1.linear.bias" in net[1].state_dict()
+    net.eval()
+    net.to("cuda:0")
+    x = torch.from_numpy(kat_inputs.smooth_images(48)).to("cuda:0")
+    with torch.no_grad():
+        y = net(x)
+    assert y.dtype == torch.float32 and tuple(y.shape) == (48, 3)
+    kat = np.load(os.path.join(golden_dir, "net_kat.npz"))
+    assert np.abs(y.cpu().numpy() - kat["smooth48_eager"]).max() <= 0.1
+    # trunk and head also work on their own, like the reference's modules
+    feats = net[0](x[:4])
+    assert tuple(feats.shape) == (4, 768)
+    assert np.abs(net[1](feats).cpu().numpy() - kat["smooth48_eager"][:4]).max() <= 0.1
+
+
+def test_training_mode_and_cpu_inputs_raise():
+    from frameID.net import load_default_net
+    net, _ = load_default_net()
+    net.to("cuda:0")
+    with pytest.raises(RuntimeError):
+        net(torch.zeros((1, 3, 144, 256), device="cuda:0"))           # still in training mode
+    net.eval()
+    with pytest.raises(RuntimeError):
+        net(torch.zeros((1, 3, 144, 256)))                            # CPU input: no fallback
+
+
+def test_three_file_checkpoint_format(tmp_path, prod_weights):
+    """load_and_glue_nets reads the reference's JSON + two state_dict files (net.py:193-217)."""
+    import json
+    from frameID.net import load_and_glue_nets, load_default_net
+    net, params = load_default_net()
+    torch.save(net[0].state_dict(), tmp_path / "m_conv.pt")
+    torch.save(net[1].state_dict(), tmp_path / "m_linear.pt")
+    json.dump(params, open(tmp_path / "m.json", "w"))
+    net2, params2 = load_and_glue_nets(str(tmp_path / "m.json"), str(tmp_path / "m_conv.pt"), str(tmp_path / "m_linear.pt"))
+    assert params2 == params
+    net.eval().to("cuda")
+    net2.eval().to("cuda")
+    x = torch.from_numpy(kat_inputs.smooth_images(3)).cuda()
+    assert torch.equal(net(x), net2(x))
+
+
+def test_cli_on_a_synthetic_clip(tmp_path, prod_weights):
+    """segment_video.py on a small synthetic mp4: CSV equals the oracle's run over the same decoded frames."""
+    import cv2
+    import subprocess, sys
+    from oracle import preprocess as opre
+    w, h, n = 640, 360, 330
+    path = str(tmp_path / "clip.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 30, (w, h))
+    plan = [(kat_inputs.stripes(h, w, 20, True), 150), (np.zeros((h, w, 3), np.uint8), 30),
+            (kat_inputs.stripes(h, w, 20, False), 150)]
+    for frame, count in plan:
+        for _ in range(count):
+            vw.write(frame)
+    vw.release()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out_csv = str(tmp_path / "out.csv")
+    r = subprocess.run([sys.executable, os.path.join(root, "cut-detection_b200", "segment_video.py"), path,
+                        "--output_path", out_csv, "--batch-size", "64", "--print-every", "2"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Found" in r.stderr and "Writing" in r.stderr
+    # oracle on the same decoded frames
+    cap = cv2.VideoCapture(path)
+    frames = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(f)
+    wts, params = prod_weights
+    logits = onet.forward_f32(wts, opre.preprocess_batch(np.stack(frames), 256), params["avg_pool_size"])
+    want = oseg.segment(logits, 100, 10)[3]
+    assert open(out_csv, "rb").read() == want
+    assert want == b"0,a22\r\n150,b\r\n180,ez\r\n"
+    # default output path and the --frame-limit quirk (check happens after the batch is scored, strict >)
+    r = subprocess.run([sys.executable, os.path.join(root, "cut-detection_b200", "segment_video.py"), path,
+                        "--batch-size", "64", "--frame-limit", "64", "--print-every", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    default_csv = os.path.splitext(path)[0] + "_segments.csv"
+    got = open(default_csv, "rb").read()
+    assert got == oseg.segment(logits[:128], 100, 10)[3]
+    r = subprocess.run([sys.executable, os.path.join(root, "cut-detection_b200", "segment_video.py"),
+                        str(tmp_path / "missing.mp4")], capture_output=True, text=True)
+    assert r.returncode != 0 and "does not exist" in r.stderr
+
+
+def test_videodataset_iteration(tmp_path):
+    import cv2
+    from frameID.data import VideoDataset
+    from oracle import preprocess as opre
+    w, h = 480, 270
+    path = str(tmp_path / "v.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 30, (w, h))
+    rng = np.random.default_rng(0)
+    for i in range(5):
+        vw.write(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+    vw.release()
+    ds = VideoDataset(path, resize=256)
+    assert ds.video_info == {"fps": 30, "length": 5, "width": w, "height": h} and len(ds) == 5
+    got = [t.cpu().numpy() for t in ds]
+    cap = cv2.VideoCapture(path)
+    for t in got:
+        ok, f = cap.read()
+        assert ok and np.array_equal(t, opre.preprocess_frame(f, 256))
+    assert len(got) == 5 and list(ds) == []        # single pass
