@@ -111,8 +111,10 @@ __global__ void __launch_bounds__(256) preprocess_generic_kernel(ResizePlanDev p
 }
 
 int check_frames(const cutdet_resize_plan *plan, const cutdet_frames *src) {
-    CUTDET_REQUIRE(plan && src && src->frames_dev, "preprocess: null plan/frames");
+    CUTDET_REQUIRE(plan && src, "preprocess: null plan/frames");
     CUTDET_REQUIRE(src->batch >= 0, "preprocess: negative batch");
+    if (src->batch == 0) return CUTDET_OK;
+    CUTDET_REQUIRE(src->frames_dev, "preprocess: null frames pointer");
     CUTDET_REQUIRE(src->row_pitch >= 3 * (int64_t)plan->host.src_w, "preprocess: row_pitch %lld < 3*width", (long long)src->row_pitch);
     const int rows = src->row_map_compact ? plan->n_rows : plan->host.src_h;
     CUTDET_REQUIRE(src->batch <= 1 || src->frame_stride >= src->row_pitch * (int64_t)(rows - 1) + 3 * (int64_t)plan->host.src_w,
@@ -123,8 +125,8 @@ int check_frames(const cutdet_resize_plan *plan, const cutdet_frames *src) {
 template <int OUT>
 static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *src, void *out, cutdet_stream_t stream) {
     if (int rc = check_frames(plan, src)) return rc;
-    CUTDET_REQUIRE(out, "preprocess: null output");
     if (src->batch == 0) return CUTDET_OK;
+    CUTDET_REQUIRE(out, "preprocess: null output");
     dim3 block(64, 4, 1);
     for (int b0 = 0; b0 < src->batch; b0 += 65535) {
         const int nb = src->batch - b0 < 65535 ? src->batch - b0 : 65535;

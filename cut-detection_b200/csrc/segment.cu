@@ -252,11 +252,18 @@ __global__ void rle_finish_kernel(RleState *st, cutdet_run_table table, int64_t 
 struct GlueScratch {
     int *prev, *next;        // neighbours in the list of live runs; prev == -2 marks a dead run
     float *key0;             // level 0 keys
-    float *lv_val[4];        // levels 1..4
+    float *lv_val[4];        // levels 1..4 (sized for the table's capacity)
     int *lv_idx[4];
-    long long lv_n[5];       // entries per level (lv_n[0] = S)
-    int n_levels;            // levels above 0 in use
+    long long lv_n[5];       // entries per level for the CURRENT run count (lv_n[0] = S), set by the kernel
+    int n_levels;            // levels above 0 in use, set by the kernel
 };
+
+__device__ __forceinline__ void glue_levels(GlueScratch &ws, long long S) {
+    ws.lv_n[0] = S;
+    int levels = 0;
+    while (ws.lv_n[levels] > 32 && levels < 4) { ws.lv_n[levels + 1] = (ws.lv_n[levels] + 31) / 32; ++levels; }
+    ws.n_levels = levels;
+}
 
 __device__ __forceinline__ bool key_less(float va, int ia, float vb, int ib) { return va < vb || (va == vb && ia < ib); }
 
@@ -301,6 +308,7 @@ glue_orphans_kernel(cutdet_run_table t, int64_t *n_runs, int k_real, int k_blank
     const long long S = *n_runs;
     if (lane == 0) *status = CUTDET_OK;
     if (S <= 0) return;
+    glue_levels(ws, S);      // the tree covers the S live rows, not the table's capacity
     volatile int64_t *start = t.start_frames_dev, *end = t.end_frames_dev, *len = t.run_lengths_dev;
     volatile int32_t *type = t.frame_types_dev;
     volatile float *mean = t.score_means_dev;
