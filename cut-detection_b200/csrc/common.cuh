@@ -38,4 +38,15 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();
 
+// Wrap every kernel launch: counts launches (cutdet_launch_count) and, while profiling is on
+// (cutdet_profile_begin/end), brackets the launch with CUDA events on its own stream.
+class KernelScope {
+public:
+    KernelScope(const char *name, cudaStream_t stream);
+    ~KernelScope();
+private:
+    int slot_;
+    cudaStream_t stream_;
+};
+
 }  // namespace cutdet

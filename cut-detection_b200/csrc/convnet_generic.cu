@@ -139,8 +139,11 @@ __global__ void fc_kernel(const float *__restrict__ in, float *__restrict__ out,
 
 }  // namespace
 
-int launch_conv_block_generic(const float *in, float *out, const ConvLayer &L, int batch, int h, int w,
+int launch_conv_block_generic(const float *in, float *out, const ConvLayer &L, int layer, int batch, int h, int w,
                               cudaStream_t stream) {
+    static const char *const kNames[] = {"conv_block_generic_L0", "conv_block_generic_L1", "conv_block_generic_L2",
+                                         "conv_block_generic_L3+"};
+    const char *name = kNames[layer < 3 ? layer : 3];
     const int ph = h / 3, pw = w / 3;
     if (ph <= 0 || pw <= 0) return fail(CUTDET_EINVAL, "conv block: %dx%d input is smaller than the 3x3 pool", h, w);
     const int co_groups = (L.cout + CO_T - 1) / CO_T;
@@ -149,9 +152,12 @@ int launch_conv_block_generic(const float *in, float *out, const ConvLayer &L, i
     for (int b0 = 0; b0 < batch; b0 += max_b) {
         const int nb = batch - b0 < max_b ? batch - b0 : max_b;
         dim3 grid((unsigned)ceil_div(pw, PT_X), (unsigned)ceil_div(ph, PT_Y), (unsigned)(nb * co_groups));
-        conv3x3_relu_pool3_bn_kernel<<<grid, PT_X * PT_Y, 0, stream>>>(
+        {
+            KernelScope scope(name, stream);
+            conv3x3_relu_pool3_bn_kernel<<<grid, PT_X * PT_Y, 0, stream>>>(
             in + (int64_t)b0 * L.cin * h * w, out + (int64_t)b0 * L.cout * ph * pw, L.d_w_t, L.d_bias, L.d_scale,
             L.d_shift, L.cin, L.cout, cout_pad, h, w, ph, pw, co_groups);
+        }
         CUTDET_LAUNCH_CHECK("conv3x3_relu_pool3_bn_kernel");
     }
     return CUTDET_OK;
@@ -161,7 +167,10 @@ int launch_avgpool_flatten(const float *in, float *out, int batch, int c, int h,
                            cudaStream_t stream) {
     const int64_t total = (int64_t)batch * c * pool * pool;
     if (total == 0) return CUTDET_OK;
-    avgpool_flatten_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(in, out, total, c, h, w, pool);
+    {
+        KernelScope scope("avgpool_flatten_kernel", stream);
+        avgpool_flatten_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(in, out, total, c, h, w, pool);
+    }
     CUTDET_LAUNCH_CHECK("avgpool_flatten_kernel");
     return CUTDET_OK;
 }
@@ -169,10 +178,13 @@ int launch_avgpool_flatten(const float *in, float *out, int batch, int c, int h,
 int launch_fc(const float *in, float *out, const FcLayer &L, int batch, bool relu, cudaStream_t stream) {
     const int64_t warps = (int64_t)batch * L.out;
     if (warps == 0) return CUTDET_OK;
-    fc_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, stream>>>(in, out, L.d_w, L.d_bias,
+    {
+        KernelScope scope("fc_kernel", stream);
+        fc_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, stream>>>(in, out, L.d_w, L.d_bias,
                                                                       L.has_bn ? L.d_scale : nullptr,
                                                                       L.has_bn ? L.d_shift : nullptr, batch, L.in, L.out,
                                                                       relu ? 1 : 0);
+    }
     CUTDET_LAUNCH_CHECK("fc_kernel");
     return CUTDET_OK;
 }

@@ -91,7 +91,7 @@ int forward_generic(cutdet_net *net, const float *x, int batch, int h, int w, fl
     std::vector<LayerGeom> geom = layer_geometry(net, h, w);
     for (size_t i = 0; i < geom.size(); ++i) {
         float *out = reinterpret_cast<float *>(ws_base + ws.conv_out[i]);
-        if (int rc = launch_conv_block_generic(cur, out, net->conv[i], batch, geom[i].h, geom[i].w, stream)) return rc;
+        if (int rc = launch_conv_block_generic(cur, out, net->conv[i], (int)i, batch, geom[i].h, geom[i].w, stream)) return rc;
         cur = out;
     }
     if (!geom.empty()) {

@@ -31,7 +31,7 @@ struct LayerGeom {
 };
 
 // generic CUDA-core kernels (any architecture the reference's constructors can build)
-int launch_conv_block_generic(const float *in, float *out, const ConvLayer &L, int batch, int h, int w,
+int launch_conv_block_generic(const float *in, float *out, const ConvLayer &L, int layer, int batch, int h, int w,
                               cudaStream_t stream);
 int launch_avgpool_flatten(const float *in, float *out, int batch, int c, int h, int w, int pool,
                            cudaStream_t stream);

@@ -133,9 +133,12 @@ static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *s
         dim3 grid((unsigned)ceil_div(plan->host.dst_w, 64), (unsigned)ceil_div(plan->host.dst_h, 4), (unsigned)nb);
         const int64_t out_frame = (int64_t)plan->host.dst_h * plan->host.dst_w * 3;
         void *o = OUT == 0 ? (void *)((float *)out + b0 * out_frame) : (void *)((uint8_t *)out + b0 * out_frame);
-        preprocess_generic_kernel<OUT><<<grid, block, 0, as_stream(stream)>>>(
+        {
+            KernelScope scope("preprocess_generic_kernel", as_stream(stream));
+            preprocess_generic_kernel<OUT><<<grid, block, 0, as_stream(stream)>>>(
             plan->host, src->frames_dev + (int64_t)b0 * src->frame_stride, src->frame_stride, src->row_pitch,
             src->row_map_compact, o);
+        }
         CUTDET_LAUNCH_CHECK("preprocess_generic_kernel");
     }
     return CUTDET_OK;
@@ -223,6 +226,43 @@ extern "C" int cutdet_resize_plan_rows(const cutdet_resize_plan *plan, int *rows
     CUTDET_REQUIRE(plan && n_rows_out, "resize_plan_rows: null argument");
     *n_rows_out = plan->n_rows;
     if (rows_host) memcpy(rows_host, plan->rows.data(), plan->rows.size() * sizeof(int));
+    return CUTDET_OK;
+}
+
+extern "C" int cutdet_upload_frames(const cutdet_resize_plan *plan, const uint8_t *frames_host, int batch,
+                                    int64_t frame_stride, int64_t row_pitch, uint8_t *dst_dev, cutdet_stream_t stream,
+                                    int64_t *bytes_copied) {
+    CUTDET_REQUIRE(plan && batch >= 0, "upload_frames: bad argument");
+    if (bytes_copied) *bytes_copied = 0;
+    if (batch == 0) return CUTDET_OK;
+    CUTDET_REQUIRE(frames_host && dst_dev, "upload_frames: null pointer");
+    const int src_h = plan->host.src_h;
+    const int64_t width = 3 * (int64_t)plan->host.src_w;
+    CUTDET_REQUIRE(row_pitch >= width, "upload_frames: row_pitch < 3*width");
+    // Smallest period p | src_h over which the set of needed rows repeats (5 at 720p -> 256x144: rows 5y+2).
+    const std::vector<int> &rows = plan->rows;
+    int period = src_h;
+    for (int p = 1; p < src_h; ++p) {
+        if (src_h % p) continue;
+        const int reps = src_h / p;
+        if (plan->n_rows % reps) continue;
+        const int g = plan->n_rows / reps;
+        bool ok = true;
+        for (int i = 0; ok && i < plan->n_rows; ++i) ok = rows[i] == rows[i % g] + (i / g) * p && rows[i % g] < p;
+        if (ok) { period = p; break; }
+    }
+    const int reps = src_h / period, g = plan->n_rows / reps;
+    const bool frames_contiguous = frame_stride == (int64_t)src_h * row_pitch;
+    const int n_calls = frames_contiguous ? 1 : batch;
+    const int64_t height = frames_contiguous ? (int64_t)batch * reps : reps;
+    for (int c = 0; c < n_calls; ++c)
+        for (int j = 0; j < g; ++j) {
+            const uint8_t *s = frames_host + (int64_t)c * frame_stride + (int64_t)rows[j] * row_pitch;
+            uint8_t *d = dst_dev + (int64_t)c * plan->n_rows * width + (int64_t)j * width;
+            CUTDET_CUDA(cudaMemcpy2DAsync(d, (size_t)g * width, s, (size_t)period * row_pitch, (size_t)width, (size_t)height,
+                                          cudaMemcpyHostToDevice, as_stream(stream)));
+        }
+    if (bytes_copied) *bytes_copied = (int64_t)batch * plan->n_rows * width;
     return CUTDET_OK;
 }
 

@@ -538,8 +538,11 @@ extern "C" int cutdet_argmax(const float *scores, int64_t n, int n_classes, uint
     if (n == 0) return CUTDET_OK;
     CUTDET_REQUIRE(scores && labels && top, "argmax: null pointer");
     const unsigned grid = (unsigned)ceil_div(n, 256);
-    if (n_classes == 3) argmax_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(scores, n, 3, labels, top);
-    else argmax_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(scores, n, n_classes, labels, top);
+    {
+        KernelScope scope("argmax_kernel", as_stream(stream));
+        if (n_classes == 3) argmax_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(scores, n, 3, labels, top);
+        else argmax_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(scores, n, n_classes, labels, top);
+    }
     CUTDET_LAUNCH_CHECK("argmax_kernel");
     return CUTDET_OK;
 }
@@ -565,8 +568,11 @@ extern "C" int cutdet_rle_append(void *state, const uint8_t *labels, const float
     const int64_t per_launch = (int64_t)RLE_MAX_BLOCKS * RLE_TILE;
     for (int64_t off = 0; off < n; off += per_launch) {
         const int64_t m = n - off < per_launch ? n - off : per_launch;
-        rle_append_kernel<<<(unsigned)ceil_div(m, RLE_TILE), RLE_THREADS, 0, as_stream(stream)>>>(
+        {
+            KernelScope scope("rle_append_kernel", as_stream(stream));
+            rle_append_kernel<<<(unsigned)ceil_div(m, RLE_TILE), RLE_THREADS, 0, as_stream(stream)>>>(
             reinterpret_cast<RleState *>(state), labels + off, top + off, (long long)m, *table);
+        }
         CUTDET_LAUNCH_CHECK("rle_append_kernel");
     }
     return CUTDET_OK;
@@ -575,7 +581,10 @@ extern "C" int cutdet_rle_append(void *state, const uint8_t *labels, const float
 extern "C" int cutdet_rle_finish(void *state, const cutdet_run_table *table, int64_t *n_runs, cutdet_stream_t stream) {
     CUTDET_REQUIRE(state, "rle_finish: null state");
     if (int rc = check_table(table, "rle_finish")) return rc;
-    rle_finish_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<RleState *>(state), *table, n_runs);
+    {
+        KernelScope scope("rle_finish_kernel", as_stream(stream));
+        rle_finish_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<RleState *>(state), *table, n_runs);
+    }
     CUTDET_LAUNCH_CHECK("rle_finish_kernel");
     return CUTDET_OK;
 }
@@ -596,7 +605,10 @@ extern "C" int cutdet_glue_orphans(const cutdet_run_table *table, int64_t *n_run
     CUTDET_REQUIRE(n_runs && status, "glue_orphans: null n_runs/status");
     GlueScratch ws;
     if (int rc = glue_scratch(table->capacity, &ws)) return rc;
-    glue_orphans_kernel<<<1, 32, 0, as_stream(stream)>>>(*table, n_runs, real_threshold, blank_threshold, status, ws);
+    {
+        KernelScope scope("glue_orphans_kernel", as_stream(stream));
+        glue_orphans_kernel<<<1, 32, 0, as_stream(stream)>>>(*table, n_runs, real_threshold, blank_threshold, status, ws);
+    }
     CUTDET_LAUNCH_CHECK("glue_orphans_kernel");
     return CUTDET_OK;
 }
@@ -604,7 +616,10 @@ extern "C" int cutdet_glue_orphans(const cutdet_run_table *table, int64_t *n_run
 extern "C" int cutdet_combine_adjacent(const cutdet_run_table *table, int64_t *n_runs, cutdet_stream_t stream) {
     if (int rc = check_table(table, "combine_adjacent")) return rc;
     CUTDET_REQUIRE(n_runs, "combine_adjacent: null n_runs");
-    combine_adjacent_kernel<<<1, 32, 0, as_stream(stream)>>>(*table, n_runs);
+    {
+        KernelScope scope("combine_adjacent_kernel", as_stream(stream));
+        combine_adjacent_kernel<<<1, 32, 0, as_stream(stream)>>>(*table, n_runs);
+    }
     CUTDET_LAUNCH_CHECK("combine_adjacent_kernel");
     return CUTDET_OK;
 }
@@ -616,7 +631,10 @@ extern "C" int cutdet_stitch_shards(const cutdet_run_table *src, int n_shards, i
     if (int rc = check_table(dst, "stitch_shards(dst)")) return rc;
     CUTDET_REQUIRE(n_shards >= 1 && shard_capacity > 0 && n_runs && offsets && n_out, "stitch_shards: bad argument");
     CUTDET_REQUIRE(src->capacity >= (int64_t)n_shards * shard_capacity, "stitch_shards: src smaller than n_shards * shard_capacity");
-    stitch_kernel<<<1, 256, 0, as_stream(stream)>>>(*src, n_shards, shard_capacity, n_runs, offsets, *dst, n_out);
+    {
+        KernelScope scope("stitch_kernel", as_stream(stream));
+        stitch_kernel<<<1, 256, 0, as_stream(stream)>>>(*src, n_shards, shard_capacity, n_runs, offsets, *dst, n_out);
+    }
     CUTDET_LAUNCH_CHECK("stitch_kernel");
     return CUTDET_OK;
 }

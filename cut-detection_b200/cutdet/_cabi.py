@@ -43,6 +43,10 @@ _SIGNATURES = {
     "cutdet_abi_version": (C.c_int, []),
     "cutdet_last_error": (C.c_char_p, []),
     "cutdet_device_check": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "cutdet_launch_count": (C.c_longlong, []),
+    "cutdet_profile_begin": (C.c_int, []),
+    "cutdet_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "cutdet_upload_frames": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64, _P, _P, C.POINTER(C.c_int64)]),
     "cutdet_target_size": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cutdet_resize_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "cutdet_resize_plan_destroy": (None, [_P]),

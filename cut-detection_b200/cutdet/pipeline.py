@@ -1,0 +1,99 @@
+"""The per-GPU frame pipeline: decoded frames in (device-resident or pinned host memory), run table out.
+
+    frames --K1--> conv stack --K3--> logits --K4--> (label, max logit) --K5--> run table        (per chunk)
+    ... finish(): close the open run;  smooth(): K6 glue_orphans + combine_adjacent_segments
+
+One instance serves one contiguous time range of a video (the whole video on one GPU, or one rank's shard).
+Host frames are uploaded on a copy stream into one of two device buffers (only the source rows the resize reads),
+so the copy of chunk i+1 overlaps the kernels of chunk i.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi, engine
+
+
+class FramePipeline:
+    def __init__(self, net: engine.NativeNet, plan: engine.ResizePlan, max_chunk: int, table_capacity: int,
+                 device="cuda"):
+        self.net, self.plan = net, plan
+        self.device = torch.device(device)
+        self.max_chunk = int(max_chunk)
+        self.encoder = engine.RunLengthEncoder(table_capacity, self.device)
+        self.logits = torch.empty((self.max_chunk, net.out_features), dtype=torch.float32, device=self.device)
+        self.labels = torch.empty(self.max_chunk, dtype=torch.uint8, device=self.device)
+        self.top = torch.empty(self.max_chunk, dtype=torch.float32, device=self.device)
+        self.n_frames = 0
+        self.h2d_bytes = 0
+        self._stage = None          # two row-compacted device buffers for host uploads
+        self._stage_events = None
+        self._copy_stream = None
+        self._turn = 0
+        net.workspace(self.max_chunk, plan.dst_h, plan.dst_w, self.device)
+
+    # ------------------------------------------------------------------ per chunk
+    def _score(self, frames: torch.Tensor, compact: bool) -> None:
+        n = frames.shape[0]
+        if n > self.max_chunk:
+            raise ValueError(f"chunk of {n} frames exceeds max_chunk={self.max_chunk}")
+        logits = self.logits[:n]
+        self.net.forward_frames(self.plan, frames, compact, out=logits)
+        labels, top = self.labels[:n], self.top[:n]
+        _cabi.check(_cabi.lib().cutdet_argmax(logits.data_ptr(), n, logits.shape[1], labels.data_ptr(), top.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+        self.encoder.append(labels, top)
+        self.n_frames += n
+
+    def push_device(self, frames: torch.Tensor, compact: bool = False) -> None:
+        """Frames already in HBM: uint8 BGR HWC [n, rows, w, 3]."""
+        self._score(frames, compact)
+
+    def push_host(self, frames: torch.Tensor) -> None:
+        """Decoded frames in (pinned) host memory, uint8 BGR HWC [n, h, w, 3]: upload the needed rows, then score."""
+        if frames.is_cuda or frames.dtype != torch.uint8 or frames.dim() != 4:
+            raise ValueError("push_host takes a uint8 [n, h, w, 3] host tensor")
+        n = frames.shape[0]
+        if tuple(frames.shape[1:]) != (self.plan.src_h, self.plan.src_w, 3) or frames.stride(3) != 1 or frames.stride(2) != 3:
+            raise ValueError(f"host frames must be dense [{self.plan.src_h}, {self.plan.src_w}, 3] rows")
+        if self._stage is None:
+            shape = (self.max_chunk, len(self.plan.rows), self.plan.src_w, 3)
+            self._stage = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._stage_events = [None, None]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        slot = self._turn
+        self._turn ^= 1
+        compute = torch.cuda.current_stream()
+        if self._stage_events[slot] is not None:
+            self._copy_stream.wait_event(self._stage_events[slot])      # kernels that read this buffer are done
+        copied = C.c_int64()
+        _cabi.check(_cabi.lib().cutdet_upload_frames(self.plan.handle, frames.data_ptr(), n, frames.stride(0), frames.stride(1),
+                                                     self._stage[slot].data_ptr(), self._copy_stream.cuda_stream,
+                                                     C.byref(copied)))
+        self.h2d_bytes += copied.value
+        uploaded = torch.cuda.Event()
+        uploaded.record(self._copy_stream)
+        compute.wait_event(uploaded)
+        self._score(self._stage[slot][:n], True)
+        done = torch.cuda.Event()
+        done.record(compute)
+        self._stage_events[slot] = done
+
+    # ------------------------------------------------------------------ end of the range
+    def finish(self) -> engine.DeviceRunTable:
+        """Close the open run; the table then equals Segmentation(scores).te for this range (local frame numbers)."""
+        return self.encoder.finish()
+
+    def reset(self) -> None:
+        self.encoder.reset()
+        self.n_frames = 0
+        self.h2d_bytes = 0
+
+
+def smooth(table: engine.DeviceRunTable, real_threshold: int = 100, blank_threshold: int = 10) -> engine.DeviceRunTable:
+    """K6 on a finished table: glue_orphans then combine_adjacent_segments (segment_video.py:64-66)."""
+    table.glue_orphans(real_threshold, blank_threshold)
+    table.combine_adjacent()
+    return table

@@ -54,6 +54,13 @@ CUTDET_API const char *cutdet_last_error(void);
 /* Fails with CUTDET_EUNSUPPORTED unless the current device is compute capability 10.x. */
 CUTDET_API int cutdet_device_check(int *sm_count, int *cc_major, int *cc_minor);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched since it was loaded; and a per-kernel
+ * CUDA-event profiler -- between begin and end every launch is bracketed by events on its own stream, end() drains
+ * the device and writes {"kernel_name": {"launches": n, "ms": total}, ...} as JSON.                               */
+CUTDET_API long long cutdet_launch_count(void);
+CUTDET_API int cutdet_profile_begin(void);
+CUTDET_API int cutdet_profile_end(char *json_out, size_t capacity);
+
 /* ------------------------------------------------------------------------------------------------
  * K1  frame preprocessing            replaces VideoDataset.__init__/__next__, frameID/data.py:197-228
  * ------------------------------------------------------------------------------------------------ */
@@ -79,6 +86,14 @@ typedef struct {
     int batch;
     int row_map_compact;
 } cutdet_frames;
+
+/* Host -> device copy of ONLY the source rows the resize reads, as a handful of strided 2-D DMA copies (one at 720p,
+ * where the rows are 5y+2; four at 1080p).  frames_host: [batch] frames of src_h rows, `row_pitch` bytes per row,
+ * `frame_stride` bytes apart (pinned memory for an asynchronous copy).  dst_dev receives row-compacted frames
+ * [batch][n_rows][3*src_w] -- pass them on with cutdet_frames.row_map_compact = 1.  Asynchronous on `stream`.      */
+CUTDET_API int cutdet_upload_frames(const cutdet_resize_plan *plan, const uint8_t *frames_host, int batch,
+                                    int64_t frame_stride, int64_t row_pitch, uint8_t *dst_dev,
+                                    cutdet_stream_t stream, int64_t *bytes_copied);
 
 /* uint8 BGR HWC -> float32 RGB CHW in [0,1]: bit-exactly what VideoDataset yields (data.py:220-228),
  * stacked to [B,3,H2,W2] as default_collate does (segment_video.py:29).                                  */
