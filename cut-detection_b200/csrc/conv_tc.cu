@@ -1,20 +1,955 @@
-// Tensor-core path: placeholder until the tcgen05 kernels land (everything runs on the generic kernels).
+// Tensor-core path of the classifier for sm_100a: tcgen05.mma with TMEM accumulators, operands fed by TMA
+// (cp.async.bulk.tensor) or cp.async gathers, bias + ReLU + 3x3 max-pool + BatchNorm fused into the epilogue.
+//
+// Stands in for the three CNNLayers of FrameConvNet plus the AdaptiveAvgPool/first FCLayer (reference
+// frameID/net.py:33-40, 122-133, 62-68) when the architecture is input_channels = 3, three conv layers and 32 or 48
+// hidden channels (prod_net: 48; the contrastive encoder of learn_contrasts.py: 32).
+//
+// The idea that shapes everything: make the 3x3 max-pool THREAD-LOCAL.  A GEMM row (= a TMEM lane = one epilogue
+// thread) is a POOLED output pixel; the nine conv outputs under it go to nine different TMEM column blocks
+// D_j, j = (dy, dx), C fp32 columns each (9 * 48 = 432 of the 512 columns).  The epilogue thread reads its lane,
+// takes the 9-way max per channel (ReLU and +bias commute with max), applies the BatchNorm affine AFTER the pool as the
+// reference does, and writes C channels.  No shuffles, no shared-memory round trip, and the full-resolution
+// activation (7 MB/frame in fp32 for layer 1) never exists anywhere.
+//
+//   conv1 (Cin = 3):   K1 writes the input "x-unfolded": for every image row and pooled column px the 5 input pixels
+//       3px-1 .. 3px+3 (x3 channels, +1 pad = 16 halves = one UMMA K-chunk).  A row of the A operand is then five such
+//       chunks (input rows 3py-1 .. 3py+3), gathered by cp.async.  For conv-row dy the MMA takes K-chunks dy..dy+2
+//       against ONE B matrix [48 x 3C] that holds the taps of the three dx positions (zero where a tap falls outside):
+//       9 MMAs of N = 3C per 128 pooled pixels.  Pixels are stored as v/256 (exact in fp16); 256/255 is folded into
+//       the weights.
+//   conv2/conv3 (Cin = C): activations live "phase-split": [y%3][x%3][frame][c/8][y/3][x/3][8 ch] fp16.  The input
+//       pixel (3Y+oy, 3X+ox) needed by pooled pixel (Y, X) is then a DENSE box of one phase plane, fetched by one TMA
+//       (out-of-range coordinates are zero-filled = the conv's zero padding).  The 25 shifted views (oy, ox in -1..3)
+//       are each used by every (dy, ky), (dx, kx) with dy+ky-1 = oy, dx+kx-1 = ox; the dx positions that share a view
+//       are adjacent column blocks, so they are ONE MMA of N = C * n_dx against a B matrix stacked [kx=2 | kx=1 | kx=0]:
+//       135 MMAs per 128 pooled pixels instead of 243.
+//
+// Numerics: 16-bit operands, fp32 accumulation, fp32 epilogue, 16-bit inter-layer activations.  The operand format is
+// fp16, not bf16: same tensor-core rate, 8x finer rounding (2^-12), and every value on this path is far inside fp16's
+// range (pixels in [0,1), BatchNorm'd activations of order 10; the epilogue clamps to +-65504 regardless).  Measured
+// against the fp32 reference the logits move by <= 0.015 with fp16 where bf16 moved them by up to 0.25 (an all-stripes
+// frame, where weight rounding errors add coherently); tolerance stated in tests/test_gpu_net.py.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "conv_tc.cuh"
+#include "tc_common.cuh"
 
 namespace cutdet {
 
-int tc_prepare(cutdet_net *) { return CUTDET_OK; }
-void tc_destroy(cutdet_net *) {}
-bool tc_supported(const cutdet_net *, int, int) { return false; }
-size_t tc_workspace_bytes(const cutdet_net *, int, int, int) { return 0; }
-int tc_forward_f32(cutdet_net *, const float *, int, int, int, float *, char *, cudaStream_t) {
-    return fail(CUTDET_EUNSUPPORTED, "tensor-core path not built");
+using namespace tc;
+
+namespace {
+
+constexpr bool kBf16 = false;           // operand format of the MMAs and of the stored activations (false = fp16)
+constexpr float kPixelScale = kBf16 ? 255.f : 255.f / 256.f;    // layer-1 input = x * kPixelScale (u8 pixels stay exact)
+constexpr float kW1Scale = kBf16 ? 1.f / 255.f : 256.f / 255.f; // ... and its weights absorb the inverse
+constexpr float kActMax = kBf16 ? 3.0e38f : 65504.f;
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return kBf16 ? pack2(lo, hi) : pack_f16x2(lo, hi); }
+
+constexpr int SUB_BATCH = 148;          // frames per pass through the conv stack: activations stay L2-resident
+constexpr int TMEM_COLS = 512;
+constexpr int MID_STAGES = 3;
+constexpr int C1_STAGES = 4;
+constexpr int C1_A_STAGE_BYTES = 10 * 128 * 16;   // 5 input rows x 2 x (128 rows x 16 B)
+
+// ------------------------------------------------------------------------------------------------ geometry
+struct TileCfg { int R, F, MT, n_rg; };
+
+TileCfg tile_cfg(int ph, int pw) {
+    TileCfg t;
+    if (ph * pw <= 64) { t.R = ph; t.F = 128 / (ph * pw); }
+    else { t.R = 128 / pw < ph ? 128 / pw : ph; t.F = 1; }
+    t.MT = t.R * t.F * pw;
+    t.n_rg = (ph + t.R - 1) / t.R;
+    return t;
 }
-int tc_forward_frames(cutdet_net *, const cutdet_resize_plan *, const cutdet_frames *, float *, char *, cudaStream_t) {
-    return fail(CUTDET_EUNSUPPORTED, "tensor-core path not built");
+
+struct Geom {
+    int H, W, C, CG;
+    int P1h, P1w, P2h, P2w, P3h, P3w;
+    int Q1h, Q1w, Q2h, Q2w;
+    TileCfg t2, t3;
+    size_t xin_frame, act1_frame, act2_frame, act3_frame;   // bytes per frame
+};
+
+Geom make_geom(int H, int W, int C) {
+    Geom g;
+    g.H = H; g.W = W; g.C = C; g.CG = C / 8;
+    g.P1h = H / 3; g.P1w = W / 3;
+    g.P2h = g.P1h / 3; g.P2w = g.P1w / 3;
+    g.P3h = g.P2h / 3; g.P3w = g.P2w / 3;
+    g.Q1h = (g.P1h + 2) / 3; g.Q1w = (g.P1w + 2) / 3;
+    g.Q2h = (g.P2h + 2) / 3; g.Q2w = (g.P2w + 2) / 3;
+    g.t2 = tile_cfg(g.P2h > 0 ? g.P2h : 1, g.P2w > 0 ? g.P2w : 1);
+    g.t3 = tile_cfg(g.P3h > 0 ? g.P3h : 1, g.P3w > 0 ? g.P3w : 1);
+    g.xin_frame = (size_t)H * g.P1w * 32;
+    g.act1_frame = (size_t)9 * g.CG * g.Q1h * g.Q1w * 16;
+    g.act2_frame = (size_t)9 * g.CG * g.Q2h * g.Q2w * 16;
+    g.act3_frame = (size_t)g.P3h * g.P3w * C * sizeof(float);
+    return g;
 }
-int tc_debug_conv_output(cutdet_net *, int, int, int, int, const char *, float *, cudaStream_t) {
-    return fail(CUTDET_EUNSUPPORTED, "tensor-core path not built");
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------ epilogue
+// Shared by conv1 and conv2/3: this thread's TMEM lane holds 9 blocks of C fp32 columns (one per pool position).
+// max over the 9 blocks, + bias, ReLU, BatchNorm affine; 16 channels at a time.
+__device__ __forceinline__ void ld_fence(float (&v)[16]) {
+    // ties the registers to the preceding tcgen05.wait::ld so the compiler cannot hoist their uses above it
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                      "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]));
+}
+
+template <int C>
+__device__ __forceinline__ void pooled_block(uint32_t lane_base, int cb, const float *s_bias, const float *s_scale,
+                                             const float *s_shift, float (&out)[16]) {
+    float a[16], b[16], c[16];
+    tmem_ld16(lane_base + 0 * C + cb * 16, a);
+    tmem_ld16(lane_base + 1 * C + cb * 16, b);
+    tmem_ld16(lane_base + 2 * C + cb * 16, c);
+    tmem_ld_wait();
+    ld_fence(a); ld_fence(b); ld_fence(c);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = fmaxf(fmaxf(a[i], b[i]), c[i]);
+#pragma unroll
+    for (int j = 3; j < 9; j += 3) {
+        tmem_ld16(lane_base + (j + 0) * C + cb * 16, a);
+        tmem_ld16(lane_base + (j + 1) * C + cb * 16, b);
+        tmem_ld16(lane_base + (j + 2) * C + cb * 16, c);
+        tmem_ld_wait();
+        ld_fence(a); ld_fence(b); ld_fence(c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) out[i] = fmaxf(out[i], fmaxf(fmaxf(a[i], b[i]), c[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int ch = cb * 16 + i;
+        out[i] = fminf(fmaxf(fmaf(fmaxf(out[i] + s_bias[ch], 0.f), s_scale[ch], s_shift[ch]), -kActMax), kActMax);
+    }
+}
+
+// Where a pooled pixel goes.  mode 0: phase-split 16-bit (input layout of the next conv); mode 1: [frame][pixel][C] fp32.
+struct OutSpec {
+    void *ptr;
+    int mode;
+    int frames;        // frame capacity of the buffer (phase-split planes are [phase][frame])
+    int Qh, Qw;        // phase-plane size (mode 0)
+    int out_h, out_w;  // pooled map size
+};
+
+template <int C>
+__device__ __forceinline__ void store_pixel(const OutSpec &o, int b, int Y, int X, int cb, const float (&v)[16]) {
+    constexpr int CG = C / 8;
+    if (o.mode == 0) {
+        const int plane = ((Y % 3) * 3 + (X % 3)) * o.frames + b;
+        uint4 *dst = reinterpret_cast<uint4 *>(o.ptr);
+        const size_t base = (((size_t)plane * CG + cb * 2) * o.Qh + Y / 3) * o.Qw + X / 3;
+        uint4 lo, hi;
+        lo.x = pack2(v[0], v[1]); lo.y = pack2(v[2], v[3]); lo.z = pack2(v[4], v[5]); lo.w = pack2(v[6], v[7]);
+        hi.x = pack2(v[8], v[9]); hi.y = pack2(v[10], v[11]); hi.z = pack2(v[12], v[13]); hi.w = pack2(v[14], v[15]);
+        dst[base] = lo;
+        dst[base + (size_t)o.Qh * o.Qw] = hi;
+    } else {
+        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(o.ptr) +
+                                                 ((size_t)b * o.out_h * o.out_w + (size_t)Y * o.out_w + X) * C + cb * 16);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+        dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ conv2 / conv3
+struct MidParams {
+    int B;                  // frames in this pass
+    int out_h, out_w;       // pooled output size
+    int R, F, MT, n_rg;     // tile: R pooled rows x F frames (MT = R*F*out_w valid GEMM rows of 128)
+    int n_tiles;
+    OutSpec out;
+    const uint4 *w_packed;  // [ky][c/8][3C rows: kx=2 | kx=1 | kx=0][8] 16-bit
+    const float *bias, *scale, *shift;
+};
+
+template <int C>
+struct MidSmem {
+    static constexpr int CG = C / 8;
+    static constexpr int W_BYTES = 3 * CG * 3 * C * 16;
+    static constexpr int W_KY_BYTES = CG * 3 * C * 16;
+    static constexpr int LBO_B = 3 * C * 16;
+    __host__ __device__ static int view_stride(int MT) { return (CG * MT * 16 + 127) / 128 * 128; }
+    __host__ __device__ static int stage_bytes(int MT) { return 5 * view_stride(MT); }
+    __host__ __device__ static int total(int MT) {
+        return W_BYTES + MID_STAGES * stage_bytes(MT) + 2048 /* slack for the M=128 over-read */ + 256 /* barriers */ + 3 * C * 4;
+    }
+};
+
+// 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 4..7 = epilogue (TMEM lane quarter
+// = warp - 4).  Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...
+template <int C>
+__global__ void __launch_bounds__(256, 1) conv_mid_tc_kernel(const __grid_constant__ CUtensorMap in_map, const MidParams p) {
+    using S = MidSmem<C>;
+    constexpr int CG = C / 8;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int view_stride = S::view_stride(p.MT), stage_bytes = 5 * view_stride;
+    uint8_t *s_w = smem;
+    uint8_t *s_stage = smem + S::W_BYTES;
+    uint8_t *s_tail = s_stage + MID_STAGES * stage_bytes + 2048;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_tail);
+    uint64_t *empty = full + MID_STAGES;
+    uint64_t *tmem_full = empty + MID_STAGES;
+    uint64_t *tmem_empty = tmem_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+    float *s_bias = reinterpret_cast<float *>(s_tail + 256);
+    float *s_scale = s_bias + C, *s_shift = s_scale + C;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // one-time setup
+    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_bias[i] = p.bias[i]; s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+    fence_proxy_async();             // the weights were written through the generic proxy; the MMA reads via the async proxy
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MID_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        fence_barrier_init();
+        tma_prefetch_desc(&in_map);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (lane 0 issues)
+        uint32_t stage = 0, phase = 0;
+        const uint32_t tx_bytes = 5u * (uint32_t)(CG * p.MT * 16);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int b0 = (tile / p.n_rg) * p.F, Y0 = (tile % p.n_rg) * p.R;
+            for (int oy = -1; oy <= 3; ++oy) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[stage], tx_bytes);
+                    const int py = (oy + 3) % 3, sy = oy < 0 ? -1 : (oy > 2 ? 1 : 0);
+                    uint8_t *dst = s_stage + stage * stage_bytes;
+                    for (int oxi = 0; oxi < 5; ++oxi) {
+                        const int ox = oxi - 1;
+                        const int px = (ox + 3) % 3, sx = ox < 0 ? -1 : (ox > 2 ? 1 : 0);
+                        tma_load_5d(dst + oxi * view_stride, &in_map, &full[stage], sx * 8, Y0 + sy, b0, 0, py * 3 + px);
+                    }
+                }
+                __syncwarp();
+                if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        uint32_t stage = 0, phase = 0, acc_phase = 0;
+        const uint32_t lbo_a = (uint32_t)p.MT * 16;
+        const uint32_t w_addr = smem_u32(s_w), stage_addr = smem_u32(s_stage);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(tmem_empty, acc_phase ^ 1);          // the epilogue has drained the previous tile
+            tc_fence_after_sync();
+            for (int oy = -1; oy <= 3; ++oy) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after_sync();
+                const uint32_t a_stage = stage_addr + stage * stage_bytes;
+                for (int dy = 0; dy < 3 && lane == 0; ++dy) {
+                    const int ky = oy + 1 - dy;
+                    if (ky < 0 || ky > 2) continue;
+#pragma unroll
+                    for (int o = 0; o < 5; ++o) {
+                        const int ox = (o == 0) ? 1 : (o == 1) ? 0 : (o == 2) ? 2 : (o == 3) ? -1 : 3;   // centre first
+                        const int dx_lo = ox - 1 < 0 ? 0 : ox - 1, dx_hi = ox + 1 > 2 ? 2 : ox + 1;
+                        const int n_dx = dx_hi - dx_lo + 1, kx_start = ox + 1 - dx_lo;
+                        const uint32_t idesc = instr_desc_16bit(128, C * n_dx, kBf16);
+                        const uint32_t a_view = a_stage + (ox + 1) * view_stride;
+                        const uint32_t b_tap = w_addr + ky * S::W_KY_BYTES + (2 - kx_start) * C * 16;
+                        const uint32_t d_col = tmem_base + C * (dy * 3 + dx_lo);
+#pragma unroll
+                        for (int ks = 0; ks < C / 16; ++ks) {
+                            const uint64_t da = smem_desc(a_view + 2 * ks * lbo_a, lbo_a, 128);
+                            const uint64_t db = smem_desc(b_tap + 2 * ks * S::LBO_B, S::LBO_B, 128);
+                            umma_16bit(d_col, da, db, idesc, (ky == 0 && ox == 1 && ks == 0) ? 0u : 1u);
+                        }
+                    }
+                }
+                if (lane == 0) umma_commit(&empty[stage]);  // frees the stage once these MMAs have read it
+                __syncwarp();
+                if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (lane == 0) umma_commit(tmem_full);
+            __syncwarp();
+            acc_phase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp - 4, m = q * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t acc_phase = 0;
+        const int per_frame = p.R * p.out_w;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int b0 = (tile / p.n_rg) * p.F, Y0 = (tile % p.n_rg) * p.R;
+            const int f = m / per_frame, rem = m % per_frame;
+            const int b = b0 + f, Y = Y0 + rem / p.out_w, X = rem % p.out_w;
+            const bool valid = m < p.MT && b < p.B && Y < p.out_h;
+            mbar_wait(tmem_full, acc_phase);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int cb = 0; cb < C / 16; ++cb) {
+                float v[16];
+                pooled_block<C>(lane_base, cb, s_bias, s_scale, s_shift, v);
+                if (valid) store_pixel<C>(p.out, b, Y, X, cb, v);
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            acc_phase ^= 1;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ conv1
+struct Conv1Params {
+    const uint4 *xin;       // [B][H][P1w][2 x 16 B]: x-unfolded input, 0..255 scale
+    int B, H, P1h, P1w;
+    long long n_pooled;     // B * P1h * P1w
+    int n_tiles;
+    OutSpec out;
+    const uint4 *w_packed;  // [ky][half][3C rows: dx=0 | dx=1 | dx=2][8] 16-bit, taps scaled by kW1Scale
+    const float *bias, *scale, *shift;
+};
+
+template <int C>
+struct C1Smem {
+    static constexpr int W_BYTES = 6 * 3 * C * 16;
+    static constexpr int LBO_B = 3 * C * 16;
+    static constexpr int total = W_BYTES + C1_STAGES * C1_A_STAGE_BYTES + 256 + 3 * C * 4;
+};
+
+// 288 threads: warps 0..3 = cp.async gather producers (thread t builds GEMM row t), warps 4..7 = epilogue,
+// warp 8 = MMA issuer (+ TMEM alloc).
+template <int C>
+__global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
+    using S = C1Smem<C>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *s_w = smem;
+    uint8_t *s_stage = smem + S::W_BYTES;
+    uint8_t *s_tail = s_stage + C1_STAGES * C1_A_STAGE_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_tail);
+    uint64_t *empty = full + C1_STAGES;
+    uint64_t *tmem_full = empty + C1_STAGES;
+    uint64_t *tmem_empty = tmem_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+    float *s_bias = reinterpret_cast<float *>(s_tail + 256);
+    float *s_scale = s_bias + C, *s_shift = s_scale + C;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_bias[i] = p.bias[i]; s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+    fence_proxy_async();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C1_STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------------ gather producers
+        const int m = threadIdx.x;
+        uint32_t stage = 0, phase = 0;
+        const int per_frame = p.P1h * p.P1w;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const long long pix = (long long)tile * 128 + m;
+            const bool in_range = pix < p.n_pooled;
+            const int b = in_range ? (int)(pix / per_frame) : 0;
+            const int rem = in_range ? (int)(pix % per_frame) : 0;
+            const int py = rem / p.P1w, px = rem % p.P1w;
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t *dst = s_stage + stage * C1_A_STAGE_BYTES + m * 16;
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                const int row = 3 * py - 1 + r;
+                const bool ok = in_range && row >= 0 && row < p.H;
+                const uint4 *src = p.xin + (ok ? (((size_t)b * p.H + row) * p.P1w + px) * 2 : 0);
+                cp_async_16(dst + (2 * r) * 2048, src, ok ? 16u : 0u);
+                cp_async_16(dst + (2 * r + 1) * 2048, src + 1, ok ? 16u : 0u);
+            }
+            cp_async_arrive_noinc(&full[stage]);
+            if (++stage == C1_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer (lane 0 issues)
+        uint32_t stage = 0, phase = 0, acc_phase = 0;
+        const uint32_t w_addr = smem_u32(s_w), stage_addr = smem_u32(s_stage);
+        const uint32_t idesc = instr_desc_16bit(128, 3 * C, kBf16);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(tmem_empty, acc_phase ^ 1);
+            mbar_wait(&full[stage], phase);
+            fence_proxy_async();
+            tc_fence_after_sync();
+            const uint32_t a_stage = stage_addr + stage * C1_A_STAGE_BYTES;
+            if (lane == 0) {
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) {
+                        const uint64_t da = smem_desc(a_stage + 2 * (dy + ks) * 2048, 2048, 128);
+                        const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
+                        umma_16bit(tmem_base + 3 * C * dy, da, db, idesc, ks > 0 ? 1u : 0u);
+                    }
+                umma_commit(&empty[stage]);
+                umma_commit(tmem_full);
+            }
+            __syncwarp();
+            if (++stage == C1_STAGES) { stage = 0; phase ^= 1; }
+            acc_phase ^= 1;
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp - 4, m = q * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t acc_phase = 0;
+        const int per_frame = p.P1h * p.P1w;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const long long pix = (long long)tile * 128 + m;
+            const bool valid = pix < p.n_pooled;
+            const int b = valid ? (int)(pix / per_frame) : 0;
+            const int rem = valid ? (int)(pix % per_frame) : 0;
+            const int Y = rem / p.P1w, X = rem % p.P1w;
+            mbar_wait(tmem_full, acc_phase);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int cb = 0; cb < C / 16; ++cb) {
+                float v[16];
+                pooled_block<C>(lane_base, cb, s_bias, s_scale, s_shift, v);
+                if (valid) store_pixel<C>(p.out, b, Y, X, cb, v);
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            acc_phase ^= 1;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ input packing
+// K1 for the tensor-core path: decoded frames -> x-unfolded 16-bit operands (pixel value * kPixelScale / 255, RGB order).
+// One thread per (frame, output row, pooled column): five resized pixels, 32 bytes out.
+__device__ __forceinline__ void resized_pixel(const ResizePlanDev &plan, const uint8_t *frame, int64_t row_pitch, int compact,
+                                              int y, int x, int (&v)[3]) {
+    if (plan.gather_step_x > 0) {       // pure gather (integer scale, e.g. 720p -> 256x144: src[5y+2][5x+2])
+        const int sy = plan.gather_off_y + y * plan.gather_step_y;
+        const int r = compact ? plan.row_slot[sy] : sy;
+        const uint8_t *q = frame + (int64_t)r * row_pitch + 3 * (plan.gather_off_x + x * plan.gather_step_x);
+        v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
+    } else if (plan.mode == RESIZE_COPY) {
+        const int r = compact ? plan.row_slot[y] : y;
+        const uint8_t *q = frame + (int64_t)r * row_pitch + 3 * x;
+        v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
+    } else if (plan.mode == RESIZE_AREA2) {
+        const int r0 = compact ? plan.row_slot[2 * y] : 2 * y, r1 = compact ? plan.row_slot[2 * y + 1] : 2 * y + 1;
+        const uint8_t *q0 = frame + (int64_t)r0 * row_pitch + 6 * x, *q1 = frame + (int64_t)r1 * row_pitch + 6 * x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = (q0[c] + q0[3 + c] + q1[c] + q1[3 + c] + 2) >> 2;
+    } else {
+        const int x0 = plan.x0[x], x1 = plan.x1[x], a0 = plan.a0[x], a1 = plan.a1[x];
+        const int y0 = plan.y0[y], y1 = plan.y1[y], b0 = plan.b0[y], b1 = plan.b1[y];
+        const uint8_t *q0 = frame + (int64_t)(compact ? plan.row_slot[y0] : y0) * row_pitch;
+        int s0[3], s1[3] = {0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s0[c] = a0 * q0[3 * x0 + c] + (a1 ? a1 * q0[3 * x1 + c] : 0);
+        if (b1) {
+            const uint8_t *q1 = frame + (int64_t)(compact ? plan.row_slot[y1] : y1) * row_pitch;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s1[c] = a0 * q1[3 * x0 + c] + (a1 ? a1 * q1[3 * x1 + c] : 0);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = min(max((((b0 * (s0[c] >> 4)) >> 16) + ((b1 * (s1[c] >> 4)) >> 16) + 2) >> 2, 0), 255);
+    }
+}
+
+__global__ void __launch_bounds__(256) preprocess_xin_kernel(ResizePlanDev plan, const uint8_t *__restrict__ frames,
+                                                             int64_t frame_stride, int64_t row_pitch, int compact, int batch,
+                                                             int P1w, uint4 *__restrict__ xin) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)batch * plan.dst_h * P1w;
+    if (idx >= total) return;
+    const int px = (int)(idx % P1w), y = (int)((idx / P1w) % plan.dst_h), b = (int)(idx / ((int64_t)P1w * plan.dst_h));
+    const uint8_t *frame = frames + (int64_t)b * frame_stride;
+    float e[16];
+#pragma unroll
+    for (int col = 0; col < 5; ++col) {
+        const int x = 3 * px - 1 + col;
+        int v[3] = {0, 0, 0};
+        if (x >= 0 && x < plan.dst_w) resized_pixel(plan, frame, row_pitch, compact, y, x, v);
+        constexpr float kU8Scale = kPixelScale / 255.f;     // 1 (bf16: 0..255) or 1/256 (fp16: exact, in [0,1))
+        e[col * 3 + 0] = (float)v[2] * kU8Scale;      // BGR -> RGB
+        e[col * 3 + 1] = (float)v[1] * kU8Scale;
+        e[col * 3 + 2] = (float)v[0] * kU8Scale;
+    }
+    e[15] = 0.f;
+    uint4 lo, hi;
+    lo.x = pack2(e[0], e[1]); lo.y = pack2(e[2], e[3]); lo.z = pack2(e[4], e[5]); lo.w = pack2(e[6], e[7]);
+    hi.x = pack2(e[8], e[9]); hi.y = pack2(e[10], e[11]); hi.z = pack2(e[12], e[13]); hi.w = pack2(e[14], e[15]);
+    xin[idx * 2] = lo;
+    xin[idx * 2 + 1] = hi;
+}
+
+// The float entry point: x float32 [B,3,H,W] in [0,1] -> x-unfolded 16-bit operands (x * kPixelScale).
+__global__ void __launch_bounds__(256) pack_xin_f32_kernel(const float *__restrict__ x, int batch, int H, int W, int P1w,
+                                                           uint4 *__restrict__ xin) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)batch * H * P1w;
+    if (idx >= total) return;
+    const int px = (int)(idx % P1w), y = (int)((idx / P1w) % H), b = (int)(idx / ((int64_t)P1w * H));
+    const float *img = x + (int64_t)b * 3 * H * W + (int64_t)y * W;
+    float e[16];
+#pragma unroll
+    for (int col = 0; col < 5; ++col) {
+        const int xx = 3 * px - 1 + col;
+        const bool ok = xx >= 0 && xx < W;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) e[col * 3 + ch] = ok ? img[(int64_t)ch * H * W + xx] * kPixelScale : 0.f;
+    }
+    e[15] = 0.f;
+    uint4 lo, hi;
+    lo.x = pack2(e[0], e[1]); lo.y = pack2(e[2], e[3]); lo.z = pack2(e[4], e[5]); lo.w = pack2(e[6], e[7]);
+    hi.x = pack2(e[8], e[9]); hi.y = pack2(e[10], e[11]); hi.z = pack2(e[12], e[13]); hi.w = pack2(e[14], e[15]);
+    xin[idx * 2] = lo;
+    xin[idx * 2 + 1] = hi;
+}
+
+// Test hook: phase-split 16-bit activation -> float32 NCHW.
+__global__ void unpack_phase_split_kernel(const uint16_t *__restrict__ act, int frames_cap, int batch, int C, int ph, int pw,
+                                          int Qh, int Qw, float *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)batch * C * ph * pw;
+    if (idx >= total) return;
+    const int x = (int)(idx % pw), y = (int)((idx / pw) % ph), c = (int)((idx / ((int64_t)pw * ph)) % C);
+    const int b = (int)(idx / ((int64_t)pw * ph * C));
+    const int plane = ((y % 3) * 3 + (x % 3)) * frames_cap + b;
+    const size_t src = ((((size_t)plane * (C / 8) + c / 8) * Qh + y / 3) * Qw + x / 3) * 8 + c % 8;
+    out[idx] = kBf16 ? __bfloat162float(__ushort_as_bfloat16(act[src])) : __half2float(__ushort_as_half(act[src]));
+}
+
+__global__ void unpack_plain_kernel(const float *__restrict__ act, int batch, int C, int npix, float *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)batch * C * npix;
+    if (idx >= total) return;
+    const int pix = (int)(idx % npix), c = (int)((idx / npix) % C), b = (int)(idx / ((int64_t)npix * C));
+    out[idx] = act[((size_t)b * npix + pix) * C + c];
+}
+
+// ------------------------------------------------------------------------------------------------ head, first FC
+// AdaptiveAvgPool2d + flatten + Linear folded into one [hidden x (P3 pixels * C)] matrix (the pool is linear), then
+// ReLU and the BatchNorm1d affine.  One warp per 4 frames, lane = hidden unit (hidden <= 32).
+__global__ void __launch_bounds__(128) head_fc1_kernel(const float *__restrict__ act3, const float *__restrict__ w_folded,
+                                                       const float *__restrict__ bias, const float *__restrict__ scale,
+                                                       const float *__restrict__ shift, int batch, int n_feat, int hidden,
+                                                       int relu, float *__restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int f0 = warp * 4;
+    if (f0 >= batch) return;
+    const int nf = min(4, batch - f0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < n_feat; k0 += 32) {
+        float a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = (i < nf && k0 + lane < n_feat) ? act3[(size_t)(f0 + i) * n_feat + k0 + lane] : 0.f;
+        const int kn = min(32, n_feat - k0);
+        for (int kk = 0; kk < kn; ++kk) {
+            const float w = lane < hidden ? w_folded[(size_t)(k0 + kk) * 32 + lane] : 0.f;     // [n_feat][32], coalesced
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(__shfl_sync(0xffffffffu, a[i], kk), w, acc[i]);
+        }
+    }
+    if (lane < hidden) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i >= nf) break;
+            float s = acc[i] + bias[lane];
+            if (relu) s = fmaxf(s, 0.f);
+            if (scale) s = fmaf(s, scale[lane], shift[lane]);
+            out[(size_t)(f0 + i) * hidden + lane] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host state
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// Phase-split activation as a 5-D tensor: (x/3 * 8 + ch%8, y/3, frame, ch/8, phase), box = one shifted view of a tile.
+int make_act_map(CUtensorMap *map, void *base, int frames_cap, int CG, int Qh, int Qw, int box_w, int box_r, int box_f) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(CUTDET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t plane = (cuuint64_t)Qh * Qw * 16;
+    cuuint64_t dims[5] = {(cuuint64_t)Qw * 8, (cuuint64_t)Qh, (cuuint64_t)frames_cap, (cuuint64_t)CG, 9};
+    cuuint64_t strides[4] = {(cuuint64_t)Qw * 16, plane * CG, plane, plane * CG * frames_cap};
+    cuuint32_t box[5] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_r, (cuuint32_t)box_f, (cuuint32_t)CG, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, kBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CUTDET_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return CUTDET_OK;
+}
+
+}  // namespace
+
+struct TcState {
+    int C = 0;
+    void *d_w1 = nullptr, *d_w2 = nullptr, *d_w3 = nullptr;   // packed 16-bit operands
+    std::map<std::tuple<const void *, int, int>, std::pair<CUtensorMap, CUtensorMap>> maps;   // (workspace, H, W) -> act1, act2 maps
+    std::map<std::pair<int, int>, float *> fc1_folded;                                        // (P3h, P3w) -> [n_feat][32]
+    std::mutex mutex;
+    int smem_set = 0;
+};
+
+namespace {
+
+struct TcWorkspace {
+    size_t xin, act1, act2, act3, fc[2], total;
+    int sub;
+};
+
+TcWorkspace tc_workspace(const cutdet_net *net, const Geom &g, int batch) {
+    TcWorkspace w;
+    w.sub = batch < SUB_BATCH ? batch : SUB_BATCH;
+    size_t off = 0;
+    w.xin = off;  off = align_up(off + g.xin_frame * w.sub, 1024);
+    w.act1 = off; off = align_up(off + g.act1_frame * w.sub, 1024);
+    w.act2 = off; off = align_up(off + g.act2_frame * w.sub, 1024);
+    w.act3 = off; off = align_up(off + g.act3_frame * batch, 1024);
+    size_t widest = net->cfg.fc_hidden_size > net->cfg.fc_input_size ? net->cfg.fc_hidden_size : net->cfg.fc_input_size;
+    for (int i = 0; i < 2; ++i) { w.fc[i] = off; off = align_up(off + widest * sizeof(float) * batch, 1024); }
+    w.total = off;
+    return w;
+}
+
+uint16_t operand_bits(float f) {      // float -> the 16-bit operand format, round to nearest even
+    if (!kBf16) {
+        const __half h = __float2half_rn(f);
+        uint16_t b;
+        memcpy(&b, &h, 2);
+        return b;
+    }
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+int upload_bytes(cutdet_net *net, const void *host, size_t bytes, void **dev) {
+    CUTDET_CUDA(cudaMalloc(dev, bytes));
+    net->dev_allocs.push_back(*dev);
+    CUTDET_CUDA(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+    return CUTDET_OK;
+}
+
+template <int C>
+int set_smem_limits() {
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1Smem<C>::total));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return CUTDET_OK;
+}
+
+template <int C>
+int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
+    const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+    {
+        KernelScope scope("conv1_tc", stream);
+        conv1_tc_kernel<C><<<grid, 288, C1Smem<C>::total, stream>>>(p);
+    }
+    CUTDET_LAUNCH_CHECK("conv1_tc_kernel");
+    return CUTDET_OK;
+}
+
+template <int C>
+int launch_mid(const CUtensorMap &map, const MidParams &p, const char *name, cudaStream_t stream) {
+    const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+    const int smem = MidSmem<C>::total(p.MT);
+    if (smem > 227 * 1024) return fail(CUTDET_EUNSUPPORTED, "conv tile needs %d bytes of shared memory", smem);
+    {
+        KernelScope scope(name, stream);
+        conv_mid_tc_kernel<C><<<grid, 256, smem, stream>>>(map, p);
+    }
+    CUTDET_LAUNCH_CHECK("conv_mid_tc_kernel");
+    return CUTDET_OK;
+}
+
+MidParams mid_params(const TileCfg &t, int nb, int out_h, int out_w) {
+    MidParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = nb; p.out_h = out_h; p.out_w = out_w;
+    p.R = t.R; p.F = t.F; p.MT = t.MT; p.n_rg = t.n_rg;
+    p.n_tiles = ((nb + t.F - 1) / t.F) * t.n_rg;
+    return p;
+}
+
+// conv stack over one sub-batch whose x-unfolded input already sits in the workspace
+template <int C>
+int run_conv_stack(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int nb, int frame0, cudaStream_t stream) {
+    TcState *tc = net->tc;
+    std::pair<CUtensorMap, CUtensorMap> *maps = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(tc->mutex);
+        auto key = std::make_tuple((const void *)ws, g.H * 65536 + g.W, w.sub);
+        auto it = tc->maps.find(key);
+        if (it == tc->maps.end()) {
+            std::pair<CUtensorMap, CUtensorMap> m;
+            if (int rc = make_act_map(&m.first, ws + w.act1, w.sub, g.CG, g.Q1h, g.Q1w, g.P2w, g.t2.R, g.t2.F)) return rc;
+            if (int rc = make_act_map(&m.second, ws + w.act2, w.sub, g.CG, g.Q2h, g.Q2w, g.P3w, g.t3.R, g.t3.F)) return rc;
+            it = tc->maps.emplace(key, m).first;
+        }
+        maps = &it->second;
+    }
+    Conv1Params c1;
+    memset(&c1, 0, sizeof(c1));
+    c1.xin = reinterpret_cast<const uint4 *>(ws + w.xin);
+    c1.B = nb; c1.H = g.H; c1.P1h = g.P1h; c1.P1w = g.P1w;
+    c1.n_pooled = (long long)nb * g.P1h * g.P1w;
+    c1.n_tiles = (int)((c1.n_pooled + 127) / 128);
+    c1.out = OutSpec{ws + w.act1, 0, w.sub, g.Q1h, g.Q1w, g.P1h, g.P1w};
+    c1.w_packed = reinterpret_cast<const uint4 *>(tc->d_w1);
+    c1.bias = net->conv[0].d_bias; c1.scale = net->conv[0].d_scale; c1.shift = net->conv[0].d_shift;
+    if (int rc = launch_conv1<C>(c1, stream)) return rc;
+
+    MidParams p2 = mid_params(g.t2, nb, g.P2h, g.P2w);
+    p2.out = OutSpec{ws + w.act2, 0, w.sub, g.Q2h, g.Q2w, g.P2h, g.P2w};
+    p2.w_packed = reinterpret_cast<const uint4 *>(tc->d_w2);
+    p2.bias = net->conv[1].d_bias; p2.scale = net->conv[1].d_scale; p2.shift = net->conv[1].d_shift;
+    if (int rc = launch_mid<C>(maps->first, p2, "conv2_tc", stream)) return rc;
+
+    MidParams p3 = mid_params(g.t3, nb, g.P3h, g.P3w);
+    p3.out = OutSpec{ws + w.act3 + (size_t)frame0 * g.act3_frame, 1, nb, 0, 0, g.P3h, g.P3w};
+    p3.w_packed = reinterpret_cast<const uint4 *>(tc->d_w3);
+    p3.bias = net->conv[2].d_bias; p3.scale = net->conv[2].d_scale; p3.shift = net->conv[2].d_shift;
+    return launch_mid<C>(maps->second, p3, "conv3_tc", stream);
+}
+
+int run_stack(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int nb, int frame0, cudaStream_t stream) {
+    return g.C == 48 ? run_conv_stack<48>(net, g, w, ws, nb, frame0, stream) : run_conv_stack<32>(net, g, w, ws, nb, frame0, stream);
+}
+
+// AdaptiveAvgPool + first FC folded, for this pooled-map size; built once and cached.
+int folded_fc1(cutdet_net *net, const Geom &g, float **out) {
+    TcState *tc = net->tc;
+    std::lock_guard<std::mutex> lock(tc->mutex);
+    auto key = std::make_pair(g.P3h, g.P3w);
+    auto it = tc->fc1_folded.find(key);
+    if (it != tc->fc1_folded.end()) { *out = it->second; return CUTDET_OK; }
+    const int P = net->cfg.avg_pool_size, C = g.C, npix = g.P3h * g.P3w, n_feat = npix * C;
+    const FcLayer &L = net->fc[0];
+    std::vector<float> folded((size_t)n_feat * 32, 0.f);
+    std::vector<double> acc((size_t)n_feat * L.out, 0.0);
+    for (int i = 0; i < P; ++i) {
+        const int r0 = (i * g.P3h) / P, r1 = ((i + 1) * g.P3h + P - 1) / P;
+        for (int j = 0; j < P; ++j) {
+            const int c0 = (j * g.P3w) / P, c1 = ((j + 1) * g.P3w + P - 1) / P;
+            const double inv = 1.0 / ((r1 - r0) * (c1 - c0));
+            for (int r = r0; r < r1; ++r)
+                for (int cc = c0; cc < c1; ++cc)
+                    for (int ch = 0; ch < C; ++ch)
+                        for (int o = 0; o < L.out; ++o)
+                            acc[((size_t)(r * g.P3w + cc) * C + ch) * L.out + o] += inv * L.w[(size_t)o * L.in + ch * P * P + i * P + j];
+        }
+    }
+    for (int f = 0; f < n_feat; ++f)
+        for (int o = 0; o < L.out; ++o) folded[(size_t)f * 32 + o] = (float)acc[(size_t)f * L.out + o];
+    void *d = nullptr;
+    if (int rc = upload_bytes(net, folded.data(), folded.size() * sizeof(float), &d)) return rc;
+    tc->fc1_folded[key] = reinterpret_cast<float *>(d);
+    *out = reinterpret_cast<float *>(d);
+    return CUTDET_OK;
+}
+
+int run_head(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int batch, float *logits, cudaStream_t stream) {
+    const float *cur = reinterpret_cast<const float *>(ws + w.act3);
+    const int n_feat = g.P3h * g.P3w * g.C;
+    if (net->cfg.n_fc_layers == 0) {
+        // a bare FrameConvNet: pooled features [B, C*P*P] in (c, i, j) order -- not on the prod path
+        return fail(CUTDET_EUNSUPPORTED, "tensor-core path needs at least one FC layer");
+    }
+    float *folded = nullptr;
+    if (int rc = folded_fc1(net, g, &folded)) return rc;
+    const FcLayer &L0 = net->fc[0];
+    const bool last0 = net->cfg.n_fc_layers == 1;
+    float *out0 = last0 ? logits : reinterpret_cast<float *>(ws + w.fc[0]);
+    {
+        KernelScope scope("head_fc1", stream);
+        const int warps = (batch + 3) / 4;
+        head_fc1_kernel<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(cur, folded, L0.d_bias, L0.has_bn ? L0.d_scale : nullptr,
+                                                                     L0.has_bn ? L0.d_shift : nullptr, batch, n_feat, L0.out,
+                                                                     last0 ? 0 : 1, out0);
+    }
+    CUTDET_LAUNCH_CHECK("head_fc1_kernel");
+    cur = out0;
+    for (int j = 1; j < net->cfg.n_fc_layers; ++j) {
+        const bool is_last = j + 1 == net->cfg.n_fc_layers;
+        float *out = is_last ? logits : reinterpret_cast<float *>(ws + w.fc[j & 1]);
+        if (int rc = launch_fc(cur, out, net->fc[j], batch, !is_last, stream)) return rc;
+        cur = out;
+    }
+    return CUTDET_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ interface
+bool tc_supported(const cutdet_net *net, int height, int width) {
+    if (!net->tc) return false;
+    const Geom g = make_geom(height, width, net->cfg.hidden_channels);
+    if (g.P3h < 1 || g.P3w < 1) return false;
+    if (g.P2w > 32 || g.P3w > 32) return false;                       // TMA box: at most 256 elements wide
+    if (MidSmem<48>::total(g.t2.MT) > 227 * 1024) return false;
+    return true;
+}
+
+int tc_prepare(cutdet_net *net) {
+    const cutdet_net_config &c = net->cfg;
+    if (c.n_conv_layers != 3 || c.input_channels != 3 || (c.hidden_channels != 48 && c.hidden_channels != 32)) return CUTDET_OK;
+    if (c.n_fc_layers < 1 || c.fc_hidden_size > 32 || (c.n_fc_layers == 1 && c.fc_output_size > 32)) return CUTDET_OK;
+    if (!encode_fn()) return CUTDET_OK;          // no TMA descriptor encoder in this driver: stay on the generic kernels
+    const int C = c.hidden_channels, CG = C / 8;
+    TcState *tc = new TcState();
+    tc->C = C;
+    net->tc = tc;
+    // conv1 B operand: [ky][half][n = dx*C + co][8], k16 = col*3 + ch, taps / 255
+    {
+        std::vector<uint16_t> w((size_t)6 * 3 * C * 8, 0);
+        const ConvLayer &L = net->conv[0];
+        for (int ky = 0; ky < 3; ++ky)
+            for (int col = 0; col < 5; ++col)
+                for (int ch = 0; ch < 3; ++ch)
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int kx = col - dx;
+                        if (kx < 0 || kx > 2) continue;
+                        const int k16 = col * 3 + ch;
+                        for (int co = 0; co < C; ++co) {
+                            const float v = L.w[((size_t)co * 3 + ch) * 9 + ky * 3 + kx] * kW1Scale;
+                            w[(((size_t)(2 * ky + k16 / 8)) * 3 * C + dx * C + co) * 8 + k16 % 8] = operand_bits(v);
+                        }
+                    }
+        if (int rc = upload_bytes(net, w.data(), w.size() * 2, &tc->d_w1)) return rc;
+    }
+    // conv2/3 B operand: [ky][ci/8][n' = blk*C + co, blk <-> kx = 2-blk][8]
+    for (int layer = 1; layer <= 2; ++layer) {
+        std::vector<uint16_t> w((size_t)3 * CG * 3 * C * 8, 0);
+        const ConvLayer &L = net->conv[layer];
+        for (int ky = 0; ky < 3; ++ky)
+            for (int ci = 0; ci < C; ++ci)
+                for (int blk = 0; blk < 3; ++blk)
+                    for (int co = 0; co < C; ++co) {
+                        const float v = L.w[((size_t)co * C + ci) * 9 + ky * 3 + (2 - blk)];
+                        w[((((size_t)ky * CG + ci / 8) * 3 * C) + blk * C + co) * 8 + ci % 8] = operand_bits(v);
+                    }
+        if (int rc = upload_bytes(net, w.data(), w.size() * 2, layer == 1 ? &tc->d_w2 : &tc->d_w3)) return rc;
+    }
+    return C == 48 ? set_smem_limits<48>() : set_smem_limits<32>();
+}
+
+void tc_destroy(cutdet_net *net) {
+    delete net->tc;
+    net->tc = nullptr;
+}
+
+size_t tc_workspace_bytes(const cutdet_net *net, int batch, int height, int width) {
+    const Geom g = make_geom(height, width, net->cfg.hidden_channels);
+    return tc_workspace(net, g, batch).total + 1024;
+}
+
+int tc_forward_f32(cutdet_net *net, const float *x, int batch, int height, int width, float *logits, char *ws, cudaStream_t stream) {
+    const Geom g = make_geom(height, width, net->cfg.hidden_channels);
+    const TcWorkspace w = tc_workspace(net, g, batch);
+    for (int f0 = 0; f0 < batch; f0 += w.sub) {
+        const int nb = batch - f0 < w.sub ? batch - f0 : w.sub;
+        const int64_t total = (int64_t)nb * g.H * g.P1w;
+        {
+            KernelScope scope("pack_xin_f32", stream);
+            pack_xin_f32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(x + (size_t)f0 * 3 * height * width, nb, g.H, g.W,
+                                                                                   g.P1w, reinterpret_cast<uint4 *>(ws + w.xin));
+        }
+        CUTDET_LAUNCH_CHECK("pack_xin_f32_kernel");
+        if (int rc = run_stack(net, g, w, ws, nb, f0, stream)) return rc;
+    }
+    return run_head(net, g, w, ws, batch, logits, stream);
+}
+
+int tc_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cutdet_frames *src, float *logits, char *ws,
+                      cudaStream_t stream) {
+    const int batch = src->batch;
+    const Geom g = make_geom(plan->host.dst_h, plan->host.dst_w, net->cfg.hidden_channels);
+    const TcWorkspace w = tc_workspace(net, g, batch);
+    for (int f0 = 0; f0 < batch; f0 += w.sub) {
+        const int nb = batch - f0 < w.sub ? batch - f0 : w.sub;
+        const int64_t total = (int64_t)nb * g.H * g.P1w;
+        {
+            KernelScope scope("preprocess_xin", stream);
+            preprocess_xin_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(
+                plan->host, src->frames_dev + (int64_t)f0 * src->frame_stride, src->frame_stride, src->row_pitch,
+                src->row_map_compact, nb, g.P1w, reinterpret_cast<uint4 *>(ws + w.xin));
+        }
+        CUTDET_LAUNCH_CHECK("preprocess_xin_kernel");
+        if (int rc = run_stack(net, g, w, ws, nb, f0, stream)) return rc;
+    }
+    return run_head(net, g, w, ws, batch, logits, stream);
+}
+
+int tc_debug_conv_output(cutdet_net *net, int layer, int batch, int height, int width, const char *ws, float *out,
+                         cudaStream_t stream) {
+    const Geom g = make_geom(height, width, net->cfg.hidden_channels);
+    const TcWorkspace w = tc_workspace(net, g, batch);
+    if (batch > w.sub && layer < 2)
+        return fail(CUTDET_EUNSUPPORTED, "debug_conv_output: layers 0 and 1 are only kept for batches of up to %d frames", SUB_BATCH);
+    if (layer == 2) {
+        const int64_t total = (int64_t)batch * g.C * g.P3h * g.P3w;
+        unpack_plain_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(reinterpret_cast<const float *>(ws + w.act3), batch, g.C,
+                                                                               g.P3h * g.P3w, out);
+    } else {
+        const int ph = layer == 0 ? g.P1h : g.P2h, pw = layer == 0 ? g.P1w : g.P2w;
+        const int Qh = layer == 0 ? g.Q1h : g.Q2h, Qw = layer == 0 ? g.Q1w : g.Q2w;
+        const int64_t total = (int64_t)batch * g.C * ph * pw;
+        unpack_phase_split_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(
+            reinterpret_cast<const uint16_t *>(ws + (layer == 0 ? w.act1 : w.act2)), w.sub, batch, g.C, ph, pw, Qh, Qw, out);
+    }
+    CUTDET_LAUNCH_CHECK("unpack kernel");
+    return CUTDET_OK;
 }
 
 }  // namespace cutdet

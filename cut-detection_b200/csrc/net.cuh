@@ -7,6 +7,8 @@
 
 namespace cutdet {
 
+struct TcState;   // tensor-core path (conv_tc.cu)
+
 struct ConvLayer {
     int cin = 0, cout = 0;
     bool set = false;
@@ -45,5 +47,5 @@ struct cutdet_net {
     std::vector<cutdet::FcLayer> fc;
     bool finalized = false;
     std::vector<void *> dev_allocs;
-    struct TcState *tc = nullptr;   // tensor-core path (conv_tc.cu), null when not applicable
+    cutdet::TcState *tc = nullptr;  // tensor-core path (conv_tc.cu), null when not applicable
 };

@@ -184,3 +184,64 @@ def forward_f64(weights: dict, x: np.ndarray, avg_pool_size: int, return_feature
             y = _bn_f64(y, g(p + ".bn.weight"), g(p + ".bn.bias"), g(p + ".bn.running_mean"),
                         g(p + ".bn.running_var"), (1, -1))
     return (y, feats) if return_features else y
+
+
+# ----------------------------------------------------------------------------- 16-bit operand emulation
+def _bf16_round(a: np.ndarray) -> np.ndarray:
+    """Round float32 values to the nearest bfloat16 (ties to even), returned as float32."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = ((u.astype(np.uint64) + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    return r.view(np.float32)
+
+
+def _f16_round(a: np.ndarray) -> np.ndarray:
+    return np.asarray(a, dtype=np.float32).astype(np.float16).astype(np.float32)
+
+
+def forward_tc_emulated(weights: dict, x: np.ndarray, avg_pool_size: int, fmt: str = "f16", return_features: bool = False):
+    """What the tensor-core path computes, restated on the CPU: conv operands rounded to 16 bits (fmt 'f16' as
+    cut-detection_b200/csrc/conv_tc.cu ships, or 'bf16'), layer-1 input stored as x*255/256 with 256/255 folded into its
+    weights (bf16: x*255 and 1/255), exact products, float32 epilogue (max-pool of the raw sums, +bias, ReLU, folded
+    BatchNorm affine), 16-bit inter-layer activations, float32 head.  It separates 'the kernel is wrong' from
+    '16-bit operands round': the CUDA path must match THIS to ~1e-3, and this differs from the fp32 reference by the
+    rounding the format implies."""
+    import torch
+    import torch.nn.functional as F
+
+    rnd = _f16_round if fmt == "f16" else _bf16_round
+    in_scale, w_scale = (np.float32(255.0 / 256.0), np.float32(256.0 / 255.0)) if fmt == "f16" else \
+        (np.float32(255.0), np.float32(1.0 / 255.0))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    n = n_conv_layers(weights)
+    feats = []
+    with torch.no_grad():
+        y = t(rnd(np.asarray(x, np.float32) * in_scale))
+        for i in range(n):
+            p = f"conv.conv_layers.{i}"
+            w = np.asarray(weights[p + ".conv.weight"], np.float32)
+            if i == 0:
+                w = w * w_scale
+            g = np.asarray(weights[p + ".bn.weight"], np.float64)
+            s = (g / np.sqrt(np.asarray(weights[p + ".bn.running_var"], np.float64) + BN_EPS)).astype(np.float32)
+            sh = (np.asarray(weights[p + ".bn.bias"], np.float64)
+                  - np.asarray(weights[p + ".bn.running_mean"], np.float64) * s.astype(np.float64)).astype(np.float32)
+            z = F.conv2d(y.double(), t(rnd(w)).double(), None, stride=1, padding=1).float()
+            z = F.max_pool2d(z, kernel_size=3)
+            z = torch.relu(z + t(weights[p + ".conv.bias"]).view(1, -1, 1, 1))
+            z = z * t(s).view(1, -1, 1, 1) + t(sh).view(1, -1, 1, 1)
+            if i < n - 1:
+                z = t(rnd(z.numpy()))
+            feats.append(z.numpy().copy())
+            y = z
+        y = F.adaptive_avg_pool2d(y, avg_pool_size)
+        y = torch.reshape(y, [y.shape[0], -1])
+        nfc = n_fc_layers(weights)
+        for j in range(nfc):
+            p = f"linear.layers.{j}"
+            y = F.linear(y, t(weights[p + ".linear.weight"]), t(weights[p + ".linear.bias"]))
+            if j < nfc - 1:
+                y = F.relu(y)
+                y = F.batch_norm(y, t(weights[p + ".bn.running_mean"]), t(weights[p + ".bn.running_var"]),
+                                 t(weights[p + ".bn.weight"]), t(weights[p + ".bn.bias"]), training=False, eps=BN_EPS)
+        out = y.numpy().copy()
+    return (out, feats) if return_features else out

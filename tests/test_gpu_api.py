@@ -28,11 +28,11 @@ def test_load_default_net_contract(prod_weights, golden_dir):
         y = net(x)
     assert y.dtype == torch.float32 and tuple(y.shape) == (48, 3)
     kat = np.load(os.path.join(golden_dir, "net_kat.npz"))
-    assert np.abs(y.cpu().numpy() - kat["smooth48_eager"]).max() <= 0.1
+    assert np.abs(y.cpu().numpy() - kat["smooth48_eager"]).max() <= 0.05
     # trunk and head also work on their own, like the reference's modules
     feats = net[0](x[:4])
     assert tuple(feats.shape) == (4, 768)
-    assert np.abs(net[1](feats).cpu().numpy() - kat["smooth48_eager"][:4]).max() <= 0.1
+    assert np.abs(net[1](feats).cpu().numpy() - kat["smooth48_eager"][:4]).max() <= 0.05
 
 
 def test_training_mode_and_cpu_inputs_raise():

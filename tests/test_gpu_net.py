@@ -1,8 +1,12 @@
 """K2/K3 on the GPU vs the oracle (float32 reference arithmetic) and the logits recorded from the reference.
 
-Tolerances (stated, per BASELINE.json north_star): the tensor-core path computes in bf16 with fp32 accumulation:
-|dlogit| <= 0.1 absolute, labels equal wherever the reference's top-2 margin is >= 0.2.  The generic CUDA-core
-path is float32 throughout: |dlogit| <= 2e-3 (summation order only).
+Tolerances (stated, per BASELINE.json north_star).  The tensor-core path multiplies 16-bit operands (fp16: pixels
+are exact, weights and inter-layer activations round at 2^-12) and accumulates in fp32:
+  * against the fp32 reference:  |dlogit| <= 0.05 absolute (observed <= 0.015), labels equal wherever the reference's
+    top-2 margin is >= 0.1;
+  * against the CPU emulation of the same 16-bit arithmetic (oracle.net.forward_tc_emulated): |dlogit| <= 5e-3 --
+    this is the check that the KERNELS are right, independent of what 16-bit rounding does.
+The generic CUDA-core path is float32 throughout: |dlogit| <= 2e-3 (summation order only).
 """
 import os
 
@@ -16,8 +20,8 @@ from oracle import preprocess as opre
 
 pytestmark = pytest.mark.gpu
 
-TOL_TC, TOL_F32 = 0.1, 2e-3
-MARGIN = 0.2
+TOL_TC, TOL_F32, TOL_EMU = 0.05, 2e-3, 5e-3
+MARGIN = 0.1
 
 
 def _check_logits(got, want, tol):
@@ -59,7 +63,7 @@ def test_layer_outputs(native, golden_dir):
         assert got.shape == want.shape
         scale = np.abs(want).max()
         err = np.abs(got - want).max()
-        assert err <= (0.03 * scale if tc else 1e-4 * scale + 1e-4), (i, err, scale)
+        assert err <= (4e-3 * scale if tc else 1e-4 * scale + 1e-4), (i, err, scale)
 
 
 def test_frames_known_answers(native, golden_dir):
@@ -83,6 +87,30 @@ def test_any_batch_size(native, prod_weights, batch):
     got = net.forward_f32(torch.from_numpy(x).cuda()).cpu().numpy()
     want = onet.forward_f32(w, x, params["avg_pool_size"])
     _check_logits(got, want, TOL_TC if net.uses_tensor_cores(144, 256) else TOL_F32)
+
+
+def test_matches_16bit_emulation(native, prod_weights):
+    """Kernel correctness proper: same operands, same rounding points, different summation order only."""
+    from cutdet import engine
+    net, params = native
+    if not net.uses_tensor_cores(144, 256):
+        pytest.skip("generic float32 path in use")
+    w, _ = prod_weights
+    x = kat_inputs.smooth_images(20, seed=77)
+    got = net.forward_f32(torch.from_numpy(x).cuda()).cpu().numpy()
+    want, feats = onet.forward_tc_emulated(w, x, params["avg_pool_size"], return_features=True)
+    assert np.abs(got - want).max() <= TOL_EMU
+    for i in range(3):
+        layer = net.debug_conv_output(i, 20, 144, 256).cpu().numpy()
+        err = np.abs(layer - feats[i]).max()
+        # a 1-ulp fp16 flip of a stored activation is 2^-11 relative; allow two of them
+        assert err <= 1e-3 * max(1.0, np.abs(feats[i]).max()), (i, err)
+    for name, frame in kat_inputs.kat_frames().items():
+        h, ww = frame.shape[:2]
+        plan = engine.ResizePlan.for_video(h, ww, 256)
+        got = net.forward_frames(plan, torch.from_numpy(frame[None]).cuda()).cpu().numpy()
+        want = onet.forward_tc_emulated(w, opre.preprocess_frame(frame)[None], params["avg_pool_size"])
+        assert np.abs(got - want).max() <= TOL_EMU, name
 
 
 def test_empty_batch(native):
@@ -113,7 +141,7 @@ def test_contrastive_encoder_architecture():
     x = kat_inputs.smooth_images(8, seed=21)
     got = net.forward_f32(torch.from_numpy(x).cuda()).cpu().numpy()
     want = onet.forward_f32(wts, x, 1)
-    tol = 0.05 if net.uses_tensor_cores(144, 256) else TOL_F32
+    tol = TOL_TC if net.uses_tensor_cores(144, 256) else TOL_F32
     assert got.shape == (8, 8) and np.abs(got - want).max() <= tol
 
 
