@@ -320,19 +320,23 @@ def run_native(args):
     kernels = json.loads(cbuf.value.decode())
     peaks = measured_peaks()
     total_ms = sum(k["ms"] for k in kernels.values()) or 1.0
-    per_launch_units = {   # algorithmic work of ONE launch (a chunk of frames)
-        "preprocess": ("hbm", K1_BYTES_720P * chunk), "conv_block_generic_L0": ("tensor", FLOPS["L0"] * chunk),
-        "conv_block_generic_L1": ("tensor", FLOPS["L1"] * chunk), "conv_block_generic_L2": ("tensor", FLOPS["L2"] * chunk),
-        "conv1_tc": ("tensor", FLOPS["L0"] * chunk), "conv2_tc": ("tensor", FLOPS["L1"] * chunk),
-        "conv3_tc": ("tensor", FLOPS["L2"] * chunk),
+    frames_profiled = prof_steps * chunk
+    per_frame_units = {   # algorithmic work per FRAME; a launch covers frames_profiled / launches frames
+        "preprocess": ("hbm", K1_BYTES_720P), "conv_block_generic_L0": ("tensor", FLOPS["L0"]),
+        "conv_block_generic_L1": ("tensor", FLOPS["L1"]), "conv_block_generic_L2": ("tensor", FLOPS["L2"]),
+        "conv1_tc": ("tensor", FLOPS["L0"]), "conv2_tc": ("tensor", FLOPS["L1"]), "conv3_tc": ("tensor", FLOPS["L2"]),
     }
     table = {}
     for name, k in kernels.items():
         avg_ms = k["ms"] / max(k["launches"], 1)
-        row = {"launches": k["launches"], "avg_ms": avg_ms, "share": k["ms"] / total_ms}
-        key = next((u for u in per_launch_units if name.startswith(u)), None)
+        frames_per_launch = frames_profiled / max(k["launches"], 1)
+        row = {"launches": k["launches"], "avg_ms": avg_ms, "share": k["ms"] / total_ms,
+               "ms_per_step": k["ms"] / prof_steps}
+        key = next((u for u in per_frame_units if name.startswith(u)), None)
         if key:
-            bound, units = per_launch_units[key]
+            bound, per_frame = per_frame_units[key]
+            units = per_frame * frames_per_launch
+            row["frames_per_launch"] = frames_per_launch
             if bound == "hbm":
                 row.update(bound="hbm", achieved=units / (avg_ms * 1e-3) / 1e9, unit="GB/s", peak=peaks["hbm_gbs"])
             else:
@@ -352,7 +356,7 @@ def run_native(args):
                     "frac": d["frac"], "traffic": traffic, "share_of_step": d["share"], "avg_launch_ms": d["avg_ms"],
                     "peak_source": peaks["source"] + (" (sustained bf16: kernel timed inside a long step)" if d["bound"] == "tensor" else ""),
                     "net_tflops_whole_conv_stack": NET_FLOPS * chunk / 1e12 / (1e-3 * sum(
-                        r["avg_ms"] for n, r in table.items() if n.startswith(("conv", "head", "fc", "avgpool"))) or 1.0)}
+                        r["ms_per_step"] for n, r in table.items() if n.startswith(("conv", "head", "fc", "avgpool"))) or 1.0)}
 
     # ---------------- CPU baseline + whole-clip parity (rank 0, N = 1)
     cpu_baseline = None
@@ -393,7 +397,7 @@ def run_native(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if uses_tc else "f32", "data": "synthetic",
+            "dtype": "f16" if uses_tc else "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: full-game synthetic 720p30 batch inference + segmentation "
                                    f"({K} steps x {chunk} frames per GPU; decode excluded)",
                        "resolution": [WIDTH, HEIGHT], "chunk_frames": chunk, "frames_per_gpu": frames_local,
