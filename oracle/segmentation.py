@@ -165,3 +165,29 @@ def segment(scores: np.ndarray, real_threshold: int = 100, blank_threshold: int 
     t1 = glue_orphans(t0, real_threshold, blank_threshold)
     t2 = combine_adjacent(t1)
     return t0, t1, t2, csv_bytes(t2)
+
+
+def stitch_tables(shards: list, frame_offsets: list) -> dict:
+    """Join the run tables of consecutive time shards (LOCAL frame numbers, each with a float64 ``score_sums``
+    column) into the table of the whole sequence: what ``Segmentation.__init__`` (segmentation.py:35-60) would
+    have built from the concatenated scores.  Runs that meet at a shard edge with the same type are merged --
+    sums and lengths add, so the mean is that of the joined slice.  Checker for cutdet_stitch_shards."""
+    end, start, length, kind, sums = [], [], [], [], []
+    for te, off in zip(shards, frame_offsets):
+        for i in range(len(te["end_frames"])):
+            e, s = int(te["end_frames"][i]) + off, int(te["start_frames"][i]) + off
+            k, sm = int(te["frame_types"][i]), float(te["score_sums"][i])
+            if i == 0 and kind and kind[-1] == k:
+                end[-1] = e
+                length[-1] = e - start[-1] + 1
+                sums[-1] += sm
+            else:
+                end.append(e); start.append(s); length.append(e - s + 1); kind.append(k); sums.append(sm)
+    return {
+        "end_frames": np.array(end, dtype=np.int64),
+        "frame_types": np.array(kind, dtype=np.int64),
+        "run_lengths": np.array(length, dtype=np.int64),
+        "start_frames": np.array(start, dtype=np.int64),
+        "score_means": np.array([np.float32(s / l) for s, l in zip(sums, length)], dtype=np.float32),
+        "score_sums": np.array(sums, dtype=np.float64),
+    }
