@@ -12,18 +12,29 @@
 // reference does, and writes C channels.  No shuffles, no shared-memory round trip, and the full-resolution
 // activation (7 MB/frame in fp32 for layer 1) never exists anywhere.
 //
+// The accumulator is drained ROW BY ROW of the pool window: the MMAs of block row dy = 0 are issued (and committed)
+// first, then dy = 1, then dy = 2, each block row with its own full/empty mbarrier pair.  The epilogue keeps a running
+// max in registers and hands a block row back the moment it has been read, so the MMAs of the next tile's row dy
+// overlap the epilogue of this tile's rows dy+1, dy+2: 432 columns behave like a three-deep accumulator ring.
+// Eight epilogue warps (two per TMEM lane quarter, each taking half of the channels) hide the TMEM load latency.
+//
 //   conv1 (Cin = 3):   K1 writes the input "x-unfolded": for every image row and pooled column px the 5 input pixels
 //       3px-1 .. 3px+3 (x3 channels, +1 pad = 16 halves = one UMMA K-chunk).  A row of the A operand is then five such
 //       chunks (input rows 3py-1 .. 3py+3), gathered by cp.async.  For conv-row dy the MMA takes K-chunks dy..dy+2
 //       against ONE B matrix [48 x 3C] that holds the taps of the three dx positions (zero where a tap falls outside):
 //       9 MMAs of N = 3C per 128 pooled pixels.  Pixels are stored as v/256 (exact in fp16); 256/255 is folded into
-//       the weights.
-//   conv2/conv3 (Cin = C): activations live "phase-split": [y%3][x%3][frame][c/8][y/3][x/3][8 ch] fp16.  The input
-//       pixel (3Y+oy, 3X+ox) needed by pooled pixel (Y, X) is then a DENSE box of one phase plane, fetched by one TMA
-//       (out-of-range coordinates are zero-filled = the conv's zero padding).  The 25 shifted views (oy, ox in -1..3)
-//       are each used by every (dy, ky), (dx, kx) with dy+ky-1 = oy, dx+kx-1 = ox; the dx positions that share a view
-//       are adjacent column blocks, so they are ONE MMA of N = C * n_dx against a B matrix stacked [kx=2 | kx=1 | kx=0]:
-//       135 MMAs per 128 pooled pixels instead of 243.
+//       the weights.  One CTA walks one frame (32 tiles at 256x144), frames round-robin over the CTAs.
+//   conv2/conv3 (Cin = C): activations live "phase-split and flattened":
+//           act[(y%3)*3 + x%3][c/8][frame*FP + (y/3)*PW + x/3][8 ch]  fp16,  PW = Win/3 + 1, QH = Hin/3 + 1, FP = QH*PW
+//       with every entry that is not a real pixel equal to zero.  A GEMM row is the flattened position g of a pooled pixel
+//       (Y, X) -> g = frame*FP + Y*PW + X; the input pixel (3Y+oy, 3X+ox) it needs (oy, ox in -1..3) is entry
+//       g + sy*PW + sx of phase plane ((oy+3)%3, (ox+3)%3), sy/sx in {-1, 0, +1}: a plain OFFSET.  The zero column PW-1
+//       and the zero row QH-1 double as the conv's zero padding of the next row / next frame, so the 25 shifted views of
+//       a tile are 25 start addresses into ONE copy of the tile's nine planes (+-32 positions of halo) in shared memory.
+//       The planes arrive by TMA 16 channels at a time (3 pipeline stages of 54 KB); positions that are padding
+//       (X >= out_w, Y >= out_h) are GEMM rows whose results are dropped (9 % at 16x28, 25 % at 5x9).
+//       The dx positions that share a view are adjacent column blocks, so they are ONE MMA of N = C * n_dx against a B
+//       matrix stacked [kx=2 | kx=1 | kx=0]: 135 MMAs per 128 GEMM rows.
 //
 // Numerics: 16-bit operands, fp32 accumulation, fp32 epilogue, 16-bit inter-layer activations.  The operand format is
 // fp16, not bf16: same tensor-core rate, 8x finer rounding (2^-12), and every value on this path is far inside fp16's
@@ -50,32 +61,26 @@ constexpr float kPixelScale = kBf16 ? 255.f : 255.f / 256.f;    // layer-1 input
 constexpr float kW1Scale = kBf16 ? 1.f / 255.f : 256.f / 255.f; // ... and its weights absorb the inverse
 constexpr float kActMax = kBf16 ? 3.0e38f : 65504.f;
 
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return kBf16 ? pack2(lo, hi) : pack_f16x2(lo, hi); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return kBf16 ? pack_bf16x2(lo, hi) : pack_f16x2(lo, hi); }
 
-constexpr int SUB_BATCH = 148;          // frames per pass through the conv stack: activations stay L2-resident
+constexpr int SUB_BATCH = 148;          // frames per pass through conv1/conv2: their activations stay L2-resident
+constexpr int GROUP = 4;                // sub-batches whose layer-2 maps are gathered for ONE conv3 launch (fills the SMs)
 constexpr int TMEM_COLS = 512;
 constexpr int MID_STAGES = 3;
+constexpr int MID_WIN = 192;            // positions per (plane, channel group) in a stage: 32 halo + 128 + 32 halo
+constexpr int MID_HALO = 32;
+constexpr int MID_STAGE_BYTES = 9 * 2 * MID_WIN * 16;            // nine planes x 16 channels
 constexpr int C1_STAGES = 4;
 constexpr int C1_A_STAGE_BYTES = 10 * 128 * 16;   // 5 input rows x 2 x (128 rows x 16 B)
+constexpr int EPI_WARPS = 8;
 
 // ------------------------------------------------------------------------------------------------ geometry
-struct TileCfg { int R, F, MT, n_rg; };
-
-TileCfg tile_cfg(int ph, int pw) {
-    TileCfg t;
-    if (ph * pw <= 64) { t.R = ph; t.F = 128 / (ph * pw); }
-    else { t.R = 128 / pw < ph ? 128 / pw : ph; t.F = 1; }
-    t.MT = t.R * t.F * pw;
-    t.n_rg = (ph + t.R - 1) / t.R;
-    return t;
-}
-
 struct Geom {
     int H, W, C, CG;
-    int P1h, P1w, P2h, P2w, P3h, P3w;
-    int Q1h, Q1w, Q2h, Q2w;
-    TileCfg t2, t3;
-    size_t xin_frame, act1_frame, act2_frame, act3_frame;   // bytes per frame
+    int P1h, P1w, P2h, P2w, P3h, P3w;   // pooled map sizes after layers 1, 2, 3
+    int Q1h, PW1, FP1;                  // phase-split layout of layer 1's output (conv2's input)
+    int Q2h, PW2, FP2;                  // ... of layer 2's output (conv3's input)
+    size_t xin_frame, act3_frame;       // bytes per frame
 };
 
 Geom make_geom(int H, int W, int C) {
@@ -84,93 +89,143 @@ Geom make_geom(int H, int W, int C) {
     g.P1h = H / 3; g.P1w = W / 3;
     g.P2h = g.P1h / 3; g.P2w = g.P1w / 3;
     g.P3h = g.P2h / 3; g.P3w = g.P2w / 3;
-    g.Q1h = (g.P1h + 2) / 3; g.Q1w = (g.P1w + 2) / 3;
-    g.Q2h = (g.P2h + 2) / 3; g.Q2w = (g.P2w + 2) / 3;
-    g.t2 = tile_cfg(g.P2h > 0 ? g.P2h : 1, g.P2w > 0 ? g.P2w : 1);
-    g.t3 = tile_cfg(g.P3h > 0 ? g.P3h : 1, g.P3w > 0 ? g.P3w : 1);
+    g.Q1h = g.P1h / 3 + 1; g.PW1 = g.P1w / 3 + 1; g.FP1 = g.Q1h * g.PW1;
+    g.Q2h = g.P2h / 3 + 1; g.PW2 = g.P2w / 3 + 1; g.FP2 = g.Q2h * g.PW2;
     g.xin_frame = (size_t)H * g.P1w * 32;
-    g.act1_frame = (size_t)9 * g.CG * g.Q1h * g.Q1w * 16;
-    g.act2_frame = (size_t)9 * g.CG * g.Q2h * g.Q2w * 16;
     g.act3_frame = (size_t)g.P3h * g.P3w * C * sizeof(float);
     return g;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// positions per (plane, channel group) of a phase-split buffer holding `frames` frames (TMA rows are 32 positions)
+int gtot_for(int frames, int FP) { return (int)align_up((size_t)frames * FP, 32); }
+size_t act_bytes(int CG, int gtot) { return (size_t)9 * CG * gtot * 16; }
+
 // ------------------------------------------------------------------------------------------------ epilogue
-// Shared by conv1 and conv2/3: this thread's TMEM lane holds 9 blocks of C fp32 columns (one per pool position).
-// max over the 9 blocks, + bias, ReLU, BatchNorm affine; 16 channels at a time.
-__device__ __forceinline__ void ld_fence(float (&v)[16]) {
-    // ties the registers to the preceding tcgen05.wait::ld so the compiler cannot hoist their uses above it
-    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
-                      "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]));
-}
-
-template <int C>
-__device__ __forceinline__ void pooled_block(uint32_t lane_base, int cb, const float *s_bias, const float *s_scale,
-                                             const float *s_shift, float (&out)[16]) {
-    float a[16], b[16], c[16];
-    tmem_ld16(lane_base + 0 * C + cb * 16, a);
-    tmem_ld16(lane_base + 1 * C + cb * 16, b);
-    tmem_ld16(lane_base + 2 * C + cb * 16, c);
-    tmem_ld_wait();
-    ld_fence(a); ld_fence(b); ld_fence(c);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) out[i] = fmaxf(fmaxf(a[i], b[i]), c[i]);
-#pragma unroll
-    for (int j = 3; j < 9; j += 3) {
-        tmem_ld16(lane_base + (j + 0) * C + cb * 16, a);
-        tmem_ld16(lane_base + (j + 1) * C + cb * 16, b);
-        tmem_ld16(lane_base + (j + 2) * C + cb * 16, c);
-        tmem_ld_wait();
-        ld_fence(a); ld_fence(b); ld_fence(c);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) out[i] = fmaxf(out[i], fmaxf(fmaxf(a[i], b[i]), c[i]));
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int ch = cb * 16 + i;
-        out[i] = fminf(fmaxf(fmaf(fmaxf(out[i] + s_bias[ch], 0.f), s_scale[ch], s_shift[ch]), -kActMax), kActMax);
-    }
-}
-
 // Where a pooled pixel goes.  mode 0: phase-split 16-bit (input layout of the next conv); mode 1: [frame][pixel][C] fp32.
 struct OutSpec {
     void *ptr;
     int mode;
-    int frames;        // frame capacity of the buffer (phase-split planes are [phase][frame])
-    int Qh, Qw;        // phase-plane size (mode 0)
+    int gtot;          // mode 0: positions per (plane, channel group)
+    int PW, FP, QH;    // mode 0: the next layer's row pitch, frame pitch, rows per frame
+    int frame0;        // first frame of this launch inside the buffer
     int out_h, out_w;  // pooled map size
 };
 
+template <int CH>
+__device__ __forceinline__ void reg_fence(float (&v)[CH]) {
+    // ties the registers to the preceding tcgen05.wait::ld so the compiler cannot hoist their uses above it
+#pragma unroll
+    for (int i = 0; i < CH; ++i) asm volatile("" : "+f"(v[i]));
+}
+
+template <int CH>
+__device__ __forceinline__ void tmem_ld_ch(uint32_t taddr, float (&v)[CH]) {
+    static_assert(CH == 16 || CH == 24, "channels per epilogue thread");
+    float a[16];
+    tmem_ld16(taddr, a);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = a[i];
+    if (CH == 24) {
+        float b[8];
+        tmem_ld8(taddr + 16, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[16 + i] = b[i];
+    }
+}
+
+// One tile's epilogue for this thread: its TMEM lane (a pooled pixel), CH = C/2 of the channels.  Block row dy of the
+// accumulator (columns [3C*dy, 3C*dy + 3C) = the three dx positions) is read as soon as its MMAs have committed and is
+// handed back right after the read.  Returns max over the 9 positions, + bias, ReLU, BatchNorm affine, clamped.
 template <int C>
-__device__ __forceinline__ void store_pixel(const OutSpec &o, int b, int Y, int X, int cb, const float (&v)[16]) {
-    constexpr int CG = C / 8;
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_thread /* lane quarter + this thread's first column */,
+                                              uint64_t *acc_full, uint64_t *acc_empty, uint32_t acc_phase, int lane,
+                                              const float *s_par /* [3][C]: bias, scale, shift */, int ch0,
+                                              float (&run)[C / 2]) {
+    constexpr int CH = C / 2;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        mbar_wait(&acc_full[dy], acc_phase);
+        tc_fence_after_sync();
+        float a[CH], b[CH], c[CH];
+        tmem_ld_ch<CH>(tmem_thread + (3 * dy + 0) * C, a);
+        tmem_ld_ch<CH>(tmem_thread + (3 * dy + 1) * C, b);
+        tmem_ld_ch<CH>(tmem_thread + (3 * dy + 2) * C, c);
+        tmem_ld_wait();
+        reg_fence<CH>(a); reg_fence<CH>(b); reg_fence<CH>(c);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[dy]);           // block row dy may be overwritten by the next tile
+        if (dy == 0) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(a[i], b[i]), c[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(fmaxf(run[i], a[i]), b[i]), c[i]);
+        }
+    }
+    const float4 *bias4 = reinterpret_cast<const float4 *>(s_par + ch0);
+    const float4 *scale4 = reinterpret_cast<const float4 *>(s_par + C + ch0);
+    const float4 *shift4 = reinterpret_cast<const float4 *>(s_par + 2 * C + ch0);
+#pragma unroll
+    for (int i = 0; i < CH / 4; ++i) {
+        const float4 b = bias4[i], s = scale4[i], t = shift4[i];
+        run[4 * i + 0] = fminf(fmaxf(fmaf(fmaxf(run[4 * i + 0] + b.x, 0.f), s.x, t.x), -kActMax), kActMax);
+        run[4 * i + 1] = fminf(fmaxf(fmaf(fmaxf(run[4 * i + 1] + b.y, 0.f), s.y, t.y), -kActMax), kActMax);
+        run[4 * i + 2] = fminf(fmaxf(fmaf(fmaxf(run[4 * i + 2] + b.z, 0.f), s.z, t.z), -kActMax), kActMax);
+        run[4 * i + 3] = fminf(fmaxf(fmaf(fmaxf(run[4 * i + 3] + b.w, 0.f), s.w, t.w), -kActMax), kActMax);
+    }
+}
+
+// b = frame inside this launch, (Y, X) = pooled pixel, ch0 = this thread's first channel (a multiple of 8).
+template <int C>
+__device__ __forceinline__ void store_pixel(const OutSpec &o, int b, int Y, int X, int ch0, const float (&v)[C / 2]) {
+    constexpr int CG = C / 8, CH = C / 2;
     if (o.mode == 0) {
-        const int plane = ((Y % 3) * 3 + (X % 3)) * o.frames + b;
-        uint4 *dst = reinterpret_cast<uint4 *>(o.ptr);
-        const size_t base = (((size_t)plane * CG + cb * 2) * o.Qh + Y / 3) * o.Qw + X / 3;
-        uint4 lo, hi;
-        lo.x = pack2(v[0], v[1]); lo.y = pack2(v[2], v[3]); lo.z = pack2(v[4], v[5]); lo.w = pack2(v[6], v[7]);
-        hi.x = pack2(v[8], v[9]); hi.y = pack2(v[10], v[11]); hi.z = pack2(v[12], v[13]); hi.w = pack2(v[14], v[15]);
-        dst[base] = lo;
-        dst[base + (size_t)o.Qh * o.Qw] = hi;
+        const int plane = (Y % 3) * 3 + (X % 3);
+        uint4 *dst = reinterpret_cast<uint4 *>(o.ptr) +
+                     ((size_t)(plane * CG + ch0 / 8) * o.gtot + (size_t)(o.frame0 + b) * o.FP + (Y / 3) * o.PW + X / 3);
+#pragma unroll
+        for (int j = 0; j < CH / 8; ++j) {
+            uint4 q;
+            q.x = pack2(v[8 * j + 0], v[8 * j + 1]); q.y = pack2(v[8 * j + 2], v[8 * j + 3]);
+            q.z = pack2(v[8 * j + 4], v[8 * j + 5]); q.w = pack2(v[8 * j + 6], v[8 * j + 7]);
+            dst[(size_t)j * o.gtot] = q;
+        }
     } else {
         float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(o.ptr) +
-                                                 ((size_t)b * o.out_h * o.out_w + (size_t)Y * o.out_w + X) * C + cb * 16);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        dst[2] = make_float4(v[8], v[9], v[10], v[11]);
-        dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+                                                 ((size_t)(o.frame0 + b) * o.out_h * o.out_w + (size_t)Y * o.out_w + X) * C + ch0);
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+}
+
+// Zero the entries of frames [f_lo, f_hi) of a phase-split buffer that are not real pixels (the last row and/or the
+// last column of each plane): they are the zero padding the next conv's shifted views read.
+__device__ __forceinline__ void zero_pads(const OutSpec &o, int CG, int f_lo, int f_hi, int tid, int nthreads) {
+    if (o.mode != 0) return;
+    const int span = o.PW + o.QH, per_frame = 9 * CG * span;
+    const long long total = (long long)(f_hi - f_lo) * per_frame;
+    uint4 *dst = reinterpret_cast<uint4 *>(o.ptr);
+    for (long long i = tid; i < total; i += nthreads) {
+        const int f = f_lo + (int)(i / per_frame), r = (int)(i % per_frame);
+        const int e = r % span, pc = r / span, plane = pc / CG;
+        const int py = plane / 3, px = plane % 3;
+        int Yq, Xq;
+        bool pad;
+        if (e < o.PW) { Yq = o.QH - 1; Xq = e; pad = 3 * Yq + py >= o.out_h; }
+        else { Yq = e - o.PW; Xq = o.PW - 1; pad = 3 * Xq + px >= o.out_w; }
+        if (pad) dst[(size_t)pc * o.gtot + (size_t)(o.frame0 + f) * o.FP + Yq * o.PW + Xq] = make_uint4(0, 0, 0, 0);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ conv2 / conv3
 struct MidParams {
-    int B;                  // frames in this pass
+    int n_frames;           // frames in this launch
+    int FP, PW;             // layout of the INPUT (= GEMM row numbering): frame pitch, row pitch
     int out_h, out_w;       // pooled output size
-    int R, F, MT, n_rg;     // tile: R pooled rows x F frames (MT = R*F*out_w valid GEMM rows of 128)
-    int n_tiles;
+    int n_tiles;            // ceil(n_frames * FP / 128)
     OutSpec out;
     const uint4 *w_packed;  // [ky][c/8][3C rows: kx=2 | kx=1 | kx=0][8] 16-bit
     const float *bias, *scale, *shift;
@@ -182,149 +237,138 @@ struct MidSmem {
     static constexpr int W_BYTES = 3 * CG * 3 * C * 16;
     static constexpr int W_KY_BYTES = CG * 3 * C * 16;
     static constexpr int LBO_B = 3 * C * 16;
-    __host__ __device__ static int view_stride(int MT) { return (CG * MT * 16 + 127) / 128 * 128; }
-    __host__ __device__ static int stage_bytes(int MT) { return 5 * view_stride(MT); }
-    __host__ __device__ static int total(int MT) {
-        return W_BYTES + MID_STAGES * stage_bytes(MT) + 2048 /* slack for the M=128 over-read */ + 256 /* barriers */ + 3 * C * 4;
-    }
+    static constexpr int total = W_BYTES + MID_STAGES * MID_STAGE_BYTES + 256 /* barriers */ + 3 * C * 4;
 };
 
-// 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 4..7 = epilogue (TMEM lane quarter
-// = warp - 4).  Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...
+// 320 threads: warps 0..7 = epilogue (TMEM lane quarter = warp % 4, channel half = warp / 4), warp 8 = TMA producer,
+// warp 9 = MMA issuer (+ TMEM alloc).  Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...
 template <int C>
-__global__ void __launch_bounds__(256, 1) conv_mid_tc_kernel(const __grid_constant__ CUtensorMap in_map, const MidParams p) {
+__global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_constant__ CUtensorMap in_map, const MidParams p) {
     using S = MidSmem<C>;
-    constexpr int CG = C / 8;
+    constexpr int CG = C / 8, KS = C / 16, CH = C / 2;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int view_stride = S::view_stride(p.MT), stage_bytes = 5 * view_stride;
     uint8_t *s_w = smem;
     uint8_t *s_stage = smem + S::W_BYTES;
-    uint8_t *s_tail = s_stage + MID_STAGES * stage_bytes + 2048;
+    uint8_t *s_tail = s_stage + MID_STAGES * MID_STAGE_BYTES;
     uint64_t *full = reinterpret_cast<uint64_t *>(s_tail);
     uint64_t *empty = full + MID_STAGES;
-    uint64_t *tmem_full = empty + MID_STAGES;
-    uint64_t *tmem_empty = tmem_full + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
-    float *s_bias = reinterpret_cast<float *>(s_tail + 256);
-    float *s_scale = s_bias + C, *s_shift = s_scale + C;
+    uint64_t *acc_full = empty + MID_STAGES;
+    uint64_t *acc_empty = acc_full + 3;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 3);
+    float *s_par = reinterpret_cast<float *>(s_tail + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // one-time setup
     for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_bias[i] = p.bias[i]; s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = p.bias[i]; s_par[C + i] = p.scale[i]; s_par[2 * C + i] = p.shift[i]; }
     fence_proxy_async();             // the weights were written through the generic proxy; the MMA reads via the async proxy
     if (threadIdx.x == 0) {
         for (int s = 0; s < MID_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], EPI_WARPS); }
         fence_barrier_init();
         tma_prefetch_desc(&in_map);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 8) {
         // ------------------------------------------------------------------ TMA producer (lane 0 issues)
         uint32_t stage = 0, phase = 0;
-        const uint32_t tx_bytes = 5u * (uint32_t)(CG * p.MT * 16);
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int b0 = (tile / p.n_rg) * p.F, Y0 = (tile % p.n_rg) * p.R;
-            for (int oy = -1; oy <= 3; ++oy) {
+            for (int ks = 0; ks < KS; ++ks) {
                 mbar_wait(&empty[stage], phase ^ 1);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full[stage], tx_bytes);
-                    const int py = (oy + 3) % 3, sy = oy < 0 ? -1 : (oy > 2 ? 1 : 0);
-                    uint8_t *dst = s_stage + stage * stage_bytes;
-                    for (int oxi = 0; oxi < 5; ++oxi) {
-                        const int ox = oxi - 1;
-                        const int px = (ox + 3) % 3, sx = ox < 0 ? -1 : (ox > 2 ? 1 : 0);
-                        tma_load_5d(dst + oxi * view_stride, &in_map, &full[stage], sx * 8, Y0 + sy, b0, 0, py * 3 + px);
-                    }
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full[stage], MID_STAGE_BYTES);
+                    uint8_t *dst = s_stage + stage * MID_STAGE_BYTES;
+                    for (int pl = 0; pl < 9; ++pl)
+                        tma_load_4d(dst + pl * (2 * MID_WIN * 16), &in_map, &full[stage], 0, 4 * tile - 1, 2 * ks, pl);
                 }
                 __syncwarp();
                 if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 9) {
         // ------------------------------------------------------------------ MMA issuer
         uint32_t stage = 0, phase = 0, acc_phase = 0;
-        const uint32_t lbo_a = (uint32_t)p.MT * 16;
         const uint32_t w_addr = smem_u32(s_w), stage_addr = smem_u32(s_stage);
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            mbar_wait(tmem_empty, acc_phase ^ 1);          // the epilogue has drained the previous tile
-            tc_fence_after_sync();
-            for (int oy = -1; oy <= 3; ++oy) {
+            for (int ks = 0; ks < KS; ++ks) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after_sync();
-                const uint32_t a_stage = stage_addr + stage * stage_bytes;
-                for (int dy = 0; dy < 3 && lane == 0; ++dy) {
-                    const int ky = oy + 1 - dy;
-                    if (ky < 0 || ky > 2) continue;
+                const uint32_t a_stage = stage_addr + stage * MID_STAGE_BYTES;
 #pragma unroll
-                    for (int o = 0; o < 5; ++o) {
-                        const int ox = (o == 0) ? 1 : (o == 1) ? 0 : (o == 2) ? 2 : (o == 3) ? -1 : 3;   // centre first
-                        const int dx_lo = ox - 1 < 0 ? 0 : ox - 1, dx_hi = ox + 1 > 2 ? 2 : ox + 1;
-                        const int n_dx = dx_hi - dx_lo + 1, kx_start = ox + 1 - dx_lo;
-                        const uint32_t idesc = instr_desc_16bit(128, C * n_dx, kBf16);
-                        const uint32_t a_view = a_stage + (ox + 1) * view_stride;
-                        const uint32_t b_tap = w_addr + ky * S::W_KY_BYTES + (2 - kx_start) * C * 16;
-                        const uint32_t d_col = tmem_base + C * (dy * 3 + dx_lo);
-#pragma unroll
-                        for (int ks = 0; ks < C / 16; ++ks) {
-                            const uint64_t da = smem_desc(a_view + 2 * ks * lbo_a, lbo_a, 128);
-                            const uint64_t db = smem_desc(b_tap + 2 * ks * S::LBO_B, S::LBO_B, 128);
-                            umma_16bit(d_col, da, db, idesc, (ky == 0 && ox == 1 && ks == 0) ? 0u : 1u);
-                        }
+                for (int dy = 0; dy < 3; ++dy) {
+                    if (ks == 0) {                          // first touch of block row dy in this tile: the epilogue must be done with it
+                        mbar_wait(&acc_empty[dy], acc_phase ^ 1);
+                        tc_fence_after_sync();
                     }
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int oy = dy + ky - 1;
+                            const int py = (oy + 3) % 3, sy = oy < 0 ? -1 : (oy > 2 ? 1 : 0);
+#pragma unroll
+                            for (int o = 0; o < 5; ++o) {
+                                const int ox = (o == 0) ? 1 : (o == 1) ? 0 : (o == 2) ? 2 : (o == 3) ? -1 : 3;   // centre first
+                                const int px = (ox + 3) % 3, sx = ox < 0 ? -1 : (ox > 2 ? 1 : 0);
+                                const int dx_lo = ox - 1 < 0 ? 0 : ox - 1, dx_hi = ox + 1 > 2 ? 2 : ox + 1;
+                                const int n_dx = dx_hi - dx_lo + 1, kx_start = ox + 1 - dx_lo;
+                                const uint32_t idesc = instr_desc_16bit(128, C * n_dx, kBf16);
+                                const uint32_t a_view = a_stage + (py * 3 + px) * (2 * MID_WIN * 16) +
+                                                        (uint32_t)(MID_HALO + sy * p.PW + sx) * 16;
+                                const uint32_t b_tap = w_addr + ky * S::W_KY_BYTES + 2 * ks * S::LBO_B + (2 - kx_start) * C * 16;
+                                const uint64_t da = smem_desc(a_view, MID_WIN * 16, 128);
+                                const uint64_t db = smem_desc(b_tap, S::LBO_B, 128);
+                                umma_16bit(tmem_base + C * (dy * 3 + dx_lo), da, db, idesc, (ks == 0 && ky == 0 && ox == 1) ? 0u : 1u);
+                            }
+                        }
+                        if (ks == KS - 1) umma_commit(&acc_full[dy]);
+                    }
+                    __syncwarp();
                 }
-                if (lane == 0) umma_commit(&empty[stage]);  // frees the stage once these MMAs have read it
+                if (elect_one()) umma_commit(&empty[stage]);  // frees the stage once these MMAs have read it
                 __syncwarp();
                 if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
             }
-            if (lane == 0) umma_commit(tmem_full);
-            __syncwarp();
             acc_phase ^= 1;
         }
-    } else if (warp >= 4) {
+    } else {
         // ------------------------------------------------------------------ epilogue
-        const int q = warp - 4, m = q * 32 + lane;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        // pads of the output buffer first (they belong to no GEMM row)
+        {
+            const int per = (p.n_frames + gridDim.x - 1) / gridDim.x;
+            const int f_lo = min(p.n_frames, (int)blockIdx.x * per), f_hi = min(p.n_frames, f_lo + per);
+            zero_pads(p.out, CG, f_lo, f_hi, threadIdx.x, EPI_WARPS * 32);
+        }
+        const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
+        const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + ch0;
         uint32_t acc_phase = 0;
-        const int per_frame = p.R * p.out_w;
+        const long long n_rows = (long long)p.n_frames * p.FP;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int b0 = (tile / p.n_rg) * p.F, Y0 = (tile % p.n_rg) * p.R;
-            const int f = m / per_frame, rem = m % per_frame;
-            const int b = b0 + f, Y = Y0 + rem / p.out_w, X = rem % p.out_w;
-            const bool valid = m < p.MT && b < p.B && Y < p.out_h;
-            mbar_wait(tmem_full, acc_phase);
-            tc_fence_after_sync();
-#pragma unroll 1
-            for (int cb = 0; cb < C / 16; ++cb) {
-                float v[16];
-                pooled_block<C>(lane_base, cb, s_bias, s_scale, s_shift, v);
-                if (valid) store_pixel<C>(p.out, b, Y, X, cb, v);
-            }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
+            const long long g = (long long)tile * 128 + m;
+            const int b = (int)(g / p.FP), pos = (int)(g % p.FP);
+            const int Y = pos / p.PW, X = pos % p.PW;
+            const bool valid = g < n_rows && Y < p.out_h && X < p.out_w;
+            float v[CH];
+            epilogue_tile<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, s_par, ch0, v);
+            if (valid) store_pixel<C>(p.out, b, Y, X, ch0, v);
             acc_phase ^= 1;
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ conv1
 struct Conv1Params {
-    const uint4 *xin;       // [B][H][P1w][2 x 16 B]: x-unfolded input, 0..255 scale
+    const uint4 *xin;       // [B][H][P1w][2 x 16 B]: x-unfolded input, v/256 scale
     int B, H, P1h, P1w;
-    long long n_pooled;     // B * P1h * P1w
-    int n_tiles;
+    int tiles_per_frame;    // ceil(P1h * P1w / 128)
     OutSpec out;
     const uint4 *w_packed;  // [ky][half][3C rows: dx=0 | dx=1 | dx=2][8] 16-bit, taps scaled by kW1Scale
     const float *bias, *scale, *shift;
@@ -337,120 +381,386 @@ struct C1Smem {
     static constexpr int total = W_BYTES + C1_STAGES * C1_A_STAGE_BYTES + 256 + 3 * C * 4;
 };
 
-// 288 threads: warps 0..3 = cp.async gather producers (thread t builds GEMM row t), warps 4..7 = epilogue,
-// warp 8 = MMA issuer (+ TMEM alloc).
+// 416 threads: warps 0..7 = epilogue, warps 8..11 = cp.async gather producers (thread t builds GEMM row t), warp 12 =
+// MMA issuer (+ TMEM alloc).  CTA b walks frames b, b + gridDim.x, ...; a tile is 128 consecutive pooled pixels of a frame.
 template <int C>
-__global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
+__global__ void __launch_bounds__(416, 1) conv1_tc_kernel(const Conv1Params p) {
     using S = C1Smem<C>;
+    constexpr int CG = C / 8, CH = C / 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *s_w = smem;
     uint8_t *s_stage = smem + S::W_BYTES;
     uint8_t *s_tail = s_stage + C1_STAGES * C1_A_STAGE_BYTES;
     uint64_t *full = reinterpret_cast<uint64_t *>(s_tail);
     uint64_t *empty = full + C1_STAGES;
-    uint64_t *tmem_full = empty + C1_STAGES;
-    uint64_t *tmem_empty = tmem_full + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
-    float *s_bias = reinterpret_cast<float *>(s_tail + 256);
-    float *s_scale = s_bias + C, *s_shift = s_scale + C;
+    uint64_t *acc_full = empty + C1_STAGES;
+    uint64_t *acc_empty = acc_full + 3;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 3);
+    float *s_par = reinterpret_cast<float *>(s_tail + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_bias[i] = p.bias[i]; s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = p.bias[i]; s_par[C + i] = p.scale[i]; s_par[2 * C + i] = p.shift[i]; }
     fence_proxy_async();
     if (threadIdx.x == 0) {
         for (int s = 0; s < C1_STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 12) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    const int per_frame = p.P1h * p.P1w;
 
-    if (warp < 4) {
+    if (warp >= 8 && warp < 12) {
         // ------------------------------------------------------------------ gather producers
-        const int m = threadIdx.x;
+        const int m = threadIdx.x - 256;
         uint32_t stage = 0, phase = 0;
-        const int per_frame = p.P1h * p.P1w;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const long long pix = (long long)tile * 128 + m;
-            const bool in_range = pix < p.n_pooled;
-            const int b = in_range ? (int)(pix / per_frame) : 0;
-            const int rem = in_range ? (int)(pix % per_frame) : 0;
-            const int py = rem / p.P1w, px = rem % p.P1w;
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t *dst = s_stage + stage * C1_A_STAGE_BYTES + m * 16;
+        for (int f = blockIdx.x; f < p.B; f += gridDim.x) {
+            for (int t = 0; t < p.tiles_per_frame; ++t) {
+                const int pix = t * 128 + m;
+                const bool in_range = pix < per_frame;
+                const int py = in_range ? pix / p.P1w : 0, px = in_range ? pix % p.P1w : 0;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t *dst = s_stage + stage * C1_A_STAGE_BYTES + m * 16;
 #pragma unroll
-            for (int r = 0; r < 5; ++r) {
-                const int row = 3 * py - 1 + r;
-                const bool ok = in_range && row >= 0 && row < p.H;
-                const uint4 *src = p.xin + (ok ? (((size_t)b * p.H + row) * p.P1w + px) * 2 : 0);
-                cp_async_16(dst + (2 * r) * 2048, src, ok ? 16u : 0u);
-                cp_async_16(dst + (2 * r + 1) * 2048, src + 1, ok ? 16u : 0u);
+                for (int r = 0; r < 5; ++r) {
+                    const int row = 3 * py - 1 + r;
+                    const bool ok = in_range && row >= 0 && row < p.H;
+                    const uint4 *src = p.xin + (ok ? (((size_t)f * p.H + row) * p.P1w + px) * 2 : 0);
+                    cp_async_16(dst + (2 * r) * 2048, src, ok ? 16u : 0u);
+                    cp_async_16(dst + (2 * r + 1) * 2048, src + 1, ok ? 16u : 0u);
+                }
+                cp_async_arrive_noinc(&full[stage]);
+                if (++stage == C1_STAGES) { stage = 0; phase ^= 1; }
             }
-            cp_async_arrive_noinc(&full[stage]);
-            if (++stage == C1_STAGES) { stage = 0; phase ^= 1; }
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // ------------------------------------------------------------------ MMA issuer (lane 0 issues)
         uint32_t stage = 0, phase = 0, acc_phase = 0;
         const uint32_t w_addr = smem_u32(s_w), stage_addr = smem_u32(s_stage);
         const uint32_t idesc = instr_desc_16bit(128, 3 * C, kBf16);
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            mbar_wait(tmem_empty, acc_phase ^ 1);
-            mbar_wait(&full[stage], phase);
-            fence_proxy_async();
-            tc_fence_after_sync();
-            const uint32_t a_stage = stage_addr + stage * C1_A_STAGE_BYTES;
-            if (lane == 0) {
+        for (int f = blockIdx.x; f < p.B; f += gridDim.x) {
+            for (int t = 0; t < p.tiles_per_frame; ++t) {
+                mbar_wait(&full[stage], phase);
+                fence_proxy_async();
+                tc_fence_after_sync();
+                const uint32_t a_stage = stage_addr + stage * C1_A_STAGE_BYTES;
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
+                for (int dy = 0; dy < 3; ++dy) {
+                    mbar_wait(&acc_empty[dy], acc_phase ^ 1);
+                    tc_fence_after_sync();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) {
-                        const uint64_t da = smem_desc(a_stage + 2 * (dy + ks) * 2048, 2048, 128);
-                        const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
-                        umma_16bit(tmem_base + 3 * C * dy, da, db, idesc, ks > 0 ? 1u : 0u);
+                        for (int ks = 0; ks < 3; ++ks) {
+                            const uint64_t da = smem_desc(a_stage + 2 * (dy + ks) * 2048, 2048, 128);
+                            const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
+                            umma_16bit(tmem_base + 3 * C * dy, da, db, idesc, ks > 0 ? 1u : 0u);
+                        }
+                        umma_commit(&acc_full[dy]);
                     }
-                umma_commit(&empty[stage]);
-                umma_commit(tmem_full);
+                    __syncwarp();
+                }
+                if (elect_one()) umma_commit(&empty[stage]);
+                __syncwarp();
+                if (++stage == C1_STAGES) { stage = 0; phase ^= 1; }
+                acc_phase ^= 1;
             }
-            __syncwarp();
-            if (++stage == C1_STAGES) { stage = 0; phase ^= 1; }
-            acc_phase ^= 1;
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else {
         // ------------------------------------------------------------------ epilogue
-        const int q = warp - 4, m = q * 32 + lane;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
+        const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + ch0;
         uint32_t acc_phase = 0;
-        const int per_frame = p.P1h * p.P1w;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const long long pix = (long long)tile * 128 + m;
-            const bool valid = pix < p.n_pooled;
-            const int b = valid ? (int)(pix / per_frame) : 0;
-            const int rem = valid ? (int)(pix % per_frame) : 0;
-            const int Y = rem / p.P1w, X = rem % p.P1w;
-            mbar_wait(tmem_full, acc_phase);
-            tc_fence_after_sync();
-#pragma unroll 1
-            for (int cb = 0; cb < C / 16; ++cb) {
-                float v[16];
-                pooled_block<C>(lane_base, cb, s_bias, s_scale, s_shift, v);
-                if (valid) store_pixel<C>(p.out, b, Y, X, cb, v);
+        for (int f = blockIdx.x; f < p.B; f += gridDim.x) {
+            zero_pads(p.out, CG, f, f + 1, threadIdx.x, EPI_WARPS * 32);
+            for (int t = 0; t < p.tiles_per_frame; ++t) {
+                const int pix = t * 128 + m;
+                const bool valid = pix < per_frame;
+                const int Y = valid ? pix / p.P1w : 0, X = valid ? pix % p.P1w : 0;
+                float v[CH];
+                epilogue_tile<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, s_par, ch0, v);
+                if (valid) store_pixel<C>(p.out, f, Y, X, ch0, v);
+                acc_phase ^= 1;
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
-            acc_phase ^= 1;
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 12) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ K1 fused into conv1
+// The same tile loop, MMA issue and epilogue as conv1_tc_kernel, but the A operand is built from the DECODED FRAMES:
+// the x-unfolded input never goes to memory.  Per CTA (= one frame at a time), warps 8..11:
+//   raw ring      the source rows each resized row needs (1 for an integer-scale gather such as 720p -> 256x144, else 2)
+//                 arrive by cp.async.bulk, one mbarrier per slot, RAW_BYTES (90 KB) in flight per SM -- with 148 SMs
+//                 that covers HBM latency x bandwidth, so the frame read streams at HBM speed;
+//   stage 1       resized rows, bit-exact with cv2.resize(INTER_LINEAR), as uint8 (B, G, R, 0x64) words in a 32-row ring;
+//   stage 2       thread m builds GEMM row m: 5 rows x 5 pixels from the ring, u8 -> fp16 v/256 through the
+//                 0x6400|v trick ((1024 + v) / 256 - 4, one PRMT + one HFMA2 per pair), 16-byte stores into the A stage.
+constexpr int F_STAGES = 3;
+constexpr int RING_ROWS = 32, RING_PITCH = 264;          // words per ring row: [4 pad][256 pixels][4 pad]
+constexpr int RAW_BYTES = 92160;                         // 24 rows of 1280 x 3, or 8 row pairs of 1920 x 3
+constexpr int RAW_SLOTS_MAX = 24;
+constexpr int F_MAX_DST = 256;
+constexpr uint32_t ZERO_PIXEL = 0x64000000u;
+
+struct FusedSrc {
+    ResizePlanDev plan;
+    const uint8_t *frames;
+    long long frame_stride, row_pitch;
+    int compact;
+    int n_src;        // raw rows per resized row
+    int row_bytes;    // 3 * src_w, a multiple of 16
+    int n_slots;      // raw ring slots of n_src * row_bytes each
+};
+
+template <int C>
+struct F1Smem {
+    static constexpr int W_BYTES = 6 * 3 * C * 16;
+    static constexpr int LBO_B = 3 * C * 16;
+    static constexpr int OFF_STAGE = W_BYTES;
+    static constexpr int OFF_RING = OFF_STAGE + F_STAGES * C1_A_STAGE_BYTES;
+    static constexpr int OFF_RAW = OFF_RING + RING_ROWS * RING_PITCH * 4;
+    static constexpr int OFF_TAB = OFF_RAW + RAW_BYTES + 64;           // 64 bytes of slack: the gather reads one word past a row
+    static constexpr int OFF_BAR = OFF_TAB + F_MAX_DST * (8 + 8 + 16);  // rowoff[256][2], yb[256][2], xtab[256] (int4)
+    static constexpr int OFF_PAR = OFF_BAR + 512;
+    static constexpr int total = OFF_PAR + 3 * C * 4;
+};
+
+__device__ __forceinline__ uint32_t u8x2_to_h2(uint32_t magic_pair) {
+    // magic_pair = two fp16 values 1024 + v (bit pattern 0x6400 | v): (1024 + v) * 2^-8 - 4 = v / 256, exact
+    const __half2 k = __floats2half2_rn(1.f / 256.f, 1.f / 256.f), m4 = __floats2half2_rn(-4.f, -4.f);
+    __half2 h = *reinterpret_cast<__half2 *>(&magic_pair);
+    h = __hfma2(h, k, m4);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <int C>
+__global__ void __launch_bounds__(416, 1) conv1_fused_tc_kernel(const Conv1Params p, const FusedSrc src) {
+    using S = F1Smem<C>;
+    constexpr int CG = C / 8, CH = C / 2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *s_w = smem;
+    uint8_t *s_stage = smem + S::OFF_STAGE;
+    uint32_t *s_ring = reinterpret_cast<uint32_t *>(smem + S::OFF_RING);
+    uint8_t *s_raw = smem + S::OFF_RAW;
+    int *s_rowoff = reinterpret_cast<int *>(smem + S::OFF_TAB);               // [y][2]
+    int *s_yb = s_rowoff + 2 * F_MAX_DST;                                       // [y][2]: b0, b1
+    int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);              // [x]: 3*x0, 3*x1, a0, a1
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);
+    uint64_t *empty = full + F_STAGES;
+    uint64_t *acc_full = empty + F_STAGES;
+    uint64_t *acc_empty = acc_full + 3;
+    uint64_t *raw_full = acc_empty + 3;                                         // [RAW_SLOTS_MAX]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_full + RAW_SLOTS_MAX);
+    float *s_par = reinterpret_cast<float *>(smem + S::OFF_PAR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ResizePlanDev &plan = src.plan;
+    const int H = p.H, W = plan.dst_w;
+
+    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = p.bias[i]; s_par[C + i] = p.scale[i]; s_par[2 * C + i] = p.shift[i]; }
+    for (int i = threadIdx.x; i < RING_ROWS * RING_PITCH; i += blockDim.x) s_ring[i] = ZERO_PIXEL;
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        int r0, r1, b0 = 2048, b1 = 0;
+        if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
+        else if (plan.mode == RESIZE_COPY) { r0 = r1 = y; }
+        else if (plan.mode == RESIZE_AREA2) { r0 = 2 * y; r1 = 2 * y + 1; }
+        else { r0 = plan.y0[y]; r1 = plan.y1[y]; b0 = plan.b0[y]; b1 = plan.b1[y]; }
+        if (src.compact) { r0 = plan.row_slot[r0]; r1 = (plan.mode == RESIZE_LINEAR && b1 == 0) ? r0 : plan.row_slot[r1]; }
+        s_rowoff[2 * y] = (int)(r0 * src.row_pitch);
+        s_rowoff[2 * y + 1] = (int)(r1 * src.row_pitch);
+        s_yb[2 * y] = b0;
+        s_yb[2 * y + 1] = b1;
+    }
+    if (plan.mode == RESIZE_LINEAR && plan.gather_step_x == 0)
+        for (int x = threadIdx.x; x < W; x += blockDim.x) s_xtab[x] = make_int4(3 * plan.x0[x], 3 * plan.x1[x], plan.a0[x], plan.a1[x]);
+    fence_proxy_async();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F_STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], EPI_WARPS); }
+        for (int s = 0; s < RAW_SLOTS_MAX; ++s) mbar_init(&raw_full[s], 1);
+        fence_barrier_init();
+    }
+    if (warp == 12) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int per_frame = p.P1h * p.P1w;
+
+    if (warp >= 8 && warp < 12) {
+        // ------------------------------------------------------------------ producers: raw rows -> resized ring -> A operand
+        const int m = threadIdx.x - 256, pwarp = warp - 8;
+        const int n_frames_cta = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const long long total_rows = (long long)n_frames_cta * H;
+        const int slot_bytes = src.n_src * src.row_bytes;
+        long long issued = 0;                      // rows whose raw loads have been issued (meaningful in pwarp 0 only)
+        auto issue_until = [&](long long limit) {  // whole warp 8, converged
+            if (limit > total_rows) limit = total_rows;
+            while (issued < limit) {
+                const int fi = (int)(issued / H), y = (int)(issued % H), slot = (int)(issued % src.n_slots);
+                if (elect_one()) {
+                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
+                    mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
+                    for (int j = 0; j < src.n_src; ++j)
+                        bulk_load_1d(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * y + j], (uint32_t)src.row_bytes,
+                                     &raw_full[slot]);
+                }
+                __syncwarp();
+                ++issued;
+            }
+        };
+        if (pwarp == 0) issue_until(src.n_slots);
+        uint32_t stage = 0, phase = 0;
+        int fi = 0;
+        for (int f = blockIdx.x; f < p.B; f += gridDim.x, ++fi) {
+            int next_row = 0;
+            const long long g0 = (long long)fi * H;
+            for (int t = 0; t < p.tiles_per_frame; ++t) {
+                // ---- stage 1: resized rows up to the last one this tile reads
+                const int last_pix = min(t * 128 + 127, per_frame - 1);
+                const int y_hi = min(H - 1, 3 * (last_pix / p.P1w) + 3);
+                const int n_items = 2 * (y_hi - next_row + 1);
+                for (int item = pwarp; item < n_items; item += 4) {
+                    const int y = next_row + (item >> 1), half = item & 1;
+                    const long long g = g0 + y;
+                    const int slot = (int)(g % src.n_slots);
+                    mbar_wait(&raw_full[slot], (uint32_t)((g / src.n_slots) & 1));
+                    const uint8_t *q0 = s_raw + slot * slot_bytes, *q1 = q0 + (src.n_src - 1) * src.row_bytes;
+                    uint32_t *ring_row = s_ring + (int)(g & (RING_ROWS - 1)) * RING_PITCH + 4;
+                    if (plan.gather_step_x > 0 && (W & 3) == 0) {
+                        const int x0 = 128 * half + 4 * lane;
+                        if (x0 < W) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int b = 3 * (plan.gather_off_x + (x0 + j) * plan.gather_step_x);
+                                const uint32_t *wp = reinterpret_cast<const uint32_t *>(q0 + (b & ~3));
+                                o[j] = (__funnelshift_r(wp[0], wp[1], (b & 3) * 8) & 0x00FFFFFFu) | ZERO_PIXEL;
+                            }
+                            *reinterpret_cast<uint4 *>(ring_row + x0) = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int x = 128 * half + 32 * j + lane;
+                            if (x >= W) continue;
+                            int v[3];
+                            if (plan.gather_step_x > 0) {
+                                const uint8_t *q = q0 + 3 * (plan.gather_off_x + x * plan.gather_step_x);
+                                v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
+                            } else if (plan.mode == RESIZE_COPY) {
+                                v[0] = q0[3 * x]; v[1] = q0[3 * x + 1]; v[2] = q0[3 * x + 2];
+                            } else if (plan.mode == RESIZE_AREA2) {
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) v[c] = (q0[6 * x + c] + q0[6 * x + 3 + c] + q1[6 * x + c] + q1[6 * x + 3 + c] + 2) >> 2;
+                            } else {
+                                const int4 xt = s_xtab[x];
+                                const int b0 = s_yb[2 * y], b1 = s_yb[2 * y + 1];
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) {
+                                    const int s0 = xt.z * q0[xt.x + c] + xt.w * q0[xt.y + c];
+                                    const int s1 = xt.z * q1[xt.x + c] + xt.w * q1[xt.y + c];
+                                    v[c] = min(max((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2, 0), 255);
+                                }
+                            }
+                            ring_row[x] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ZERO_PIXEL;
+                        }
+                    }
+                }
+                next_row = y_hi + 1;
+                bar_sync_named(3, 128);                 // the ring rows are visible; the raw slots of rows < next_row are free
+                if (pwarp == 0) issue_until(g0 + next_row + src.n_slots);
+
+                // ---- stage 2: GEMM row m of this tile
+                const int pix = t * 128 + m;
+                const bool in_range = pix < per_frame;
+                const int py = in_range ? pix / p.P1w : 0, px = in_range ? pix % p.P1w : 0;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t *dst = s_stage + stage * C1_A_STAGE_BYTES + m * 16;
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    const int row = 3 * py - 1 + r;
+                    uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+                    if (in_range && row >= 0 && row < H) {
+                        const uint32_t *rp = s_ring + (int)((g0 + row) & (RING_ROWS - 1)) * RING_PITCH + 3 + 3 * px;
+                        const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2], w3 = rp[3], w4 = rp[4];     // (B, G, R, 0x64) of pixels 3px-1 .. 3px+3
+                        lo.x = u8x2_to_h2(__byte_perm(w0, w0, 0x3132));     // R0 G0
+                        lo.y = u8x2_to_h2(__byte_perm(w0, w1, 0x7630));     // B0 R1
+                        lo.z = u8x2_to_h2(__byte_perm(w1, w1, 0x3031));     // G1 B1
+                        lo.w = u8x2_to_h2(__byte_perm(w2, w2, 0x3132));     // R2 G2
+                        hi.x = u8x2_to_h2(__byte_perm(w2, w3, 0x7630));     // B2 R3
+                        hi.y = u8x2_to_h2(__byte_perm(w3, w3, 0x3031));     // G3 B3
+                        hi.z = u8x2_to_h2(__byte_perm(w4, w4, 0x3132));     // R4 G4
+                        hi.w = u8x2_to_h2(__byte_perm(w4, ZERO_PIXEL, 0x7430)); // B4 0   (bytes: B4, 0x64, 0x00, 0x64)
+                    }
+                    *reinterpret_cast<uint4 *>(dst + (2 * r) * 2048) = lo;
+                    *reinterpret_cast<uint4 *>(dst + (2 * r + 1) * 2048) = hi;
+                }
+                fence_proxy_async();                    // generic-proxy stores -> visible to the MMA's async-proxy reads
+                mbar_arrive(&full[stage]);
+                if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 12) {
+        // ------------------------------------------------------------------ MMA issuer
+        uint32_t stage = 0, phase = 0, acc_phase = 0;
+        const uint32_t w_addr = smem_u32(s_w), stage_addr = smem_u32(s_stage);
+        const uint32_t idesc = instr_desc_16bit(128, 3 * C, kBf16);
+        for (int f = blockIdx.x; f < p.B; f += gridDim.x) {
+            for (int t = 0; t < p.tiles_per_frame; ++t) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after_sync();
+                const uint32_t a_stage = stage_addr + stage * C1_A_STAGE_BYTES;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    mbar_wait(&acc_empty[dy], acc_phase ^ 1);
+                    tc_fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) {
+                            const uint64_t da = smem_desc(a_stage + 2 * (dy + ks) * 2048, 2048, 128);
+                            const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
+                            umma_16bit(tmem_base + 3 * C * dy, da, db, idesc, ks > 0 ? 1u : 0u);
+                        }
+                        umma_commit(&acc_full[dy]);
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) umma_commit(&empty[stage]);
+                __syncwarp();
+                if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
+        const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + ch0;
+        uint32_t acc_phase = 0;
+        for (int f = blockIdx.x; f < p.B; f += gridDim.x) {
+            zero_pads(p.out, CG, f, f + 1, threadIdx.x, EPI_WARPS * 32);
+            for (int t = 0; t < p.tiles_per_frame; ++t) {
+                const int pix = t * 128 + m;
+                const bool valid = pix < per_frame;
+                const int Y = valid ? pix / p.P1w : 0, X = valid ? pix % p.P1w : 0;
+                float v[CH];
+                epilogue_tile<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, s_par, ch0, v);
+                if (valid) store_pixel<C>(p.out, f, Y, X, ch0, v);
+                acc_phase ^= 1;
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ input packing
@@ -541,15 +851,15 @@ __global__ void __launch_bounds__(256) pack_xin_f32_kernel(const float *__restri
 }
 
 // Test hook: phase-split 16-bit activation -> float32 NCHW.
-__global__ void unpack_phase_split_kernel(const uint16_t *__restrict__ act, int frames_cap, int batch, int C, int ph, int pw,
-                                          int Qh, int Qw, float *__restrict__ out) {
+__global__ void unpack_phase_split_kernel(const uint16_t *__restrict__ act, int gtot, int FP, int PW, int batch, int C, int ph,
+                                          int pw, float *__restrict__ out) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)batch * C * ph * pw;
     if (idx >= total) return;
     const int x = (int)(idx % pw), y = (int)((idx / pw) % ph), c = (int)((idx / ((int64_t)pw * ph)) % C);
     const int b = (int)(idx / ((int64_t)pw * ph * C));
-    const int plane = ((y % 3) * 3 + (x % 3)) * frames_cap + b;
-    const size_t src = ((((size_t)plane * (C / 8) + c / 8) * Qh + y / 3) * Qw + x / 3) * 8 + c % 8;
+    const int plane = (y % 3) * 3 + (x % 3);
+    const size_t src = (((size_t)plane * (C / 8) + c / 8) * gtot + (size_t)b * FP + (y / 3) * PW + x / 3) * 8 + c % 8;
     out[idx] = kBf16 ? __bfloat162float(__ushort_as_bfloat16(act[src])) : __half2float(__ushort_as_half(act[src]));
 }
 
@@ -562,36 +872,73 @@ __global__ void unpack_plain_kernel(const float *__restrict__ act, int batch, in
 }
 
 // ------------------------------------------------------------------------------------------------ head, first FC
-// AdaptiveAvgPool2d + flatten + Linear folded into one [hidden x (P3 pixels * C)] matrix (the pool is linear), then
-// ReLU and the BatchNorm1d affine.  One warp per 4 frames, lane = hidden unit (hidden <= 32).
+// AdaptiveAvgPool2d + flatten + Linear folded into one [n_feat x 32] matrix (the pool is linear), then ReLU and the
+// BatchNorm1d affine: out[f][o] = act(sum_k act3[f][k] * W[k][o] + bias[o]).  A block takes 16 frames; its two halves
+// (64 threads each) walk alternate k slabs of HEAD_KT staged through shared memory (activations read coalesced along k
+// and stored transposed, so that two frames are one 64-bit load); thread (fy, ox) of a half accumulates a 2 frame x
+// 4 output register tile; the halves are summed through shared memory at the end.
+constexpr int HEAD_FRAMES = 16, HEAD_KT = 96, HEAD_PITCH = HEAD_FRAMES + 4;
+
 __global__ void __launch_bounds__(128) head_fc1_kernel(const float *__restrict__ act3, const float *__restrict__ w_folded,
                                                        const float *__restrict__ bias, const float *__restrict__ scale,
                                                        const float *__restrict__ shift, int batch, int n_feat, int hidden,
                                                        int relu, float *__restrict__ out) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int f0 = warp * 4;
-    if (f0 >= batch) return;
-    const int nf = min(4, batch - f0);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < n_feat; k0 += 32) {
-        float a[4];
+    __shared__ __align__(16) float s_a[2][HEAD_KT * HEAD_PITCH];    // [half][k][frame]
+    __shared__ __align__(16) float s_w[2][HEAD_KT * 32];            // [half][k][out]
+    const int half = threadIdx.x >> 6, tid = threadIdx.x & 63, fy = tid >> 3, ox = tid & 7;   // frames 2*fy.., outputs 4*ox..
+    const int f0 = blockIdx.x * HEAD_FRAMES;
+    float *sa = s_a[half], *sw = s_w[half];
+    float acc[2][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = (i < nf && k0 + lane < n_feat) ? act3[(size_t)(f0 + i) * n_feat + k0 + lane] : 0.f;
-        const int kn = min(32, n_feat - k0);
-        for (int kk = 0; kk < kn; ++kk) {
-            const float w = lane < hidden ? w_folded[(size_t)(k0 + kk) * 32 + lane] : 0.f;     // [n_feat][32], coalesced
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = fmaf(__shfl_sync(0xffffffffu, a[i], kk), w, acc[i]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = half * HEAD_KT; k0 < n_feat; k0 += 2 * HEAD_KT) {
+        const int kn = min(HEAD_KT, n_feat - k0);
+        bar_sync_named(1 + half, 64);                 // the previous slab has been consumed
+        for (int i = tid; i < HEAD_FRAMES * HEAD_KT; i += 64) {
+            const int f = i / HEAD_KT, k = i % HEAD_KT;            // coalesced along k
+            sa[k * HEAD_PITCH + f] = (f0 + f < batch && k < kn) ? act3[(size_t)(f0 + f) * n_feat + k0 + k] : 0.f;
+        }
+        for (int i = tid; i < HEAD_KT * 8; i += 64) {
+            const int k = i >> 3;
+            reinterpret_cast<float4 *>(sw)[i] = k < kn ? reinterpret_cast<const float4 *>(w_folded)[(size_t)(k0 + k) * 8 + (i & 7)]
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        bar_sync_named(1 + half, 64);
+#pragma unroll 8
+        for (int k = 0; k < HEAD_KT; ++k) {
+            const float2 a = *reinterpret_cast<const float2 *>(&sa[k * HEAD_PITCH + 2 * fy]);
+            const float4 w = *reinterpret_cast<const float4 *>(&sw[k * 32 + 4 * ox]);
+            acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
+            acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
+            acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
+            acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
         }
     }
-    if (lane < hidden) {
+    __syncthreads();
+    float *red = s_w[0];                              // [64 threads][8]
+    if (half == 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (i >= nf) break;
-            float s = acc[i] + bias[lane];
-            if (relu) s = fmaxf(s, 0.f);
-            if (scale) s = fmaf(s, scale[lane], shift[lane]);
-            out[(size_t)(f0 + i) * hidden + lane] = s;
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[tid * 8 + i * 4 + j] = acc[i][j];
+    }
+    __syncthreads();
+    if (half == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int f = f0 + 2 * fy + i;
+            if (f >= batch) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = 4 * ox + j;
+                if (o >= hidden) continue;
+                float v = acc[i][j] + red[tid * 8 + i * 4 + j] + bias[o];
+                if (relu) v = fmaxf(v, 0.f);
+                if (scale) v = fmaf(v, scale[o], shift[o]);
+                out[(size_t)f * hidden + o] = v;
+            }
         }
     }
 }
@@ -614,17 +961,18 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// Phase-split activation as a 5-D tensor: (x/3 * 8 + ch%8, y/3, frame, ch/8, phase), box = one shifted view of a tile.
-int make_act_map(CUtensorMap *map, void *base, int frames_cap, int CG, int Qh, int Qw, int box_w, int box_r, int box_f) {
+// A phase-split activation buffer as a 4-D tensor: (32 positions x 8 channels = 256 halves, block of 32 positions,
+// channel group, phase plane); the box is one plane's window of a tile: 6 blocks x 2 channel groups.
+int make_act_map(CUtensorMap *map, void *base, int CG, int gtot) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(CUTDET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    const cuuint64_t plane = (cuuint64_t)Qh * Qw * 16;
-    cuuint64_t dims[5] = {(cuuint64_t)Qw * 8, (cuuint64_t)Qh, (cuuint64_t)frames_cap, (cuuint64_t)CG, 9};
-    cuuint64_t strides[4] = {(cuuint64_t)Qw * 16, plane * CG, plane, plane * CG * frames_cap};
-    cuuint32_t box[5] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_r, (cuuint32_t)box_f, (cuuint32_t)CG, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, kBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint64_t dims[4] = {256, (cuuint64_t)gtot / 32, (cuuint64_t)CG, 9};
+    cuuint64_t strides[3] = {512, (cuuint64_t)gtot * 16, (cuuint64_t)gtot * 16 * CG};
+    cuuint32_t box[4] = {256, MID_WIN / 32, 2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, kBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CUTDET_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return CUTDET_OK;
 }
@@ -634,26 +982,29 @@ int make_act_map(CUtensorMap *map, void *base, int frames_cap, int CG, int Qh, i
 struct TcState {
     int C = 0;
     void *d_w1 = nullptr, *d_w2 = nullptr, *d_w3 = nullptr;   // packed 16-bit operands
-    std::map<std::tuple<const void *, int, int>, std::pair<CUtensorMap, CUtensorMap>> maps;   // (workspace, H, W) -> act1, act2 maps
+    std::map<std::tuple<const void *, int, int>, std::pair<CUtensorMap, CUtensorMap>> maps;   // (workspace, H*65536+W, sub) -> act1, act2 maps
     std::map<std::pair<int, int>, float *> fc1_folded;                                        // (P3h, P3w) -> [n_feat][32]
     std::mutex mutex;
-    int smem_set = 0;
 };
 
 namespace {
 
 struct TcWorkspace {
     size_t xin, act1, act2, act3, fc[2], total;
-    int sub;
+    int sub, group_frames;      // frames per conv1/conv2 pass; frame capacity of the layer-2 buffer
+    int gtot1, gtot2;
 };
 
 TcWorkspace tc_workspace(const cutdet_net *net, const Geom &g, int batch) {
     TcWorkspace w;
     w.sub = batch < SUB_BATCH ? batch : SUB_BATCH;
+    w.group_frames = batch < GROUP * SUB_BATCH ? batch : GROUP * SUB_BATCH;
+    w.gtot1 = gtot_for(w.sub, g.FP1);
+    w.gtot2 = gtot_for(w.group_frames, g.FP2);
     size_t off = 0;
     w.xin = off;  off = align_up(off + g.xin_frame * w.sub, 1024);
-    w.act1 = off; off = align_up(off + g.act1_frame * w.sub, 1024);
-    w.act2 = off; off = align_up(off + g.act2_frame * w.sub, 1024);
+    w.act1 = off; off = align_up(off + act_bytes(g.CG, w.gtot1), 1024);
+    w.act2 = off; off = align_up(off + act_bytes(g.CG, w.gtot2), 1024);
     w.act3 = off; off = align_up(off + g.act3_frame * batch, 1024);
     size_t widest = net->cfg.fc_hidden_size > net->cfg.fc_input_size ? net->cfg.fc_hidden_size : net->cfg.fc_input_size;
     for (int i = 0; i < 2; ++i) { w.fc[i] = off; off = align_up(off + widest * sizeof(float) * batch, 1024); }
@@ -685,86 +1036,129 @@ int upload_bytes(cutdet_net *net, const void *host, size_t bytes, void **dev) {
 template <int C>
 int set_smem_limits() {
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1Smem<C>::total));
-    CUTDET_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, F1Smem<C>::total));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, MidSmem<C>::total));
     return CUTDET_OK;
 }
 
 template <int C>
 int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
-    const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+    const int grid = p.B < sm_count() ? p.B : sm_count();
     {
         KernelScope scope("conv1_tc", stream);
-        conv1_tc_kernel<C><<<grid, 288, C1Smem<C>::total, stream>>>(p);
+        conv1_tc_kernel<C><<<grid, 416, C1Smem<C>::total, stream>>>(p);
     }
     CUTDET_LAUNCH_CHECK("conv1_tc_kernel");
     return CUTDET_OK;
 }
 
 template <int C>
+int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src, cudaStream_t stream) {
+    const int grid = p.B < sm_count() ? p.B : sm_count();
+    {
+        KernelScope scope("conv1_fused_tc", stream);
+        conv1_fused_tc_kernel<C><<<grid, 416, F1Smem<C>::total, stream>>>(p, src);
+    }
+    CUTDET_LAUNCH_CHECK("conv1_fused_tc_kernel");
+    return CUTDET_OK;
+}
+
+// Can K1 be fused into conv1 for these frames?  (16-byte aligned rows for the bulk copies, tables that fit, enough raw slots.)
+bool fused_source(const cutdet_resize_plan *plan, const cutdet_frames *frames, const Geom &g, FusedSrc *out) {
+    const ResizePlanDev &h = plan->host;
+    const long long row_bytes = 3LL * h.src_w;
+    if (h.dst_w > F_MAX_DST || h.dst_h > F_MAX_DST || g.P1w < 64) return false;
+    if (row_bytes % 16 || frames->row_pitch % 16 || frames->frame_stride % 16 || reinterpret_cast<uintptr_t>(frames->frames_dev) % 16)
+        return false;
+    const int rows = frames->row_map_compact ? plan->n_rows : h.src_h;
+    if ((long long)rows * frames->row_pitch >= (1LL << 31)) return false;
+    const int n_src = (h.gather_step_x > 0 || h.mode == RESIZE_COPY) ? 1 : 2;
+    const long long slot = n_src * row_bytes;
+    long long n_slots = RAW_BYTES / slot;
+    if (n_slots > RAW_SLOTS_MAX) n_slots = RAW_SLOTS_MAX;
+    if (n_slots < 8) return false;
+    out->plan = h;
+    out->frames = frames->frames_dev;
+    out->frame_stride = frames->frame_stride;
+    out->row_pitch = frames->row_pitch;
+    out->compact = frames->row_map_compact;
+    out->n_src = n_src;
+    out->row_bytes = (int)row_bytes;
+    out->n_slots = (int)n_slots;
+    return true;
+}
+
+template <int C>
 int launch_mid(const CUtensorMap &map, const MidParams &p, const char *name, cudaStream_t stream) {
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-    const int smem = MidSmem<C>::total(p.MT);
-    if (smem > 227 * 1024) return fail(CUTDET_EUNSUPPORTED, "conv tile needs %d bytes of shared memory", smem);
     {
         KernelScope scope(name, stream);
-        conv_mid_tc_kernel<C><<<grid, 256, smem, stream>>>(map, p);
+        conv_mid_tc_kernel<C><<<grid, 320, MidSmem<C>::total, stream>>>(map, p);
     }
     CUTDET_LAUNCH_CHECK("conv_mid_tc_kernel");
     return CUTDET_OK;
 }
 
-MidParams mid_params(const TileCfg &t, int nb, int out_h, int out_w) {
+MidParams mid_params(int n_frames, int FP, int PW, int out_h, int out_w) {
     MidParams p;
     memset(&p, 0, sizeof(p));
-    p.B = nb; p.out_h = out_h; p.out_w = out_w;
-    p.R = t.R; p.F = t.F; p.MT = t.MT; p.n_rg = t.n_rg;
-    p.n_tiles = ((nb + t.F - 1) / t.F) * t.n_rg;
+    p.n_frames = n_frames; p.FP = FP; p.PW = PW; p.out_h = out_h; p.out_w = out_w;
+    p.n_tiles = (int)(((long long)n_frames * FP + 127) / 128);
     return p;
 }
 
-// conv stack over one sub-batch whose x-unfolded input already sits in the workspace
-template <int C>
-int run_conv_stack(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int nb, int frame0, cudaStream_t stream) {
+int get_maps(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, std::pair<CUtensorMap, CUtensorMap> **out) {
     TcState *tc = net->tc;
-    std::pair<CUtensorMap, CUtensorMap> *maps = nullptr;
-    {
-        std::lock_guard<std::mutex> lock(tc->mutex);
-        auto key = std::make_tuple((const void *)ws, g.H * 65536 + g.W, w.sub);
-        auto it = tc->maps.find(key);
-        if (it == tc->maps.end()) {
-            std::pair<CUtensorMap, CUtensorMap> m;
-            if (int rc = make_act_map(&m.first, ws + w.act1, w.sub, g.CG, g.Q1h, g.Q1w, g.P2w, g.t2.R, g.t2.F)) return rc;
-            if (int rc = make_act_map(&m.second, ws + w.act2, w.sub, g.CG, g.Q2h, g.Q2w, g.P3w, g.t3.R, g.t3.F)) return rc;
-            it = tc->maps.emplace(key, m).first;
-        }
-        maps = &it->second;
+    std::lock_guard<std::mutex> lock(tc->mutex);
+    auto key = std::make_tuple((const void *)ws, g.H * 65536 + g.W, w.sub * 65536 + w.group_frames);
+    auto it = tc->maps.find(key);
+    if (it == tc->maps.end()) {
+        std::pair<CUtensorMap, CUtensorMap> m;
+        if (int rc = make_act_map(&m.first, ws + w.act1, g.CG, w.gtot1)) return rc;
+        if (int rc = make_act_map(&m.second, ws + w.act2, g.CG, w.gtot2)) return rc;
+        it = tc->maps.emplace(key, m).first;
     }
+    *out = &it->second;
+    return CUTDET_OK;
+}
+
+// conv1 + conv2 over one sub-batch whose x-unfolded input already sits in the workspace; layer 2's maps land in the
+// group buffer at frame slot `slot0`.
+template <int C>
+int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, const CUtensorMap &map1, int nb, int slot0,
+               cudaStream_t stream, const FusedSrc *fused, int f0) {
+    TcState *tc = net->tc;
     Conv1Params c1;
     memset(&c1, 0, sizeof(c1));
     c1.xin = reinterpret_cast<const uint4 *>(ws + w.xin);
     c1.B = nb; c1.H = g.H; c1.P1h = g.P1h; c1.P1w = g.P1w;
-    c1.n_pooled = (long long)nb * g.P1h * g.P1w;
-    c1.n_tiles = (int)((c1.n_pooled + 127) / 128);
-    c1.out = OutSpec{ws + w.act1, 0, w.sub, g.Q1h, g.Q1w, g.P1h, g.P1w};
+    c1.tiles_per_frame = (g.P1h * g.P1w + 127) / 128;
+    c1.out = OutSpec{ws + w.act1, 0, w.gtot1, g.PW1, g.FP1, g.Q1h, 0, g.P1h, g.P1w};
     c1.w_packed = reinterpret_cast<const uint4 *>(tc->d_w1);
     c1.bias = net->conv[0].d_bias; c1.scale = net->conv[0].d_scale; c1.shift = net->conv[0].d_shift;
-    if (int rc = launch_conv1<C>(c1, stream)) return rc;
+    if (fused) {
+        FusedSrc fs = *fused;
+        fs.frames += (long long)f0 * fs.frame_stride;
+        if (int rc = launch_conv1_fused<C>(c1, fs, stream)) return rc;
+    } else if (int rc = launch_conv1<C>(c1, stream)) return rc;
 
-    MidParams p2 = mid_params(g.t2, nb, g.P2h, g.P2w);
-    p2.out = OutSpec{ws + w.act2, 0, w.sub, g.Q2h, g.Q2w, g.P2h, g.P2w};
+    MidParams p2 = mid_params(nb, g.FP1, g.PW1, g.P2h, g.P2w);
+    p2.out = OutSpec{ws + w.act2, 0, w.gtot2, g.PW2, g.FP2, g.Q2h, slot0, g.P2h, g.P2w};
     p2.w_packed = reinterpret_cast<const uint4 *>(tc->d_w2);
     p2.bias = net->conv[1].d_bias; p2.scale = net->conv[1].d_scale; p2.shift = net->conv[1].d_shift;
-    if (int rc = launch_mid<C>(maps->first, p2, "conv2_tc", stream)) return rc;
-
-    MidParams p3 = mid_params(g.t3, nb, g.P3h, g.P3w);
-    p3.out = OutSpec{ws + w.act3 + (size_t)frame0 * g.act3_frame, 1, nb, 0, 0, g.P3h, g.P3w};
-    p3.w_packed = reinterpret_cast<const uint4 *>(tc->d_w3);
-    p3.bias = net->conv[2].d_bias; p3.scale = net->conv[2].d_scale; p3.shift = net->conv[2].d_shift;
-    return launch_mid<C>(maps->second, p3, "conv3_tc", stream);
+    return launch_mid<C>(map1, p2, "conv2_tc", stream);
 }
 
-int run_stack(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int nb, int frame0, cudaStream_t stream) {
-    return g.C == 48 ? run_conv_stack<48>(net, g, w, ws, nb, frame0, stream) : run_conv_stack<32>(net, g, w, ws, nb, frame0, stream);
+// conv3 over the `n` frames gathered in the group buffer; their layer-3 maps go to frames [frame0, frame0 + n) of act3.
+template <int C>
+int run_conv3(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, const CUtensorMap &map2, int n, int frame0,
+              cudaStream_t stream) {
+    TcState *tc = net->tc;
+    MidParams p3 = mid_params(n, g.FP2, g.PW2, g.P3h, g.P3w);
+    p3.out = OutSpec{ws + w.act3, 1, 0, 0, 0, 0, frame0, g.P3h, g.P3w};
+    p3.w_packed = reinterpret_cast<const uint4 *>(tc->d_w3);
+    p3.bias = net->conv[2].d_bias; p3.scale = net->conv[2].d_scale; p3.shift = net->conv[2].d_shift;
+    return launch_mid<C>(map2, p3, "conv3_tc", stream);
 }
 
 // AdaptiveAvgPool + first FC folded, for this pooled-map size; built once and cached.
@@ -813,10 +1207,9 @@ int run_head(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int
     float *out0 = last0 ? logits : reinterpret_cast<float *>(ws + w.fc[0]);
     {
         KernelScope scope("head_fc1", stream);
-        const int warps = (batch + 3) / 4;
-        head_fc1_kernel<<<(warps * 32 + 127) / 128, 128, 0, stream>>>(cur, folded, L0.d_bias, L0.has_bn ? L0.d_scale : nullptr,
-                                                                     L0.has_bn ? L0.d_shift : nullptr, batch, n_feat, L0.out,
-                                                                     last0 ? 0 : 1, out0);
+        head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, 128, 0, stream>>>(
+            cur, folded, L0.d_bias, L0.has_bn ? L0.d_scale : nullptr, L0.has_bn ? L0.d_shift : nullptr, batch, n_feat, L0.out,
+            last0 ? 0 : 1, out0);
     }
     CUTDET_LAUNCH_CHECK("head_fc1_kernel");
     cur = out0;
@@ -829,6 +1222,28 @@ int run_head(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int
     return CUTDET_OK;
 }
 
+// The whole stack over a batch: `pack(f0, nb)` writes the x-unfolded input of frames [f0, f0 + nb) into the workspace.
+template <int C, typename Pack>
+int run_batch(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int batch, float *logits, cudaStream_t stream,
+              Pack pack, const FusedSrc *fused = nullptr) {
+    std::pair<CUtensorMap, CUtensorMap> *maps = nullptr;
+    if (int rc = get_maps(net, g, w, ws, &maps)) return rc;
+    int group_start = 0, in_group = 0;
+    for (int f0 = 0; f0 < batch; f0 += w.sub) {
+        const int nb = batch - f0 < w.sub ? batch - f0 : w.sub;
+        if (!fused)
+            if (int rc = pack(f0, nb)) return rc;
+        if (int rc = run_conv12<C>(net, g, w, ws, maps->first, nb, in_group, stream, fused, f0)) return rc;
+        in_group += nb;
+        if (in_group + w.sub > w.group_frames || f0 + nb >= batch) {
+            if (int rc = run_conv3<C>(net, g, w, ws, maps->second, in_group, group_start, stream)) return rc;
+            group_start += in_group;
+            in_group = 0;
+        }
+    }
+    return run_head(net, g, w, ws, batch, logits, stream);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ interface
@@ -836,8 +1251,7 @@ bool tc_supported(const cutdet_net *net, int height, int width) {
     if (!net->tc) return false;
     const Geom g = make_geom(height, width, net->cfg.hidden_channels);
     if (g.P3h < 1 || g.P3w < 1) return false;
-    if (g.P2w > 32 || g.P3w > 32) return false;                       // TMA box: at most 256 elements wide
-    if (MidSmem<48>::total(g.t2.MT) > 227 * 1024) return false;
+    if (g.PW1 + 1 > MID_HALO || g.PW2 + 1 > MID_HALO) return false;      // a shifted view must stay inside the tile's window
     return true;
 }
 
@@ -897,8 +1311,7 @@ size_t tc_workspace_bytes(const cutdet_net *net, int batch, int height, int widt
 int tc_forward_f32(cutdet_net *net, const float *x, int batch, int height, int width, float *logits, char *ws, cudaStream_t stream) {
     const Geom g = make_geom(height, width, net->cfg.hidden_channels);
     const TcWorkspace w = tc_workspace(net, g, batch);
-    for (int f0 = 0; f0 < batch; f0 += w.sub) {
-        const int nb = batch - f0 < w.sub ? batch - f0 : w.sub;
+    auto pack = [&](int f0, int nb) -> int {
         const int64_t total = (int64_t)nb * g.H * g.P1w;
         {
             KernelScope scope("pack_xin_f32", stream);
@@ -906,9 +1319,9 @@ int tc_forward_f32(cutdet_net *net, const float *x, int batch, int height, int w
                                                                                    g.P1w, reinterpret_cast<uint4 *>(ws + w.xin));
         }
         CUTDET_LAUNCH_CHECK("pack_xin_f32_kernel");
-        if (int rc = run_stack(net, g, w, ws, nb, f0, stream)) return rc;
-    }
-    return run_head(net, g, w, ws, batch, logits, stream);
+        return CUTDET_OK;
+    };
+    return g.C == 48 ? run_batch<48>(net, g, w, ws, batch, logits, stream, pack) : run_batch<32>(net, g, w, ws, batch, logits, stream, pack);
 }
 
 int tc_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cutdet_frames *src, float *logits, char *ws,
@@ -916,8 +1329,7 @@ int tc_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cut
     const int batch = src->batch;
     const Geom g = make_geom(plan->host.dst_h, plan->host.dst_w, net->cfg.hidden_channels);
     const TcWorkspace w = tc_workspace(net, g, batch);
-    for (int f0 = 0; f0 < batch; f0 += w.sub) {
-        const int nb = batch - f0 < w.sub ? batch - f0 : w.sub;
+    auto pack = [&](int f0, int nb) -> int {
         const int64_t total = (int64_t)nb * g.H * g.P1w;
         {
             KernelScope scope("preprocess_xin", stream);
@@ -926,9 +1338,12 @@ int tc_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cut
                 src->row_map_compact, nb, g.P1w, reinterpret_cast<uint4 *>(ws + w.xin));
         }
         CUTDET_LAUNCH_CHECK("preprocess_xin_kernel");
-        if (int rc = run_stack(net, g, w, ws, nb, f0, stream)) return rc;
-    }
-    return run_head(net, g, w, ws, batch, logits, stream);
+        return CUTDET_OK;
+    };
+    FusedSrc fs;
+    const FusedSrc *fused = fused_source(plan, src, g, &fs) ? &fs : nullptr;
+    return g.C == 48 ? run_batch<48>(net, g, w, ws, batch, logits, stream, pack, fused)
+                     : run_batch<32>(net, g, w, ws, batch, logits, stream, pack, fused);
 }
 
 int tc_debug_conv_output(cutdet_net *net, int layer, int batch, int height, int width, const char *ws, float *out,
@@ -943,10 +1358,10 @@ int tc_debug_conv_output(cutdet_net *net, int layer, int batch, int height, int 
                                                                                g.P3h * g.P3w, out);
     } else {
         const int ph = layer == 0 ? g.P1h : g.P2h, pw = layer == 0 ? g.P1w : g.P2w;
-        const int Qh = layer == 0 ? g.Q1h : g.Q2h, Qw = layer == 0 ? g.Q1w : g.Q2w;
         const int64_t total = (int64_t)batch * g.C * ph * pw;
         unpack_phase_split_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(
-            reinterpret_cast<const uint16_t *>(ws + (layer == 0 ? w.act1 : w.act2)), w.sub, batch, g.C, ph, pw, Qh, Qw, out);
+            reinterpret_cast<const uint16_t *>(ws + (layer == 0 ? w.act1 : w.act2)), layer == 0 ? w.gtot1 : w.gtot2,
+            layer == 0 ? g.FP1 : g.FP2, layer == 0 ? g.PW1 : g.PW2, batch, g.C, ph, pw, out);
     }
     CUTDET_LAUNCH_CHECK("unpack kernel");
     return CUTDET_OK;

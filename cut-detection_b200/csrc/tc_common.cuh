@@ -13,15 +13,21 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of the (converged) warp.  Written the way ptxas recognises: a branch on this predicate is a one-thread region, so
+// the uniform-datapath instructions inside it (UTCHMMA, UTMALDG, UTCBAR) are emitted directly.  Under a plain
+// `if (lane == 0)` ptxas wraps every one of them in an ELECT / BRA.U.ANY loop (about 16 instructions and ~120 cycles per MMA).
 __device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
+    uint32_t pred = 0, laneid = 0;
     asm volatile(
         "{\n\t"
-        ".reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
+        ".reg .b32 %%rx;\n\t"
+        ".reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %2;\n\t"
+        "@%%px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, %%rx;\n\t"
         "}\n"
-        : "=r"(pred));
+        : "+r"(laneid), "+r"(pred)
+        : "r"(0xffffffffu));
     return pred != 0;
 }
 
@@ -56,6 +62,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// Named barrier among `count` threads (a multiple of 32) of the CTA; id 0 is __syncthreads.
+__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -68,6 +77,22 @@ __device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
         "r"(c3), "r"(c4)
         : "memory");
+}
+
+// 4-D tiled load.
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+        : "memory");
+}
+// 1-D bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16), completion on an mbarrier.
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------- cp.async (LDGSTS)
@@ -120,6 +145,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         : "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// ... and 8 consecutive columns.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

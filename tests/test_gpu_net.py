@@ -166,3 +166,30 @@ def test_bad_inputs(native):
         net.forward_f32(torch.zeros((1, 4, 144, 256), device="cuda"))        # channel mismatch
     with pytest.raises(ValueError):
         net.forward_f32(torch.zeros((1, 3, 20, 20), device="cuda"))          # too small for 3 pools
+
+
+@pytest.mark.parametrize("h,w,batch,compact", [
+    (720, 1280, 5, False), (720, 1280, 150, True), (720, 1280, 301, False),     # integer-scale gather, > 1 frame per CTA, > 1 sub-batch
+    (1080, 1920, 21, False), (1080, 1920, 9, True),                             # fixed-point bilinear, two source rows per output row
+    (360, 640, 33, False),                                                       # scale 2.5
+    (288, 512, 7, False),                                                        # exact 2x2 box mean
+    (144, 256, 12, False),                                                       # plain copy
+    (2160, 3840, 3, False),                                                      # scale 15, 11.5 KB source rows
+    (800, 1920, 4, False),                                                       # H' = 106
+])
+def test_fused_frames_equal_unfused(native, h, w, batch, compact):
+    """K1 fused into conv1 (bulk-copied source rows -> resized ring -> A operand) must give the SAME logits as
+    preprocessing to float32 first and entering through net(x): both feed the MMAs the identical fp16 pixels v/256."""
+    from cutdet import engine
+    net, _ = native
+    rng = np.random.default_rng(h * 7 + batch)
+    frames = rng.integers(0, 256, (batch, h, w, 3), dtype=np.uint8)
+    frames[0, : h // 2] = 255                                   # some structure besides noise
+    plan = engine.ResizePlan.for_video(h, w, 256)
+    dev = torch.from_numpy(frames).cuda()
+    x = engine.preprocess_f32(plan, dev)
+    want = net.forward_f32(x).cpu().numpy()
+    if compact:
+        dev = dev[:, torch.from_numpy(plan.rows.astype(np.int64)).cuda()].contiguous()
+    got = net.forward_frames(plan, dev, compact).cpu().numpy()
+    assert np.array_equal(got, want), float(np.abs(got - want).max())
