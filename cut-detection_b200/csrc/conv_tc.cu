@@ -494,18 +494,28 @@ __global__ void __launch_bounds__(416, 1) conv1_tc_kernel(const Conv1Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------ K1 fused into conv1
-// The same tile loop, MMA issue and epilogue as conv1_tc_kernel, but the A operand is built from the DECODED FRAMES:
-// the x-unfolded input never goes to memory.  Per CTA (= one frame at a time), warps 8..11:
-//   raw ring      the source rows each resized row needs (1 for an integer-scale gather such as 720p -> 256x144, else 2)
-//                 arrive by cp.async.bulk, one mbarrier per slot, RAW_BYTES (90 KB) in flight per SM -- with 148 SMs
-//                 that covers HBM latency x bandwidth, so the frame read streams at HBM speed;
-//   stage 1       resized rows, bit-exact with cv2.resize(INTER_LINEAR), as uint8 (B, G, R, 0x64) words in a 32-row ring;
-//   stage 2       thread m builds GEMM row m: 5 rows x 5 pixels from the ring, u8 -> fp16 v/256 through the
-//                 0x6400|v trick ((1024 + v) / 256 - 4, one PRMT + one HFMA2 per pair), 16-byte stores into the A stage.
-constexpr int F_STAGES = 3;
-constexpr int RING_ROWS = 32, RING_PITCH = 264;          // words per ring row: [4 pad][256 pixels][4 pad]
-constexpr int RAW_BYTES = 92160;                         // 24 rows of 1280 x 3, or 8 row pairs of 1920 x 3
-constexpr int RAW_SLOTS_MAX = 24;
+// conv1 straight from the DECODED FRAMES: neither the resized image nor the x-unfolded input ever goes to memory, and
+// the MMA reads its A operand where the resize wrote it.  One CTA walks one frame at a time.
+//
+//   loader (warp 13)     the source rows each resized row needs (1 for an integer-scale gather such as 720p -> 256x144,
+//                        else 2) arrive by cp.async.bulk into a ring of slots with full/empty mbarriers -- 64 KB in flight
+//                        per SM, enough to cover HBM latency x bandwidth, so the frame read streams at HBM speed;
+//   unfold (warps 8..11) a lane takes one pooled column px of one resized row y: the five pixels 3px-1 .. 3px+3, bit-exact
+//                        with cv2.resize(INTER_LINEAR), u8 -> fp16 v/256 through the 0x6400|v trick ((1024 + v) / 256 - 4:
+//                        one PRMT + one HFMA2 per pair) = one 16-half K-chunk, stored as two 16-byte halves;
+//   the ring             three sub-rings, one per y % 3, each [k-half][position][16 B] over the FLATTENED position
+//                        g = R * P1w + px, R = frame_in_cta * (P1h + 1) + y / 3 (one all-zero row per frame doubles as the
+//                        conv's zero padding above the next frame and below this one).  GEMM row m of tile t is position
+//                        128 t + m, and its K-chunk for input row 3py - 1 + c is position 128 t + m + {-P1w, 0, 0, 0, +P1w}[c]
+//                        of sub-ring {2, 0, 1, 2, 0}[c]: for a whole tile that is 128 CONSECUTIVE 16-byte entries, i.e. a
+//                        K-major UMMA operand at a plain offset.  Positions wrap at FR_CAP; the first 128 are mirrored past
+//                        the end so a window never straddles the wrap.
+constexpr int FR_DEPTH = 4;                  // tiles in flight between the unfold warps and the MMAs
+constexpr int FR_CAP = 1024;                 // positions per sub-ring (a power of two)
+constexpr int FR_PLANE = (FR_CAP + 128) * 16;            // bytes of one k-half plane incl. the mirror
+constexpr int FR_SUB = 2 * FR_PLANE;
+constexpr int RAW_BYTES = 65536;
+constexpr int RAW_SLOTS_MAX = 16;
 constexpr int F_MAX_DST = 256;
 constexpr uint32_t ZERO_PIXEL = 0x64000000u;
 
@@ -516,16 +526,15 @@ struct FusedSrc {
     int compact;
     int n_src;        // raw rows per resized row
     int row_bytes;    // 3 * src_w, a multiple of 16
-    int n_slots;      // raw ring slots of n_src * row_bytes each
+    int log2_slots;   // raw ring slots (a power of two) of n_src * row_bytes each
 };
 
 template <int C>
 struct F1Smem {
     static constexpr int W_BYTES = 6 * 3 * C * 16;
     static constexpr int LBO_B = 3 * C * 16;
-    static constexpr int OFF_STAGE = W_BYTES;
-    static constexpr int OFF_RING = OFF_STAGE + F_STAGES * C1_A_STAGE_BYTES;
-    static constexpr int OFF_RAW = OFF_RING + RING_ROWS * RING_PITCH * 4;
+    static constexpr int OFF_RING = W_BYTES;
+    static constexpr int OFF_RAW = OFF_RING + 3 * FR_SUB;
     static constexpr int OFF_TAB = OFF_RAW + RAW_BYTES + 64;           // 64 bytes of slack: the gather reads one word past a row
     static constexpr int OFF_BAR = OFF_TAB + F_MAX_DST * (8 + 8 + 16);  // rowoff[256][2], yb[256][2], xtab[256] (int4)
     static constexpr int OFF_PAR = OFF_BAR + 512;
@@ -540,33 +549,68 @@ __device__ __forceinline__ uint32_t u8x2_to_h2(uint32_t magic_pair) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-template <int C>
-__global__ void __launch_bounds__(416, 1) conv1_fused_tc_kernel(const Conv1Params p, const FusedSrc src) {
+// One resized pixel as a (B, G, R, 0x64) word, from the source rows staged in shared memory.
+__device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, const uint8_t *q0, const uint8_t *q1, const int4 *s_xtab,
+                                                 int b0, int b1, int x) {
+    if (x < 0 || x >= plan.dst_w) return ZERO_PIXEL;
+    if (plan.gather_step_x > 0) {
+        const int b = 3 * (plan.gather_off_x + x * plan.gather_step_x);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(q0 + (b & ~3));
+        return (__funnelshift_r(wp[0], wp[1], (b & 3) * 8) & 0x00FFFFFFu) | ZERO_PIXEL;
+    }
+    int v[3];
+    if (plan.mode == RESIZE_COPY) {
+        v[0] = q0[3 * x]; v[1] = q0[3 * x + 1]; v[2] = q0[3 * x + 2];
+    } else if (plan.mode == RESIZE_AREA2) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = (q0[6 * x + c] + q0[6 * x + 3 + c] + q1[6 * x + c] + q1[6 * x + 3 + c] + 2) >> 2;
+    } else {
+        const int4 xt = s_xtab[x];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int s0 = xt.z * q0[xt.x + c] + xt.w * q0[xt.y + c];
+            const int s1 = xt.z * q1[xt.x + c] + xt.w * q1[xt.y + c];
+            v[c] = min(max((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2, 0), 255);
+        }
+    }
+    return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ZERO_PIXEL;
+}
+
+// 576 threads: warps 0..7 = epilogue, 8..15 = unfold, 16 = MMA issuer (+ TMEM alloc), 17 = loader.
+// GATHER: the resize is out[y][x] = src[off_y + y*step_y][off_x + x*step_x] (every second tap has zero weight).
+constexpr int UNFOLD_WARPS = 8, F1_MMA_WARP = 8 + UNFOLD_WARPS, F1_LOAD_WARP = 9 + UNFOLD_WARPS, F1_THREADS = 32 * (10 + UNFOLD_WARPS);
+template <int C, bool GATHER>
+__global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Conv1Params p, const FusedSrc src) {
     using S = F1Smem<C>;
     constexpr int CG = C / 8, CH = C / 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *s_w = smem;
-    uint8_t *s_stage = smem + S::OFF_STAGE;
-    uint32_t *s_ring = reinterpret_cast<uint32_t *>(smem + S::OFF_RING);
+    uint8_t *s_ring = smem + S::OFF_RING;
     uint8_t *s_raw = smem + S::OFF_RAW;
     int *s_rowoff = reinterpret_cast<int *>(smem + S::OFF_TAB);               // [y][2]
     int *s_yb = s_rowoff + 2 * F_MAX_DST;                                       // [y][2]: b0, b1
     int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);              // [x]: 3*x0, 3*x1, a0, a1
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);
-    uint64_t *empty = full + F_STAGES;
-    uint64_t *acc_full = empty + F_STAGES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);           // [FR_DEPTH] tile's rows are in the ring
+    uint64_t *empty = full + FR_DEPTH;                                          // [FR_DEPTH] tile's MMAs have read them
+    uint64_t *acc_full = empty + FR_DEPTH;
     uint64_t *acc_empty = acc_full + 3;
     uint64_t *raw_full = acc_empty + 3;                                         // [RAW_SLOTS_MAX]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_full + RAW_SLOTS_MAX);
+    uint64_t *raw_empty = raw_full + RAW_SLOTS_MAX;                             // [RAW_SLOTS_MAX]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + RAW_SLOTS_MAX);
     float *s_par = reinterpret_cast<float *>(smem + S::OFF_PAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ResizePlanDev &plan = src.plan;
-    const int H = p.H, W = plan.dst_w;
+    const int H = p.H, P1w = p.P1w, RPF = p.P1h + 1;          // pooled rows per frame incl. the zero row
+    const int Hc = min(H, 3 * p.P1h + 1);                     // resized rows the conv reads (row 3*P1h only if it exists)
+    const int n_parts = (P1w + 31) / 32;
+    const int n_frames_cta = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_tiles = (n_frames_cta * RPF * P1w + 127) / 128;
+    const int n_slots = 1 << src.log2_slots, slot_bytes = src.n_src * src.row_bytes;
 
     for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = p.bias[i]; s_par[C + i] = p.scale[i]; s_par[2 * C + i] = p.shift[i]; }
-    for (int i = threadIdx.x; i < RING_ROWS * RING_PITCH; i += blockDim.x) s_ring[i] = ZERO_PIXEL;
+    for (int i = threadIdx.x; i < 3 * FR_SUB / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_ring)[i] = make_uint4(0, 0, 0, 0);
     for (int y = threadIdx.x; y < H; y += blockDim.x) {
         int r0, r1, b0 = 2048, b1 = 0;
         if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
@@ -580,187 +624,162 @@ __global__ void __launch_bounds__(416, 1) conv1_fused_tc_kernel(const Conv1Param
         s_yb[2 * y + 1] = b1;
     }
     if (plan.mode == RESIZE_LINEAR && plan.gather_step_x == 0)
-        for (int x = threadIdx.x; x < W; x += blockDim.x) s_xtab[x] = make_int4(3 * plan.x0[x], 3 * plan.x1[x], plan.a0[x], plan.a1[x]);
+        for (int x = threadIdx.x; x < plan.dst_w; x += blockDim.x) s_xtab[x] = make_int4(3 * plan.x0[x], 3 * plan.x1[x], plan.a0[x], plan.a1[x]);
     fence_proxy_async();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < FR_DEPTH; ++s) { mbar_init(&full[s], 32 * UNFOLD_WARPS); mbar_init(&empty[s], 1); }
         for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], EPI_WARPS); }
-        for (int s = 0; s < RAW_SLOTS_MAX; ++s) mbar_init(&raw_full[s], 1);
+        for (int s = 0; s < RAW_SLOTS_MAX; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], n_parts); }
         fence_barrier_init();
     }
-    if (warp == 12) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == F1_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const int per_frame = p.P1h * p.P1w;
 
-    if (warp >= 8 && warp < 12) {
-        // ------------------------------------------------------------------ producers: raw rows -> resized ring -> A operand
-        const int m = threadIdx.x - 256, pwarp = warp - 8;
-        const int n_frames_cta = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        const long long total_rows = (long long)n_frames_cta * H;
-        const int slot_bytes = src.n_src * src.row_bytes;
-        long long issued = 0;                      // rows whose raw loads have been issued (meaningful in pwarp 0 only)
-        auto issue_until = [&](long long limit) {  // whole warp 8, converged
-            if (limit > total_rows) limit = total_rows;
-            while (issued < limit) {
-                const int fi = (int)(issued / H), y = (int)(issued % H), slot = (int)(issued % src.n_slots);
+    if (warp == F1_LOAD_WARP) {
+        // ------------------------------------------------------------------ loader: source rows -> raw ring
+        int n = 0;                                          // resized rows loaded so far (frame-major)
+        for (int fi = 0; fi < n_frames_cta; ++fi) {
+            const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
+            for (int y = 0; y < Hc; ++y, ++n) {
+                const int slot = n & (n_slots - 1);
+                mbar_wait(&raw_empty[slot], ((n >> src.log2_slots) & 1) ^ 1);
                 if (elect_one()) {
-                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
                     mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
                     for (int j = 0; j < src.n_src; ++j)
                         bulk_load_1d(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * y + j], (uint32_t)src.row_bytes,
                                      &raw_full[slot]);
                 }
                 __syncwarp();
-                ++issued;
-            }
-        };
-        if (pwarp == 0) issue_until(src.n_slots);
-        uint32_t stage = 0, phase = 0;
-        int fi = 0;
-        for (int f = blockIdx.x; f < p.B; f += gridDim.x, ++fi) {
-            int next_row = 0;
-            const long long g0 = (long long)fi * H;
-            for (int t = 0; t < p.tiles_per_frame; ++t) {
-                // ---- stage 1: resized rows up to the last one this tile reads
-                const int last_pix = min(t * 128 + 127, per_frame - 1);
-                const int y_hi = min(H - 1, 3 * (last_pix / p.P1w) + 3);
-                const int n_items = 2 * (y_hi - next_row + 1);
-                for (int item = pwarp; item < n_items; item += 4) {
-                    const int y = next_row + (item >> 1), half = item & 1;
-                    const long long g = g0 + y;
-                    const int slot = (int)(g % src.n_slots);
-                    mbar_wait(&raw_full[slot], (uint32_t)((g / src.n_slots) & 1));
-                    const uint8_t *q0 = s_raw + slot * slot_bytes, *q1 = q0 + (src.n_src - 1) * src.row_bytes;
-                    uint32_t *ring_row = s_ring + (int)(g & (RING_ROWS - 1)) * RING_PITCH + 4;
-                    if (plan.gather_step_x > 0 && (W & 3) == 0) {
-                        const int x0 = 128 * half + 4 * lane;
-                        if (x0 < W) {
-                            uint32_t o[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int b = 3 * (plan.gather_off_x + (x0 + j) * plan.gather_step_x);
-                                const uint32_t *wp = reinterpret_cast<const uint32_t *>(q0 + (b & ~3));
-                                o[j] = (__funnelshift_r(wp[0], wp[1], (b & 3) * 8) & 0x00FFFFFFu) | ZERO_PIXEL;
-                            }
-                            *reinterpret_cast<uint4 *>(ring_row + x0) = make_uint4(o[0], o[1], o[2], o[3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int x = 128 * half + 32 * j + lane;
-                            if (x >= W) continue;
-                            int v[3];
-                            if (plan.gather_step_x > 0) {
-                                const uint8_t *q = q0 + 3 * (plan.gather_off_x + x * plan.gather_step_x);
-                                v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
-                            } else if (plan.mode == RESIZE_COPY) {
-                                v[0] = q0[3 * x]; v[1] = q0[3 * x + 1]; v[2] = q0[3 * x + 2];
-                            } else if (plan.mode == RESIZE_AREA2) {
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) v[c] = (q0[6 * x + c] + q0[6 * x + 3 + c] + q1[6 * x + c] + q1[6 * x + 3 + c] + 2) >> 2;
-                            } else {
-                                const int4 xt = s_xtab[x];
-                                const int b0 = s_yb[2 * y], b1 = s_yb[2 * y + 1];
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) {
-                                    const int s0 = xt.z * q0[xt.x + c] + xt.w * q0[xt.y + c];
-                                    const int s1 = xt.z * q1[xt.x + c] + xt.w * q1[xt.y + c];
-                                    v[c] = min(max((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2, 0), 255);
-                                }
-                            }
-                            ring_row[x] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ZERO_PIXEL;
-                        }
-                    }
-                }
-                next_row = y_hi + 1;
-                bar_sync_named(3, 128);                 // the ring rows are visible; the raw slots of rows < next_row are free
-                if (pwarp == 0) issue_until(g0 + next_row + src.n_slots);
-
-                // ---- stage 2: GEMM row m of this tile
-                const int pix = t * 128 + m;
-                const bool in_range = pix < per_frame;
-                const int py = in_range ? pix / p.P1w : 0, px = in_range ? pix % p.P1w : 0;
-                mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t *dst = s_stage + stage * C1_A_STAGE_BYTES + m * 16;
-#pragma unroll
-                for (int r = 0; r < 5; ++r) {
-                    const int row = 3 * py - 1 + r;
-                    uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
-                    if (in_range && row >= 0 && row < H) {
-                        const uint32_t *rp = s_ring + (int)((g0 + row) & (RING_ROWS - 1)) * RING_PITCH + 3 + 3 * px;
-                        const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2], w3 = rp[3], w4 = rp[4];     // (B, G, R, 0x64) of pixels 3px-1 .. 3px+3
-                        lo.x = u8x2_to_h2(__byte_perm(w0, w0, 0x3132));     // R0 G0
-                        lo.y = u8x2_to_h2(__byte_perm(w0, w1, 0x7630));     // B0 R1
-                        lo.z = u8x2_to_h2(__byte_perm(w1, w1, 0x3031));     // G1 B1
-                        lo.w = u8x2_to_h2(__byte_perm(w2, w2, 0x3132));     // R2 G2
-                        hi.x = u8x2_to_h2(__byte_perm(w2, w3, 0x7630));     // B2 R3
-                        hi.y = u8x2_to_h2(__byte_perm(w3, w3, 0x3031));     // G3 B3
-                        hi.z = u8x2_to_h2(__byte_perm(w4, w4, 0x3132));     // R4 G4
-                        hi.w = u8x2_to_h2(__byte_perm(w4, ZERO_PIXEL, 0x7430)); // B4 0   (bytes: B4, 0x64, 0x00, 0x64)
-                    }
-                    *reinterpret_cast<uint4 *>(dst + (2 * r) * 2048) = lo;
-                    *reinterpret_cast<uint4 *>(dst + (2 * r + 1) * 2048) = hi;
-                }
-                fence_proxy_async();                    // generic-proxy stores -> visible to the MMA's async-proxy reads
-                mbar_arrive(&full[stage]);
-                if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 12) {
-        // ------------------------------------------------------------------ MMA issuer
-        uint32_t stage = 0, phase = 0, acc_phase = 0;
-        const uint32_t w_addr = smem_u32(s_w), stage_addr = smem_u32(s_stage);
-        const uint32_t idesc = instr_desc_16bit(128, 3 * C, kBf16);
-        for (int f = blockIdx.x; f < p.B; f += gridDim.x) {
-            for (int t = 0; t < p.tiles_per_frame; ++t) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after_sync();
-                const uint32_t a_stage = stage_addr + stage * C1_A_STAGE_BYTES;
+    } else if (warp >= 8 && warp < 8 + UNFOLD_WARPS) {
+        // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
+        const int pwarp = warp - 8;
+        // an item = (pooled row R, sub-row, 32-column part); a pooled row has 3 * n_parts of them, dealt round-robin
+        // to the warps with a per-row rotation.  Lane constants of the integer-scale gather: byte offset of pixel 3px-1.
+        const int BS = 3 * plan.gather_step_x;
+        int next_R = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            mbar_wait(&empty[t % FR_DEPTH], ((t / FR_DEPTH) & 1) ^ 1);          // tile t - FR_DEPTH has been consumed
+            const int R_hi = min(n_frames_cta * RPF - 1, (t * 128 + 127) / P1w + 1);
+            for (int R = next_R; R <= R_hi; ++R) {
+                const int fi = R / RPF, py = R - fi * RPF;
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    mbar_wait(&acc_empty[dy], acc_phase ^ 1);
-                    tc_fence_after_sync();
-                    if (elect_one()) {
+                for (int sub = 0; sub < 3; ++sub) {
+                    const int y = 3 * py + sub;
+                    const bool real = y < H && (py < p.P1h || sub == 0);   // index P1h: row 3*P1h if the image has it, else zeros
+                    const int n = fi * Hc + y, slot = n & (n_slots - 1);
 #pragma unroll
-                        for (int ks = 0; ks < 3; ++ks) {
-                            const uint64_t da = smem_desc(a_stage + 2 * (dy + ks) * 2048, 2048, 128);
-                            const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
-                            umma_16bit(tmem_base + 3 * C * dy, da, db, idesc, ks > 0 ? 1u : 0u);
+                    for (int part = 0; part < 3; ++part) {
+                        if (part >= n_parts) continue;
+                        if (((R * 9 + sub * 3 + part) % UNFOLD_WARPS) != pwarp) continue;
+                        const int px = part * 32 + lane;
+                        uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+                        if (real) {
+                            mbar_wait(&raw_full[slot], (n >> src.log2_slots) & 1);
+                            if (px < P1w) {
+                                const uint8_t *q0 = s_raw + slot * slot_bytes;
+                                uint32_t w[5];
+                                if (GATHER) {
+                                    const int base = 3 * plan.gather_off_x + BS * (3 * px - 1);
+#pragma unroll
+                                    for (int j = 0; j < 5; ++j) {
+                                        const int b = base + BS * j;
+                                        const bool ok = (j > 0 || px > 0) && (j < 4 || 3 * px + 3 < plan.dst_w);
+                                        const uint32_t *wp = reinterpret_cast<const uint32_t *>(q0 + (ok ? (b & ~3) : 0));
+                                        const uint32_t v = __byte_perm(wp[0], wp[1], 0x3210u + (uint32_t)(b & 3) * 0x1111u);
+                                        w[j] = ok ? ((v & 0x00FFFFFFu) | ZERO_PIXEL) : ZERO_PIXEL;
+                                    }
+                                } else {
+                                    const uint8_t *q1 = q0 + (src.n_src - 1) * src.row_bytes;
+                                    const int b0 = s_yb[2 * y], b1 = s_yb[2 * y + 1];
+#pragma unroll
+                                    for (int j = 0; j < 5; ++j) w[j] = resized_word(plan, q0, q1, s_xtab, b0, b1, 3 * px - 1 + j);
+                                }
+                                lo.x = u8x2_to_h2(__byte_perm(w[0], w[0], 0x3132));     // R0 G0
+                                lo.y = u8x2_to_h2(__byte_perm(w[0], w[1], 0x7630));     // B0 R1
+                                lo.z = u8x2_to_h2(__byte_perm(w[1], w[1], 0x3031));     // G1 B1
+                                lo.w = u8x2_to_h2(__byte_perm(w[2], w[2], 0x3132));     // R2 G2
+                                hi.x = u8x2_to_h2(__byte_perm(w[2], w[3], 0x7630));     // B2 R3
+                                hi.y = u8x2_to_h2(__byte_perm(w[3], w[3], 0x3031));     // G3 B3
+                                hi.z = u8x2_to_h2(__byte_perm(w[4], w[4], 0x3132));     // R4 G4
+                                hi.w = u8x2_to_h2(__byte_perm(w[4], ZERO_PIXEL, 0x7430));   // B4 0
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&raw_empty[slot]);        // this part of the source row has been read
                         }
-                        umma_commit(&acc_full[dy]);
+                        if (px < P1w) {
+                            const int pos = (R * P1w + px) & (FR_CAP - 1);
+                            uint8_t *dst = s_ring + sub * FR_SUB + pos * 16;
+                            *reinterpret_cast<uint4 *>(dst) = lo;
+                            *reinterpret_cast<uint4 *>(dst + FR_PLANE) = hi;
+                            if (pos < 128) {                                     // mirror past the end of the ring
+                                *reinterpret_cast<uint4 *>(dst + FR_CAP * 16) = lo;
+                                *reinterpret_cast<uint4 *>(dst + FR_CAP * 16 + FR_PLANE) = hi;
+                            }
+                        }
                     }
-                    __syncwarp();
                 }
-                if (elect_one()) umma_commit(&empty[stage]);
-                __syncwarp();
-                if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
-                acc_phase ^= 1;
             }
+            next_R = R_hi + 1;
+            fence_proxy_async();                        // generic-proxy stores -> visible to the MMA's async-proxy reads
+            mbar_arrive(&full[t % FR_DEPTH]);
+        }
+    } else if (warp == F1_MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issuer
+        uint32_t acc_phase = 0;
+        const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
+        const uint32_t idesc = instr_desc_16bit(128, 3 * C, kBf16);
+        for (int t = 0; t < n_tiles; ++t) {
+            mbar_wait(&full[t % FR_DEPTH], (t / FR_DEPTH) & 1);
+            tc_fence_after_sync();
+            uint32_t a_chunk[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const int sub = (c + 2) % 3, shift = c == 0 ? -P1w : (c == 4 ? P1w : 0);
+                a_chunk[c] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
+            }
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                mbar_wait(&acc_empty[dy], acc_phase ^ 1);
+                tc_fence_after_sync();
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) {
+                        const uint64_t da = smem_desc(a_chunk[dy + ks], FR_PLANE, 128);
+                        const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
+                        umma_16bit(tmem_base + 3 * C * dy, da, db, idesc, ks > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&acc_full[dy]);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(&empty[t % FR_DEPTH]);
+            __syncwarp();
+            acc_phase ^= 1;
         }
     } else {
         // ------------------------------------------------------------------ epilogue
         const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
         const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + ch0;
         uint32_t acc_phase = 0;
-        for (int f = blockIdx.x; f < p.B; f += gridDim.x) {
-            zero_pads(p.out, CG, f, f + 1, threadIdx.x, EPI_WARPS * 32);
-            for (int t = 0; t < p.tiles_per_frame; ++t) {
-                const int pix = t * 128 + m;
-                const bool valid = pix < per_frame;
-                const int Y = valid ? pix / p.P1w : 0, X = valid ? pix % p.P1w : 0;
-                float v[CH];
-                epilogue_tile<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, s_par, ch0, v);
-                if (valid) store_pixel<C>(p.out, f, Y, X, ch0, v);
-                acc_phase ^= 1;
-            }
+        for (int fi = 0; fi < n_frames_cta; ++fi) zero_pads(p.out, CG, blockIdx.x + fi * gridDim.x, blockIdx.x + fi * gridDim.x + 1, threadIdx.x, EPI_WARPS * 32);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int g = t * 128 + m, R = g / P1w, X = g - R * P1w;
+            const int fi = R / RPF, Y = R - fi * RPF;
+            const bool valid = fi < n_frames_cta && Y < p.P1h;
+            float v[CH];
+            epilogue_tile<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, s_par, ch0, v);
+            if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
+            acc_phase ^= 1;
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == F1_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ input packing
@@ -1036,7 +1055,8 @@ int upload_bytes(cutdet_net *net, const void *host, size_t bytes, void **dev) {
 template <int C>
 int set_smem_limits() {
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1Smem<C>::total));
-    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, F1Smem<C>::total));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F1Smem<C>::total));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F1Smem<C>::total));
     CUTDET_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, MidSmem<C>::total));
     return CUTDET_OK;
 }
@@ -1057,7 +1077,8 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src, cudaStream_t s
     const int grid = p.B < sm_count() ? p.B : sm_count();
     {
         KernelScope scope("conv1_fused_tc", stream);
-        conv1_fused_tc_kernel<C><<<grid, 416, F1Smem<C>::total, stream>>>(p, src);
+        if (src.plan.gather_step_x > 0) conv1_fused_tc_kernel<C, true><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
+        else conv1_fused_tc_kernel<C, false><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
     }
     CUTDET_LAUNCH_CHECK("conv1_fused_tc_kernel");
     return CUTDET_OK;
@@ -1074,9 +1095,9 @@ bool fused_source(const cutdet_resize_plan *plan, const cutdet_frames *frames, c
     if ((long long)rows * frames->row_pitch >= (1LL << 31)) return false;
     const int n_src = (h.gather_step_x > 0 || h.mode == RESIZE_COPY) ? 1 : 2;
     const long long slot = n_src * row_bytes;
-    long long n_slots = RAW_BYTES / slot;
-    if (n_slots > RAW_SLOTS_MAX) n_slots = RAW_SLOTS_MAX;
-    if (n_slots < 8) return false;
+    int log2_slots = 0;
+    while ((2LL << log2_slots) * slot <= RAW_BYTES && (2 << log2_slots) <= RAW_SLOTS_MAX) ++log2_slots;
+    if (slot > RAW_BYTES || log2_slots < 1) return false;
     out->plan = h;
     out->frames = frames->frames_dev;
     out->frame_stride = frames->frame_stride;
@@ -1084,7 +1105,7 @@ bool fused_source(const cutdet_resize_plan *plan, const cutdet_frames *frames, c
     out->compact = frames->row_map_compact;
     out->n_src = n_src;
     out->row_bytes = (int)row_bytes;
-    out->n_slots = (int)n_slots;
+    out->log2_slots = log2_slots;
     return true;
 }
 
