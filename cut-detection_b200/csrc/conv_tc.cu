@@ -61,7 +61,8 @@ constexpr float kPixelScale = kBf16 ? 255.f : 255.f / 256.f;    // layer-1 input
 constexpr float kW1Scale = kBf16 ? 1.f / 255.f : 256.f / 255.f; // ... and its weights absorb the inverse
 constexpr float kActMax = kBf16 ? 3.0e38f : 65504.f;
 
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return kBf16 ? pack_bf16x2(lo, hi) : pack_f16x2(lo, hi); }
+// two floats -> packed 16-bit operands; fp16 saturates to +-65504 in the conversion itself (F2FP.SATFINITE)
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return kBf16 ? pack_bf16x2(lo, hi) : pack_f16x2_sat(lo, hi); }
 
 constexpr int SUB_BATCH = 148;          // frames per pass through conv1/conv2: their activations stay L2-resident
 constexpr int GROUP = 4;                // sub-batches whose layer-2 maps are gathered for ONE conv3 launch (fills the SMs)
@@ -137,7 +138,7 @@ __device__ __forceinline__ void tmem_ld_ch(uint32_t taddr, float (&v)[CH]) {
 
 // One tile's epilogue for this thread: its TMEM lane (a pooled pixel), CH = C/2 of the channels.  Block row dy of the
 // accumulator (columns [3C*dy, 3C*dy + 3C) = the three dx positions) is read as soon as its MMAs have committed and is
-// handed back right after the read.  Returns max over the 9 positions, + bias, ReLU, BatchNorm affine, clamped.
+// handed back right after the read.  Returns max over the 9 positions, + bias, ReLU, BatchNorm affine (the 16-bit store saturates).
 template <int C>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_thread /* lane quarter + this thread's first column */,
                                               uint64_t *acc_full, uint64_t *acc_empty, uint32_t acc_phase, int lane,
@@ -171,10 +172,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_thread /* lane quart
 #pragma unroll
     for (int i = 0; i < CH / 4; ++i) {
         const float4 b = bias4[i], s = scale4[i], t = shift4[i];
-        run[4 * i + 0] = fminf(fmaxf(fmaf(fmaxf(run[4 * i + 0] + b.x, 0.f), s.x, t.x), -kActMax), kActMax);
-        run[4 * i + 1] = fminf(fmaxf(fmaf(fmaxf(run[4 * i + 1] + b.y, 0.f), s.y, t.y), -kActMax), kActMax);
-        run[4 * i + 2] = fminf(fmaxf(fmaf(fmaxf(run[4 * i + 2] + b.z, 0.f), s.z, t.z), -kActMax), kActMax);
-        run[4 * i + 3] = fminf(fmaxf(fmaf(fmaxf(run[4 * i + 3] + b.w, 0.f), s.w, t.w), -kActMax), kActMax);
+        run[4 * i + 0] = fmaf(fmaxf(run[4 * i + 0] + b.x, 0.f), s.x, t.x);
+        run[4 * i + 1] = fmaf(fmaxf(run[4 * i + 1] + b.y, 0.f), s.y, t.y);
+        run[4 * i + 2] = fmaf(fmaxf(run[4 * i + 2] + b.z, 0.f), s.z, t.z);
+        run[4 * i + 3] = fmaf(fmaxf(run[4 * i + 3] + b.w, 0.f), s.w, t.w);
     }
 }
 
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     if (threadIdx.x == 0) {
         for (int s = 0; s < FR_DEPTH; ++s) { mbar_init(&full[s], 32 * UNFOLD_WARPS); mbar_init(&empty[s], 1); }
         for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], EPI_WARPS); }
-        for (int s = 0; s < RAW_SLOTS_MAX; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], n_parts); }
+        for (int s = 0; s < RAW_SLOTS_MAX; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
         fence_barrier_init();
     }
     if (warp == F1_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -658,71 +659,72 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     } else if (warp >= 8 && warp < 8 + UNFOLD_WARPS) {
         // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
         const int pwarp = warp - 8;
-        // an item = (pooled row R, sub-row, 32-column part); a pooled row has 3 * n_parts of them, dealt round-robin
-        // to the warps with a per-row rotation.  Lane constants of the integer-scale gather: byte offset of pixel 3px-1.
+        // A resized row goes to ONE warp, which unfolds its n_parts 32-column parts.  The warp is a function of the row's raw
+        // slot, so consecutive uses of a slot's mbarriers are always waited on by the same warp, in order: a warp that
+        // skipped a phase could otherwise mistake "two phases behind" for "complete" (mbarrier waits see one parity bit).
+        // Zero rows (no source row) rotate over the warps.  Lane constants of the integer-scale gather: byte offset of pixel 3px-1.
         const int BS = 3 * plan.gather_step_x;
-        int next_R = 0;
+        const int owner_mask = (n_slots < UNFOLD_WARPS ? n_slots : UNFOLD_WARPS) - 1;
+        int next_R = 0, fi = 0, py = 0;                     // (fi, py) <-> next_R
         for (int t = 0; t < n_tiles; ++t) {
             mbar_wait(&empty[t % FR_DEPTH], ((t / FR_DEPTH) & 1) ^ 1);          // tile t - FR_DEPTH has been consumed
             const int R_hi = min(n_frames_cta * RPF - 1, (t * 128 + 127) / P1w + 1);
-            for (int R = next_R; R <= R_hi; ++R) {
-                const int fi = R / RPF, py = R - fi * RPF;
+            for (int R = next_R; R <= R_hi; ++R, ++py) {
+              if (py == RPF) { py = 0; ++fi; }
 #pragma unroll
-                for (int sub = 0; sub < 3; ++sub) {
-                    const int y = 3 * py + sub;
-                    const bool real = y < H && (py < p.P1h || sub == 0);   // index P1h: row 3*P1h if the image has it, else zeros
-                    const int n = fi * Hc + y, slot = n & (n_slots - 1);
+              for (int sub = 0; sub < 3; ++sub) {
+                const int y = 3 * py + sub;
+                const bool real = y < H && (py < p.P1h || sub == 0);   // index P1h: row 3*P1h if the image has it, else zeros
+                const int n = fi * Hc + y, slot = n & (n_slots - 1);
+                if ((real ? (n & owner_mask) : ((R + sub) & (UNFOLD_WARPS - 1))) != pwarp) continue;
+                const uint8_t *q0 = s_raw + slot * slot_bytes;
+                if (real) mbar_wait(&raw_full[slot], (n >> src.log2_slots) & 1);
+                for (int part = 0; part < n_parts; ++part) {
+                    const int px = part * 32 + lane;
+                    uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+                    if (real && px < P1w) {
+                        uint32_t w[5];
+                        if (GATHER) {
+                            const int base = 3 * plan.gather_off_x + BS * (3 * px - 1);
 #pragma unroll
-                    for (int part = 0; part < 3; ++part) {
-                        if (part >= n_parts) continue;
-                        if (((R * 9 + sub * 3 + part) % UNFOLD_WARPS) != pwarp) continue;
-                        const int px = part * 32 + lane;
-                        uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
-                        if (real) {
-                            mbar_wait(&raw_full[slot], (n >> src.log2_slots) & 1);
-                            if (px < P1w) {
-                                const uint8_t *q0 = s_raw + slot * slot_bytes;
-                                uint32_t w[5];
-                                if (GATHER) {
-                                    const int base = 3 * plan.gather_off_x + BS * (3 * px - 1);
-#pragma unroll
-                                    for (int j = 0; j < 5; ++j) {
-                                        const int b = base + BS * j;
-                                        const bool ok = (j > 0 || px > 0) && (j < 4 || 3 * px + 3 < plan.dst_w);
-                                        const uint32_t *wp = reinterpret_cast<const uint32_t *>(q0 + (ok ? (b & ~3) : 0));
-                                        const uint32_t v = __byte_perm(wp[0], wp[1], 0x3210u + (uint32_t)(b & 3) * 0x1111u);
-                                        w[j] = ok ? ((v & 0x00FFFFFFu) | ZERO_PIXEL) : ZERO_PIXEL;
-                                    }
-                                } else {
-                                    const uint8_t *q1 = q0 + (src.n_src - 1) * src.row_bytes;
-                                    const int b0 = s_yb[2 * y], b1 = s_yb[2 * y + 1];
-#pragma unroll
-                                    for (int j = 0; j < 5; ++j) w[j] = resized_word(plan, q0, q1, s_xtab, b0, b1, 3 * px - 1 + j);
-                                }
-                                lo.x = u8x2_to_h2(__byte_perm(w[0], w[0], 0x3132));     // R0 G0
-                                lo.y = u8x2_to_h2(__byte_perm(w[0], w[1], 0x7630));     // B0 R1
-                                lo.z = u8x2_to_h2(__byte_perm(w[1], w[1], 0x3031));     // G1 B1
-                                lo.w = u8x2_to_h2(__byte_perm(w[2], w[2], 0x3132));     // R2 G2
-                                hi.x = u8x2_to_h2(__byte_perm(w[2], w[3], 0x7630));     // B2 R3
-                                hi.y = u8x2_to_h2(__byte_perm(w[3], w[3], 0x3031));     // G3 B3
-                                hi.z = u8x2_to_h2(__byte_perm(w[4], w[4], 0x3132));     // R4 G4
-                                hi.w = u8x2_to_h2(__byte_perm(w[4], ZERO_PIXEL, 0x7430));   // B4 0
+                            for (int j = 0; j < 5; ++j) {
+                                const int b = base + BS * j;
+                                const bool ok = (j > 0 || px > 0) && (j < 4 || 3 * px + 3 < plan.dst_w);
+                                const uint32_t *wp = reinterpret_cast<const uint32_t *>(q0 + (ok ? (b & ~3) : 0));
+                                const uint32_t v = __byte_perm(wp[0], wp[1], 0x3210u + (uint32_t)(b & 3) * 0x1111u);
+                                w[j] = ok ? ((v & 0x00FFFFFFu) | ZERO_PIXEL) : ZERO_PIXEL;
                             }
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&raw_empty[slot]);        // this part of the source row has been read
+                        } else {
+                            const uint8_t *q1 = q0 + (src.n_src - 1) * src.row_bytes;
+                            const int b0 = s_yb[2 * y], b1 = s_yb[2 * y + 1];
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) w[j] = resized_word(plan, q0, q1, s_xtab, b0, b1, 3 * px - 1 + j);
                         }
-                        if (px < P1w) {
-                            const int pos = (R * P1w + px) & (FR_CAP - 1);
-                            uint8_t *dst = s_ring + sub * FR_SUB + pos * 16;
-                            *reinterpret_cast<uint4 *>(dst) = lo;
-                            *reinterpret_cast<uint4 *>(dst + FR_PLANE) = hi;
-                            if (pos < 128) {                                     // mirror past the end of the ring
-                                *reinterpret_cast<uint4 *>(dst + FR_CAP * 16) = lo;
-                                *reinterpret_cast<uint4 *>(dst + FR_CAP * 16 + FR_PLANE) = hi;
-                            }
+                        lo.x = u8x2_to_h2(__byte_perm(w[0], w[0], 0x3132));     // R0 G0
+                        lo.y = u8x2_to_h2(__byte_perm(w[0], w[1], 0x7630));     // B0 R1
+                        lo.z = u8x2_to_h2(__byte_perm(w[1], w[1], 0x3031));     // G1 B1
+                        lo.w = u8x2_to_h2(__byte_perm(w[2], w[2], 0x3132));     // R2 G2
+                        hi.x = u8x2_to_h2(__byte_perm(w[2], w[3], 0x7630));     // B2 R3
+                        hi.y = u8x2_to_h2(__byte_perm(w[3], w[3], 0x3031));     // G3 B3
+                        hi.z = u8x2_to_h2(__byte_perm(w[4], w[4], 0x3132));     // R4 G4
+                        hi.w = u8x2_to_h2(__byte_perm(w[4], ZERO_PIXEL, 0x7430));   // B4 0
+                    }
+                    if (px < P1w) {
+                        const int pos = (R * P1w + px) & (FR_CAP - 1);
+                        uint8_t *dst = s_ring + sub * FR_SUB + pos * 16;
+                        *reinterpret_cast<uint4 *>(dst) = lo;
+                        *reinterpret_cast<uint4 *>(dst + FR_PLANE) = hi;
+                        if (pos < 128) {                                     // mirror past the end of the ring
+                            *reinterpret_cast<uint4 *>(dst + FR_CAP * 16) = lo;
+                            *reinterpret_cast<uint4 *>(dst + FR_CAP * 16 + FR_PLANE) = hi;
                         }
                     }
                 }
+                if (real) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&raw_empty[slot]);            // the source row has been read
+                }
+              }
             }
             next_R = R_hi + 1;
             fence_proxy_async();                        // generic-proxy stores -> visible to the MMA's async-proxy reads
@@ -767,14 +769,17 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + ch0;
         uint32_t acc_phase = 0;
         for (int fi = 0; fi < n_frames_cta; ++fi) zero_pads(p.out, CG, blockIdx.x + fi * gridDim.x, blockIdx.x + fi * gridDim.x + 1, threadIdx.x, EPI_WARPS * 32);
+        int X = m % P1w, Y = m / P1w, fi = 0;              // position 128 t + m = ((fi * RPF + Y) * P1w + X), advanced tile by tile
+        while (Y >= RPF) { Y -= RPF; ++fi; }
         for (int t = 0; t < n_tiles; ++t) {
-            const int g = t * 128 + m, R = g / P1w, X = g - R * P1w;
-            const int fi = R / RPF, Y = R - fi * RPF;
             const bool valid = fi < n_frames_cta && Y < p.P1h;
             float v[CH];
             epilogue_tile<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, s_par, ch0, v);
             if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
             acc_phase ^= 1;
+            X += 128;
+            while (X >= P1w) { X -= P1w; ++Y; }
+            while (Y >= RPF) { Y -= RPF; ++fi; }
         }
     }
     tc_fence_before_sync();
@@ -915,14 +920,27 @@ __global__ void __launch_bounds__(128) head_fc1_kernel(const float *__restrict__
     for (int k0 = half * HEAD_KT; k0 < n_feat; k0 += 2 * HEAD_KT) {
         const int kn = min(HEAD_KT, n_feat - k0);
         bar_sync_named(1 + half, 64);                 // the previous slab has been consumed
-        for (int i = tid; i < HEAD_FRAMES * HEAD_KT; i += 64) {
-            const int f = i / HEAD_KT, k = i % HEAD_KT;            // coalesced along k
-            sa[k * HEAD_PITCH + f] = (f0 + f < batch && k < kn) ? act3[(size_t)(f0 + f) * n_feat + k0 + k] : 0.f;
-        }
-        for (int i = tid; i < HEAD_KT * 8; i += 64) {
-            const int k = i >> 3;
-            reinterpret_cast<float4 *>(sw)[i] = k < kn ? reinterpret_cast<const float4 *>(w_folded)[(size_t)(k0 + k) * 8 + (i & 7)]
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        {   // all the global loads of the slab first (they are independent), then the shared-memory stores
+            constexpr int NA = HEAD_FRAMES * HEAD_KT / 64, NW = HEAD_KT * 8 / 64;
+            float ta[NA];
+            float4 tw[NW];
+#pragma unroll
+            for (int j = 0; j < NA; ++j) {
+                const int i = tid + 64 * j, f = i / HEAD_KT, k = i % HEAD_KT;          // coalesced along k
+                ta[j] = (f0 + f < batch && k < kn) ? __ldg(&act3[(size_t)(f0 + f) * n_feat + k0 + k]) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+                const int i = tid + 64 * j, k = i >> 3;
+                tw[j] = k < kn ? __ldg(&reinterpret_cast<const float4 *>(w_folded)[(size_t)(k0 + k) * 8 + (i & 7)]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < NA; ++j) {
+                const int i = tid + 64 * j;
+                sa[(i % HEAD_KT) * HEAD_PITCH + i / HEAD_KT] = ta[j];
+            }
+#pragma unroll
+            for (int j = 0; j < NW; ++j) reinterpret_cast<float4 *>(sw)[tid + 64 * j] = tw[j];
         }
         bar_sync_named(1 + half, 64);
 #pragma unroll 8

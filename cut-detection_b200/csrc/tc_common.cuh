@@ -182,6 +182,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);
 }
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {      // clamps to +-65504 instead of overflowing to inf
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     __half2 v = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);
