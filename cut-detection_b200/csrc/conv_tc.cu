@@ -42,6 +42,7 @@
 // against the fp32 reference the logits move by <= 0.015 with fp16 where bf16 moved them by up to 0.25 (an all-stripes
 // frame, where weight rounding errors add coherently); tolerance stated in tests/test_gpu_net.py.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -59,7 +60,6 @@ namespace {
 constexpr bool kBf16 = false;           // operand format of the MMAs and of the stored activations (false = fp16)
 constexpr float kPixelScale = kBf16 ? 255.f : 255.f / 256.f;    // layer-1 input = x * kPixelScale (u8 pixels stay exact)
 constexpr float kW1Scale = kBf16 ? 1.f / 255.f : 256.f / 255.f; // ... and its weights absorb the inverse
-constexpr float kActMax = kBf16 ? 3.0e38f : 65504.f;
 
 // two floats -> packed 16-bit operands; fp16 saturates to +-65504 in the conversion itself (F2FP.SATFINITE)
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) { return kBf16 ? pack_bf16x2(lo, hi) : pack_f16x2_sat(lo, hi); }
@@ -230,6 +230,7 @@ struct MidParams {
     OutSpec out;
     const uint4 *w_packed;  // [ky][c/8][3C rows: kx=2 | kx=1 | kx=0][8] 16-bit
     const float *bias, *scale, *shift;
+    long long *timeline;    // debug: clock64 stamps of CTA 0 (null = off)
 };
 
 template <int C>
@@ -259,6 +260,8 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
     float *s_par = reinterpret_cast<float *>(s_tail + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[0] = clock64();
+    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[128 + 4 * blockIdx.x] = g; }
 
     // one-time setup
     for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
@@ -296,10 +299,19 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
         // ------------------------------------------------------------------ MMA issuer
         uint32_t stage = 0, phase = 0, acc_phase = 0;
         const uint32_t w_addr = smem_u32(s_w), stage_addr = smem_u32(s_stage);
+        long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;
+        int tli = 1;
+        if (tl && lane == 0) tl[tli] = clock64();
+        ++tli;
+        bool first_stamp = true;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             for (int ks = 0; ks < KS; ++ks) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after_sync();
+                if (tl && lane == 0) tl[tli] = clock64();      // stage data present
+                ++tli;
+                if (p.timeline && first_stamp && lane == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[128 + 4 * blockIdx.x + 2] = g; }
+                first_stamp = false;
                 const uint32_t a_stage = stage_addr + stage * MID_STAGE_BYTES;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
@@ -333,6 +345,8 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
                 }
                 if (elect_one()) umma_commit(&empty[stage]);  // frees the stage once these MMAs have read it
                 __syncwarp();
+                if (tl && lane == 0) tl[tli] = clock64();      // stage issued
+                ++tli;
                 if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
             }
             acc_phase ^= 1;
@@ -358,8 +372,11 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
             epilogue_tile<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, s_par, ch0, v);
             if (valid) store_pixel<C>(p.out, b, Y, X, ch0, v);
             acc_phase ^= 1;
+            if (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[64 + tile / gridDim.x] = clock64();   // tile stored
         }
     }
+    if (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[63] = clock64();
+    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[128 + 4 * blockIdx.x + 1] = g; }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -641,7 +658,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
 
     if (warp == F1_LOAD_WARP) {
         // ------------------------------------------------------------------ loader: source rows -> raw ring
-        int n = 0;                                          // resized rows loaded so far (frame-major)
+        int n = 0;                                          // resized rows loaded so far (frame-major: n = fi * Hc + y)
         for (int fi = 0; fi < n_frames_cta; ++fi) {
             const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
             for (int y = 0; y < Hc; ++y, ++n) {
@@ -1185,6 +1202,31 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     p2.out = OutSpec{ws + w.act2, 0, w.gtot2, g.PW2, g.FP2, g.Q2h, slot0, g.P2h, g.P2w};
     p2.w_packed = reinterpret_cast<const uint4 *>(tc->d_w2);
     p2.bias = net->conv[1].d_bias; p2.scale = net->conv[1].d_scale; p2.shift = net->conv[1].d_shift;
+    static const bool want_timeline = getenv("CUTDET_TIMELINE") != nullptr;     // debug aid: clock stamps of CTA 0, printed once
+    static int timeline_runs = 0;
+    if (want_timeline && nb >= 148 && timeline_runs++ == 20) {
+        long long *d = nullptr, h[128 + 4 * 148];
+        CUTDET_CUDA(cudaMalloc(&d, sizeof(h)));
+        CUTDET_CUDA(cudaMemsetAsync(d, 0, sizeof(h), stream));
+        p2.timeline = d;
+        if (int rc = launch_mid<C>(map1, p2, "conv2_tc", stream)) return rc;
+        CUTDET_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        CUTDET_CUDA(cudaStreamSynchronize(stream));
+        fprintf(stderr, "conv2 timeline (cycles since kernel entry): mma-loop-start %lld |", h[1] - h[0]);
+        for (int i = 2; i < 63 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+        fprintf(stderr, " | epilogue tiles:");
+        for (int i = 64; i < 96 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+        fprintf(stderr, " | end %lld\n", h[63] - h[0]);
+        long long t0 = h[128];
+        for (int c = 0; c < 148; ++c) if (h[128 + 4 * c] && h[128 + 4 * c] < t0) t0 = h[128 + 4 * c];
+        fprintf(stderr, "conv2 timeline per CTA (ns since first CTA entry: entry/first-data/end):");
+        for (int c = 0; c < 148; c += 7) fprintf(stderr, " [%d] %lld/%lld/%lld", c, h[128 + 4 * c] - t0, h[128 + 4 * c + 2] - t0, h[128 + 4 * c + 1] - t0);
+        long long worst = 0;
+        for (int c = 0; c < 148; ++c) if (h[128 + 4 * c + 1] - t0 > worst) worst = h[128 + 4 * c + 1] - t0;
+        fprintf(stderr, " | last end %lld\n", worst);
+        cudaFree(d);
+        return CUTDET_OK;
+    }
     return launch_mid<C>(map1, p2, "conv2_tc", stream);
 }
 

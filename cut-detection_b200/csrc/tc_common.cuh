@@ -95,6 +95,11 @@ __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gmem_sr
                  : "memory");
 }
 
+// L2 prefetch of a contiguous range (no destination): hides HBM latency ahead of a bulk_load_1d of the same bytes.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- cp.async (LDGSTS)
 // 16-byte global->shared copy; src_bytes == 0 zero-fills the destination (used for the conv's zero padding).
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, uint32_t src_bytes) {

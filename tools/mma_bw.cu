@@ -27,22 +27,67 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 }
 
 // pattern p: which (N, D column, A offset) sequence one "round" of 15 MMAs uses
-template <int P>
-__global__ void __launch_bounds__(32) bench(int rounds, long long *cycles) {
+template <int P, int CONT>
+__global__ void __launch_bounds__(192) bench(int rounds, long long *cycles, const uint8_t *gsrc) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, lbar;
+    __shared__ volatile int done;
     __shared__ uint32_t slot;
-    for (int i = threadIdx.x; i < 98304 / 16; i += 32) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 98304 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
+        done = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&lbar)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncwarp();
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp >= 1 && warp <= 4) {            // contention: TMEM loads from columns the MMAs do not touch
+        if (CONT & 1) {
+            const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16) + 448;
+            uint32_t acc = 0;
+            while (!done) {
+                uint32_t r[16];
+                for (int j = 0; j < 3; ++j)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(base + 16 * j) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                acc ^= r[0];
+            }
+            if (acc == 0x1234567u) cycles[1] = acc;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        return;
+    }
+    if (warp == 5) {                          // contention: bulk copies global -> shared into a region the MMAs do not read
+        if (CONT & 2) {
+            uint32_t ph = 0;
+            while (!done) {
+                if (elect_one()) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&lbar)), "r"(3 * 6144u) : "memory");
+                    for (int j = 0; j < 3; ++j)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(smem_u32(smem) + 73728 + j * 6144), "l"(gsrc + (size_t)((ph * 3 + j) % 512) * 6144), "r"(6144u), "r"(smem_u32(&lbar)) : "memory");
+                }
+                __syncwarp();
+                uint32_t ok = 0;
+                while (!ok) asm volatile("{\n.reg .pred P;\nmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(ok) : "r"(smem_u32(&lbar)), "r"(ph & 1) : "memory");
+                ++ph;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        return;
+    }
     const uint32_t tm = slot;
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 65536;
     long long t0 = 0, t1 = 0;
@@ -77,24 +122,28 @@ __global__ void __launch_bounds__(32) bench(int rounds, long long *cycles) {
         }
         t1 = clock64();
     }
-    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+    if (threadIdx.x == 0) { cycles[0] = t1 - t0; done = 1; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncwarp();
+    __syncthreads();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
 }
 
-template <int P>
+template <int P, int CONT = 0>
 void run(const char *what, double ideal_per_round) {
     long long *d, h = 0;
-    cudaMalloc(&d, 8);
-    cudaFuncSetAttribute(bench<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+    uint8_t *g;
+    cudaMalloc(&d, 16);
+    cudaMalloc(&g, 512 * 6144);
+    cudaMemset(g, 0, 512 * 6144);
+    cudaFuncSetAttribute(bench<P, CONT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
     const int rounds = 200;
-    bench<P><<<1, 32, 98304>>>(rounds, d);
+    bench<P, CONT><<<1, 192, 98304>>>(rounds, d, g);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
     printf("P%d %-52s %8lld cycles  %6.1f per MMA  (math floor %.1f per MMA)  %s\n", P, what, h, (double)h / (rounds * 15),
            ideal_per_round / 15, cudaGetErrorString(e));
     cudaFree(d);
+    cudaFree(g);
 }
 
 int main() {
@@ -108,5 +157,9 @@ int main() {
     run<7>("conv_mid round as issued (shape, D, A all move)", 3 * (72 + 48 + 48 + 24 + 24.0));
     run<8>("same MMAs sorted by shape", 3 * (72 + 48 + 48 + 24 + 24.0));
     run<9>("N=144, A address moves", 15 * 72.0);
+    run<7, 1>("conv_mid round + 4 warps of TMEM loads", 3 * (72 + 48 + 48 + 24 + 24.0));
+    run<7, 2>("conv_mid round + bulk copies into smem", 3 * (72 + 48 + 48 + 24 + 24.0));
+    run<7, 3>("conv_mid round + both", 3 * (72 + 48 + 48 + 24 + 24.0));
+    run<0, 3>("N=144 + both", 15 * 72.0);
     return 0;
 }
