@@ -45,6 +45,7 @@
 #include <stdlib.h>
 
 #include <map>
+#include <vector>
 #include <mutex>
 #include <tuple>
 
@@ -390,6 +391,7 @@ struct Conv1Params {
     OutSpec out;
     const uint4 *w_packed;  // [ky][half][3C rows: dx=0 | dx=1 | dx=2][8] 16-bit, taps scaled by kW1Scale
     const float *bias, *scale, *shift;
+    long long *timeline;    // debug: clock64 stamps of CTA 0 (null = off)
 };
 
 template <int C>
@@ -528,7 +530,6 @@ __global__ void __launch_bounds__(416, 1) conv1_tc_kernel(const Conv1Params p) {
 //                        of sub-ring {2, 0, 1, 2, 0}[c]: for a whole tile that is 128 CONSECUTIVE 16-byte entries, i.e. a
 //                        K-major UMMA operand at a plain offset.  Positions wrap at FR_CAP; the first 128 are mirrored past
 //                        the end so a window never straddles the wrap.
-constexpr int FR_DEPTH = 4;                  // tiles in flight between the unfold warps and the MMAs
 constexpr int FR_CAP = 1024;                 // positions per sub-ring (a power of two)
 constexpr int FR_PLANE = (FR_CAP + 128) * 16;            // bytes of one k-half plane incl. the mirror
 constexpr int FR_SUB = 2 * FR_PLANE;
@@ -594,13 +595,51 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
     return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ZERO_PIXEL;
 }
 
-// 576 threads: warps 0..7 = epilogue, 8..15 = unfold, 16 = MMA issuer (+ TMEM alloc), 17 = loader.
+// 672 threads: warps 0..7 = epilogue, 8..15 = unfold, 16 = MMA issuer (+ TMEM alloc), 17..20 = loaders.
+//
+// The four stages run DECOUPLED, each at its own pace, joined by two rings:
+//   loaders   rows of the source frame -> raw ring by cp.async.bulk, row n issued by loader n % 4: ONE issuing thread sustains a
+//             3,840-byte row per ~370 cycles (10 bytes/clock), four reach HBM speed (tools/hbm_rows.cu).  raw_full[slot]
+//             counts the bytes, raw_empty[slot] the reader's release, s_rows_issued[loader] says how far each loader is:
+//             a reader first checks that ITS row has been issued, because an mbarrier wait sees one parity bit and a reader
+//             that is a whole ring ahead would otherwise take the previous row's phase for its own.
+//   unfold    resized row u = 3R + sub goes to warp u % 8, which publishes its progress in s_rows_done[warp] (a monotone
+//             counter, st.release after fence.proxy.async); it may run ahead of the MMAs by the capacity of the operand ring
+//             and waits on the monotone s_tiles_done before overwriting positions an unfinished tile still reads.
+//   MMA       tile t needs every row u <= 3 * ((128t + 127) / P1w + 1): lane w polls s_rows_done[w].
+//   epilogue  unchanged (three accumulator block rows with full/empty mbarriers).
+// Counters instead of per-tile mbarriers: a row is produced by ONE warp, tiles need rows from all of them, and a warp must never
+// have to wait for a tile it contributes nothing to (the lock-step version spent 2/3 of its time in such waits).
 // GATHER: the resize is out[y][x] = src[off_y + y*step_y][off_x + x*step_x] (every second tap has zero weight).
-constexpr int UNFOLD_WARPS = 8, F1_MMA_WARP = 8 + UNFOLD_WARPS, F1_LOAD_WARP = 9 + UNFOLD_WARPS, F1_THREADS = 32 * (10 + UNFOLD_WARPS);
+constexpr int UNFOLD_WARPS = 8, LOADER_WARPS = 4 /* 1, 2 or 4 */, F1_MMA_WARP = 8 + UNFOLD_WARPS, F1_LOAD_WARP0 = 9 + UNFOLD_WARPS;
+constexpr int F1_THREADS = 32 * (9 + UNFOLD_WARPS + LOADER_WARPS);
+
+__device__ __forceinline__ void st_release_shared(int *p, int v) {
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_shared(const int *p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+// Sixteen halves of one K-chunk from five (B, G, R, 0x64) words: RGB of pixels 0..4, then one zero.
+__device__ __forceinline__ void chunk_from_words(const uint32_t (&w)[5], uint4 &lo, uint4 &hi) {
+    lo.x = u8x2_to_h2(__byte_perm(w[0], w[0], 0x3132));     // R0 G0
+    lo.y = u8x2_to_h2(__byte_perm(w[0], w[1], 0x7630));     // B0 R1
+    lo.z = u8x2_to_h2(__byte_perm(w[1], w[1], 0x3031));     // G1 B1
+    lo.w = u8x2_to_h2(__byte_perm(w[2], w[2], 0x3132));     // R2 G2
+    hi.x = u8x2_to_h2(__byte_perm(w[2], w[3], 0x7630));     // B2 R3
+    hi.y = u8x2_to_h2(__byte_perm(w[3], w[3], 0x3031));     // G3 B3
+    hi.z = u8x2_to_h2(__byte_perm(w[4], w[4], 0x3132));     // R4 G4
+    hi.w = u8x2_to_h2(__byte_perm(w[4], ZERO_PIXEL, 0x7430));   // B4 0
+}
+
 template <int C, bool GATHER>
 __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Conv1Params p, const FusedSrc src) {
     using S = F1Smem<C>;
     constexpr int CG = C / 8, CH = C / 2;
+    constexpr int NP = (F_MAX_DST / 3 + 31) / 32;                               // 32-column parts of a resized row (P1w <= 85)
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *s_w = smem;
     uint8_t *s_ring = smem + S::OFF_RING;
@@ -608,27 +647,30 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     int *s_rowoff = reinterpret_cast<int *>(smem + S::OFF_TAB);               // [y][2]
     int *s_yb = s_rowoff + 2 * F_MAX_DST;                                       // [y][2]: b0, b1
     int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);              // [x]: 3*x0, 3*x1, a0, a1
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);           // [FR_DEPTH] tile's rows are in the ring
-    uint64_t *empty = full + FR_DEPTH;                                          // [FR_DEPTH] tile's MMAs have read them
-    uint64_t *acc_full = empty + FR_DEPTH;
+    uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);
     uint64_t *acc_empty = acc_full + 3;
     uint64_t *raw_full = acc_empty + 3;                                         // [RAW_SLOTS_MAX]
     uint64_t *raw_empty = raw_full + RAW_SLOTS_MAX;                             // [RAW_SLOTS_MAX]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + RAW_SLOTS_MAX);
+    int *s_rows_done = reinterpret_cast<int *>(tmem_slot + 2);                  // [UNFOLD_WARPS] rows finished by each unfold warp
+    int *s_tiles_done = s_rows_done + UNFOLD_WARPS;                             // tiles whose MMAs have completed
+    int *s_rows_issued = s_tiles_done + 1;                                      // [LOADER_WARPS] rows issued by each loader
     float *s_par = reinterpret_cast<float *>(smem + S::OFF_PAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ResizePlanDev &plan = src.plan;
     const int H = p.H, P1w = p.P1w, RPF = p.P1h + 1;          // pooled rows per frame incl. the zero row
     const int Hc = min(H, 3 * p.P1h + 1);                     // resized rows the conv reads (row 3*P1h only if it exists)
-    const int n_parts = (P1w + 31) / 32;
     const int n_frames_cta = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_tiles = (n_frames_cta * RPF * P1w + 127) / 128;
+    const int total_u = 3 * n_frames_cta * RPF;               // resized rows incl. the zero rows, u = 3R + sub
     const int n_slots = 1 << src.log2_slots, slot_bytes = src.n_src * src.row_bytes;
 
     for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = p.bias[i]; s_par[C + i] = p.scale[i]; s_par[2 * C + i] = p.shift[i]; }
-    for (int i = threadIdx.x; i < 3 * FR_SUB / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_ring)[i] = make_uint4(0, 0, 0, 0);
+    // The only positions read before they are written: the row above the first frame (tile 0's view shifted by -P1w).
+    for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
+        reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] = make_uint4(0, 0, 0, 0);
     for (int y = threadIdx.x; y < H; y += blockDim.x) {
         int r0, r1, b0 = 2048, b1 = 0;
         if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
@@ -643,9 +685,9 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     }
     if (plan.mode == RESIZE_LINEAR && plan.gather_step_x == 0)
         for (int x = threadIdx.x; x < plan.dst_w; x += blockDim.x) s_xtab[x] = make_int4(3 * plan.x0[x], 3 * plan.x1[x], plan.a0[x], plan.a1[x]);
+    if (threadIdx.x <= UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;   // ... s_tiles_done and s_rows_issued
     fence_proxy_async();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < FR_DEPTH; ++s) { mbar_init(&full[s], 32 * UNFOLD_WARPS); mbar_init(&empty[s], 1); }
         for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], EPI_WARPS); }
         for (int s = 0; s < RAW_SLOTS_MAX; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
         fence_barrier_init();
@@ -655,20 +697,30 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;     // debug stamps of CTA 0 (CUTDET_TIMELINE1)
+    if (tl && threadIdx.x == 0) tl[2047] = clock64();
 
-    if (warp == F1_LOAD_WARP) {
-        // ------------------------------------------------------------------ loader: source rows -> raw ring
-        int n = 0;                                          // resized rows loaded so far (frame-major: n = fi * Hc + y)
-        for (int fi = 0; fi < n_frames_cta; ++fi) {
-            const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
-            for (int y = 0; y < Hc; ++y, ++n) {
+    if (warp >= F1_LOAD_WARP0) {
+        // ------------------------------------------------------------------ loaders: source rows -> raw ring
+        // (a slot's consecutive rows n, n + n_slots go through the same loader -- n_slots is a multiple of n_loaders -- so the
+        // in-order waits on raw_empty never skip a phase)
+        const int lw = warp - F1_LOAD_WARP0, total_rows = n_frames_cta * Hc;
+        const int n_loaders = min(LOADER_WARPS, n_slots);
+        if (lw < n_loaders) {
+            int fi = 0, y = lw, issued = 0;
+            for (int n = lw; n < total_rows; n += n_loaders, y += n_loaders) {
+                while (y >= Hc) { y -= Hc; ++fi; }
                 const int slot = n & (n_slots - 1);
                 mbar_wait(&raw_empty[slot], ((n >> src.log2_slots) & 1) ^ 1);
+                if (tl && lane == 0 && n < 256) tl[n] = clock64();
+                ++issued;
                 if (elect_one()) {
+                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
                     mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
                     for (int j = 0; j < src.n_src; ++j)
                         bulk_load_1d(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * y + j], (uint32_t)src.row_bytes,
                                      &raw_full[slot]);
+                    st_release_shared(&s_rows_issued[lw], issued);   // raw_full[slot] is now in row n's phase
                 }
                 __syncwarp();
             }
@@ -676,76 +728,81 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     } else if (warp >= 8 && warp < 8 + UNFOLD_WARPS) {
         // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
         const int pwarp = warp - 8;
-        // A resized row goes to ONE warp, which unfolds its n_parts 32-column parts.  The warp is a function of the row's raw
-        // slot, so consecutive uses of a slot's mbarriers are always waited on by the same warp, in order: a warp that
-        // skipped a phase could otherwise mistake "two phases behind" for "complete" (mbarrier waits see one parity bit).
-        // Zero rows (no source row) rotate over the warps.  Lane constants of the integer-scale gather: byte offset of pixel 3px-1.
-        const int BS = 3 * plan.gather_step_x;
-        const int owner_mask = (n_slots < UNFOLD_WARPS ? n_slots : UNFOLD_WARPS) - 1;
-        int next_R = 0, fi = 0, py = 0;                     // (fi, py) <-> next_R
-        for (int t = 0; t < n_tiles; ++t) {
-            mbar_wait(&empty[t % FR_DEPTH], ((t / FR_DEPTH) & 1) ^ 1);          // tile t - FR_DEPTH has been consumed
-            const int R_hi = min(n_frames_cta * RPF - 1, (t * 128 + 127) / P1w + 1);
-            for (int R = next_R; R <= R_hi; ++R, ++py) {
-              if (py == RPF) { py = 0; ++fi; }
-#pragma unroll
-              for (int sub = 0; sub < 3; ++sub) {
-                const int y = 3 * py + sub;
-                const bool real = y < H && (py < p.P1h || sub == 0);   // index P1h: row 3*P1h if the image has it, else zeros
-                const int n = fi * Hc + y, slot = n & (n_slots - 1);
-                if ((real ? (n & owner_mask) : ((R + sub) & (UNFOLD_WARPS - 1))) != pwarp) continue;
-                const uint8_t *q0 = s_raw + slot * slot_bytes;
-                if (real) mbar_wait(&raw_full[slot], (n >> src.log2_slots) & 1);
-                for (int part = 0; part < n_parts; ++part) {
-                    const int px = part * 32 + lane;
-                    uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
-                    if (real && px < P1w) {
-                        uint32_t w[5];
-                        if (GATHER) {
-                            const int base = 3 * plan.gather_off_x + BS * (3 * px - 1);
-#pragma unroll
-                            for (int j = 0; j < 5; ++j) {
-                                const int b = base + BS * j;
-                                const bool ok = (j > 0 || px > 0) && (j < 4 || 3 * px + 3 < plan.dst_w);
-                                const uint32_t *wp = reinterpret_cast<const uint32_t *>(q0 + (ok ? (b & ~3) : 0));
-                                const uint32_t v = __byte_perm(wp[0], wp[1], 0x3210u + (uint32_t)(b & 3) * 0x1111u);
-                                w[j] = ok ? ((v & 0x00FFFFFFu) | ZERO_PIXEL) : ZERO_PIXEL;
-                            }
-                        } else {
-                            const uint8_t *q1 = q0 + (src.n_src - 1) * src.row_bytes;
-                            const int b0 = s_yb[2 * y], b1 = s_yb[2 * y + 1];
-#pragma unroll
-                            for (int j = 0; j < 5; ++j) w[j] = resized_word(plan, q0, q1, s_xtab, b0, b1, 3 * px - 1 + j);
-                        }
-                        lo.x = u8x2_to_h2(__byte_perm(w[0], w[0], 0x3132));     // R0 G0
-                        lo.y = u8x2_to_h2(__byte_perm(w[0], w[1], 0x7630));     // B0 R1
-                        lo.z = u8x2_to_h2(__byte_perm(w[1], w[1], 0x3031));     // G1 B1
-                        lo.w = u8x2_to_h2(__byte_perm(w[2], w[2], 0x3132));     // R2 G2
-                        hi.x = u8x2_to_h2(__byte_perm(w[2], w[3], 0x7630));     // B2 R3
-                        hi.y = u8x2_to_h2(__byte_perm(w[3], w[3], 0x3031));     // G3 B3
-                        hi.z = u8x2_to_h2(__byte_perm(w[4], w[4], 0x3132));     // R4 G4
-                        hi.w = u8x2_to_h2(__byte_perm(w[4], ZERO_PIXEL, 0x7430));   // B4 0
-                    }
-                    if (px < P1w) {
-                        const int pos = (R * P1w + px) & (FR_CAP - 1);
-                        uint8_t *dst = s_ring + sub * FR_SUB + pos * 16;
-                        *reinterpret_cast<uint4 *>(dst) = lo;
-                        *reinterpret_cast<uint4 *>(dst + FR_PLANE) = hi;
-                        if (pos < 128) {                                     // mirror past the end of the ring
-                            *reinterpret_cast<uint4 *>(dst + FR_CAP * 16) = lo;
-                            *reinterpret_cast<uint4 *>(dst + FR_CAP * 16 + FR_PLANE) = hi;
-                        }
-                    }
+        const int BS = 3 * plan.gather_step_x;               // integer-scale gather: bytes between resized pixels
+        const int n_loaders = min(LOADER_WARPS, n_slots);
+        int R = 0, sub = pwarp, fi = 0, py = 0;              // u = 3R + sub, R = fi * RPF + py
+        while (sub >= 3) { sub -= 3; ++R; ++py; }
+        int tiles_seen = 0, rows_done = 0;
+        for (int u = pwarp; u < total_u; u += UNFOLD_WARPS) {
+            while (py >= RPF) { py -= RPF; ++fi; }
+            const int y = 3 * py + sub;
+            const bool real = y < H && (py < p.P1h || sub == 0);   // index P1h: row 3*P1h if the image has it, else zeros
+            const int n = fi * Hc + y, slot = n & (n_slots - 1);
+            // positions [R*P1w, (R+1)*P1w) replace those FR_CAP earlier, last read by tile (pos - FR_CAP + P1w) / 128
+            const int last_reader = ((R + 2) * P1w - 1 - FR_CAP) >> 7;      // arithmetic shift: negative = none
+            while (tiles_seen <= last_reader) tiles_seen = ld_acquire_shared(s_tiles_done);
+            const uint8_t *q0 = s_raw + slot * slot_bytes;
+            if (real) {
+                const int ld = n & (n_loaders - 1), want = (n >> (n_loaders == 4 ? 2 : n_loaders == 2 ? 1 : 0)) + 1;
+                while (ld_acquire_shared(&s_rows_issued[ld]) < want) {
                 }
-                if (real) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&raw_empty[slot]);            // the source row has been read
-                }
-              }
+                mbar_wait(&raw_full[slot], (n >> src.log2_slots) & 1);
             }
-            next_R = R_hi + 1;
+            if (tl && pwarp == 0 && lane == 0 && rows_done < 128) tl[256 + rows_done] = clock64();
+            uint32_t w[NP][5];
+#pragma unroll
+            for (int part = 0; part < NP; ++part) {
+                const int px = part * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) w[part][j] = ZERO_PIXEL;
+                if (real && px < P1w) {
+                    if (GATHER) {
+                        const int base = 3 * plan.gather_off_x + BS * (3 * px - 1);
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) {
+                            const int b = base + BS * j;
+                            const bool ok = (j > 0 || px > 0) && (j < 4 || 3 * px + 3 < plan.dst_w);
+                            const uint32_t *wp = reinterpret_cast<const uint32_t *>(q0 + (ok ? (b & ~3) : 0));
+                            const uint32_t v = __byte_perm(wp[0], wp[1], 0x3210u + (uint32_t)(b & 3) * 0x1111u);
+                            w[part][j] = ok ? ((v & 0x00FFFFFFu) | ZERO_PIXEL) : ZERO_PIXEL;
+                        }
+                    } else {
+                        const uint8_t *q1 = q0 + (src.n_src - 1) * src.row_bytes;
+                        const int b0 = s_yb[2 * y], b1 = s_yb[2 * y + 1];
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) w[part][j] = resized_word(plan, q0, q1, s_xtab, b0, b1, 3 * px - 1 + j);
+                    }
+                }
+            }
+            if (real) {
+                fence_proxy_async();                                     // these reads, then the async-proxy refill of the slot
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&raw_empty[slot]);            // the source row is in registers
+            }
+#pragma unroll
+            for (int part = 0; part < NP; ++part) {
+                const int px = part * 32 + lane;
+                if (px < P1w) {
+                    uint4 lo, hi;
+                    chunk_from_words(w[part], lo, hi);
+                    if (!real) lo = hi = make_uint4(0, 0, 0, 0);
+                    const int pos = (R * P1w + px) & (FR_CAP - 1);
+                    uint8_t *dst = s_ring + sub * FR_SUB + pos * 16;
+                    *reinterpret_cast<uint4 *>(dst) = lo;
+                    *reinterpret_cast<uint4 *>(dst + FR_PLANE) = hi;
+                    if (pos < 128) {                                     // mirror past the end of the ring
+                        *reinterpret_cast<uint4 *>(dst + FR_CAP * 16) = lo;
+                        *reinterpret_cast<uint4 *>(dst + FR_CAP * 16 + FR_PLANE) = hi;
+                    }
+                }
+            }
             fence_proxy_async();                        // generic-proxy stores -> visible to the MMA's async-proxy reads
-            mbar_arrive(&full[t % FR_DEPTH]);
+            __syncwarp();
+            ++rows_done;
+            if (lane == 0) st_release_shared(&s_rows_done[pwarp], rows_done);
+            if (tl && pwarp == 0 && lane == 0 && rows_done <= 128) tl[384 + rows_done - 1] = clock64();
+            sub += UNFOLD_WARPS % 3; R += UNFOLD_WARPS / 3; py += UNFOLD_WARPS / 3;
+            if (sub >= 3) { sub -= 3; ++R; ++py; }
         }
     } else if (warp == F1_MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
@@ -753,8 +810,15 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
         const uint32_t idesc = instr_desc_16bit(128, 3 * C, kBf16);
         for (int t = 0; t < n_tiles; ++t) {
-            mbar_wait(&full[t % FR_DEPTH], (t / FR_DEPTH) & 1);
+            // rows of sub-rings 1 and 2 up to pooled row (128t + 127) / P1w, of sub-ring 0 one pooled row further
+            const int u_hi = min(total_u - 1, 3 * ((t * 128 + 127) / P1w + 1));
+            const int mine = lane & (UNFOLD_WARPS - 1);
+            const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
+            while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) {
+            }
+            __syncwarp();
             tc_fence_after_sync();
+            if (tl && lane == 0 && t < 64) tl[1024 + t] = clock64();
             uint32_t a_chunk[5];
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
@@ -765,6 +829,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             for (int dy = 0; dy < 3; ++dy) {
                 mbar_wait(&acc_empty[dy], acc_phase ^ 1);
                 tc_fence_after_sync();
+                // block row 2 of tile t-1 has been drained, so every MMA of tiles < t has completed: their ring positions are free
+                if (dy == 2 && lane == 0) st_release_shared(s_tiles_done, t);
                 if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 3; ++ks) {
@@ -776,8 +842,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                 }
                 __syncwarp();
             }
-            if (elect_one()) umma_commit(&empty[t % FR_DEPTH]);
-            __syncwarp();
+            if (tl && lane == 0 && t < 64) tl[1088 + t] = clock64();
             acc_phase ^= 1;
         }
     } else {
@@ -793,6 +858,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             float v[CH];
             epilogue_tile<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, s_par, ch0, v);
             if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
+            if (tl && threadIdx.x == 0 && t < 64) tl[1152 + t] = clock64();
             acc_phase ^= 1;
             X += 128;
             while (X >= P1w) { X -= P1w; ++Y; }
@@ -1195,7 +1261,22 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     if (fused) {
         FusedSrc fs = *fused;
         fs.frames += (long long)f0 * fs.frame_stride;
-        if (int rc = launch_conv1_fused<C>(c1, fs, stream)) return rc;
+        static const bool want_tl = getenv("CUTDET_TIMELINE1") != nullptr;       // debug aid: clock stamps of CTA 0, dumped once
+        static int tl_runs = 0;
+        if (want_tl && nb >= 148 && tl_runs++ == 20) {
+            long long *d = nullptr;
+            std::vector<long long> h(2048);
+            CUTDET_CUDA(cudaMalloc(&d, 2048 * 8));
+            CUTDET_CUDA(cudaMemsetAsync(d, 0, 2048 * 8, stream));
+            c1.timeline = d;
+            if (int rc = launch_conv1_fused<C>(c1, fs, stream)) return rc;
+            CUTDET_CUDA(cudaMemcpyAsync(h.data(), d, 2048 * 8, cudaMemcpyDeviceToHost, stream));
+            CUTDET_CUDA(cudaStreamSynchronize(stream));
+            FILE *f = fopen(getenv("CUTDET_TIMELINE1"), "w");
+            if (f) { for (int i = 0; i < 2048; ++i) fprintf(f, "%lld\n", h[i] ? h[i] - h[2047] : -1LL); fclose(f); }
+            cudaFree(d);
+            c1.timeline = nullptr;
+        } else if (int rc = launch_conv1_fused<C>(c1, fs, stream)) return rc;
     } else if (int rc = launch_conv1<C>(c1, stream)) return rc;
 
     MidParams p2 = mid_params(nb, g.FP1, g.PW1, g.P2h, g.P2w);
