@@ -180,6 +180,96 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_thread /* lane quart
     }
 }
 
+// ---- software-pipelined variant for kernels whose epilogue is the critical path (conv1: 9 short MMAs per tile) ----
+// The accumulator is read as nine sub-blocks s = 3 dy + dx of CH columns, in pairs; the TMEM loads of the next pair are in
+// flight while the running max takes in the current one (tcgen05.wait::ld waits for everything outstanding, so exactly one
+// pair is outstanding at each wait).  Two pair buffers + the running max = 5 CH registers: the epilogue warps raise their
+// register budget with setmaxnreg.  The first pair of the NEXT tile is requested before the bias/ReLU/BatchNorm/store of this
+// one.  Per channel: max2, 3 x max3, max2 (FMNMX3), the same five operations as the block-row version.
+template <int CH>
+struct EpiPair { float a[CH], b[CH]; };
+
+template <int C>
+__device__ __forceinline__ void epi_issue_pair(uint32_t tmem_thread, int s, EpiPair<C / 2> &q, bool second) {
+    tmem_ld_ch<C / 2>(tmem_thread + s * C, q.a);
+    if (second) tmem_ld_ch<C / 2>(tmem_thread + (s + 1) * C, q.b);
+}
+
+template <int C>
+__device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, uint64_t *acc_full, uint64_t *acc_empty, uint32_t acc_phase,
+                                                        int lane, bool more_tiles, EpiPair<C / 2> &A /* in: pair (0,1) in flight */,
+                                                        float (&run)[C / 2]) {
+    constexpr int CH = C / 2;
+    EpiPair<CH> B;
+    auto release = [&](int dy) {                      // every sub-block of block row dy is in registers
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[dy]);
+    };
+    // pair (0,1) -> A arrives; request (2,3) -> B
+    tmem_ld_wait();
+    reg_fence<CH>(A.a); reg_fence<CH>(A.b);
+    mbar_wait(&acc_full[1], acc_phase);
+    tc_fence_after_sync();
+    epi_issue_pair<C>(tmem_thread, 2, B, true);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) run[i] = fmaxf(A.a[i], A.b[i]);
+    reg_fence<CH>(run);
+    // (2,3) arrives: block row 0 done; request (4,5) -> A
+    tmem_ld_wait();
+    reg_fence<CH>(B.a); reg_fence<CH>(B.b);
+    release(0);
+    epi_issue_pair<C>(tmem_thread, 4, A, true);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(run[i], B.a[i]), B.b[i]);
+    reg_fence<CH>(run);
+    // (4,5) arrives: block row 1 done; request (6,7) -> B
+    tmem_ld_wait();
+    reg_fence<CH>(A.a); reg_fence<CH>(A.b);
+    release(1);
+    mbar_wait(&acc_full[2], acc_phase);
+    tc_fence_after_sync();
+    epi_issue_pair<C>(tmem_thread, 6, B, true);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(run[i], A.a[i]), A.b[i]);
+    reg_fence<CH>(run);
+    // (6,7) arrives; request 8 -> A.a
+    tmem_ld_wait();
+    reg_fence<CH>(B.a); reg_fence<CH>(B.b);
+    epi_issue_pair<C>(tmem_thread, 8, A, false);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(run[i], B.a[i]), B.b[i]);
+    reg_fence<CH>(run);
+    // 8 arrives: block row 2 done; request the next tile's (0,1) -> A before the affine + store of this tile
+    tmem_ld_wait();
+    reg_fence<CH>(A.a);
+    release(2);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) run[i] = fmaxf(run[i], A.a[i]);
+    reg_fence<CH>(run);
+    if (more_tiles) {
+        mbar_wait(&acc_full[0], acc_phase ^ 1);
+        tc_fence_after_sync();
+        epi_issue_pair<C>(tmem_thread, 0, A, true);
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void epilogue_affine(const float *s_par, int ch0, float (&run)[C / 2]) {
+    constexpr int CH = C / 2;
+    const float4 *bias4 = reinterpret_cast<const float4 *>(s_par + ch0);
+    const float4 *scale4 = reinterpret_cast<const float4 *>(s_par + C + ch0);
+    const float4 *shift4 = reinterpret_cast<const float4 *>(s_par + 2 * C + ch0);
+#pragma unroll
+    for (int i = 0; i < CH / 4; ++i) {
+        const float4 b = bias4[i], s = scale4[i], t = shift4[i];
+        run[4 * i + 0] = fmaf(fmaxf(run[4 * i + 0] + b.x, 0.f), s.x, t.x);
+        run[4 * i + 1] = fmaf(fmaxf(run[4 * i + 1] + b.y, 0.f), s.y, t.y);
+        run[4 * i + 2] = fmaf(fmaxf(run[4 * i + 2] + b.z, 0.f), s.z, t.z);
+        run[4 * i + 3] = fmaf(fmaxf(run[4 * i + 3] + b.w, 0.f), s.w, t.w);
+    }
+}
+
 // b = frame inside this launch, (Y, X) = pooled pixel, ch0 = this thread's first channel (a multiple of 8).
 template <int C>
 __device__ __forceinline__ void store_pixel(const OutSpec &o, int b, int Y, int X, int ch0, const float (&v)[C / 2]) {
@@ -595,11 +685,11 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
     return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ZERO_PIXEL;
 }
 
-// 672 threads: warps 0..7 = epilogue, 8..15 = unfold, 16 = MMA issuer (+ TMEM alloc), 17..20 = loaders.
+// 640 threads: warps 0..7 = epilogue, 8..15 = unfold, 16 = MMA issuer (+ TMEM alloc), 17..18 = loaders, 19 idle.
 //
 // The four stages run DECOUPLED, each at its own pace, joined by two rings:
-//   loaders   rows of the source frame -> raw ring by cp.async.bulk, row n issued by loader n % 4: ONE issuing thread sustains a
-//             3,840-byte row per ~370 cycles (10 bytes/clock), four reach HBM speed (tools/hbm_rows.cu).  raw_full[slot]
+//   loaders   rows of the source frame -> raw ring by cp.async.bulk, row n issued by loader n % 2: ONE issuing thread sustains a
+//             3,840-byte row per ~370 cycles (10 bytes/clock), two reach 5 TB/s (tools/hbm_rows.cu).  raw_full[slot]
 //             counts the bytes, raw_empty[slot] the reader's release, s_rows_issued[loader] says how far each loader is:
 //             a reader first checks that ITS row has been issued, because an mbarrier wait sees one parity bit and a reader
 //             that is a whole ring ahead would otherwise take the previous row's phase for its own.
@@ -611,8 +701,16 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
 // Counters instead of per-tile mbarriers: a row is produced by ONE warp, tiles need rows from all of them, and a warp must never
 // have to wait for a tile it contributes nothing to (the lock-step version spent 2/3 of its time in such waits).
 // GATHER: the resize is out[y][x] = src[off_y + y*step_y][off_x + x*step_x] (every second tap has zero weight).
-constexpr int UNFOLD_WARPS = 8, LOADER_WARPS = 4 /* 1, 2 or 4 */, F1_MMA_WARP = 8 + UNFOLD_WARPS, F1_LOAD_WARP0 = 9 + UNFOLD_WARPS;
-constexpr int F1_THREADS = 32 * (9 + UNFOLD_WARPS + LOADER_WARPS);
+// Warpgroups (setmaxnreg works on four consecutive warps): 0-1 epilogue, 2-3 unfold, 4 = MMA issuer, two loaders, one idle warp.
+// Registers: 640 threads start with 96 each (61,440, all a CTA of this size can own); a group can only grow by what the
+// others of the SAME CTA have given up, so unfold drops to 72, group 4 to 48, and the epilogue rises to 144:
+// 256 x 144 + 256 x 72 + 128 x 48 = 61,440.  (A request beyond the pool would block for ever: the launcher checks the count.)
+constexpr int UNFOLD_WARPS = 8, LOADER_WARPS = 2 /* 1, 2 or 4 */, F1_MMA_WARP = 8 + UNFOLD_WARPS, F1_LOAD_WARP0 = 9 + UNFOLD_WARPS;
+constexpr int F1_THREADS = 32 * (12 + UNFOLD_WARPS);
+constexpr int F1_REGS_START = 96, F1_REGS_EPI = 144, F1_REGS_UNFOLD = 72, F1_REGS_LIGHT = 48;
+static_assert(F1_THREADS * F1_REGS_START == 256 * F1_REGS_EPI + 256 * F1_REGS_UNFOLD + 128 * F1_REGS_LIGHT, "register pool");
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 __device__ __forceinline__ void st_release_shared(int *p, int v) {
     asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
@@ -700,33 +798,78 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;     // debug stamps of CTA 0 (CUTDET_TIMELINE1)
     if (tl && threadIdx.x == 0) tl[2047] = clock64();
 
-    if (warp >= F1_LOAD_WARP0) {
-        // ------------------------------------------------------------------ loaders: source rows -> raw ring
-        // (a slot's consecutive rows n, n + n_slots go through the same loader -- n_slots is a multiple of n_loaders -- so the
-        // in-order waits on raw_empty never skip a phase)
-        const int lw = warp - F1_LOAD_WARP0, total_rows = n_frames_cta * Hc;
-        const int n_loaders = min(LOADER_WARPS, n_slots);
-        if (lw < n_loaders) {
-            int fi = 0, y = lw, issued = 0;
-            for (int n = lw; n < total_rows; n += n_loaders, y += n_loaders) {
-                while (y >= Hc) { y -= Hc; ++fi; }
-                const int slot = n & (n_slots - 1);
-                mbar_wait(&raw_empty[slot], ((n >> src.log2_slots) & 1) ^ 1);
-                if (tl && lane == 0 && n < 256) tl[n] = clock64();
-                ++issued;
-                if (elect_one()) {
-                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
-                    mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
-                    for (int j = 0; j < src.n_src; ++j)
-                        bulk_load_1d(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * y + j], (uint32_t)src.row_bytes,
-                                     &raw_full[slot]);
-                    st_release_shared(&s_rows_issued[lw], issued);   // raw_full[slot] is now in row n's phase
+    if (warp >= F1_MMA_WARP) {
+        reg_dealloc<F1_REGS_LIGHT>();                            // one instruction for the whole warpgroup (.sync.aligned)
+        if (warp > F1_MMA_WARP) {
+            // ------------------------------------------------------------------ loaders: source rows -> raw ring
+            // (a slot's consecutive rows n, n + n_slots go through the same loader -- n_slots is a multiple of n_loaders -- so the
+            // in-order waits on raw_empty never skip a phase)
+            const int lw = warp - F1_LOAD_WARP0, total_rows = n_frames_cta * Hc;
+            const int n_loaders = min(LOADER_WARPS, n_slots);
+            if (lw < n_loaders) {                                // (warp 19 only fills the warpgroup)
+                int fi = 0, y = lw, issued = 0;
+                for (int n = lw; n < total_rows; n += n_loaders, y += n_loaders) {
+                    while (y >= Hc) { y -= Hc; ++fi; }
+                    const int slot = n & (n_slots - 1);
+                    mbar_wait(&raw_empty[slot], ((n >> src.log2_slots) & 1) ^ 1);
+                    if (tl && lane == 0 && n < 256) tl[n] = clock64();
+                    ++issued;
+                    if (elect_one()) {
+                        const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
+                        mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
+                        for (int j = 0; j < src.n_src; ++j)
+                            bulk_load_1d(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * y + j], (uint32_t)src.row_bytes,
+                                         &raw_full[slot]);
+                        st_release_shared(&s_rows_issued[lw], issued);   // raw_full[slot] is now in row n's phase
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
+            // ------------------------------------------------------------------ MMA issuer
+            uint32_t acc_phase = 0;
+            const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
+            const uint32_t idesc = instr_desc_16bit(128, 3 * C, kBf16);
+            for (int t = 0; t < n_tiles; ++t) {
+                // rows of sub-rings 1 and 2 up to pooled row (128t + 127) / P1w, of sub-ring 0 one pooled row further
+                const int u_hi = min(total_u - 1, 3 * ((t * 128 + 127) / P1w + 1));
+                const int mine = lane & (UNFOLD_WARPS - 1);
+                const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
+                while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) {
                 }
                 __syncwarp();
+                tc_fence_after_sync();
+                if (tl && lane == 0 && t < 64) tl[1024 + t] = clock64();
+                uint32_t a_chunk[5];
+    #pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const int sub = (c + 2) % 3, shift = c == 0 ? -P1w : (c == 4 ? P1w : 0);
+                    a_chunk[c] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
+                }
+    #pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    mbar_wait(&acc_empty[dy], acc_phase ^ 1);
+                    tc_fence_after_sync();
+                    // block row 2 of tile t-1 has been drained, so every MMA of tiles < t has completed: their ring positions are free
+                    if (dy == 2 && lane == 0) st_release_shared(s_tiles_done, t);
+                    if (elect_one()) {
+    #pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) {
+                            const uint64_t da = smem_desc(a_chunk[dy + ks], FR_PLANE, 128);
+                            const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
+                            umma_16bit(tmem_base + 3 * C * dy, da, db, idesc, ks > 0 ? 1u : 0u);
+                        }
+                        umma_commit(&acc_full[dy]);
+                    }
+                    __syncwarp();
+                }
+                if (tl && lane == 0 && t < 64) tl[1088 + t] = clock64();
+                acc_phase ^= 1;
             }
         }
     } else if (warp >= 8 && warp < 8 + UNFOLD_WARPS) {
         // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
+        reg_dealloc<F1_REGS_UNFOLD>();
         const int pwarp = warp - 8;
         const int BS = 3 * plan.gather_step_x;               // integer-scale gather: bytes between resized pixels
         const int n_loaders = min(LOADER_WARPS, n_slots);
@@ -804,59 +947,26 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             sub += UNFOLD_WARPS % 3; R += UNFOLD_WARPS / 3; py += UNFOLD_WARPS / 3;
             if (sub >= 3) { sub -= 3; ++R; ++py; }
         }
-    } else if (warp == F1_MMA_WARP) {
-        // ------------------------------------------------------------------ MMA issuer
-        uint32_t acc_phase = 0;
-        const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
-        const uint32_t idesc = instr_desc_16bit(128, 3 * C, kBf16);
-        for (int t = 0; t < n_tiles; ++t) {
-            // rows of sub-rings 1 and 2 up to pooled row (128t + 127) / P1w, of sub-ring 0 one pooled row further
-            const int u_hi = min(total_u - 1, 3 * ((t * 128 + 127) / P1w + 1));
-            const int mine = lane & (UNFOLD_WARPS - 1);
-            const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
-            while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) {
-            }
-            __syncwarp();
-            tc_fence_after_sync();
-            if (tl && lane == 0 && t < 64) tl[1024 + t] = clock64();
-            uint32_t a_chunk[5];
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const int sub = (c + 2) % 3, shift = c == 0 ? -P1w : (c == 4 ? P1w : 0);
-                a_chunk[c] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
-            }
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                mbar_wait(&acc_empty[dy], acc_phase ^ 1);
-                tc_fence_after_sync();
-                // block row 2 of tile t-1 has been drained, so every MMA of tiles < t has completed: their ring positions are free
-                if (dy == 2 && lane == 0) st_release_shared(s_tiles_done, t);
-                if (elect_one()) {
-#pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) {
-                        const uint64_t da = smem_desc(a_chunk[dy + ks], FR_PLANE, 128);
-                        const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
-                        umma_16bit(tmem_base + 3 * C * dy, da, db, idesc, ks > 0 ? 1u : 0u);
-                    }
-                    umma_commit(&acc_full[dy]);
-                }
-                __syncwarp();
-            }
-            if (tl && lane == 0 && t < 64) tl[1088 + t] = clock64();
-            acc_phase ^= 1;
-        }
     } else {
         // ------------------------------------------------------------------ epilogue
+        reg_alloc<F1_REGS_EPI>();
         const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
         const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + ch0;
         uint32_t acc_phase = 0;
         for (int fi = 0; fi < n_frames_cta; ++fi) zero_pads(p.out, CG, blockIdx.x + fi * gridDim.x, blockIdx.x + fi * gridDim.x + 1, threadIdx.x, EPI_WARPS * 32);
         int X = m % P1w, Y = m / P1w, fi = 0;              // position 128 t + m = ((fi * RPF + Y) * P1w + X), advanced tile by tile
         while (Y >= RPF) { Y -= RPF; ++fi; }
+        EpiPair<CH> A;
+        if (n_tiles > 0) {
+            mbar_wait(&acc_full[0], 0);
+            tc_fence_after_sync();
+            epi_issue_pair<C>(tmem_thread, 0, A, true);
+        }
         for (int t = 0; t < n_tiles; ++t) {
             const bool valid = fi < n_frames_cta && Y < p.P1h;
             float v[CH];
-            epilogue_tile<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, s_par, ch0, v);
+            epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, A, v);
+            epilogue_affine<C>(s_par, ch0, v);
             if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
             if (tl && threadIdx.x == 0 && t < 64) tl[1152 + t] = clock64();
             acc_phase ^= 1;
@@ -1176,6 +1286,12 @@ int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
 template <int C>
 int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src, cudaStream_t stream) {
     const int grid = p.B < sm_count() ? p.B : sm_count();
+    static const int regs_g = [] { cudaFuncAttributes a{}; cudaFuncGetAttributes(&a, conv1_fused_tc_kernel<C, true>); return a.numRegs; }();
+    static const int regs_l = [] { cudaFuncAttributes a{}; cudaFuncGetAttributes(&a, conv1_fused_tc_kernel<C, false>); return a.numRegs; }();
+    if (regs_g != F1_REGS_START || regs_l != F1_REGS_START) {
+        fprintf(stderr, "cutdet: conv1_fused_tc compiled with %d/%d registers, the setmaxnreg budget assumes %d\n", regs_g, regs_l, F1_REGS_START);
+        return CUTDET_EUNSUPPORTED;
+    }
     {
         KernelScope scope("conv1_fused_tc", stream);
         if (src.plan.gather_step_x > 0) conv1_fused_tc_kernel<C, true><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
