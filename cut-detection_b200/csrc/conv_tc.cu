@@ -181,81 +181,71 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_thread /* lane quart
 }
 
 // ---- software-pipelined variant for kernels whose epilogue is the critical path (conv1: 9 short MMAs per tile) ----
-// The accumulator is read as nine sub-blocks s = 3 dy + dx of CH columns, in pairs; the TMEM loads of the next pair are in
-// flight while the running max takes in the current one (tcgen05.wait::ld waits for everything outstanding, so exactly one
-// pair is outstanding at each wait).  Two pair buffers + the running max = 5 CH registers: the epilogue warps raise their
-// register budget with setmaxnreg.  The first pair of the NEXT tile is requested before the bias/ReLU/BatchNorm/store of this
-// one.  Per channel: max2, 3 x max3, max2 (FMNMX3), the same five operations as the block-row version.
+// A batch of tcgen05.ld followed by tcgen05.wait::ld costs ~250 cycles whatever its size (tools/tmem_bw.cu: 148 cycles for one
+// x16 load, 255 for six), so the tile is read in as few batches as possible -- its three block rows -- and the batch of the
+// next block row is in flight while the running max takes in the current one: two buffers of 3 * CH registers plus the
+// running max, 7 * CH = 168 at C = 48, which is why the epilogue warps raise their register budget with setmaxnreg.
+// Block row 0 of the NEXT tile is requested before the bias/ReLU/BatchNorm/store of this one.  Per channel: max3, then twice
+// max3 + max (FMNMX3), the same five operations as the unpipelined version.
 template <int CH>
-struct EpiPair { float a[CH], b[CH]; };
+struct EpiRow { float a[CH], b[CH], c[CH]; };
 
 template <int C>
-__device__ __forceinline__ void epi_issue_pair(uint32_t tmem_thread, int s, EpiPair<C / 2> &q, bool second) {
-    tmem_ld_ch<C / 2>(tmem_thread + s * C, q.a);
-    if (second) tmem_ld_ch<C / 2>(tmem_thread + (s + 1) * C, q.b);
+__device__ __forceinline__ void epi_issue_row(uint32_t tmem_thread, int dy, EpiRow<C / 2> &q) {
+    tmem_ld_ch<C / 2>(tmem_thread + (3 * dy + 0) * C, q.a);
+    tmem_ld_ch<C / 2>(tmem_thread + (3 * dy + 1) * C, q.b);
+    tmem_ld_ch<C / 2>(tmem_thread + (3 * dy + 2) * C, q.c);
 }
 
+// X: block row 0 of this tile, in flight on entry.  Y: free on entry; on exit it holds the next tile's block row 0 in flight.
 template <int C>
 __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, uint64_t *acc_full, uint64_t *acc_empty, uint32_t acc_phase,
-                                                        int lane, bool more_tiles, EpiPair<C / 2> &A /* in: pair (0,1) in flight */,
-                                                        float (&run)[C / 2]) {
+                                                        int lane, bool more_tiles, EpiRow<C / 2> &X, EpiRow<C / 2> &Y,
+                                                        float (&run)[C / 2], long long *stamp = nullptr) {
     constexpr int CH = C / 2;
-    EpiPair<CH> B;
-    auto release = [&](int dy) {                      // every sub-block of block row dy is in registers
+    if (stamp) stamp[0] = clock64();
+    auto arrived = [&](EpiRow<CH> &q, int dy) {       // block row dy is in registers: hand it back to the MMA issuer
+        tmem_ld_wait();
+        reg_fence<CH>(q.a); reg_fence<CH>(q.b); reg_fence<CH>(q.c);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[dy]);
     };
-    // pair (0,1) -> A arrives; request (2,3) -> B
-    tmem_ld_wait();
-    reg_fence<CH>(A.a); reg_fence<CH>(A.b);
+    arrived(X, 0);
+    if (stamp) stamp[1] = clock64();
     mbar_wait(&acc_full[1], acc_phase);
     tc_fence_after_sync();
-    epi_issue_pair<C>(tmem_thread, 2, B, true);
+    if (stamp) stamp[2] = clock64();
+    epi_issue_row<C>(tmem_thread, 1, Y);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) run[i] = fmaxf(A.a[i], A.b[i]);
+    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(X.a[i], X.b[i]), X.c[i]);
     reg_fence<CH>(run);
-    // (2,3) arrives: block row 0 done; request (4,5) -> A
-    tmem_ld_wait();
-    reg_fence<CH>(B.a); reg_fence<CH>(B.b);
-    release(0);
-    epi_issue_pair<C>(tmem_thread, 4, A, true);
-#pragma unroll
-    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(run[i], B.a[i]), B.b[i]);
-    reg_fence<CH>(run);
-    // (4,5) arrives: block row 1 done; request (6,7) -> B
-    tmem_ld_wait();
-    reg_fence<CH>(A.a); reg_fence<CH>(A.b);
-    release(1);
+    if (stamp) stamp[3] = clock64();
+    arrived(Y, 1);
+    if (stamp) stamp[4] = clock64();
     mbar_wait(&acc_full[2], acc_phase);
     tc_fence_after_sync();
-    epi_issue_pair<C>(tmem_thread, 6, B, true);
+    if (stamp) stamp[5] = clock64();
+    epi_issue_row<C>(tmem_thread, 2, X);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(run[i], A.a[i]), A.b[i]);
+    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(fmaxf(run[i], Y.a[i]), Y.b[i]), Y.c[i]);
     reg_fence<CH>(run);
-    // (6,7) arrives; request 8 -> A.a
-    tmem_ld_wait();
-    reg_fence<CH>(B.a); reg_fence<CH>(B.b);
-    epi_issue_pair<C>(tmem_thread, 8, A, false);
-#pragma unroll
-    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(run[i], B.a[i]), B.b[i]);
-    reg_fence<CH>(run);
-    // 8 arrives: block row 2 done; request the next tile's (0,1) -> A before the affine + store of this tile
-    tmem_ld_wait();
-    reg_fence<CH>(A.a);
-    release(2);
-#pragma unroll
-    for (int i = 0; i < CH; ++i) run[i] = fmaxf(run[i], A.a[i]);
-    reg_fence<CH>(run);
+    if (stamp) stamp[6] = clock64();
+    arrived(X, 2);
+    if (stamp) stamp[7] = clock64();
     if (more_tiles) {
         mbar_wait(&acc_full[0], acc_phase ^ 1);
         tc_fence_after_sync();
-        epi_issue_pair<C>(tmem_thread, 0, A, true);
+        if (stamp) stamp[8] = clock64();
+        epi_issue_row<C>(tmem_thread, 0, Y);
     }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(fmaxf(run[i], X.a[i]), X.b[i]), X.c[i]);
+    reg_fence<CH>(run);
 }
 
 template <int C>
-__device__ __forceinline__ void epilogue_affine(const float *s_par, int ch0, float (&run)[C / 2]) {
+__device__ __forceinline__ void epilogue_affine(const float *s_par, int ch0, float acc_scale, float (&run)[C / 2]) {
     constexpr int CH = C / 2;
     const float4 *bias4 = reinterpret_cast<const float4 *>(s_par + ch0);
     const float4 *scale4 = reinterpret_cast<const float4 *>(s_par + C + ch0);
@@ -263,10 +253,10 @@ __device__ __forceinline__ void epilogue_affine(const float *s_par, int ch0, flo
 #pragma unroll
     for (int i = 0; i < CH / 4; ++i) {
         const float4 b = bias4[i], s = scale4[i], t = shift4[i];
-        run[4 * i + 0] = fmaf(fmaxf(run[4 * i + 0] + b.x, 0.f), s.x, t.x);
-        run[4 * i + 1] = fmaf(fmaxf(run[4 * i + 1] + b.y, 0.f), s.y, t.y);
-        run[4 * i + 2] = fmaf(fmaxf(run[4 * i + 2] + b.z, 0.f), s.z, t.z);
-        run[4 * i + 3] = fmaf(fmaxf(run[4 * i + 3] + b.w, 0.f), s.w, t.w);
+        run[4 * i + 0] = fmaf(fmaxf(fmaf(run[4 * i + 0], acc_scale, b.x), 0.f), s.x, t.x);
+        run[4 * i + 1] = fmaf(fmaxf(fmaf(run[4 * i + 1], acc_scale, b.y), 0.f), s.y, t.y);
+        run[4 * i + 2] = fmaf(fmaxf(fmaf(run[4 * i + 2], acc_scale, b.z), 0.f), s.z, t.z);
+        run[4 * i + 3] = fmaf(fmaxf(fmaf(run[4 * i + 3], acc_scale, b.w), 0.f), s.w, t.w);
     }
 }
 
@@ -482,6 +472,7 @@ struct Conv1Params {
     const uint4 *w_packed;  // [ky][half][3C rows: dx=0 | dx=1 | dx=2][8] 16-bit, taps scaled by kW1Scale
     const float *bias, *scale, *shift;
     long long *timeline;    // debug: clock64 stamps of CTA 0 (null = off)
+    const float *bias_magic; // fused kernel, integer-scale gather: bias - 4 * sum of the layer's rounded taps (pixels enter as 1024 + v)
 };
 
 template <int C>
@@ -685,7 +676,7 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
     return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ZERO_PIXEL;
 }
 
-// 640 threads: warps 0..7 = epilogue, 8..15 = unfold, 16 = MMA issuer (+ TMEM alloc), 17..18 = loaders, 19 idle.
+// 512 threads: warps 0..7 = epilogue, 8..11 = unfold, 12 = MMA issuer (+ TMEM alloc), 13..14 = loaders, 15 idle.
 //
 // The four stages run DECOUPLED, each at its own pace, joined by two rings:
 //   loaders   rows of the source frame -> raw ring by cp.async.bulk, row n issued by loader n % 2: ONE issuing thread sustains a
@@ -693,22 +684,31 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
 //             counts the bytes, raw_empty[slot] the reader's release, s_rows_issued[loader] says how far each loader is:
 //             a reader first checks that ITS row has been issued, because an mbarrier wait sees one parity bit and a reader
 //             that is a whole ring ahead would otherwise take the previous row's phase for its own.
-//   unfold    resized row u = 3R + sub goes to warp u % 8, which publishes its progress in s_rows_done[warp] (a monotone
+//   unfold    resized row u = 3R + sub goes to warp u % 4, which publishes its progress in s_rows_done[warp] (a monotone
 //             counter, st.release after fence.proxy.async); it may run ahead of the MMAs by the capacity of the operand ring
-//             and waits on the monotone s_tiles_done before overwriting positions an unfinished tile still reads.
+//             and waits for tile_done[t % 8] (committed by the MMA issuer after tile t's last MMA) before overwriting positions
+//             tile t still reads; the row it then writes is needed by tile t + 7 at the latest, so that barrier is never more
+//             than one phase ahead of a waiter.
+//             Integer-scale gathers (720p, 1440p, 2160p -> 256 wide) take the fast path: per-lane word offsets and funnel
+//             selectors are computed once (the byte phase of tap j is the same in all three 32-column parts), and pixels enter
+//             the MMA as the fp16 numbers 1024 + v (bit pattern 0x6400 | v, exact): the chunk is a byte permutation of the
+//             source row.  acc = sum w * (1024 + v) = 256 * (z + 4 * sum w); the epilogue's first FFMA undoes it
+//             (z = acc / 256 + (bias - 4 * sum w), sum over the rounded taps, so padding pixels -- 1024 -- cancel exactly).
 //   MMA       tile t needs every row u <= 3 * ((128t + 127) / P1w + 1): lane w polls s_rows_done[w].
 //   epilogue  unchanged (three accumulator block rows with full/empty mbarriers).
 // Counters instead of per-tile mbarriers: a row is produced by ONE warp, tiles need rows from all of them, and a warp must never
 // have to wait for a tile it contributes nothing to (the lock-step version spent 2/3 of its time in such waits).
 // GATHER: the resize is out[y][x] = src[off_y + y*step_y][off_x + x*step_x] (every second tap has zero weight).
-// Warpgroups (setmaxnreg works on four consecutive warps): 0-1 epilogue, 2-3 unfold, 4 = MMA issuer, two loaders, one idle warp.
-// Registers: 640 threads start with 96 each (61,440, all a CTA of this size can own); a group can only grow by what the
-// others of the SAME CTA have given up, so unfold drops to 72, group 4 to 48, and the epilogue rises to 144:
-// 256 x 144 + 256 x 72 + 128 x 48 = 61,440.  (A request beyond the pool would block for ever: the launcher checks the count.)
-constexpr int UNFOLD_WARPS = 8, LOADER_WARPS = 2 /* 1, 2 or 4 */, F1_MMA_WARP = 8 + UNFOLD_WARPS, F1_LOAD_WARP0 = 9 + UNFOLD_WARPS;
+// Warpgroups (setmaxnreg works on four consecutive warps): 0-1 epilogue, 2 unfold, 3 = MMA issuer, two loaders, one idle warp.
+// Registers: 512 threads start with 128 each (the whole file); a group can only grow by what the others of the SAME CTA
+// have given up, so unfold drops to 80, group 3 to 48, and the epilogue rises to 192: 256 x 192 + 128 x 80 + 128 x 48 = 65,536.
+// (A request beyond the pool would block for ever: the launcher checks the compiled register count.)
+constexpr int UNFOLD_WARPS = 4, LOADER_WARPS = 2 /* 1, 2 or 4 */, F1_MMA_WARP = 8 + UNFOLD_WARPS, F1_LOAD_WARP0 = 9 + UNFOLD_WARPS;
 constexpr int F1_THREADS = 32 * (12 + UNFOLD_WARPS);
-constexpr int F1_REGS_START = 96, F1_REGS_EPI = 144, F1_REGS_UNFOLD = 72, F1_REGS_LIGHT = 48;
-static_assert(F1_THREADS * F1_REGS_START == 256 * F1_REGS_EPI + 256 * F1_REGS_UNFOLD + 128 * F1_REGS_LIGHT, "register pool");
+constexpr int TILE_RING = 8;                 // tile_done barriers; FR_CAP / 128 tiles of run-ahead at most
+constexpr int F1_REGS_START = 128, F1_REGS_EPI = 192, F1_REGS_UNFOLD = 80, F1_REGS_LIGHT = 48;
+static_assert(F1_THREADS * F1_REGS_START == 256 * F1_REGS_EPI + 32 * UNFOLD_WARPS * F1_REGS_UNFOLD + 128 * F1_REGS_LIGHT, "register pool");
+static_assert(UNFOLD_WARPS == 4 || UNFOLD_WARPS == 8, "whole warpgroups");
 template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -733,6 +733,20 @@ __device__ __forceinline__ void chunk_from_words(const uint32_t (&w)[5], uint4 &
     hi.w = u8x2_to_h2(__byte_perm(w[4], ZERO_PIXEL, 0x7430));   // B4 0
 }
 
+// The same chunk in the 1024 + v format, straight from funnel-shifted source words (B, G, R, <any>): every half is the byte
+// 0x64 over a pixel byte, so a word is one PRMT against the constant, or PRMT + LOP3 where its halves come from two pixels.
+__device__ __forceinline__ void chunk_from_raw(const uint32_t (&w)[5], uint4 &lo, uint4 &hi) {
+    constexpr uint32_t K = 0x64646464u, K0 = 0x00006464u, M = 0x00ff00ffu, O = 0x64006400u;
+    lo.x = __byte_perm(w[0], K, 0x4142);                        // R0 G0
+    lo.y = (__byte_perm(w[0], w[1], 0x0600) & M) | O;           // B0 R1
+    lo.z = __byte_perm(w[1], K, 0x4041);                        // G1 B1
+    lo.w = __byte_perm(w[2], K, 0x4142);                        // R2 G2
+    hi.x = (__byte_perm(w[2], w[3], 0x0600) & M) | O;           // B2 R3
+    hi.y = __byte_perm(w[3], K, 0x4041);                        // G3 B3
+    hi.z = __byte_perm(w[4], K, 0x4142);                        // R4 G4
+    hi.w = __byte_perm(w[4], K0, 0x7640);                       // B4, then a true zero (its weights are zero)
+}
+
 template <int C, bool GATHER>
 __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Conv1Params p, const FusedSrc src) {
     using S = F1Smem<C>;
@@ -751,8 +765,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     uint64_t *raw_empty = raw_full + RAW_SLOTS_MAX;                             // [RAW_SLOTS_MAX]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + RAW_SLOTS_MAX);
     int *s_rows_done = reinterpret_cast<int *>(tmem_slot + 2);                  // [UNFOLD_WARPS] rows finished by each unfold warp
-    int *s_tiles_done = s_rows_done + UNFOLD_WARPS;                             // tiles whose MMAs have completed
-    int *s_rows_issued = s_tiles_done + 1;                                      // [LOADER_WARPS] rows issued by each loader
+    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;                            // [LOADER_WARPS] rows issued by each loader
+    uint64_t *tile_done = reinterpret_cast<uint64_t *>(s_rows_issued + 4);      // [TILE_RING] tile t's MMAs have completed
     float *s_par = reinterpret_cast<float *>(smem + S::OFF_PAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -765,10 +779,14 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     const int n_slots = 1 << src.log2_slots, slot_bytes = src.n_src * src.row_bytes;
 
     for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = p.bias[i]; s_par[C + i] = p.scale[i]; s_par[2 * C + i] = p.shift[i]; }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        s_par[i] = GATHER ? p.bias_magic[i] : p.bias[i]; s_par[C + i] = p.scale[i]; s_par[2 * C + i] = p.shift[i];
+    }
     // The only positions read before they are written: the row above the first frame (tile 0's view shifted by -P1w).
+    const uint32_t Z2 = GATHER ? 0x64006400u : 0u;           // two zero pixels values in the operand format
     for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
-        reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
+            make_uint4(Z2, Z2, Z2, i >= P1w ? (Z2 & 0xffffu) : Z2);
     for (int y = threadIdx.x; y < H; y += blockDim.x) {
         int r0, r1, b0 = 2048, b1 = 0;
         if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
@@ -783,11 +801,12 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     }
     if (plan.mode == RESIZE_LINEAR && plan.gather_step_x == 0)
         for (int x = threadIdx.x; x < plan.dst_w; x += blockDim.x) s_xtab[x] = make_int4(3 * plan.x0[x], 3 * plan.x1[x], plan.a0[x], plan.a1[x]);
-    if (threadIdx.x <= UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;   // ... s_tiles_done and s_rows_issued
+    if (threadIdx.x < UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;    // ... and s_rows_issued
     fence_proxy_async();
     if (threadIdx.x == 0) {
         for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], EPI_WARPS); }
         for (int s = 0; s < RAW_SLOTS_MAX; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
+        for (int s = 0; s < TILE_RING; ++s) mbar_init(&tile_done[s], 1);
         fence_barrier_init();
     }
     if (warp == F1_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -806,7 +825,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             // in-order waits on raw_empty never skip a phase)
             const int lw = warp - F1_LOAD_WARP0, total_rows = n_frames_cta * Hc;
             const int n_loaders = min(LOADER_WARPS, n_slots);
-            if (lw < n_loaders) {                                // (warp 19 only fills the warpgroup)
+            if (lw < n_loaders) {                                // (warp 15 only fills the warpgroup)
                 int fi = 0, y = lw, issued = 0;
                 for (int n = lw; n < total_rows; n += n_loaders, y += n_loaders) {
                     while (y >= Hc) { y -= Hc; ++fi; }
@@ -835,8 +854,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                 const int u_hi = min(total_u - 1, 3 * ((t * 128 + 127) / P1w + 1));
                 const int mine = lane & (UNFOLD_WARPS - 1);
                 const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
-                while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) {
-                }
+                while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(32);
                 __syncwarp();
                 tc_fence_after_sync();
                 if (tl && lane == 0 && t < 64) tl[1024 + t] = clock64();
@@ -850,8 +868,6 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                 for (int dy = 0; dy < 3; ++dy) {
                     mbar_wait(&acc_empty[dy], acc_phase ^ 1);
                     tc_fence_after_sync();
-                    // block row 2 of tile t-1 has been drained, so every MMA of tiles < t has completed: their ring positions are free
-                    if (dy == 2 && lane == 0) st_release_shared(s_tiles_done, t);
                     if (elect_one()) {
     #pragma unroll
                         for (int ks = 0; ks < 3; ++ks) {
@@ -860,6 +876,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                             umma_16bit(tmem_base + 3 * C * dy, da, db, idesc, ks > 0 ? 1u : 0u);
                         }
                         umma_commit(&acc_full[dy]);
+                        if (dy == 2) umma_commit(&tile_done[t & (TILE_RING - 1)]);   // tile t no longer reads the operand ring
                     }
                     __syncwarp();
                 }
@@ -871,66 +888,58 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
         reg_dealloc<F1_REGS_UNFOLD>();
         const int pwarp = warp - 8;
-        const int BS = 3 * plan.gather_step_x;               // integer-scale gather: bytes between resized pixels
-        const int n_loaders = min(LOADER_WARPS, n_slots);
+        const int n_loaders = min(LOADER_WARPS, n_slots), log2_loaders = n_loaders == 4 ? 2 : n_loaders == 2 ? 1 : 0;
+        // fast path constants: tap j of pooled column px starts at byte 3*off_x + BS*(3px - 1 + j), BS = 3*step_x; a part is
+        // 32 columns = 96*BS bytes further on (a multiple of 4), so the word offset of part 0 and the byte phase serve all parts
+        const int BS = 3 * plan.gather_step_x, PB = 96 * BS;
+        int off0[5];
+        uint32_t sel[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int b = 3 * plan.gather_off_x + BS * (3 * lane - 1 + j);
+            off0[j] = b & ~3;
+            sel[j] = 0x3210u + (uint32_t)(b & 3) * 0x1111u;
+        }
+        struct Row { int R, sub, slot; bool real; const uint8_t *q0; };
         int R = 0, sub = pwarp, fi = 0, py = 0;              // u = 3R + sub, R = fi * RPF + py
         while (sub >= 3) { sub -= 3; ++R; ++py; }
-        int tiles_seen = 0, rows_done = 0;
-        for (int u = pwarp; u < total_u; u += UNFOLD_WARPS) {
-            while (py >= RPF) { py -= RPF; ++fi; }
+        int tiles_waited = 0, rows_done = 0;
+        auto next_row = [&](Row &r, int &y_out) {            // describes the row (R, sub, fi, py) point at, waits until it may be
+            while (py >= RPF) { py -= RPF; ++fi; }           // produced (ring space, source row landed), then advances
             const int y = 3 * py + sub;
-            const bool real = y < H && (py < p.P1h || sub == 0);   // index P1h: row 3*P1h if the image has it, else zeros
-            const int n = fi * Hc + y, slot = n & (n_slots - 1);
+            r.real = y < H && (py < p.P1h || sub == 0);      // index P1h: row 3*P1h if the image has it, else zeros
+            const int n = fi * Hc + y;
+            r.slot = n & (n_slots - 1);
+            r.R = R; r.sub = sub; y_out = y;
+            r.q0 = s_raw + r.slot * slot_bytes;
             // positions [R*P1w, (R+1)*P1w) replace those FR_CAP earlier, last read by tile (pos - FR_CAP + P1w) / 128
             const int last_reader = ((R + 2) * P1w - 1 - FR_CAP) >> 7;      // arithmetic shift: negative = none
-            while (tiles_seen <= last_reader) tiles_seen = ld_acquire_shared(s_tiles_done);
-            const uint8_t *q0 = s_raw + slot * slot_bytes;
-            if (real) {
-                const int ld = n & (n_loaders - 1), want = (n >> (n_loaders == 4 ? 2 : n_loaders == 2 ? 1 : 0)) + 1;
-                while (ld_acquire_shared(&s_rows_issued[ld]) < want) {
-                }
-                mbar_wait(&raw_full[slot], (n >> src.log2_slots) & 1);
+            if (last_reader >= tiles_waited) {
+                mbar_wait(&tile_done[last_reader & (TILE_RING - 1)], (last_reader / TILE_RING) & 1);
+                tiles_waited = last_reader + 1;
             }
-            if (tl && pwarp == 0 && lane == 0 && rows_done < 128) tl[256 + rows_done] = clock64();
-            uint32_t w[NP][5];
-#pragma unroll
-            for (int part = 0; part < NP; ++part) {
-                const int px = part * 32 + lane;
-#pragma unroll
-                for (int j = 0; j < 5; ++j) w[part][j] = ZERO_PIXEL;
-                if (real && px < P1w) {
-                    if (GATHER) {
-                        const int base = 3 * plan.gather_off_x + BS * (3 * px - 1);
-#pragma unroll
-                        for (int j = 0; j < 5; ++j) {
-                            const int b = base + BS * j;
-                            const bool ok = (j > 0 || px > 0) && (j < 4 || 3 * px + 3 < plan.dst_w);
-                            const uint32_t *wp = reinterpret_cast<const uint32_t *>(q0 + (ok ? (b & ~3) : 0));
-                            const uint32_t v = __byte_perm(wp[0], wp[1], 0x3210u + (uint32_t)(b & 3) * 0x1111u);
-                            w[part][j] = ok ? ((v & 0x00FFFFFFu) | ZERO_PIXEL) : ZERO_PIXEL;
-                        }
-                    } else {
-                        const uint8_t *q1 = q0 + (src.n_src - 1) * src.row_bytes;
-                        const int b0 = s_yb[2 * y], b1 = s_yb[2 * y + 1];
-#pragma unroll
-                        for (int j = 0; j < 5; ++j) w[part][j] = resized_word(plan, q0, q1, s_xtab, b0, b1, 3 * px - 1 + j);
-                    }
-                }
+            if (r.real) {
+                const int ld = n & (n_loaders - 1), want = (n >> log2_loaders) + 1;
+                while (ld_acquire_shared(&s_rows_issued[ld]) < want) __nanosleep(32);
+                mbar_wait(&raw_full[r.slot], (n >> src.log2_slots) & 1);
             }
-            if (real) {
-                fence_proxy_async();                                     // these reads, then the async-proxy refill of the slot
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&raw_empty[slot]);            // the source row is in registers
-            }
+            sub += UNFOLD_WARPS % 3; R += UNFOLD_WARPS / 3; py += UNFOLD_WARPS / 3;
+            if (sub >= 3) { sub -= 3; ++R; ++py; }
+        };
+        auto emit = [&](const Row &r, uint32_t (&w)[NP][5]) {
+            const int pos0 = r.R * P1w + lane;
 #pragma unroll
             for (int part = 0; part < NP; ++part) {
                 const int px = part * 32 + lane;
                 if (px < P1w) {
                     uint4 lo, hi;
-                    chunk_from_words(w[part], lo, hi);
-                    if (!real) lo = hi = make_uint4(0, 0, 0, 0);
-                    const int pos = (R * P1w + px) & (FR_CAP - 1);
-                    uint8_t *dst = s_ring + sub * FR_SUB + pos * 16;
+                    if (GATHER) chunk_from_raw(w[part], lo, hi);         // zero rows: w = 0 gives the format's zeros
+                    else {
+                        chunk_from_words(w[part], lo, hi);
+                        if (!r.real) lo = hi = make_uint4(0, 0, 0, 0);
+                    }
+                    const int pos = (pos0 + part * 32) & (FR_CAP - 1);
+                    uint8_t *dst = s_ring + r.sub * FR_SUB + pos * 16;
                     *reinterpret_cast<uint4 *>(dst) = lo;
                     *reinterpret_cast<uint4 *>(dst + FR_PLANE) = hi;
                     if (pos < 128) {                                     // mirror past the end of the ring
@@ -939,13 +948,56 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                     }
                 }
             }
-            fence_proxy_async();                        // generic-proxy stores -> visible to the MMA's async-proxy reads
+        };
+        auto gather = [&](const Row &r, uint32_t (&w)[NP][5]) {
+            // (lanes past the last column and lane 0's tap -1 read a few bytes outside the row: still this CTA's shared memory)
+#pragma unroll
+            for (int part = 0; part < NP; ++part)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(r.q0 + part * PB + off0[j]);
+                    w[part][j] = r.real ? __byte_perm(wp[0], wp[1], sel[j]) : 0u;
+                }
+            if (lane == 0) w[0][0] = 0u;                                 // the padding column left of the image
+        };
+        // (taking two rows per step -- a second row's waits and loads in flight -- was tried: no gain, the SM's ALU pipe is the limit)
+        for (int u = pwarp; u < total_u; u += UNFOLD_WARPS) {
+            Row r0;
+            int y0;
+            next_row(r0, y0);
+            if (tl && pwarp == 0 && lane == 0 && rows_done < 128) tl[256 + rows_done] = clock64();
+            uint32_t w0[NP][5];
+            if (GATHER) {
+                gather(r0, w0);
+            } else {
+#pragma unroll
+                for (int part = 0; part < NP; ++part)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) w0[part][j] = ZERO_PIXEL;
+                if (r0.real) {
+                    const uint8_t *q1 = r0.q0 + (src.n_src - 1) * src.row_bytes;
+                    const int b0 = s_yb[2 * y0], b1 = s_yb[2 * y0 + 1];
+#pragma unroll
+                    for (int part = 0; part < NP; ++part) {
+                        const int px = part * 32 + lane;
+                        if (px < P1w) {
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) w0[part][j] = resized_word(plan, r0.q0, q1, s_xtab, b0, b1, 3 * px - 1 + j);
+                        }
+                    }
+                }
+            }
+            emit(r0, w0);
+            // one fence for both directions: the stores above become visible to the MMA's async-proxy reads, and the loads from
+            // the raw slot are ordered before the async-proxy refill that the release below allows
+            fence_proxy_async();
             __syncwarp();
             ++rows_done;
-            if (lane == 0) st_release_shared(&s_rows_done[pwarp], rows_done);
+            if (lane == 0) {
+                if (r0.real) mbar_arrive(&raw_empty[r0.slot]);
+                st_release_shared(&s_rows_done[pwarp], rows_done);
+            }
             if (tl && pwarp == 0 && lane == 0 && rows_done <= 128) tl[384 + rows_done - 1] = clock64();
-            sub += UNFOLD_WARPS % 3; R += UNFOLD_WARPS / 3; py += UNFOLD_WARPS / 3;
-            if (sub >= 3) { sub -= 3; ++R; ++py; }
         }
     } else {
         // ------------------------------------------------------------------ epilogue
@@ -956,23 +1008,28 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         for (int fi = 0; fi < n_frames_cta; ++fi) zero_pads(p.out, CG, blockIdx.x + fi * gridDim.x, blockIdx.x + fi * gridDim.x + 1, threadIdx.x, EPI_WARPS * 32);
         int X = m % P1w, Y = m / P1w, fi = 0;              // position 128 t + m = ((fi * RPF + Y) * P1w + X), advanced tile by tile
         while (Y >= RPF) { Y -= RPF; ++fi; }
-        EpiPair<CH> A;
+        EpiRow<CH> bufA, bufB;
         if (n_tiles > 0) {
             mbar_wait(&acc_full[0], 0);
             tc_fence_after_sync();
-            epi_issue_pair<C>(tmem_thread, 0, A, true);
+            epi_issue_row<C>(tmem_thread, 0, bufA);
         }
-        for (int t = 0; t < n_tiles; ++t) {
+        auto tile = [&](int t, EpiRow<CH> &cur, EpiRow<CH> &nxt) {
             const bool valid = fi < n_frames_cta && Y < p.P1h;
             float v[CH];
-            epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, A, v);
-            epilogue_affine<C>(s_par, ch0, v);
+            epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v,
+                                       (tl && threadIdx.x == 0 && t < 40) ? tl + 1280 + 10 * t : nullptr);
+            epilogue_affine<C>(s_par, ch0, GATHER ? 1.f / 256.f : 1.f, v);
             if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
             if (tl && threadIdx.x == 0 && t < 64) tl[1152 + t] = clock64();
             acc_phase ^= 1;
             X += 128;
             while (X >= P1w) { X -= P1w; ++Y; }
             while (Y >= RPF) { Y -= RPF; ++fi; }
+        };
+        for (int t = 0; t < n_tiles; t += 2) {          // the two buffers swap roles from one tile to the next
+            tile(t, bufA, bufB);
+            if (t + 1 < n_tiles) tile(t + 1, bufB, bufA);
         }
     }
     tc_fence_before_sync();
@@ -1212,6 +1269,7 @@ int make_act_map(CUtensorMap *map, void *base, int CG, int gtot) {
 struct TcState {
     int C = 0;
     void *d_w1 = nullptr, *d_w2 = nullptr, *d_w3 = nullptr;   // packed 16-bit operands
+    void *d_bias1_magic = nullptr;                             // conv1 bias for pixels entering as 1024 + v (fused gather path)
     std::map<std::tuple<const void *, int, int>, std::pair<CUtensorMap, CUtensorMap>> maps;   // (workspace, H*65536+W, sub) -> act1, act2 maps
     std::map<std::pair<int, int>, float *> fc1_folded;                                        // (P3h, P3w) -> [n_feat][32]
     std::mutex mutex;
@@ -1294,7 +1352,8 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src, cudaStream_t s
     }
     {
         KernelScope scope("conv1_fused_tc", stream);
-        if (src.plan.gather_step_x > 0) conv1_fused_tc_kernel<C, true><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
+        // fast path: integer-scale gather whose last pooled column has its right neighbour inside the image (dst_w % 3 != 0)
+        if (src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0 && !kBf16) conv1_fused_tc_kernel<C, true><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
         else conv1_fused_tc_kernel<C, false><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
     }
     CUTDET_LAUNCH_CHECK("conv1_fused_tc_kernel");
@@ -1374,6 +1433,7 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     c1.out = OutSpec{ws + w.act1, 0, w.gtot1, g.PW1, g.FP1, g.Q1h, 0, g.P1h, g.P1w};
     c1.w_packed = reinterpret_cast<const uint4 *>(tc->d_w1);
     c1.bias = net->conv[0].d_bias; c1.scale = net->conv[0].d_scale; c1.shift = net->conv[0].d_shift;
+    c1.bias_magic = reinterpret_cast<const float *>(tc->d_bias1_magic);
     if (fused) {
         FusedSrc fs = *fused;
         fs.frames += (long long)f0 * fs.frame_stride;
@@ -1559,6 +1619,17 @@ int tc_prepare(cutdet_net *net) {
                         }
                     }
         if (int rc = upload_bytes(net, w.data(), w.size() * 2, &tc->d_w1)) return rc;
+        // sum w1 * (1024 + v) / 256 = z + 4 * sum w1 over the 27 taps AS ROUNDED (dx = 0 holds each tap exactly once)
+        std::vector<float> bm(C);
+        for (int co = 0; co < C; ++co) {
+            double sum = 0;
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx)
+                    for (int ch = 0; ch < 3; ++ch)
+                        sum += (double)__half2float(__float2half_rn(L.w[((size_t)co * 3 + ch) * 9 + ky * 3 + kx] * kW1Scale));
+            bm[co] = (float)((double)L.bias[co] - 4.0 * sum);
+        }
+        if (int rc = upload_bytes(net, bm.data(), bm.size() * 4, &tc->d_bias1_magic)) return rc;
     }
     // conv2/3 B operand: [ky][ci/8][n' = blk*C + co, blk <-> kx = 2-blk][8]
     for (int layer = 1; layer <= 2; ++layer) {
