@@ -198,12 +198,14 @@ __device__ __forceinline__ void epi_issue_row(uint32_t tmem_thread, int dy, EpiR
 }
 
 // X: block row 0 of this tile, in flight on entry.  Y: free on entry; on exit it holds the next tile's block row 0 in flight.
+// The MMAs run well ahead of this code, so the full-barriers of rows 1 and 2 (and of the next tile's row 0) have normally
+// completed long before they are needed: they are polled EARLY, back to back, and the ~130-cycle round trip of a try_wait hides
+// behind the TMEM loads in flight; only a failed poll turns into a blocking wait.
 template <int C>
 __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, uint64_t *acc_full, uint64_t *acc_empty, uint32_t acc_phase,
                                                         int lane, bool more_tiles, EpiRow<C / 2> &X, EpiRow<C / 2> &Y,
-                                                        float (&run)[C / 2], long long *stamp = nullptr) {
+                                                        float (&run)[C / 2]) {
     constexpr int CH = C / 2;
-    if (stamp) stamp[0] = clock64();
     auto arrived = [&](EpiRow<CH> &q, int dy) {       // block row dy is in registers: hand it back to the MMA issuer
         tmem_ld_wait();
         reg_fence<CH>(q.a); reg_fence<CH>(q.b); reg_fence<CH>(q.c);
@@ -211,32 +213,26 @@ __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, ui
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[dy]);
     };
+    const bool f1 = mbar_try_wait(&acc_full[1], acc_phase), f2 = mbar_try_wait(&acc_full[2], acc_phase);
     arrived(X, 0);
-    if (stamp) stamp[1] = clock64();
-    mbar_wait(&acc_full[1], acc_phase);
+    if (!f1) mbar_wait(&acc_full[1], acc_phase);
     tc_fence_after_sync();
-    if (stamp) stamp[2] = clock64();
     epi_issue_row<C>(tmem_thread, 1, Y);
 #pragma unroll
     for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(X.a[i], X.b[i]), X.c[i]);
     reg_fence<CH>(run);
-    if (stamp) stamp[3] = clock64();
     arrived(Y, 1);
-    if (stamp) stamp[4] = clock64();
-    mbar_wait(&acc_full[2], acc_phase);
+    if (!f2) mbar_wait(&acc_full[2], acc_phase);
     tc_fence_after_sync();
-    if (stamp) stamp[5] = clock64();
     epi_issue_row<C>(tmem_thread, 2, X);
+    const bool f0 = more_tiles && mbar_try_wait(&acc_full[0], acc_phase ^ 1);
 #pragma unroll
     for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(fmaxf(run[i], Y.a[i]), Y.b[i]), Y.c[i]);
     reg_fence<CH>(run);
-    if (stamp) stamp[6] = clock64();
     arrived(X, 2);
-    if (stamp) stamp[7] = clock64();
     if (more_tiles) {
-        mbar_wait(&acc_full[0], acc_phase ^ 1);
+        if (!f0) mbar_wait(&acc_full[0], acc_phase ^ 1);
         tc_fence_after_sync();
-        if (stamp) stamp[8] = clock64();
         epi_issue_row<C>(tmem_thread, 0, Y);
     }
 #pragma unroll
@@ -1017,8 +1013,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         auto tile = [&](int t, EpiRow<CH> &cur, EpiRow<CH> &nxt) {
             const bool valid = fi < n_frames_cta && Y < p.P1h;
             float v[CH];
-            epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v,
-                                       (tl && threadIdx.x == 0 && t < 40) ? tl + 1280 + 10 * t : nullptr);
+            epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v);
             epilogue_affine<C>(s_par, ch0, GATHER ? 1.f / 256.f : 1.f, v);
             if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
             if (tl && threadIdx.x == 0 && t < 64) tl[1152 + t] = clock64();
