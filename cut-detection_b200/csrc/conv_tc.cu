@@ -44,6 +44,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <cmath>
+
 #include <map>
 #include <vector>
 #include <mutex>
@@ -201,7 +203,7 @@ __device__ __forceinline__ void epi_issue_row(uint32_t tmem_thread, int dy, EpiR
 // The MMAs run well ahead of this code, so the full-barriers of rows 1 and 2 (and of the next tile's row 0) have normally
 // completed long before they are needed: they are polled EARLY, back to back, and the ~130-cycle round trip of a try_wait hides
 // behind the TMEM loads in flight; only a failed poll turns into a blocking wait.
-template <int C>
+template <int C, bool RELU /* fold max(., 0) into the last step */>
 __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, uint64_t *acc_full, uint64_t *acc_empty, uint32_t acc_phase,
                                                         int lane, bool more_tiles, EpiRow<C / 2> &X, EpiRow<C / 2> &Y,
                                                         float (&run)[C / 2]) {
@@ -236,8 +238,27 @@ __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, ui
         epi_issue_row<C>(tmem_thread, 0, Y);
     }
 #pragma unroll
-    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(fmaxf(run[i], X.a[i]), X.b[i]), X.c[i]);
+    for (int i = 0; i < CH; ++i) {
+        const float m = fmaxf(fmaxf(run[i], X.a[i]), X.b[i]);
+        run[i] = RELU ? fmaxf(fmaxf(m, X.c[i]), 0.f) : fmaxf(m, X.c[i]);
+    }
     reg_fence<CH>(run);
+}
+
+// run = relu(accumulator incl. bias) on entry: scale (+-1/256) and shift only
+template <int C>
+__device__ __forceinline__ void epilogue_scale_shift(const float *s_par, int ch0, float (&run)[C / 2]) {
+    constexpr int CH = C / 2;
+    const float4 *scale4 = reinterpret_cast<const float4 *>(s_par + C + ch0);
+    const float4 *shift4 = reinterpret_cast<const float4 *>(s_par + 2 * C + ch0);
+#pragma unroll
+    for (int i = 0; i < CH / 4; ++i) {
+        const float4 s = scale4[i], t = shift4[i];
+        run[4 * i + 0] = fmaf(run[4 * i + 0], s.x, t.x);
+        run[4 * i + 1] = fmaf(run[4 * i + 1], s.y, t.y);
+        run[4 * i + 2] = fmaf(run[4 * i + 2], s.z, t.z);
+        run[4 * i + 3] = fmaf(run[4 * i + 3], s.w, t.w);
+    }
 }
 
 template <int C>
@@ -468,7 +489,8 @@ struct Conv1Params {
     const uint4 *w_packed;  // [ky][half][3C rows: dx=0 | dx=1 | dx=2][8] 16-bit, taps scaled by kW1Scale
     const float *bias, *scale, *shift;
     long long *timeline;    // debug: clock64 stamps of CTA 0 (null = off)
-    const float *bias_magic; // fused kernel, integer-scale gather: bias - 4 * sum of the layer's rounded taps (pixels enter as 1024 + v)
+    int folded;             // the taps carry |BN scale| and the bias row (the fast fused path needs it)
+    const float *scale_magic; // fused kernel, integer-scale gather: +-1/256 (bias and ReLU happen inside the MMA / the max, see tc_prepare)
 };
 
 template <int C>
@@ -688,10 +710,9 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
 //             Integer-scale gathers (720p, 1440p, 2160p -> 256 wide) take the fast path: per-lane word offsets and funnel
 //             selectors are computed once (the byte phase of tap j is the same in all three 32-column parts), and pixels enter
 //             the MMA as the fp16 numbers 1024 + v (bit pattern 0x6400 | v, exact): the chunk is a byte permutation of the
-//             source row.  acc = sum w * (1024 + v) = 256 * (z + 4 * sum w); the epilogue's first FFMA undoes it
-//             (z = acc / 256 + (bias - 4 * sum w), sum over the rounded taps, so padding pixels -- 1024 -- cancel exactly).
-//   MMA       tile t needs every row u <= 3 * ((128t + 127) / P1w + 1): lane w polls s_rows_done[w].
-//   epilogue  unchanged (three accumulator block rows with full/empty mbarriers).
+//             source row, and its 16th element is the constant 1024, which multiplies a weight row holding the bias
+//             (tc_prepare): acc = 256 * (|s| z + |s| bias) with |BatchNorm scale| folded into the taps, so the epilogue is
+//             relu inside the last max3, then one FFMA by +-1/256 and the BatchNorm shift.
 // Counters instead of per-tile mbarriers: a row is produced by ONE warp, tiles need rows from all of them, and a warp must never
 // have to wait for a tile it contributes nothing to (the lock-step version spent 2/3 of its time in such waits).
 // GATHER: the resize is out[y][x] = src[off_y + y*step_y][off_x + x*step_x] (every second tap has zero weight).
@@ -732,7 +753,7 @@ __device__ __forceinline__ void chunk_from_words(const uint32_t (&w)[5], uint4 &
 // The same chunk in the 1024 + v format, straight from funnel-shifted source words (B, G, R, <any>): every half is the byte
 // 0x64 over a pixel byte, so a word is one PRMT against the constant, or PRMT + LOP3 where its halves come from two pixels.
 __device__ __forceinline__ void chunk_from_raw(const uint32_t (&w)[5], uint4 &lo, uint4 &hi) {
-    constexpr uint32_t K = 0x64646464u, K0 = 0x00006464u, M = 0x00ff00ffu, O = 0x64006400u;
+    constexpr uint32_t K = 0x64646464u, K0 = 0x64006464u, M = 0x00ff00ffu, O = 0x64006400u;
     lo.x = __byte_perm(w[0], K, 0x4142);                        // R0 G0
     lo.y = (__byte_perm(w[0], w[1], 0x0600) & M) | O;           // B0 R1
     lo.z = __byte_perm(w[1], K, 0x4041);                        // G1 B1
@@ -740,7 +761,7 @@ __device__ __forceinline__ void chunk_from_raw(const uint32_t (&w)[5], uint4 &lo
     hi.x = (__byte_perm(w[2], w[3], 0x0600) & M) | O;           // B2 R3
     hi.y = __byte_perm(w[3], K, 0x4041);                        // G3 B3
     hi.z = __byte_perm(w[4], K, 0x4142);                        // R4 G4
-    hi.w = __byte_perm(w[4], K0, 0x7640);                       // B4, then a true zero (its weights are zero)
+    hi.w = __byte_perm(w[4], K0, 0x7640);                       // B4, then the constant 1024 that multiplies the bias row
 }
 
 template <int C, bool GATHER>
@@ -776,13 +797,13 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
 
     for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
-        s_par[i] = GATHER ? p.bias_magic[i] : p.bias[i]; s_par[C + i] = p.scale[i]; s_par[2 * C + i] = p.shift[i];
+        s_par[i] = p.bias[i]; s_par[C + i] = GATHER ? p.scale_magic[i] : p.scale[i]; s_par[2 * C + i] = p.shift[i];
     }
     // The only positions read before they are written: the row above the first frame (tile 0's view shifted by -P1w).
     const uint32_t Z2 = GATHER ? 0x64006400u : 0u;           // two zero pixels values in the operand format
     for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
         reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
-            make_uint4(Z2, Z2, Z2, i >= P1w ? (Z2 & 0xffffu) : Z2);
+            make_uint4(Z2, Z2, Z2, Z2);
     for (int y = threadIdx.x; y < H; y += blockDim.x) {
         int r0, r1, b0 = 2048, b1 = 0;
         if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
@@ -1013,8 +1034,9 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         auto tile = [&](int t, EpiRow<CH> &cur, EpiRow<CH> &nxt) {
             const bool valid = fi < n_frames_cta && Y < p.P1h;
             float v[CH];
-            epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v);
-            epilogue_affine<C>(s_par, ch0, GATHER ? 1.f / 256.f : 1.f, v);
+            epilogue_tile_pipelined<C, GATHER>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v);
+            if (GATHER) epilogue_scale_shift<C>(s_par, ch0, v);
+            else epilogue_affine<C>(s_par, ch0, 1.f, v);
             if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
             if (tl && threadIdx.x == 0 && t < 64) tl[1152 + t] = clock64();
             acc_phase ^= 1;
@@ -1264,7 +1286,9 @@ int make_act_map(CUtensorMap *map, void *base, int CG, int gtot) {
 struct TcState {
     int C = 0;
     void *d_w1 = nullptr, *d_w2 = nullptr, *d_w3 = nullptr;   // packed 16-bit operands
-    void *d_bias1_magic = nullptr;                             // conv1 bias for pixels entering as 1024 + v (fused gather path)
+    // conv1 with |BN scale| folded into its taps (see tc_prepare): epilogue parameters |s|*bias, sign(s), sign(s)/256
+    float *d_c1_bias = nullptr, *d_c1_sign = nullptr, *d_c1_sign256 = nullptr;
+    bool c1_folded = false;
     std::map<std::tuple<const void *, int, int>, std::pair<CUtensorMap, CUtensorMap>> maps;   // (workspace, H*65536+W, sub) -> act1, act2 maps
     std::map<std::pair<int, int>, float *> fc1_folded;                                        // (P3h, P3w) -> [n_feat][32]
     std::mutex mutex;
@@ -1348,7 +1372,7 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src, cudaStream_t s
     {
         KernelScope scope("conv1_fused_tc", stream);
         // fast path: integer-scale gather whose last pooled column has its right neighbour inside the image (dst_w % 3 != 0)
-        if (src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0 && !kBf16) conv1_fused_tc_kernel<C, true><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
+        if (src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0 && !kBf16 && p.folded) conv1_fused_tc_kernel<C, true><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
         else conv1_fused_tc_kernel<C, false><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
     }
     CUTDET_LAUNCH_CHECK("conv1_fused_tc_kernel");
@@ -1427,8 +1451,11 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     c1.tiles_per_frame = (g.P1h * g.P1w + 127) / 128;
     c1.out = OutSpec{ws + w.act1, 0, w.gtot1, g.PW1, g.FP1, g.Q1h, 0, g.P1h, g.P1w};
     c1.w_packed = reinterpret_cast<const uint4 *>(tc->d_w1);
-    c1.bias = net->conv[0].d_bias; c1.scale = net->conv[0].d_scale; c1.shift = net->conv[0].d_shift;
-    c1.bias_magic = reinterpret_cast<const float *>(tc->d_bias1_magic);
+    c1.bias = tc->c1_folded ? tc->d_c1_bias : net->conv[0].d_bias;
+    c1.scale = tc->c1_folded ? tc->d_c1_sign : net->conv[0].d_scale;
+    c1.shift = net->conv[0].d_shift;
+    c1.scale_magic = tc->d_c1_sign256;
+    c1.folded = tc->c1_folded ? 1 : 0;
     if (fused) {
         FusedSrc fs = *fused;
         fs.frames += (long long)f0 * fs.frame_stride;
@@ -1597,34 +1624,54 @@ int tc_prepare(cutdet_net *net) {
     TcState *tc = new TcState();
     tc->C = C;
     net->tc = tc;
-    // conv1 B operand: [ky][half][n = dx*C + co][8], k16 = col*3 + ch, taps / 255
+    // conv1 B operand: [ky][half][n = dx*C + co][8], k16 = col*3 + ch, taps / 255.
+    // |BN scale| is folded into the taps (s * relu(u) = sign(s) * relu(|s| * u)), so the epilogue is relu(max + |s|*bias) * sign + shift;
+    // and K element 15, which no pixel uses, carries the bias for the fused gather path: there the pixels enter as 1024 + v and
+    // that element is the constant 1024, so with taps w'' and W = sum of the 27 rounded taps,
+    //     acc = sum w'' (1024 + v) + 1024 * (wb0 + wb1 + wb2) = 256 * (z'' + 4W) + 1024 * wb,   wb = (|s|*bias - 4W) / 4 in three fp16 pieces
+    // = 256 * (z'' + |s|*bias): bias and ReLU need no instruction of their own.  (Other paths leave element 15 at zero.)
     {
         std::vector<uint16_t> w((size_t)6 * 3 * C * 8, 0);
         const ConvLayer &L = net->conv[0];
-        for (int ky = 0; ky < 3; ++ky)
-            for (int col = 0; col < 5; ++col)
-                for (int ch = 0; ch < 3; ++ch)
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int kx = col - dx;
-                        if (kx < 0 || kx > 2) continue;
-                        const int k16 = col * 3 + ch;
-                        for (int co = 0; co < C; ++co) {
-                            const float v = L.w[((size_t)co * 3 + ch) * 9 + ky * 3 + kx] * kW1Scale;
-                            w[(((size_t)(2 * ky + k16 / 8)) * 3 * C + dx * C + co) * 8 + k16 % 8] = operand_bits(v);
-                        }
-                    }
-        if (int rc = upload_bytes(net, w.data(), w.size() * 2, &tc->d_w1)) return rc;
-        // sum w1 * (1024 + v) / 256 = z + 4 * sum w1 over the 27 taps AS ROUNDED (dx = 0 holds each tap exactly once)
-        std::vector<float> bm(C);
-        for (int co = 0; co < C; ++co) {
-            double sum = 0;
-            for (int ky = 0; ky < 3; ++ky)
-                for (int kx = 0; kx < 3; ++kx)
-                    for (int ch = 0; ch < 3; ++ch)
-                        sum += (double)__half2float(__float2half_rn(L.w[((size_t)co * 3 + ch) * 9 + ky * 3 + kx] * kW1Scale));
-            bm[co] = (float)((double)L.bias[co] - 4.0 * sum);
+        bool fold = !kBf16;
+        for (int co = 0; co < C && fold; ++co) {
+            const float a = fabsf(L.scale[co]);
+            if (!std::isfinite(a)) fold = false;
+            for (int i = 0; i < 27 && fold; ++i)
+                if (!(fabsf(L.w[(size_t)co * 27 + i] * kW1Scale * a) < 16384.f)) fold = false;
         }
-        if (int rc = upload_bytes(net, bm.data(), bm.size() * 4, &tc->d_bias1_magic)) return rc;
+        tc->c1_folded = fold;
+        std::vector<float> pb(C), ps(C), ps256(C);
+        for (int co = 0; co < C; ++co) {
+            const float a = fold ? fabsf(L.scale[co]) : 1.f;
+            double W = 0;
+            for (int ky = 0; ky < 3; ++ky)
+                for (int col = 0; col < 5; ++col)
+                    for (int ch = 0; ch < 3; ++ch)
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int kx = col - dx;
+                            if (kx < 0 || kx > 2) continue;
+                            const int k16 = col * 3 + ch;
+                            const uint16_t bits = operand_bits(L.w[((size_t)co * 3 + ch) * 9 + ky * 3 + kx] * kW1Scale * a);
+                            w[(((size_t)(2 * ky + k16 / 8)) * 3 * C + dx * C + co) * 8 + k16 % 8] = bits;
+                            if (dx == 0 && !kBf16) W += (double)__half2float(__ushort_as_half(bits));
+                        }
+            pb[co] = a * L.bias[co];
+            ps[co] = L.scale[co] < 0.f ? -1.f : 1.f;
+            ps256[co] = ps[co] / 256.f;
+            if (fold) {
+                double rest = ((double)pb[co] - 4.0 * W) / 4.0;
+                for (int ky = 0; ky < 3; ++ky) {
+                    const __half piece = __float2half_rn((float)rest);
+                    rest -= (double)__half2float(piece);
+                    for (int dx = 0; dx < 3; ++dx) w[(((size_t)(2 * ky + 1)) * 3 * C + dx * C + co) * 8 + 7] = __half_as_ushort(piece);
+                }
+            }
+        }
+        if (int rc = upload_bytes(net, w.data(), w.size() * 2, &tc->d_w1)) return rc;
+        if (int rc = upload_bytes(net, pb.data(), C * 4, reinterpret_cast<void **>(&tc->d_c1_bias))) return rc;
+        if (int rc = upload_bytes(net, ps.data(), C * 4, reinterpret_cast<void **>(&tc->d_c1_sign))) return rc;
+        if (int rc = upload_bytes(net, ps256.data(), C * 4, reinterpret_cast<void **>(&tc->d_c1_sign256))) return rc;
     }
     // conv2/3 B operand: [ky][ci/8][n' = blk*C + co, blk <-> kx = 2-blk][8]
     for (int layer = 1; layer <= 2; ++layer) {

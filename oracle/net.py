@@ -202,7 +202,7 @@ def forward_tc_emulated(weights: dict, x: np.ndarray, avg_pool_size: int, fmt: s
     """What the tensor-core path computes, restated on the CPU: conv operands rounded to 16 bits (fmt 'f16' as
     cut-detection_b200/csrc/conv_tc.cu ships, or 'bf16'), layer-1 input stored as x*255/256 with 256/255 folded into its
     weights (bf16: x*255 and 1/255), exact products, float32 epilogue (max-pool of the raw sums, +bias, ReLU, folded
-    BatchNorm affine), 16-bit inter-layer activations, float32 head.  It separates 'the kernel is wrong' from
+    BatchNorm affine; layer 1 carries |scale| in its taps), 16-bit inter-layer activations, float32 head.  It separates 'the kernel is wrong' from
     '16-bit operands round': the CUDA path must match THIS to ~1e-3, and this differs from the fp32 reference by the
     rounding the format implies."""
     import torch
@@ -225,9 +225,16 @@ def forward_tc_emulated(weights: dict, x: np.ndarray, avg_pool_size: int, fmt: s
             s = (g / np.sqrt(np.asarray(weights[p + ".bn.running_var"], np.float64) + BN_EPS)).astype(np.float32)
             sh = (np.asarray(weights[p + ".bn.bias"], np.float64)
                   - np.asarray(weights[p + ".bn.running_mean"], np.float64) * s.astype(np.float64)).astype(np.float32)
+            bias = np.asarray(weights[p + ".conv.bias"], np.float32)
+            if i == 0 and fmt == "f16":
+                # conv_tc.cu folds |BatchNorm scale| into the layer-1 taps BEFORE rounding them (s * relu(u) = sign(s) * relu(|s| u)),
+                # which frees the fused kernel's epilogue of the bias add and the ReLU
+                w = w * np.abs(s).reshape(-1, 1, 1, 1)
+                bias = bias * np.abs(s)
+                s = np.where(s < 0, np.float32(-1), np.float32(1)).astype(np.float32)
             z = F.conv2d(y.double(), t(rnd(w)).double(), None, stride=1, padding=1).float()
             z = F.max_pool2d(z, kernel_size=3)
-            z = torch.relu(z + t(weights[p + ".conv.bias"]).view(1, -1, 1, 1))
+            z = torch.relu(z + t(bias).view(1, -1, 1, 1))
             z = z * t(s).view(1, -1, 1, 1) + t(sh).view(1, -1, 1, 1)
             if i < n - 1:
                 z = t(rnd(z.numpy()))
