@@ -354,20 +354,21 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
     uint64_t *empty = full + MID_STAGES;
     uint64_t *acc_full = empty + MID_STAGES;
     uint64_t *acc_empty = acc_full + 3;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 3);
+    uint64_t *w_full = acc_empty + 3;                      // the packed taps have landed (bulk copy issued by the producer warp)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
     float *s_par = reinterpret_cast<float *>(s_tail + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[0] = clock64();
     if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[128 + 4 * blockIdx.x] = g; }
 
-    // one-time setup
-    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
+    // one-time setup.  The 41 KB of taps come by bulk copy, issued by the producer warp together with its first stages, so the
+    // pipeline fills while they are in flight (copying them with LDG/STS before the first TMA cost ~2 us per launch).
     for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = p.bias[i]; s_par[C + i] = p.scale[i]; s_par[2 * C + i] = p.shift[i]; }
-    fence_proxy_async();             // the weights were written through the generic proxy; the MMA reads via the async proxy
     if (threadIdx.x == 0) {
         for (int s = 0; s < MID_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], EPI_WARPS); }
+        mbar_init(w_full, 1);
         fence_barrier_init();
         tma_prefetch_desc(&in_map);
     }
@@ -380,6 +381,12 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
     if (warp == 8) {
         // ------------------------------------------------------------------ TMA producer (lane 0 issues)
         uint32_t stage = 0, phase = 0;
+        if (elect_one()) {
+            mbar_arrive_expect_tx(w_full, S::W_BYTES);
+            for (int ky = 0; ky < 3; ++ky)
+                bulk_load_1d(s_w + ky * S::W_KY_BYTES, reinterpret_cast<const uint8_t *>(p.w_packed) + ky * S::W_KY_BYTES, S::W_KY_BYTES, w_full);
+        }
+        __syncwarp();
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             for (int ks = 0; ks < KS; ++ks) {
                 mbar_wait(&empty[stage], phase ^ 1);
@@ -402,6 +409,7 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
         if (tl && lane == 0) tl[tli] = clock64();
         ++tli;
         bool first_stamp = true;
+        mbar_wait(w_full, 0);
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             for (int ks = 0; ks < KS; ++ks) {
                 mbar_wait(&full[stage], phase);
