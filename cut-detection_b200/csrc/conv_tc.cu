@@ -68,7 +68,7 @@ constexpr float kW1Scale = kBf16 ? 1.f / 255.f : 256.f / 255.f; // ... and its w
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) { return kBf16 ? pack_bf16x2(lo, hi) : pack_f16x2_sat(lo, hi); }
 
 constexpr int SUB_BATCH = 148;          // frames per pass through conv1/conv2: their activations stay L2-resident
-constexpr int GROUP = 4;                // sub-batches whose layer-2 maps are gathered for ONE conv3 launch (fills the SMs)
+constexpr int GROUP = 8;                // sub-batches whose layer-2 maps are gathered for ONE conv3 launch (fills the SMs)
 constexpr int TMEM_COLS = 512;
 constexpr int MID_STAGES = 3;
 constexpr int MID_WIN = 192;            // positions per (plane, channel group) in a stage: 32 halo + 128 + 32 halo
@@ -851,6 +851,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             const int lw = warp - F1_LOAD_WARP0, total_rows = n_frames_cta * Hc;
             const int n_loaders = min(LOADER_WARPS, n_slots);
             if (lw < n_loaders) {                                // (warp 15 only fills the warpgroup)
+                const uint64_t stream_once = l2_policy_evict_first();   // frames are read once: keep the L2 for the activations
                 int fi = 0, y = lw, issued = 0;
                 for (int n = lw; n < total_rows; n += n_loaders, y += n_loaders) {
                     while (y >= Hc) { y -= Hc; ++fi; }
@@ -862,8 +863,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                         const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
                         mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
                         for (int j = 0; j < src.n_src; ++j)
-                            bulk_load_1d(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * y + j], (uint32_t)src.row_bytes,
-                                         &raw_full[slot]);
+                            bulk_load_1d_hint(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * y + j],
+                                              (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
                         st_release_shared(&s_rows_issued[lw], issued);   // raw_full[slot] is now in row n's phase
                     }
                     __syncwarp();

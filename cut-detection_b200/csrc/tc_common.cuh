@@ -95,6 +95,19 @@ __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gmem_sr
                  : "memory");
 }
 
+// ... with an L2 eviction policy: read-once streams (the decoded frames) take `evict_first` so they do not push the
+// activations that the next kernel re-reads out of the L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
 // L2 prefetch of a contiguous range (no destination): hides HBM latency ahead of a bulk_load_1d of the same bytes.
 __device__ __forceinline__ void bulk_prefetch_l2(const void *gmem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
