@@ -187,8 +187,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_thread /* lane quart
 // x16 load, 255 for six), so the tile is read in as few batches as possible -- its three block rows -- and the batch of the
 // next block row is in flight while the running max takes in the current one: two buffers of 3 * CH registers plus the
 // running max, 7 * CH = 168 at C = 48, which is why the epilogue warps raise their register budget with setmaxnreg.
-// Block row 0 of the NEXT tile is requested before the bias/ReLU/BatchNorm/store of this one.  Per channel: max3, then twice
-// max3 + max (FMNMX3), the same five operations as the unpipelined version.
+// Block row 0 of the NEXT tile is requested before the BatchNorm/store of this one.  Per channel: max3, max3 + max, max3 + max3
+// with zero (FMNMX3): five operations, ReLU included.
 template <int CH>
 struct EpiRow { float a[CH], b[CH], c[CH]; };
 
@@ -203,7 +203,7 @@ __device__ __forceinline__ void epi_issue_row(uint32_t tmem_thread, int dy, EpiR
 // The MMAs run well ahead of this code, so the full-barriers of rows 1 and 2 (and of the next tile's row 0) have normally
 // completed long before they are needed: they are polled EARLY, back to back, and the ~130-cycle round trip of a try_wait hides
 // behind the TMEM loads in flight; only a failed poll turns into a blocking wait.
-template <int C, bool RELU /* fold max(., 0) into the last step */>
+template <int C>
 __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, uint64_t *acc_full, uint64_t *acc_empty, uint32_t acc_phase,
                                                         int lane, bool more_tiles, EpiRow<C / 2> &X, EpiRow<C / 2> &Y,
                                                         float (&run)[C / 2]) {
@@ -240,7 +240,7 @@ __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, ui
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
         const float m = fmaxf(fmaxf(run[i], X.a[i]), X.b[i]);
-        run[i] = RELU ? fmaxf(fmaxf(m, X.c[i]), 0.f) : fmaxf(m, X.c[i]);
+        run[i] = fmaxf(fmaxf(m, X.c[i]), 0.f);          // the ReLU rides in the last max3 (the bias is inside the accumulator)
     }
     reg_fence<CH>(run);
 }
@@ -258,22 +258,6 @@ __device__ __forceinline__ void epilogue_scale_shift(const float *s_par, int ch0
         run[4 * i + 1] = fmaf(run[4 * i + 1], s.y, t.y);
         run[4 * i + 2] = fmaf(run[4 * i + 2], s.z, t.z);
         run[4 * i + 3] = fmaf(run[4 * i + 3], s.w, t.w);
-    }
-}
-
-template <int C>
-__device__ __forceinline__ void epilogue_affine(const float *s_par, int ch0, float acc_scale, float (&run)[C / 2]) {
-    constexpr int CH = C / 2;
-    const float4 *bias4 = reinterpret_cast<const float4 *>(s_par + ch0);
-    const float4 *scale4 = reinterpret_cast<const float4 *>(s_par + C + ch0);
-    const float4 *shift4 = reinterpret_cast<const float4 *>(s_par + 2 * C + ch0);
-#pragma unroll
-    for (int i = 0; i < CH / 4; ++i) {
-        const float4 b = bias4[i], s = scale4[i], t = shift4[i];
-        run[4 * i + 0] = fmaf(fmaxf(fmaf(run[4 * i + 0], acc_scale, b.x), 0.f), s.x, t.x);
-        run[4 * i + 1] = fmaf(fmaxf(fmaf(run[4 * i + 1], acc_scale, b.y), 0.f), s.y, t.y);
-        run[4 * i + 2] = fmaf(fmaxf(fmaf(run[4 * i + 2], acc_scale, b.z), 0.f), s.z, t.z);
-        run[4 * i + 3] = fmaf(fmaxf(fmaf(run[4 * i + 3], acc_scale, b.w), 0.f), s.w, t.w);
     }
 }
 
@@ -643,7 +627,7 @@ constexpr int FR_SUB = 2 * FR_PLANE;
 constexpr int RAW_BYTES = 65536;
 constexpr int RAW_SLOTS_MAX = 16;
 constexpr int F_MAX_DST = 256;
-constexpr uint32_t ZERO_PIXEL = 0x64000000u;
+constexpr int F1_CMP_WARPS = 4, F1_CMP_STRIDE = F_MAX_DST + 8;   // [0] = the pixel left of the image, [1 + x] = pixel x, zeros after
 
 struct FusedSrc {
     ResizePlanDev plan;
@@ -662,27 +646,20 @@ struct F1Smem {
     static constexpr int OFF_RING = W_BYTES;
     static constexpr int OFF_RAW = OFF_RING + 3 * FR_SUB;
     static constexpr int OFF_TAB = OFF_RAW + RAW_BYTES + 64;           // 64 bytes of slack: the gather reads one word past a row
-    static constexpr int OFF_BAR = OFF_TAB + F_MAX_DST * (8 + 8 + 16);  // rowoff[256][2], yb[256][2], xtab[256] (int4)
+    static constexpr int OFF_CMP = OFF_TAB + F_MAX_DST * (8 + 8 + 16);  // rowoff[256][2], yb[256][2], xtab[256] (int4)
+    static constexpr int OFF_BAR = OFF_CMP + F1_CMP_WARPS * F1_CMP_STRIDE * 4;   // one resized row per unfold warp (general resize)
     static constexpr int OFF_PAR = OFF_BAR + 512;
     static constexpr int total = OFF_PAR + 3 * C * 4;
 };
 
-__device__ __forceinline__ uint32_t u8x2_to_h2(uint32_t magic_pair) {
-    // magic_pair = two fp16 values 1024 + v (bit pattern 0x6400 | v): (1024 + v) * 2^-8 - 4 = v / 256, exact
-    const __half2 k = __floats2half2_rn(1.f / 256.f, 1.f / 256.f), m4 = __floats2half2_rn(-4.f, -4.f);
-    __half2 h = *reinterpret_cast<__half2 *>(&magic_pair);
-    h = __hfma2(h, k, m4);
-    return *reinterpret_cast<uint32_t *>(&h);
-}
-
-// One resized pixel as a (B, G, R, 0x64) word, from the source rows staged in shared memory.
+// One resized pixel x (inside the image) as a (B, G, R, 0) word, from the source rows staged in shared memory: bit-exact
+// with cv2.resize(INTER_LINEAR) (reference frameID/data.py:197-222).
 __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, const uint8_t *q0, const uint8_t *q1, const int4 *s_xtab,
                                                  int b0, int b1, int x) {
-    if (x < 0 || x >= plan.dst_w) return ZERO_PIXEL;
     if (plan.gather_step_x > 0) {
         const int b = 3 * (plan.gather_off_x + x * plan.gather_step_x);
         const uint32_t *wp = reinterpret_cast<const uint32_t *>(q0 + (b & ~3));
-        return (__funnelshift_r(wp[0], wp[1], (b & 3) * 8) & 0x00FFFFFFu) | ZERO_PIXEL;
+        return __funnelshift_r(wp[0], wp[1], (b & 3) * 8) & 0x00FFFFFFu;
     }
     int v[3];
     if (plan.mode == RESIZE_COPY) {
@@ -699,7 +676,7 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
             v[c] = min(max((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2, 0), 255);
         }
     }
-    return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ZERO_PIXEL;
+    return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16);
 }
 
 // 512 threads: warps 0..7 = epilogue, 8..11 = unfold, 12 = MMA issuer (+ TMEM alloc), 13..14 = loaders, 15 idle.
@@ -715,12 +692,14 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
 //             and waits for tile_done[t % 8] (committed by the MMA issuer after tile t's last MMA) before overwriting positions
 //             tile t still reads; the row it then writes is needed by tile t + 7 at the latest, so that barrier is never more
 //             than one phase ahead of a waiter.
-//             Integer-scale gathers (720p, 1440p, 2160p -> 256 wide) take the fast path: per-lane word offsets and funnel
-//             selectors are computed once (the byte phase of tap j is the same in all three 32-column parts), and pixels enter
-//             the MMA as the fp16 numbers 1024 + v (bit pattern 0x6400 | v, exact): the chunk is a byte permutation of the
-//             source row, and its 16th element is the constant 1024, which multiplies a weight row holding the bias
-//             (tc_prepare): acc = 256 * (|s| z + |s| bias) with |BatchNorm scale| folded into the taps, so the epilogue is
+//             Pixels enter the MMA as the fp16 numbers 1024 + v (bit pattern 0x6400 | v, exact), so a chunk is a byte permutation
+//             of five (B, G, R) words; its 16th element is the constant 1024, which multiplies a weight row holding the bias
+//             (tc_prepare): acc = 256 * (|s| z + |s| bias) with |BatchNorm scale| folded into the taps, and the epilogue is
 //             relu inside the last max3, then one FFMA by +-1/256 and the BatchNorm shift.
+//             Integer-scale gathers (720p, 1440p, 2160p -> 256 wide; template GATHER) funnel-shift those words straight out of
+//             the source row: per-lane word offsets and selectors are computed once (the byte phase of tap j is the same in all
+//             three 32-column parts).  Every other resize first writes the resized row -- each pixel computed once, OpenCV's
+//             fixed-point bilinear -- into a 1 KB per-warp buffer and unfolds from there (five consecutive words per column).
 // Counters instead of per-tile mbarriers: a row is produced by ONE warp, tiles need rows from all of them, and a warp must never
 // have to wait for a tile it contributes nothing to (the lock-step version spent 2/3 of its time in such waits).
 // GATHER: the resize is out[y][x] = src[off_y + y*step_y][off_x + x*step_x] (every second tap has zero weight).
@@ -746,20 +725,9 @@ __device__ __forceinline__ int ld_acquire_shared(const int *p) {
     return v;
 }
 
-// Sixteen halves of one K-chunk from five (B, G, R, 0x64) words: RGB of pixels 0..4, then one zero.
-__device__ __forceinline__ void chunk_from_words(const uint32_t (&w)[5], uint4 &lo, uint4 &hi) {
-    lo.x = u8x2_to_h2(__byte_perm(w[0], w[0], 0x3132));     // R0 G0
-    lo.y = u8x2_to_h2(__byte_perm(w[0], w[1], 0x7630));     // B0 R1
-    lo.z = u8x2_to_h2(__byte_perm(w[1], w[1], 0x3031));     // G1 B1
-    lo.w = u8x2_to_h2(__byte_perm(w[2], w[2], 0x3132));     // R2 G2
-    hi.x = u8x2_to_h2(__byte_perm(w[2], w[3], 0x7630));     // B2 R3
-    hi.y = u8x2_to_h2(__byte_perm(w[3], w[3], 0x3031));     // G3 B3
-    hi.z = u8x2_to_h2(__byte_perm(w[4], w[4], 0x3132));     // R4 G4
-    hi.w = u8x2_to_h2(__byte_perm(w[4], ZERO_PIXEL, 0x7430));   // B4 0
-}
-
-// The same chunk in the 1024 + v format, straight from funnel-shifted source words (B, G, R, <any>): every half is the byte
-// 0x64 over a pixel byte, so a word is one PRMT against the constant, or PRMT + LOP3 where its halves come from two pixels.
+// Sixteen halves of one K-chunk in the 1024 + v format from five source words (B, G, R, <any>): RGB of pixels 0..4, then the
+// constant 1024.  Every half is the byte 0x64 over a pixel byte, so a word is one PRMT against the constant, or PRMT + LOP3
+// where its halves come from two pixels.
 __device__ __forceinline__ void chunk_from_raw(const uint32_t (&w)[5], uint4 &lo, uint4 &hi) {
     constexpr uint32_t K = 0x64646464u, K0 = 0x64006464u, M = 0x00ff00ffu, O = 0x64006400u;
     lo.x = __byte_perm(w[0], K, 0x4142);                        // R0 G0
@@ -784,6 +752,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     int *s_rowoff = reinterpret_cast<int *>(smem + S::OFF_TAB);               // [y][2]
     int *s_yb = s_rowoff + 2 * F_MAX_DST;                                       // [y][2]: b0, b1
     int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);              // [x]: 3*x0, 3*x1, a0, a1
+    uint32_t *s_cmp = reinterpret_cast<uint32_t *>(smem + S::OFF_CMP);          // [unfold warp][F1_CMP_STRIDE]
     uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);
     uint64_t *acc_empty = acc_full + 3;
     uint64_t *raw_full = acc_empty + 3;                                         // [RAW_SLOTS_MAX]
@@ -805,10 +774,11 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
 
     for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
-        s_par[i] = p.bias[i]; s_par[C + i] = GATHER ? p.scale_magic[i] : p.scale[i]; s_par[2 * C + i] = p.shift[i];
+        s_par[i] = p.bias[i]; s_par[C + i] = p.scale_magic[i]; s_par[2 * C + i] = p.shift[i];
     }
     // The only positions read before they are written: the row above the first frame (tile 0's view shifted by -P1w).
-    const uint32_t Z2 = GATHER ? 0x64006400u : 0u;           // two zero pixels values in the operand format
+    const uint32_t Z2 = 0x64006400u;                          // two zero pixel values in the operand format
+    for (int i = threadIdx.x; i < F1_CMP_WARPS * F1_CMP_STRIDE; i += blockDim.x) s_cmp[i] = 0u;
     for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
         reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
             make_uint4(Z2, Z2, Z2, Z2);
@@ -959,11 +929,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                 const int px = part * 32 + lane;
                 if (px < P1w) {
                     uint4 lo, hi;
-                    if (GATHER) chunk_from_raw(w[part], lo, hi);         // zero rows: w = 0 gives the format's zeros
-                    else {
-                        chunk_from_words(w[part], lo, hi);
-                        if (!r.real) lo = hi = make_uint4(0, 0, 0, 0);
-                    }
+                    chunk_from_raw(w[part], lo, hi);                     // zero rows: w = 0 gives the format's zeros
                     const int pos = (pos0 + part * 32) & (FR_CAP - 1);
                     uint8_t *dst = s_ring + r.sub * FR_SUB + pos * 16;
                     *reinterpret_cast<uint4 *>(dst) = lo;
@@ -996,21 +962,19 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             if (GATHER) {
                 gather(r0, w0);
             } else {
-#pragma unroll
-                for (int part = 0; part < NP; ++part)
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) w0[part][j] = ZERO_PIXEL;
+                // the resized row, each pixel once, into this warp's buffer; then five consecutive words per pooled column
+                uint32_t *cmp = s_cmp + pwarp * F1_CMP_STRIDE;
                 if (r0.real) {
                     const uint8_t *q1 = r0.q0 + (src.n_src - 1) * src.row_bytes;
                     const int b0 = s_yb[2 * y0], b1 = s_yb[2 * y0 + 1];
+                    for (int x = lane; x < plan.dst_w; x += 32) cmp[1 + x] = resized_word(plan, r0.q0, q1, s_xtab, b0, b1, x);
+                }
+                __syncwarp();
 #pragma unroll
-                    for (int part = 0; part < NP; ++part) {
-                        const int px = part * 32 + lane;
-                        if (px < P1w) {
+                for (int part = 0; part < NP; ++part) {
+                    const int px = part * 32 + lane;
 #pragma unroll
-                            for (int j = 0; j < 5; ++j) w0[part][j] = resized_word(plan, r0.q0, q1, s_xtab, b0, b1, 3 * px - 1 + j);
-                        }
-                    }
+                    for (int j = 0; j < 5; ++j) w0[part][j] = (r0.real && px < P1w) ? cmp[3 * px + j] : 0u;
                 }
             }
             emit(r0, w0);
@@ -1043,9 +1007,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         auto tile = [&](int t, EpiRow<CH> &cur, EpiRow<CH> &nxt) {
             const bool valid = fi < n_frames_cta && Y < p.P1h;
             float v[CH];
-            epilogue_tile_pipelined<C, GATHER>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v);
-            if (GATHER) epilogue_scale_shift<C>(s_par, ch0, v);
-            else epilogue_affine<C>(s_par, ch0, 1.f, v);
+            epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v);
+            epilogue_scale_shift<C>(s_par, ch0, v);
             if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
             if (tl && threadIdx.x == 0 && t < 64) tl[1152 + t] = clock64();
             acc_phase ^= 1;
@@ -1381,7 +1344,7 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src, cudaStream_t s
     {
         KernelScope scope("conv1_fused_tc", stream);
         // fast path: integer-scale gather whose last pooled column has its right neighbour inside the image (dst_w % 3 != 0)
-        if (src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0 && !kBf16 && p.folded) conv1_fused_tc_kernel<C, true><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
+        if (src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0) conv1_fused_tc_kernel<C, true><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
         else conv1_fused_tc_kernel<C, false><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
     }
     CUTDET_LAUNCH_CHECK("conv1_fused_tc_kernel");
@@ -1741,7 +1704,7 @@ int tc_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cut
         return CUTDET_OK;
     };
     FusedSrc fs;
-    const FusedSrc *fused = fused_source(plan, src, g, &fs) ? &fs : nullptr;
+    const FusedSrc *fused = (net->tc->c1_folded && fused_source(plan, src, g, &fs)) ? &fs : nullptr;   // the fused kernel needs the bias row
     return g.C == 48 ? run_batch<48>(net, g, w, ws, batch, logits, stream, pack, fused)
                      : run_batch<32>(net, g, w, ws, batch, logits, stream, pack, fused);
 }

@@ -178,10 +178,10 @@ def test_bad_inputs(native):
     (800, 1920, 4, False),                                                       # H' = 106
 ])
 def test_fused_frames_equal_unfused(native, h, w, batch, compact):
-    """K1 fused into conv1 (bulk-copied source rows -> resized ring -> A operand) must give the SAME logits as
-    preprocessing to float32 first and entering through net(x): both feed the MMAs the identical fp16 pixels v/256.
-    Integer-scale gathers (720p, 2160p) enter the MMAs as 1024 + v with the offset taken out of the bias: same 16-bit
-    operands, float32 sums in another order, so those agree to float32 rounding of the layer-1 sums (<= 2e-3 on a logit)."""
+    """K1 fused into conv1 (bulk-copied source rows -> resized pixels -> A operand) must give the same logits as
+    preprocessing to float32 first and entering through net(x).  Both feed the MMAs the same 16-bit taps and the same pixel
+    values; the fused kernel enters them as 1024 + v with the offset and the bias carried by a weight row, so the float32 sums
+    of layer 1 differ in rounding only: <= 2e-3 on a logit (observed <= 3e-4)."""
     from cutdet import engine
     net, _ = native
     rng = np.random.default_rng(h * 7 + batch)
@@ -194,7 +194,4 @@ def test_fused_frames_equal_unfused(native, h, w, batch, compact):
     if compact:
         dev = dev[:, torch.from_numpy(plan.rows.astype(np.int64)).cuda()].contiguous()
     got = net.forward_frames(plan, dev, compact).cpu().numpy()
-    if w % 256 == 0 and (w // 256) % 2 == 1 and w > 256:   # odd integer scale: the resize is a pure gather
-        assert float(np.abs(got - want).max()) <= 2e-3, float(np.abs(got - want).max())
-    else:
-        assert np.array_equal(got, want), float(np.abs(got - want).max())
+    assert float(np.abs(got - want).max()) <= 2e-3, float(np.abs(got - want).max())
