@@ -1,0 +1,31 @@
+#!/usr/bin/env python3
+"""profiles/<round>_ncu_full.csv -> profiles/ncu_traffic.json (DRAM bytes per launch of each profiled kernel; bench.py reads it
+for roofline.traffic).     python profiles/make_traffic.py profiles/r01_v4_ncu_full.csv"""
+import csv, json, os, sys
+
+src = sys.argv[1]
+rows = list(csv.reader(open(src)))
+h = rows[0]
+col = {n: i for i, n in enumerate(h)}
+names = {"conv1_fused_tc_kernel": "conv1_fused_tc", "conv_mid_tc_kernel": "conv_mid_tc"}
+out = {}
+for key, short in names.items():
+    sel = [r for r in rows[2:] if key in r[0]]
+    if not sel:
+        continue
+    f = lambda c: sum(float(r[col[c]]) for r in sel) / len(sel)
+    out[short] = {
+        "dram_bytes_per_launch": (f("dram__bytes_read.sum") + f("dram__bytes_write.sum")) * 1e6,
+        "dram_read_bytes_per_launch": f("dram__bytes_read.sum") * 1e6,
+        "dram_write_bytes_per_launch": f("dram__bytes_write.sum") * 1e6,
+        "launches_profiled": len(sel),
+        "avg_duration_us_under_ncu": f("gpu__time_duration.sum"),
+        "tensor_pipe_active_pct": f("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+        "dram_throughput_pct": f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+        "source": f"{src} (ncu --set full --clock-control none, 148-frame sub-batch launches; ncu flushes the L2 between kernels)",
+    }
+# bench.py's kernel table names conv2/conv3 separately; both are conv_mid_tc_kernel
+if "conv_mid_tc" in out:
+    out["conv2_tc"] = out["conv_mid_tc"]
+json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json"), "w"), indent=1)
+print(json.dumps(out, indent=1))
