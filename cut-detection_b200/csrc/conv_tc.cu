@@ -44,6 +44,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <cmath>
 
 #include <map>
@@ -624,8 +625,8 @@ __global__ void __launch_bounds__(416, 1) conv1_tc_kernel(const Conv1Params p) {
 constexpr int FR_CAP = 1024;                 // positions per sub-ring (a power of two)
 constexpr int FR_PLANE = (FR_CAP + 128) * 16;            // bytes of one k-half plane incl. the mirror
 constexpr int FR_SUB = 2 * FR_PLANE;
-constexpr int RAW_BYTES = 65536;
-constexpr int RAW_SLOTS_MAX = 16;
+constexpr int RAW_BYTES = 92160;              // raw-row ring: 24 rows of 720p, 8 row pairs of 1080p (what is left of the 227 KB)
+constexpr int RAW_SLOTS_MAX = 24;
 constexpr int F_MAX_DST = 256;
 constexpr int F1_CMP_WARPS = 4, F1_CMP_STRIDE = F_MAX_DST + 8;   // [0] = the pixel left of the image, [1 + x] = pixel x, zeros after
 
@@ -636,7 +637,7 @@ struct FusedSrc {
     int compact;
     int n_src;        // raw rows per resized row
     int row_bytes;    // 3 * src_w, a multiple of 16
-    int log2_slots;   // raw ring slots (a power of two) of n_src * row_bytes each
+    int n_slots;      // raw ring slots of n_src * row_bytes each (2 .. RAW_SLOTS_MAX)
 };
 
 template <int C>
@@ -648,7 +649,7 @@ struct F1Smem {
     static constexpr int OFF_TAB = OFF_RAW + RAW_BYTES + 64;           // 64 bytes of slack: the gather reads one word past a row
     static constexpr int OFF_CMP = OFF_TAB + F_MAX_DST * (8 + 8 + 16);  // rowoff[256][2], yb[256][2], xtab[256] (int4)
     static constexpr int OFF_BAR = OFF_CMP + F1_CMP_WARPS * F1_CMP_STRIDE * 4;   // one resized row per unfold warp (general resize)
-    static constexpr int OFF_PAR = OFF_BAR + 512;
+    static constexpr int OFF_PAR = OFF_BAR + 1024;
     static constexpr int total = OFF_PAR + 3 * C * 4;
 };
 
@@ -668,12 +669,20 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
 #pragma unroll
         for (int c = 0; c < 3; ++c) v[c] = (q0[6 * x + c] + q0[6 * x + 3 + c] + q1[6 * x + c] + q1[6 * x + 3 + c] + 2) >> 2;
     } else {
+        // OpenCV's fixed-point bilinear: horizontal S = a0 p[x0] + a1 p[x0+1] (11-bit coefficients, one
+        // DP2A per channel and row on the byte pair), vertical (((b0 (S0 >> 4)) >> 16) + ((b1 (S1 >> 4)) >> 16) + 2) >> 2
         const int4 xt = s_xtab[x];
+        const uint32_t sh = (uint32_t)(xt.x & 3) * 8, aw = (uint32_t)xt.y;
+        const uint32_t *r0 = reinterpret_cast<const uint32_t *>(q0 + (xt.x & ~3));
+        const uint32_t *r1 = reinterpret_cast<const uint32_t *>(q1 + (xt.x & ~3));
+        const uint32_t lo0 = __funnelshift_r(r0[0], r0[1], sh), hi0 = __funnelshift_r(r0[1], r0[2], sh);   // bytes 0..3, 4..7 of the pair
+        const uint32_t lo1 = __funnelshift_r(r1[0], r1[1], sh), hi1 = __funnelshift_r(r1[1], r1[2], sh);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const int s0 = xt.z * q0[xt.x + c] + xt.w * q0[xt.y + c];
-            const int s1 = xt.z * q1[xt.x + c] + xt.w * q1[xt.y + c];
-            v[c] = min(max((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2, 0), 255);
+            const uint32_t selc = c == 0 ? 0x7730u : (c == 1 ? 0x7741u : 0x7752u);          // (p[x0][c], p[x0+1][c]) in the low half
+            const int s0 = (int)__dp2a_lo(aw, __byte_perm(lo0, hi0, selc), 0u);
+            const int s1 = (int)__dp2a_lo(aw, __byte_perm(lo1, hi1, selc), 0u);
+            v[c] = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;           // <= 255 by construction
         }
     }
     return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16);
@@ -770,7 +779,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     const int n_frames_cta = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_tiles = (n_frames_cta * RPF * P1w + 127) / 128;
     const int total_u = 3 * n_frames_cta * RPF;               // resized rows incl. the zero rows, u = 3R + sub
-    const int n_slots = 1 << src.log2_slots, slot_bytes = src.n_src * src.row_bytes;
+    const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;
+    const uint32_t inv_slots = 0xffffffffu / (uint32_t)n_slots + 1u;       // n / n_slots = umulhi(n, inv_slots), exact while n * n_slots < 2^32
 
     for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -795,7 +805,14 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         s_yb[2 * y + 1] = b1;
     }
     if (plan.mode == RESIZE_LINEAR && plan.gather_step_x == 0)
-        for (int x = threadIdx.x; x < plan.dst_w; x += blockDim.x) s_xtab[x] = make_int4(3 * plan.x0[x], 3 * plan.x1[x], plan.a0[x], plan.a1[x]);
+        for (int x = threadIdx.x; x < plan.dst_w; x += blockDim.x) {
+            // the second tap is the next pixel or (clamped at the edge) the same one: fold that case into the first coefficient, so
+            // the kernel always reads the six bytes of pixels x0 and x0 + 1
+            const int x0 = plan.x0[x], x1 = plan.x1[x];
+            int a0 = plan.a0[x], a1 = plan.a1[x];
+            if (x1 != x0 + 1) { a0 += a1; a1 = 0; }
+            s_xtab[x] = make_int4(3 * x0, a0 | (a1 << 16), 0, 0);
+        }
     if (threadIdx.x < UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;    // ... and s_rows_issued
     fence_proxy_async();
     if (threadIdx.x == 0) {
@@ -816,8 +833,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         reg_dealloc<F1_REGS_LIGHT>();                            // one instruction for the whole warpgroup (.sync.aligned)
         if (warp > F1_MMA_WARP) {
             // ------------------------------------------------------------------ loaders: source rows -> raw ring
-            // (a slot's consecutive rows n, n + n_slots go through the same loader -- n_slots is a multiple of n_loaders -- so the
-            // in-order waits on raw_empty never skip a phase)
+            // (the wait on raw_empty is for row n - n_slots to have been read; the slot cannot be a phase further, since that
+            // takes row n itself)
             const int lw = warp - F1_LOAD_WARP0, total_rows = n_frames_cta * Hc;
             const int n_loaders = min(LOADER_WARPS, n_slots);
             if (lw < n_loaders) {                                // (warp 15 only fills the warpgroup)
@@ -825,8 +842,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                 int fi = 0, y = lw, issued = 0;
                 for (int n = lw; n < total_rows; n += n_loaders, y += n_loaders) {
                     while (y >= Hc) { y -= Hc; ++fi; }
-                    const int slot = n & (n_slots - 1);
-                    mbar_wait(&raw_empty[slot], ((n >> src.log2_slots) & 1) ^ 1);
+                    const int use = (int)__umulhi((uint32_t)n, inv_slots), slot = n - use * n_slots;
+                    mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
                     if (tl && lane == 0 && n < 256) tl[n] = clock64();
                     ++issued;
                     if (elect_one()) {
@@ -905,7 +922,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             const int y = 3 * py + sub;
             r.real = y < H && (py < p.P1h || sub == 0);      // index P1h: row 3*P1h if the image has it, else zeros
             const int n = fi * Hc + y;
-            r.slot = n & (n_slots - 1);
+            const int use = (int)__umulhi((uint32_t)n, inv_slots);
+            r.slot = n - use * n_slots;
             r.R = R; r.sub = sub; y_out = y;
             r.q0 = s_raw + r.slot * slot_bytes;
             // positions [R*P1w, (R+1)*P1w) replace those FR_CAP earlier, last read by tile (pos - FR_CAP + P1w) / 128
@@ -917,7 +935,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             if (r.real) {
                 const int ld = n & (n_loaders - 1), want = (n >> log2_loaders) + 1;
                 while (ld_acquire_shared(&s_rows_issued[ld]) < want) __nanosleep(32);
-                mbar_wait(&raw_full[r.slot], (n >> src.log2_slots) & 1);
+                mbar_wait(&raw_full[r.slot], use & 1);
             }
             sub += UNFOLD_WARPS % 3; R += UNFOLD_WARPS / 3; py += UNFOLD_WARPS / 3;
             if (sub >= 3) { sub -= 3; ++R; ++py; }
@@ -1362,9 +1380,8 @@ bool fused_source(const cutdet_resize_plan *plan, const cutdet_frames *frames, c
     if ((long long)rows * frames->row_pitch >= (1LL << 31)) return false;
     const int n_src = (h.gather_step_x > 0 || h.mode == RESIZE_COPY) ? 1 : 2;
     const long long slot = n_src * row_bytes;
-    int log2_slots = 0;
-    while ((2LL << log2_slots) * slot <= RAW_BYTES && (2 << log2_slots) <= RAW_SLOTS_MAX) ++log2_slots;
-    if (slot > RAW_BYTES || log2_slots < 1) return false;
+    const long long n_slots = std::min<long long>(RAW_BYTES / slot, RAW_SLOTS_MAX);
+    if (n_slots < 2) return false;
     out->plan = h;
     out->frames = frames->frames_dev;
     out->frame_stride = frames->frame_stride;
@@ -1372,7 +1389,7 @@ bool fused_source(const cutdet_resize_plan *plan, const cutdet_frames *frames, c
     out->compact = frames->row_map_compact;
     out->n_src = n_src;
     out->row_bytes = (int)row_bytes;
-    out->log2_slots = log2_slots;
+    out->n_slots = (int)n_slots;
     return true;
 }
 
