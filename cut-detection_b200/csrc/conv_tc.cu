@@ -728,6 +728,10 @@ template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("s
 __device__ __forceinline__ void st_release_shared(int *p, int v) {
     asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
+// after a fence that already ordered this thread's (and, through __syncwarp, its warp's) earlier writes: no second MEMBAR
+__device__ __forceinline__ void st_relaxed_shared(int *p, int v) {
+    asm volatile("st.relaxed.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ int ld_acquire_shared(const int *p) {
     int v;
     asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -975,7 +979,6 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             Row r0;
             int y0;
             next_row(r0, y0);
-            if (tl && pwarp == 0 && lane == 0 && rows_done < 128) tl[256 + rows_done] = clock64();
             uint32_t w0[NP][5];
             if (GATHER) {
                 gather(r0, w0);
@@ -1003,9 +1006,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             ++rows_done;
             if (lane == 0) {
                 if (r0.real) mbar_arrive(&raw_empty[r0.slot]);
-                st_release_shared(&s_rows_done[pwarp], rows_done);
+                st_relaxed_shared(&s_rows_done[pwarp], rows_done);      // (every lane fenced its stores before the __syncwarp)
             }
-            if (tl && pwarp == 0 && lane == 0 && rows_done <= 128) tl[384 + rows_done - 1] = clock64();
         }
     } else {
         // ------------------------------------------------------------------ epilogue
