@@ -176,6 +176,37 @@ def load_and_glue_nets(param_file, conv_file, linear_file):
     return GluedNet(conv_net, linear_net), model_params
 
 
+def load_torchscript_net(trace_file):
+    """Addition to the reference API: take the parameters out of a TorchScript export of the
+    glued net -- ``saved_model_trace.pt`` as written by the reference's training_scripts/make_torchscript_model.py:17-34
+    (``torch.jit.trace(nn.Sequential(conv_net, linear_net), ...).save``) -- so that a deployment that ships only the
+    traced file runs on the native path too.  The architecture is read off the tensor shapes: state-dict keys
+    ``0.conv_layers.{i}.*`` / ``1.layers.{j}.*``, ``avg_pool_size = sqrt(linear_in / conv_channels)``.
+    Returns ``(net, model_params)`` like ``load_and_glue_nets``."""
+    scripted = torch.jit.load(trace_file, map_location="cpu")
+    sd = {k: v.detach().clone() for k, v in scripted.state_dict().items()}
+    conv = {k[2:]: v for k, v in sd.items() if k.startswith("0.")}
+    linear = {k[2:]: v for k, v in sd.items() if k.startswith("1.")}
+    if not conv or not linear or len(conv) + len(linear) != len(sd):
+        raise ValueError(f"{trace_file}: not a traced nn.Sequential(FrameConvNet, FrameLinearNet)")
+    n_conv = 1 + max(int(k.split(".")[1]) for k in conv if k.startswith("conv_layers."))
+    n_lin = 1 + max(int(k.split(".")[1]) for k in linear if k.startswith("layers."))
+    channels = int(conv["conv_layers.0.conv.weight"].shape[0])
+    lin_in = int(linear["layers.0.linear.weight"].shape[1])
+    pool = int(round((lin_in / channels) ** 0.5))
+    if channels * pool * pool != lin_in:
+        raise ValueError(f"{trace_file}: linear input {lin_in} is not conv_channels {channels} x a square pool size")
+    model_params = {
+        "conv_layers": n_conv, "conv_channels": channels, "avg_pool_size": pool, "linear_layers": n_lin,
+        "linear_size": int(linear["layers.0.linear.weight"].shape[0]) if n_lin > 1 else 0,
+        "linear_output_size": int(linear[f"layers.{n_lin - 1}.linear.weight"].shape[0]),
+    }
+    conv_net, linear_net = _build(model_params)
+    conv_net.load_state_dict(conv)          # strict: a file of another architecture fails loudly, as in the reference
+    linear_net.load_state_dict(linear)
+    return GluedNet(conv_net, linear_net), model_params
+
+
 def _load_npz(path):
     with np.load(path, allow_pickle=False) as z:
         model_params = json.loads(bytes(z["__params_json__"]).decode("utf-8"))

@@ -62,6 +62,22 @@ def test_three_file_checkpoint_format(tmp_path, prod_weights):
     assert torch.equal(net(x), net2(x))
 
 
+def test_torchscript_export_as_weight_source(golden_dir):
+    """the reference's saved_model_trace.pt (training_scripts/make_torchscript_model.py:17-34, written by the
+    unmodified reference: tests/golden/make_trace_golden.py) loads into the native path and gives the shipped net's logits."""
+    from frameID.net import load_default_net, load_torchscript_net
+    net, params = load_default_net()
+    net2, params2 = load_torchscript_net(os.path.join(golden_dir, "saved_model_trace.pt"))
+    assert {k: params[k] for k in params2} == params2
+    net.eval().to("cuda")
+    net2.eval().to("cuda")
+    x = torch.from_numpy(kat_inputs.smooth_images(5, seed=11)).cuda()
+    assert torch.equal(net(x), net2(x))
+    kat = np.load(os.path.join(golden_dir, "net_kat.npz"))      # what the reference's traced module gave for these inputs
+    got = net2(torch.from_numpy(kat_inputs.smooth_images(48)).cuda()).cpu().numpy()
+    assert np.abs(got - kat["smooth48_traced"]).max() <= 0.05
+
+
 def test_cli_on_a_synthetic_clip(tmp_path, prod_weights):
     """segment_video.py on a small synthetic mp4: CSV equals the oracle's run over the same decoded frames."""
     import cv2

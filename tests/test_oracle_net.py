@@ -97,3 +97,20 @@ def test_live_reference_module(prod_weights):
         subprocess.run([sys.executable, "-c", code], check=True)
         got = np.load(os.path.join(td, "y.npy"))
     assert np.array_equal(got, want)
+
+
+def test_torchscript_export_parameters(golden_dir):
+    """The loader of the reference's TorchScript export recovers the shipped architecture and the
+    exact parameters -- checked on the CPU against the re-encoded prod_net weights (no forward pass, no GPU)."""
+    import numpy as np
+    import torch
+    from frameID.net import load_torchscript_net, load_default_net
+    net, params = load_torchscript_net(os.path.join(golden_dir, "saved_model_trace.pt"))
+    ref, ref_params = load_default_net()
+    assert params == {k: ref_params[k] for k in params}
+    a, b = net.state_dict(), ref.state_dict()
+    assert a.keys() == b.keys()
+    for k in a:
+        if k.endswith("num_batches_tracked"):        # a training counter (18762 in the export), not a parameter of the forward pass
+            continue
+        assert torch.equal(a[k], b[k]), k
