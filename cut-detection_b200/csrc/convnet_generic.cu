@@ -93,7 +93,7 @@ conv3x3_relu_pool3_bn_kernel(const float *__restrict__ in, float *__restrict__ o
 #pragma unroll
         for (int p = 1; p < 9; ++p) m = fmaxf(m, acc[p][c]);
         m = fmaxf(m + bias[co], 0.f);
-        out[(((int64_t)b * cout + co) * ph + py) * pw + px] = fmaf(m, scale[co], shift[co]);
+        out[(((int64_t)b * cout + co) * ph + py) * pw + px] = scale ? fmaf(m, scale[co], shift[co]) : m;
     }
 }
 
@@ -137,10 +137,48 @@ __global__ void fc_kernel(const float *__restrict__ in, float *__restrict__ out,
     }
 }
 
+// BatchNorm in training mode (the reference's learn_contrasts.py never calls .eval(): nn.BatchNorm2d/1d normalise with the
+// batch mean and the BIASED batch variance).  One block per channel: sums in double, then the affine in place.
+__global__ void __launch_bounds__(256) bn_batchstats_kernel(float *__restrict__ data, int outer, int channels, int inner,
+                                                            const float *__restrict__ gamma, const float *__restrict__ beta, float eps) {
+    const int c = blockIdx.x;
+    const int64_t n = (int64_t)outer * inner;
+    double s = 0.0, ss = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = data[((i / inner) * channels + c) * inner + i % inner];
+        s += v; ss += (double)v * v;
+    }
+    __shared__ double sh[2][256];
+    sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = ss;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+        __syncthreads();
+    }
+    const double mean = sh[0][0] / (double)n;
+    const double var = fmax(sh[1][0] / (double)n - mean * mean, 0.0);
+    const float scale = gamma[c] * (float)(1.0 / sqrt(var + (double)eps)), shift = beta[c] - (float)mean * scale;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        float *q = data + ((i / inner) * channels + c) * inner + i % inner;
+        *q = fmaf(*q, scale, shift);
+    }
+}
+
 }  // namespace
 
+int launch_bn_batchstats(float *data, int outer, int channels, int inner, const float *gamma, const float *beta, float eps,
+                         cudaStream_t stream) {
+    if (outer <= 0 || channels <= 0 || inner <= 0) return CUTDET_OK;
+    {
+        KernelScope scope("bn_batchstats_kernel", stream);
+        bn_batchstats_kernel<<<channels, 256, 0, stream>>>(data, outer, channels, inner, gamma, beta, eps);
+    }
+    CUTDET_LAUNCH_CHECK("bn_batchstats_kernel");
+    return CUTDET_OK;
+}
+
 int launch_conv_block_generic(const float *in, float *out, const ConvLayer &L, int layer, int batch, int h, int w,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, bool apply_bn) {
     static const char *const kNames[] = {"conv_block_generic_L0", "conv_block_generic_L1", "conv_block_generic_L2",
                                          "conv_block_generic_L3+"};
     const char *name = kNames[layer < 3 ? layer : 3];
@@ -155,7 +193,7 @@ int launch_conv_block_generic(const float *in, float *out, const ConvLayer &L, i
         {
             KernelScope scope(name, stream);
             conv3x3_relu_pool3_bn_kernel<<<grid, PT_X * PT_Y, 0, stream>>>(
-            in + (int64_t)b0 * L.cin * h * w, out + (int64_t)b0 * L.cout * ph * pw, L.d_w_t, L.d_bias, L.d_scale,
+            in + (int64_t)b0 * L.cin * h * w, out + (int64_t)b0 * L.cout * ph * pw, L.d_w_t, L.d_bias, apply_bn ? L.d_scale : nullptr,
             L.d_shift, L.cin, L.cout, cout_pad, h, w, ph, pw, co_groups);
         }
         CUTDET_LAUNCH_CHECK("conv3x3_relu_pool3_bn_kernel");
@@ -175,14 +213,14 @@ int launch_avgpool_flatten(const float *in, float *out, int batch, int c, int h,
     return CUTDET_OK;
 }
 
-int launch_fc(const float *in, float *out, const FcLayer &L, int batch, bool relu, cudaStream_t stream) {
+int launch_fc(const float *in, float *out, const FcLayer &L, int batch, bool relu, cudaStream_t stream, bool apply_bn) {
     const int64_t warps = (int64_t)batch * L.out;
     if (warps == 0) return CUTDET_OK;
     {
         KernelScope scope("fc_kernel", stream);
         fc_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, stream>>>(in, out, L.d_w, L.d_bias,
-                                                                      L.has_bn ? L.d_scale : nullptr,
-                                                                      L.has_bn ? L.d_shift : nullptr, batch, L.in, L.out,
+                                                                      L.has_bn && apply_bn ? L.d_scale : nullptr,
+                                                                      L.has_bn && apply_bn ? L.d_shift : nullptr, batch, L.in, L.out,
                                                                       relu ? 1 : 0);
     }
     CUTDET_LAUNCH_CHECK("fc_kernel");

@@ -85,13 +85,17 @@ int check_input_size(const cutdet_net *net, int h, int w) {
     return CUTDET_OK;
 }
 
+// batch_stats: every BatchNorm uses the statistics of this batch (training-mode forward) instead of its running statistics
 int forward_generic(cutdet_net *net, const float *x, int batch, int h, int w, float *logits, char *ws_base,
-                    const GenericWorkspace &ws, cudaStream_t stream) {
+                    const GenericWorkspace &ws, cudaStream_t stream, bool batch_stats = false) {
     const float *cur = x;
     std::vector<LayerGeom> geom = layer_geometry(net, h, w);
     for (size_t i = 0; i < geom.size(); ++i) {
         float *out = reinterpret_cast<float *>(ws_base + ws.conv_out[i]);
-        if (int rc = launch_conv_block_generic(cur, out, net->conv[i], (int)i, batch, geom[i].h, geom[i].w, stream)) return rc;
+        const ConvLayer &L = net->conv[i];
+        if (int rc = launch_conv_block_generic(cur, out, L, (int)i, batch, geom[i].h, geom[i].w, stream, !batch_stats)) return rc;
+        if (batch_stats)
+            if (int rc = launch_bn_batchstats(out, batch, L.cout, geom[i].ph * geom[i].pw, L.d_gamma, L.d_beta, L.eps, stream)) return rc;
         cur = out;
     }
     if (!geom.empty()) {
@@ -104,7 +108,10 @@ int forward_generic(cutdet_net *net, const float *x, int batch, int h, int w, fl
     for (int j = 0; j < net->cfg.n_fc_layers; ++j) {
         const bool is_last = j + 1 == net->cfg.n_fc_layers;
         float *out = is_last ? logits : reinterpret_cast<float *>(ws_base + ws.fc_out[j]);
-        if (int rc = launch_fc(cur, out, net->fc[j], batch, !is_last, stream)) return rc;
+        if (int rc = launch_fc(cur, out, net->fc[j], batch, !is_last, stream, !batch_stats)) return rc;
+        if (batch_stats && net->fc[j].has_bn)
+            if (int rc = launch_bn_batchstats(out, batch, net->fc[j].out, 1, net->fc[j].d_gamma, net->fc[j].d_beta, net->fc[j].eps, stream))
+                return rc;
         cur = out;
     }
     return CUTDET_OK;
@@ -158,6 +165,9 @@ extern "C" int cutdet_net_set_conv_layer(cutdet_net *net, int layer, const float
     L.w.assign(w, w + (size_t)L.cout * L.cin * 9);
     L.bias.assign(b, b + L.cout);
     fold_bn(L.cout, g, beta, mean, var, eps, L.scale, L.shift);
+    L.gamma.assign(g, g + L.cout);
+    L.beta.assign(beta, beta + L.cout);
+    L.eps = eps;
     L.set = true;
     return CUTDET_OK;
 }
@@ -171,6 +181,9 @@ extern "C" int cutdet_net_set_fc_layer(cutdet_net *net, int layer, const float *
     if (L.has_bn) {
         CUTDET_REQUIRE(g && beta && mean && var, "set_fc_layer: layer %d needs BatchNorm parameters", layer);
         fold_bn(L.out, g, beta, mean, var, eps, L.scale, L.shift);
+        L.gamma.assign(g, g + L.out);
+        L.beta.assign(beta, beta + L.out);
+        L.eps = eps;
     } else {
         CUTDET_REQUIRE(!g && !beta && !mean && !var, "set_fc_layer: the last layer has no BatchNorm (net.py:164-167)");
     }
@@ -195,6 +208,8 @@ extern "C" int cutdet_net_finalize(cutdet_net *net) {
         if (int rc = upload(net, L.bias, &L.d_bias)) return rc;
         if (int rc = upload(net, L.scale, &L.d_scale)) return rc;
         if (int rc = upload(net, L.shift, &L.d_shift)) return rc;
+        if (int rc = upload(net, L.gamma, &L.d_gamma)) return rc;
+        if (int rc = upload(net, L.beta, &L.d_beta)) return rc;
     }
     for (FcLayer &L : net->fc) {
         if (int rc = upload(net, L.w, &L.d_w)) return rc;
@@ -202,6 +217,8 @@ extern "C" int cutdet_net_finalize(cutdet_net *net) {
         if (L.has_bn) {
             if (int rc = upload(net, L.scale, &L.d_scale)) return rc;
             if (int rc = upload(net, L.shift, &L.d_shift)) return rc;
+            if (int rc = upload(net, L.gamma, &L.d_gamma)) return rc;
+            if (int rc = upload(net, L.beta, &L.d_beta)) return rc;
         }
     }
     if (int rc = tc_prepare(net)) return rc;
@@ -241,6 +258,23 @@ extern "C" int cutdet_net_forward_f32(cutdet_net *net, const float *x, int batch
         return tc_forward_f32(net, x, batch, height, width, logits, base, as_stream(stream));
     GenericWorkspace ws = generic_workspace(net, batch, height, width, true);
     return forward_generic(net, x, batch, height, width, logits, base, ws, as_stream(stream));
+}
+
+extern "C" int cutdet_net_forward_f32_batchstats(cutdet_net *net, const float *x, int batch, int height, int width, float *out,
+                                                 void *workspace, size_t workspace_bytes, cutdet_stream_t stream) {
+    CUTDET_REQUIRE(net && net->finalized, "net_forward_f32_batchstats: net not finalized");
+    CUTDET_REQUIRE(batch >= 0 && height > 0 && width > 0, "net_forward_f32_batchstats: bad shape");
+    if (batch == 0) return CUTDET_OK;
+    CUTDET_REQUIRE(batch >= 2, "net_forward_f32_batchstats: batch statistics need more than one value per channel");
+    CUTDET_REQUIRE(x && out && workspace, "net_forward_f32_batchstats: null pointer");
+    if (int rc = check_input_size(net, height, width)) return rc;
+    size_t need = 0;
+    if (int rc = cutdet_net_workspace_bytes(net, batch, height, width, &need)) return rc;
+    if (workspace_bytes < need)
+        return fail(CUTDET_ECAPACITY, "net_forward_f32_batchstats: workspace %zu < %zu bytes", workspace_bytes, need);
+    char *base = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    GenericWorkspace ws = generic_workspace(net, batch, height, width, true);
+    return forward_generic(net, x, batch, height, width, out, base, ws, as_stream(stream), true);
 }
 
 extern "C" int cutdet_net_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cutdet_frames *src,

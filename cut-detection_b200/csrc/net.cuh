@@ -16,16 +16,20 @@ struct ConvLayer {
     std::vector<float> bias;    // [cout]
     std::vector<float> scale;   // gamma / sqrt(var + eps)
     std::vector<float> shift;   // beta - mean * scale
+    std::vector<float> gamma, beta;   // BatchNorm weight/bias as given (batch-statistics forward)
+    float eps = 1e-5f;
     // generic path (device, float32)
     float *d_w_t = nullptr;     // [cin][9][cout_padded8]
     float *d_bias = nullptr, *d_scale = nullptr, *d_shift = nullptr;
+    float *d_gamma = nullptr, *d_beta = nullptr;
 };
 
 struct FcLayer {
     int in = 0, out = 0;
     bool set = false, has_bn = false;
-    std::vector<float> w, bias, scale, shift;
-    float *d_w = nullptr, *d_bias = nullptr, *d_scale = nullptr, *d_shift = nullptr;
+    std::vector<float> w, bias, scale, shift, gamma, beta;
+    float eps = 1e-5f;
+    float *d_w = nullptr, *d_bias = nullptr, *d_scale = nullptr, *d_shift = nullptr, *d_gamma = nullptr, *d_beta = nullptr;
 };
 
 struct LayerGeom {
@@ -34,10 +38,13 @@ struct LayerGeom {
 
 // generic CUDA-core kernels (any architecture the reference's constructors can build)
 int launch_conv_block_generic(const float *in, float *out, const ConvLayer &L, int layer, int batch, int h, int w,
-                              cudaStream_t stream);
+                              cudaStream_t stream, bool apply_bn = true);
 int launch_avgpool_flatten(const float *in, float *out, int batch, int c, int h, int w, int pool,
                            cudaStream_t stream);
-int launch_fc(const float *in, float *out, const FcLayer &L, int batch, bool relu, cudaStream_t stream);
+int launch_fc(const float *in, float *out, const FcLayer &L, int batch, bool relu, cudaStream_t stream, bool apply_bn = true);
+// BatchNorm with the statistics of THIS batch (training-mode forward, biased variance), in place over [outer][channels][inner]
+int launch_bn_batchstats(float *data, int outer, int channels, int inner, const float *gamma, const float *beta, float eps,
+                         cudaStream_t stream);
 
 }  // namespace cutdet
 

@@ -191,6 +191,27 @@ class NativeNet:
                                                        ws.numel(), _stream()))
         return out
 
+    def forward_f32_batchstats(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """The forward pass of a module left in training mode: every BatchNorm normalises with this batch's mean and biased
+        variance (reference training_scripts/learn_contrasts.py:100-107).  Forward only."""
+        _need_cuda(x, "input")
+        if x.dim() == 2:
+            x = x[:, :, None, None]
+        if x.dtype != torch.float32 or x.dim() != 4:
+            raise ValueError(f"input must be float32 [B,C,H,W], got {x.dtype} {tuple(x.shape)}")
+        if x.shape[1] != self.cfg.input_channels:
+            raise ValueError(f"input has {x.shape[1]} channels, the net expects {self.cfg.input_channels}")
+        if x.shape[0] < 2:
+            raise ValueError("Expected more than 1 value per channel when training")      # what nn.BatchNorm raises
+        x = x.contiguous()
+        b, _, h, w = x.shape
+        if out is None:
+            out = torch.empty((b, self.out_features), dtype=torch.float32, device=x.device)
+        ws = self.workspace(b, h, w, x.device)
+        _cabi.check(_cabi.lib().cutdet_net_forward_f32_batchstats(self.handle, x.data_ptr(), b, h, w, out.data_ptr(),
+                                                                  ws.data_ptr(), ws.numel(), _stream()))
+        return out
+
     def forward_frames(self, plan: ResizePlan, frames: torch.Tensor, compact: bool = False,
                        out: torch.Tensor | None = None) -> torch.Tensor:
         """Decoded uint8 BGR HWC frames -> logits, K1 fused in front of the conv stack."""
@@ -342,3 +363,20 @@ def stitch_shards(shards: "list[DeviceRunTable] | DeviceRunTable", n_runs: torch
     _cabi.check(_cabi.lib().cutdet_stitch_shards(C.byref(s), n_shards, int(shard_capacity), n_runs.data_ptr(),
                                                  frame_offsets.data_ptr(), C.byref(d), dst.n_runs.data_ptr(), _stream()))
     return dst
+
+
+def contrastive_loss(x: torch.Tensor, temperature: float = 1.0, h_norm: bool = True):
+    """ContrastiveLoss.forward of the reference (frameID/metrics.py:23-47) on the GPU: x float32 [2B, D] ->
+    (loss 0-d tensor, logits_ab [B, B])."""
+    _need_cuda(x, "input")
+    if x.dtype != torch.float32 or x.dim() != 2 or x.shape[0] % 2 or x.shape[0] == 0:
+        raise ValueError(f"input must be float32 [2B, D], got {x.dtype} {tuple(x.shape)}")
+    x = x.contiguous()
+    pairs, dim = x.shape[0] // 2, x.shape[1]
+    loss = torch.empty((), dtype=torch.float32, device=x.device)
+    logits_ab = torch.empty((pairs, pairs), dtype=torch.float32, device=x.device)
+    lib = _cabi.lib()
+    ws = torch.empty(lib.cutdet_contrastive_loss_workspace_bytes(pairs), dtype=torch.uint8, device=x.device)
+    _cabi.check(lib.cutdet_contrastive_loss(x.data_ptr(), pairs, dim, float(temperature), 1 if h_norm else 0, loss.data_ptr(),
+                                            logits_ab.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return loss, logits_ab

@@ -11,8 +11,10 @@ Same public names and constructor arguments as the reference:
 The modules hold ordinary torch parameters under the reference's state_dict keys, so the reference's
 checkpoint files load with ``load_state_dict`` unchanged, ``.eval()``, ``.to(device)`` and ``num_params()``
 behave as before -- but ``forward`` does not run PyTorch operators: it hands the input to libcutdet_b200.so
-(hand-written sm_100a kernels) through the C ABI.  Inference only: a module left in training mode (batch-statistic
-BatchNorm) raises, as does a CPU input -- there is no fallback path.
+(hand-written sm_100a kernels) through the C ABI.  Forward passes only (no autograd): after ``.eval()`` BatchNorm uses
+its running statistics; a module left in training mode, as in the reference's learn_contrasts.py, normalises with the
+statistics of the batch (float32 CUDA-core kernels) without updating the running ones.  A CPU input raises -- there is
+no fallback path.
 """
 from __future__ import annotations
 
@@ -73,8 +75,6 @@ class _NativeBacked(nn.Module):
         return tuple((id(p), p._version, p.data_ptr()) for p in list(self.parameters()) + list(self.buffers()))
 
     def _native(self) -> _engine.NativeNet:
-        if self.training:
-            raise RuntimeError("this build implements inference only (BatchNorm running statistics): call .eval() first")
         fp = self._fingerprint()
         cache = self.__dict__.get("_native_cache")
         if cache is None or cache[0] != fp:
@@ -82,6 +82,14 @@ class _NativeBacked(nn.Module):
             cache = (fp, _engine.NativeNet(weights, pool))
             self.__dict__["_native_cache"] = cache
         return cache[1]
+
+    def _run(self, x):
+        """eval(): BatchNorm running statistics, tensor-core path where it applies.  A module left in training mode (the
+        reference's learn_contrasts.py never calls .eval()) normalises with the statistics of the batch: forward only --
+        the running statistics are not updated and no autograd graph is built."""
+        if self.training:
+            return self._native().forward_f32_batchstats(x)
+        return self._native().forward_f32(x)
 
     def num_params(self):
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
@@ -109,7 +117,7 @@ class FrameConvNet(_NativeBacked):
 
     def forward(self, x):
         """float32 [B, Cin, H, W] on the GPU -> [B, hidden_channels * average_pool_size^2]."""
-        return self._native().forward_f32(x)
+        return self._run(x)
 
 
 class FrameLinearNet(_NativeBacked):
@@ -133,7 +141,7 @@ class FrameLinearNet(_NativeBacked):
 
     def forward(self, x):
         """float32 [B, input_size] on the GPU -> [B, output_size] raw scores."""
-        return self._native().forward_f32(x)
+        return self._run(x)
 
 
 class GluedNet(nn.Sequential, _NativeBacked):
@@ -150,7 +158,7 @@ class GluedNet(nn.Sequential, _NativeBacked):
 
     def forward(self, x):
         """float32 [B, 3, H', W'] RGB in [0, 1] -> raw logits [B, output_size] (class order a22, ez, b)."""
-        return self._native().forward_f32(x)
+        return self._run(x)
 
     def forward_frames(self, plan: _engine.ResizePlan, frames, compact: bool = False):
         """Addition to the reference API: decoded uint8 BGR HWC frames [B, h, w, 3] on the GPU -> logits."""

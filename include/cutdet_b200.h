@@ -145,6 +145,12 @@ CUTDET_API int cutdet_net_workspace_bytes(const cutdet_net *net, int batch, int 
 CUTDET_API int cutdet_net_forward_f32(cutdet_net *net, const float *x_nchw_dev, int batch, int height, int width,
                            float *logits_dev, void *workspace_dev, size_t workspace_bytes,
                            cutdet_stream_t stream);
+/* The same forward pass with every BatchNorm in TRAINING mode -- normalised with the mean and biased variance of this batch, as
+ * nn.BatchNorm2d/1d do on a module that was never put in .eval() -- which is how the reference's contrastive script runs its
+ * encoder (training_scripts/learn_contrasts.py:100-107: no .eval() anywhere).  Forward only: running statistics are not
+ * updated and nothing is recorded for a backward pass.  float32 CUDA-core kernels; batch >= 2.                       */
+CUTDET_API int cutdet_net_forward_f32_batchstats(cutdet_net *net, const float *x_nchw_dev, int batch, int height, int width,
+                           float *out_dev, void *workspace_dev, size_t workspace_bytes, cutdet_stream_t stream);
 /* Fused entry: decoded frames in, logits out (K1 feeds the conv stack directly). */
 CUTDET_API int cutdet_net_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cutdet_frames *src,
                               float *logits_dev, void *workspace_dev, size_t workspace_bytes,
@@ -153,6 +159,15 @@ CUTDET_API int cutdet_net_forward_frames(cutdet_net *net, const cutdet_resize_pl
  * layer in [0, n_conv_layers) is the output of that CNNLayer.                                         */
 CUTDET_API int cutdet_net_debug_conv_output(cutdet_net *net, int layer, int batch, int height, int width,
                                  const void *workspace_dev, float *out_nchw_dev, cutdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Contrastive objective (forward)   replaces ContrastiveLoss.forward, frameID/metrics.py:23-47
+ * ------------------------------------------------------------------------------------------------ */
+/* x [2*pairs, dim] float32 (first half = view 1, second half = view 2 of the same images, learn_contrasts.py:104) ->
+ * *loss_dev (mean over pairs of the two cross entropies) and, if not null, logits_ab_dev [pairs, pairs].          */
+CUTDET_API size_t cutdet_contrastive_loss_workspace_bytes(int pairs);
+CUTDET_API int cutdet_contrastive_loss(const float *x_dev, int pairs, int dim, float temperature, int h_norm, float *loss_dev,
+                           float *logits_ab_dev, void *workspace_dev, size_t workspace_bytes, cutdet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4  per-frame decision            replaces torch.max(scores, dim=1), frameID/segmentation.py:37

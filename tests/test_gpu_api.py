@@ -39,8 +39,8 @@ def test_training_mode_and_cpu_inputs_raise():
     from frameID.net import load_default_net
     net, _ = load_default_net()
     net.to("cuda:0")
-    with pytest.raises(RuntimeError):
-        net(torch.zeros((1, 3, 144, 256), device="cuda:0"))           # still in training mode
+    with pytest.raises(ValueError):
+        net(torch.zeros((1, 3, 144, 256), device="cuda:0"))           # training mode: batch statistics of ONE frame (as nn.BatchNorm)
     net.eval()
     with pytest.raises(RuntimeError):
         net(torch.zeros((1, 3, 144, 256)))                            # CPU input: no fallback
