@@ -57,7 +57,22 @@ __global__ void __launch_bounds__(256) preprocess_generic_kernel(ResizePlanDev p
     if (x >= plan.dst_w || y >= plan.dst_h) return;
     const uint8_t *frame = frames + (int64_t)b * frame_stride;
     int v[3];
-    if (plan.mode == RESIZE_COPY) {
+    if (plan.gather_step_x > 0) {
+        // integer scale (720p, 1440p, 2160p -> 256 wide): every second tap has zero weight, out[y][x] = src[off_y + y sy][off_x + x sx].
+        // No tap tables; the three bytes come from two aligned 32-bit loads (rows and frames are 4-byte aligned or we fall back).
+        const int sy = plan.gather_off_y + y * plan.gather_step_y;
+        const int r = compact ? plan.row_slot[sy] : sy;
+        const uint8_t *p = frame + (int64_t)r * row_pitch + 3 * (plan.gather_off_x + x * plan.gather_step_x);
+        if (((frame_stride | row_pitch | reinterpret_cast<uintptr_t>(frames)) & 3) == 0) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+            const uint32_t lo = __ldg(wp), hi = (a & 3) > 1 ? __ldg(wp + 1) : 0u;     // the 2nd word only when the pixel straddles it
+            const uint32_t px = __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8);
+            v[0] = px & 0xff; v[1] = (px >> 8) & 0xff; v[2] = (px >> 16) & 0xff;
+        } else {
+            v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+        }
+    } else if (plan.mode == RESIZE_COPY) {
         const int r = compact ? plan.row_slot[y] : y;
         const uint8_t *p = frame + (int64_t)r * row_pitch + 3 * x;
         v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
