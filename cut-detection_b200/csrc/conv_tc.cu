@@ -1354,7 +1354,9 @@ int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
 
 template <int C>
 int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src, cudaStream_t stream) {
-    const int grid = p.B < sm_count() ? p.B : sm_count();
+    // CUTDET_CONV1_GRID caps the grid (test hook: several frames per CTA, as on a part with fewer SMs than a sub-batch has frames)
+    static const int grid_cap = [] { const char *e = getenv("CUTDET_CONV1_GRID"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 1 << 30; }();
+    const int grid = std::min(std::min(p.B, sm_count()), grid_cap);
     static const int regs_g = [] { cudaFuncAttributes a{}; cudaFuncGetAttributes(&a, conv1_fused_tc_kernel<C, true>); return a.numRegs; }();
     static const int regs_l = [] { cudaFuncAttributes a{}; cudaFuncGetAttributes(&a, conv1_fused_tc_kernel<C, false>); return a.numRegs; }();
     if (regs_g != F1_REGS_START || regs_l != F1_REGS_START) {

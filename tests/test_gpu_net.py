@@ -195,3 +195,32 @@ def test_fused_frames_equal_unfused(native, h, w, batch, compact):
         dev = dev[:, torch.from_numpy(plan.rows.astype(np.int64)).cuda()].contiguous()
     got = net.forward_frames(plan, dev, compact).cpu().numpy()
     assert float(np.abs(got - want).max()) <= 2e-3, float(np.abs(got - want).max())
+
+
+def test_fused_kernel_with_several_frames_per_cta():
+    """On B200 a sub-batch has as many frames as the GPU has SMs, so conv1_fused_tc walks ONE frame per CTA.  The kernel is written
+    for any number (frames follow each other in the flattened position space, with one zero row between them): cap its grid
+    through the CUTDET_CONV1_GRID test hook -- 37 CTAs, up to 4 frames each -- in a fresh process and compare with the float path."""
+    import subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path[:0] = [%r, %r]
+        from cutdet import engine
+        from frameID.net import load_default_net
+        net, _ = load_default_net()
+        net.eval().to("cuda")
+        worst = 0.0
+        for (h, w, batch) in ((720, 1280, 301), (1080, 1920, 75), (360, 640, 140)):
+            rng = np.random.default_rng(h + batch)
+            frames = torch.from_numpy(rng.integers(0, 256, (batch, h, w, 3), dtype=np.uint8)).cuda()
+            plan = engine.ResizePlan.for_video(h, w, 256)
+            want = net.forward_f32(engine.preprocess_f32(plan, frames)).cpu().numpy()
+            got = net.forward_frames(plan, frames).cpu().numpy()
+            worst = max(worst, float(np.abs(got - want).max()))
+        print("WORST", worst)
+        assert worst <= 2e-3, worst
+    """) % (root, os.path.join(root, "cut-detection_b200"))
+    env = dict(os.environ, CUTDET_CONV1_GRID="37")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
