@@ -1281,6 +1281,7 @@ struct TcState {
     // conv1 with |BN scale| folded into its taps (see tc_prepare): epilogue parameters |s|*bias, sign(s), sign(s)/256
     float *d_c1_bias = nullptr, *d_c1_sign = nullptr, *d_c1_sign256 = nullptr;
     bool c1_folded = false;
+    float *d_zero32 = nullptr;                                 // bias of the head when there is no FC layer
     std::map<std::tuple<const void *, int, int>, std::pair<CUtensorMap, CUtensorMap>> maps;   // (workspace, H*65536+W, sub) -> act1, act2 maps
     std::map<std::pair<int, int>, float *> fc1_folded;                                        // (P3h, P3w) -> [n_feat][32]
     std::mutex mutex;
@@ -1522,7 +1523,11 @@ int folded_fc1(cutdet_net *net, const Geom &g, float **out) {
     auto it = tc->fc1_folded.find(key);
     if (it != tc->fc1_folded.end()) { *out = it->second; return CUTDET_OK; }
     const int P = net->cfg.avg_pool_size, C = g.C, npix = g.P3h * g.P3w, n_feat = npix * C;
-    const FcLayer &L = net->fc[0];
+    // no FC layer: the "weights" are the identity on the flattened pooled features (c, i, j), so the fold is the pooling matrix
+    const bool identity = net->cfg.n_fc_layers == 0;
+    struct { int in, out; const float *w; } L;
+    if (identity) { L.in = L.out = C * P * P; L.w = nullptr; }
+    else { L.in = net->fc[0].in; L.out = net->fc[0].out; L.w = net->fc[0].w.data(); }
     std::vector<float> folded((size_t)n_feat * 32, 0.f);
     std::vector<double> acc((size_t)n_feat * L.out, 0.0);
     for (int i = 0; i < P; ++i) {
@@ -1532,9 +1537,12 @@ int folded_fc1(cutdet_net *net, const Geom &g, float **out) {
             const double inv = 1.0 / ((r1 - r0) * (c1 - c0));
             for (int r = r0; r < r1; ++r)
                 for (int cc = c0; cc < c1; ++cc)
-                    for (int ch = 0; ch < C; ++ch)
+                    for (int ch = 0; ch < C; ++ch) {
+                        const int feat = ch * P * P + i * P + j;
+                        if (identity) { acc[((size_t)(r * g.P3w + cc) * C + ch) * L.out + feat] += inv; continue; }
                         for (int o = 0; o < L.out; ++o)
-                            acc[((size_t)(r * g.P3w + cc) * C + ch) * L.out + o] += inv * L.w[(size_t)o * L.in + ch * P * P + i * P + j];
+                            acc[((size_t)(r * g.P3w + cc) * C + ch) * L.out + o] += inv * L.w[(size_t)o * L.in + feat];
+                    }
         }
     }
     for (int f = 0; f < n_feat; ++f)
@@ -1549,12 +1557,16 @@ int folded_fc1(cutdet_net *net, const Geom &g, float **out) {
 int run_head(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int batch, float *logits, cudaStream_t stream) {
     const float *cur = reinterpret_cast<const float *>(ws + w.act3);
     const int n_feat = g.P3h * g.P3w * g.C;
-    if (net->cfg.n_fc_layers == 0) {
-        // a bare FrameConvNet: pooled features [B, C*P*P] in (c, i, j) order -- not on the prod path
-        return fail(CUTDET_EUNSUPPORTED, "tensor-core path needs at least one FC layer");
-    }
     float *folded = nullptr;
     if (int rc = folded_fc1(net, g, &folded)) return rc;
+    if (net->cfg.n_fc_layers == 0) {
+        // a bare FrameConvNet: the pooled features [B, C*P*P] in (c, i, j) order ARE the output (avg-pool as a matrix, no bias)
+        KernelScope scope("head_fc1", stream);
+        head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, 128, 0, stream>>>(
+            cur, folded, net->tc->d_zero32, nullptr, nullptr, batch, n_feat, g.C * net->cfg.avg_pool_size * net->cfg.avg_pool_size, 0, logits);
+        CUTDET_LAUNCH_CHECK("head_fc1_kernel");
+        return CUTDET_OK;
+    }
     const FcLayer &L0 = net->fc[0];
     const bool last0 = net->cfg.n_fc_layers == 1;
     float *out0 = last0 ? logits : reinterpret_cast<float *>(ws + w.fc[0]);
@@ -1611,12 +1623,20 @@ bool tc_supported(const cutdet_net *net, int height, int width) {
 int tc_prepare(cutdet_net *net) {
     const cutdet_net_config &c = net->cfg;
     if (c.n_conv_layers != 3 || c.input_channels != 3 || (c.hidden_channels != 48 && c.hidden_channels != 32)) return CUTDET_OK;
-    if (c.n_fc_layers < 1 || c.fc_hidden_size > 32 || (c.n_fc_layers == 1 && c.fc_output_size > 32)) return CUTDET_OK;
+    // the head kernel produces up to 32 features per frame: the first FC layer's outputs, or -- for a bare FrameConvNet
+    // (the contrastive encoder's trunk, learn_contrasts.py:68-70) -- the C * P * P pooled features themselves
+    if (c.n_fc_layers == 0 ? c.hidden_channels * c.avg_pool_size * c.avg_pool_size > 32
+                           : (c.fc_hidden_size > 32 || (c.n_fc_layers == 1 && c.fc_output_size > 32)))
+        return CUTDET_OK;
     if (!encode_fn()) return CUTDET_OK;          // no TMA descriptor encoder in this driver: stay on the generic kernels
     const int C = c.hidden_channels, CG = C / 8;
     TcState *tc = new TcState();
     tc->C = C;
     net->tc = tc;
+    {
+        const std::vector<float> zeros(32, 0.f);
+        if (int rc = upload_bytes(net, zeros.data(), zeros.size() * sizeof(float), reinterpret_cast<void **>(&tc->d_zero32))) return rc;
+    }
     // conv1 B operand: [ky][half][n = dx*C + co][8], k16 = col*3 + ch, taps / 255.
     // |BN scale| is folded into the taps (s * relu(u) = sign(s) * relu(|s| * u)), so the epilogue is relu(max + |s|*bias) * sign + shift;
     // and K element 15, which no pixel uses, carries the bias for the fused gather path: there the pixels enter as 1024 + v and

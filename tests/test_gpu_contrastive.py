@@ -86,3 +86,24 @@ def test_batchstats_full_size_batch():
     want = ocon.forward_batchstats(w, x.cpu().numpy(), 1)
     assert np.abs(y - want).max() <= 2e-3
     assert np.abs(y.mean(axis=0)).max() <= 1e-3        # gamma = 1, beta = 0 on a fresh module
+
+
+def test_eval_mode_trunk_alone_runs_on_tensor_cores(kat):
+    """The contrastive encoder's trunk is a BARE FrameConvNet (learn_contrasts.py:68-70: no FC layer behind it in the same module);
+    after .eval() it takes the tensor-core path too, its 32 pooled features coming out of the head kernel with the avg-pool folded
+    into a matrix.  Against the float32 oracle with the same running statistics, at the 16-bit-operand tolerance."""
+    from oracle import net as onet
+    conv_net, _ = build_nets(kat)
+    with torch.no_grad():                       # non-trivial running statistics
+        for m in conv_net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.uniform_(-0.2, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+    conv_net.eval()
+    assert conv_net._native().uses_tensor_cores(144, 256)
+    x = kat_inputs.smooth_images(40, seed=9)
+    got = conv_net(torch.from_numpy(x).cuda()).cpu().numpy()
+    w = {"conv." + k: v.detach().cpu().numpy() for k, v in conv_net.state_dict().items()}
+    want = onet.forward_f32(w, x, 1)
+    assert got.shape == want.shape == (40, 32)
+    assert np.abs(got - want).max() <= 0.05 * max(1.0, float(np.abs(want).max())), float(np.abs(got - want).max())

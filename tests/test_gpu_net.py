@@ -215,7 +215,7 @@ def test_fused_kernel_with_several_frames_per_cta():
             rng = np.random.default_rng(h + batch)
             frames = torch.from_numpy(rng.integers(0, 256, (batch, h, w, 3), dtype=np.uint8)).cuda()
             plan = engine.ResizePlan.for_video(h, w, 256)
-            want = net.forward_f32(engine.preprocess_f32(plan, frames)).cpu().numpy()
+            want = net(engine.preprocess_f32(plan, frames)).cpu().numpy()
             got = net.forward_frames(plan, frames).cpu().numpy()
             worst = max(worst, float(np.abs(got - want).max()))
         print("WORST", worst)
