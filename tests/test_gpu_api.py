@@ -143,3 +143,37 @@ def test_videodataset_iteration(tmp_path):
         ok, f = cap.read()
         assert ok and np.array_equal(t, opre.preprocess_frame(f, 256))
     assert len(got) == 5 and list(ds) == []        # single pass
+
+
+def test_split_video_script_writes_the_references_jpegs(tmp_path):
+    """training_scripts/split_video.py: the resize runs in K1 on the GPU; the files must be byte-identical to
+    what the reference's loop writes (cv2.resize(INTER_LINEAR) + cv2.imwrite, split_video.py:40-53), here redone with cv2."""
+    import cv2
+    import subprocess, sys
+    w, h, n = 640, 360, 70
+    path = str(tmp_path / "clip.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 30, (w, h))
+    rng = np.random.default_rng(2)
+    for i in range(n):
+        frame = kat_inputs.stripes(h, w, 20, i % 2 == 0).copy()
+        frame[: h // 3] = rng.integers(0, 256, (h // 3, w, 3), dtype=np.uint8)
+        vw.write(frame)
+    vw.release()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "frames"
+    r = subprocess.run([sys.executable, os.path.join(root, "cut-detection_b200", "training_scripts", "split_video.py"), path, str(out),
+                        "--resize", "256", "--max-frames", "66"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.splitlines()[0] == f"Processing 66 frames from {path}." and r.stdout.splitlines()[-1] == "Done"
+    cap = cv2.VideoCapture(path)
+    ref_dir = tmp_path / "ref"
+    ref_dir.mkdir()
+    for i in range(66):
+        ok, frame = cap.read()
+        assert ok
+        frame = cv2.resize(frame, (256, int(h * (256 / w))), interpolation=cv2.INTER_LINEAR)
+        cv2.imwrite(f"{ref_dir}/frame_{i:07}.jpg", frame)
+    names = sorted(os.listdir(out))
+    assert names == sorted(os.listdir(ref_dir)) and len(names) == 66
+    for name in names:
+        assert open(out / name, "rb").read() == open(ref_dir / name, "rb").read(), name
