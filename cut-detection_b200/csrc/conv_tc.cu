@@ -1154,6 +1154,74 @@ __global__ void unpack_plain_kernel(const float *__restrict__ act, int batch, in
     out[idx] = act[((size_t)b * npix + pix) * C + c];
 }
 
+// ------------------------------------------------------------------------------------------------ batch-statistics BatchNorm
+// Training-mode forward on the tensor-core path (reference training_scripts/learn_contrasts.py:100-107: modules never put in
+// .eval()): a conv layer runs with the identity affine, which leaves relu(max + bias) in the phase-split buffer; these kernels
+// take the per-channel sums over the batch (entries that are not pixels are zero and add nothing), turn them into
+// scale = gamma / sqrt(var_biased + eps), shift = beta - mean * scale, and apply that to the real entries in place.
+__global__ void __launch_bounds__(256) bn_ps_stats_kernel(const uint4 *__restrict__ act, int CG, int gtot, int n_pos, double *__restrict__ sums) {
+    const int pc = blockIdx.y, cg = pc % CG;                 // pc = plane * CG + channel group; n_pos = frames * FP (the tail up to gtot is unused)
+    float s[8], ss[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s[c] = ss[c] = 0.f;
+    for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n_pos; pos += gridDim.x * blockDim.x) {
+        const uint4 q = act[(size_t)pc * gtot + pos];
+        const __half2 *h = reinterpret_cast<const __half2 *>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            s[2 * j] += f.x; ss[2 * j] = fmaf(f.x, f.x, ss[2 * j]);
+            s[2 * j + 1] += f.y; ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
+        }
+    }
+    __shared__ float red[2][8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float a = s[c], b = ss[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane == 0) { red[0][c][warp] = a; red[1][c][warp] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        const int k = threadIdx.x >> 3, c = threadIdx.x & 7;
+        double t = 0.0;
+        for (int w8 = 0; w8 < 8; ++w8) t += (double)red[k][c][w8];
+        atomicAdd(&sums[(cg * 8 + c) * 2 + k], t);
+    }
+}
+
+__global__ void bn_finalize_kernel(double *__restrict__ sums, double count, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                   float eps, int C, float *__restrict__ scale, float *__restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = sums[2 * c] / count, var = fmax(sums[2 * c + 1] / count - mean * mean, 0.0);
+    const float sc = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    sums[2 * c] = 0.0; sums[2 * c + 1] = 0.0;                // ready for the next layer
+}
+
+__global__ void __launch_bounds__(256) bn_ps_apply_kernel(uint4 *__restrict__ act, int CG, int gtot, int n_frames, int FP, int PW, int out_h,
+                                                          int out_w, const float *__restrict__ scale, const float *__restrict__ shift) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x, pc = blockIdx.y;
+    if (pos >= gtot) return;
+    const int plane = pc / CG, cg = pc % CG;
+    const int f = pos / FP, r = pos % FP, y = 3 * (r / PW) + plane / 3, x = 3 * (r % PW) + plane % 3;
+    if (f >= n_frames || y >= out_h || x >= out_w) return;   // not a pixel: stays zero (the next conv's padding)
+    uint4 q = act[(size_t)pc * gtot + pos];
+    __half2 *h = reinterpret_cast<__half2 *>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 v = __half22float2(h[j]);
+        const int c = cg * 8 + 2 * j;
+        const uint32_t packed = pack2(fmaf(v.x, scale[c], shift[c]), fmaf(v.y, scale[c + 1], shift[c + 1]));
+        h[j] = *reinterpret_cast<const __half2 *>(&packed);
+    }
+    act[(size_t)pc * gtot + pos] = q;
+}
+
 // ------------------------------------------------------------------------------------------------ head, first FC
 // AdaptiveAvgPool2d + flatten + Linear folded into one [n_feat x 32] matrix (the pool is linear), then ReLU and the
 // BatchNorm1d affine: out[f][o] = act(sum_k act3[f][k] * W[k][o] + bias[o]).  A block takes 16 frames; its two halves
@@ -1282,6 +1350,11 @@ struct TcState {
     float *d_c1_bias = nullptr, *d_c1_sign = nullptr, *d_c1_sign256 = nullptr;
     bool c1_folded = false;
     float *d_zero32 = nullptr;                                 // bias of the head when there is no FC layer
+    // batch-statistics forward (training-mode BatchNorm): conv1 taps WITHOUT the folded BatchNorm scale, identity affine, scratch
+    void *d_w1_plain = nullptr;
+    float *d_ones = nullptr, *d_zeros = nullptr;               // [C]
+    double *d_bn_sums = nullptr;                               // [C][2]
+    float *d_bn_scale = nullptr, *d_bn_shift = nullptr;        // [C]
     std::map<std::tuple<const void *, int, int>, std::pair<CUtensorMap, CUtensorMap>> maps;   // (workspace, H*65536+W, sub) -> act1, act2 maps
     std::map<std::pair<int, int>, float *> fc1_folded;                                        // (P3h, P3w) -> [n_feat][32]
     std::mutex mutex;
@@ -1682,6 +1755,27 @@ int tc_prepare(cutdet_net *net) {
             }
         }
         if (int rc = upload_bytes(net, w.data(), w.size() * 2, &tc->d_w1)) return rc;
+        {   // the taps as given (no BatchNorm scale, no bias row) for the batch-statistics forward pass
+            std::vector<uint16_t> wp((size_t)6 * 3 * C * 8, 0);
+            for (int co = 0; co < C; ++co)
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int col = 0; col < 5; ++col)
+                        for (int ch = 0; ch < 3; ++ch)
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const int kx = col - dx, k16 = col * 3 + ch;
+                                if (kx < 0 || kx > 2) continue;
+                                wp[(((size_t)(2 * ky + k16 / 8)) * 3 * C + dx * C + co) * 8 + k16 % 8] =
+                                    operand_bits(L.w[((size_t)co * 3 + ch) * 9 + ky * 3 + kx] * kW1Scale);
+                            }
+            if (int rc = upload_bytes(net, wp.data(), wp.size() * 2, &tc->d_w1_plain)) return rc;
+            const std::vector<float> ones(C, 1.f), zeros(C, 0.f);
+            if (int rc = upload_bytes(net, ones.data(), C * 4, reinterpret_cast<void **>(&tc->d_ones))) return rc;
+            if (int rc = upload_bytes(net, zeros.data(), C * 4, reinterpret_cast<void **>(&tc->d_zeros))) return rc;
+            if (int rc = upload_bytes(net, zeros.data(), C * 4, reinterpret_cast<void **>(&tc->d_bn_scale))) return rc;
+            if (int rc = upload_bytes(net, zeros.data(), C * 4, reinterpret_cast<void **>(&tc->d_bn_shift))) return rc;
+            const std::vector<double> dz(2 * C, 0.0);
+            if (int rc = upload_bytes(net, dz.data(), dz.size() * 8, reinterpret_cast<void **>(&tc->d_bn_sums))) return rc;
+        }
         if (int rc = upload_bytes(net, pb.data(), C * 4, reinterpret_cast<void **>(&tc->d_c1_bias))) return rc;
         if (int rc = upload_bytes(net, ps.data(), C * 4, reinterpret_cast<void **>(&tc->d_c1_sign))) return rc;
         if (int rc = upload_bytes(net, ps256.data(), C * 4, reinterpret_cast<void **>(&tc->d_c1_sign256))) return rc;
@@ -1726,6 +1820,108 @@ int tc_forward_f32(cutdet_net *net, const float *x, int batch, int height, int w
         return CUTDET_OK;
     };
     return g.C == 48 ? run_batch<48>(net, g, w, ws, batch, logits, stream, pack) : run_batch<32>(net, g, w, ws, batch, logits, stream, pack);
+}
+
+// Training-mode forward of the whole stack on the tensor-core path (one sub-batch: the statistics span the batch, so every
+// frame's activations must be resident together).  Layer by layer: kernel with the identity affine, batch statistics, affine.
+template <int C>
+int run_batchstats(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, const float *x, int batch, float *out, cudaStream_t stream) {
+    TcState *tc = net->tc;
+    std::pair<CUtensorMap, CUtensorMap> *maps = nullptr;
+    if (int rc = get_maps(net, g, w, ws, &maps)) return rc;
+    auto phase_split_bn = [&](char *act, int gtot, int FP, int PW, int out_h, int out_w, const ConvLayer &L) -> int {
+        const dim3 grid_s(std::min(64, (int)ceil_div(gtot, 256)), 9 * g.CG), grid_a((unsigned)ceil_div(gtot, 256), 9 * g.CG);
+        {
+            KernelScope scope("bn_ps_stats", stream);
+            bn_ps_stats_kernel<<<grid_s, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(act), g.CG, gtot, batch * FP, tc->d_bn_sums);
+        }
+        CUTDET_LAUNCH_CHECK("bn_ps_stats_kernel");
+        {
+            KernelScope scope("bn_finalize", stream);
+            bn_finalize_kernel<<<1, 64, 0, stream>>>(tc->d_bn_sums, (double)batch * out_h * out_w, L.d_gamma, L.d_beta, L.eps, C, tc->d_bn_scale,
+                                                     tc->d_bn_shift);
+        }
+        CUTDET_LAUNCH_CHECK("bn_finalize_kernel");
+        {
+            KernelScope scope("bn_ps_apply", stream);
+            bn_ps_apply_kernel<<<grid_a, 256, 0, stream>>>(reinterpret_cast<uint4 *>(act), g.CG, gtot, batch, FP, PW, out_h, out_w, tc->d_bn_scale,
+                                                           tc->d_bn_shift);
+        }
+        CUTDET_LAUNCH_CHECK("bn_ps_apply_kernel");
+        return CUTDET_OK;
+    };
+    // layer 1 (float input: the x-unfolded operand goes through L2)
+    {
+        const int64_t total = (int64_t)batch * g.H * g.P1w;
+        KernelScope scope("pack_xin_f32", stream);
+        pack_xin_f32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(x, batch, g.H, g.W, g.P1w, reinterpret_cast<uint4 *>(ws + w.xin));
+    }
+    CUTDET_LAUNCH_CHECK("pack_xin_f32_kernel");
+    Conv1Params c1;
+    memset(&c1, 0, sizeof(c1));
+    c1.xin = reinterpret_cast<const uint4 *>(ws + w.xin);
+    c1.B = batch; c1.H = g.H; c1.P1h = g.P1h; c1.P1w = g.P1w;
+    c1.tiles_per_frame = (g.P1h * g.P1w + 127) / 128;
+    c1.out = OutSpec{ws + w.act1, 0, w.gtot1, g.PW1, g.FP1, g.Q1h, 0, g.P1h, g.P1w};
+    c1.w_packed = reinterpret_cast<const uint4 *>(tc->d_w1_plain);
+    c1.bias = net->conv[0].d_bias; c1.scale = tc->d_ones; c1.shift = tc->d_zeros;
+    if (int rc = launch_conv1<C>(c1, stream)) return rc;
+    if (int rc = phase_split_bn(ws + w.act1, w.gtot1, g.FP1, g.PW1, g.P1h, g.P1w, net->conv[0])) return rc;
+    // layer 2
+    MidParams p2 = mid_params(batch, g.FP1, g.PW1, g.P2h, g.P2w);
+    p2.out = OutSpec{ws + w.act2, 0, w.gtot2, g.PW2, g.FP2, g.Q2h, 0, g.P2h, g.P2w};
+    p2.w_packed = reinterpret_cast<const uint4 *>(tc->d_w2);
+    p2.bias = net->conv[1].d_bias; p2.scale = tc->d_ones; p2.shift = tc->d_zeros;
+    if (int rc = launch_mid<C>(maps->first, p2, "conv2_tc", stream)) return rc;
+    if (int rc = phase_split_bn(ws + w.act2, w.gtot2, g.FP2, g.PW2, g.P2h, g.P2w, net->conv[1])) return rc;
+    // layer 3: [frame][pixel][C] float32
+    MidParams p3 = mid_params(batch, g.FP2, g.PW2, g.P3h, g.P3w);
+    p3.out = OutSpec{ws + w.act3, 1, 0, 0, 0, 0, 0, g.P3h, g.P3w};
+    p3.w_packed = reinterpret_cast<const uint4 *>(tc->d_w3);
+    p3.bias = net->conv[2].d_bias; p3.scale = tc->d_ones; p3.shift = tc->d_zeros;
+    if (int rc = launch_mid<C>(maps->second, p3, "conv3_tc", stream)) return rc;
+    if (int rc = launch_bn_batchstats(reinterpret_cast<float *>(ws + w.act3), batch * g.P3h * g.P3w, C, 1, net->conv[2].d_gamma,
+                                      net->conv[2].d_beta, net->conv[2].eps, stream))
+        return rc;
+    // head: avg-pool folded into the first matrix; every BatchNorm1d on batch statistics
+    const float *cur = reinterpret_cast<const float *>(ws + w.act3);
+    const int n_feat = g.P3h * g.P3w * g.C;
+    float *folded = nullptr;
+    if (int rc = folded_fc1(net, g, &folded)) return rc;
+    if (net->cfg.n_fc_layers == 0) {
+        KernelScope scope("head_fc1", stream);
+        head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, 128, 0, stream>>>(
+            cur, folded, tc->d_zero32, nullptr, nullptr, batch, n_feat, g.C * net->cfg.avg_pool_size * net->cfg.avg_pool_size, 0, out);
+        CUTDET_LAUNCH_CHECK("head_fc1_kernel");
+        return CUTDET_OK;
+    }
+    for (int j = 0; j < net->cfg.n_fc_layers; ++j) {
+        const FcLayer &L = net->fc[j];
+        const bool is_last = j + 1 == net->cfg.n_fc_layers;
+        float *o = is_last ? out : reinterpret_cast<float *>(ws + w.fc[j & 1]);
+        if (j == 0) {
+            KernelScope scope("head_fc1", stream);
+            head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, 128, 0, stream>>>(cur, folded, L.d_bias, nullptr, nullptr, batch, n_feat, L.out,
+                                                                                        is_last ? 0 : 1, o);
+            CUTDET_LAUNCH_CHECK("head_fc1_kernel");
+        } else if (int rc = launch_fc(cur, o, L, batch, !is_last, stream, false)) {
+            return rc;
+        }
+        if (L.has_bn)
+            if (int rc = launch_bn_batchstats(o, batch, L.out, 1, L.d_gamma, L.d_beta, L.eps, stream)) return rc;
+        cur = o;
+    }
+    return CUTDET_OK;
+}
+
+bool tc_batchstats_supported(const cutdet_net *net, int batch, int height, int width) {
+    return tc_supported(net, height, width) && batch <= SUB_BATCH;
+}
+
+int tc_forward_f32_batchstats(cutdet_net *net, const float *x, int batch, int height, int width, float *out, char *ws, cudaStream_t stream) {
+    const Geom g = make_geom(height, width, net->cfg.hidden_channels);
+    const TcWorkspace w = tc_workspace(net, g, batch);
+    return g.C == 48 ? run_batchstats<48>(net, g, w, ws, x, batch, out, stream) : run_batchstats<32>(net, g, w, ws, x, batch, out, stream);
 }
 
 int tc_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cutdet_frames *src, float *logits, char *ws,

@@ -261,7 +261,7 @@ extern "C" int cutdet_net_forward_f32(cutdet_net *net, const float *x, int batch
 }
 
 extern "C" int cutdet_net_forward_f32_batchstats(cutdet_net *net, const float *x, int batch, int height, int width, float *out,
-                                                 void *workspace, size_t workspace_bytes, cutdet_stream_t stream) {
+                                                 void *workspace, size_t workspace_bytes, int use_tensor_cores, cutdet_stream_t stream) {
     CUTDET_REQUIRE(net && net->finalized, "net_forward_f32_batchstats: net not finalized");
     CUTDET_REQUIRE(batch >= 0 && height > 0 && width > 0, "net_forward_f32_batchstats: bad shape");
     if (batch == 0) return CUTDET_OK;
@@ -273,6 +273,8 @@ extern "C" int cutdet_net_forward_f32_batchstats(cutdet_net *net, const float *x
     if (workspace_bytes < need)
         return fail(CUTDET_ECAPACITY, "net_forward_f32_batchstats: workspace %zu < %zu bytes", workspace_bytes, need);
     char *base = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    if (use_tensor_cores && tc_batchstats_supported(net, batch, height, width))
+        return tc_forward_f32_batchstats(net, x, batch, height, width, out, base, as_stream(stream));
     GenericWorkspace ws = generic_workspace(net, batch, height, width, true);
     return forward_generic(net, x, batch, height, width, out, base, ws, as_stream(stream), true);
 }

@@ -61,7 +61,7 @@ _SIGNATURES = {
     "cutdet_net_uses_tensor_cores": (C.c_int, [_P, C.c_int, C.c_int]),
     "cutdet_net_workspace_bytes": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "cutdet_net_forward_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
-    "cutdet_net_forward_f32_batchstats": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
+    "cutdet_net_forward_f32_batchstats": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, C.c_int, _P]),
     "cutdet_net_forward_frames": (C.c_int, [_P, _P, C.POINTER(Frames), _P, _P, C.c_size_t, _P]),
     "cutdet_contrastive_loss_workspace_bytes": (C.c_size_t, [C.c_int]),
     "cutdet_contrastive_loss": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P, _P, C.c_size_t, _P]),

@@ -191,9 +191,10 @@ class NativeNet:
                                                        ws.numel(), _stream()))
         return out
 
-    def forward_f32_batchstats(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    def forward_f32_batchstats(self, x: torch.Tensor, out: torch.Tensor | None = None, tensor_cores: bool = True) -> torch.Tensor:
         """The forward pass of a module left in training mode: every BatchNorm normalises with this batch's mean and biased
-        variance (reference training_scripts/learn_contrasts.py:100-107).  Forward only."""
+        variance (reference training_scripts/learn_contrasts.py:100-107).  Forward only.  ``tensor_cores=False`` keeps the
+        float32 CUDA-core kernels (also used for architectures and batch sizes the tensor-core path does not cover)."""
         _need_cuda(x, "input")
         if x.dim() == 2:
             x = x[:, :, None, None]
@@ -209,7 +210,7 @@ class NativeNet:
             out = torch.empty((b, self.out_features), dtype=torch.float32, device=x.device)
         ws = self.workspace(b, h, w, x.device)
         _cabi.check(_cabi.lib().cutdet_net_forward_f32_batchstats(self.handle, x.data_ptr(), b, h, w, out.data_ptr(),
-                                                                  ws.data_ptr(), ws.numel(), _stream()))
+                                                                  ws.data_ptr(), ws.numel(), 1 if tensor_cores else 0, _stream()))
         return out
 
     def forward_frames(self, plan: ResizePlan, frames: torch.Tensor, compact: bool = False,

@@ -68,6 +68,10 @@ def _weights_of(module: nn.Module, prefix: str) -> dict:
 class _NativeBacked(nn.Module):
     """Builds (and caches) the native net for the module's current parameters."""
 
+    # training-mode forward: tcgen05 kernels + batch-statistics kernels where the tensor-core path applies (batches of up to 148
+    # frames); False keeps the float32 CUDA-core kernels everywhere
+    batchstats_tensor_cores = True
+
     def _native_parts(self):   # -> (weights dict, avg_pool_size)
         raise NotImplementedError
 
@@ -88,7 +92,7 @@ class _NativeBacked(nn.Module):
         reference's learn_contrasts.py never calls .eval()) normalises with the statistics of the batch: forward only --
         the running statistics are not updated and no autograd graph is built."""
         if self.training:
-            return self._native().forward_f32_batchstats(x)
+            return self._native().forward_f32_batchstats(x, tensor_cores=self.batchstats_tensor_cores)
         return self._native().forward_f32(x)
 
     def num_params(self):

@@ -148,9 +148,12 @@ CUTDET_API int cutdet_net_forward_f32(cutdet_net *net, const float *x_nchw_dev, 
 /* The same forward pass with every BatchNorm in TRAINING mode -- normalised with the mean and biased variance of this batch, as
  * nn.BatchNorm2d/1d do on a module that was never put in .eval() -- which is how the reference's contrastive script runs its
  * encoder (training_scripts/learn_contrasts.py:100-107: no .eval() anywhere).  Forward only: running statistics are not
- * updated and nothing is recorded for a backward pass.  float32 CUDA-core kernels; batch >= 2.                       */
+ * updated and nothing is recorded for a backward pass.  batch >= 2.  use_tensor_cores != 0: the tcgen05 kernels with the
+ * identity affine, then per-layer statistics/affine kernels (architectures the tensor-core path covers, batches of up to 148
+ * frames -- the statistics span the batch); otherwise, and for everything else, float32 CUDA-core kernels.            */
 CUTDET_API int cutdet_net_forward_f32_batchstats(cutdet_net *net, const float *x_nchw_dev, int batch, int height, int width,
-                           float *out_dev, void *workspace_dev, size_t workspace_bytes, cutdet_stream_t stream);
+                           float *out_dev, void *workspace_dev, size_t workspace_bytes, int use_tensor_cores,
+                           cutdet_stream_t stream);
 /* Fused entry: decoded frames in, logits out (K1 feeds the conv stack directly). */
 CUTDET_API int cutdet_net_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cutdet_frames *src,
                               float *logits_dev, void *workspace_dev, size_t workspace_bytes,

@@ -28,22 +28,26 @@ def build_nets(kat):
 
 
 def test_training_mode_forward_matches_reference(kat):
-    """learn_contrasts.py:100-108: x = cat(x_t1, x_t2); intermediate = conv_net(x); res = linear_net(intermediate)."""
+    """learn_contrasts.py:100-108: x = cat(x_t1, x_t2); intermediate = conv_net(x); res = linear_net(intermediate).
+    Twice: on the float32 CUDA-core kernels (summation order only) and on the tensor-core path (16-bit operands, batch statistics
+    taken from the stored 16-bit activations)."""
     conv_net, linear_net = build_nets(kat)
     assert conv_net.training and linear_net.training           # never put in .eval(), as in the reference script
     n = int(kat["pairs"])
     x = torch.from_numpy(np.concatenate([kat_inputs.smooth_images(n, seed=21), kat_inputs.smooth_images(n, seed=22)])).cuda()
-    inter = conv_net(x)
-    res = linear_net(inter)
-    d_inter = float(np.abs(inter.cpu().numpy() - kat["intermediate"]).max())
-    assert d_inter <= 1e-4, d_inter                             # float32 both sides, other summation order
+    for tensor_cores, tol_trunk, tol_chain in ((False, 1e-4, 1e-3), (True, 2e-2, 1e-1)):
+        conv_net.batchstats_tensor_cores = tensor_cores
+        inter = conv_net(x)
+        res = linear_net(inter)
+        d_inter = float(np.abs(inter.cpu().numpy() - kat["intermediate"]).max())
+        assert d_inter <= tol_trunk, (tensor_cores, d_inter)
+        # chained (BatchNorm over 12 samples divides by the batch deviation of each feature, which magnifies the trunk's differences)
+        d_chain = float(np.abs(res.cpu().numpy() - kat["projection"]).max())
+        assert d_chain <= tol_chain, (tensor_cores, d_chain)
+        print(f"contrastive forward, tensor cores {tensor_cores}: trunk {d_inter:.2e}, chained {d_chain:.2e}")
     # the projection head on the reference's own intermediate: one stage, no error carried in
     d_head = float(np.abs(linear_net(torch.from_numpy(kat["intermediate"]).cuda()).cpu().numpy() - kat["projection"]).max())
     assert d_head <= 1e-4, d_head
-    # chained (BatchNorm over 12 samples divides by the batch deviation of each feature, which magnifies the trunk's differences)
-    d_chain = float(np.abs(res.cpu().numpy() - kat["projection"]).max())
-    assert d_chain <= 1e-3, d_chain
-    print(f"contrastive forward: trunk {d_inter:.2e}, head {d_head:.2e}, chained {d_chain:.2e}")
     # eval() switches the same modules to the running statistics (fresh modules: mean 0, var 1): a different function
     conv_net.eval()
     assert np.abs(conv_net(x).cpu().numpy() - kat["intermediate"]).max() > 1e-2
@@ -81,11 +85,30 @@ def test_batchstats_full_size_batch():
     torch.manual_seed(0)
     net = FrameConvNet(hidden_channels=32, n_conv_layers=3).to("cuda")
     x = torch.from_numpy(kat_inputs.smooth_images(64, seed=5)).cuda()
-    y = net(x).cpu().numpy()            # avgpool 1x1 of the last BatchNorm'd map (5 x 9 positions)
     w = {"conv." + k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
     want = ocon.forward_batchstats(w, x.cpu().numpy(), 1)
-    assert np.abs(y - want).max() <= 2e-3
-    assert np.abs(y.mean(axis=0)).max() <= 1e-3        # gamma = 1, beta = 0 on a fresh module
+    for tensor_cores, tol in ((False, 1e-4), (True, 2e-2)):
+        net.batchstats_tensor_cores = tensor_cores
+        y = net(x).cpu().numpy()            # avgpool 1x1 of the last BatchNorm'd map (5 x 9 positions)
+        assert np.abs(y - want).max() <= tol, (tensor_cores, float(np.abs(y - want).max()))
+        assert np.abs(y.mean(axis=0)).max() <= 1e-3        # gamma = 1, beta = 0 on a fresh module
+
+
+def test_batchstats_whole_classifier_and_large_batches():
+    """A glued conv + linear net (the prod architecture) left in training mode: tensor-core path for up to 148 frames, the float32
+    kernels beyond (the statistics span the batch) -- both against the oracle."""
+    from frameID.net import load_default_net
+    from oracle import net as onet
+    net, params = load_default_net()
+    net.to("cuda")
+    assert net.training
+    w = {("conv." if i == 0 else "linear.") + k: v.detach().cpu().numpy() for i in (0, 1) for k, v in net[i].state_dict().items()}
+    for batch, tol in ((40, 5e-2), (200, 1e-3)):
+        x = kat_inputs.smooth_images(batch, seed=batch)
+        want = ocon.forward_batchstats(w, x, params["avg_pool_size"])
+        got = net(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= tol * max(1.0, float(np.abs(want).max())), (batch, float(np.abs(got - want).max()))
 
 
 def test_eval_mode_trunk_alone_runs_on_tensor_cores(kat):
