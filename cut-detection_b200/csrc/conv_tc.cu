@@ -190,14 +190,33 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_thread /* lane quart
 // running max, 7 * CH = 168 at C = 48, which is why the epilogue warps raise their register budget with setmaxnreg.
 // Block row 0 of the NEXT tile is requested before the BatchNorm/store of this one.  Per channel: max3, max3 + max, max3 + max3
 // with zero (FMNMX3): five operations, ReLU included.
+// The accumulator columns of a block row are ordered [channel half][dx][CH channels] (the B operand's rows are packed to match),
+// so the 3 * CH values a thread needs of a block row are CONTIGUOUS: two tcgen05.ld per block row (x64 + x8 at C = 48, x32 +
+// x16 at C = 32) instead of six, and a third of the address set-up.
 template <int CH>
-struct EpiRow { float a[CH], b[CH], c[CH]; };
+struct EpiRow { float v[3 * CH]; };
 
 template <int C>
 __device__ __forceinline__ void epi_issue_row(uint32_t tmem_thread, int dy, EpiRow<C / 2> &q) {
-    tmem_ld_ch<C / 2>(tmem_thread + (3 * dy + 0) * C, q.a);
-    tmem_ld_ch<C / 2>(tmem_thread + (3 * dy + 1) * C, q.b);
-    tmem_ld_ch<C / 2>(tmem_thread + (3 * dy + 2) * C, q.c);
+    static_assert(C == 48 || C == 32, "channels");
+    const uint32_t t = tmem_thread + dy * 3 * C;
+    if constexpr (C == 48) {
+        float lo[64], hi[8];
+        tmem_ld64(t, lo);
+        tmem_ld8(t + 64, hi);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) q.v[i] = lo[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q.v[64 + i] = hi[i];
+    } else {
+        float lo[32], hi[16];
+        tmem_ld32(t, lo);
+        tmem_ld16(t + 32, hi);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) q.v[i] = lo[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) q.v[32 + i] = hi[i];
+    }
 }
 
 // X: block row 0 of this tile, in flight on entry.  Y: free on entry; on exit it holds the next tile's block row 0 in flight.
@@ -211,7 +230,7 @@ __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, ui
     constexpr int CH = C / 2;
     auto arrived = [&](EpiRow<CH> &q, int dy) {       // block row dy is in registers: hand it back to the MMA issuer
         tmem_ld_wait();
-        reg_fence<CH>(q.a); reg_fence<CH>(q.b); reg_fence<CH>(q.c);
+        reg_fence<3 * CH>(q.v);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[dy]);
@@ -222,7 +241,7 @@ __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, ui
     tc_fence_after_sync();
     epi_issue_row<C>(tmem_thread, 1, Y);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(X.a[i], X.b[i]), X.c[i]);
+    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(X.v[i], X.v[CH + i]), X.v[2 * CH + i]);
     reg_fence<CH>(run);
     arrived(Y, 1);
     if (!f2) mbar_wait(&acc_full[2], acc_phase);
@@ -230,7 +249,7 @@ __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, ui
     epi_issue_row<C>(tmem_thread, 2, X);
     const bool f0 = more_tiles && mbar_try_wait(&acc_full[0], acc_phase ^ 1);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(fmaxf(run[i], Y.a[i]), Y.b[i]), Y.c[i]);
+    for (int i = 0; i < CH; ++i) run[i] = fmaxf(fmaxf(fmaxf(run[i], Y.v[i]), Y.v[CH + i]), Y.v[2 * CH + i]);
     reg_fence<CH>(run);
     arrived(X, 2);
     if (more_tiles) {
@@ -240,8 +259,8 @@ __device__ __forceinline__ void epilogue_tile_pipelined(uint32_t tmem_thread, ui
     }
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
-        const float m = fmaxf(fmaxf(run[i], X.a[i]), X.b[i]);
-        run[i] = fmaxf(fmaxf(m, X.c[i]), 0.f);          // the ReLU rides in the last max3 (the bias is inside the accumulator)
+        const float m = fmaxf(fmaxf(run[i], X.v[i]), X.v[CH + i]);
+        run[i] = fmaxf(fmaxf(m, X.v[2 * CH + i]), 0.f);  // the ReLU rides in the last max3 (the bias is inside the accumulator)
     }
     reg_fence<CH>(run);
 }
@@ -483,6 +502,7 @@ struct Conv1Params {
     const float *bias, *scale, *shift;
     long long *timeline;    // debug: clock64 stamps of CTA 0 (null = off)
     int folded;             // the taps carry |BN scale| and the bias row (the fast fused path needs it)
+    const uint4 *w_perm;    // fused kernel: w_packed with the rows of each block ordered [channel half][dx][C/2]
     const float *scale_magic; // fused kernel, integer-scale gather: +-1/256 (bias and ReLU happen inside the MMA / the max, see tc_prepare)
 };
 
@@ -786,7 +806,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;
     const uint32_t inv_slots = 0xffffffffu / (uint32_t)n_slots + 1u;       // n / n_slots = umulhi(n, inv_slots), exact while n * n_slots < 2^32
 
-    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_packed[i];
+    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_perm[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         s_par[i] = p.bias[i]; s_par[C + i] = p.scale_magic[i]; s_par[2 * C + i] = p.shift[i];
     }
@@ -1013,7 +1033,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         // ------------------------------------------------------------------ epilogue
         reg_alloc<F1_REGS_EPI>();
         const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
-        const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + ch0;
+        const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + half * 3 * CH;   // columns [dy][half][dx][CH]
         uint32_t acc_phase = 0;
         for (int fi = 0; fi < n_frames_cta; ++fi) zero_pads(p.out, CG, blockIdx.x + fi * gridDim.x, blockIdx.x + fi * gridDim.x + 1, threadIdx.x, EPI_WARPS * 32);
         int X = m % P1w, Y = m / P1w, fi = 0;              // position 128 t + m = ((fi * RPF + Y) * P1w + X), advanced tile by tile
@@ -1346,6 +1366,7 @@ int make_act_map(CUtensorMap *map, void *base, int CG, int gtot) {
 struct TcState {
     int C = 0;
     void *d_w1 = nullptr, *d_w2 = nullptr, *d_w3 = nullptr;   // packed 16-bit operands
+    void *d_w1_perm = nullptr;                                 // conv1 taps, rows ordered [channel half][dx][C/2] (fused kernel)
     // conv1 with |BN scale| folded into its taps (see tc_prepare): epilogue parameters |s|*bias, sign(s), sign(s)/256
     float *d_c1_bias = nullptr, *d_c1_sign = nullptr, *d_c1_sign256 = nullptr;
     bool c1_folded = false;
@@ -1518,6 +1539,7 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     c1.tiles_per_frame = (g.P1h * g.P1w + 127) / 128;
     c1.out = OutSpec{ws + w.act1, 0, w.gtot1, g.PW1, g.FP1, g.Q1h, 0, g.P1h, g.P1w};
     c1.w_packed = reinterpret_cast<const uint4 *>(tc->d_w1);
+    c1.w_perm = reinterpret_cast<const uint4 *>(tc->d_w1_perm);
     c1.bias = tc->c1_folded ? tc->d_c1_bias : net->conv[0].d_bias;
     c1.scale = tc->c1_folded ? tc->d_c1_sign : net->conv[0].d_scale;
     c1.shift = net->conv[0].d_shift;
@@ -1755,6 +1777,16 @@ int tc_prepare(cutdet_net *net) {
             }
         }
         if (int rc = upload_bytes(net, w.data(), w.size() * 2, &tc->d_w1)) return rc;
+        {   // the same rows in the order the fused kernel's epilogue reads its accumulator columns: [channel half][dx][C/2]
+            const int CHh = C / 2;
+            std::vector<uint16_t> wq(w.size(), 0);
+            for (int kyh = 0; kyh < 6; ++kyh)
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int co = 0; co < C; ++co)
+                        for (int e = 0; e < 8; ++e)
+                            wq[(((size_t)kyh) * 3 * C + (co / CHh) * 3 * CHh + dx * CHh + co % CHh) * 8 + e] = w[(((size_t)kyh) * 3 * C + dx * C + co) * 8 + e];
+            if (int rc = upload_bytes(net, wq.data(), wq.size() * 2, &tc->d_w1_perm)) return rc;
+        }
         {   // the taps as given (no BatchNorm scale, no bias row) for the batch-statistics forward pass
             std::vector<uint16_t> wp((size_t)6 * 3 * C * 8, 0);
             for (int co = 0; co < C; ++co)
