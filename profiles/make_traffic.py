@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """profiles/<round>_ncu_full.csv -> profiles/ncu_traffic.json (DRAM bytes per launch of each profiled kernel; bench.py reads it
-for roofline.traffic).     python profiles/make_traffic.py profiles/r01_v4_ncu_full.csv"""
+for roofline.traffic).     python profiles/make_traffic.py profiles/r01_v5_ncu_full.csv"""
 import csv, json, os, sys
 
 src = sys.argv[1]
