@@ -51,6 +51,7 @@
 #include <vector>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
@@ -304,6 +305,105 @@ __device__ __forceinline__ void store_pixel(const OutSpec &o, int b, int Y, int 
     }
 }
 
+
+// ---- the same pipeline on fp16 accumulators (conv1_fused_tc_kernel<.., ACC16 = true>) ----
+// The MMA writes D as fp16, one value per 32-bit column; tcgen05.ld.pack::16b returns two adjacent columns per register, i.e. a
+// half2 of two adjacent CHANNELS of one dx: half the TMEM read traffic, half the registers, and the 9-way max, the ReLU and the
+// affine run on channel pairs (VHMNMX, HFMA2).  The result IS the packed activation that gets stored.
+template <int CH>
+struct EpiRow16 { uint32_t v[3 * CH / 2]; };
+
+template <int N>
+__device__ __forceinline__ void reg_fence_u(uint32_t (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("" : "+r"(v[i]));
+}
+
+template <int C>
+__device__ __forceinline__ void epi_issue_row16(uint32_t tmem_thread, int dy, EpiRow16<C / 2> &q) {
+    static_assert(C == 48 || C == 32, "channels");
+    const uint32_t t = tmem_thread + dy * 3 * C;
+    if constexpr (C == 48) {            // 72 columns: 64 + 8
+        tmem_ld_pack32(t, q.v);
+        tmem_ld_pack4(t + 64, q.v + 32);
+    } else {                            // 48 columns: 32 + 16
+        tmem_ld_pack16(t, q.v);
+        tmem_ld_pack8(t + 32, q.v + 16);
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void epilogue_tile_pipelined16(uint32_t tmem_thread, uint64_t *acc_full, uint64_t *acc_empty, uint32_t acc_phase,
+                                                          int lane, bool more_tiles, EpiRow16<C / 2> &X, EpiRow16<C / 2> &Y,
+                                                          uint32_t (&run)[C / 4], long long *stamps = nullptr) {
+    constexpr int CP = C / 4;           // channel pairs per thread
+    if (stamps) stamps[0] = clock64();
+    auto arrived = [&](EpiRow16<C / 2> &q, int dy) {
+        tmem_ld_wait();
+        reg_fence_u<3 * CP>(q.v);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[dy]);
+    };
+    const bool f1 = mbar_try_wait(&acc_full[1], acc_phase), f2 = mbar_try_wait(&acc_full[2], acc_phase);
+    arrived(X, 0);
+    if (!f1) mbar_wait(&acc_full[1], acc_phase);
+    tc_fence_after_sync();
+    epi_issue_row16<C>(tmem_thread, 1, Y);
+#pragma unroll
+    for (int i = 0; i < CP; ++i) run[i] = hmax3(X.v[i], X.v[CP + i], X.v[2 * CP + i]);
+    reg_fence_u<CP>(run);
+    if (stamps) stamps[1] = clock64();
+    arrived(Y, 1);
+    if (stamps) stamps[2] = clock64();
+    if (!f2) mbar_wait(&acc_full[2], acc_phase);
+    tc_fence_after_sync();
+    epi_issue_row16<C>(tmem_thread, 2, X);
+    const bool f0 = more_tiles && mbar_try_wait(&acc_full[0], acc_phase ^ 1);
+#pragma unroll
+    for (int i = 0; i < CP; ++i) run[i] = hmax2(hmax3(run[i], Y.v[i], Y.v[CP + i]), Y.v[2 * CP + i]);
+    reg_fence_u<CP>(run);
+    if (stamps) stamps[3] = clock64();
+    arrived(X, 2);
+    if (stamps) stamps[4] = clock64();
+    if (more_tiles) {
+        if (!f0) mbar_wait(&acc_full[0], acc_phase ^ 1);
+        tc_fence_after_sync();
+        epi_issue_row16<C>(tmem_thread, 0, Y);
+    }
+#pragma unroll
+    for (int i = 0; i < CP; ++i) run[i] = hmax3(hmax3(run[i], X.v[i], X.v[CP + i]), X.v[2 * CP + i], 0u);   // ... and the ReLU
+    reg_fence_u<CP>(run);
+    if (stamps) stamps[5] = clock64();
+}
+
+// run = relu(accumulator incl. bias) as channel pairs: scale (+-2^k, exact) and BatchNorm shift, one HFMA2 per pair
+template <int C>
+__device__ __forceinline__ void epilogue_scale_shift16(const uint32_t *s_par16, int ch0, uint32_t (&run)[C / 4]) {
+    constexpr int CP = C / 4;
+    const uint4 *scale4 = reinterpret_cast<const uint4 *>(s_par16 + ch0 / 2);
+    const uint4 *shift4 = reinterpret_cast<const uint4 *>(s_par16 + C / 2 + ch0 / 2);
+#pragma unroll
+    for (int i = 0; i < CP / 4; ++i) {
+        const uint4 s = scale4[i], t = shift4[i];
+        run[4 * i + 0] = hfma2(run[4 * i + 0], s.x, t.x);
+        run[4 * i + 1] = hfma2(run[4 * i + 1], s.y, t.y);
+        run[4 * i + 2] = hfma2(run[4 * i + 2], s.z, t.z);
+        run[4 * i + 3] = hfma2(run[4 * i + 3], s.w, t.w);
+    }
+}
+
+// phase-split store of channel pairs that are already packed (mode 0 only: conv1 always feeds conv2)
+template <int C>
+__device__ __forceinline__ void store_pixel16(const OutSpec &o, int b, int Y, int X, int ch0, const uint32_t (&v)[C / 4]) {
+    constexpr int CG = C / 8, CH = C / 2;
+    const int plane = (Y % 3) * 3 + (X % 3);
+    uint4 *dst = reinterpret_cast<uint4 *>(o.ptr) +
+                 ((size_t)(plane * CG + ch0 / 8) * o.gtot + (size_t)(o.frame0 + b) * o.FP + (Y / 3) * o.PW + X / 3);
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j) dst[(size_t)j * o.gtot] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
 // Zero the entries of frames [f_lo, f_hi) of a phase-split buffer that are not real pixels (the last row and/or the
 // last column of each plane): they are the zero padding the next conv's shifted views read.
 __device__ __forceinline__ void zero_pads(const OutSpec &o, int CG, int f_lo, int f_hi, int tid, int nthreads) {
@@ -504,6 +604,10 @@ struct Conv1Params {
     int folded;             // the taps carry |BN scale| and the bias row (the fast fused path needs it)
     const uint4 *w_perm;    // fused kernel: w_packed with the rows of each block ordered [channel half][dx][C/2]
     const float *scale_magic; // fused kernel, integer-scale gather: +-1/256 (bias and ReLU happen inside the MMA / the max, see tc_prepare)
+    // fused kernel with fp16 accumulators (ACC16): taps scaled per channel by a power of two, pixels as fp16 subnormals, and the
+    // epilogue's scale (+-2^k) and BatchNorm shift as half2 pairs [C/2 scales | C/2 shifts]
+    const uint4 *w_perm16;
+    const uint32_t *par16;
 };
 
 template <int C>
@@ -645,10 +749,11 @@ __global__ void __launch_bounds__(416, 1) conv1_tc_kernel(const Conv1Params p) {
 constexpr int FR_CAP = 1024;                 // positions per sub-ring (a power of two)
 constexpr int FR_PLANE = (FR_CAP + 128) * 16;            // bytes of one k-half plane incl. the mirror
 constexpr int FR_SUB = 2 * FR_PLANE;
-constexpr int RAW_BYTES = 92160;              // raw-row ring: 24 rows of 720p, 8 row pairs of 1080p (what is left of the 227 KB)
+// raw-row ring: what is left of the 227 KB (24 rows of 720p, 8 row pairs of 1080p with four unfold warps; 22 / 7 with eight)
+constexpr int raw_bytes(int unfold_warps) { return 92160 - (unfold_warps - 4) * 1056; }
 constexpr int RAW_SLOTS_MAX = 24;
 constexpr int F_MAX_DST = 256;
-constexpr int F1_CMP_WARPS = 4, F1_CMP_STRIDE = F_MAX_DST + 8;   // [0] = the pixel left of the image, [1 + x] = pixel x, zeros after
+constexpr int F1_CMP_STRIDE = F_MAX_DST + 8;   // [0] = the pixel left of the image, [1 + x] = pixel x, zeros after
 
 struct FusedSrc {
     ResizePlanDev plan;
@@ -660,15 +765,16 @@ struct FusedSrc {
     int n_slots;      // raw ring slots of n_src * row_bytes each (2 .. RAW_SLOTS_MAX)
 };
 
-template <int C>
+template <int C, int UW>
 struct F1Smem {
+    static constexpr int RAW_BYTES = raw_bytes(UW);
     static constexpr int W_BYTES = 6 * 3 * C * 16;
     static constexpr int LBO_B = 3 * C * 16;
     static constexpr int OFF_RING = W_BYTES;
     static constexpr int OFF_RAW = OFF_RING + 3 * FR_SUB;
     static constexpr int OFF_TAB = OFF_RAW + RAW_BYTES + 64;           // 64 bytes of slack: the gather reads one word past a row
     static constexpr int OFF_CMP = OFF_TAB + F_MAX_DST * (8 + 8 + 16);  // rowoff[256][2], yb[256][2], xtab[256] (int4)
-    static constexpr int OFF_BAR = OFF_CMP + F1_CMP_WARPS * F1_CMP_STRIDE * 4;   // one resized row per unfold warp (general resize)
+    static constexpr int OFF_BAR = OFF_CMP + UW * F1_CMP_STRIDE * 4;   // one resized row per unfold warp (general resize)
     static constexpr int OFF_PAR = OFF_BAR + 1024;
     static constexpr int total = OFF_PAR + 3 * C * 4;
 };
@@ -711,7 +817,8 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
 // 512 threads: warps 0..7 = epilogue, 8..11 = unfold, 12 = MMA issuer (+ TMEM alloc), 13..14 = loaders, 15 idle.
 //
 // The four stages run DECOUPLED, each at its own pace, joined by two rings:
-//   loaders   rows of the source frame -> raw ring by cp.async.bulk, row n issued by loader n % 2: ONE issuing thread sustains a
+//   loaders   rows of the source frame -> raw ring by cp.async.bulk, row n issued by loader n % n_loaders (the slot count is a
+//             multiple of the loader count, so a slot is always refilled by the same loader): ONE issuing thread sustains a
 //             3,840-byte row per ~370 cycles (10 bytes/clock), two reach 5 TB/s (tools/hbm_rows.cu).  raw_full[slot]
 //             counts the bytes, raw_empty[slot] the reader's release, s_rows_issued[loader] says how far each loader is:
 //             a reader first checks that ITS row has been issued, because an mbarrier wait sees one parity bit and a reader
@@ -736,12 +843,19 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
 // Registers: 512 threads start with 128 each (the whole file); a group can only grow by what the others of the SAME CTA
 // have given up, so unfold drops to 80, group 3 to 48, and the epilogue rises to 192: 256 x 192 + 128 x 80 + 128 x 48 = 65,536.
 // (A request beyond the pool would block for ever: the launcher checks the compiled register count.)
-constexpr int UNFOLD_WARPS = 4, LOADER_WARPS = 2 /* 1, 2 or 4 */, F1_MMA_WARP = 8 + UNFOLD_WARPS, F1_LOAD_WARP0 = 9 + UNFOLD_WARPS;
-constexpr int F1_THREADS = 32 * (12 + UNFOLD_WARPS);
+// With fp16 accumulators (ACC16) the epilogue needs half the registers, which pays for a second warpgroup of unfold warps: the
+// unfold's per-row chain of barrier polls, shared-memory loads and stores (~1,600 cycles per row and warp) was what set the tile
+// period with four.  640 threads x 96 registers = 256 x 128 + 256 x 88 + 128 x 48.
+constexpr int LOADER_WARPS = 3 /* 1, 2 or 3: what is left of the MMA issuer's warpgroup */;
 constexpr int TILE_RING = 8;                 // tile_done barriers; FR_CAP / 128 tiles of run-ahead at most
-constexpr int F1_REGS_START = 128, F1_REGS_EPI = 192, F1_REGS_UNFOLD = 80, F1_REGS_LIGHT = 48;
-static_assert(F1_THREADS * F1_REGS_START == 256 * F1_REGS_EPI + 32 * UNFOLD_WARPS * F1_REGS_UNFOLD + 128 * F1_REGS_LIGHT, "register pool");
-static_assert(UNFOLD_WARPS == 4 || UNFOLD_WARPS == 8, "whole warpgroups");
+template <bool ACC16>
+struct F1Roles {
+    static constexpr int UNFOLD_WARPS = ACC16 ? 8 : 4;
+    static constexpr int MMA_WARP = 8 + UNFOLD_WARPS, LOAD_WARP0 = 9 + UNFOLD_WARPS;
+    static constexpr int THREADS = 32 * (12 + UNFOLD_WARPS);
+    static constexpr int REGS_START = ACC16 ? 96 : 128, REGS_EPI = ACC16 ? 128 : 192, REGS_UNFOLD = ACC16 ? 88 : 80, REGS_LIGHT = 48;
+    static_assert(THREADS * REGS_START == 256 * REGS_EPI + 32 * UNFOLD_WARPS * REGS_UNFOLD + 128 * REGS_LIGHT, "register pool");
+};
 template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -761,8 +875,11 @@ __device__ __forceinline__ int ld_acquire_shared(const int *p) {
 // Sixteen halves of one K-chunk in the 1024 + v format from five source words (B, G, R, <any>): RGB of pixels 0..4, then the
 // constant 1024.  Every half is the byte 0x64 over a pixel byte, so a word is one PRMT against the constant, or PRMT + LOP3
 // where its halves come from two pixels.
+// SUBN (the fp16-accumulator kernel): the halves are the fp16 SUBNORMALS v * 2^-24 (high byte zero: no offset to cancel,
+// which an fp16 accumulator could not carry) and the constant is 1.0.
+template <bool SUBN>
 __device__ __forceinline__ void chunk_from_raw(const uint32_t (&w)[5], uint4 &lo, uint4 &hi) {
-    constexpr uint32_t K = 0x64646464u, K0 = 0x64006464u, M = 0x00ff00ffu, O = 0x64006400u;
+    constexpr uint32_t K = SUBN ? 0u : 0x64646464u, K0 = SUBN ? 0x3c000000u : 0x64006464u, M = 0x00ff00ffu, O = SUBN ? 0u : 0x64006400u;
     lo.x = __byte_perm(w[0], K, 0x4142);                        // R0 G0
     lo.y = (__byte_perm(w[0], w[1], 0x0600) & M) | O;           // B0 R1
     lo.z = __byte_perm(w[1], K, 0x4041);                        // G1 B1
@@ -773,9 +890,11 @@ __device__ __forceinline__ void chunk_from_raw(const uint32_t (&w)[5], uint4 &lo
     hi.w = __byte_perm(w[4], K0, 0x7640);                       // B4, then the constant 1024 that multiplies the bias row
 }
 
-template <int C, bool GATHER>
-__global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Conv1Params p, const FusedSrc src) {
-    using S = F1Smem<C>;
+template <int C, bool GATHER, bool ACC16>
+__global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_kernel(const Conv1Params p, const FusedSrc src) {
+    using RL = F1Roles<ACC16>;
+    constexpr int UNFOLD_WARPS = RL::UNFOLD_WARPS, F1_MMA_WARP = RL::MMA_WARP, F1_LOAD_WARP0 = RL::LOAD_WARP0;
+    using S = F1Smem<C, UNFOLD_WARPS>;
     constexpr int CG = C / 8, CH = C / 2;
     constexpr int NP = (F_MAX_DST / 3 + 31) / 32;                               // 32-column parts of a resized row (P1w <= 85)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -806,16 +925,18 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;
     const uint32_t inv_slots = 0xffffffffu / (uint32_t)n_slots + 1u;       // n / n_slots = umulhi(n, inv_slots), exact while n * n_slots < 2^32
 
-    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_perm[i];
+    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = (ACC16 ? p.w_perm16 : p.w_perm)[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
-        s_par[i] = p.bias[i]; s_par[C + i] = p.scale_magic[i]; s_par[2 * C + i] = p.shift[i];
+        if (ACC16) { reinterpret_cast<uint32_t *>(s_par)[i] = p.par16[i]; }
+        else { s_par[i] = p.bias[i]; s_par[C + i] = p.scale_magic[i]; s_par[2 * C + i] = p.shift[i]; }
     }
     // The only positions read before they are written: the row above the first frame (tile 0's view shifted by -P1w).
-    const uint32_t Z2 = 0x64006400u;                          // two zero pixel values in the operand format
-    for (int i = threadIdx.x; i < F1_CMP_WARPS * F1_CMP_STRIDE; i += blockDim.x) s_cmp[i] = 0u;
+    // two zero pixel values in the operand format; the last half of the second plane is the constant that multiplies the bias row
+    const uint32_t Z2 = ACC16 ? 0u : 0x64006400u, Z2K = ACC16 ? 0x3c000000u : 0x64006400u;
+    for (int i = threadIdx.x; i < UNFOLD_WARPS * F1_CMP_STRIDE; i += blockDim.x) s_cmp[i] = 0u;
     for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
         reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
-            make_uint4(Z2, Z2, Z2, Z2);
+            make_uint4(Z2, Z2, Z2, i >= P1w ? Z2K : Z2);
     for (int y = threadIdx.x; y < H; y += blockDim.x) {
         int r0, r1, b0 = 2048, b1 = 0;
         if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
@@ -854,7 +975,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
     if (tl && threadIdx.x == 0) tl[2047] = clock64();
 
     if (warp >= F1_MMA_WARP) {
-        reg_dealloc<F1_REGS_LIGHT>();                            // one instruction for the whole warpgroup (.sync.aligned)
+        reg_dealloc<RL::REGS_LIGHT>();                            // one instruction for the whole warpgroup (.sync.aligned)
         if (warp > F1_MMA_WARP) {
             // ------------------------------------------------------------------ loaders: source rows -> raw ring
             // (the wait on raw_empty is for row n - n_slots to have been read; the slot cannot be a phase further, since that
@@ -885,12 +1006,13 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             // ------------------------------------------------------------------ MMA issuer
             uint32_t acc_phase = 0;
             const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
-            const uint32_t idesc = instr_desc_16bit(128, 3 * C, kBf16);
+            const uint32_t idesc = ACC16 ? instr_desc_f16_acc16(128, 3 * C) : instr_desc_16bit(128, 3 * C, kBf16);
             for (int t = 0; t < n_tiles; ++t) {
                 // rows of sub-rings 1 and 2 up to pooled row (128t + 127) / P1w, of sub-ring 0 one pooled row further
                 const int u_hi = min(total_u - 1, 3 * ((t * 128 + 127) / P1w + 1));
                 const int mine = lane & (UNFOLD_WARPS - 1);
                 const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
+                if (tl && lane == 0 && t < 60) tl[1800 + 4 * t + 3] = clock64();
                 while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(32);
                 __syncwarp();
                 tc_fence_after_sync();
@@ -905,6 +1027,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                 for (int dy = 0; dy < 3; ++dy) {
                     mbar_wait(&acc_empty[dy], acc_phase ^ 1);
                     tc_fence_after_sync();
+                    if (tl && lane == 0 && t < 60) tl[1800 + 4 * t + dy] = clock64();
                     if (elect_one()) {
     #pragma unroll
                         for (int ks = 0; ks < 3; ++ks) {
@@ -923,9 +1046,9 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         }
     } else if (warp >= 8 && warp < 8 + UNFOLD_WARPS) {
         // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
-        reg_dealloc<F1_REGS_UNFOLD>();
+        reg_dealloc<RL::REGS_UNFOLD>();
         const int pwarp = warp - 8;
-        const int n_loaders = min(LOADER_WARPS, n_slots), log2_loaders = n_loaders == 4 ? 2 : n_loaders == 2 ? 1 : 0;
+        const int n_loaders = min(LOADER_WARPS, n_slots);
         // fast path constants: tap j of pooled column px starts at byte 3*off_x + BS*(3px - 1 + j), BS = 3*step_x; a part is
         // 32 columns = 96*BS bytes further on (a multiple of 4), so the word offset of part 0 and the byte phase serve all parts
         const int BS = 3 * plan.gather_step_x, PB = 96 * BS;
@@ -957,7 +1080,9 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                 tiles_waited = last_reader + 1;
             }
             if (r.real) {
-                const int ld = n & (n_loaders - 1), want = (n >> log2_loaders) + 1;
+                int ld, want;                                // row n is loader n % n_loaders' (n / n_loaders + 1)-th
+                if (n_loaders == 3) { ld = n % 3; want = n / 3 + 1; }
+                else { ld = n & (n_loaders - 1); want = (n >> (n_loaders - 1)) + 1; }     // 1 or 2 loaders
                 while (ld_acquire_shared(&s_rows_issued[ld]) < want) __nanosleep(32);
                 mbar_wait(&raw_full[r.slot], use & 1);
             }
@@ -971,7 +1096,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
                 const int px = part * 32 + lane;
                 if (px < P1w) {
                     uint4 lo, hi;
-                    chunk_from_raw(w[part], lo, hi);                     // zero rows: w = 0 gives the format's zeros
+                    chunk_from_raw<ACC16>(w[part], lo, hi);                     // zero rows: w = 0 gives the format's zeros
                     const int pos = (pos0 + part * 32) & (FR_CAP - 1);
                     uint8_t *dst = s_ring + r.sub * FR_SUB + pos * 16;
                     *reinterpret_cast<uint4 *>(dst) = lo;
@@ -998,7 +1123,10 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         for (int u = pwarp; u < total_u; u += UNFOLD_WARPS) {
             Row r0;
             int y0;
+            const bool stamp = tl && pwarp == 0 && lane == 0 && rows_done < 96;
+            if (stamp) tl[256 + 4 * rows_done] = clock64();
             next_row(r0, y0);
+            if (stamp) tl[256 + 4 * rows_done + 1] = clock64();
             uint32_t w0[NP][5];
             if (GATHER) {
                 gather(r0, w0);
@@ -1021,8 +1149,10 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
             emit(r0, w0);
             // one fence for both directions: the stores above become visible to the MMA's async-proxy reads, and the loads from
             // the raw slot are ordered before the async-proxy refill that the release below allows
+            if (stamp) tl[256 + 4 * rows_done + 2] = clock64();
             fence_proxy_async();
             __syncwarp();
+            if (stamp) tl[256 + 4 * rows_done + 3] = clock64();
             ++rows_done;
             if (lane == 0) {
                 if (r0.real) mbar_arrive(&raw_empty[r0.slot]);
@@ -1031,30 +1161,43 @@ __global__ void __launch_bounds__(F1_THREADS, 1) conv1_fused_tc_kernel(const Con
         }
     } else {
         // ------------------------------------------------------------------ epilogue
-        reg_alloc<F1_REGS_EPI>();
+        reg_alloc<RL::REGS_EPI>();
         const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
         const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + half * 3 * CH;   // columns [dy][half][dx][CH]
         uint32_t acc_phase = 0;
         for (int fi = 0; fi < n_frames_cta; ++fi) zero_pads(p.out, CG, blockIdx.x + fi * gridDim.x, blockIdx.x + fi * gridDim.x + 1, threadIdx.x, EPI_WARPS * 32);
         int X = m % P1w, Y = m / P1w, fi = 0;              // position 128 t + m = ((fi * RPF + Y) * P1w + X), advanced tile by tile
         while (Y >= RPF) { Y -= RPF; ++fi; }
-        EpiRow<CH> bufA, bufB;
+        using Row = typename std::conditional<ACC16, EpiRow16<CH>, EpiRow<CH>>::type;
+        Row bufA, bufB;
         if (n_tiles > 0) {
             mbar_wait(&acc_full[0], 0);
             tc_fence_after_sync();
-            epi_issue_row<C>(tmem_thread, 0, bufA);
+            if constexpr (ACC16) epi_issue_row16<C>(tmem_thread, 0, bufA);
+            else epi_issue_row<C>(tmem_thread, 0, bufA);
         }
-        auto tile = [&](int t, EpiRow<CH> &cur, EpiRow<CH> &nxt) {
+        auto tile = [&](int t, Row &cur, Row &nxt) {
             const bool valid = fi < n_frames_cta && Y < p.P1h;
-            float v[CH];
-            epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v);
-            epilogue_scale_shift<C>(s_par, ch0, v);
-            if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
+            if constexpr (ACC16) {
+                uint32_t v[CH / 2];
+                epilogue_tile_pipelined16<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v,
+                                             (tl && threadIdx.x == 0 && t < 64) ? tl + 1216 + 8 * t : nullptr);
+                epilogue_scale_shift16<C>(reinterpret_cast<const uint32_t *>(s_par), ch0, v);
+                if (valid) store_pixel16<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
+            } else {
+                float v[CH];
+                epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v);
+                epilogue_scale_shift<C>(s_par, ch0, v);
+                if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
+            }
             if (tl && threadIdx.x == 0 && t < 64) tl[1152 + t] = clock64();
             acc_phase ^= 1;
+            // next tile: 128 positions on.  64 <= P1w (fused_source), so at most three rows further; branch-free, the lanes differ
             X += 128;
-            while (X >= P1w) { X -= P1w; ++Y; }
-            while (Y >= RPF) { Y -= RPF; ++fi; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const bool c = X >= P1w; X -= c ? P1w : 0; Y += c ? 1 : 0; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const bool c = Y >= RPF; Y -= c ? RPF : 0; fi += c ? 1 : 0; }
         };
         for (int t = 0; t < n_tiles; t += 2) {          // the two buffers swap roles from one tile to the next
             tile(t, bufA, bufB);
@@ -1370,6 +1513,9 @@ struct TcState {
     // conv1 with |BN scale| folded into its taps (see tc_prepare): epilogue parameters |s|*bias, sign(s), sign(s)/256
     float *d_c1_bias = nullptr, *d_c1_sign = nullptr, *d_c1_sign256 = nullptr;
     bool c1_folded = false;
+    // ... and for the fused kernel with fp16 accumulators: taps * 2^a[co] (see tc_prepare), half2 pairs of +-2^(16-a) and shift
+    void *d_w1_perm16 = nullptr;
+    uint32_t *d_c1_par16 = nullptr;
     float *d_zero32 = nullptr;                                 // bias of the head when there is no FC layer
     // batch-statistics forward (training-mode BatchNorm): conv1 taps WITHOUT the folded BatchNorm scale, identity affine, scratch
     void *d_w1_plain = nullptr;
@@ -1430,8 +1576,12 @@ int upload_bytes(cutdet_net *net, const void *host, size_t bytes, void **dev) {
 template <int C>
 int set_smem_limits() {
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1Smem<C>::total));
-    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F1Smem<C>::total));
-    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F1Smem<C>::total));
+    constexpr int smem32 = F1Smem<C, F1Roles<false>::UNFOLD_WARPS>::total, smem16 = F1Smem<C, F1Roles<true>::UNFOLD_WARPS>::total;
+    static_assert(smem32 <= 232448 && smem16 <= 232448, "227 KB of shared memory per CTA");
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, MidSmem<C>::total));
     return CUTDET_OK;
 }
@@ -1448,21 +1598,45 @@ int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
 }
 
 template <int C>
-int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src, cudaStream_t stream) {
+int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream) {
     // CUTDET_CONV1_GRID caps the grid (test hook: several frames per CTA, as on a part with fewer SMs than a sub-batch has frames)
     static const int grid_cap = [] { const char *e = getenv("CUTDET_CONV1_GRID"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 1 << 30; }();
     const int grid = std::min(std::min(p.B, sm_count()), grid_cap);
-    static const int regs_g = [] { cudaFuncAttributes a{}; cudaFuncGetAttributes(&a, conv1_fused_tc_kernel<C, true>); return a.numRegs; }();
-    static const int regs_l = [] { cudaFuncAttributes a{}; cudaFuncGetAttributes(&a, conv1_fused_tc_kernel<C, false>); return a.numRegs; }();
-    if (regs_g != F1_REGS_START || regs_l != F1_REGS_START) {
-        fprintf(stderr, "cutdet: conv1_fused_tc compiled with %d/%d registers, the setmaxnreg budget assumes %d\n", regs_g, regs_l, F1_REGS_START);
-        return CUTDET_EUNSUPPORTED;
-    }
+    static const bool regs_ok = [] {
+        const void *fns[4] = {(const void *)conv1_fused_tc_kernel<C, true, false>, (const void *)conv1_fused_tc_kernel<C, false, false>,
+                              (const void *)conv1_fused_tc_kernel<C, true, true>, (const void *)conv1_fused_tc_kernel<C, false, true>};
+        bool ok = true;
+        for (int i = 0; i < 4; ++i) {
+            cudaFuncAttributes a{};
+            cudaFuncGetAttributes(&a, fns[i]);
+            const int want = i < 2 ? F1Roles<false>::REGS_START : F1Roles<true>::REGS_START;
+            if (a.numRegs != want) {
+                fprintf(stderr, "cutdet: conv1_fused_tc compiled with %d registers, the setmaxnreg budget assumes %d\n", a.numRegs, want);
+                ok = false;
+            }
+        }
+        return ok;
+    }();
+    if (!regs_ok) return CUTDET_EUNSUPPORTED;
+    // fp16 accumulators (half the TMEM read traffic, the max/affine on channel pairs) unless CUTDET_CONV1_ACC32 asks for the fp32 ones
+    static const bool acc32 = getenv("CUTDET_CONV1_ACC32") != nullptr;
+    const bool acc16 = !acc32 && p.w_perm16 != nullptr;
+    FusedSrc src = src_in;
+    src.n_slots = (int)std::min<long long>(raw_bytes(acc16 ? F1Roles<true>::UNFOLD_WARPS : F1Roles<false>::UNFOLD_WARPS) / ((long long)src.n_src * src.row_bytes),
+                                           RAW_SLOTS_MAX);
+    // Every slot must belong to ONE loader (row n goes to loader n % n_loaders and to slot n % n_slots): a loader's wait on
+    // raw_empty sees one parity bit, and only its own earlier fill of that slot keeps it from running two phases ahead.
+    src.n_slots -= src.n_slots % std::min(LOADER_WARPS, src.n_slots);
+    constexpr int smem32 = F1Smem<C, F1Roles<false>::UNFOLD_WARPS>::total, smem16 = F1Smem<C, F1Roles<true>::UNFOLD_WARPS>::total;
+    constexpr int thr32 = F1Roles<false>::THREADS, thr16 = F1Roles<true>::THREADS;
     {
         KernelScope scope("conv1_fused_tc", stream);
         // fast path: integer-scale gather whose last pooled column has its right neighbour inside the image (dst_w % 3 != 0)
-        if (src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0) conv1_fused_tc_kernel<C, true><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
-        else conv1_fused_tc_kernel<C, false><<<grid, F1_THREADS, F1Smem<C>::total, stream>>>(p, src);
+        const bool gather = src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0;
+        if (gather && acc16) conv1_fused_tc_kernel<C, true, true><<<grid, thr16, smem16, stream>>>(p, src);
+        else if (gather) conv1_fused_tc_kernel<C, true, false><<<grid, thr32, smem32, stream>>>(p, src);
+        else if (acc16) conv1_fused_tc_kernel<C, false, true><<<grid, thr16, smem16, stream>>>(p, src);
+        else conv1_fused_tc_kernel<C, false, false><<<grid, thr32, smem32, stream>>>(p, src);
     }
     CUTDET_LAUNCH_CHECK("conv1_fused_tc_kernel");
     return CUTDET_OK;
@@ -1479,7 +1653,7 @@ bool fused_source(const cutdet_resize_plan *plan, const cutdet_frames *frames, c
     if ((long long)rows * frames->row_pitch >= (1LL << 31)) return false;
     const int n_src = (h.gather_step_x > 0 || h.mode == RESIZE_COPY) ? 1 : 2;
     const long long slot = n_src * row_bytes;
-    const long long n_slots = std::min<long long>(RAW_BYTES / slot, RAW_SLOTS_MAX);
+    const long long n_slots = std::min<long long>(raw_bytes(8) / slot, RAW_SLOTS_MAX);   // the smaller ring; launch_conv1_fused sets the final count
     if (n_slots < 2) return false;
     out->plan = h;
     out->frames = frames->frames_dev;
@@ -1544,6 +1718,8 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     c1.scale = tc->c1_folded ? tc->d_c1_sign : net->conv[0].d_scale;
     c1.shift = net->conv[0].d_shift;
     c1.scale_magic = tc->d_c1_sign256;
+    c1.w_perm16 = reinterpret_cast<const uint4 *>(tc->d_w1_perm16);
+    c1.par16 = tc->d_c1_par16;
     c1.folded = tc->c1_folded ? 1 : 0;
     if (fused) {
         FusedSrc fs = *fused;
@@ -1786,6 +1962,53 @@ int tc_prepare(cutdet_net *net) {
                         for (int e = 0; e < 8; ++e)
                             wq[(((size_t)kyh) * 3 * C + (co / CHh) * 3 * CHh + dx * CHh + co % CHh) * 8 + e] = w[(((size_t)kyh) * 3 * C + dx * C + co) * 8 + e];
             if (int rc = upload_bytes(net, wq.data(), wq.size() * 2, &tc->d_w1_perm)) return rc;
+        }
+        if (fold) {
+            // The fused kernel with fp16 accumulators.  Pixels enter as the fp16 subnormals v * 2^-24 (the byte itself under a zero
+            // byte), taps as w'' * 2^a with a per channel such that the largest tap lands in [2^14, 2^15): acc = 2^(a-16) * (z'' +
+            // |s| bias) is at most 27 * 2^15 * 255 * 2^-24 = 13.4, so no partial sum can overflow, and values down to 2^-24 * 2^(16-a)
+            // are kept (fp16 subnormals).  The constant K element is 1.0 and multiplies the bias, split over the three kernel rows
+            // in fp16 pieces (each refines the rest).  The epilogue multiplies by +-2^(16-a) (exact) and adds the shift.
+            const int CHh = C / 2;
+            std::vector<uint16_t> wq((size_t)6 * 3 * C * 8, 0);
+            std::vector<uint32_t> par(C, 0);
+            auto half_bits = [](float f) { const __half h = __float2half_rn(f); return __half_as_ushort(h); };
+            bool ok = true;
+            for (int co = 0; co < C && ok; ++co) {
+                const float a = fabsf(L.scale[co]);
+                float wmax = 0.f;
+                for (int i = 0; i < 27; ++i) wmax = std::max(wmax, fabsf(L.w[(size_t)co * 27 + i] * kW1Scale * a));
+                int e = 0;
+                if (wmax > 0.f) { frexpf(wmax, &e); }                    // wmax = m * 2^e, m in [0.5, 1)
+                const int ae = 15 - e;                                    // wmax * 2^ae in [2^14, 2^15)
+                if (ae < 2 || ae > 30) { ok = false; break; }             // scale 2^(16-ae) and the pieces must be fp16 numbers
+                const float up = ldexpf(1.f, ae);
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int col = 0; col < 5; ++col)
+                        for (int ch = 0; ch < 3; ++ch)
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const int kx = col - dx, k16 = col * 3 + ch;
+                                if (kx < 0 || kx > 2) continue;
+                                const float v = L.w[((size_t)co * 3 + ch) * 9 + ky * 3 + kx] * kW1Scale * a;
+                                wq[(((size_t)(2 * ky + k16 / 8)) * 3 * C + (co / CHh) * 3 * CHh + dx * CHh + co % CHh) * 8 + k16 % 8] = half_bits(v * up);
+                            }
+                double rest = (double)(a * L.bias[co]) * (double)ldexpf(1.f, ae - 16);
+                for (int ky = 0; ky < 3; ++ky) {
+                    const __half piece = __float2half_rn((float)rest);
+                    rest -= (double)__half2float(piece);
+                    for (int dx = 0; dx < 3; ++dx)
+                        wq[(((size_t)(2 * ky + 1)) * 3 * C + (co / CHh) * 3 * CHh + dx * CHh + co % CHh) * 8 + 7] = __half_as_ushort(piece);
+                }
+                const uint16_t sc = half_bits((L.scale[co] < 0.f ? -1.f : 1.f) * ldexpf(1.f, 16 - ae)), sh = half_bits(L.shift[co]);
+                uint32_t &ps = par[co / 2], &pt = par[C / 2 + co / 2];
+                ps |= (uint32_t)sc << (16 * (co & 1));
+                pt |= (uint32_t)sh << (16 * (co & 1));
+                if (!std::isfinite(L.shift[co]) || fabsf(L.shift[co]) > 60000.f) ok = false;
+            }
+            if (ok) {
+                if (int rc = upload_bytes(net, wq.data(), wq.size() * 2, &tc->d_w1_perm16)) return rc;
+                if (int rc = upload_bytes(net, par.data(), par.size() * 4, reinterpret_cast<void **>(&tc->d_c1_par16))) return rc;
+            }
         }
         {   // the taps as given (no BatchNorm scale, no bias row) for the batch-statistics forward pass
             std::vector<uint16_t> wp((size_t)6 * 3 * C * 8, 0);

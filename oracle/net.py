@@ -198,13 +198,49 @@ def _f16_round(a: np.ndarray) -> np.ndarray:
     return np.asarray(a, dtype=np.float32).astype(np.float16).astype(np.float32)
 
 
-def forward_tc_emulated(weights: dict, x: np.ndarray, avg_pool_size: int, fmt: str = "f16", return_features: bool = False):
+def _conv1_acc16(y, w_folded: np.ndarray, bias_folded: np.ndarray, sign: np.ndarray, shift: np.ndarray):
+    """Layer 1 as conv1_fused_tc_kernel<.., ACC16> computes it (cut-detection_b200/csrc/conv_tc.cu, tc_prepare): pixels v = 256 y
+    enter as v * 2^-24, the taps of channel co as fp16(w * 2^a), a such that the largest lands in [2^14, 2^15); the fp16
+    accumulator takes the three kernel rows one after the other (one rounding each), the bias rides on a constant 1.0 in three
+    fp16 pieces; 9-way max and ReLU on the fp16 values; one fused multiply-add by +-2^(16-a) and the fp16 shift."""
+    import torch
+    import torch.nn.functional as F
+
+    C = w_folded.shape[0]
+    wmax = np.abs(w_folded.reshape(C, -1)).max(axis=1)
+    e = np.where(wmax > 0, np.frexp(wmax)[1], 0).astype(np.int64)
+    ae = 15 - e
+    up = np.ldexp(np.float32(1), ae).astype(np.float32)
+    taps = _f16_round(w_folded * up.reshape(-1, 1, 1, 1)).astype(np.float64)
+    pieces = np.zeros((3, C))
+    rest = bias_folded.astype(np.float64) * np.ldexp(1.0, ae - 16)
+    for ky in range(3):
+        pieces[ky] = _f16_round(rest.astype(np.float32)).astype(np.float64)
+        rest = rest - pieces[ky]
+    v = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)) * 256.0          # integers 0..255 for decoded frames
+    vp = F.pad(v, (1, 1, 1, 1))
+    H = v.shape[2]
+    acc = None
+    for ky in range(3):
+        part = F.conv2d(vp[:, :, ky:ky + H, :], torch.from_numpy(taps[:, :, ky:ky + 1, :].copy()), None) * 2.0 ** -24
+        part = part + torch.from_numpy(pieces[ky]).view(1, -1, 1, 1)
+        tot = part if acc is None else acc.double() + part
+        acc = tot.half()                                                            # round to nearest even, subnormals kept
+    m = torch.relu(F.max_pool2d(acc.double(), kernel_size=3))
+    sc = torch.from_numpy(sign.astype(np.float64) * np.ldexp(1.0, 16 - ae)).view(1, -1, 1, 1)
+    sh = torch.from_numpy(_f16_round(shift).astype(np.float64)).view(1, -1, 1, 1)
+    return (m * sc + sh).half().float()
+
+
+def forward_tc_emulated(weights: dict, x: np.ndarray, avg_pool_size: int, fmt: str = "f16", return_features: bool = False,
+                        conv1_acc16: bool = False):
     """What the tensor-core path computes, restated on the CPU: conv operands rounded to 16 bits (fmt 'f16' as
     cut-detection_b200/csrc/conv_tc.cu ships, or 'bf16'), layer-1 input stored as x*255/256 with 256/255 folded into its
     weights (bf16: x*255 and 1/255), exact products, float32 epilogue (max-pool of the raw sums, +bias, ReLU, folded
     BatchNorm affine; layer 1 carries |scale| in its taps), 16-bit inter-layer activations, float32 head.  It separates 'the kernel is wrong' from
     '16-bit operands round': the CUDA path must match THIS to ~1e-3, and this differs from the fp32 reference by the
-    rounding the format implies."""
+    rounding the format implies.  conv1_acc16: layer 1 as the fused frames kernel computes it by default (fp16 accumulators,
+    see _conv1_acc16)."""
     import torch
     import torch.nn.functional as F
 
@@ -232,10 +268,13 @@ def forward_tc_emulated(weights: dict, x: np.ndarray, avg_pool_size: int, fmt: s
                 w = w * np.abs(s).reshape(-1, 1, 1, 1)
                 bias = bias * np.abs(s)
                 s = np.where(s < 0, np.float32(-1), np.float32(1)).astype(np.float32)
-            z = F.conv2d(y.double(), t(rnd(w)).double(), None, stride=1, padding=1).float()
-            z = F.max_pool2d(z, kernel_size=3)
-            z = torch.relu(z + t(bias).view(1, -1, 1, 1))
-            z = z * t(s).view(1, -1, 1, 1) + t(sh).view(1, -1, 1, 1)
+            if i == 0 and conv1_acc16 and fmt == "f16":
+                z = _conv1_acc16(y.numpy(), w, bias, s, sh)
+            else:
+                z = F.conv2d(y.double(), t(rnd(w)).double(), None, stride=1, padding=1).float()
+                z = F.max_pool2d(z, kernel_size=3)
+                z = torch.relu(z + t(bias).view(1, -1, 1, 1))
+                z = z * t(s).view(1, -1, 1, 1) + t(sh).view(1, -1, 1, 1)
             if i < n - 1:
                 z = t(rnd(z.numpy()))
             feats.append(z.numpy().copy())

@@ -1,7 +1,8 @@
 """K2/K3 on the GPU vs the oracle (float32 reference arithmetic) and the logits recorded from the reference.
 
 Tolerances (stated, per BASELINE.json north_star).  The tensor-core path multiplies 16-bit operands (fp16: pixels
-are exact, weights and inter-layer activations round at 2^-12) and accumulates in fp32:
+are exact, weights and inter-layer activations round at 2^-12) and accumulates in fp32 (layer 1 of the fused frames kernel
+in fp16, one rounding per kernel row -- the layer's output is stored as fp16 anyway):
   * against the fp32 reference:  |dlogit| <= 0.05 absolute (observed <= 0.015), labels equal wherever the reference's
     top-2 margin is >= 0.1;
   * against the CPU emulation of the same 16-bit arithmetic (oracle.net.forward_tc_emulated): |dlogit| <= 5e-3 --
@@ -21,6 +22,9 @@ from oracle import preprocess as opre
 pytestmark = pytest.mark.gpu
 
 TOL_TC, TOL_F32, TOL_EMU = 0.05, 2e-3, 5e-3
+# fused frames kernel against the unfused float entry: same taps and pixels.  With fp32 accumulators (CUTDET_CONV1_ACC32) the sums
+# differ in rounding only (observed <= 3e-4); the default fp16 accumulators round once per kernel row (emulation: <= 8e-3)
+FUSED_TOL = 2e-3 if "CUTDET_CONV1_ACC32" in os.environ else 2e-2
 MARGIN = 0.1
 
 
@@ -109,7 +113,9 @@ def test_matches_16bit_emulation(native, prod_weights):
         h, ww = frame.shape[:2]
         plan = engine.ResizePlan.for_video(h, ww, 256)
         got = net.forward_frames(plan, torch.from_numpy(frame[None]).cuda()).cpu().numpy()
-        want = onet.forward_tc_emulated(w, opre.preprocess_frame(frame)[None], params["avg_pool_size"])
+        # the fused frames kernel accumulates layer 1 in fp16 unless CUTDET_CONV1_ACC32 is set (csrc/conv_tc.cu launch_conv1_fused)
+        want = onet.forward_tc_emulated(w, opre.preprocess_frame(frame)[None], params["avg_pool_size"],
+                                        conv1_acc16="CUTDET_CONV1_ACC32" not in os.environ)
         assert np.abs(got - want).max() <= TOL_EMU, name
 
 
@@ -180,8 +186,7 @@ def test_bad_inputs(native):
 def test_fused_frames_equal_unfused(native, h, w, batch, compact):
     """K1 fused into conv1 (bulk-copied source rows -> resized pixels -> A operand) must give the same logits as
     preprocessing to float32 first and entering through net(x).  Both feed the MMAs the same 16-bit taps and the same pixel
-    values; the fused kernel enters them as 1024 + v with the offset and the bias carried by a weight row, so the float32 sums
-    of layer 1 differ in rounding only: <= 2e-3 on a logit (observed <= 3e-4)."""
+    values (FUSED_TOL above)."""
     from cutdet import engine
     net, _ = native
     rng = np.random.default_rng(h * 7 + batch)
@@ -194,7 +199,7 @@ def test_fused_frames_equal_unfused(native, h, w, batch, compact):
     if compact:
         dev = dev[:, torch.from_numpy(plan.rows.astype(np.int64)).cuda()].contiguous()
     got = net.forward_frames(plan, dev, compact).cpu().numpy()
-    assert float(np.abs(got - want).max()) <= 2e-3, float(np.abs(got - want).max())
+    assert float(np.abs(got - want).max()) <= FUSED_TOL, float(np.abs(got - want).max())
 
 
 def test_fused_kernel_with_several_frames_per_cta():
@@ -219,8 +224,8 @@ def test_fused_kernel_with_several_frames_per_cta():
             got = net.forward_frames(plan, frames).cpu().numpy()
             worst = max(worst, float(np.abs(got - want).max()))
         print("WORST", worst)
-        assert worst <= 2e-3, worst
-    """) % (root, os.path.join(root, "cut-detection_b200"))
+        assert worst <= %r, worst
+    """) % (root, os.path.join(root, "cut-detection_b200"), FUSED_TOL)
     env = dict(os.environ, CUTDET_CONV1_GRID="37")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
