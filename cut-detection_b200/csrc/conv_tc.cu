@@ -332,8 +332,12 @@ __device__ __forceinline__ void epi_issue_row16(uint32_t tmem_thread, int dy, Ep
     }
 }
 
+// Returns whether the next tile's block row 0 has been requested (into Y).  Its MMAs can only start once this tile's row 0 has
+// been handed back, so it is often NOT complete yet when this tile's reads are done: it is then polled without blocking
+// (mbarrier.test_wait) and the caller tries again after the store -- blocking here would put the rest of this tile behind the
+// next tile's first MMAs, and the MMA issuer behind that in turn.
 template <int C>
-__device__ __forceinline__ void epilogue_tile_pipelined16(uint32_t tmem_thread, uint64_t *acc_full, uint64_t *acc_empty, uint32_t acc_phase,
+__device__ __forceinline__ bool epilogue_tile_pipelined16(uint32_t tmem_thread, uint64_t *acc_full, uint64_t *acc_empty, uint32_t acc_phase,
                                                           int lane, bool more_tiles, EpiRow16<C / 2> &X, EpiRow16<C / 2> &Y,
                                                           uint32_t (&run)[C / 4], long long *stamps = nullptr) {
     constexpr int CP = C / 4;           // channel pairs per thread
@@ -345,7 +349,7 @@ __device__ __forceinline__ void epilogue_tile_pipelined16(uint32_t tmem_thread, 
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[dy]);
     };
-    const bool f1 = mbar_try_wait(&acc_full[1], acc_phase), f2 = mbar_try_wait(&acc_full[2], acc_phase);
+    const bool f1 = mbar_test_wait(&acc_full[1], acc_phase), f2 = mbar_test_wait(&acc_full[2], acc_phase);
     arrived(X, 0);
     if (!f1) mbar_wait(&acc_full[1], acc_phase);
     tc_fence_after_sync();
@@ -359,15 +363,14 @@ __device__ __forceinline__ void epilogue_tile_pipelined16(uint32_t tmem_thread, 
     if (!f2) mbar_wait(&acc_full[2], acc_phase);
     tc_fence_after_sync();
     epi_issue_row16<C>(tmem_thread, 2, X);
-    const bool f0 = more_tiles && mbar_try_wait(&acc_full[0], acc_phase ^ 1);
 #pragma unroll
     for (int i = 0; i < CP; ++i) run[i] = hmax2(hmax3(run[i], Y.v[i], Y.v[CP + i]), Y.v[2 * CP + i]);
     reg_fence_u<CP>(run);
     if (stamps) stamps[3] = clock64();
+    const bool f0 = more_tiles && mbar_test_wait(&acc_full[0], acc_phase ^ 1);
     arrived(X, 2);
     if (stamps) stamps[4] = clock64();
-    if (more_tiles) {
-        if (!f0) mbar_wait(&acc_full[0], acc_phase ^ 1);
+    if (f0) {
         tc_fence_after_sync();
         epi_issue_row16<C>(tmem_thread, 0, Y);
     }
@@ -375,6 +378,7 @@ __device__ __forceinline__ void epilogue_tile_pipelined16(uint32_t tmem_thread, 
     for (int i = 0; i < CP; ++i) run[i] = hmax3(hmax3(run[i], X.v[i], X.v[CP + i]), X.v[2 * CP + i], 0u);   // ... and the ReLU
     reg_fence_u<CP>(run);
     if (stamps) stamps[5] = clock64();
+    return f0 || !more_tiles;
 }
 
 // run = relu(accumulator incl. bias) as channel pairs: scale (+-2^k, exact) and BatchNorm shift, one HFMA2 per pair
@@ -393,15 +397,18 @@ __device__ __forceinline__ void epilogue_scale_shift16(const uint32_t *s_par16, 
     }
 }
 
-// phase-split store of channel pairs that are already packed (mode 0 only: conv1 always feeds conv2)
+// phase-split store of channel pairs that are already packed (mode 0 only: conv1 always feeds conv2).  The address is computed at
+// the START of the tile, where its chain of dependent integer operations hides behind the TMEM loads, not at the end.
 template <int C>
-__device__ __forceinline__ void store_pixel16(const OutSpec &o, int b, int Y, int X, int ch0, const uint32_t (&v)[C / 4]) {
-    constexpr int CG = C / 8, CH = C / 2;
+__device__ __forceinline__ uint4 *store_addr16(const OutSpec &o, int b, int Y, int X, int ch0) {
+    constexpr int CG = C / 8;
     const int plane = (Y % 3) * 3 + (X % 3);
-    uint4 *dst = reinterpret_cast<uint4 *>(o.ptr) +
-                 ((size_t)(plane * CG + ch0 / 8) * o.gtot + (size_t)(o.frame0 + b) * o.FP + (Y / 3) * o.PW + X / 3);
+    return reinterpret_cast<uint4 *>(o.ptr) + ((size_t)(plane * CG + ch0 / 8) * o.gtot + (size_t)(o.frame0 + b) * o.FP + (Y / 3) * o.PW + X / 3);
+}
+template <int C>
+__device__ __forceinline__ void store_pixel16(uint4 *dst, int gtot, const uint32_t (&v)[C / 4]) {
 #pragma unroll
-    for (int j = 0; j < CH / 8; ++j) dst[(size_t)j * o.gtot] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < C / 16; ++j) dst[(size_t)j * gtot] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
 // Zero the entries of frames [f_lo, f_hi) of a phase-split buffer that are not real pixels (the last row and/or the
@@ -814,7 +821,8 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
     return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16);
 }
 
-// 512 threads: warps 0..7 = epilogue, 8..11 = unfold, 12 = MMA issuer (+ TMEM alloc), 13..14 = loaders, 15 idle.
+// Warps 0..7 = epilogue, then the unfold warps, the MMA issuer (+ TMEM alloc) and three loaders (F1Roles below: 640 threads with
+// fp16 accumulators, 512 with fp32 ones).
 //
 // The four stages run DECOUPLED, each at its own pace, joined by two rings:
 //   loaders   rows of the source frame -> raw ring by cp.async.bulk, row n issued by loader n % n_loaders (the slot count is a
@@ -839,22 +847,26 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
 // Counters instead of per-tile mbarriers: a row is produced by ONE warp, tiles need rows from all of them, and a warp must never
 // have to wait for a tile it contributes nothing to (the lock-step version spent 2/3 of its time in such waits).
 // GATHER: the resize is out[y][x] = src[off_y + y*step_y][off_x + x*step_x] (every second tap has zero weight).
-// Warpgroups (setmaxnreg works on four consecutive warps): 0-1 epilogue, 2 unfold, 3 = MMA issuer, two loaders, one idle warp.
-// Registers: 512 threads start with 128 each (the whole file); a group can only grow by what the others of the SAME CTA
-// have given up, so unfold drops to 80, group 3 to 48, and the epilogue rises to 192: 256 x 192 + 128 x 80 + 128 x 48 = 65,536.
-// (A request beyond the pool would block for ever: the launcher checks the compiled register count.)
+// Registers: setmaxnreg works on four consecutive warps, and a group can only grow by what the others of the SAME CTA have given
+// up (a request beyond the pool would block for ever: the launcher checks the compiled register count).
 // With fp16 accumulators (ACC16) the epilogue needs half the registers, which pays for a second warpgroup of unfold warps: the
-// unfold's per-row chain of barrier polls, shared-memory loads and stores (~1,600 cycles per row and warp) was what set the tile
-// period with four.  640 threads x 96 registers = 256 x 128 + 256 x 88 + 128 x 48.
-constexpr int LOADER_WARPS = 3 /* 1, 2 or 3: what is left of the MMA issuer's warpgroup */;
+// unfold's per-row chain of barrier polls, shared-memory loads and stores (~1,600 cycles per row and warp) set the tile period
+// with four.  MMA_WARPS = 3 (one issuer per block row; a block row's issue -- barrier wait, three descriptors moved to uniform
+// registers, three UTCHMMA, commit -- costs a warp 300-450 cycles) with six unfold warps measured the same at 720p and lower
+// where the unfold computes the resize (360p 1.50 -> 1.37 M frames/s), so one issuer it stays.
+// Warps: 0-7 epilogue | 8.. unfold | MMA issuer(s) | three loaders.  Registers are set per WARPGROUP (setmaxnreg.sync.aligned):
+// the epilogue groups rise, the last group (issuer + loaders) drops to 48, the groups between take the unfold budget.
+// ACC16: 640 threads x 96 = 256 x 128 + 256 x 88 + 128 x 48.   ACC32: 512 x 128 = 256 x 192 + 128 x 80 + 128 x 48.
+constexpr int LOADER_WARPS = 3;
 constexpr int TILE_RING = 8;                 // tile_done barriers; FR_CAP / 128 tiles of run-ahead at most
 template <bool ACC16>
 struct F1Roles {
-    static constexpr int UNFOLD_WARPS = ACC16 ? 8 : 4;
-    static constexpr int MMA_WARP = 8 + UNFOLD_WARPS, LOAD_WARP0 = 9 + UNFOLD_WARPS;
-    static constexpr int THREADS = 32 * (12 + UNFOLD_WARPS);
+    static constexpr int UNFOLD_WARPS = ACC16 ? 8 : 4, MMA_WARPS = 1;
+    static constexpr int MMA_WARP0 = 8 + UNFOLD_WARPS, LOAD_WARP0 = MMA_WARP0 + MMA_WARPS;
+    static constexpr int WARPS = LOAD_WARP0 + LOADER_WARPS, THREADS = 32 * WARPS;
     static constexpr int REGS_START = ACC16 ? 96 : 128, REGS_EPI = ACC16 ? 128 : 192, REGS_UNFOLD = ACC16 ? 88 : 80, REGS_LIGHT = 48;
-    static_assert(THREADS * REGS_START == 256 * REGS_EPI + 32 * UNFOLD_WARPS * REGS_UNFOLD + 128 * REGS_LIGHT, "register pool");
+    static_assert(WARPS % 4 == 0 && MMA_WARP0 + MMA_WARPS > WARPS - 4 && (MMA_WARPS == 1 || MMA_WARPS == 3), "whole warpgroups; an issuer in the last");
+    static_assert(THREADS * REGS_START == 256 * REGS_EPI + (THREADS - 384) * REGS_UNFOLD + 128 * REGS_LIGHT, "register pool");
 };
 template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -893,7 +905,7 @@ __device__ __forceinline__ void chunk_from_raw(const uint32_t (&w)[5], uint4 &lo
 template <int C, bool GATHER, bool ACC16>
 __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_kernel(const Conv1Params p, const FusedSrc src) {
     using RL = F1Roles<ACC16>;
-    constexpr int UNFOLD_WARPS = RL::UNFOLD_WARPS, F1_MMA_WARP = RL::MMA_WARP, F1_LOAD_WARP0 = RL::LOAD_WARP0;
+    constexpr int UNFOLD_WARPS = RL::UNFOLD_WARPS, MMA_WARPS = RL::MMA_WARPS, F1_MMA_WARP = RL::MMA_WARP0, F1_LOAD_WARP0 = RL::LOAD_WARP0;
     using S = F1Smem<C, UNFOLD_WARPS>;
     constexpr int CG = C / 8, CH = C / 2;
     constexpr int NP = (F_MAX_DST / 3 + 31) / 32;                               // 32-column parts of a resized row (P1w <= 85)
@@ -963,7 +975,7 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
     if (threadIdx.x == 0) {
         for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], EPI_WARPS); }
         for (int s = 0; s < RAW_SLOTS_MAX; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
-        for (int s = 0; s < TILE_RING; ++s) mbar_init(&tile_done[s], 1);
+        for (int s = 0; s < TILE_RING; ++s) mbar_init(&tile_done[s], MMA_WARPS);
         fence_barrier_init();
     }
     if (warp == F1_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -974,15 +986,17 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
     long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;     // debug stamps of CTA 0 (CUTDET_TIMELINE1)
     if (tl && threadIdx.x == 0) tl[2047] = clock64();
 
+    if (warp < 8) reg_alloc<RL::REGS_EPI>();                     // one instruction per warpgroup (.sync.aligned)
+    else if (warp >= RL::WARPS - 4) reg_dealloc<RL::REGS_LIGHT>();
+    else reg_dealloc<RL::REGS_UNFOLD>();
     if (warp >= F1_MMA_WARP) {
-        reg_dealloc<RL::REGS_LIGHT>();                            // one instruction for the whole warpgroup (.sync.aligned)
-        if (warp > F1_MMA_WARP) {
+        if (warp >= F1_LOAD_WARP0) {
             // ------------------------------------------------------------------ loaders: source rows -> raw ring
             // (the wait on raw_empty is for row n - n_slots to have been read; the slot cannot be a phase further, since that
             // takes row n itself)
             const int lw = warp - F1_LOAD_WARP0, total_rows = n_frames_cta * Hc;
             const int n_loaders = min(LOADER_WARPS, n_slots);
-            if (lw < n_loaders) {                                // (warp 15 only fills the warpgroup)
+            if (lw < n_loaders) {
                 const uint64_t stream_once = l2_policy_evict_first();   // frames are read once: keep the L2 for the activations
                 int fi = 0, y = lw, issued = 0;
                 for (int n = lw; n < total_rows; n += n_loaders, y += n_loaders) {
@@ -1003,20 +1017,26 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
                 }
             }
         } else {
-            // ------------------------------------------------------------------ MMA issuer
+            // ------------------------------------------------------------------ MMA issuers: warp m takes block rows dy % MMA_WARPS == m
+            const int m_warp = warp - F1_MMA_WARP;
+            const bool tl_mma = tl && m_warp == 0 && lane == 0;
             uint32_t acc_phase = 0;
             const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
             const uint32_t idesc = ACC16 ? instr_desc_f16_acc16(128, 3 * C) : instr_desc_16bit(128, 3 * C, kBf16);
+            int r_hi = 127 / P1w, r_rem = 127 % P1w;      // pooled row of the tile's last position, kept without a division per tile
             for (int t = 0; t < n_tiles; ++t) {
                 // rows of sub-rings 1 and 2 up to pooled row (128t + 127) / P1w, of sub-ring 0 one pooled row further
-                const int u_hi = min(total_u - 1, 3 * ((t * 128 + 127) / P1w + 1));
-                const int mine = lane & (UNFOLD_WARPS - 1);
+                const int u_hi = min(total_u - 1, 3 * (r_hi + 1));
+                r_rem += 128;                                 // 64 <= P1w: at most three rows further
+    #pragma unroll
+                for (int k = 0; k < 3; ++k) { const bool c = r_rem >= P1w; r_rem -= c ? P1w : 0; r_hi += c ? 1 : 0; }
+                const int mine = lane % UNFOLD_WARPS;
                 const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
-                if (tl && lane == 0 && t < 60) tl[1800 + 4 * t + 3] = clock64();
+                if (tl_mma && t < 60) tl[1800 + 4 * t + 3] = clock64();
                 while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(32);
                 __syncwarp();
                 tc_fence_after_sync();
-                if (tl && lane == 0 && t < 64) tl[1024 + t] = clock64();
+                if (tl_mma && t < 64) tl[1024 + t] = clock64();
                 uint32_t a_chunk[5];
     #pragma unroll
                 for (int c = 0; c < 5; ++c) {
@@ -1025,9 +1045,10 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
                 }
     #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
+                    if (MMA_WARPS > 1 && dy != m_warp) continue;
                     mbar_wait(&acc_empty[dy], acc_phase ^ 1);
                     tc_fence_after_sync();
-                    if (tl && lane == 0 && t < 60) tl[1800 + 4 * t + dy] = clock64();
+                    if (tl_mma && t < 60) tl[1800 + 4 * t + dy] = clock64();
                     if (elect_one()) {
     #pragma unroll
                         for (int ks = 0; ks < 3; ++ks) {
@@ -1036,17 +1057,17 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
                             umma_16bit(tmem_base + 3 * C * dy, da, db, idesc, ks > 0 ? 1u : 0u);
                         }
                         umma_commit(&acc_full[dy]);
-                        if (dy == 2) umma_commit(&tile_done[t & (TILE_RING - 1)]);   // tile t no longer reads the operand ring
+                        // tile t no longer reads the operand ring once every issuer's MMAs of it have completed
+                        if (MMA_WARPS > 1 || dy == 2) umma_commit(&tile_done[t & (TILE_RING - 1)]);
                     }
                     __syncwarp();
                 }
-                if (tl && lane == 0 && t < 64) tl[1088 + t] = clock64();
+                if (tl_mma && t < 64) tl[1088 + t] = clock64();
                 acc_phase ^= 1;
             }
         }
     } else if (warp >= 8 && warp < 8 + UNFOLD_WARPS) {
         // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
-        reg_dealloc<RL::REGS_UNFOLD>();
         const int pwarp = warp - 8;
         const int n_loaders = min(LOADER_WARPS, n_slots);
         // fast path constants: tap j of pooled column px starts at byte 3*off_x + BS*(3px - 1 + j), BS = 3*step_x; a part is
@@ -1161,7 +1182,6 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
         }
     } else {
         // ------------------------------------------------------------------ epilogue
-        reg_alloc<RL::REGS_EPI>();
         const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
         const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + half * 3 * CH;   // columns [dy][half][dx][CH]
         uint32_t acc_phase = 0;
@@ -1176,28 +1196,45 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
             if constexpr (ACC16) epi_issue_row16<C>(tmem_thread, 0, bufA);
             else epi_issue_row<C>(tmem_thread, 0, bufA);
         }
-        auto tile = [&](int t, Row &cur, Row &nxt) {
-            const bool valid = fi < n_frames_cta && Y < p.P1h;
-            if constexpr (ACC16) {
-                uint32_t v[CH / 2];
-                epilogue_tile_pipelined16<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v,
-                                             (tl && threadIdx.x == 0 && t < 64) ? tl + 1216 + 8 * t : nullptr);
-                epilogue_scale_shift16<C>(reinterpret_cast<const uint32_t *>(s_par), ch0, v);
-                if (valid) store_pixel16<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
-            } else {
-                float v[CH];
-                epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v);
-                epilogue_scale_shift<C>(s_par, ch0, v);
-                if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
-            }
-            if (tl && threadIdx.x == 0 && t < 64) tl[1152 + t] = clock64();
-            acc_phase ^= 1;
+        auto advance = [&]() {
             // next tile: 128 positions on.  64 <= P1w (fused_source), so at most three rows further; branch-free, the lanes differ
             X += 128;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { const bool c = X >= P1w; X -= c ? P1w : 0; Y += c ? 1 : 0; }
 #pragma unroll
             for (int k = 0; k < 3; ++k) { const bool c = Y >= RPF; Y -= c ? RPF : 0; fi += c ? 1 : 0; }
+        };
+        auto tile = [&](int t, Row &cur, Row &nxt) {
+            const bool valid = fi < n_frames_cta && Y < p.P1h;
+            if constexpr (ACC16) {
+                // (a table of store offsets by position inside the frame, fetched a tile ahead, was tried instead of this
+                // div/mod chain: no gain)
+                uint4 *dst = store_addr16<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0);
+                advance();
+                uint32_t v[CH / 2];
+                bool requested = epilogue_tile_pipelined16<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v,
+                                                              (tl && threadIdx.x == 0 && t < 64) ? tl + 1216 + 8 * t : nullptr);
+                epilogue_scale_shift16<C>(reinterpret_cast<const uint32_t *>(s_par), ch0, v);
+                if (!requested && mbar_test_wait(&acc_full[0], acc_phase ^ 1)) {      // second chance: the load flies behind the store
+                    tc_fence_after_sync();
+                    epi_issue_row16<C>(tmem_thread, 0, nxt);
+                    requested = true;
+                }
+                if (valid) store_pixel16<C>(dst, p.out.gtot, v);
+                if (!requested) {
+                    mbar_wait(&acc_full[0], acc_phase ^ 1);
+                    tc_fence_after_sync();
+                    epi_issue_row16<C>(tmem_thread, 0, nxt);
+                }
+            } else {
+                float v[CH];
+                epilogue_tile_pipelined<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v);
+                epilogue_scale_shift<C>(s_par, ch0, v);
+                if (valid) store_pixel<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, ch0, v);
+                advance();
+            }
+            if (tl && threadIdx.x == 0 && t < 64) tl[1152 + t] = clock64();
+            acc_phase ^= 1;
         };
         for (int t = 0; t < n_tiles; t += 2) {          // the two buffers swap roles from one tile to the next
             tile(t, bufA, bufB);
