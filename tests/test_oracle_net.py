@@ -70,6 +70,25 @@ def test_f64_restatement_agrees(prod_weights, kat):
     assert feats[0].shape == (6, 48, 48, 85) and feats[1].shape == (6, 48, 16, 28) and feats[2].shape == (6, 48, 5, 9)
 
 
+def test_16bit_emulations_stay_within_the_stated_tolerance(prod_weights, kat):
+    """The two CPU restatements of what the tensor-core kernels compute (fp32 accumulators everywhere / fp16 accumulators in
+    layer 1 of the fused frames kernel, oracle.net._conv1_acc16) against the logits recorded from the reference: both must sit
+    well inside the 0.05 the GPU tests allow (tests/test_gpu_net.py), with labels unchanged where the margin is >= 0.1."""
+    w, params = prod_weights
+    frames = kat_inputs.kat_frames()
+    x = np.stack([opre.preprocess_frame(f) for f in frames.values()])
+    ref = np.stack([kat["frame_" + n] for n in frames])
+    for acc16 in (False, True):
+        got = onet.forward_tc_emulated(w, x, params["avg_pool_size"], conv1_acc16=acc16)
+        assert np.abs(got - ref).max() <= 0.02, acc16
+        srt = np.sort(ref, axis=1)
+        ok = (srt[:, -1] - srt[:, -2]) >= 0.1
+        assert np.array_equal(got.argmax(1)[ok], ref.argmax(1)[ok])
+    # the fp16-accumulator variant cannot overflow: per-channel scaling bounds every partial sum by 27 * 2^15 * 255 * 2^-24
+    white = np.ones((1, 3, 144, 256), np.float32)
+    assert np.isfinite(onet.forward_tc_emulated(w, white, params["avg_pool_size"], conv1_acc16=True)).all()
+
+
 def test_adaptive_windows():
     assert onet.adaptive_windows(5, 4) == [(0, 2), (1, 3), (2, 4), (3, 5)]
     assert onet.adaptive_windows(9, 4) == [(0, 3), (2, 5), (4, 7), (6, 9)]
