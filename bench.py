@@ -178,7 +178,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- native arm
@@ -415,14 +415,28 @@ def run_native(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "kernels": table, "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _emit(line: dict) -> None:
+    """The ONE JSON line, on the process's original stdout."""
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
+
+
 def main():
+    # Libraries write to file descriptor 1 behind Python's back (NCCL prints its version banner there when NCCL_DEBUG is set):
+    # keep a private handle on the real stdout for the JSON line and point descriptor 1 at stderr for everything else.
+    global _JSON_OUT
     args = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
