@@ -488,6 +488,10 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch (launch_mid): everything above ran while the kernel before this one was still draining; from
+    // here on its output is read and buffers it may still be reading are written.
+    grid_dep_launch();
+    grid_dep_wait();
 
     if (warp == 8) {
         // ------------------------------------------------------------------ TMA producer (lane 0 issues)
@@ -985,6 +989,10 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
     const uint32_t tmem_base = *tmem_slot;
     long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;     // debug stamps of CTA 0 (CUTDET_TIMELINE1)
     if (tl && threadIdx.x == 0) tl[2047] = clock64();
+    // Programmatic dependent launch (launch_conv1_fused): the kernel before this one -- conv2 of the previous sub-batch -- may
+    // still be READING the activation buffer this kernel writes.  Loaders, unfold and MMAs do not touch it and start at once;
+    // the epilogue warps wait for that kernel to complete before their first store.  The next kernel may be scheduled now.
+    grid_dep_launch();
 
     if (warp < 8) reg_alloc<RL::REGS_EPI>();                     // one instruction per warpgroup (.sync.aligned)
     else if (warp >= RL::WARPS - 4) reg_dealloc<RL::REGS_LIGHT>();
@@ -1185,6 +1193,7 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
         const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
         const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + half * 3 * CH;   // columns [dy][half][dx][CH]
         uint32_t acc_phase = 0;
+        grid_dep_wait();
         for (int fi = 0; fi < n_frames_cta; ++fi) zero_pads(p.out, CG, blockIdx.x + fi * gridDim.x, blockIdx.x + fi * gridDim.x + 1, threadIdx.x, EPI_WARPS * 32);
         int X = m % P1w, Y = m / P1w, fi = 0;              // position 128 t + m = ((fi * RPF + Y) * P1w + X), advanced tile by tile
         while (Y >= RPF) { Y -= RPF; ++fi; }
@@ -1623,6 +1632,26 @@ int set_smem_limits() {
     return CUTDET_OK;
 }
 
+// Launch with programmatic stream serialization: the kernel may start while the one before it in the stream drains (see
+// grid_dep_launch / grid_dep_wait in tc_common.cuh; every kernel launched this way orders its dependent accesses itself).
+// Grids are at most one CTA per SM, so a waiting successor can never keep a predecessor's CTA from being scheduled.
+// CUTDET_NO_PDL=1 falls back to ordinary launches.
+template <typename... KArgs, typename... Args>
+void launch_pdl(bool pdl, void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t stream, Args &&...args) {
+    static const bool off = getenv("CUTDET_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (off || !pdl) ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <int C>
 int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
     const int grid = p.B < sm_count() ? p.B : sm_count();
@@ -1635,7 +1664,7 @@ int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
 }
 
 template <int C>
-int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream) {
+int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream, bool pdl) {
     // CUTDET_CONV1_GRID caps the grid (test hook: several frames per CTA, as on a part with fewer SMs than a sub-batch has frames)
     static const int grid_cap = [] { const char *e = getenv("CUTDET_CONV1_GRID"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 1 << 30; }();
     const int grid = std::min(std::min(p.B, sm_count()), grid_cap);
@@ -1670,10 +1699,12 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_
         KernelScope scope("conv1_fused_tc", stream);
         // fast path: integer-scale gather whose last pooled column has its right neighbour inside the image (dst_w % 3 != 0)
         const bool gather = src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0;
-        if (gather && acc16) conv1_fused_tc_kernel<C, true, true><<<grid, thr16, smem16, stream>>>(p, src);
-        else if (gather) conv1_fused_tc_kernel<C, true, false><<<grid, thr32, smem32, stream>>>(p, src);
-        else if (acc16) conv1_fused_tc_kernel<C, false, true><<<grid, thr16, smem16, stream>>>(p, src);
-        else conv1_fused_tc_kernel<C, false, false><<<grid, thr32, smem32, stream>>>(p, src);
+        // pdl: only when the kernel before this one is one of ours (conv2/conv3 of the previous sub-batch): the loaders read the
+        // frames without waiting for it, so it must not be what produced them
+        if (gather && acc16) launch_pdl(pdl, conv1_fused_tc_kernel<C, true, true>, grid, thr16, smem16, stream, p, src);
+        else if (gather) launch_pdl(pdl, conv1_fused_tc_kernel<C, true, false>, grid, thr32, smem32, stream, p, src);
+        else if (acc16) launch_pdl(pdl, conv1_fused_tc_kernel<C, false, true>, grid, thr16, smem16, stream, p, src);
+        else launch_pdl(pdl, conv1_fused_tc_kernel<C, false, false>, grid, thr32, smem32, stream, p, src);
     }
     CUTDET_LAUNCH_CHECK("conv1_fused_tc_kernel");
     return CUTDET_OK;
@@ -1708,7 +1739,7 @@ int launch_mid(const CUtensorMap &map, const MidParams &p, const char *name, cud
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
     {
         KernelScope scope(name, stream);
-        conv_mid_tc_kernel<C><<<grid, 320, MidSmem<C>::total, stream>>>(map, p);
+        launch_pdl(true, conv_mid_tc_kernel<C>, grid, 320, MidSmem<C>::total, stream, map, p);
     }
     CUTDET_LAUNCH_CHECK("conv_mid_tc_kernel");
     return CUTDET_OK;
@@ -1769,14 +1800,14 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
             CUTDET_CUDA(cudaMalloc(&d, 2048 * 8));
             CUTDET_CUDA(cudaMemsetAsync(d, 0, 2048 * 8, stream));
             c1.timeline = d;
-            if (int rc = launch_conv1_fused<C>(c1, fs, stream)) return rc;
+            if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0)) return rc;
             CUTDET_CUDA(cudaMemcpyAsync(h.data(), d, 2048 * 8, cudaMemcpyDeviceToHost, stream));
             CUTDET_CUDA(cudaStreamSynchronize(stream));
             FILE *f = fopen(getenv("CUTDET_TIMELINE1"), "w");
             if (f) { for (int i = 0; i < 2048; ++i) fprintf(f, "%lld\n", h[i] ? h[i] - h[2047] : -1LL); fclose(f); }
             cudaFree(d);
             c1.timeline = nullptr;
-        } else if (int rc = launch_conv1_fused<C>(c1, fs, stream)) return rc;
+        } else if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0)) return rc;
     } else if (int rc = launch_conv1<C>(c1, stream)) return rc;
 
     MidParams p2 = mid_params(nb, g.FP1, g.PW1, g.P2h, g.P2w);

@@ -79,6 +79,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // Named barrier among `count` threads (a multiple of 32) of the CTA; id 0 is __syncthreads.
 __device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+// ---------------------------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start once every CTA of the kernel before it in
+// the stream has executed launch_dependents (or exited): its CTAs take the SMs as they come free and run their set-up, and
+// grid_dep_wait() then blocks until that earlier kernel has COMPLETED and its writes are visible.  Both are no-ops in a kernel
+// launched the ordinary way.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
