@@ -229,3 +229,35 @@ def test_fused_kernel_with_several_frames_per_cta():
     env = dict(os.environ, CUTDET_CONV1_GRID="37")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_dependent_launch_changes_nothing():
+    """conv1/conv2/conv3 are launched with programmatic stream serialization (csrc/conv_tc.cu launch_pdl): a kernel's set-up runs
+    while the previous one drains and griddepcontrol.wait orders the dependent accesses.  The logits must be bit-identical to
+    those of ordinary launches (CUTDET_NO_PDL=1, a fresh process), over several sub-batches and repeated calls."""
+    import subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys, hashlib, numpy as np, torch
+        sys.path[:0] = [%r, %r]
+        from cutdet import engine
+        from frameID.net import load_default_net
+        net, _ = load_default_net()
+        net.eval().to("cuda")
+        h = hashlib.sha256()
+        for (hh, ww, batch) in ((720, 1280, 700), (1080, 1920, 310), (360, 640, 450)):
+            rng = np.random.default_rng(hh + batch)
+            frames = torch.from_numpy(rng.integers(0, 256, (batch, hh, ww, 3), dtype=np.uint8)).cuda()
+            plan = engine.ResizePlan.for_video(hh, ww, 256)
+            for _ in range(3):
+                h.update(net.forward_frames(plan, frames).cpu().numpy().tobytes())
+        print("DIGEST", h.hexdigest())
+    """) % (root, os.path.join(root, "cut-detection_b200"))
+    digests = []
+    for extra in ({}, {"CUTDET_NO_PDL": "1"}):
+        env = dict(os.environ, **extra)
+        env.pop("CUTDET_NO_PDL", None) if not extra else None
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        digests.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert digests[0] == digests[1]
