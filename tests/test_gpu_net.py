@@ -151,6 +151,32 @@ def test_contrastive_encoder_architecture():
     assert got.shape == (8, 8) and np.abs(got - want).max() <= tol
 
 
+def test_frames_path_with_32_channels():
+    """The fused frames kernel has a 32-channel instantiation (the contrastive encoder's width) with its own TMEM load shapes:
+    decoded frames -> logits against the fp32 oracle and against the CPU emulation of the kernel's arithmetic."""
+    from cutdet import engine
+    wts = onet.random_weights(seed=5, hidden_channels=32, conv_layers=3, avg_pool_size=1, linear_layers=3,
+                              linear_size=32, output_size=8)
+    net = engine.NativeNet(wts, 1)
+    assert net.uses_tensor_cores(144, 256)
+    rng = np.random.default_rng(11)
+    for h, w, batch in ((720, 1280, 5), (1080, 1920, 3), (360, 640, 150)):
+        frames = rng.integers(0, 256, (batch, h, w, 3), dtype=np.uint8)
+        frames[0, : h // 3] = 255
+        frames[-1, :, : w // 2] = 0
+        plan = engine.ResizePlan.for_video(h, w, 256)
+        got = net.forward_frames(plan, torch.from_numpy(frames).cuda()).cpu().numpy()
+        x = np.stack([opre.preprocess_frame(f) for f in frames[:4]])
+        want = onet.forward_f32(wts, x, 1)
+        emu = onet.forward_tc_emulated(wts, x, 1, conv1_acc16="CUTDET_CONV1_ACC32" not in os.environ)
+        assert got.shape == (batch, 8)
+        assert np.abs(got[:4] - want).max() <= TOL_TC, (h, np.abs(got[:4] - want).max())
+        assert np.abs(got[:4] - emu).max() <= TOL_EMU, (h, np.abs(got[:4] - emu).max())
+        # the same frames through the unfused float entry
+        ref = net.forward_f32(engine.preprocess_f32(plan, torch.from_numpy(frames).cuda())).cpu().numpy()
+        assert np.abs(got - ref).max() <= FUSED_TOL
+
+
 def test_conv_only_and_fc_only(prod_weights):
     from cutdet import engine
     wts, params = prod_weights
