@@ -1433,52 +1433,60 @@ __global__ void __launch_bounds__(256) bn_ps_apply_kernel(uint4 *__restrict__ ac
 
 // ------------------------------------------------------------------------------------------------ head, first FC
 // AdaptiveAvgPool2d + flatten + Linear folded into one [n_feat x 32] matrix (the pool is linear), then ReLU and the
-// BatchNorm1d affine: out[f][o] = act(sum_k act3[f][k] * W[k][o] + bias[o]).  A block takes 16 frames; its two halves
+// BatchNorm1d affine: out[f][o] = act(sum_k act3[f][k] * W[k][o] + bias[o]).  A block takes 16 frames; its HEAD_KG groups
 // (64 threads each) walk alternate k slabs of HEAD_KT staged through shared memory (activations read coalesced along k
-// and stored transposed, so that two frames are one 64-bit load); thread (fy, ox) of a half accumulates a 2 frame x
-// 4 output register tile; the halves are summed through shared memory at the end.
-constexpr int HEAD_FRAMES = 16, HEAD_KT = 96, HEAD_PITCH = HEAD_FRAMES + 4;
+// and stored transposed, so that two frames are one 64-bit load); thread (fy, ox) of a group accumulates a 2 frame x
+// 4 output register tile; the groups are summed through shared memory at the end.  A block's time is the chain of its
+// groups' slabs (global-load latency + the slab's FMAs), not bandwidth: hence four short chains instead of two, and the next
+// slab's loads are in flight in registers while the current one is consumed.
+constexpr int HEAD_FRAMES = 16, HEAD_KT = 48, HEAD_KG = 4, HEAD_THREADS = 64 * HEAD_KG, HEAD_PITCH = HEAD_FRAMES + 4;
 
-__global__ void __launch_bounds__(128) head_fc1_kernel(const float *__restrict__ act3, const float *__restrict__ w_folded,
-                                                       const float *__restrict__ bias, const float *__restrict__ scale,
-                                                       const float *__restrict__ shift, int batch, int n_feat, int hidden,
-                                                       int relu, float *__restrict__ out) {
-    __shared__ __align__(16) float s_a[2][HEAD_KT * HEAD_PITCH];    // [half][k][frame]
-    __shared__ __align__(16) float s_w[2][HEAD_KT * 32];            // [half][k][out]
-    const int half = threadIdx.x >> 6, tid = threadIdx.x & 63, fy = tid >> 3, ox = tid & 7;   // frames 2*fy.., outputs 4*ox..
+__global__ void __launch_bounds__(HEAD_THREADS) head_fc1_kernel(const float *__restrict__ act3, const float *__restrict__ w_folded,
+                                                                const float *__restrict__ bias, const float *__restrict__ scale,
+                                                                const float *__restrict__ shift, int batch, int n_feat, int hidden,
+                                                                int relu, float *__restrict__ out) {
+    __shared__ __align__(16) float s_a[HEAD_KG][HEAD_KT * HEAD_PITCH];    // [group][k][frame]
+    __shared__ __align__(16) float s_w[HEAD_KG][HEAD_KT * 32];            // [group][k][out]
+    static_assert((HEAD_KG - 1) * 64 * 8 <= HEAD_KG * HEAD_KT * 32, "the partial sums reuse s_w");
+    const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63, fy = tid >> 3, ox = tid & 7;   // frames 2*fy.., outputs 4*ox..
     const int f0 = blockIdx.x * HEAD_FRAMES;
-    float *sa = s_a[half], *sw = s_w[half];
+    float *sa = s_a[grp], *sw = s_w[grp];
     float acc[2][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = half * HEAD_KT; k0 < n_feat; k0 += 2 * HEAD_KT) {
+    constexpr int NA = HEAD_FRAMES * HEAD_KT / 64, NW = HEAD_KT * 8 / 64;
+    static_assert(NA * 64 == HEAD_FRAMES * HEAD_KT && NW * 64 == HEAD_KT * 8, "a slab is a whole number of loads per thread");
+    float ta[NA];
+    float4 tw[NW];
+    // all the global loads of a slab (they are independent) into registers
+    auto fetch = [&](int k0) {
         const int kn = min(HEAD_KT, n_feat - k0);
-        bar_sync_named(1 + half, 64);                 // the previous slab has been consumed
-        {   // all the global loads of the slab first (they are independent), then the shared-memory stores
-            constexpr int NA = HEAD_FRAMES * HEAD_KT / 64, NW = HEAD_KT * 8 / 64;
-            float ta[NA];
-            float4 tw[NW];
 #pragma unroll
-            for (int j = 0; j < NA; ++j) {
-                const int i = tid + 64 * j, f = i / HEAD_KT, k = i % HEAD_KT;          // coalesced along k
-                ta[j] = (f0 + f < batch && k < kn) ? __ldg(&act3[(size_t)(f0 + f) * n_feat + k0 + k]) : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < NW; ++j) {
-                const int i = tid + 64 * j, k = i >> 3;
-                tw[j] = k < kn ? __ldg(&reinterpret_cast<const float4 *>(w_folded)[(size_t)(k0 + k) * 8 + (i & 7)]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < NA; ++j) {
-                const int i = tid + 64 * j;
-                sa[(i % HEAD_KT) * HEAD_PITCH + i / HEAD_KT] = ta[j];
-            }
-#pragma unroll
-            for (int j = 0; j < NW; ++j) reinterpret_cast<float4 *>(sw)[tid + 64 * j] = tw[j];
+        for (int j = 0; j < NA; ++j) {
+            const int i = tid + 64 * j, f = i / HEAD_KT, k = i % HEAD_KT;          // coalesced along k
+            ta[j] = (f0 + f < batch && k < kn) ? __ldg(&act3[(size_t)(f0 + f) * n_feat + k0 + k]) : 0.f;
         }
-        bar_sync_named(1 + half, 64);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            const int i = tid + 64 * j, k = i >> 3;
+            tw[j] = k < kn ? __ldg(&reinterpret_cast<const float4 *>(w_folded)[(size_t)(k0 + k) * 8 + (i & 7)]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    int k0 = grp * HEAD_KT;
+    if (k0 < n_feat) fetch(k0);
+    for (; k0 < n_feat; k0 += HEAD_KG * HEAD_KT) {
+        bar_sync_named(1 + grp, 64);                  // the previous slab has been consumed
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const int i = tid + 64 * j;
+            sa[(i % HEAD_KT) * HEAD_PITCH + i / HEAD_KT] = ta[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NW; ++j) reinterpret_cast<float4 *>(sw)[tid + 64 * j] = tw[j];
+        bar_sync_named(1 + grp, 64);
+        if (k0 + HEAD_KG * HEAD_KT < n_feat) fetch(k0 + HEAD_KG * HEAD_KT);      // in flight while this slab is consumed
 #pragma unroll 8
         for (int k = 0; k < HEAD_KT; ++k) {
             const float2 a = *reinterpret_cast<const float2 *>(&sa[k * HEAD_PITCH + 2 * fy]);
@@ -1490,15 +1498,15 @@ __global__ void __launch_bounds__(128) head_fc1_kernel(const float *__restrict__
         }
     }
     __syncthreads();
-    float *red = s_w[0];                              // [64 threads][8]
-    if (half == 1) {
+    float *red = s_w[0];                              // [group - 1][64 threads][8]
+    if (grp > 0) {
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) red[tid * 8 + i * 4 + j] = acc[i][j];
+            for (int j = 0; j < 4; ++j) red[((grp - 1) * 64 + tid) * 8 + i * 4 + j] = acc[i][j];
     }
     __syncthreads();
-    if (half == 0) {
+    if (grp == 0) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int f = f0 + 2 * fy + i;
@@ -1507,7 +1515,10 @@ __global__ void __launch_bounds__(128) head_fc1_kernel(const float *__restrict__
             for (int j = 0; j < 4; ++j) {
                 const int o = 4 * ox + j;
                 if (o >= hidden) continue;
-                float v = acc[i][j] + red[tid * 8 + i * 4 + j] + bias[o];
+                float v = acc[i][j];
+#pragma unroll
+                for (int g = 0; g < HEAD_KG - 1; ++g) v += red[(g * 64 + tid) * 8 + i * 4 + j];
+                v += bias[o];
                 if (relu) v = fmaxf(v, 0.f);
                 if (scale) v = fmaf(v, scale[o], shift[o]);
                 out[(size_t)f * hidden + o] = v;
@@ -1901,7 +1912,7 @@ int run_head(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int
     if (net->cfg.n_fc_layers == 0) {
         // a bare FrameConvNet: the pooled features [B, C*P*P] in (c, i, j) order ARE the output (avg-pool as a matrix, no bias)
         KernelScope scope("head_fc1", stream);
-        head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, 128, 0, stream>>>(
+        head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, HEAD_THREADS, 0, stream>>>(
             cur, folded, net->tc->d_zero32, nullptr, nullptr, batch, n_feat, g.C * net->cfg.avg_pool_size * net->cfg.avg_pool_size, 0, logits);
         CUTDET_LAUNCH_CHECK("head_fc1_kernel");
         return CUTDET_OK;
@@ -1911,7 +1922,7 @@ int run_head(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int
     float *out0 = last0 ? logits : reinterpret_cast<float *>(ws + w.fc[0]);
     {
         KernelScope scope("head_fc1", stream);
-        head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, 128, 0, stream>>>(
+        head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, HEAD_THREADS, 0, stream>>>(
             cur, folded, L0.d_bias, L0.has_bn ? L0.d_scale : nullptr, L0.has_bn ? L0.d_shift : nullptr, batch, n_feat, L0.out,
             last0 ? 0 : 1, out0);
     }
@@ -2213,7 +2224,7 @@ int run_batchstats(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *w
     if (int rc = folded_fc1(net, g, &folded)) return rc;
     if (net->cfg.n_fc_layers == 0) {
         KernelScope scope("head_fc1", stream);
-        head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, 128, 0, stream>>>(
+        head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, HEAD_THREADS, 0, stream>>>(
             cur, folded, tc->d_zero32, nullptr, nullptr, batch, n_feat, g.C * net->cfg.avg_pool_size * net->cfg.avg_pool_size, 0, out);
         CUTDET_LAUNCH_CHECK("head_fc1_kernel");
         return CUTDET_OK;
@@ -2224,7 +2235,7 @@ int run_batchstats(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *w
         float *o = is_last ? out : reinterpret_cast<float *>(ws + w.fc[j & 1]);
         if (j == 0) {
             KernelScope scope("head_fc1", stream);
-            head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, 128, 0, stream>>>(cur, folded, L.d_bias, nullptr, nullptr, batch, n_feat, L.out,
+            head_fc1_kernel<<<(batch + HEAD_FRAMES - 1) / HEAD_FRAMES, HEAD_THREADS, 0, stream>>>(cur, folded, L.d_bias, nullptr, nullptr, batch, n_feat, L.out,
                                                                                         is_last ? 0 : 1, o);
             CUTDET_LAUNCH_CHECK("head_fc1_kernel");
         } else if (int rc = launch_fc(cur, o, L, batch, !is_last, stream, false)) {
