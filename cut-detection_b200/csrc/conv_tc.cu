@@ -69,8 +69,14 @@ constexpr float kW1Scale = kBf16 ? 1.f / 255.f : 256.f / 255.f; // ... and its w
 // two floats -> packed 16-bit operands; fp16 saturates to +-65504 in the conversion itself (F2FP.SATFINITE)
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) { return kBf16 ? pack_bf16x2(lo, hi) : pack_f16x2_sat(lo, hi); }
 
-constexpr int SUB_BATCH = 148;          // frames per pass through conv1/conv2: their activations stay L2-resident
-constexpr int GROUP = 8;                // sub-batches whose layer-2 maps are gathered for ONE conv3 launch (fills the SMs)
+// Frames per pass through conv1/conv2: one frame per conv1 CTA on 148 SMs, and the layer-1 activations of a pass (59 MB) stay
+// L2-resident until conv2 reads them.  Two frames per CTA (296) pay a CTA's set-up, pipeline fill and drain once per two frames,
+// but programmatic dependent launch already hides most of that and the 118 MB of activations go through HBM: measured on one
+// box, 80-step runs 2.132 / 2.136 M frames/s (148 / 296), 30-step runs 2.21 / 2.25 M (profiles/README.md, v9).  CUTDET_SUB_BATCH
+// overrides it for such experiments.
+constexpr int SUB_BATCH = 148;
+constexpr int BATCHSTATS_MAX = 148;     // training-mode BatchNorm on the tensor-core path: one frame per CTA, everything resident
+constexpr int GROUP_FRAMES = 1184;      // frames whose layer-2 maps are gathered for ONE conv3 launch (fills the SMs)
 constexpr int TMEM_COLS = 512;
 constexpr int MID_STAGES = 3;
 constexpr int MID_WIN = 192;            // positions per (plane, channel group) in a stage: 32 halo + 128 + 32 halo
@@ -1594,8 +1600,11 @@ struct TcWorkspace {
 
 TcWorkspace tc_workspace(const cutdet_net *net, const Geom &g, int batch) {
     TcWorkspace w;
-    w.sub = batch < SUB_BATCH ? batch : SUB_BATCH;
-    w.group_frames = batch < GROUP * SUB_BATCH ? batch : GROUP * SUB_BATCH;
+    static const int sub_batch = [] { const char *e = getenv("CUTDET_SUB_BATCH"); const int v = e ? atoi(e) : 0; return v > 0 ? v : SUB_BATCH; }();
+    static const int group_frames = [] { const char *e = getenv("CUTDET_GROUP_FRAMES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : GROUP_FRAMES; }();
+    const int group_cap = std::max(group_frames, sub_batch);
+    w.sub = batch < sub_batch ? batch : sub_batch;
+    w.group_frames = batch < group_cap ? batch : group_cap;
     w.gtot1 = gtot_for(w.sub, g.FP1);
     w.gtot2 = gtot_for(w.group_frames, g.FP2);
     size_t off = 0;
@@ -2249,7 +2258,7 @@ int run_batchstats(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *w
 }
 
 bool tc_batchstats_supported(const cutdet_net *net, int batch, int height, int width) {
-    return tc_supported(net, height, width) && batch <= SUB_BATCH;
+    return tc_supported(net, height, width) && batch <= BATCHSTATS_MAX;
 }
 
 int tc_forward_f32_batchstats(cutdet_net *net, const float *x, int batch, int height, int width, float *out, char *ws, cudaStream_t stream) {
@@ -2285,7 +2294,7 @@ int tc_debug_conv_output(cutdet_net *net, int layer, int batch, int height, int 
     const Geom g = make_geom(height, width, net->cfg.hidden_channels);
     const TcWorkspace w = tc_workspace(net, g, batch);
     if (batch > w.sub && layer < 2)
-        return fail(CUTDET_EUNSUPPORTED, "debug_conv_output: layers 0 and 1 are only kept for batches of up to %d frames", SUB_BATCH);
+        return fail(CUTDET_EUNSUPPORTED, "debug_conv_output: layers 0 and 1 are only kept for batches of up to %d frames", w.sub);
     if (layer == 2) {
         const int64_t total = (int64_t)batch * g.C * g.P3h * g.P3w;
         unpack_plain_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(reinterpret_cast<const float *>(ws + w.act3), batch, g.C,

@@ -13,6 +13,9 @@ for key, short in names.items():
     sel = [r for r in rows[2:] if key in r[0]]
     if not sel:
         continue
+    # full sub-batches only: a chunk's last, partial sub-batch and (for conv_mid) the conv3 launches read far less
+    most = max(float(r[col["dram__bytes_read.sum"]]) for r in sel)
+    sel = [r for r in sel if float(r[col["dram__bytes_read.sum"]]) >= 0.9 * most]
     f = lambda c: sum(float(r[col[c]]) for r in sel) / len(sel)
     out[short] = {
         "dram_bytes_per_launch": (f("dram__bytes_read.sum") + f("dram__bytes_write.sum")) * 1e6,
@@ -22,7 +25,7 @@ for key, short in names.items():
         "avg_duration_us_under_ncu": f("gpu__time_duration.sum"),
         "tensor_pipe_active_pct": f("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
         "dram_throughput_pct": f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
-        "source": f"{src} (ncu --set full --clock-control none, 148-frame sub-batch launches; ncu flushes the L2 between kernels)",
+        "source": f"{src} (ncu --set full --clock-control none, full sub-batch launches only; ncu flushes the L2 between kernels)",
     }
 # bench.py's kernel table names conv2/conv3 separately; both are conv_mid_tc_kernel
 if "conv_mid_tc" in out:

@@ -201,7 +201,7 @@ def test_bad_inputs(native):
 
 
 @pytest.mark.parametrize("h,w,batch,compact", [
-    (720, 1280, 5, False), (720, 1280, 150, True), (720, 1280, 301, False),     # integer-scale gather, > 1 frame per CTA, > 1 sub-batch
+    (720, 1280, 5, False), (720, 1280, 150, True), (720, 1280, 301, False),     # integer-scale gather, > 1 sub-batch (148 frames)
     (1080, 1920, 21, False), (1080, 1920, 9, True),                             # fixed-point bilinear, two source rows per output row
     (360, 640, 33, False),                                                       # scale 2.5
     (288, 512, 7, False),                                                        # exact 2x2 box mean
