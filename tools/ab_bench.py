@@ -1,0 +1,62 @@
+#!/usr/bin/env python3
+"""Same-box A/B of bench.py under different environment switches (one gpurun call).
+
+Boxes differ by several per cent and the default 80-step run is power-capped (profiles/README.md, v9), so two variants are only
+comparable when they are measured on ONE box, interleaved, a few times each:
+
+    python tools/ab_bench.py --reps 2 --steps 30,80 -- "" "CUTDET_SUB_BATCH=296" "CUTDET_NO_PDL=1"
+
+Each variant is a space-separated list of NAME=VALUE pairs ("" = the defaults).  Prints one line per run and a summary table
+(mean / min / max frames per second per variant and step count); with --out also writes them to a text file for profiles/."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--steps", default="80", help="comma-separated step counts")
+    ap.add_argument("--timeout", type=int, default=120, help="seconds per bench run")
+    ap.add_argument("--out", default=None)
+    ap.add_argument("variants", nargs="+")
+    a = ap.parse_args()
+    steps = [int(s) for s in a.steps.split(",")]
+    results = {}
+    lines = []
+    for rep in range(a.reps):
+        for v in a.variants:                                     # interleaved: drift over the call hits every variant alike
+            for st in steps:
+                env = dict(os.environ)
+                for kv in v.split():
+                    k, _, val = kv.partition("=")
+                    env[k] = val
+                cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(st), "--no-e2e", "--no-cpu-baseline"]
+                try:
+                    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=a.timeout)
+                    d = json.loads(r.stdout.strip().splitlines()[-1])
+                    ok = bool(d.get("parity", {}).get("timed_job_runs_equal_plan"))
+                    line = f"AB rep={rep} variant='{v}' steps={st} frames_per_s={d['value']:.0f} ms_per_step={d['ms_per_step']:.4f} parity={ok} clocks={d.get('clocks')}"
+                    if ok:
+                        results.setdefault((v, st), []).append(d["value"])
+                except Exception as e:                            # a failed variant must not cost the others their measurement
+                    line = f"AB rep={rep} variant='{v}' steps={st} FAILED: {type(e).__name__}: {e}"
+                print(line, flush=True)
+                lines.append(line)
+    lines.append("")
+    lines.append(f"{'variant':40s} {'steps':>5s} {'mean':>10s} {'min':>10s} {'max':>10s}  n")
+    for (v, st), vals in results.items():
+        lines.append(f"{(v or '(defaults)'):40s} {st:5d} {statistics.mean(vals):10.0f} {min(vals):10.0f} {max(vals):10.0f}  {len(vals)}")
+    print("\n".join(lines[-(len(results) + 1):]))
+    if a.out:
+        with open(a.out, "w") as f:
+            f.write("\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    main()
