@@ -1600,8 +1600,8 @@ struct TcWorkspace {
 
 TcWorkspace tc_workspace(const cutdet_net *net, const Geom &g, int batch) {
     TcWorkspace w;
-    static const int sub_batch = [] { const char *e = getenv("CUTDET_SUB_BATCH"); const int v = e ? atoi(e) : 0; return v > 0 ? v : SUB_BATCH; }();
-    static const int group_frames = [] { const char *e = getenv("CUTDET_GROUP_FRAMES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : GROUP_FRAMES; }();
+    const int sub_batch = net->opt.sub_batch > 0 ? net->opt.sub_batch : SUB_BATCH;
+    const int group_frames = net->opt.group_frames > 0 ? net->opt.group_frames : GROUP_FRAMES;
     const int group_cap = std::max(group_frames, sub_batch);
     w.sub = batch < sub_batch ? batch : sub_batch;
     w.group_frames = batch < group_cap ? batch : group_cap;
@@ -1655,10 +1655,9 @@ int set_smem_limits() {
 // Launch with programmatic stream serialization: the kernel may start while the one before it in the stream drains (see
 // grid_dep_launch / grid_dep_wait in tc_common.cuh; every kernel launched this way orders its dependent accesses itself).
 // Grids are at most one CTA per SM, so a waiting successor can never keep a predecessor's CTA from being scheduled.
-// CUTDET_NO_PDL=1 falls back to ordinary launches.
+// cutdet_net_set_option(CUTDET_OPT_NO_PDL) falls back to ordinary launches (pdl = false everywhere).
 template <typename... KArgs, typename... Args>
 void launch_pdl(bool pdl, void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t stream, Args &&...args) {
-    static const bool off = getenv("CUTDET_NO_PDL") != nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)threads);
@@ -1668,7 +1667,7 @@ void launch_pdl(bool pdl, void (*kernel)(KArgs...), int grid, int threads, size_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (off || !pdl) ? 0 : 1;
+    cfg.numAttrs = pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -1684,10 +1683,9 @@ int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
 }
 
 template <int C>
-int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream, bool pdl) {
-    // CUTDET_CONV1_GRID caps the grid (test hook: several frames per CTA, as on a part with fewer SMs than a sub-batch has frames)
-    static const int grid_cap = [] { const char *e = getenv("CUTDET_CONV1_GRID"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 1 << 30; }();
-    const int grid = std::min(std::min(p.B, sm_count()), grid_cap);
+int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream, bool pdl, bool acc32, int grid_cap) {
+    // grid_cap (CUTDET_OPT_CONV1_GRID) is a test hook: several frames per CTA, as on a part with fewer SMs than a sub-batch has frames
+    const int grid = std::min(std::min(p.B, sm_count()), grid_cap > 0 ? grid_cap : 1 << 30);
     static const bool regs_ok = [] {
         const void *fns[4] = {(const void *)conv1_fused_tc_kernel<C, true, false>, (const void *)conv1_fused_tc_kernel<C, false, false>,
                               (const void *)conv1_fused_tc_kernel<C, true, true>, (const void *)conv1_fused_tc_kernel<C, false, true>};
@@ -1704,8 +1702,8 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_
         return ok;
     }();
     if (!regs_ok) return CUTDET_EUNSUPPORTED;
-    // fp16 accumulators (half the TMEM read traffic, the max/affine on channel pairs) unless CUTDET_CONV1_ACC32 asks for the fp32 ones
-    static const bool acc32 = getenv("CUTDET_CONV1_ACC32") != nullptr;
+    // fp16 accumulators (half the TMEM read traffic, the max/affine on channel pairs) unless the net was told to keep fp32 ones
+    // (cutdet_net_set_option(CUTDET_OPT_CONV1_ACC32))
     const bool acc16 = !acc32 && p.w_perm16 != nullptr;
     FusedSrc src = src_in;
     src.n_slots = (int)std::min<long long>(raw_bytes(acc16 ? F1Roles<true>::UNFOLD_WARPS : F1Roles<false>::UNFOLD_WARPS) / ((long long)src.n_src * src.row_bytes),
@@ -1755,11 +1753,11 @@ bool fused_source(const cutdet_resize_plan *plan, const cutdet_frames *frames, c
 }
 
 template <int C>
-int launch_mid(const CUtensorMap &map, const MidParams &p, const char *name, cudaStream_t stream) {
+int launch_mid(const CUtensorMap &map, const MidParams &p, const char *name, cudaStream_t stream, bool pdl) {
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
     {
         KernelScope scope(name, stream);
-        launch_pdl(true, conv_mid_tc_kernel<C>, grid, 320, MidSmem<C>::total, stream, map, p);
+        launch_pdl(pdl, conv_mid_tc_kernel<C>, grid, 320, MidSmem<C>::total, stream, map, p);
     }
     CUTDET_LAUNCH_CHECK("conv_mid_tc_kernel");
     return CUTDET_OK;
@@ -1809,57 +1807,21 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     c1.w_perm16 = reinterpret_cast<const uint4 *>(tc->d_w1_perm16);
     c1.par16 = tc->d_c1_par16;
     c1.folded = tc->c1_folded ? 1 : 0;
+    // debug stamps (cutdet_net_debug_timeline): the armed buffer is caller-owned device memory; nothing is allocated, copied or
+    // synchronised here
+    if (net->opt.timeline_kernel == 1 && nb >= SUB_BATCH) c1.timeline = net->opt.timeline_dev;
     if (fused) {
         FusedSrc fs = *fused;
         fs.frames += (long long)f0 * fs.frame_stride;
-        static const bool want_tl = getenv("CUTDET_TIMELINE1") != nullptr;       // debug aid: clock stamps of CTA 0, dumped once
-        static int tl_runs = 0;
-        if (want_tl && nb >= 148 && tl_runs++ == 20) {
-            long long *d = nullptr;
-            std::vector<long long> h(2048);
-            CUTDET_CUDA(cudaMalloc(&d, 2048 * 8));
-            CUTDET_CUDA(cudaMemsetAsync(d, 0, 2048 * 8, stream));
-            c1.timeline = d;
-            if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0)) return rc;
-            CUTDET_CUDA(cudaMemcpyAsync(h.data(), d, 2048 * 8, cudaMemcpyDeviceToHost, stream));
-            CUTDET_CUDA(cudaStreamSynchronize(stream));
-            FILE *f = fopen(getenv("CUTDET_TIMELINE1"), "w");
-            if (f) { for (int i = 0; i < 2048; ++i) fprintf(f, "%lld\n", h[i] ? h[i] - h[2047] : -1LL); fclose(f); }
-            cudaFree(d);
-            c1.timeline = nullptr;
-        } else if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0)) return rc;
+        if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0 && !net->opt.no_pdl, net->opt.conv1_acc32 != 0, net->opt.conv1_grid)) return rc;
     } else if (int rc = launch_conv1<C>(c1, stream)) return rc;
 
     MidParams p2 = mid_params(nb, g.FP1, g.PW1, g.P2h, g.P2w);
     p2.out = OutSpec{ws + w.act2, 0, w.gtot2, g.PW2, g.FP2, g.Q2h, slot0, g.P2h, g.P2w};
     p2.w_packed = reinterpret_cast<const uint4 *>(tc->d_w2);
     p2.bias = net->conv[1].d_bias; p2.scale = net->conv[1].d_scale; p2.shift = net->conv[1].d_shift;
-    static const bool want_timeline = getenv("CUTDET_TIMELINE") != nullptr;     // debug aid: clock stamps of CTA 0, printed once
-    static int timeline_runs = 0;
-    if (want_timeline && nb >= 148 && timeline_runs++ == 20) {
-        long long *d = nullptr, h[128 + 4 * 148];
-        CUTDET_CUDA(cudaMalloc(&d, sizeof(h)));
-        CUTDET_CUDA(cudaMemsetAsync(d, 0, sizeof(h), stream));
-        p2.timeline = d;
-        if (int rc = launch_mid<C>(map1, p2, "conv2_tc", stream)) return rc;
-        CUTDET_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream));
-        CUTDET_CUDA(cudaStreamSynchronize(stream));
-        fprintf(stderr, "conv2 timeline (cycles since kernel entry): mma-loop-start %lld |", h[1] - h[0]);
-        for (int i = 2; i < 63 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
-        fprintf(stderr, " | epilogue tiles:");
-        for (int i = 64; i < 96 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
-        fprintf(stderr, " | end %lld\n", h[63] - h[0]);
-        long long t0 = h[128];
-        for (int c = 0; c < 148; ++c) if (h[128 + 4 * c] && h[128 + 4 * c] < t0) t0 = h[128 + 4 * c];
-        fprintf(stderr, "conv2 timeline per CTA (ns since first CTA entry: entry/first-data/end):");
-        for (int c = 0; c < 148; c += 7) fprintf(stderr, " [%d] %lld/%lld/%lld", c, h[128 + 4 * c] - t0, h[128 + 4 * c + 2] - t0, h[128 + 4 * c + 1] - t0);
-        long long worst = 0;
-        for (int c = 0; c < 148; ++c) if (h[128 + 4 * c + 1] - t0 > worst) worst = h[128 + 4 * c + 1] - t0;
-        fprintf(stderr, " | last end %lld\n", worst);
-        cudaFree(d);
-        return CUTDET_OK;
-    }
-    return launch_mid<C>(map1, p2, "conv2_tc", stream);
+    if (net->opt.timeline_kernel == 2 && nb >= SUB_BATCH) p2.timeline = net->opt.timeline_dev;
+    return launch_mid<C>(map1, p2, "conv2_tc", stream, !net->opt.no_pdl);
 }
 
 // conv3 over the `n` frames gathered in the group buffer; their layer-3 maps go to frames [frame0, frame0 + n) of act3.
@@ -1871,7 +1833,7 @@ int run_conv3(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, co
     p3.out = OutSpec{ws + w.act3, 1, 0, 0, 0, 0, frame0, g.P3h, g.P3w};
     p3.w_packed = reinterpret_cast<const uint4 *>(tc->d_w3);
     p3.bias = net->conv[2].d_bias; p3.scale = net->conv[2].d_scale; p3.shift = net->conv[2].d_shift;
-    return launch_mid<C>(map2, p3, "conv3_tc", stream);
+    return launch_mid<C>(map2, p3, "conv3_tc", stream, !net->opt.no_pdl);
 }
 
 // AdaptiveAvgPool + first FC folded, for this pooled-map size; built once and cached.
@@ -2215,14 +2177,14 @@ int run_batchstats(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *w
     p2.out = OutSpec{ws + w.act2, 0, w.gtot2, g.PW2, g.FP2, g.Q2h, 0, g.P2h, g.P2w};
     p2.w_packed = reinterpret_cast<const uint4 *>(tc->d_w2);
     p2.bias = net->conv[1].d_bias; p2.scale = tc->d_ones; p2.shift = tc->d_zeros;
-    if (int rc = launch_mid<C>(maps->first, p2, "conv2_tc", stream)) return rc;
+    if (int rc = launch_mid<C>(maps->first, p2, "conv2_tc", stream, !net->opt.no_pdl)) return rc;
     if (int rc = phase_split_bn(ws + w.act2, w.gtot2, g.FP2, g.PW2, g.P2h, g.P2w, net->conv[1])) return rc;
     // layer 3: [frame][pixel][C] float32
     MidParams p3 = mid_params(batch, g.FP2, g.PW2, g.P3h, g.P3w);
     p3.out = OutSpec{ws + w.act3, 1, 0, 0, 0, 0, 0, g.P3h, g.P3w};
     p3.w_packed = reinterpret_cast<const uint4 *>(tc->d_w3);
     p3.bias = net->conv[2].d_bias; p3.scale = tc->d_ones; p3.shift = tc->d_zeros;
-    if (int rc = launch_mid<C>(maps->second, p3, "conv3_tc", stream)) return rc;
+    if (int rc = launch_mid<C>(maps->second, p3, "conv3_tc", stream, !net->opt.no_pdl)) return rc;
     if (int rc = launch_bn_batchstats(reinterpret_cast<float *>(ws + w.act3), batch * g.P3h * g.P3w, C, 1, net->conv[2].d_gamma,
                                       net->conv[2].d_beta, net->conv[2].eps, stream))
         return rc;
@@ -2258,7 +2220,9 @@ int run_batchstats(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *w
 }
 
 bool tc_batchstats_supported(const cutdet_net *net, int batch, int height, int width) {
-    return tc_supported(net, height, width) && batch <= BATCHSTATS_MAX;
+    // everything resident in one pass: the workspace (tc_workspace) holds `sub` frames of input and layer-1 activations
+    const int sub = net->opt.sub_batch > 0 ? net->opt.sub_batch : SUB_BATCH;
+    return tc_supported(net, height, width) && batch <= BATCHSTATS_MAX && batch <= sub;
 }
 
 int tc_forward_f32_batchstats(cutdet_net *net, const float *x, int batch, int height, int width, float *out, char *ws, cudaStream_t stream) {

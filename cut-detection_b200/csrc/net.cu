@@ -184,8 +184,16 @@ extern "C" int cutdet_net_set_fc_layer(cutdet_net *net, int layer, const float *
         L.gamma.assign(g, g + L.out);
         L.beta.assign(beta, beta + L.out);
         L.eps = eps;
-    } else {
-        CUTDET_REQUIRE(!g && !beta && !mean && !var, "set_fc_layer: the last layer has no BatchNorm (net.py:164-167)");
+    } else if (g || beta || mean || var) {
+        // FrameLinearNet never puts a BatchNorm on its last layer (net.py:164-167), a lone FCLayer may have one (net.py:43-68):
+        // accepted on a one-layer FC-only net, which is what FCLayer.forward builds
+        CUTDET_REQUIRE(net->cfg.n_conv_layers == 0 && net->cfg.n_fc_layers == 1 && g && beta && mean && var,
+                       "set_fc_layer: the last layer has no BatchNorm (net.py:164-167)");
+        L.has_bn = true;
+        fold_bn(L.out, g, beta, mean, var, eps, L.scale, L.shift);
+        L.gamma.assign(g, g + L.out);
+        L.beta.assign(beta, beta + L.out);
+        L.eps = eps;
     }
     L.w.assign(w, w + (size_t)L.out * L.in);
     L.bias.assign(b, b + L.out);
@@ -223,6 +231,73 @@ extern "C" int cutdet_net_finalize(cutdet_net *net) {
     }
     if (int rc = tc_prepare(net)) return rc;
     net->finalized = true;
+    return CUTDET_OK;
+}
+
+extern "C" int cutdet_net_set_option(cutdet_net *net, int option, int value) {
+    CUTDET_REQUIRE(net, "net_set_option: null net");
+    CUTDET_REQUIRE(value >= 0, "net_set_option: negative value");
+    switch (option) {
+        case CUTDET_OPT_CONV1_ACC32: net->opt.conv1_acc32 = value != 0; break;
+        case CUTDET_OPT_SUB_BATCH: net->opt.sub_batch = value; break;
+        case CUTDET_OPT_GROUP_FRAMES: net->opt.group_frames = value; break;
+        case CUTDET_OPT_NO_PDL: net->opt.no_pdl = value != 0; break;
+        case CUTDET_OPT_CONV1_GRID: net->opt.conv1_grid = value; break;
+        default: return fail(CUTDET_EINVAL, "net_set_option: unknown option %d", option);
+    }
+    return CUTDET_OK;
+}
+
+extern "C" int cutdet_net_get_option(const cutdet_net *net, int option, int *value) {
+    CUTDET_REQUIRE(net && value, "net_get_option: null argument");
+    switch (option) {
+        case CUTDET_OPT_CONV1_ACC32: *value = net->opt.conv1_acc32; break;
+        case CUTDET_OPT_SUB_BATCH: *value = net->opt.sub_batch; break;
+        case CUTDET_OPT_GROUP_FRAMES: *value = net->opt.group_frames; break;
+        case CUTDET_OPT_NO_PDL: *value = net->opt.no_pdl; break;
+        case CUTDET_OPT_CONV1_GRID: *value = net->opt.conv1_grid; break;
+        default: return fail(CUTDET_EINVAL, "net_get_option: unknown option %d", option);
+    }
+    return CUTDET_OK;
+}
+
+extern "C" int cutdet_net_debug_timeline(cutdet_net *net, int kernel, long long *stamps_dev, size_t n_entries) {
+    CUTDET_REQUIRE(net, "net_debug_timeline: null net");
+    if (kernel == 0 || !stamps_dev) { net->opt.timeline_kernel = 0; net->opt.timeline_dev = nullptr; return CUTDET_OK; }
+    CUTDET_REQUIRE((kernel == 1 || kernel == 2) && n_entries >= 2048, "net_debug_timeline: kernel 1 or 2 and >= 2048 entries");
+    net->opt.timeline_kernel = kernel;
+    net->opt.timeline_dev = stamps_dev;
+    return CUTDET_OK;
+}
+
+extern "C" int cutdet_net_forward_conv_layer(cutdet_net *net, int layer, const float *x, int batch, int height, int width,
+                                             float *out, int bn_mode, cutdet_stream_t stream) {
+    CUTDET_REQUIRE(net && net->finalized, "net_forward_conv_layer: net not finalized");
+    CUTDET_REQUIRE(layer >= 0 && layer < net->cfg.n_conv_layers, "net_forward_conv_layer: layer %d out of range", layer);
+    CUTDET_REQUIRE(batch >= 0 && height > 0 && width > 0 && bn_mode >= 0 && bn_mode <= 2, "net_forward_conv_layer: bad argument");
+    if (batch == 0) return CUTDET_OK;
+    CUTDET_REQUIRE(x && out, "net_forward_conv_layer: null pointer");
+    CUTDET_REQUIRE(bn_mode != 2 || batch * (height / 3) * (width / 3) >= 2,
+                   "net_forward_conv_layer: batch statistics need more than one value per channel");
+    const ConvLayer &L = net->conv[layer];
+    if (int rc = launch_conv_block_generic(x, out, L, layer, batch, height, width, as_stream(stream), bn_mode == 1)) return rc;
+    if (bn_mode == 2)
+        return launch_bn_batchstats(out, batch, L.cout, (height / 3) * (width / 3), L.d_gamma, L.d_beta, L.eps, as_stream(stream));
+    return CUTDET_OK;
+}
+
+extern "C" int cutdet_net_forward_fc_layer(cutdet_net *net, int layer, const float *x, int batch, float *out, int relu, int bn_mode,
+                                           cutdet_stream_t stream) {
+    CUTDET_REQUIRE(net && net->finalized, "net_forward_fc_layer: net not finalized");
+    CUTDET_REQUIRE(layer >= 0 && layer < net->cfg.n_fc_layers, "net_forward_fc_layer: layer %d out of range", layer);
+    CUTDET_REQUIRE(batch >= 0 && bn_mode >= 0 && bn_mode <= 2, "net_forward_fc_layer: bad argument");
+    if (batch == 0) return CUTDET_OK;
+    CUTDET_REQUIRE(x && out, "net_forward_fc_layer: null pointer");
+    const FcLayer &L = net->fc[layer];
+    CUTDET_REQUIRE(bn_mode == 0 || L.has_bn, "net_forward_fc_layer: layer %d has no BatchNorm", layer);
+    CUTDET_REQUIRE(bn_mode != 2 || batch >= 2, "net_forward_fc_layer: batch statistics need more than one value per channel");
+    if (int rc = launch_fc(x, out, L, batch, relu != 0, as_stream(stream), bn_mode == 1)) return rc;
+    if (bn_mode == 2) return launch_bn_batchstats(out, batch, L.out, 1, L.d_gamma, L.d_beta, L.eps, as_stream(stream));
     return CUTDET_OK;
 }
 

@@ -48,8 +48,20 @@ int launch_bn_batchstats(float *data, int outer, int channels, int inner, const 
 
 }  // namespace cutdet
 
+// cutdet_net_set_option: experiment and test switches, per net (nothing is read from the environment)
+struct cutdet_net_options {
+    int conv1_acc32 = 0;      // layer 1 of the fused frames kernel accumulates in fp32 instead of fp16
+    int sub_batch = 0;        // frames per conv1/conv2 pass (0 = default, one frame per SM)
+    int group_frames = 0;     // frames gathered per conv3 launch (0 = default)
+    int no_pdl = 0;           // ordinary launches instead of programmatic dependent launch
+    int conv1_grid = 0;       // cap on the fused conv1 grid (test hook: several frames per CTA)
+    int timeline_kernel = 0;  // cutdet_net_debug_timeline: 1 = conv1_fused_tc, 2 = conv2_tc
+    long long *timeline_dev = nullptr;
+};
+
 struct cutdet_net {
     cutdet_net_config cfg;
+    cutdet_net_options opt;
     std::vector<cutdet::ConvLayer> conv;
     std::vector<cutdet::FcLayer> fc;
     bool finalized = false;

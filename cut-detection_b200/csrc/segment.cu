@@ -4,7 +4,7 @@
 //   K5  run boundaries, run lengths, per-run mean of the max logit   :39-60
 //   K6  glue_orphans (:91-166, _find_orphans :12-17, _update_neighbor :69-89), combine_adjacent_segments (:168-183)
 // These are integer/byte passes over 5 bytes per frame: HBM/latency bound, no tensor-core work.
-#include <mutex>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -249,10 +249,13 @@ __global__ void rle_finish_kernel(RleState *st, cutdet_run_table table, int64_t 
 // +inf when the run is dead or not an orphan; level l: min of 32 children with the run index that attains it) and
 // each step is root lookup -> merge by lane 0 -> two leaf-to-root refreshes, each level one coalesced 32-wide load
 // and a shuffle reduction.  Ties go to the lowest run index.
+// Keys are the means mapped to unsigned integers of the same order (so a NaN mean can be given a place: LAST among the orphans,
+// where torch.argsort puts it -- the reference still glues such a run, after every orphan with a number for a mean), KEY_NONE
+// = not an orphan / dead.
 struct GlueScratch {
     int *prev, *next;        // neighbours in the list of live runs; prev == -2 marks a dead run
-    float *key0;             // level 0 keys
-    float *lv_val[4];        // levels 1..4 (sized for the table's capacity)
+    uint32_t *key0;          // level 0 keys
+    uint32_t *lv_val[4];     // levels 1..4 (sized for the table's capacity)
     int *lv_idx[4];
     long long lv_n[5];       // entries per level for the CURRENT run count (lv_n[0] = S), set by the kernel
     int n_levels;            // levels above 0 in use, set by the kernel
@@ -265,12 +268,20 @@ __device__ __forceinline__ void glue_levels(GlueScratch &ws, long long S) {
     ws.n_levels = levels;
 }
 
-__device__ __forceinline__ bool key_less(float va, int ia, float vb, int ib) { return va < vb || (va == vb && ia < ib); }
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu, KEY_NAN = 0xFFFFFFFEu;
 
-__device__ __forceinline__ void warp_argmin(float &v, int &i) {
+__device__ __forceinline__ uint32_t orphan_key(float mean) {
+    if (mean != mean) return KEY_NAN;
+    const uint32_t u = __float_as_uint(mean + 0.0f);           // -0 -> +0: equal floats keep equal keys
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ bool key_less(uint32_t va, int ia, uint32_t vb, int ib) { return va < vb || (va == vb && ia < ib); }
+
+__device__ __forceinline__ void warp_argmin(uint32_t &v, int &i) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, v, off);
+        const uint32_t ov = __shfl_xor_sync(0xffffffffu, v, off);
         const int oi = __shfl_xor_sync(0xffffffffu, i, off);
         if (key_less(ov, oi, v, i)) { v = ov; i = oi; }
     }
@@ -286,15 +297,15 @@ __device__ void refresh_path(const GlueScratch &ws, long long leaf, int lane) {
     for (int l = 0; l < ws.n_levels; ++l) {
         const long long group = child >> 5;
         const long long c = (group << 5) + lane;
-        float v = INFINITY;
+        uint32_t v = KEY_NONE;
         int i = 0x7fffffff;
         if (c < ws.lv_n[l]) {
-            if (l == 0) { v = ((volatile float *)ws.key0)[c]; i = (int)c; }
-            else { v = ((volatile float *)ws.lv_val[l - 1])[c]; i = ((volatile int *)ws.lv_idx[l - 1])[c]; }
+            if (l == 0) { v = ((volatile uint32_t *)ws.key0)[c]; i = (int)c; }
+            else { v = ((volatile uint32_t *)ws.lv_val[l - 1])[c]; i = ((volatile int *)ws.lv_idx[l - 1])[c]; }
         }
         warp_argmin(v, i);
         if (lane == 0) {
-            ((volatile float *)ws.lv_val[l])[group] = v;
+            ((volatile uint32_t *)ws.lv_val[l])[group] = v;
             ((volatile int *)ws.lv_idx[l])[group] = i;
         }
         __syncwarp();
@@ -313,40 +324,40 @@ glue_orphans_kernel(cutdet_run_table t, int64_t *n_runs, int k_real, int k_blank
     volatile int32_t *type = t.frame_types_dev;
     volatile float *mean = t.score_means_dev;
     volatile int *prev = ws.prev, *next = ws.next;
-    volatile float *key0 = ws.key0;
+    volatile uint32_t *key0 = ws.key0;
     // build
     for (long long i = lane; i < S; i += 32) {
         prev[i] = (int)i - 1;
         next[i] = i + 1 < S ? (int)i + 1 : -1;
-        key0[i] = is_orphan(type[i], len[i], k_real, k_blank) ? mean[i] : INFINITY;
+        key0[i] = is_orphan(type[i], len[i], k_real, k_blank) ? orphan_key(mean[i]) : KEY_NONE;
     }
     __syncwarp();
     for (int l = 0; l < ws.n_levels; ++l) {
         for (long long g = 0; g < ws.lv_n[l + 1]; ++g) {
             const long long c = (g << 5) + lane;
-            float v = INFINITY;
+            uint32_t v = KEY_NONE;
             int i = 0x7fffffff;
             if (c < ws.lv_n[l]) {
                 if (l == 0) { v = key0[c]; i = (int)c; }
-                else { v = ((volatile float *)ws.lv_val[l - 1])[c]; i = ((volatile int *)ws.lv_idx[l - 1])[c]; }
+                else { v = ((volatile uint32_t *)ws.lv_val[l - 1])[c]; i = ((volatile int *)ws.lv_idx[l - 1])[c]; }
             }
             warp_argmin(v, i);
-            if (lane == 0) { ((volatile float *)ws.lv_val[l])[g] = v; ((volatile int *)ws.lv_idx[l])[g] = i; }
+            if (lane == 0) { ((volatile uint32_t *)ws.lv_val[l])[g] = v; ((volatile int *)ws.lv_idx[l])[g] = i; }
         }
         __syncwarp();
     }
     // glue
     bool lone = false;
     while (true) {
-        float v = INFINITY;
+        uint32_t v = KEY_NONE;
         int target = 0x7fffffff;
         const int top = ws.n_levels;     // top level has <= 32 entries
         if (lane < ws.lv_n[top]) {
             if (top == 0) { v = key0[lane]; target = lane; }
-            else { v = ((volatile float *)ws.lv_val[top - 1])[lane]; target = ((volatile int *)ws.lv_idx[top - 1])[lane]; }
+            else { v = ((volatile uint32_t *)ws.lv_val[top - 1])[lane]; target = ((volatile int *)ws.lv_idx[top - 1])[lane]; }
         }
         warp_argmin(v, target);
-        if (!(v < INFINITY)) break;                 // no orphan left
+        if (v == KEY_NONE) break;                   // no orphan left
         int nb = -1;
         if (lane == 0) {
             const int p = prev[target], n = next[target];
@@ -364,8 +375,8 @@ glue_orphans_kernel(cutdet_run_table t, int64_t *n_runs, int k_real, int k_blank
                 if (p >= 0) next[p] = n;
                 if (n >= 0) prev[n] = p;
                 prev[target] = -2;
-                key0[target] = INFINITY;
-                key0[nb] = is_orphan(type[nb], len[nb], k_real, k_blank) ? mean[nb] : INFINITY;
+                key0[target] = KEY_NONE;
+                key0[nb] = is_orphan(type[nb], len[nb], k_real, k_blank) ? orphan_key(mean[nb]) : KEY_NONE;
             }
         }
         nb = __shfl_sync(0xffffffffu, nb, 0);
@@ -482,40 +493,121 @@ stitch_kernel(cutdet_run_table src, int n_shards, int64_t shard_capacity, const 
     if (threadIdx.x == 0) *n_out = s_out;     // > dst.capacity means rows were dropped; the caller checks
 }
 
-// ------------------------------------------------------------------------------------------- scratch for K6
-std::mutex g_scratch_mutex;
-void *g_scratch = nullptr;
-size_t g_scratch_bytes = 0;
+// ------------------------------------------------------------------------------------------- packed shard tables
+// What travels in the one exchange step of the multi-GPU path: a 16-byte header (n_runs, n_frames) and `capacity`
+// rows of 40 bytes -- end, start, length (int64), sum (float64), type (int32), mean (float32) -- per shard.  Sums and lengths,
+// not means, so a run cut by a shard edge is re-joined exactly.
+struct __align__(8) PackedRow { long long end, start, length; double sum; int type; float mean; };
+static_assert(sizeof(PackedRow) == 40, "packed run-table row");
+constexpr size_t PACK_HEADER = 16;
 
-int glue_scratch(long long capacity, GlueScratch *ws) {
-    // layout: prev[S] next[S] key0[S] then (val, idx) per level
-    long long n[5];
+__global__ void __launch_bounds__(256) shard_pack_kernel(cutdet_run_table t, const int64_t *n_runs, long long n_frames,
+                                                         long long capacity, uint8_t *packed) {
+    const long long n = *n_runs;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        reinterpret_cast<long long *>(packed)[0] = n;          // may exceed `capacity`: the stitch reports it
+        reinterpret_cast<long long *>(packed)[1] = n_frames;
+    }
+    PackedRow *rows = reinterpret_cast<PackedRow *>(packed + PACK_HEADER);
+    const long long m = n < capacity ? n : capacity;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        PackedRow r;
+        r.end = t.end_frames_dev[i]; r.start = t.start_frames_dev[i]; r.length = t.run_lengths_dev[i];
+        r.sum = t.score_sums_dev[i]; r.type = t.frame_types_dev[i]; r.mean = t.score_means_dev[i];
+        rows[i] = r;
+    }
+}
+
+// Joins the gathered shards (one block; S is tens to thousands).  Frame offsets are the running sum of the headers' frame
+// counts.  *n_out < 0 reports a shard whose table did not fit the gather capacity: -(1 + its run count).
+__global__ void __launch_bounds__(256)
+stitch_packed_kernel(const uint8_t *__restrict__ gathered, int n_shards, long long capacity, cutdet_run_table dst, int64_t *n_out,
+                     int64_t *total_frames) {
+    __shared__ long long s_out;
+    const size_t stride = PACK_HEADER + (size_t)capacity * sizeof(PackedRow);
+    if (threadIdx.x == 0) s_out = 0;
+    __syncthreads();
+    long long off = 0, worst = 0;
+    for (int sh = 0; sh < n_shards; ++sh) {
+        const uint8_t *base = gathered + (size_t)sh * stride;
+        const long long n = reinterpret_cast<const long long *>(base)[0], frames = reinterpret_cast<const long long *>(base)[1];
+        const PackedRow *rows = reinterpret_cast<const PackedRow *>(base + PACK_HEADER);
+        if (n > capacity && n > worst) worst = n;
+        if (n > 0 && n <= capacity) {                      // uniform across the block
+            const long long out0 = s_out;
+            const bool join = out0 > 0 && dst.frame_types_dev[out0 - 1] == rows[0].type;
+            __syncthreads();
+            const long long skip = join ? 1 : 0;
+            if (threadIdx.x == 0 && join) {
+                const long long o = out0 - 1;
+                const double sum = dst.score_sums_dev[o] + rows[0].sum;
+                const long long e = off + rows[0].end, len = e - dst.start_frames_dev[o] + 1;
+                dst.end_frames_dev[o] = e;
+                dst.run_lengths_dev[o] = len;
+                dst.score_sums_dev[o] = sum;
+                dst.score_means_dev[o] = (float)(sum / (double)len);
+            }
+            for (long long k = skip + threadIdx.x; k < n; k += blockDim.x) {
+                const long long o = out0 + k - skip;
+                if (o < dst.capacity) {
+                    const PackedRow r = rows[k];
+                    dst.end_frames_dev[o] = off + r.end;
+                    dst.start_frames_dev[o] = off + r.start;
+                    dst.run_lengths_dev[o] = r.length;
+                    dst.frame_types_dev[o] = r.type;
+                    dst.score_sums_dev[o] = r.sum;
+                    dst.score_means_dev[o] = r.mean;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_out = out0 + n - skip;
+            __syncthreads();
+        }
+        off += frames;
+    }
+    if (threadIdx.x == 0) {
+        *n_out = worst > 0 ? -(1 + worst) : s_out;        // > dst.capacity means rows were dropped; the caller checks
+        if (total_frames) *total_frames = off;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- scratch for K6
+// The caller owns it (cutdet_glue_orphans_workspace_bytes): prev[S] next[S] key0[S], then (key, index) per tree level.
+int glue_level_sizes(long long capacity, long long (&n)[5]) {      // returns the levels above 0, -1 if the table is too large
     n[0] = capacity;
     int levels = 0;
     while (n[levels] > 32 && levels < 4) { n[levels + 1] = (n[levels] + 31) / 32; ++levels; }
-    if (n[levels] > 32) return fail(CUTDET_ECAPACITY, "glue_orphans: run table of %lld rows is too large", capacity);
+    for (int l = levels + 1; l < 5; ++l) n[l] = 0;
+    return n[levels] > 32 ? -1 : levels;
+}
+
+size_t glue_scratch_bytes(long long capacity) {
+    long long n[5];
+    const int levels = glue_level_sizes(capacity, n);
+    if (levels < 0) return 0;
     size_t bytes = (size_t)capacity * 12;
     for (int l = 1; l <= levels; ++l) bytes += (size_t)n[l] * 8;
-    bytes += 256;
-    {
-        std::lock_guard<std::mutex> lock(g_scratch_mutex);
-        if (bytes > g_scratch_bytes) {
-            if (g_scratch) cudaFree(g_scratch);
-            g_scratch = nullptr;
-            g_scratch_bytes = 0;
-            CUTDET_CUDA(cudaMalloc(&g_scratch, bytes));
-            g_scratch_bytes = bytes;
-        }
-    }
-    char *p = reinterpret_cast<char *>(g_scratch);
+    return bytes + 256;
+}
+
+int glue_scratch(long long capacity, void *workspace, size_t workspace_bytes, GlueScratch *ws) {
+    long long n[5];
+    const int levels = glue_level_sizes(capacity, n);
+    if (levels < 0) return fail(CUTDET_ECAPACITY, "glue_orphans: run table of %lld rows is too large", capacity);
+    if (!workspace || workspace_bytes < glue_scratch_bytes(capacity))
+        return fail(CUTDET_ECAPACITY, "glue_orphans: workspace of %zu bytes, %zu needed (cutdet_glue_orphans_workspace_bytes)",
+                    workspace_bytes, glue_scratch_bytes(capacity));
+    if (reinterpret_cast<uintptr_t>(workspace) % 16) return fail(CUTDET_EINVAL, "glue_orphans: workspace must be 16-byte aligned");
+    char *p = reinterpret_cast<char *>(workspace);
     ws->prev = reinterpret_cast<int *>(p); p += (size_t)capacity * 4;
     ws->next = reinterpret_cast<int *>(p); p += (size_t)capacity * 4;
-    ws->key0 = reinterpret_cast<float *>(p); p += (size_t)capacity * 4;
+    ws->key0 = reinterpret_cast<uint32_t *>(p); p += (size_t)capacity * 4;
     for (int l = 1; l <= levels; ++l) {
-        ws->lv_val[l - 1] = reinterpret_cast<float *>(p); p += (size_t)n[l] * 4;
+        ws->lv_val[l - 1] = reinterpret_cast<uint32_t *>(p); p += (size_t)n[l] * 4;
         ws->lv_idx[l - 1] = reinterpret_cast<int *>(p); p += (size_t)n[l] * 4;
     }
-    for (int l = 0; l < 5; ++l) ws->lv_n[l] = l <= levels ? n[l] : 0;
+    for (int l = levels; l < 4; ++l) { ws->lv_val[l] = nullptr; ws->lv_idx[l] = nullptr; }
+    for (int l = 0; l < 5; ++l) ws->lv_n[l] = n[l];
     ws->n_levels = levels;
     return CUTDET_OK;
 }
@@ -599,12 +691,14 @@ extern "C" int cutdet_rle_count(const void *state, int64_t *n_runs_host, cutdet_
     return CUTDET_OK;
 }
 
+extern "C" size_t cutdet_glue_orphans_workspace_bytes(int64_t capacity) { return capacity > 0 ? glue_scratch_bytes(capacity) : 0; }
+
 extern "C" int cutdet_glue_orphans(const cutdet_run_table *table, int64_t *n_runs, int real_threshold, int blank_threshold,
-                                   int32_t *status, cutdet_stream_t stream) {
+                                   int32_t *status, void *workspace, size_t workspace_bytes, cutdet_stream_t stream) {
     if (int rc = check_table(table, "glue_orphans")) return rc;
     CUTDET_REQUIRE(n_runs && status, "glue_orphans: null n_runs/status");
     GlueScratch ws;
-    if (int rc = glue_scratch(table->capacity, &ws)) return rc;
+    if (int rc = glue_scratch(table->capacity, workspace, workspace_bytes, &ws)) return rc;
     {
         KernelScope scope("glue_orphans_kernel", as_stream(stream));
         glue_orphans_kernel<<<1, 32, 0, as_stream(stream)>>>(*table, n_runs, real_threshold, blank_threshold, status, ws);
@@ -636,5 +730,36 @@ extern "C" int cutdet_stitch_shards(const cutdet_run_table *src, int n_shards, i
         stitch_kernel<<<1, 256, 0, as_stream(stream)>>>(*src, n_shards, shard_capacity, n_runs, offsets, *dst, n_out);
     }
     CUTDET_LAUNCH_CHECK("stitch_kernel");
+    return CUTDET_OK;
+}
+
+extern "C" size_t cutdet_shard_pack_bytes(int64_t capacity) { return capacity > 0 ? PACK_HEADER + (size_t)capacity * sizeof(PackedRow) : 0; }
+
+extern "C" int cutdet_shard_pack(const cutdet_run_table *table, const int64_t *n_runs, int64_t n_frames, int64_t capacity,
+                                 void *packed, cutdet_stream_t stream) {
+    if (int rc = check_table(table, "shard_pack")) return rc;
+    CUTDET_REQUIRE(n_runs && packed && capacity > 0 && n_frames >= 0, "shard_pack: bad argument");
+    CUTDET_REQUIRE(reinterpret_cast<uintptr_t>(packed) % 8 == 0, "shard_pack: the packed buffer must be 8-byte aligned");
+    const long long rows = capacity < table->capacity ? capacity : table->capacity;
+    {
+        KernelScope scope("shard_pack_kernel", as_stream(stream));
+        shard_pack_kernel<<<(unsigned)std::min<long long>(ceil_div(rows, 256), 64), 256, 0, as_stream(stream)>>>(
+            *table, n_runs, (long long)n_frames, (long long)rows, reinterpret_cast<uint8_t *>(packed));
+    }
+    CUTDET_LAUNCH_CHECK("shard_pack_kernel");
+    return CUTDET_OK;
+}
+
+extern "C" int cutdet_stitch_packed(const void *gathered, int n_shards, int64_t capacity, const cutdet_run_table *dst, int64_t *n_out,
+                                    int64_t *total_frames, cutdet_stream_t stream) {
+    if (int rc = check_table(dst, "stitch_packed(dst)")) return rc;
+    CUTDET_REQUIRE(gathered && n_shards >= 1 && capacity > 0 && n_out, "stitch_packed: bad argument");
+    CUTDET_REQUIRE(reinterpret_cast<uintptr_t>(gathered) % 8 == 0, "stitch_packed: the gathered buffer must be 8-byte aligned");
+    {
+        KernelScope scope("stitch_packed_kernel", as_stream(stream));
+        stitch_packed_kernel<<<1, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint8_t *>(gathered), n_shards, (long long)capacity,
+                                                               *dst, n_out, total_frames);
+    }
+    CUTDET_LAUNCH_CHECK("stitch_packed_kernel");
     return CUTDET_OK;
 }

@@ -16,6 +16,8 @@ _lock = threading.Lock()
 _lib = None
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ECAPACITY, ELONE_ORPHAN = range(6)
+ABI_VERSION = 2
+NET_OPTIONS = {"conv1_acc32": 1, "sub_batch": 2, "group_frames": 3, "no_pdl": 4, "conv1_grid": 5}
 
 
 class Frames(C.Structure):
@@ -58,6 +60,11 @@ _SIGNATURES = {
     "cutdet_net_set_conv_layer": (C.c_int, [_P, C.c_int, _PF, _PF, _PF, _PF, _PF, _PF, C.c_float]),
     "cutdet_net_set_fc_layer": (C.c_int, [_P, C.c_int, _PF, _PF, _PF, _PF, _PF, _PF, C.c_float]),
     "cutdet_net_finalize": (C.c_int, [_P]),
+    "cutdet_net_set_option": (C.c_int, [_P, C.c_int, C.c_int]),
+    "cutdet_net_get_option": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
+    "cutdet_net_forward_conv_layer": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "cutdet_net_forward_fc_layer": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "cutdet_net_debug_timeline": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "cutdet_net_uses_tensor_cores": (C.c_int, [_P, C.c_int, C.c_int]),
     "cutdet_net_workspace_bytes": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "cutdet_net_forward_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
@@ -72,9 +79,13 @@ _SIGNATURES = {
     "cutdet_rle_append": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(RunTable), _P]),
     "cutdet_rle_finish": (C.c_int, [_P, C.POINTER(RunTable), _P, _P]),
     "cutdet_rle_count": (C.c_int, [_P, C.POINTER(C.c_int64), _P]),
-    "cutdet_glue_orphans": (C.c_int, [C.POINTER(RunTable), _P, C.c_int, C.c_int, _P, _P]),
+    "cutdet_glue_orphans_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "cutdet_glue_orphans": (C.c_int, [C.POINTER(RunTable), _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "cutdet_combine_adjacent": (C.c_int, [C.POINTER(RunTable), _P, _P]),
     "cutdet_stitch_shards": (C.c_int, [C.POINTER(RunTable), C.c_int, C.c_int64, _P, _P, C.POINTER(RunTable), _P, _P]),
+    "cutdet_shard_pack_bytes": (C.c_size_t, [C.c_int64]),
+    "cutdet_shard_pack": (C.c_int, [C.POINTER(RunTable), _P, C.c_int64, C.c_int64, _P, _P]),
+    "cutdet_stitch_packed": (C.c_int, [_P, C.c_int, C.c_int64, C.POINTER(RunTable), _P, _P, _P]),
 }
 
 
@@ -101,17 +112,13 @@ def lib() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = library_path()
-        if not os.path.isfile(path):
-            raise RuntimeError(
-                f"libcutdet_b200.so not found at {path}: build it with `python -m cutdet.build` "
-                "(or __graft_entry__.build()); there is no fallback implementation")
+        path = _build.ensure_current()      # raises when the library is missing or stale and cannot be rebuilt
         handle = C.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)      # AttributeError here = header/library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args
-        if handle.cutdet_abi_version() != 1:
+        if handle.cutdet_abi_version() != ABI_VERSION:
             raise RuntimeError("libcutdet_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -26,6 +26,11 @@ NVCC_FLAGS = [
 ]
 
 
+def find_nvcc():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return nvcc if os.path.exists(nvcc) else None
+
+
 def sources() -> list[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -34,8 +39,9 @@ def _digest() -> str:
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     files.append(os.path.join(os.path.dirname(PKG_ROOT), "include", "cutdet_b200.h"))
+    root = os.path.dirname(PKG_ROOT)
     for p in files:
-        h.update(p.encode())
+        h.update(os.path.relpath(p, root).encode())      # repo-relative: the stamp holds on any checkout location
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -49,12 +55,25 @@ def is_current() -> bool:
         return False
 
 
+def ensure_current() -> str:
+    """Path of a library that matches the sources: rebuilds a stale or missing one when nvcc is here, raises otherwise.
+    (Called by cutdet._cabi.lib(): tests and the CLI never run a binary older than the sources next to it.)"""
+    if is_current():
+        return LIB_PATH
+    if find_nvcc():
+        return build_native(force=True)
+    if os.path.isfile(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is older than the sources in {CSRC} and nvcc is not available to rebuild it")
+    raise RuntimeError(f"libcutdet_b200.so not found at {LIB_PATH} and nvcc is not available: build it with "
+                       "`python -m cutdet.build` (or __graft_entry__.build()); there is no fallback implementation")
+
+
 def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ into one shared library.  Returns its path."""
     if not force and is_current():
         return LIB_PATH
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
+    nvcc = find_nvcc()
+    if not nvcc:
         raise RuntimeError("nvcc not found: cannot build libcutdet_b200.so")
     os.makedirs(LIB_DIR, exist_ok=True)
     objs = []

@@ -147,7 +147,7 @@ class NativeNet:
         for j in range(n_fc):
             p = f"linear.layers.{j}"
             arrs = [_f32(weights[p + ".linear.weight"]), _f32(weights[p + ".linear.bias"])]
-            if j < n_fc - 1:
+            if j < n_fc - 1 or (n_conv == 0 and n_fc == 1 and p + ".bn.weight" in weights):     # a lone FCLayer may carry a BatchNorm
                 arrs += [_f32(weights[p + s]) for s in (".bn.weight", ".bn.bias", ".bn.running_mean", ".bn.running_var")]
             else:
                 arrs += [None] * 4
@@ -162,6 +162,52 @@ class NativeNet:
                 self.handle = None
         except Exception:
             pass
+
+    def set_option(self, name: str, value: int) -> None:
+        """Scheduling / precision switches of the tensor-core path (include/cutdet_b200.h CUTDET_OPT_*): ``conv1_acc32``,
+        ``sub_batch``, ``group_frames``, ``no_pdl``, ``conv1_grid``.  They are per net; nothing is read from the environment."""
+        if name not in _cabi.NET_OPTIONS:
+            raise ValueError(f"unknown option {name!r}; known: {sorted(_cabi.NET_OPTIONS)}")
+        _cabi.check(_cabi.lib().cutdet_net_set_option(self.handle, _cabi.NET_OPTIONS[name], int(value)))
+        self._ws = None             # the workspace layout depends on sub_batch / group_frames
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int()
+        _cabi.check(_cabi.lib().cutdet_net_get_option(self.handle, _cabi.NET_OPTIONS[name], C.byref(v)))
+        return v.value
+
+    def forward_conv_layer(self, layer: int, x: torch.Tensor, bn_mode: int = 1) -> torch.Tensor:
+        """CNNLayer.forward (reference frameID/net.py:33-40) of conv layer ``layer`` alone: float32 [B,Cin,H,W] ->
+        [B,Cout,H//3,W//3].  bn_mode 0 = no BatchNorm, 1 = running statistics, 2 = batch statistics."""
+        _need_cuda(x, "input")
+        if x.dtype != torch.float32 or x.dim() != 4:
+            raise ValueError(f"input must be float32 [B,C,H,W], got {x.dtype} {tuple(x.shape)}")
+        cin = self.cfg.input_channels if layer == 0 else self.cfg.hidden_channels
+        if x.shape[1] != cin:
+            raise ValueError(f"input has {x.shape[1]} channels, the layer expects {cin}")
+        x = x.contiguous()
+        b, _, h, w = x.shape
+        if h < 3 or w < 3:
+            raise ValueError(f"input {h}x{w} is smaller than the 3x3 pool")
+        out = torch.empty((b, self.cfg.hidden_channels, h // 3, w // 3), dtype=torch.float32, device=x.device)
+        _cabi.check(_cabi.lib().cutdet_net_forward_conv_layer(self.handle, layer, x.data_ptr(), b, h, w, out.data_ptr(),
+                                                              int(bn_mode), _stream()))
+        return out
+
+    def forward_fc_layer(self, layer: int, x: torch.Tensor, relu: bool, bn_mode: int) -> torch.Tensor:
+        """FCLayer.forward (reference frameID/net.py:62-68) of FC layer ``layer`` alone: float32 [B,in] -> [B,out]."""
+        _need_cuda(x, "input")
+        if x.dtype != torch.float32 or x.dim() != 2:
+            raise ValueError(f"input must be float32 [B,in], got {x.dtype} {tuple(x.shape)}")
+        x = x.contiguous()
+        n_out = self.cfg.fc_output_size if layer == self.cfg.n_fc_layers - 1 else self.cfg.fc_hidden_size
+        n_in = self.cfg.fc_input_size if layer == 0 else self.cfg.fc_hidden_size
+        if x.shape[1] != n_in:
+            raise ValueError(f"input has {x.shape[1]} features, the layer expects {n_in}")
+        out = torch.empty((x.shape[0], n_out), dtype=torch.float32, device=x.device)
+        _cabi.check(_cabi.lib().cutdet_net_forward_fc_layer(self.handle, layer, x.data_ptr(), x.shape[0], out.data_ptr(),
+                                                            1 if relu else 0, int(bn_mode), _stream()))
+        return out
 
     def uses_tensor_cores(self, height: int, width: int) -> bool:
         return bool(_cabi.lib().cutdet_net_uses_tensor_cores(self.handle, height, width))
@@ -252,6 +298,14 @@ def argmax(scores: torch.Tensor):
 
 
 # ----------------------------------------------------------------------------------------------- K5/K6
+class ShardOverflow(RuntimeError):
+    """A shard's run table had more rows than the gather capacity of the exchange step (cutdet.shard)."""
+
+    def __init__(self, needed: int, capacity):
+        super().__init__(f"a shard's run table has {needed} runs, the gather capacity is {capacity}")
+        self.needed = needed
+
+
 class DeviceRunTable:
     """A cutdet_run_table backed by torch tensors."""
 
@@ -265,8 +319,12 @@ class DeviceRunTable:
         self.frame_types = torch.empty(capacity, dtype=torch.int32, device=device)
         self.score_means = torch.empty(capacity, dtype=torch.float32, device=device)
         self.score_sums = torch.empty(capacity, dtype=torch.float64, device=device)
-        self.n_runs = torch.zeros(1, dtype=torch.int64, device=device)
-        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        # run count and K6 status side by side: ONE 16-byte device->host copy reads both (to_te / count)
+        self._head = torch.zeros(2, dtype=torch.int64, device=device)
+        self.n_runs = self._head[0:1]
+        self.status = self._head[1:2].view(torch.int32)[0:1]
+        self._glue_ws = None        # K6 scratch, owned by this table (the library keeps none of its own)
+        self.shard_capacity = None  # set by shard.stitch_packed: what a negative run count is reported against
 
     def struct(self) -> _cabi.RunTable:
         return _cabi.RunTable(self.end_frames.data_ptr(), self.start_frames.data_ptr(), self.run_lengths.data_ptr(),
@@ -288,26 +346,48 @@ class DeviceRunTable:
         return t
 
     def count(self) -> int:
-        return int(self.n_runs.item())
-
-    def to_te(self) -> dict:
-        """The five columns as CPU tensors with the reference's dtypes (int64 / float32)."""
-        n = self.count()
+        """Run count (one device->host copy = one synchronisation).  Raises what the queued kernels reported: a deferred K6
+        status (IndexError for a lone orphan run), ShardOverflow from the stitch, RuntimeError for a table overflow."""
+        head = self._head.cpu()
+        n, status = int(head[0]), int(head[1]) & 0xFFFFFFFF
+        if n < 0:
+            raise ShardOverflow(-n - 1, self.shard_capacity)
+        if status:
+            self.status.zero_()
+            _cabi.check(status)
         if n > self.capacity:
             raise RuntimeError(f"run table overflow: {n} runs, capacity {self.capacity}")
+        return n
+
+    def to_te(self) -> dict:
+        """The five columns as CPU tensors with the reference's dtypes (int64 / float32): the run count, then ONE packed
+        device->host copy of the rows (cutdet_shard_pack's layout)."""
+        from . import shard
+        n = self.count()
+        if n == 0:
+            rows = np.zeros(0, dtype=shard.ROW_DTYPE)
+        else:
+            packed = shard.pack_table(self, 0, n).cpu().numpy()
+            rows = packed[shard.HEADER_BYTES:].view(shard.ROW_DTYPE)
         return {
-            "end_frames": self.end_frames[:n].cpu(),
-            "frame_types": self.frame_types[:n].to(torch.int64).cpu(),
-            "run_lengths": self.run_lengths[:n].cpu(),
-            "start_frames": self.start_frames[:n].cpu(),
-            "score_means": self.score_means[:n].cpu(),
+            "end_frames": torch.from_numpy(rows["end"].copy()),
+            "frame_types": torch.from_numpy(rows["type"].astype(np.int64)),
+            "run_lengths": torch.from_numpy(rows["length"].copy()),
+            "start_frames": torch.from_numpy(rows["start"].copy()),
+            "score_means": torch.from_numpy(rows["mean"].copy()),
         }
 
-    def glue_orphans(self, real_threshold: int = 100, blank_threshold: int = 10) -> None:
+    def glue_orphans(self, real_threshold: int = 100, blank_threshold: int = 10, defer_status: bool = False) -> None:
+        """K6.  ``defer_status``: do not synchronise here; a lone-orphan status is raised by the next count() / to_te()."""
         ts = self.struct()
-        _cabi.check(_cabi.lib().cutdet_glue_orphans(C.byref(ts), self.n_runs.data_ptr(), int(real_threshold),
-                                                    int(blank_threshold), self.status.data_ptr(), _stream()))
-        _cabi.check(int(self.status.item()))      # ELONE_ORPHAN -> IndexError, like the reference
+        lib = _cabi.lib()
+        if self._glue_ws is None:
+            self._glue_ws = torch.empty(lib.cutdet_glue_orphans_workspace_bytes(self.capacity), dtype=torch.uint8,
+                                        device=self.device)
+        _cabi.check(lib.cutdet_glue_orphans(C.byref(ts), self.n_runs.data_ptr(), int(real_threshold), int(blank_threshold),
+                                            self.status.data_ptr(), self._glue_ws.data_ptr(), self._glue_ws.numel(), _stream()))
+        if not defer_status:
+            _cabi.check(int(self.status.item()))      # ELONE_ORPHAN -> IndexError, like the reference
 
     def combine_adjacent(self) -> None:
         ts = self.struct()
@@ -338,8 +418,7 @@ class RunLengthEncoder:
         ts = self.table.struct()
         _cabi.check(_cabi.lib().cutdet_rle_finish(self.state.data_ptr(), C.byref(ts), self.table.n_runs.data_ptr(),
                                                   _stream()))
-        n = C.c_int64()
-        _cabi.check(_cabi.lib().cutdet_rle_count(self.state.data_ptr(), C.byref(n), _stream()))
+        # no synchronisation here: a table that overflowed reports n_runs > capacity, which count() / to_te() raise on
         return self.table
 
 

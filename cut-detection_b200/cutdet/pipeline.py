@@ -51,13 +51,20 @@ class FramePipeline:
         """Frames already in HBM: uint8 BGR HWC [n, rows, w, 3]."""
         self._score(frames, compact)
 
-    def push_host(self, frames: torch.Tensor) -> None:
-        """Decoded frames in (pinned) host memory, uint8 BGR HWC [n, h, w, 3]: upload the needed rows, then score."""
+    def push_host(self, frames: torch.Tensor, compact: bool = False) -> torch.cuda.Event:
+        """Decoded frames in host memory, uint8 BGR HWC [n, h, w, 3] (``compact``: [n, len(plan.rows), w, 3], only the source
+        rows the resize reads, as the decode workers store them): upload the needed rows, then score.
+
+        OWNERSHIP OF THE HOST BUFFER.  From PINNED memory the copy is asynchronous: the call returns as soon as it is queued and
+        the buffer must stay untouched until the returned event has completed (``event.synchronize()`` / ``event.query()``, or
+        ``wait_uploaded()`` for the most recent call) -- a decode loop that refills the buffer earlier overwrites frames still
+        in flight.  From pageable memory the driver stages the copy, and the call returns only after the buffer has been read."""
         if frames.is_cuda or frames.dtype != torch.uint8 or frames.dim() != 4:
             raise ValueError("push_host takes a uint8 [n, h, w, 3] host tensor")
         n = frames.shape[0]
-        if tuple(frames.shape[1:]) != (self.plan.src_h, self.plan.src_w, 3) or frames.stride(3) != 1 or frames.stride(2) != 3:
-            raise ValueError(f"host frames must be dense [{self.plan.src_h}, {self.plan.src_w}, 3] rows")
+        rows_in = len(self.plan.rows) if compact else self.plan.src_h
+        if tuple(frames.shape[1:]) != (rows_in, self.plan.src_w, 3) or frames.stride(3) != 1 or frames.stride(2) != 3:
+            raise ValueError(f"host frames must be dense [{rows_in}, {self.plan.src_w}, 3] rows")
         if self._stage is None:
             shape = (self.max_chunk, len(self.plan.rows), self.plan.src_w, 3)
             self._stage = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
@@ -68,18 +75,32 @@ class FramePipeline:
         compute = torch.cuda.current_stream()
         if self._stage_events[slot] is not None:
             self._copy_stream.wait_event(self._stage_events[slot])      # kernels that read this buffer are done
-        copied = C.c_int64()
-        _cabi.check(_cabi.lib().cutdet_upload_frames(self.plan.handle, frames.data_ptr(), n, frames.stride(0), frames.stride(1),
-                                                     self._stage[slot].data_ptr(), self._copy_stream.cuda_stream,
-                                                     C.byref(copied)))
-        self.h2d_bytes += copied.value
+        if compact:         # already row-compacted on the host: one contiguous copy
+            with torch.cuda.stream(self._copy_stream):
+                self._stage[slot][:n].copy_(frames, non_blocking=True)
+            self.h2d_bytes += frames.numel()
+        else:
+            copied = C.c_int64()
+            _cabi.check(_cabi.lib().cutdet_upload_frames(self.plan.handle, frames.data_ptr(), n, frames.stride(0), frames.stride(1),
+                                                         self._stage[slot].data_ptr(), self._copy_stream.cuda_stream,
+                                                         C.byref(copied)))
+            self.h2d_bytes += copied.value
         uploaded = torch.cuda.Event()
         uploaded.record(self._copy_stream)
+        self._last_upload = uploaded
+        if not frames.is_pinned():
+            uploaded.synchronize()          # pageable source: never leave a copy in flight behind the caller's back
         compute.wait_event(uploaded)
         self._score(self._stage[slot][:n], True)
         done = torch.cuda.Event()
         done.record(compute)
         self._stage_events[slot] = done
+        return uploaded
+
+    def wait_uploaded(self) -> None:
+        """Block until the host buffer of the most recent push_host() has been read (it may then be refilled)."""
+        if getattr(self, "_last_upload", None) is not None:
+            self._last_upload.synchronize()
 
     # ------------------------------------------------------------------ end of the range
     def finish(self) -> engine.DeviceRunTable:
@@ -93,7 +114,8 @@ class FramePipeline:
 
 
 def smooth(table: engine.DeviceRunTable, real_threshold: int = 100, blank_threshold: int = 10) -> engine.DeviceRunTable:
-    """K6 on a finished table: glue_orphans then combine_adjacent_segments (segment_video.py:64-66)."""
-    table.glue_orphans(real_threshold, blank_threshold)
+    """K6 on a finished table: glue_orphans then combine_adjacent_segments (segment_video.py:64-66).  Queued without a host
+    synchronisation: a lone-orphan run (the reference's IndexError) is raised by the table's next count() / to_te()."""
+    table.glue_orphans(real_threshold, blank_threshold, defer_status=True)
     table.combine_adjacent()
     return table

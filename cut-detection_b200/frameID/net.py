@@ -30,9 +30,41 @@ from cutdet import engine as _engine
 package_directory = os.path.dirname(os.path.abspath(__file__))
 
 
-class CNNLayer(nn.Module):
-    """conv3x3 -> activation -> max-pool -> batch-norm (in that order; reference net.py:33-40).
-    Parameter container: the fused kernel for the whole layer is launched by FrameConvNet."""
+def _weights_of(module: nn.Module, prefix: str) -> dict:
+    return {prefix + k: v.detach().to("cpu", torch.float32).numpy()
+            for k, v in module.state_dict().items() if not k.endswith("num_batches_tracked")}
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+class _LayerBacked(nn.Module):
+    """A single layer run on its own: a one-layer native net, rebuilt when the parameters change."""
+
+    def _layer_weights(self):   # -> weights dict in NativeNet's key layout
+        raise NotImplementedError
+
+    def _native_layer(self) -> _engine.NativeNet:
+        fp = tuple((id(p), p._version, p.data_ptr()) for p in list(self.parameters()) + list(self.buffers()))
+        cache = self.__dict__.get("_native_cache")
+        if cache is None or cache[0] != fp:
+            cache = (fp, _engine.NativeNet(self._layer_weights(), 1))
+            self.__dict__["_native_cache"] = cache
+        return cache[1]
+
+    def _bn_mode(self) -> int:
+        if not self.batch_norm:
+            return 0
+        return 2 if self.training else 1
+
+
+class CNNLayer(_LayerBacked):
+    """conv3x3 -> activation -> max-pool -> batch-norm (in that order; reference net.py:33-40).  Inside a FrameConvNet the whole
+    trunk is launched by the enclosing module (tensor-core kernels); called on its own, the layer runs the float32 kernel
+    ``cutdet_net_forward_conv_layer`` -- for the one shape of layer the reference's networks are made of: k3 / stride 1 /
+    padding 1 convolution, ReLU, MaxPool2d(3).  Other arguments are accepted by the constructor (the parameters load and save
+    as in the reference) and refused by ``forward``."""
 
     def __init__(self, conv_args: dict, max_pool_args: dict, activation=nn.ReLU, batch_norm=True):
         super().__init__()
@@ -42,12 +74,38 @@ class CNNLayer(nn.Module):
         self.max_pool = nn.MaxPool2d(**max_pool_args)
         self.bn = nn.BatchNorm2d(conv_args["out_channels"]) if batch_norm else nn.Identity()
 
+    def _check_shape(self):
+        c, p = self.conv, self.max_pool
+        ok = (_pair(c.kernel_size) == (3, 3) and _pair(c.stride) == (1, 1) and _pair(c.padding) == (1, 1) and
+              _pair(c.dilation) == (1, 1) and c.groups == 1 and c.bias is not None and c.padding_mode == "zeros" and
+              _pair(p.kernel_size) == (3, 3) and _pair(p.stride if p.stride is not None else p.kernel_size) == (3, 3) and
+              _pair(p.padding) == (0, 0) and _pair(p.dilation) == (1, 1) and not p.ceil_mode and
+              isinstance(self.activation, nn.ReLU))
+        if not ok:
+            raise NotImplementedError("the native kernels implement conv3x3(stride 1, padding 1) -> ReLU -> MaxPool2d(3) -> "
+                                      "BatchNorm2d, the only layer shape FrameConvNet builds (reference net.py:91-120)")
+
+    def _layer_weights(self):
+        w = {"conv.conv_layers.0.conv.weight": self.conv.weight, "conv.conv_layers.0.conv.bias": self.conv.bias}
+        n = self.conv.out_channels
+        if self.batch_norm:
+            w.update({"conv.conv_layers.0.bn.weight": self.bn.weight, "conv.conv_layers.0.bn.bias": self.bn.bias,
+                      "conv.conv_layers.0.bn.running_mean": self.bn.running_mean,
+                      "conv.conv_layers.0.bn.running_var": self.bn.running_var})
+        else:
+            w.update({"conv.conv_layers.0.bn.weight": torch.ones(n), "conv.conv_layers.0.bn.bias": torch.zeros(n),
+                      "conv.conv_layers.0.bn.running_mean": torch.zeros(n), "conv.conv_layers.0.bn.running_var": torch.ones(n)})
+        return {k: v.detach().to("cpu", torch.float32).numpy() for k, v in w.items()}
+
     def forward(self, x):
-        raise NotImplementedError("CNNLayer is a parameter container here; call the enclosing FrameConvNet")
+        """float32 [B, Cin, H, W] on the GPU -> [B, Cout, H//3, W//3]."""
+        self._check_shape()
+        return self._native_layer().forward_conv_layer(0, x, self._bn_mode())
 
 
-class FCLayer(nn.Module):
-    """linear -> activation -> batch-norm (reference net.py:62-68).  Parameter container."""
+class FCLayer(_LayerBacked):
+    """linear -> activation -> batch-norm (reference net.py:62-68).  Inside a FrameLinearNet the enclosing module launches the
+    head; called on its own the layer runs ``cutdet_net_forward_fc_layer`` (activation ReLU or Identity)."""
 
     def __init__(self, linear_args: dict, activation=nn.ReLU, batch_norm=True):
         super().__init__()
@@ -56,17 +114,32 @@ class FCLayer(nn.Module):
         self.activation = activation()
         self.bn = nn.BatchNorm1d(linear_args["out_features"]) if batch_norm else nn.Identity()
 
+    def _layer_weights(self):
+        if self.linear.bias is None:
+            raise NotImplementedError("the native FC kernel expects a bias (nn.Linear default, as FrameLinearNet builds it)")
+        w = {"linear.layers.0.linear.weight": self.linear.weight, "linear.layers.0.linear.bias": self.linear.bias}
+        if self.batch_norm:
+            w.update({"linear.layers.0.bn.weight": self.bn.weight, "linear.layers.0.bn.bias": self.bn.bias,
+                      "linear.layers.0.bn.running_mean": self.bn.running_mean,
+                      "linear.layers.0.bn.running_var": self.bn.running_var})
+        return {k: v.detach().to("cpu", torch.float32).numpy() for k, v in w.items()}
+
     def forward(self, x):
-        raise NotImplementedError("FCLayer is a parameter container here; call the enclosing FrameLinearNet")
-
-
-def _weights_of(module: nn.Module, prefix: str) -> dict:
-    return {prefix + k: v.detach().to("cpu", torch.float32).numpy()
-            for k, v in module.state_dict().items() if not k.endswith("num_batches_tracked")}
+        """float32 [B, in_features] on the GPU -> [B, out_features]."""
+        if isinstance(self.activation, nn.ReLU):
+            relu = True
+        elif isinstance(self.activation, nn.Identity):
+            relu = False
+        else:
+            raise NotImplementedError("the native FC kernel implements ReLU and Identity activations (reference net.py:164-178)")
+        return self._native_layer().forward_fc_layer(0, x, relu, self._bn_mode())
 
 
 class _NativeBacked(nn.Module):
     """Builds (and caches) the native net for the module's current parameters."""
+
+    # options applied to the native net whenever it is (re)built: see engine.NativeNet.set_option
+    native_options: dict = {}
 
     # training-mode forward: tcgen05 kernels + batch-statistics kernels where the tensor-core path applies (batches of up to 148
     # frames); False keeps the float32 CUDA-core kernels everywhere
@@ -83,7 +156,10 @@ class _NativeBacked(nn.Module):
         cache = self.__dict__.get("_native_cache")
         if cache is None or cache[0] != fp:
             weights, pool = self._native_parts()
-            cache = (fp, _engine.NativeNet(weights, pool))
+            native = _engine.NativeNet(weights, pool)
+            for name, value in self.native_options.items():
+                native.set_option(name, value)
+            cache = (fp, native)
             self.__dict__["_native_cache"] = cache
         return cache[1]
 
@@ -94,6 +170,11 @@ class _NativeBacked(nn.Module):
         if self.training:
             return self._native().forward_f32_batchstats(x, tensor_cores=self.batchstats_tensor_cores)
         return self._native().forward_f32(x)
+
+    def set_native_option(self, name: str, value: int) -> None:
+        """E.g. ``net.set_native_option("conv1_acc32", 1)``: layer 1 of the fused frames kernel accumulates in fp32."""
+        self.native_options = dict(self.native_options, **{name: int(value)})
+        self.__dict__.pop("_native_cache", None)
 
     def num_params(self):
         return sum(p.numel() for p in self.parameters() if p.requires_grad)

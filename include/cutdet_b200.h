@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CUTDET_ABI_VERSION 1
+#define CUTDET_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CUTDET_API __attribute__((visibility("default")))
@@ -137,6 +137,19 @@ CUTDET_API int cutdet_net_finalize(cutdet_net *net);
  * CUDA-core kernels run instead).                                                                   */
 CUTDET_API int cutdet_net_uses_tensor_cores(const cutdet_net *net, int height, int width);
 
+/* Switches of the tensor-core path, per net (the library reads nothing from the environment).  They change how the
+ * work is scheduled or which accumulator precision layer 1 uses, never what is computed; the workspace size depends on
+ * SUB_BATCH / GROUP_FRAMES, so set them before asking for it.                                                       */
+enum {
+    CUTDET_OPT_CONV1_ACC32 = 1,  /* fused frames kernel: fp32 accumulators in layer 1 (default 0: fp16 accumulators)    */
+    CUTDET_OPT_SUB_BATCH = 2,    /* frames per conv1/conv2 pass (default 0 = one frame per SM of a B200: 148)           */
+    CUTDET_OPT_GROUP_FRAMES = 3, /* frames gathered for one conv3 launch (default 0 = 1184)                             */
+    CUTDET_OPT_NO_PDL = 4,       /* 1: ordinary launches instead of programmatic dependent launch                       */
+    CUTDET_OPT_CONV1_GRID = 5    /* test hook: cap on the fused conv1 grid (several frames per CTA); 0 = no cap         */
+};
+CUTDET_API int cutdet_net_set_option(cutdet_net *net, int option, int value);
+CUTDET_API int cutdet_net_get_option(const cutdet_net *net, int option, int *value);
+
 /* Bytes of device scratch the forward pass needs for `batch` inputs of height x width. */
 CUTDET_API int cutdet_net_workspace_bytes(const cutdet_net *net, int batch, int height, int width, size_t *bytes);
 
@@ -158,6 +171,22 @@ CUTDET_API int cutdet_net_forward_f32_batchstats(cutdet_net *net, const float *x
 CUTDET_API int cutdet_net_forward_frames(cutdet_net *net, const cutdet_resize_plan *plan, const cutdet_frames *src,
                               float *logits_dev, void *workspace_dev, size_t workspace_bytes,
                               cutdet_stream_t stream);
+/* ONE layer of a finalized net, float32 CUDA-core kernels (the per-layer modules of the reference are callable on
+ * their own):
+ *   CNNLayer.forward, frameID/net.py:33-40   x [B,Cin,H,W] -> conv3x3(p1) -> ReLU -> MaxPool(3) -> BatchNorm -> [B,Cout,H/3,W/3]
+ *   FCLayer.forward,  frameID/net.py:62-68   x [B,in] -> Linear -> (ReLU if relu) -> BatchNorm1d -> [B,out]
+ * bn_mode: 0 = no BatchNorm (nn.Identity), 1 = running statistics (.eval()), 2 = statistics of this batch (training
+ * mode, forward only).  A lone FCLayer with a BatchNorm is a one-layer FC-only net whose layer was given BN parameters. */
+CUTDET_API int cutdet_net_forward_conv_layer(cutdet_net *net, int layer, const float *x_nchw_dev, int batch, int height,
+                                  int width, float *out_nchw_dev, int bn_mode, cutdet_stream_t stream);
+CUTDET_API int cutdet_net_forward_fc_layer(cutdet_net *net, int layer, const float *x_dev, int batch, float *out_dev,
+                                int relu, int bn_mode, cutdet_stream_t stream);
+
+/* Debug aid (tools/timeline.py): while armed (kernel 1 = conv1_fused_tc, 2 = conv2_tc; 0 or a null buffer disarms), CTA 0 of
+ * every full sub-batch launch of that kernel writes clock stamps into the caller's device buffer of >= 2048 int64 entries.
+ * The library allocates, copies and synchronises nothing for it.                                                          */
+CUTDET_API int cutdet_net_debug_timeline(cutdet_net *net, int kernel, long long *stamps_dev, size_t n_entries);
+
 /* Intermediate activations of the last forward, converted to float32 NCHW (test hook):
  * layer in [0, n_conv_layers) is the output of that CNNLayer.                                         */
 CUTDET_API int cutdet_net_debug_conv_output(cutdet_net *net, int layer, int batch, int height, int width,
@@ -219,9 +248,15 @@ CUTDET_API int cutdet_rle_count(const void *state_dev, int64_t *n_runs_host, cut
 /* In place on the first *n_runs_dev rows of `table` (start/end/length/type/mean columns; sums untouched);
  * *n_runs_dev is updated.  *status_dev (device int32) receives CUTDET_OK or CUTDET_ELONE_ORPHAN.
  * Exact ties between orphan means are broken towards the lowest run index (the reference's
- * torch.argsort is unstable, so its tie order is unspecified).                                         */
+ * torch.argsort is unstable, so its tie order is unspecified); a NaN mean sorts after every number,
+ * as torch.argsort places it.
+ * workspace_dev: cutdet_glue_orphans_workspace_bytes(table->capacity) bytes of device scratch, 16-byte
+ * aligned, owned by the caller and private to this call until `stream` has run it (the library keeps
+ * no state of its own: calls on different streams or devices need different workspaces).              */
+CUTDET_API size_t cutdet_glue_orphans_workspace_bytes(int64_t capacity);
 CUTDET_API int cutdet_glue_orphans(const cutdet_run_table *table, int64_t *n_runs_dev, int real_threshold,
-                        int blank_threshold, int32_t *status_dev, cutdet_stream_t stream);
+                        int blank_threshold, int32_t *status_dev, void *workspace_dev, size_t workspace_bytes,
+                        cutdet_stream_t stream);
 CUTDET_API int cutdet_combine_adjacent(const cutdet_run_table *table, int64_t *n_runs_dev, cutdet_stream_t stream);
 
 /* Joins the run tables of consecutive shards (time ranges) into one: `src` holds `n_shards` tables
@@ -232,6 +267,20 @@ CUTDET_API int cutdet_combine_adjacent(const cutdet_run_table *table, int64_t *n
 CUTDET_API int cutdet_stitch_shards(const cutdet_run_table *src, int n_shards, int64_t shard_capacity,
                          const int64_t *n_runs_dev, const int64_t *frame_offsets_dev,
                          const cutdet_run_table *dst, int64_t *n_runs_out_dev, cutdet_stream_t stream);
+
+/* The exchange step of the multi-GPU path in two launches around ONE all-gather (the reference is
+ * single-process).  cutdet_shard_pack writes this shard's table into a fixed-size packed buffer of
+ * cutdet_shard_pack_bytes(capacity) bytes: {int64 n_runs, int64 n_frames} then `capacity` rows of 40 bytes {int64 end, start,
+ * length; float64 sum; int32 type; float32 mean} with LOCAL frame numbers.  After the all-gather (ncclAllGather of equal-size
+ * buffers, rank order = time order) cutdet_stitch_packed reads the gathered buffer as it is -- run counts and frame offsets
+ * come from the headers, on the device -- and writes the joined table with global frame numbers.  No host synchronisation on
+ * either side.  *n_runs_out_dev: the joined run count; > dst->capacity if rows were dropped; -(1 + k) if some shard had
+ * k > capacity runs (nothing useful was written: gather again with a larger capacity).                                      */
+CUTDET_API size_t cutdet_shard_pack_bytes(int64_t capacity);
+CUTDET_API int cutdet_shard_pack(const cutdet_run_table *table, const int64_t *n_runs_dev, int64_t n_frames, int64_t capacity,
+                      void *packed_dev, cutdet_stream_t stream);
+CUTDET_API int cutdet_stitch_packed(const void *gathered_dev, int n_shards, int64_t capacity, const cutdet_run_table *dst,
+                         int64_t *n_runs_out_dev, int64_t *total_frames_out_dev, cutdet_stream_t stream);
 
 #ifdef __cplusplus
 }

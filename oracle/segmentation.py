@@ -123,7 +123,8 @@ def glue_orphans(te: dict, real_threshold: int = 100, blank_threshold: int = 10)
         orphans = [i for i in range(len(r.start)) if r.is_orphan(i, real_threshold, blank_threshold)]
         if not orphans:
             break
-        target = min(orphans, key=lambda i: (r.mean[i], i))   # least confident, lowest index on ties
+        # least confident, lowest index on ties; a NaN mean sorts after every number, where torch.argsort puts it
+        target = min(orphans, key=lambda i: (bool(np.isnan(r.mean[i])), r.mean[i], i))
         last = len(r.start) - 1
         if target == 0:
             if last == 0:

@@ -42,7 +42,7 @@ def test_every_declaration_cites_the_reference():
 
 def test_no_gpu_calls_needed_for_host_helpers(handle):
     handle.cutdet_abi_version.restype = ctypes.c_int
-    assert handle.cutdet_abi_version() == 1
+    assert handle.cutdet_abi_version() == 2
     nw, nh = ctypes.c_int(), ctypes.c_int()
     assert handle.cutdet_target_size(1280, 720, 256, ctypes.byref(nw), ctypes.byref(nh)) == 0
     assert (nw.value, nh.value) == (256, 144)
@@ -72,7 +72,20 @@ def test_missing_library_fails_loudly(tmp_path):
     code = ("import sys; sys.path.insert(0, %r)\n"
             "from cutdet import _cabi, build\n"
             "build.LIB_PATH = %r\n"
+            "build.find_nvcc = lambda: None\n"
             "try:\n    _cabi.lib()\nexcept RuntimeError as e:\n    print('RAISED', e)\n") % (
         os.path.join(ROOT, "cut-detection_b200"), str(tmp_path / "nope.so"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert "RAISED" in out.stdout and "no fallback" in out.stdout
+
+
+def test_stale_library_is_not_loaded(tmp_path):
+    """A library older than the sources next to it is rebuilt (nvcc here) or refused (no nvcc), never run."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from cutdet import _cabi, build\n"
+            "build.STAMP_PATH = %r\n"
+            "build.find_nvcc = lambda: None\n"
+            "try:\n    _cabi.lib()\nexcept RuntimeError as e:\n    print('RAISED', e)\n") % (
+        os.path.join(ROOT, "cut-detection_b200"), str(tmp_path / "no_stamp.txt"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "RAISED" in out.stdout and "older than the sources" in out.stdout

@@ -22,9 +22,9 @@ from oracle import preprocess as opre
 pytestmark = pytest.mark.gpu
 
 TOL_TC, TOL_F32, TOL_EMU = 0.05, 2e-3, 5e-3
-# fused frames kernel against the unfused float entry: same taps and pixels.  With fp32 accumulators (CUTDET_CONV1_ACC32) the sums
-# differ in rounding only (observed <= 3e-4); the default fp16 accumulators round once per kernel row (emulation: <= 8e-3)
-FUSED_TOL = 2e-3 if "CUTDET_CONV1_ACC32" in os.environ else 2e-2
+# fused frames kernel against the unfused float entry: same taps and pixels.  With fp32 accumulators (net option conv1_acc32) the
+# sums differ in rounding only (observed <= 3e-4); the default fp16 accumulators round once per kernel row (emulation: <= 8e-3)
+FUSED_TOL, FUSED_TOL_ACC32 = 2e-2, 2e-3
 MARGIN = 0.1
 
 
@@ -113,10 +113,19 @@ def test_matches_16bit_emulation(native, prod_weights):
         h, ww = frame.shape[:2]
         plan = engine.ResizePlan.for_video(h, ww, 256)
         got = net.forward_frames(plan, torch.from_numpy(frame[None]).cuda()).cpu().numpy()
-        # the fused frames kernel accumulates layer 1 in fp16 unless CUTDET_CONV1_ACC32 is set (csrc/conv_tc.cu launch_conv1_fused)
-        want = onet.forward_tc_emulated(w, opre.preprocess_frame(frame)[None], params["avg_pool_size"],
-                                        conv1_acc16="CUTDET_CONV1_ACC32" not in os.environ)
+        # the fused frames kernel accumulates layer 1 in fp16 unless the net option conv1_acc32 is set (csrc/conv_tc.cu launch_conv1_fused)
+        want = onet.forward_tc_emulated(w, opre.preprocess_frame(frame)[None], params["avg_pool_size"], conv1_acc16=True)
         assert np.abs(got - want).max() <= TOL_EMU, name
+    net.set_option("conv1_acc32", 1)
+    try:
+        for name, frame in kat_inputs.kat_frames().items():
+            h, ww = frame.shape[:2]
+            plan = engine.ResizePlan.for_video(h, ww, 256)
+            got = net.forward_frames(plan, torch.from_numpy(frame[None]).cuda()).cpu().numpy()
+            want = onet.forward_tc_emulated(w, opre.preprocess_frame(frame)[None], params["avg_pool_size"], conv1_acc16=False)
+            assert np.abs(got - want).max() <= TOL_EMU, name
+    finally:
+        net.set_option("conv1_acc32", 0)
 
 
 def test_empty_batch(native):
@@ -168,7 +177,7 @@ def test_frames_path_with_32_channels():
         got = net.forward_frames(plan, torch.from_numpy(frames).cuda()).cpu().numpy()
         x = np.stack([opre.preprocess_frame(f) for f in frames[:4]])
         want = onet.forward_f32(wts, x, 1)
-        emu = onet.forward_tc_emulated(wts, x, 1, conv1_acc16="CUTDET_CONV1_ACC32" not in os.environ)
+        emu = onet.forward_tc_emulated(wts, x, 1, conv1_acc16=True)
         assert got.shape == (batch, 8)
         assert np.abs(got[:4] - want).max() <= TOL_TC, (h, np.abs(got[:4] - want).max())
         assert np.abs(got[:4] - emu).max() <= TOL_EMU, (h, np.abs(got[:4] - emu).max())
@@ -228,62 +237,162 @@ def test_fused_frames_equal_unfused(native, h, w, batch, compact):
     assert float(np.abs(got - want).max()) <= FUSED_TOL, float(np.abs(got - want).max())
 
 
-def test_fused_kernel_with_several_frames_per_cta():
-    """On B200 a sub-batch has as many frames as the GPU has SMs, so conv1_fused_tc walks ONE frame per CTA.  The kernel is written
-    for any number (frames follow each other in the flattened position space, with one zero row between them): cap its grid
-    through the CUTDET_CONV1_GRID test hook -- 37 CTAs, up to 4 frames each -- in a fresh process and compare with the float path."""
-    import subprocess, sys, textwrap
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = textwrap.dedent("""
-        import sys, numpy as np, torch
-        sys.path[:0] = [%r, %r]
-        from cutdet import engine
-        from frameID.net import load_default_net
-        net, _ = load_default_net()
-        net.eval().to("cuda")
-        worst = 0.0
-        for (h, w, batch) in ((720, 1280, 301), (1080, 1920, 75), (360, 640, 140)):
-            rng = np.random.default_rng(h + batch)
+def test_fp32_accumulator_option(native):
+    """net option conv1_acc32: the fused kernel's fp32-accumulator variant agrees with the unfused float entry to rounding."""
+    from cutdet import engine
+    net, _ = native
+    rng = np.random.default_rng(5)
+    net.set_option("conv1_acc32", 1)
+    try:
+        assert net.get_option("conv1_acc32") == 1
+        for h, w, batch in ((720, 1280, 150), (1080, 1920, 9), (360, 640, 33)):
             frames = torch.from_numpy(rng.integers(0, 256, (batch, h, w, 3), dtype=np.uint8)).cuda()
             plan = engine.ResizePlan.for_video(h, w, 256)
-            want = net(engine.preprocess_f32(plan, frames)).cpu().numpy()
+            want = net.forward_f32(engine.preprocess_f32(plan, frames)).cpu().numpy()
             got = net.forward_frames(plan, frames).cpu().numpy()
-            worst = max(worst, float(np.abs(got - want).max()))
-        print("WORST", worst)
-        assert worst <= %r, worst
-    """) % (root, os.path.join(root, "cut-detection_b200"), FUSED_TOL)
-    env = dict(os.environ, CUTDET_CONV1_GRID="37")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            assert float(np.abs(got - want).max()) <= FUSED_TOL_ACC32
+    finally:
+        net.set_option("conv1_acc32", 0)
 
 
-def test_dependent_launch_changes_nothing():
+def test_fused_kernel_with_several_frames_per_cta(prod_weights):
+    """On B200 a sub-batch has as many frames as the GPU has SMs, so conv1_fused_tc walks ONE frame per CTA.  The kernel is written
+    for any number (frames follow each other in the flattened position space, with one zero row between them): cap its grid
+    through the conv1_grid test option -- 37 CTAs, up to 4 frames each -- and compare with the float path."""
+    from cutdet import engine
+    wts, params = prod_weights
+    net = engine.NativeNet(wts, params["avg_pool_size"])
+    net.set_option("conv1_grid", 37)
+    worst = 0.0
+    for (h, w, batch) in ((720, 1280, 301), (1080, 1920, 75), (360, 640, 140)):
+        rng = np.random.default_rng(h + batch)
+        frames = torch.from_numpy(rng.integers(0, 256, (batch, h, w, 3), dtype=np.uint8)).cuda()
+        plan = engine.ResizePlan.for_video(h, w, 256)
+        want = net.forward_f32(engine.preprocess_f32(plan, frames)).cpu().numpy()
+        got = net.forward_frames(plan, frames).cpu().numpy()
+        worst = max(worst, float(np.abs(got - want).max()))
+    assert worst <= FUSED_TOL, worst
+
+
+def test_dependent_launch_changes_nothing(prod_weights):
     """conv1/conv2/conv3 are launched with programmatic stream serialization (csrc/conv_tc.cu launch_pdl): a kernel's set-up runs
     while the previous one drains and griddepcontrol.wait orders the dependent accesses.  The logits must be bit-identical to
-    those of ordinary launches (CUTDET_NO_PDL=1, a fresh process), over several sub-batches and repeated calls."""
-    import subprocess, sys, textwrap
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = textwrap.dedent("""
-        import sys, hashlib, numpy as np, torch
-        sys.path[:0] = [%r, %r]
-        from cutdet import engine
-        from frameID.net import load_default_net
-        net, _ = load_default_net()
-        net.eval().to("cuda")
-        h = hashlib.sha256()
-        for (hh, ww, batch) in ((720, 1280, 700), (1080, 1920, 310), (360, 640, 450)):
-            rng = np.random.default_rng(hh + batch)
-            frames = torch.from_numpy(rng.integers(0, 256, (batch, hh, ww, 3), dtype=np.uint8)).cuda()
-            plan = engine.ResizePlan.for_video(hh, ww, 256)
+    those of ordinary launches (net option no_pdl), over several sub-batches and repeated calls; the same holds for other
+    sub-batch sizes (net option sub_batch: a scheduling switch, never a numerical one)."""
+    from cutdet import engine
+    wts, params = prod_weights
+    nets = {}
+    for name, opts in (("pdl", {}), ("no_pdl", {"no_pdl": 1}), ("sub74", {"sub_batch": 74}), ("sub296", {"sub_batch": 296, "group_frames": 592})):
+        nets[name] = engine.NativeNet(wts, params["avg_pool_size"])
+        for k, v in opts.items():
+            nets[name].set_option(k, v)
+    for (hh, ww, batch) in ((720, 1280, 700), (1080, 1920, 310), (360, 640, 450)):
+        rng = np.random.default_rng(hh + batch)
+        frames = torch.from_numpy(rng.integers(0, 256, (batch, hh, ww, 3), dtype=np.uint8)).cuda()
+        plan = engine.ResizePlan.for_video(hh, ww, 256)
+        want = nets["pdl"].forward_frames(plan, frames).cpu().numpy()
+        for name, net in nets.items():
             for _ in range(3):
-                h.update(net.forward_frames(plan, frames).cpu().numpy().tobytes())
-        print("DIGEST", h.hexdigest())
-    """) % (root, os.path.join(root, "cut-detection_b200"))
-    digests = []
-    for extra in ({}, {"CUTDET_NO_PDL": "1"}):
-        env = dict(os.environ, **extra)
-        env.pop("CUTDET_NO_PDL", None) if not extra else None
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-        digests.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0])
-    assert digests[0] == digests[1]
+                got = net.forward_frames(plan, frames).cpu().numpy()
+                assert np.array_equal(got, want), (name, hh, float(np.abs(got - want).max()))
+
+
+def test_single_layer_forward(prod_weights):
+    """CNNLayer.forward / FCLayer.forward of the mirror (reference frameID/net.py:33-40, 62-68) on their own: float32 kernels
+    against the oracle's layer functions, eval and training mode, with and without BatchNorm."""
+    import torch.nn as nn
+    from frameID.net import CNNLayer, FCLayer
+    wts, params = prod_weights
+    torch.manual_seed(3)
+    x = torch.rand(5, 3, 31, 47)
+    for batch_norm in (True, False):
+        layer = CNNLayer({"in_channels": 3, "out_channels": 10, "kernel_size": 3, "padding": 1}, {"kernel_size": 3}, nn.ReLU, batch_norm)
+        if batch_norm:
+            with torch.no_grad():
+                layer.bn.running_mean.uniform_(-0.5, 0.5); layer.bn.running_var.uniform_(0.5, 2.0)
+                layer.bn.weight.uniform_(-1, 1); layer.bn.bias.uniform_(-1, 1)
+        for training in (False, True):
+            layer.train(training)
+            z = torch.nn.functional.max_pool2d(torch.relu(torch.nn.functional.conv2d(x, layer.conv.weight, layer.conv.bias, padding=1)), 3)
+            if batch_norm:
+                z = torch.nn.functional.batch_norm(z, layer.bn.running_mean.clone(), layer.bn.running_var.clone(), layer.bn.weight,
+                                                   layer.bn.bias, training=training, eps=1e-5)
+            got = layer(x.cuda()).cpu()
+            assert got.shape == z.shape and float((got - z.detach()).abs().max()) <= 2e-4, (batch_norm, training)
+    with pytest.raises(NotImplementedError):
+        CNNLayer({"in_channels": 3, "out_channels": 4, "kernel_size": 5, "padding": 2}, {"kernel_size": 3})(x.cuda())
+    v = torch.randn(9, 20)
+    for batch_norm, act in ((True, nn.ReLU), (False, nn.Identity), (False, nn.ReLU)):
+        layer = FCLayer({"in_features": 20, "out_features": 7}, act, batch_norm)
+        if batch_norm:
+            with torch.no_grad():
+                layer.bn.running_mean.uniform_(-0.5, 0.5); layer.bn.running_var.uniform_(0.5, 2.0)
+                layer.bn.weight.uniform_(-1, 1); layer.bn.bias.uniform_(-1, 1)
+        for training in (False, True):
+            layer.train(training)
+            z = torch.nn.functional.linear(v, layer.linear.weight, layer.linear.bias)
+            if act is nn.ReLU:
+                z = torch.relu(z)
+            if batch_norm:
+                z = torch.nn.functional.batch_norm(z, layer.bn.running_mean.clone(), layer.bn.running_var.clone(), layer.bn.weight,
+                                                   layer.bn.bias, training=training, eps=1e-5)
+            got = layer(v.cuda()).cpu()
+            assert float((got - z.detach()).abs().max()) <= 1e-4, (batch_norm, training)
+
+
+@pytest.mark.parametrize("h,w", [(720, 1280), (1080, 1920)])
+def test_fp16_accumulator_statistics(native, prod_weights, h, w):
+    """The default frames path (fp16 operands, fp16 accumulators in layer 1) against the fp32 oracle on 512 frames per
+    resolution that are NOT the synthetic stripe clips: uniform noise, noise x 0.1 (dark), flat mid-grey (the class with the
+    weakest margin), stripes under heavy noise, and smooth gradients.  Stated bar (BASELINE north_star):
+    |dlogit| <= 0.1 everywhere (the kernels' own bar, 0.05, is asserted too), no argmax flip where the oracle's top-2 margin
+    is >= 0.2; the statistics are printed for the record (pytest -s)."""
+    from cutdet import engine
+    net, params = native
+    if not net.uses_tensor_cores(144, 256):
+        pytest.skip("generic float32 path in use")
+    wts, _ = prod_weights
+    plan = engine.ResizePlan.for_video(h, w, 256)
+    rng = np.random.default_rng(h)
+    n_total, chunk = 512, 64
+    errs, margins, flips_confident, flips_any = [], [], 0, 0
+    yy = (np.arange(h) // max(h // 18, 2)) % 2
+    xx = (np.arange(w) // max(w // 32, 2)) % 2
+    for c0 in range(0, n_total, chunk):
+        frames = np.empty((chunk, h, w, 3), dtype=np.uint8)
+        for i in range(chunk):
+            kind = (c0 + i) % 8
+            noise = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            if kind == 0:
+                f = noise
+            elif kind == 1:
+                f = noise // 10
+            elif kind == 2:
+                f = np.full((h, w, 3), rng.integers(96, 160), dtype=np.uint8)
+            elif kind == 3:
+                f = (np.full((h, w, 3), 128, dtype=np.int16) + (noise.astype(np.int16) - 128) // 8).astype(np.uint8)
+            elif kind == 4:
+                f = ((yy[:, None, None] * 255).astype(np.int16) * 3 // 4 + noise.astype(np.int16) // 4).astype(np.uint8)
+            elif kind == 5:
+                f = ((xx[None, :, None] * 255).astype(np.int16) * 3 // 4 + noise.astype(np.int16) // 4).astype(np.uint8)
+            elif kind == 6:
+                g = np.linspace(0, 255, w)[None, :, None] * rng.uniform(0.2, 1.0, (1, 1, 3)) + np.linspace(0, 60, h)[:, None, None]
+                f = np.clip(g, 0, 255).astype(np.uint8)
+            else:
+                f = np.where(rng.uniform(size=(h, w, 1)) < 0.5, noise, noise // 16).astype(np.uint8)
+            frames[i] = f
+        got = net.forward_frames(plan, torch.from_numpy(frames).cuda()).cpu().numpy()
+        want = onet.forward_f32(wts, opre.preprocess_batch(frames, 256), params["avg_pool_size"])
+        errs.append(np.abs(got - want).max(axis=1))
+        srt = np.sort(want, axis=1)
+        margin = srt[:, -1] - srt[:, -2]
+        margins.append(margin)
+        flip = got.argmax(1) != want.argmax(1)
+        flips_any += int(flip.sum())
+        flips_confident += int((flip & (margin >= 0.2)).sum())
+    errs, margins = np.concatenate(errs), np.concatenate(margins)
+    print(f"\n[acc16 statistics {w}x{h}] frames={n_total} max|dlogit|={errs.max():.4f} mean={errs.mean():.5f} "
+          f"p99={np.quantile(errs, 0.99):.4f} min_margin={margins.min():.3f} frames_with_margin<0.2={int((margins < 0.2).sum())} "
+          f"flips={flips_any} flips_at_margin>=0.2={flips_confident}")
+    assert errs.max() <= TOL_TC, errs.max()
+    assert flips_confident == 0

@@ -187,3 +187,158 @@ def test_stitch_shards_equals_whole():
         out = engine.stitch_shards(big, torch.tensor(counts, dtype=torch.int64, device="cuda"),
                                    torch.tensor(offsets, dtype=torch.int64, device="cuda"), cap)
         _same(_np(out.to_te()), want)
+
+
+def _encode(lab, top, cap=None):
+    from cutdet import engine
+    enc = engine.RunLengthEncoder(cap or max(len(lab), 1), "cuda")
+    if len(lab):
+        enc.append(torch.from_numpy(lab).cuda(), torch.from_numpy(top).cuda())
+    return enc.finish()
+
+
+def test_packed_exchange_equals_whole():
+    """The exchange step as the multi-GPU path runs it, on one device: cutdet_shard_pack per shard (bytes checked against the
+    numpy restatement of the layout, cutdet.shard.pack_columns), the gathered buffer read by cutdet_stitch_packed (offsets and
+    counts from the headers, on the device) == the table of the whole sequence.  Shards of every kind: empty, one frame, cut
+    inside a run and on a run boundary."""
+    from cutdet import shard
+    n = 30_000
+    rng = np.random.default_rng(5)
+    lab = np.repeat(rng.integers(0, 3, n // 61 + 2), 61)[:n].astype(np.uint8)
+    top = rng.uniform(1, 9, n).astype(np.float32)
+    want = oseg.run_table_from_labels(lab, top)
+    for edges in ([0, n], [0, 15_000, n], [0, 61 * 100, 61 * 100 + 1, 20_000, 20_000, n], list(range(0, n, 3_750)) + [n]):
+        tables, counts = [], []
+        for lo, hi in zip(edges, edges[1:]):
+            tables.append(_encode(lab[lo:hi], top[lo:hi]))
+            counts.append(hi - lo)
+        cap = 1024
+        for t, c in zip(tables, counts):
+            packed = shard.pack_table(t, c, cap).cpu()
+            k = t.count()
+            cols = {name: getattr(t, name)[:k].cpu().numpy() for name in
+                    ("end_frames", "start_frames", "run_lengths", "score_sums", "frame_types", "score_means")}
+            ref = shard.pack_columns(cols, k, c, cap)
+            used = shard.HEADER_BYTES + k * shard.ROW_BYTES        # rows past the count are not written by the kernel
+            assert torch.equal(packed[:used], ref[:used])
+        out, total = shard.stitch_local(tables, counts, cap)
+        _same(_np(out.to_te()), want)
+        assert int(total.item()) == n
+
+
+def test_exchange_overflow_is_reported_and_retried():
+    """A shard with more runs than the gather capacity: the stitch kernel reports it through a negative count (ShardOverflow
+    from to_te), and finish_checked repeats the exchange with a capacity that fits."""
+    from cutdet import engine, pipeline, shard
+    n = 6_000
+    lab = (np.arange(n) // 3 % 3).astype(np.uint8)                 # 2,000 runs
+    top = np.linspace(1, 9, n).astype(np.float32)
+    halves = [_encode(lab[:3000], top[:3000]), _encode(lab[3000:], top[3000:])]
+    out, _ = shard.stitch_local(halves, [3000, 3000], 64)
+    with pytest.raises(engine.ShardOverflow) as e:
+        out.to_te()
+    assert e.value.needed == 1000
+    te, total = shard.finish_checked(lambda cap: shard.stitch_local(halves, [3000, 3000], cap), capacity=64)
+    _same(_np(te), oseg.run_table_from_labels(lab, top))
+    assert total == n
+
+
+def test_deferred_status_and_independent_workspaces():
+    """pipeline.smooth queues K6 without a host synchronisation: the lone-orphan IndexError of the reference surfaces at the
+    next to_te().  Two tables smoothed concurrently on two streams own their scratch and do not disturb each other."""
+    from cutdet import engine, pipeline
+    lone = engine.run_table_from_scores(torch.from_numpy(kat_inputs.scores_from_runs([(0, 50)], 13)).cuda())
+    pipeline.smooth(lone, 100, 10)
+    with pytest.raises(IndexError):
+        lone.to_te()
+    cases = []
+    for seed in (0, 1):
+        scores = kat_inputs.scores_from_runs(kat_inputs.random_runs(50 + seed, 1500), 60 + seed)
+        cases.append((engine.run_table_from_scores(torch.from_numpy(scores).cuda()), oseg.segment(scores, 100, 10)[2]))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for _ in range(3):
+        for (table, _), st in zip(cases, streams):
+            with torch.cuda.stream(st):
+                pipeline.smooth(table, 100, 10)
+    torch.cuda.synchronize()
+    for table, want in cases:
+        _same(_np(table.to_te()), want, means_rtol=1e-5)
+
+
+def test_nan_mean_orphans_sort_last():
+    """torch.argsort places NaN after every number: an orphan whose mean is NaN is still glued, after the others
+    (oracle.segmentation.glue_orphans restates that order)."""
+    from cutdet import engine
+    runs = [(0, 300), (1, 20), (0, 150), (2, 4), (1, 200), (0, 30), (1, 400)]
+    scores = kat_inputs.scores_from_runs(runs, 3)
+    te0 = oseg.run_table(scores)
+    te0["score_means"] = te0["score_means"].copy()
+    te0["score_means"][1] = np.nan
+    want = oseg.combine_adjacent(oseg.glue_orphans(te0, 100, 10))
+    t = engine.DeviceRunTable.from_te({k: torch.from_numpy(np.asarray(v)) for k, v in te0.items()}, "cuda")
+    t.glue_orphans(100, 10)
+    t.combine_adjacent()
+    got = _np(t.to_te())
+    for k in INT_COLS:
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(np.isnan(got["score_means"]), np.isnan(want["score_means"]))
+
+
+def _nccl_worker(rank, world, port, n, seed, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from cutdet import engine, pipeline, shard
+        rng = np.random.default_rng(seed)
+        lab = np.repeat(rng.integers(0, 3, n // 53 + 2), 53)[:n].astype(np.uint8)
+        lab[rng.uniform(size=n) < 0.01] = 2
+        top = rng.uniform(1, 9, n).astype(np.float32)
+        lo, hi = shard.shard_range(n, rank, world)
+        enc = engine.RunLengthEncoder(max(hi - lo, 1), f"cuda:{rank}")
+        if hi > lo:
+            enc.append(torch.from_numpy(lab[lo:hi]).cuda(), torch.from_numpy(top[lo:hi]).cuda())
+        table, total = shard.stitch_all(enc.finish(), hi - lo, 1024)
+        raw = table.to_te()
+        pipeline.smooth(table, 100, 10)
+        te = table.to_te()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), total=int(total.item()),
+                 **{"raw_" + k: v.numpy() for k, v in raw.items()}, **{k: v.numpy() for k, v in te.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_nccl_exchange_on_real_ranks(tmp_path, world):
+    """Two processes, one GPU each, NCCL: every rank's stitched and smoothed table == what one process computes over the
+    whole sequence (the contract of the N > 1 path; reference frameID/segmentation.py:35-60, 91-183)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()} (the 1-GPU emulation of the same kernels "
+                    "is test_packed_exchange_equals_whole; bench.py checks the same equality at N = 2/4/8)")
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    n, seed = 200_003, 17
+    mp.spawn(_nccl_worker, args=(world, port, n, seed, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(seed)
+    lab = np.repeat(rng.integers(0, 3, n // 53 + 2), 53)[:n].astype(np.uint8)
+    lab[rng.uniform(size=n) < 0.01] = 2
+    top = rng.uniform(1, 9, n).astype(np.float32)
+    whole = _encode(lab, top)
+    want_raw = _np(whole.to_te())
+    whole.glue_orphans(100, 10)
+    whole.combine_adjacent()
+    want = _np(whole.to_te())
+    for rank in range(world):
+        got = np.load(os.path.join(tmp_path, f"rank{rank}.npz"))
+        assert int(got["total"]) == n
+        for k in INT_COLS:
+            assert np.array_equal(got["raw_" + k], want_raw[k]), (rank, k)
+            assert np.array_equal(got[k], want[k]), (rank, k)
+        assert np.allclose(got["score_means"], want["score_means"], rtol=1e-5)

@@ -1,8 +1,9 @@
 """The N > 1 host path on CPU: two ranks over gloo, each encodes its contiguous time shard, the packed run tables
 are exchanged with ONE all-gather (cutdet.shard), and the gathered shards -- joined by the oracle's stitch, the
 checker of the CUDA stitch kernel -- must equal the run table of the whole sequence.  No CUDA, no compute calls
-into libcutdet_b200.so: the per-shard tables come from the oracle; what is under test is shard_range / pack_columns /
-all_gather_packed / gather_tables (reference: none -- the reference is single-process)."""
+into libcutdet_b200.so: the per-shard tables come from the oracle; what is under test is shard_range, the packed byte
+layout (pack_columns / unpack_columns, the numpy restatement of cutdet_shard_pack that the GPU suite checks the kernel
+against) and all_gather_packed (reference: none -- the reference is single-process)."""
 import os
 import socket
 
@@ -40,26 +41,26 @@ def _worker(rank: int, world: int, port: int, n: int, seed: int, out_dir: str):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from cutdet import engine, shard
+        from cutdet import shard
 
         lab, top = _sequence(n, seed)
         lo, hi = shard.shard_range(n, rank, world)
         te = _local_table(lab[lo:hi], top[lo:hi]) if hi > lo else None
         n_runs = 0 if te is None else len(te["end_frames"])
         cap = 4096
-        table = engine.DeviceRunTable(cap, "cpu")
-        if te is not None:
-            for k in ("end_frames", "start_frames", "run_lengths", "score_means", "score_sums"):
-                getattr(table, k)[:n_runs] = torch.from_numpy(te[k])
-            table.frame_types[:n_runs] = torch.from_numpy(te["frame_types"]).to(torch.int32)
-        table.n_runs.fill_(n_runs)
-        big, counts, offsets, total = shard.gather_tables(table, hi - lo, cap)
-        assert total == n
-        shards = []
+        cols = te if te is not None else {k: np.zeros(0) for k in ("end_frames", "start_frames", "run_lengths", "score_sums",
+                                                                   "frame_types", "score_means")}
+        packed = shard.pack_columns(cols, n_runs, hi - lo, cap)
+        assert packed.numel() == shard.packed_bytes(cap)
+        gathered = shard.all_gather_packed(packed).view(world, -1)
+        shards, offsets, total = [], [], 0
         for r in range(world):
-            c = int(counts[r])
-            shards.append({k: getattr(big, k)[r * cap:r * cap + c].numpy() for k in
-                           ("end_frames", "start_frames", "run_lengths", "frame_types", "score_means", "score_sums")})
+            c, n_r, frames_r = shard.unpack_columns(gathered[r], cap)
+            assert len(c["end_frames"]) == n_r
+            shards.append(c)
+            offsets.append(total)
+            total += frames_r
+        assert total == n
         joined = oseg.stitch_tables(shards, [int(o) for o in offsets])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **joined)
     finally:
