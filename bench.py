@@ -3,11 +3,12 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the box's host cores
+    python bench.py --workload 1080p|contrastive|cli         # BASELINE configs[3] / configs[4] / the CLI on a video file
 
 A STEP is one pass of the hot path over one chunk of synthetic pre-decoded 720p frames (video decode is excluded on
 both arms):  K1 preprocess -> conv stack -> head -> K4 max/argmax -> K5 run-length append.
 After the K timed steps, still inside the timed region, the job is finished exactly once: close the run table,
-(N > 1: all-gather the shard tables over NCCL and stitch), K6 glue_orphans + combine_adjacent_segments, and copy the
+(N > 1: pack + all-gather the shard tables over NCCL + stitch), K6 glue_orphans + combine_adjacent_segments, and copy the
 run table to the host.  Workload at N = 1: BASELINE.json configs[1], a full synthetic game (K = 80 chunks of 4,050
 frames = 324,000 frames); every rank processes its own K chunks (weak scaling: per-GPU work is fixed).
 
@@ -15,20 +16,25 @@ frames = 324,000 frames); every rank processes its own K chunks (weak scaling: p
           every step's input is far larger than the 126 MB L2; no flush needed).
   e2e     the same job fed from PINNED HOST memory through the public pipeline (FramePipeline.push_host ->
           cutdet_upload_frames): the host->device copy of every step's frames and a device->host read of every
-          step's (label, max logit) columns are inside the timed region.
+          step's (label, max logit) columns are inside the timed region.  Per-rank copy rates are reported.
+  strong  (N > 1) configs[2] as BASELINE words it: the SAME 324,000-frame game time-sharded over the N ranks.
   roofline      the kernel with the largest share of the step, timed with CUDA events on its own stream by the
                 library's launch profiler in a separate pass over the same job (so `value` is unperturbed).
   cpu_baseline  the reference's CPU path (oracle.reference_path: cv2.resize + traced torch net + segmentation) on
                 the host cores, on BASELINE configs[0] (an 1,800-frame 720p clip), rank 0 at N = 1 only; the GPU
                 path's CSV for the same clip is checked against it.
+  cli     (N = 1) the drop-in CLI (cut-detection_b200/segment_video.py: decode workers -> pinned ring -> FramePipeline)
+          on an mp4 of that clip, decode INCLUDED, next to the reference's loop (cv2 decode + CPU path) on the same file.
+  parity  the timed job's own result: run table == the plan the frames were drawn from (at N > 1: the global plan of
+          all ranks in time order), K6 result == the oracle's glue/combine of that table, every rank holds the same table.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
-import subprocess
 import sys
 import tempfile
 import time
@@ -45,9 +51,11 @@ HEIGHT, WIDTH = 720, 1280
 FULL_GAME_FRAMES = 324_000
 # algorithmic work per frame
 K1_SRC_BYTES_720P = 552_960                # the 144 source rows (5y+2) of a 720p frame the resize reads
+K1_SRC_BYTES_1080P = 1_658_880             # 288 rows of 1080p
 K1_BYTES_720P = K1_SRC_BYTES_720P + 221_184  # ... + a bf16 [3,144,256] output (the unfused K1)
 FLOPS = {"L0": 95_551_488, "L1": 169_205_760, "L2": 18_579_456, "head": 49_152 + 192}
 NET_FLOPS = sum(FLOPS.values())            # 283,386,048
+CONTRASTIVE_FLOPS = 147_165_696            # config 5 encoder (C = 32), SURVEY 8 a-13
 
 
 def parse_args():
@@ -56,12 +64,18 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=80)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--workload", choices=["game", "1080p", "contrastive", "cli"], default="game")
     ap.add_argument("--chunk", type=int, default=4050, help="frames per step")
     ap.add_argument("--pool", type=int, default=4, help="distinct chunks kept resident in HBM")
     ap.add_argument("--cpu-sample", type=int, default=1800, help="frames of the CPU baseline sample (configs[0])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--net-opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="engine.NativeNet.set_option switches (sub_batch, group_frames, no_pdl, conv1_acc32), for A/B runs")
+    ap.add_argument("--lib", default=None, help="load this libcutdet_b200.so instead of the in-tree build (A/B of kernel builds)")
     return ap.parse_args()
 
 
@@ -77,18 +91,25 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples SM clock and throttle reasons DURING a timed region (NVML from a side thread every 50 ms; the main thread
-    sits in CUDA calls with the GIL released)."""
+    """Samples SM clock and throttle reasons DURING timed regions.  NVML is initialised once, on a side thread started before
+    the warm-up (pynvml import + nvmlInit take longer than a 36 ms timed region); ``begin()``/``end()`` bracket a region, the
+    thread records every 10 ms in between (the main thread sits in CUDA calls with the GIL released)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, device_index: int):
         import threading
         self.index = device_index
-        self.samples, self.reason_bits, self.power = [], 0, []
         self.sm_max = None
-        self._stop = threading.Event()
-        self._thread = threading.Thread(target=self._run, daemon=True)
         self.error = None
+        self._ready = threading.Event()
+        self._active = threading.Event()
+        self._stop = threading.Event()
+        self._lock = threading.Lock()
+        self._reset()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _reset(self):
+        self.samples, self.reason_bits, self.power = [], 0, []
 
     def _run(self):
         try:
@@ -103,34 +124,57 @@ class ClockSampler:
             else:
                 handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)        # first call out of the way
+            self._ready.set()
             while not self._stop.is_set():
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
-                self.reason_bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                if not self._active.wait(0.05):
+                    continue
+                sm = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
                 try:
-                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0)
+                    watts = pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0
                 except Exception:
-                    pass
-                self._stop.wait(0.05)
+                    watts = None
+                with self._lock:
+                    if self._active.is_set():
+                        self.samples.append(sm)
+                        self.reason_bits |= bits
+                        if watts is not None:
+                            self.power.append(watts)
+                self._stop.wait(0.01)
         except Exception as e:      # pragma: no cover
             self.error = repr(e)
+            self._ready.set()
 
     def start(self):
         self._thread.start()
 
-    def stop(self) -> dict:
-        self._stop.set()
-        self._thread.join(timeout=5)
-        if not self.samples:
+    def begin(self):
+        self._ready.wait(timeout=20)
+        with self._lock:
+            self._reset()
+        self._active.set()
+
+    def end(self) -> dict:
+        self._active.clear()
+        with self._lock:
+            samples, bits, power = list(self.samples), self.reason_bits, list(self.power)
+        if not samples:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [self.error or "no samples"]}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.sm_max,
-                "reasons": sorted(name for bit, name in self.REASONS.items() if self.reason_bits & bit),
-                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+        return {"sm_mhz": statistics.median(samples), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(name for bit, name in self.REASONS.items() if bits & bit),
+                "samples": len(samples), "power_w_max": max(power) if power else None}
+
+    def stop(self):
+        self._stop.set()
+        self._active.set()
+        self._thread.join(timeout=5)
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def numpy_frames(n: int, seed: int):
+def numpy_frames(n: int, seed: int, height=HEIGHT, width=WIDTH):
     from cutdet import synth
-    clip = synth.SyntheticClip(HEIGHT, WIDTH, n, seed=seed)
+    clip = synth.SyntheticClip(height, width, n, seed=seed)
     return clip, clip.frames_numpy(0, n)
 
 
@@ -146,9 +190,34 @@ def run_reference(args):
     from oracle import net as onet
     from oracle.reference_path import CpuReferencePath
 
-    weights, params = onet.load_weights_npz(os.path.join(PKG, "frameID", "prod_net", "prod_net_weights.npz"))
     batch = 128
-    clip, frames = numpy_frames(2 * batch, args.seed)
+    if args.workload == "contrastive":
+        weights = onet.random_weights(seed=3, hidden_channels=32, conv_layers=3, avg_pool_size=1, linear_layers=3,
+                                      linear_size=32, output_size=8)
+        from oracle.reference_path import build_torch_net
+        torch.set_num_threads(os.cpu_count() or 1)
+        net = build_torch_net(weights, 1)
+        net.train()                                   # learn_contrasts.py:100-107 never calls .eval()
+        x = torch.rand(64, 3, 144, 256)
+        with torch.no_grad():
+            for _ in range(max(args.warmup, 1)):
+                net(x)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                net(x)
+            total = time.perf_counter() - t0
+        fps = args.steps * 64 / total
+        _emit({"impl": "reference", "metric": "frames_per_sec_contrastive_encoder", "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "configs[4]: contrastive encoder forward (C=32 trunk + 3-layer head, training-mode BatchNorm), "
+                                      "batches of 64 synthetic 256x144 frames, torch CPU"},
+               "cpu_baseline": {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"{args.steps} batches of 64"},
+               "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+        return
+    height, width = (1080, 1920) if args.workload == "1080p" else (HEIGHT, WIDTH)
+    weights, params = onet.load_weights_npz(os.path.join(PKG, "frameID", "prod_net", "prod_net_weights.npz"))
+    clip, frames = numpy_frames(2 * batch, args.seed, height, width)
     path = CpuReferencePath(weights, params)
     for w in range(args.warmup):
         path.score_batch(frames[(w % 2) * batch:(w % 2 + 1) * batch])
@@ -165,15 +234,16 @@ def run_reference(args):
     total = time.perf_counter() - t0
     n = args.steps * batch
     fps = n / total
-    sample = (f"{args.steps} batches of {batch} synthetic 720p frames: cv2.resize+tensor ops {path.t_pre:.2f}s, "
+    sample = (f"{args.steps} batches of {batch} synthetic {width}x{height} frames: cv2.resize+tensor ops {path.t_pre:.2f}s, "
               f"traced net {path.t_net:.2f}s, segmentation {path.t_seg:.3f}s")
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC if args.workload != "1080p" else "frames_per_sec_1080p", "value": fps, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "reference CPU path (cv2.resize + TorchScript-traced prod_net + Segmentation) on a bounded "
-                               "sample of the full-game 720p workload; decode excluded", "batch": batch, "frames": n,
-                   "resolution": [WIDTH, HEIGHT]},
+                               "sample of the full-game workload; decode excluded", "batch": batch, "frames": n,
+                   "resolution": [width, height]},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": path.threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -181,60 +251,145 @@ def run_reference(args):
     _emit(line)
 
 
-# ------------------------------------------------------------------------------------------------- native arm
-def run_native(args):
+# ------------------------------------------------------------------------------------------------- native arm: set-up
+class Rig:
+    """Process group, device, library and the classifier for one rank."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from cutdet import _cabi, engine
+        from cutdet import build as native_build
+        from frameID.net import load_default_net
+
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        if args.lib:
+            _cabi.LIB_OVERRIDE = os.path.abspath(args.lib)
+        else:
+            if self.rank == 0:
+                native_build.ensure_current()          # rebuilds a missing or stale library once, not once per rank
+            if self.world > 1:
+                dist.barrier()
+        self.lib = _cabi.lib()
+        engine.device_check()
+        self.sampler = ClockSampler(self.local_rank)
+        if self.rank == 0:
+            self.sampler.start()
+        net, self.params = load_default_net()
+        self.net = net
+        self.native = net.eval().to(self.dev)._native()
+        self.net_opts = {}
+        for kv in args.net_opt:
+            k, _, v = kv.partition("=")
+            self.native.set_option(k, int(v))
+            self.net_opts[k] = int(v)
+
+    def barrier(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+
+    def max_over_ranks(self, value: float) -> float:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([value], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_floats(self, value: float):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([value], dtype=torch.float64, device=self.dev)
+        if self.world == 1:
+            return [float(value)]
+        out = torch.empty(self.world, dtype=torch.float64, device=self.dev)
+        dist.all_gather_into_tensor(out, t)
+        return [float(v) for v in out.cpu()]
+
+    def timed(self, fn, warm):
+        """warm(); barrier + sync; K timed calls are inside fn(); barrier + sync.  Returns (max ms over ranks, this rank's ms,
+        fn's result, launches, clocks)."""
+        import torch
+        warm()
+        self.barrier()
+        torch.cuda.synchronize()
+        launches0 = self.lib.cutdet_launch_count()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if self.rank == 0:
+            self.sampler.begin()
+        start.record()
+        out = fn()
+        stop.record()
+        torch.cuda.synchronize()
+        self.barrier()
+        clocks = self.sampler.end() if self.rank == 0 else None
+        mine = start.elapsed_time(stop)
+        return self.max_over_ranks(mine), mine, out, self.lib.cutdet_launch_count() - launches0, clocks
+
+    def close(self):
+        import torch.distributed as dist
+        if self.rank == 0:
+            self.sampler.stop()
+        if self.world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+def te_digest(te) -> float:
+    """A number that any difference between two run tables changes (exactly representable: 48 bits of a SHA-256)."""
+    h = hashlib.sha256()
+    for k in ("end_frames", "frame_types", "run_lengths", "start_frames", "score_means"):
+        h.update(te[k].numpy().tobytes())
+    return float(int.from_bytes(h.digest()[:6], "little"))
+
+
+# ------------------------------------------------------------------------------------------------- native arm: the game
+def run_game(rig: Rig):
     import numpy as np
     import torch
-    import torch.distributed as dist
 
     from cutdet import _cabi, engine, pipeline, shard, synth
-    from cutdet import build as native_build
-    from frameID.net import load_default_net
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    if not os.path.isfile(native_build.LIB_PATH):
-        if rank == 0:
-            native_build.build_native()
-        if world > 1:
-            dist.barrier()
-    lib = _cabi.lib()
-    engine.device_check()
-
+    args, world, rank, dev, lib, native = rig.args, rig.world, rig.rank, rig.dev, rig.lib, rig.native
     K, W, chunk = args.steps, max(args.warmup, 0), args.chunk
     pool_n = max(1, min(args.pool, K))
-    net, params = load_default_net()
-    native = net.eval().to(dev)._native()
     plan = engine.ResizePlan.for_video(HEIGHT, WIDTH, 256)
     uses_tc = native.uses_tensor_cores(plan.dst_h, plan.dst_w)
 
     # This rank's slice of the synthetic game: a pool of distinct chunks, cycled over the K steps.
     clip = synth.SyntheticClip(HEIGHT, WIDTH, pool_n * chunk, seed=args.seed + rank)
     pool = [clip.frames_torch(i * chunk, chunk, device=dev) for i in range(pool_n)]
-    def planned_labels(cycle):
-        return np.concatenate([clip.labels[(s % cycle) * chunk:(s % cycle + 1) * chunk] for s in range(K)])
-    frames_local = K * chunk
-    capacity = frames_local                       # a run table can never have more rows than frames
-    gather_capacity = min(capacity, 1 << 16)
+
+    def planned_labels(rank_clip, cycle, steps):
+        return np.concatenate([rank_clip.labels[(s % cycle) * chunk:(s % cycle + 1) * chunk] for s in range(steps)])
+
+    capacity = K * chunk                          # a run table can never have more rows than frames
     pipe = pipeline.FramePipeline(native, plan, chunk, capacity, dev)
     step_results = torch.empty((chunk, 5), dtype=torch.uint8).pin_memory()     # (label u8, max logit f32) per frame
+    host_pool = []
 
-    def finalize():
+    def finalize(frames_local):
+        """close the table, exchange (N > 1), raw copy, K6, final copy: all queued without a host synchronisation until the
+        first device->host copy.  Returns (raw te, smoothed te, total frames)."""
         table = pipe.finish()
-        total = frames_local
+        total = None
         if world > 1:
-            table, total = shard.stitch_all(table, frames_local, gather_capacity)
-        raw = table.to_te() if world == 1 else None
+            table, total = shard.stitch_all(table, frames_local)
+        raw = table.to_te()
         pipeline.smooth(table, 100, 10)
-        return raw, table.to_te(), total                     # to_te() = the device->host copy of the run table
+        te = table.to_te()
+        return raw, te, (int(total.item()) if total is not None else frames_local)
 
     def job(source, steps):
         pipe.reset()
@@ -246,68 +401,67 @@ def run_native(args):
                 n = chunk
                 step_results[:n, 0].copy_(pipe.labels[:n], non_blocking=True)
                 step_results[:n, 1:].copy_(pipe.top[:n].view(torch.uint8).view(n, 4), non_blocking=True)
-        return finalize()
+        return finalize(steps * chunk)
 
-    def timed(source):
-        if W > 0:
-            job(source, W)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        launches0 = lib.cutdet_launch_count()
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(local_rank)
+    def check_parity(raw, te, total, cycle, steps):
+        """rank 0: the gathered, stitched table against the global plan (every rank's clip is a function of seed + rank), K6
+        against the oracle's glue/combine of the same table; all ranks: identical tables."""
+        from oracle import segmentation as oseg
+        out = {"frames_covered": int(te["run_lengths"].sum().item()), "total_frames": int(total), "segments": int(te["end_frames"].shape[0])}
+        digests = rig.gather_floats(te_digest(te))
+        out["all_ranks_hold_the_same_table"] = len(set(digests)) == 1
         if rank == 0:
-            sampler.start()
-        start.record()
-        out = job(source, K)
-        stop.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop() if rank == 0 else None
-        ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), out, lib.cutdet_launch_count() - launches0, clocks
+            labels = np.concatenate([planned_labels(clip if r == 0 else synth.SyntheticClip(HEIGHT, WIDTH, pool_n * chunk, seed=args.seed + r),
+                                                    cycle, steps) for r in range(world)])
+            want = oseg.run_table_from_labels(labels, np.ones(len(labels), np.float32))
+            out["runs_equal_plan"] = bool(np.array_equal(raw["end_frames"].numpy(), want["end_frames"]) and
+                                          np.array_equal(raw["frame_types"].numpy(), want["frame_types"]) and
+                                          np.array_equal(raw["start_frames"].numpy(), want["start_frames"]))
+            raw_np = {k: v.numpy() for k, v in raw.items()}
+            smoothed = oseg.combine_adjacent(oseg.glue_orphans(raw_np, 100, 10))
+            out["smoothed_equal_oracle"] = bool(all(np.array_equal(te[k].numpy(), smoothed[k]) for k in
+                                                    ("end_frames", "frame_types", "run_lengths", "start_frames")))
+            out["frames_covered_equals_total"] = out["frames_covered"] == world * steps * chunk == out["total_frames"]
+        return out
 
     # ---------------- value: inputs resident in HBM
-    ms, (raw_te, te, total_frames), launches, clocks = timed("device")
-    value = world * frames_local / (ms / 1e3)
+    ms, _, (raw_te, te, total_frames), launches, clocks = rig.timed(lambda: job("device", K), lambda: W and job("device", W))
+    value = world * K * chunk / (ms / 1e3)
+    parity = check_parity(raw_te, te, total_frames, pool_n, K)
 
-    # parity of the timed job itself: the initial run table must equal the plan the frames were drawn from
-    parity = {}
-    if world == 1:
-        from oracle import segmentation as oseg
-
-        def runs_equal_plan(raw, cycle):
-            labels = planned_labels(cycle)
-            want = oseg.run_table_from_labels(labels, np.ones(len(labels), np.float32))
-            return bool(np.array_equal(raw["end_frames"].numpy(), want["end_frames"]) and
-                        np.array_equal(raw["frame_types"].numpy(), want["frame_types"]))
-
-        parity["timed_job_runs_equal_plan"] = runs_equal_plan(raw_te, pool_n)
-    parity["segments"] = int(te["end_frames"].shape[0])
-    parity["frames_covered"] = int(te["run_lengths"].sum().item())
+    # ---------------- strong scaling: the SAME full game over N ranks (configs[2] as worded)
+    strong = None
+    if world > 1 and not args.no_strong:
+        Ks = max(1, -(-K // world))
+        ms_s, _, (raw_s, te_s, total_s), _, _ = rig.timed(lambda: job("device", Ks), lambda: job("device", min(W, Ks)))
+        strong = {"value": world * Ks * chunk / (ms_s / 1e3), "unit": UNIT, "total_frames": world * Ks * chunk,
+                  "steps_per_gpu": Ks, "ms_total": ms_s,
+                  "note": "the K-step game divided over the ranks (K/N steps each), exchange + K6 + copies inside the timed region",
+                  "parity": check_parity(raw_s, te_s, total_s, pool_n, Ks)}
 
     # ---------------- e2e: pinned host frames through the public pipeline
     e2e = None
     if not args.no_e2e:
-        host_pool = []
         for i in range(min(2, pool_n)):
             h = torch.empty((chunk, HEIGHT, WIDTH, 3), dtype=torch.uint8).pin_memory()
             h.copy_(pool[i])
             host_pool.append(h)
         torch.cuda.synchronize()
-        ms_e, (raw_e, te_e, _), _, clocks_e = timed("host")
-        e2e = {"value": world * frames_local / (ms_e / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": int(pipe.h2d_bytes // K), "d2h_bytes_per_step": int(chunk * 5),
+        ms_e, mine_e, (raw_e, te_e, total_e), _, clocks_e = rig.timed(lambda: job("host", K), lambda: W and job("host", W))
+        h2d = pipe.h2d_bytes
+        per_rank_ms = rig.gather_floats(mine_e)
+        per_rank_gbs = [h2d / (m * 1e-3) / 1e9 for m in per_rank_ms]
+        e2e = {"value": world * K * chunk / (ms_e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d // K), "d2h_bytes_per_step": int(chunk * 5),
                "ms_per_step": ms_e / K,
+               "h2d_gbs_per_rank": {"min": min(per_rank_gbs), "median": statistics.median(per_rank_gbs), "max": max(per_rank_gbs),
+                                    "sum": sum(per_rank_gbs), "all": [round(v, 2) for v in per_rank_gbs]},
+               "ms_per_rank": [round(m, 2) for m in per_rank_ms],
                "note": "H2D copies only the 144 source rows per frame the 720p->256x144 resize reads "
                        "(cutdet_upload_frames: one strided 2-D DMA per chunk); full frames are 11.2 GB per step",
-               "runs_equal_plan": runs_equal_plan(raw_e, len(host_pool)) if world == 1 else None,
+               "parity": check_parity(raw_e, te_e, total_e, len(host_pool), K),
                "clocks": clocks_e}
-        del host_pool
+        host_pool.clear()
 
     # ---------------- roofline: per-kernel CUDA-event timings of the same job (separate pass)
     prof_steps = min(K, 8)
@@ -319,54 +473,10 @@ def run_native(args):
     cbuf = ctypes.create_string_buffer(65536)
     _cabi.check(lib.cutdet_profile_end(cbuf, 65536))
     kernels = json.loads(cbuf.value.decode())
-    peaks = measured_peaks()
-    total_ms = sum(k["ms"] for k in kernels.values()) or 1.0
-    frames_profiled = prof_steps * chunk
-    per_frame_units = {   # algorithmic work per FRAME; a launch covers frames_profiled / launches frames
-        "preprocess": ("hbm", K1_BYTES_720P), "conv_block_generic_L0": ("tensor", FLOPS["L0"]),
-        # K1 fused into conv1: reads the 144 source rows a frame needs (552,960 B), writes nothing to HBM by design (its
-        # output stays in L2 for conv2); HBM time floor 0.086 us/frame > tensor floor 0.068 us/frame, so it is HBM-bound.
-        "conv1_fused_tc": ("hbm", K1_SRC_BYTES_720P),
-        "conv_block_generic_L1": ("tensor", FLOPS["L1"]), "conv_block_generic_L2": ("tensor", FLOPS["L2"]),
-        "conv1_tc": ("tensor", FLOPS["L0"]), "conv2_tc": ("tensor", FLOPS["L1"]), "conv3_tc": ("tensor", FLOPS["L2"]),
-    }
-    table = {}
-    for name, k in kernels.items():
-        avg_ms = k["ms"] / max(k["launches"], 1)
-        frames_per_launch = frames_profiled / max(k["launches"], 1)
-        row = {"launches": k["launches"], "avg_ms": avg_ms, "share": k["ms"] / total_ms,
-               "ms_per_step": k["ms"] / prof_steps}
-        key = next((u for u in per_frame_units if name.startswith(u)), None)
-        if key:
-            bound, per_frame = per_frame_units[key]
-            units = per_frame * frames_per_launch
-            row["frames_per_launch"] = frames_per_launch
-            if bound == "hbm":
-                row.update(bound="hbm", achieved=units / (avg_ms * 1e-3) / 1e9, unit="GB/s", peak=peaks["hbm_gbs"])
-            else:
-                row.update(bound="tensor", achieved=units / (avg_ms * 1e-3) / 1e12, unit="TFLOP/s", peak=peaks["tflops_sustained"])
-            row["frac"] = row["achieved"] / row["peak"]
-            if key == "conv1_fused_tc":          # the same launch is also layer 1's MMAs
-                row["tensor_tflops"] = FLOPS["L0"] * frames_per_launch / (avg_ms * 1e-3) / 1e12
-                row["tensor_frac_of_sustained"] = row["tensor_tflops"] / peaks["tflops_sustained"]
-        table[name] = row
-    dominant = max((n for n in table if "frac" in table[n]), key=lambda n: table[n]["share"], default=None)
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dominant, {}).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = None
-    if dominant:
-        d = table[dominant]
-        roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                    "frac": d["frac"], "traffic": traffic, "share_of_step": d["share"], "avg_launch_ms": d["avg_ms"],
-                    "peak_source": peaks["source"] + (" (sustained bf16: kernel timed inside a long step)" if d["bound"] == "tensor" else ""),
-                    "net_tflops_whole_conv_stack": NET_FLOPS * chunk / 1e12 / (1e-3 * sum(
-                        r["ms_per_step"] for n, r in table.items() if n.startswith(("conv", "head", "fc", "avgpool"))) or 1.0)}
+    table, roofline = kernel_table(kernels, prof_steps, chunk, K1_SRC_BYTES_720P)
 
-    # ---------------- CPU baseline + whole-clip parity (rank 0, N = 1)
-    cpu_baseline = None
+    # ---------------- CPU baseline + whole-clip parity + the CLI on a file (rank 0, N = 1)
+    cpu_baseline, cli = None, None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import net as onet
         from oracle.reference_path import CpuReferencePath
@@ -399,6 +509,9 @@ def run_native(args):
         parity.update({"clip_frames": n, "clip_csv_equal_cpu_reference": rows.encode() == csv_cpu,
                        "clip_max_abs_dlogit": float(np.abs(g - logits).max()),
                        "clip_label_mismatches": int((g.argmax(1) != logits.argmax(1)).sum())})
+        if not args.no_cli:
+            cli = run_cli_measurement(rig, frames_host, path)
+        del frames_dev, frames_host
 
     if rank == 0:
         line = {
@@ -407,18 +520,264 @@ def run_native(args):
             "dtype": "f16" if uses_tc else "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: full-game synthetic 720p30 batch inference + segmentation "
                                    f"({K} steps x {chunk} frames per GPU; decode excluded)",
-                       "resolution": [WIDTH, HEIGHT], "chunk_frames": chunk, "frames_per_gpu": frames_local,
-                       "total_frames": world * frames_local, "pool_chunks": pool_n,
+                       "resolution": [WIDTH, HEIGHT], "chunk_frames": chunk, "frames_per_gpu": K * chunk,
+                       "total_frames": world * K * chunk, "pool_chunks": pool_n,
                        "l2_policy": "inputs larger than L2: each step reads a distinct 11.2 GB chunk",
                        "weights": "shipped prod_net", "conv_path": "tcgen05" if uses_tc else "generic-cuda-core",
-                       "parallelism": f"time-shard x{world}" + (" + NCCL all-gather of run tables" if world > 1 else "")},
+                       "net_options": rig.net_opts,
+                       "parallelism": f"time-shard x{world}" + (" + NCCL all-gather of packed run tables" if world > 1 else "")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "kernels": table, "parity": parity,
+            "cpu_baseline": cpu_baseline, "strong": strong, "cli": cli, "kernels": table, "parity": parity,
         }
         _emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+
+
+def kernel_table(kernels: dict, prof_steps: int, chunk: int, k1_src_bytes: int):
+    """Per-kernel rows {launches, avg_ms, share, achieved, frac ...} and the roofline object of the dominant kernel."""
+    peaks = measured_peaks()
+    total_ms = sum(k["ms"] for k in kernels.values()) or 1.0
+    frames_profiled = prof_steps * chunk
+    per_frame_units = {   # algorithmic work per FRAME (SURVEY.md section 8d); a launch covers frames_profiled / launches frames
+        "preprocess": ("hbm", k1_src_bytes + 221_184), "conv_block_generic_L0": ("tensor", FLOPS["L0"]),
+        # K1 fused into conv1: reads the source rows a frame needs (552,960 B at 720p), writes nothing to HBM by design (its
+        # output stays in L2 for conv2); HBM time floor 0.086 us/frame > tensor floor 0.068 us/frame, so it is HBM-bound.
+        "conv1_fused_tc": ("hbm", k1_src_bytes),
+        "conv_block_generic_L1": ("tensor", FLOPS["L1"]), "conv_block_generic_L2": ("tensor", FLOPS["L2"]),
+        "conv1_tc": ("tensor", FLOPS["L0"]), "conv2_tc": ("tensor", FLOPS["L1"]), "conv3_tc": ("tensor", FLOPS["L2"]),
+    }
+    table = {}
+    for name, k in kernels.items():
+        avg_ms = k["ms"] / max(k["launches"], 1)
+        frames_per_launch = frames_profiled / max(k["launches"], 1)
+        row = {"launches": k["launches"], "avg_ms": avg_ms, "share": k["ms"] / total_ms,
+               "ms_per_step": k["ms"] / prof_steps}
+        key = next((u for u in per_frame_units if name.startswith(u)), None)
+        if key:
+            bound, per_frame = per_frame_units[key]
+            units = per_frame * frames_per_launch
+            row["frames_per_launch"] = frames_per_launch
+            if bound == "hbm":
+                row.update(bound="hbm", achieved=units / (avg_ms * 1e-3) / 1e9, unit="GB/s", peak=peaks["hbm_gbs"])
+            else:
+                row.update(bound="tensor", achieved=units / (avg_ms * 1e-3) / 1e12, unit="TFLOP/s", peak=peaks["tflops_sustained"])
+            row["frac"] = row["achieved"] / row["peak"]
+            if key == "conv1_fused_tc":          # the same launch is also layer 1's MMAs
+                row["tensor_tflops"] = FLOPS["L0"] * frames_per_launch / (avg_ms * 1e-3) / 1e12
+                row["tensor_frac_of_sustained"] = row["tensor_tflops"] / peaks["tflops_sustained"]
+        table[name] = row
+    dominant = max((n for n in table if "frac" in table[n]), key=lambda n: table[n]["share"], default=None)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dominant, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = None
+    if dominant:
+        d = table[dominant]
+        conv_ms = sum(r["ms_per_step"] for n, r in table.items() if n.startswith(("conv", "head", "fc", "avgpool"))) or 1.0
+        roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+                    "frac": d["frac"], "traffic": traffic, "share_of_step": d["share"], "avg_launch_ms": d["avg_ms"],
+                    "peak_source": peaks["source"] + (" (sustained bf16: kernel timed inside a long step)" if d["bound"] == "tensor" else ""),
+                    "net_tflops_whole_conv_stack": NET_FLOPS * chunk / 1e12 / (1e-3 * conv_ms),
+                    "net_frac_of_sustained_tensor_peak": NET_FLOPS * chunk / 1e12 / (1e-3 * conv_ms) / peaks["tflops_sustained"]}
+    return table, roofline
+
+
+def run_cli_measurement(rig: Rig, frames_host, cpu_path):
+    """The drop-in CLI on a FILE (decode included): write the configs[0] clip as an mp4, run segment_video.main on it, and time
+    the reference's own loop (one cv2.VideoCapture thread -> cv2.resize -> traced net on the CPU -> Segmentation) on the same file."""
+    import cv2
+    import numpy as np
+    import segment_video as sv
+    from oracle import segmentation as oseg
+
+    n = frames_host.shape[0]
+    tmp = tempfile.mkdtemp(prefix="cutdet_cli_")
+    path = os.path.join(tmp, "clip.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 30, (WIDTH, HEIGHT))
+    for f in frames_host:
+        vw.write(f)
+    vw.release()
+    out = {"video": f"{n} frames 720p mp4v written with cv2.VideoWriter", "video_bytes": os.path.getsize(path)}
+    results = {}
+    for workers in (1, None):
+        csv_path = os.path.join(tmp, f"out_{workers}.csv")
+        argv = [path, "--output_path", csv_path, "--print-every", "0"] + (["--decode-workers", str(workers)] if workers else [])
+        t0 = time.perf_counter()
+        sv.main(sv.sv_parser.parse_args(argv))
+        dt = time.perf_counter() - t0
+        results["sequential_decode" if workers else "default_workers"] = {"frames_per_s": n / dt, "seconds": dt}
+        out["csv_" + ("w1" if workers else "default")] = open(csv_path, "rb").read().decode()
+    from cutdet import decode
+    out["decode_workers_default"] = decode.default_workers()
+    out.update(results)
+    # the reference's loop on the same file (oracle port), decode included
+    t0 = time.perf_counter()
+    cap = cv2.VideoCapture(path)
+    logits, batch = [], []
+    while True:
+        ok, frame = cap.read()
+        if ok:
+            batch.append(frame)
+        if len(batch) == 128 or (not ok and batch):
+            logits.append(cpu_path.score_batch(np.stack(batch)).numpy())
+            batch = []
+        if not ok:
+            break
+    csv_ref = cpu_path.segment(np.concatenate(logits))[3]
+    dt = time.perf_counter() - t0
+    out["reference_loop"] = {"frames_per_s": n / dt, "seconds": dt, "cores": cpu_path.threads,
+                             "what": "cv2.VideoCapture.read() + cv2.resize + traced prod_net (CPU, all threads) + Segmentation"}
+    out["csv_equal_reference_loop"] = out["csv_default"].encode() == csv_ref and out["csv_w1"].encode() == csv_ref
+    out.pop("csv_w1")
+    out["csv"] = out.pop("csv_default")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------- configs[3]: 1080p sweep
+def run_1080p(rig: Rig):
+    """BASELINE configs[3]: 1080p input, batch-size sweep 64..4096 through the fused preprocessing + conv stack (frames
+    resident in HBM; each batch size cycles over distinct buffers larger than L2 in total)."""
+    import torch
+    from cutdet import _cabi, engine, synth
+
+    args, dev, native, lib = rig.args, rig.dev, rig.native, rig.lib
+    h, w = 1080, 1920
+    plan = engine.ResizePlan.for_video(h, w, 256)
+    clip = synth.SyntheticClip(h, w, 4096, seed=args.seed + rig.rank)
+    frames = clip.frames_torch(0, 4096, device=dev)            # 25.5 GB
+    sweep = {}
+    K, W = max(args.steps, 1), max(args.warmup, 3)
+    value_ms = None
+    for b in (64, 128, 256, 512, 1024, 2048, 4096):
+        out = torch.empty((b, 3), dtype=torch.float32, device=dev)
+        n_buf = 4096 // b
+
+        def step(i):
+            native.forward_frames(plan, frames[(i % n_buf) * b:(i % n_buf + 1) * b], out=out)
+
+        def steps():
+            for i in range(K):
+                step(i)
+
+        ms, _, _, launches, clocks = rig.timed(steps, lambda: [step(i) for i in range(W)])
+        sweep[str(b)] = {"frames_per_s": rig.world * K * b / (ms / 1e3), "ms_per_step": ms / K}
+        if b == 4096:
+            value_ms, value_launches, value_clocks = ms, launches, clocks
+    # e2e at the largest batch: pinned host frames, H2D of the 288 needed rows + logits D2H inside the timed region
+    from cutdet import pipeline
+    pipe = pipeline.FramePipeline(native, plan, 1024, 1024 * K + 1024, dev)
+    host = torch.empty((1024, h, w, 3), dtype=torch.uint8).pin_memory()
+    host.copy_(frames[:1024])
+    logits_host = torch.empty((1024, 3), dtype=torch.float32).pin_memory()
+
+    def e2e_steps():
+        pipe.reset()
+        for i in range(K):
+            pipe.push_host(host)
+            logits_host.copy_(pipe.logits[:1024], non_blocking=True)
+
+    ms_e, _, _, _, _ = rig.timed(e2e_steps, e2e_steps)
+    h2d = pipe.h2d_bytes
+    lib.cutdet_profile_begin()
+    for i in range(2):
+        native.forward_frames(plan, frames)
+    import ctypes
+    cbuf = ctypes.create_string_buffer(65536)
+    _cabi.check(lib.cutdet_profile_end(cbuf, 65536))
+    table, roofline = kernel_table(json.loads(cbuf.value.decode()), 2, 4096, K1_SRC_BYTES_1080P)
+    if rig.rank == 0:
+        _emit({"metric": "frames_per_sec_1080p", "value": rig.world * K * 4096 / (value_ms / 1e3), "unit": UNIT, "n_gpus": rig.world,
+               "steps": K, "warmup": W, "ms_per_step": value_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f16", "data": "synthetic",
+               "config": {"workload": "configs[3]: 1080p batch-size sweep (64-4096 frames per step) through fused preprocessing + conv "
+                                      "stack + head; value = batch 4096", "resolution": [w, h], "sweep": sweep,
+                          "l2_policy": "each step reads a distinct slice of a 25.5 GB frame buffer"},
+               "clocks": value_clocks, "gpu_launches": int(value_launches), "roofline": roofline, "kernels": table,
+               "e2e": {"value": rig.world * K * 1024 / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d // K),
+                       "d2h_bytes_per_step": 1024 * 12, "batch": 1024},
+               "cpu_baseline": None})
+
+
+# ------------------------------------------------------------------------------------------------- configs[4]: contrastive
+def run_contrastive(rig: Rig):
+    """BASELINE configs[4]: the contrastive encoder of learn_contrasts.py:68-76 (C = 32 trunk + 3-layer head to 8) + NT-Xent
+    loss forward on synthetic frame pairs, random-init weights.  The reference runs it in TRAINING mode (no .eval():
+    BatchNorm on batch statistics) in batches of 64 = 32 pairs; each rank runs its own batches (data-parallel replicas: the
+    script has no cross-replica step in its forward)."""
+    import torch
+    from frameID.metrics import ContrastiveLoss
+    from frameID.net import FrameConvNet, FrameLinearNet, GluedNet
+
+    args, dev = rig.args, rig.dev
+    torch.manual_seed(3)
+    conv_net = FrameConvNet(hidden_channels=32, n_conv_layers=3)                 # learn_contrasts.py:68-76
+    linear_net = FrameLinearNet(n_layers=3, input_size=32, hidden_size=32, output_size=8)
+    net = GluedNet(conv_net, linear_net).to(dev)                                 # trunk + head as ONE native pipeline
+    K, W = max(args.steps, 1), max(args.warmup, 3)
+    results = {}
+    g = torch.Generator(device=dev)
+    g.manual_seed(args.seed + rig.rank)
+    for name, batch, train in (("train_bn_batch64", 64, True), ("train_bn_batch148", 148, True), ("eval_bn_batch1184", 1184, False)):
+        net.train(train)
+        criterion = ContrastiveLoss(batch_size=batch // 2).to(dev)
+        n_buf = max(2, min(8, (160 << 20) // (batch * 3 * 144 * 256 * 4) + 1))      # > L2 in total
+        xs = [torch.rand((batch, 3, 144, 256), device=dev, generator=g) for _ in range(n_buf)]
+        host = torch.empty((batch, 3, 144, 256), dtype=torch.float32).pin_memory()
+        host.copy_(xs[0])
+        x_dev = torch.empty_like(xs[0])
+        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+        def step(x):
+            with torch.no_grad():
+                return criterion(net(x))[0]
+
+        def steps():
+            for i in range(K):
+                step(xs[i % n_buf])
+
+        def e2e_steps():
+            for i in range(K):
+                x_dev.copy_(host, non_blocking=True)
+                loss_host.copy_(step(x_dev), non_blocking=True)
+
+        ms, _, _, launches, clocks = rig.timed(steps, lambda: [step(xs[i % n_buf]) for i in range(W)])
+        ms_e, _, _, _, _ = rig.timed(e2e_steps, e2e_steps)
+        results[name] = {"frames_per_s": rig.world * K * batch / (ms / 1e3), "ms_per_step": ms / K, "launches": int(launches),
+                         "e2e_frames_per_s": rig.world * K * batch / (ms_e / 1e3), "clocks": clocks,
+                         "tflops": CONTRASTIVE_FLOPS * rig.world * K * batch / (ms / 1e3) / 1e12}
+        del xs
+    head = results["train_bn_batch64"]
+    if rig.rank == 0:
+        _emit({"metric": "frames_per_sec_contrastive_encoder", "value": head["frames_per_s"], "unit": UNIT, "n_gpus": rig.world,
+               "steps": K, "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+               "config": {"workload": "configs[4]: contrastive encoder forward + NT-Xent loss on synthetic frame pairs, batches of 64 "
+                                      "frames per GPU, training-mode BatchNorm as learn_contrasts.py runs it; other batch sizes in 'variants'",
+                          "variants": results, "weights": "random init (torch.manual_seed) through the mirror's FrameConvNet / FrameLinearNet constructors", "input": "[64,3,144,256] float32 in [0,1]"},
+               "clocks": head["clocks"], "gpu_launches": head["launches"],
+               "e2e": {"value": head["e2e_frames_per_s"], "unit": UNIT, "h2d_bytes_per_step": 64 * 3 * 144 * 256 * 4, "d2h_bytes_per_step": 4},
+               "roofline": {"bound": "tensor", "achieved": results["eval_bn_batch1184"]["tflops"] / rig.world, "peak": measured_peaks()["tflops_burst"],
+                            "unit": "TFLOP/s", "frac": results["eval_bn_batch1184"]["tflops"] / rig.world / measured_peaks()["tflops_burst"],
+                            "traffic": None, "note": "whole forward at batch 1184 per GPU (launch-bound below that)"},
+               "cpu_baseline": None})
+
+
+def run_cli_only(rig: Rig):
+    import numpy as np
+    from cutdet import synth
+    from oracle import net as onet
+    from oracle.reference_path import CpuReferencePath
+    n = rig.args.cpu_sample
+    frames = synth.SyntheticClip(HEIGHT, WIDTH, n, seed=rig.args.seed + 101).frames_numpy(0, n)
+    weights, wparams = onet.load_weights_npz(os.path.join(PKG, "frameID", "prod_net", "prod_net_weights.npz"))
+    path = CpuReferencePath(weights, wparams)
+    cli = run_cli_measurement(rig, frames, path)
+    if rig.rank == 0:
+        _emit({"metric": "frames_per_sec_720p_cli_with_decode", "value": cli["default_workers"]["frames_per_s"], "unit": UNIT,
+               "n_gpus": 1, "steps": 1, "warmup": 0, "ms_per_step": 1e3 * cli["default_workers"]["seconds"], "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+               "config": {"workload": "segment_video.py on an mp4 of the configs[0] clip, decode included"}, "cli": cli})
 
 
 _JSON_OUT = None
@@ -439,8 +798,12 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_native(args)
+        return
+    rig = Rig(args)
+    try:
+        {"game": run_game, "1080p": run_1080p, "contrastive": run_contrastive, "cli": run_cli_only}[args.workload](rig)
+    finally:
+        rig.close()
 
 
 if __name__ == "__main__":

@@ -14,6 +14,7 @@ from . import build as _build
 
 _lock = threading.Lock()
 _lib = None
+LIB_OVERRIDE = None      # development aid (bench.py --lib): load this build of the library instead of the in-tree one
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ECAPACITY, ELONE_ORPHAN = range(6)
 ABI_VERSION = 2
@@ -112,7 +113,8 @@ def lib() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.ensure_current()      # raises when the library is missing or stale and cannot be rebuilt
+        # raises when the library is missing or stale and cannot be rebuilt
+        path = LIB_OVERRIDE if LIB_OVERRIDE else _build.ensure_current()
         handle = C.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)      # AttributeError here = header/library mismatch: fail loudly

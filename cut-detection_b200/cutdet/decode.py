@@ -1,0 +1,258 @@
+"""Frame decode feeding K1: N decoder processes -> one reusable pinned ring -> FramePipeline.
+
+The reference decodes on one Python thread, one ``cap.read()`` per frame inside the DataLoader loop (reference
+frameID/data.py:211-213, segment_video.py:28-45): end to end it is decode-bound at ~10^2 frames/s whatever the classifier
+costs.  Hardware decode (NVDEC) is not available in this image (no nvcuvid header or library, no PyAV/ffmpeg binding other
+than OpenCV's), so this is the CPU half of that row: the video's frame range is cut into W contiguous TIME RANGES, one
+decoder process each (``cv2.VideoCapture`` + one seek), and every process writes the frames it decodes -- only the source
+rows the resize reads, e.g. 144 of 720 -- straight into its slots of ONE shared-memory ring that the parent has registered
+as pinned memory once (no per-batch ``pin_memory()``).  The parent hands full slots to ``FramePipeline.push_host`` (an
+asynchronous H2D copy + the kernels) and gives a slot back to its worker when the copy's event has completed.  Each range has
+its own streaming run-length encoder; the ranges' run tables are joined on the device at the end with the same pack/stitch
+kernels the multi-GPU path uses (cutdet.shard.stitch_local), so the result is the table of the whole video.
+
+Frame exactness.  A worker that starts at frame ``lo`` relies on OpenCV's frame-accurate seek.  That is checked, not assumed:
+every worker but the last decodes ONE frame past its range and reports a CRC of it, which must equal the CRC of the next
+worker's first frame; on a mismatch (a container whose seek is not frame accurate) ``DecodePool`` raises ``SeekMismatch`` and
+the caller falls back to one sequential decoder, which reads exactly what the reference reads.
+
+Workers import only numpy and cv2 (this module has no torch import at module level).
+"""
+from __future__ import annotations
+
+import multiprocessing as mp
+import os
+import queue
+import zlib
+from multiprocessing import shared_memory
+
+import numpy as np
+
+
+class SeekMismatch(RuntimeError):
+    """The first frame a worker decoded after its seek is not the frame that follows the previous worker's range."""
+
+
+def probe_video(path: str):
+    """(n_frames from the container, height, width) -- the size from a decoded frame, which is authoritative."""
+    import cv2
+    cap = cv2.VideoCapture(path)
+    n = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    ret, frame = cap.read()
+    cap.release()
+    if not ret:
+        return 0, 0, 0
+    return n, int(frame.shape[0]), int(frame.shape[1])
+
+
+def _crc(a: np.ndarray) -> int:
+    return zlib.crc32(memoryview(np.ascontiguousarray(a))) & 0xFFFFFFFF
+
+
+def _worker_main(worker: int, path: str, shm_name: str, ring_shape: tuple, my_slots: list, lo: int, hi: int, to_eof: bool,
+                 rows: np.ndarray, check_next: bool, free_q, ready_q):
+    """Decode frames [lo, hi) (or to the end of the file when ``to_eof``) into this worker's ring slots.
+    Messages to the parent: ("chunk", worker, slot, n_frames, first_frame, crc_of_first_frame_or_None),
+    ("done", worker, frames_decoded, crc_of_frame_hi_or_None), ("error", worker, text)."""
+    shm = None
+    try:
+        import cv2
+        cap = cv2.VideoCapture(path)
+        if not cap.isOpened():
+            raise RuntimeError(f"cannot open {path}")
+        if lo > 0:
+            cap.set(cv2.CAP_PROP_POS_FRAMES, lo)
+        shm = shared_memory.SharedMemory(name=shm_name)
+        ring = np.ndarray(ring_shape, dtype=np.uint8, buffer=shm.buf)
+        chunk = ring_shape[1]
+        done, eof, first = 0, False, True
+        while not eof and (to_eof or lo + done < hi):
+            slot = free_q.get()
+            if slot is None:                    # the parent is shutting down
+                return
+            view, k, crc = ring[slot], 0, None
+            while k < chunk and (to_eof or lo + done < hi):
+                ret, frame = cap.read()
+                if not ret:
+                    eof = True
+                    break
+                view[k] = frame[rows]           # only the source rows the resize reads
+                if first:
+                    crc, first = _crc(view[k]), False
+                k += 1
+                done += 1
+            if k:
+                ready_q.put(("chunk", worker, slot, k, lo + done - k, crc))
+            else:
+                free_q.put(slot)
+        tail = None
+        if check_next and not eof:              # one frame past my range: must be the next worker's first frame
+            ret, frame = cap.read()
+            if ret:
+                tail = _crc(frame[rows])
+        cap.release()
+        ready_q.put(("done", worker, done, tail))
+    except Exception as e:      # pragma: no cover  (reported to the parent, which raises)
+        ready_q.put(("error", worker, repr(e)))
+    finally:
+        if shm is not None:
+            shm.close()
+
+
+class DecodePool:
+    """Iterate over decoded chunks: ``for worker, frames, first_frame, slot in pool`` where ``frames`` is a pinned uint8 torch
+    tensor view [n, len(rows), w, 3] of the ring (row-compacted BGR frames in decode order within the worker's range).  Call
+    ``pool.release(slot, event)`` once the frames have been queued for upload: the slot goes back to its worker when the CUDA
+    event has completed.  ``pool.ranges`` lists each worker's [lo, hi); ``pool.frames_decoded`` the true counts afterwards."""
+
+    def __init__(self, path: str, rows: np.ndarray, src_h: int, src_w: int, chunk: int, n_workers: int, n_frames: int,
+                 to_eof: bool = True, slots_per_worker: int = 2, pin: bool = True, start_method: str | None = None):
+        import torch
+        self.path, self.chunk = path, int(chunk)
+        self.rows = np.ascontiguousarray(rows, dtype=np.int64)
+        n_workers = max(1, min(int(n_workers), max(1, -(-n_frames // self.chunk)))) if n_frames > 0 else 1
+        self.n_workers = n_workers
+        per = -(-n_frames // n_workers) if n_frames > 0 else 0
+        per = -(-per // self.chunk) * self.chunk                     # whole chunks per range (the last range takes the rest)
+        self.ranges = []
+        for w in range(n_workers):
+            lo = min(n_frames, w * per) if n_frames > 0 else 0
+            hi = n_frames if w == n_workers - 1 else min(n_frames, lo + per)
+            self.ranges.append((lo, hi))
+        self.to_eof = bool(to_eof)
+        n_slots = n_workers * slots_per_worker
+        self.ring_shape = (n_slots, self.chunk, len(self.rows), src_w, 3)
+        nbytes = int(np.prod(self.ring_shape))
+        self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        self._ring_np = np.ndarray(self.ring_shape, dtype=np.uint8, buffer=self._shm.buf)
+        self.ring = torch.from_numpy(self._ring_np)
+        self._registered = False
+        if pin and torch.cuda.is_available():
+            err = torch.cuda.cudart().cudaHostRegister(self.ring.data_ptr(), nbytes, 0)
+            self._registered = int(err) == 0
+        # fork: the workers start at once and never touch CUDA or torch (they run _worker_main: numpy + cv2 only), which is what
+        # torch's own DataLoader workers rely on; "spawn" re-imports the parent's __main__ (and torch with it) in every worker
+        if start_method is None:
+            start_method = "fork" if "fork" in mp.get_all_start_methods() else "spawn"
+        ctx = mp.get_context(start_method)
+        self._ready = ctx.Queue()
+        self._free = [ctx.Queue() for _ in range(n_workers)]
+        self._procs = []
+        self._pending = []                 # (event, slot)
+        self._slot_owner = {}
+        for w in range(n_workers):
+            slots = list(range(w * slots_per_worker, (w + 1) * slots_per_worker))
+            for s in slots:
+                self._slot_owner[s] = w
+                self._free[w].put(s)
+            lo, hi = self.ranges[w]
+            last = w == n_workers - 1
+            p = ctx.Process(target=_worker_main, daemon=True,
+                            args=(w, path, self._shm.name, self.ring_shape, slots, lo, hi, self.to_eof and last, self.rows,
+                                  not last, self._free[w], self._ready))
+            p.start()
+            self._procs.append(p)
+        self.frames_decoded = [0] * n_workers
+        self._first_crc = [None] * n_workers
+        self._tail_crc = [None] * n_workers
+        self._closed = False
+
+    # ------------------------------------------------------------------ slots
+    def release(self, slot: int, event=None) -> None:
+        """The slot's frames have been handed to the GPU; ``event`` completes when the H2D copy has read them."""
+        if event is None:
+            self._free[self._slot_owner[slot]].put(slot)
+        else:
+            self._pending.append((event, slot))
+
+    def _reap(self, block: bool = False) -> None:
+        keep = []
+        for i, (ev, slot) in enumerate(self._pending):
+            if block and i == 0:
+                ev.synchronize()
+            if ev.query():
+                self._free[self._slot_owner[slot]].put(slot)
+            else:
+                keep.append((ev, slot))
+        self._pending = keep
+
+    # ------------------------------------------------------------------ iteration
+    def __iter__(self):
+        running = self.n_workers
+        while running:
+            self._reap()
+            try:
+                msg = self._ready.get(timeout=0.002 if self._pending else 1.0)
+            except queue.Empty:
+                if self._pending:
+                    self._reap(block=True)
+                elif not any(p.is_alive() for p in self._procs) and self._ready.empty():
+                    raise RuntimeError("decode workers exited without reporting")
+                continue
+            kind = msg[0]
+            if kind == "error":
+                self.close()
+                raise RuntimeError(f"decode worker {msg[1]} failed: {msg[2]}")
+            if kind == "done":
+                _, w, n, tail = msg
+                self.frames_decoded[w] = n
+                self._tail_crc[w] = tail
+                running -= 1
+                continue
+            _, w, slot, k, first_frame, crc = msg
+            if crc is not None:
+                self._first_crc[w] = crc
+            yield w, self.ring[slot, :k], first_frame, slot
+        self._check_seams()
+
+    def _check_seams(self) -> None:
+        for w in range(self.n_workers - 1):
+            lo, hi = self.ranges[w]
+            if self.frames_decoded[w] != hi - lo:
+                raise SeekMismatch(f"worker {w} decoded {self.frames_decoded[w]} frames of its range [{lo}, {hi}): the "
+                                   "container's frame count is not reliable")
+            nxt = self._first_crc[w + 1]
+            if self._tail_crc[w] is not None and nxt is not None and self._tail_crc[w] != nxt:
+                raise SeekMismatch(f"frame {hi} decoded after a seek differs from the same frame decoded in sequence")
+
+    # ------------------------------------------------------------------ teardown
+    def close(self) -> None:
+        if self._closed:
+            return
+        self._closed = True
+        for q in self._free:
+            try:
+                q.put(None)
+            except Exception:
+                pass
+        for p in self._procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.terminate()
+        import torch
+        if self._registered:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaHostUnregister(self.ring.data_ptr())
+        self.ring = None
+        self._ring_np = None
+        try:
+            self._shm.close()
+            self._shm.unlink()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def default_workers() -> int:
+    return max(1, min(8, (os.cpu_count() or 2) // 2))

@@ -3,9 +3,11 @@
     frames --K1--> conv stack --K3--> logits --K4--> (label, max logit) --K5--> run table        (per chunk)
     ... finish(): close the open run;  smooth(): K6 glue_orphans + combine_adjacent_segments
 
-One instance serves one contiguous time range of a video (the whole video on one GPU, or one rank's shard).
-Host frames are uploaded on a copy stream into one of two device buffers (only the source rows the resize reads),
-so the copy of chunk i+1 overlaps the kernels of chunk i.
+One instance serves one contiguous time range of a video (the whole video on one GPU, or one rank's shard) -- or, with
+``n_ranges`` > 1, several time ranges that arrive interleaved (the decode workers of cutdet.decode each own one): every range
+has its own streaming run-length encoder, the kernels, buffers and staging are shared, and ``finish_ranges()`` joins the
+ranges' tables on the device.  Host frames are uploaded on a copy stream into one of two device buffers (only the source rows
+the resize reads), so the copy of chunk i+1 overlaps the kernels of chunk i.
 """
 from __future__ import annotations
 
@@ -18,11 +20,13 @@ from . import _cabi, engine
 
 class FramePipeline:
     def __init__(self, net: engine.NativeNet, plan: engine.ResizePlan, max_chunk: int, table_capacity: int,
-                 device="cuda"):
+                 device="cuda", n_ranges: int = 1):
         self.net, self.plan = net, plan
         self.device = torch.device(device)
         self.max_chunk = int(max_chunk)
-        self.encoder = engine.RunLengthEncoder(table_capacity, self.device)
+        self.encoders = [engine.RunLengthEncoder(table_capacity, self.device) for _ in range(max(1, int(n_ranges)))]
+        self.encoder = self.encoders[0]
+        self.range_frames = [0] * len(self.encoders)
         self.logits = torch.empty((self.max_chunk, net.out_features), dtype=torch.float32, device=self.device)
         self.labels = torch.empty(self.max_chunk, dtype=torch.uint8, device=self.device)
         self.top = torch.empty(self.max_chunk, dtype=torch.float32, device=self.device)
@@ -35,7 +39,7 @@ class FramePipeline:
         net.workspace(self.max_chunk, plan.dst_h, plan.dst_w, self.device)
 
     # ------------------------------------------------------------------ per chunk
-    def _score(self, frames: torch.Tensor, compact: bool) -> None:
+    def _score(self, frames: torch.Tensor, compact: bool, rng: int = 0) -> None:
         n = frames.shape[0]
         if n > self.max_chunk:
             raise ValueError(f"chunk of {n} frames exceeds max_chunk={self.max_chunk}")
@@ -44,14 +48,15 @@ class FramePipeline:
         labels, top = self.labels[:n], self.top[:n]
         _cabi.check(_cabi.lib().cutdet_argmax(logits.data_ptr(), n, logits.shape[1], labels.data_ptr(), top.data_ptr(),
                                               torch.cuda.current_stream().cuda_stream))
-        self.encoder.append(labels, top)
+        self.encoders[rng].append(labels, top)
+        self.range_frames[rng] += n
         self.n_frames += n
 
-    def push_device(self, frames: torch.Tensor, compact: bool = False) -> None:
+    def push_device(self, frames: torch.Tensor, compact: bool = False, rng: int = 0) -> None:
         """Frames already in HBM: uint8 BGR HWC [n, rows, w, 3]."""
-        self._score(frames, compact)
+        self._score(frames, compact, rng)
 
-    def push_host(self, frames: torch.Tensor, compact: bool = False) -> torch.cuda.Event:
+    def push_host(self, frames: torch.Tensor, compact: bool = False, rng: int = 0) -> torch.cuda.Event:
         """Decoded frames in host memory, uint8 BGR HWC [n, h, w, 3] (``compact``: [n, len(plan.rows), w, 3], only the source
         rows the resize reads, as the decode workers store them): upload the needed rows, then score.
 
@@ -91,7 +96,7 @@ class FramePipeline:
         if not frames.is_pinned():
             uploaded.synchronize()          # pageable source: never leave a copy in flight behind the caller's back
         compute.wait_event(uploaded)
-        self._score(self._stage[slot][:n], True)
+        self._score(self._stage[slot][:n], True, rng)
         done = torch.cuda.Event()
         done.record(compute)
         self._stage_events[slot] = done
@@ -105,10 +110,21 @@ class FramePipeline:
     # ------------------------------------------------------------------ end of the range
     def finish(self) -> engine.DeviceRunTable:
         """Close the open run; the table then equals Segmentation(scores).te for this range (local frame numbers)."""
+        if len(self.encoders) > 1:
+            return self.finish_ranges()[0]
         return self.encoder.finish()
 
+    def finish_ranges(self, capacity: int | None = None):
+        """Several time ranges: close every range's open run and join the tables in range order (cutdet_shard_pack +
+        cutdet_stitch_packed, no host synchronisation).  Returns (table of the whole sequence, total_frames device tensor)."""
+        from . import shard
+        tables = [e.finish() for e in self.encoders]
+        return shard.stitch_local(tables, self.range_frames, capacity or shard.DEFAULT_CAPACITY)
+
     def reset(self) -> None:
-        self.encoder.reset()
+        for e in self.encoders:
+            e.reset()
+        self.range_frames = [0] * len(self.encoders)
         self.n_frames = 0
         self.h2d_bytes = 0
 

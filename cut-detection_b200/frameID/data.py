@@ -9,8 +9,9 @@ does to each decoded frame on the CPU -- cv2.resize(INTER_LINEAR), float convers
 (data.py:218-228) -- is the K1 CUDA kernel here, bit-exact with the reference's result.  Consequently the tensors
 this dataset yields live on the GPU; ``batch.to(device)`` in the reference's loop becomes a no-op.
 
-Addition: ``VideoDataset.frame_batches(n)`` yields pinned uint8 batches of raw decoded frames for the fused
-frames->logits path (see cut-detection_b200/segment_video.py).
+``VideoDataset`` keeps the reference's one-frame-at-a-time contract.  The CLI does not go through it: it decodes with worker
+processes into a reusable pinned ring and streams chunks through ``cutdet.pipeline.FramePipeline`` (cutdet/decode.py,
+cut-detection_b200/segment_video.py).
 """
 from __future__ import annotations
 
@@ -80,28 +81,6 @@ class VideoDataset(IterableDataset):
         plan = self._plan_for(frame)
         dev = torch.from_numpy(np.ascontiguousarray(frame)).to(self.device)[None]
         return _engine.preprocess_f32(plan, dev)[0]
-
-    def frame_batches(self, batch_size: int, compact_rows: bool = True):
-        """Yield (plan, frames_u8_pinned [b, rows, w, 3], compact) with raw decoded frames; only the source rows the
-        resize reads are kept when ``compact_rows`` (at 720p that is 144 of 720 rows, a 5x smaller H2D copy)."""
-        buf = None
-        n = 0
-        plan = None
-        while True:
-            ret, frame = self.cap.read()
-            if ret:
-                plan = self._plan_for(frame)
-                if buf is None:
-                    rows = len(plan.rows) if compact_rows else plan.src_h
-                    buf = torch.empty((batch_size, rows, plan.src_w, 3), dtype=torch.uint8).pin_memory()
-                    view = buf.numpy()
-                view[n] = frame[plan.rows] if compact_rows else frame
-                n += 1
-            if n == batch_size or (not ret and n > 0):
-                yield plan, buf[:n], compact_rows
-                buf, n = None, 0        # a fresh pinned buffer: the previous one may still be in flight
-            if not ret:
-                return
 
     def __len__(self):
         """Frame count reported by the container."""

@@ -3,14 +3,18 @@ running on the B200 kernels.
 
     python segment_video.py <video> [--output_path CSV] [--base-threshold 100] [--blank-threshold 10]
                             [--batch-size 128] [--print-every 50] [--frame-limit N] [--cpu] [@argsfile]
+                            [--decode-workers W]
 
 Differences from the reference, all behind the same interface:
-  * decoded frames go to the GPU as uint8 (only the source rows the resize reads), K1 does resize/layout/normalise
-    there and feeds the classifier directly; logits never leave the device until the run table is built;
+  * the frames are decoded by W worker processes, each on its own contiguous time range of the video, into one reusable
+    pinned ring (cutdet.decode; W = 1 is the reference's sequential decode moved off the main thread);
+  * decoded frames go to the GPU as uint8 (only the source rows the resize reads) through ``FramePipeline.push_host``: K1 does
+    resize/layout/normalise there and feeds the classifier directly, K4/K5 turn the logits into a run table chunk by chunk --
+    logits never leave the device and nothing per-frame is kept until the end;
   * ``--cpu`` is accepted for compatibility but refused: this build has no CPU path.
 """
 from frameID.net import load_default_net
-from frameID.data import VideoDataset
+from frameID.data import open_video
 from frameID.segmentation import Segmentation
 
 import torch
@@ -25,6 +29,56 @@ logging.basicConfig(
 )
 
 
+def score_video(path, net, batch_size, frame_limit=None, print_every=0, decode_workers=None, device="cuda:0"):
+    """Decode -> K1 -> CNN -> K4 -> K5 for a whole video: returns (DeviceRunTable of the initial runs, frames scored).
+    What the reference's batch loop plus ``Segmentation.__init__`` compute (segment_video.py:38-62), streamed."""
+    from cutdet import decode, engine, pipeline
+
+    n_meta, h, w = decode.probe_video(path)
+    if h == 0:
+        raise IndexError("the video has no decodable frame")          # what Segmentation(empty scores) ends in
+    # the reference stops after the first batch that takes it past the limit: (i + 1) * batch_size > frame_limit
+    n_frames = n_meta
+    if frame_limit is not None:
+        n_frames = (frame_limit // batch_size + 1) * batch_size
+        if n_meta > 0:
+            n_frames = min(n_meta, n_frames)
+    to_eof = frame_limit is None           # the last worker reads until cap.read() fails, like the reference
+    workers = decode.default_workers() if decode_workers is None else max(1, int(decode_workers))
+    if n_frames <= 0:
+        workers = 1
+    native = net._native()
+    plan = engine.ResizePlan.for_video(h, w, 256)
+    for attempt in range(2):
+        pool = decode.DecodePool(path, plan.rows, h, w, batch_size, workers, max(n_frames, 0), to_eof=to_eof)
+        # a run table never has more rows than frames; a range that outgrows this (a container that under-reports its length)
+        # is reported as an overflow by the table, not silently truncated
+        capacity = max(hi - lo for lo, hi in pool.ranges) + (1 << 16)
+        pipe = pipeline.FramePipeline(native, plan, batch_size, capacity, device, n_ranges=pool.n_workers)
+        try:
+            scored = 0
+            for worker, frames, first_frame, slot in pool:
+                uploaded = pipe.push_host(frames, compact=True, rng=worker)
+                pool.release(slot, uploaded)
+                scored += 1
+                if print_every > 0 and scored % print_every == 0:
+                    logging.info(f"Scored batch {scored} ({scored * batch_size} frames).")
+            table, total = pipe.finish_ranges()
+            try:
+                table.count()
+            except engine.ShardOverflow as e:        # a range with more runs than the default join capacity
+                table, total = pipe.finish_ranges(capacity=1 << int(e.needed - 1).bit_length())
+            return table, pipe.n_frames
+        except decode.SeekMismatch as e:
+            if attempt or workers == 1:
+                raise
+            logging.warning(f"{e}; decoding sequentially instead")
+            workers = 1
+        finally:
+            torch.cuda.synchronize()
+            pool.close()
+
+
 def main(args):
 
     if not os.path.isfile(args.input_path):
@@ -35,34 +89,16 @@ def main(args):
     device = "cuda:0"
     logging.info(f"Using {device}")
 
-    ds = VideoDataset(args.input_path, resize=256, device=device)
-
     net, params = load_default_net()
     net.eval()
     net.to(device)
     logging.info("Loaded default classifier.")
 
-    copy_stream = torch.cuda.Stream(device=device)
-    yy = []
     with torch.no_grad():
-        for i, (plan, frames, compact) in enumerate(ds.frame_batches(args.batch_size)):
-            with torch.cuda.stream(copy_stream):
-                on_device = frames.to(device, non_blocking=True)
-            torch.cuda.current_stream().wait_stream(copy_stream)
-            yy.append(net.forward_frames(plan, on_device, compact))
-            on_device.record_stream(torch.cuda.current_stream())
+        table, n_scored = score_video(args.input_path, net, args.batch_size, args.frame_limit, args.print_every,
+                                      getattr(args, "decode_workers", None), device)
 
-            if args.print_every > 0:
-                if i % args.print_every == args.print_every - 1:
-                    logging.info(f"Scored batch {i+1} ({(i+1) * args.batch_size} frames).")
-
-            # same check as the reference: after the batch is scored, strict '>'
-            if args.frame_limit is not None and (i + 1) * args.batch_size > args.frame_limit:
-                break
-
-        yy = torch.cat(yy, 0)
-
-        seg = Segmentation(yy)
+        seg = Segmentation.from_table(table)
         logging.info(f"Found {len(seg)} initial segments")
         seg.glue_orphans(args.base_threshold, args.blank_threshold)
         logging.info(f"Revised to {len(seg)} segments through orphan combination.")
@@ -91,6 +127,8 @@ sv_parser.add_argument("--frame-limit", type=int, default=None,
                        help="Limit how many frames are processed. Mainly for testing.")
 sv_parser.add_argument("--cpu", action="store_true",
                        help="Accepted for compatibility; refused (this build has no CPU path).")
+sv_parser.add_argument("--decode-workers", type=int, default=None,
+                       help="Decoder processes, each on its own time range of the video (default: half the host cores, at most 8).")
 
 if __name__ == "__main__":
 

@@ -112,6 +112,13 @@ def test_cli_on_a_synthetic_clip(tmp_path, prod_weights):
     want = oseg.segment(logits, 100, 10)[3]
     assert open(out_csv, "rb").read() == want
     assert want == b"0,a22\r\n150,b\r\n180,ez\r\n"
+    # any number of decode workers (time ranges joined on the device) gives the same bytes; 1 = sequential decode
+    for workers in ("1", "2", "3"):
+        r = subprocess.run([sys.executable, os.path.join(root, "cut-detection_b200", "segment_video.py"), path,
+                            "--output_path", out_csv, "--batch-size", "32", "--print-every", "0", "--decode-workers", workers],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out_csv, "rb").read() == want, workers
     # default output path and the --frame-limit quirk (check happens after the batch is scored, strict >)
     r = subprocess.run([sys.executable, os.path.join(root, "cut-detection_b200", "segment_video.py"), path,
                         "--batch-size", "64", "--frame-limit", "64", "--print-every", "0"], capture_output=True, text=True)
@@ -177,3 +184,82 @@ def test_split_video_script_writes_the_references_jpegs(tmp_path):
     assert names == sorted(os.listdir(ref_dir)) and len(names) == 66
     for name in names:
         assert open(out / name, "rb").read() == open(ref_dir / name, "rb").read(), name
+
+
+def test_decode_pool_ranges_equal_sequential_decode(tmp_path):
+    """cutdet.decode: W worker processes on contiguous time ranges write row-compacted frames into the pinned ring; put back in
+    frame order they are byte for byte what one cv2.VideoCapture reads in sequence (reference frameID/data.py:211-213), the
+    seam check passes, and the streamed run table of noisy content equals Segmentation(scores) over the whole clip."""
+    import cv2
+    from cutdet import decode, engine, pipeline
+    from frameID.net import load_default_net
+    from frameID.segmentation import Segmentation
+    w, h, n = 640, 360, 300
+    path = str(tmp_path / "noisy.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 30, (w, h))
+    rng = np.random.default_rng(4)
+    for i in range(n):
+        frame = kat_inputs.stripes(h, w, 20, (i // 40) % 2 == 0).copy()
+        frame[: h // 4, : w // 4] = rng.integers(0, 256, (h // 4, w // 4, 3), dtype=np.uint8)
+        vw.write(frame)
+    vw.release()
+    cap = cv2.VideoCapture(path)
+    seq = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        seq.append(f)
+    seq = np.stack(seq)
+    n_meta, hh, ww = decode.probe_video(path)
+    assert (n_meta, hh, ww) == (n, h, w)
+    plan = engine.ResizePlan.for_video(h, w, 256)
+    net, _ = load_default_net()
+    net.eval().to("cuda")
+    with torch.no_grad():
+        want_scores = net.forward_frames(plan, torch.from_numpy(seq).cuda())
+    want = Segmentation(want_scores).te
+    for workers in (1, 2, 4):
+        pool = decode.DecodePool(path, plan.rows, h, w, 48, workers, n)
+        assert pool.ring.is_pinned()
+        pipe = pipeline.FramePipeline(net._native(), plan, 48, n, "cuda", n_ranges=pool.n_workers)
+        got = np.zeros((n, len(plan.rows), w, 3), np.uint8)
+        for wk, frames, first, slot in pool:
+            got[first:first + frames.shape[0]] = frames.numpy()
+            pool.release(slot, pipe.push_host(frames, compact=True, rng=wk))
+        table, total = pipe.finish_ranges()
+        te = table.to_te()
+        pool.close()
+        assert np.array_equal(got, seq[:, plan.rows]), workers
+        assert int(total.item()) == n and sum(pool.frames_decoded) == n
+        for k in ("end_frames", "frame_types", "run_lengths", "start_frames"):
+            assert torch.equal(te[k], want[k]), (workers, k)
+        assert torch.allclose(te["score_means"], want["score_means"], rtol=2e-6)
+
+
+def test_push_host_ownership_contract():
+    """FramePipeline.push_host from pinned memory is asynchronous: the returned event says when the buffer may be refilled.
+    Scribbling over it after the event has completed must not change the result; pageable memory is safe at once."""
+    from cutdet import engine, pipeline, synth
+    from frameID.net import load_default_net
+    net, _ = load_default_net()
+    net.eval().to("cuda")
+    h, w, n = 360, 640, 200
+    clip = synth.SyntheticClip(h, w, n, seed=9, runs=[(0, 70), (2, 30), (1, 100)])
+    frames = torch.from_numpy(clip.frames_numpy(0, n))
+    plan = engine.ResizePlan.for_video(h, w, 256)
+    results = []
+    for pinned in (True, False):
+        pipe = pipeline.FramePipeline(net._native(), plan, 100, n, "cuda")
+        buf = torch.empty((100, h, w, 3), dtype=torch.uint8)
+        if pinned:
+            buf = buf.pin_memory()
+        for c in range(2):
+            buf.copy_(frames[c * 100:(c + 1) * 100])
+            ev = pipe.push_host(buf)
+            if pinned:
+                ev.synchronize()
+            buf.fill_(255)                       # refill: must not reach the frames already handed over
+        results.append(pipe.finish().to_te())
+    for te in results:
+        assert te["frame_types"].tolist() == [0, 2, 1] and te["run_lengths"].tolist() == [70, 30, 100]

@@ -1,12 +1,13 @@
 #!/usr/bin/env python3
-"""Same-box A/B of bench.py under different environment switches (one gpurun call).
+"""Same-box A/B of bench.py under different net options or builds of the library (one gpurun call).
 
 Boxes differ by several per cent and the default 80-step run is power-capped (profiles/README.md, v9), so two variants are only
 comparable when they are measured on ONE box, interleaved, a few times each:
 
-    python tools/ab_bench.py --reps 2 --steps 30,80 -- "" "CUTDET_SUB_BATCH=296" "CUTDET_NO_PDL=1"
+    python tools/ab_bench.py --reps 2 --steps 30,80 -- "" "sub_batch=296" "no_pdl=1" "lib=gpurun_out/libcutdet_old.so"
 
-Each variant is a space-separated list of NAME=VALUE pairs ("" = the defaults).  Prints one line per run and a summary table
+Each variant is a space-separated list of NAME=VALUE pairs ("" = the defaults): net options (bench.py --net-opt) or
+``lib=PATH`` (bench.py --lib: another build of libcutdet_b200.so).  Prints one line per run and a summary table
 (mean / min / max frames per second per variant and step count); with --out also writes them to a text file for profiles/."""
 import argparse
 import json
@@ -32,15 +33,14 @@ def main():
     for rep in range(a.reps):
         for v in a.variants:                                     # interleaved: drift over the call hits every variant alike
             for st in steps:
-                env = dict(os.environ)
+                cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(st), "--no-e2e", "--no-cpu-baseline"]
                 for kv in v.split():
                     k, _, val = kv.partition("=")
-                    env[k] = val
-                cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(st), "--no-e2e", "--no-cpu-baseline"]
+                    cmd += ["--lib", val] if k == "lib" else ["--net-opt", kv]
                 try:
-                    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=a.timeout)
+                    r = subprocess.run(cmd, capture_output=True, text=True, timeout=a.timeout)
                     d = json.loads(r.stdout.strip().splitlines()[-1])
-                    ok = bool(d.get("parity", {}).get("timed_job_runs_equal_plan"))
+                    ok = bool(d.get("parity", {}).get("runs_equal_plan")) and bool(d.get("parity", {}).get("smoothed_equal_oracle"))
                     line = f"AB rep={rep} variant='{v}' steps={st} frames_per_s={d['value']:.0f} ms_per_step={d['ms_per_step']:.4f} parity={ok} clocks={d.get('clocks')}"
                     if ok:
                         results.setdefault((v, st), []).append(d["value"])

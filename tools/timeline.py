@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""Clock stamps of CTA 0 of conv1_fused_tc (kernel 1) or conv2_tc (kernel 2): cutdet_net_debug_timeline arms a caller-owned
+device buffer, one full sub-batch is run, the stamps come back relative to the kernel's first stamp.
+
+    python tools/timeline.py --kernel 1 --out gpurun_out/timeline1.txt [--height 720 --width 1280]
+
+Stamp indices are documented next to the `tl[...]` stores in csrc/conv_tc.cu."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "cut-detection_b200")]
+
+
+def main():
+    import torch
+    from cutdet import _cabi, engine, synth
+    from frameID.net import load_default_net
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--kernel", type=int, default=1)
+    ap.add_argument("--height", type=int, default=720)
+    ap.add_argument("--width", type=int, default=1280)
+    ap.add_argument("--frames", type=int, default=444)
+    ap.add_argument("--out", default="gpurun_out/timeline.txt")
+    ap.add_argument("--net-opt", action="append", default=[])
+    a = ap.parse_args()
+    net, _ = load_default_net()
+    native = net.eval().to("cuda")._native()
+    for kv in a.net_opt:
+        k, _, v = kv.partition("=")
+        native.set_option(k, int(v))
+    plan = engine.ResizePlan.for_video(a.height, a.width, 256)
+    frames = synth.SyntheticClip(a.height, a.width, a.frames, seed=1).frames_torch(0, a.frames, device="cuda")
+    for _ in range(3):
+        native.forward_frames(plan, frames)
+    torch.cuda.synchronize()
+    stamps = torch.zeros(2048, dtype=torch.int64, device="cuda")
+    _cabi.check(_cabi.lib().cutdet_net_debug_timeline(native.handle, a.kernel, stamps.data_ptr(), 2048))
+    native.forward_frames(plan, frames)
+    torch.cuda.synchronize()
+    _cabi.check(_cabi.lib().cutdet_net_debug_timeline(native.handle, 0, None, 0))
+    h = stamps.cpu().tolist()
+    t0 = h[2047] if a.kernel == 1 else h[0]
+    os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+    with open(a.out, "w") as f:
+        for i, v in enumerate(h):
+            if v:
+                f.write(f"{i} {v - t0}\n")
+    print(f"wrote {sum(1 for v in h if v)} stamps to {a.out}")
+
+
+if __name__ == "__main__":
+    main()
