@@ -56,6 +56,9 @@ K1_BYTES_720P = K1_SRC_BYTES_720P + 221_184  # ... + a bf16 [3,144,256] output (
 FLOPS = {"L0": 95_551_488, "L1": 169_205_760, "L2": 18_579_456, "head": 49_152 + 192}
 NET_FLOPS = sum(FLOPS.values())            # 283,386,048
 CONTRASTIVE_FLOPS = 147_165_696            # config 5 encoder (C = 32), SURVEY 8 a-13
+# configs[0]: the 60 s clip as a fixed plan of (label, frames) runs with every kind of run the smoothing pass treats differently
+# (long runs, sub-threshold real runs, sub-threshold blanks), 1,800 frames in all
+CLIP_RUNS = [(0, 420), (2, 20), (1, 380), (2, 5), (0, 40), (1, 300), (2, 12), (0, 90), (1, 333), (2, 30), (0, 170)]
 
 
 def parse_args():
@@ -481,7 +484,7 @@ def run_game(rig: Rig):
         from oracle import net as onet
         from oracle.reference_path import CpuReferencePath
         n = args.cpu_sample
-        sample_clip = synth.SyntheticClip(HEIGHT, WIDTH, n, seed=args.seed + 101)
+        sample_clip = synth.SyntheticClip(HEIGHT, WIDTH, n, seed=args.seed + 101, runs=clip_runs(n))
         frames_dev = sample_clip.frames_torch(0, n, device=dev)
         frames_host = frames_dev.cpu().numpy()
         weights, wparams = onet.load_weights_npz(os.path.join(PKG, "frameID", "prod_net", "prod_net_weights.npz"))
@@ -530,6 +533,20 @@ def run_game(rig: Rig):
             "cpu_baseline": cpu_baseline, "strong": strong, "cli": cli, "kernels": table, "parity": parity,
         }
         _emit(line)
+
+
+def clip_runs(n: int):
+    """CLIP_RUNS cut or stretched to n frames."""
+    runs, total = [], 0
+    for lab, length in CLIP_RUNS * (n // 1800 + 1):
+        if runs and runs[-1][0] == lab:
+            lab = (lab + 1) % 3
+        length = min(length, n - total)
+        if length <= 0:
+            break
+        runs.append((lab, length))
+        total += length
+    return runs
 
 
 def kernel_table(kernels: dict, prof_steps: int, chunk: int, k1_src_bytes: int):
@@ -769,7 +786,7 @@ def run_cli_only(rig: Rig):
     from oracle import net as onet
     from oracle.reference_path import CpuReferencePath
     n = rig.args.cpu_sample
-    frames = synth.SyntheticClip(HEIGHT, WIDTH, n, seed=rig.args.seed + 101).frames_numpy(0, n)
+    frames = synth.SyntheticClip(HEIGHT, WIDTH, n, seed=rig.args.seed + 101, runs=clip_runs(n)).frames_numpy(0, n)
     weights, wparams = onet.load_weights_npz(os.path.join(PKG, "frameID", "prod_net", "prod_net_weights.npz"))
     path = CpuReferencePath(weights, wparams)
     cli = run_cli_measurement(rig, frames, path)

@@ -912,6 +912,149 @@ __device__ __forceinline__ void chunk_from_raw(const uint32_t (&w)[5], uint4 &lo
     hi.w = __byte_perm(w[4], K0, 0x7640);                       // B4, then the constant 1024 that multiplies the bias row
 }
 
+// ---- the unfold role of the fused kernels (shared by conv1_fused_tc_kernel and conv1_fused_teams_kernel) ----
+struct F1Ctx {
+    const Conv1Params *p;
+    const FusedSrc *src;
+    uint8_t *s_ring, *s_raw;
+    uint32_t *s_cmp;
+    int *s_yb;
+    int4 *s_xtab;
+    uint64_t *raw_full, *raw_empty, *tile_done;
+    int *s_rows_done, *s_rows_issued;
+    int RPF, Hc, total_u, n_slots, slot_bytes, n_loaders;
+    uint32_t inv_slots;
+    long long *tl;
+};
+
+template <int C, bool GATHER, bool ACC16, int UNFOLD_WARPS>
+__device__ __forceinline__ void f1_unfold_role(const F1Ctx &cx, const int pwarp, const int lane) {
+    constexpr int NP = (F_MAX_DST / 3 + 31) / 32;
+    const Conv1Params &p = *cx.p;
+    const FusedSrc &src = *cx.src;
+    const ResizePlanDev &plan = src.plan;
+    uint8_t *const s_ring = cx.s_ring, *const s_raw = cx.s_raw;
+    uint32_t *const s_cmp = cx.s_cmp;
+    int *const s_yb = cx.s_yb;
+    int4 *const s_xtab = cx.s_xtab;
+    uint64_t *const raw_full = cx.raw_full, *const raw_empty = cx.raw_empty, *const tile_done = cx.tile_done;
+    int *const s_rows_done = cx.s_rows_done, *const s_rows_issued = cx.s_rows_issued;
+    const int H = p.H, P1w = p.P1w, RPF = cx.RPF, Hc = cx.Hc, total_u = cx.total_u, n_slots = cx.n_slots, slot_bytes = cx.slot_bytes;
+    const uint32_t inv_slots = cx.inv_slots;
+    long long *const tl = cx.tl;
+    const int n_loaders = cx.n_loaders;
+    // fast path constants: tap j of pooled column px starts at byte 3*off_x + BS*(3px - 1 + j), BS = 3*step_x; a part is
+    // 32 columns = 96*BS bytes further on (a multiple of 4), so the word offset of part 0 and the byte phase serve all parts
+    const int BS = 3 * plan.gather_step_x, PB = 96 * BS;
+    int off0[5];
+    uint32_t sel[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int b = 3 * plan.gather_off_x + BS * (3 * lane - 1 + j);
+        off0[j] = b & ~3;
+        sel[j] = 0x3210u + (uint32_t)(b & 3) * 0x1111u;
+    }
+    struct Row { int R, sub, slot; bool real; const uint8_t *q0; };
+    int R = 0, sub = pwarp, fi = 0, py = 0;              // u = 3R + sub, R = fi * RPF + py
+    while (sub >= 3) { sub -= 3; ++R; ++py; }
+    int tiles_waited = 0, rows_done = 0;
+    auto next_row = [&](Row &r, int &y_out) {            // describes the row (R, sub, fi, py) point at, waits until it may be
+        while (py >= RPF) { py -= RPF; ++fi; }           // produced (ring space, source row landed), then advances
+        const int y = 3 * py + sub;
+        r.real = y < H && (py < p.P1h || sub == 0);      // index P1h: row 3*P1h if the image has it, else zeros
+        const int n = fi * Hc + y;
+        const int use = (int)__umulhi((uint32_t)n, inv_slots);
+        r.slot = n - use * n_slots;
+        r.R = R; r.sub = sub; y_out = y;
+        r.q0 = s_raw + r.slot * slot_bytes;
+        // positions [R*P1w, (R+1)*P1w) replace those FR_CAP earlier, last read by tile (pos - FR_CAP + P1w) / 128
+        const int last_reader = ((R + 2) * P1w - 1 - FR_CAP) >> 7;      // arithmetic shift: negative = none
+        if (last_reader >= tiles_waited) {
+            mbar_wait(&tile_done[last_reader & (TILE_RING - 1)], (last_reader / TILE_RING) & 1);
+            tiles_waited = last_reader + 1;
+        }
+        if (r.real) {
+            int ld, want;                                // row n is loader n % n_loaders' (n / n_loaders + 1)-th
+            if (n_loaders == 3) { ld = n % 3; want = n / 3 + 1; }
+            else { ld = n & (n_loaders - 1); want = (n >> (n_loaders - 1)) + 1; }     // 1 or 2 loaders
+            while (ld_acquire_shared(&s_rows_issued[ld]) < want) __nanosleep(32);
+            mbar_wait(&raw_full[r.slot], use & 1);
+        }
+        sub += UNFOLD_WARPS % 3; R += UNFOLD_WARPS / 3; py += UNFOLD_WARPS / 3;
+        if (sub >= 3) { sub -= 3; ++R; ++py; }
+    };
+    auto emit = [&](const Row &r, uint32_t (&w)[NP][5]) {
+        const int pos0 = r.R * P1w + lane;
+#pragma unroll
+        for (int part = 0; part < NP; ++part) {
+            const int px = part * 32 + lane;
+            if (px < P1w) {
+                uint4 lo, hi;
+                chunk_from_raw<ACC16>(w[part], lo, hi);                     // zero rows: w = 0 gives the format's zeros
+                const int pos = (pos0 + part * 32) & (FR_CAP - 1);
+                uint8_t *dst = s_ring + r.sub * FR_SUB + pos * 16;
+                *reinterpret_cast<uint4 *>(dst) = lo;
+                *reinterpret_cast<uint4 *>(dst + FR_PLANE) = hi;
+                if (pos < 128) {                                     // mirror past the end of the ring
+                    *reinterpret_cast<uint4 *>(dst + FR_CAP * 16) = lo;
+                    *reinterpret_cast<uint4 *>(dst + FR_CAP * 16 + FR_PLANE) = hi;
+                }
+            }
+        }
+    };
+    auto gather = [&](const Row &r, uint32_t (&w)[NP][5]) {
+        // (lanes past the last column and lane 0's tap -1 read a few bytes outside the row: still this CTA's shared memory)
+#pragma unroll
+        for (int part = 0; part < NP; ++part)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(r.q0 + part * PB + off0[j]);
+                w[part][j] = r.real ? __byte_perm(wp[0], wp[1], sel[j]) : 0u;
+            }
+        if (lane == 0) w[0][0] = 0u;                                 // the padding column left of the image
+    };
+    // (taking two rows per step -- a second row's waits and loads in flight -- was tried: no gain, the SM's ALU pipe is the limit)
+    for (int u = pwarp; u < total_u; u += UNFOLD_WARPS) {
+        Row r0;
+        int y0;
+        const bool stamp = tl && pwarp == 0 && lane == 0 && rows_done < 96;
+        if (stamp) tl[256 + 4 * rows_done] = clock64();
+        next_row(r0, y0);
+        if (stamp) tl[256 + 4 * rows_done + 1] = clock64();
+        uint32_t w0[NP][5];
+        if (GATHER) {
+            gather(r0, w0);
+        } else {
+            // the resized row, each pixel once, into this warp's buffer; then five consecutive words per pooled column
+            uint32_t *cmp = s_cmp + pwarp * F1_CMP_STRIDE;
+            if (r0.real) {
+                const uint8_t *q1 = r0.q0 + (src.n_src - 1) * src.row_bytes;
+                const int b0 = s_yb[2 * y0], b1 = s_yb[2 * y0 + 1];
+                for (int x = lane; x < plan.dst_w; x += 32) cmp[1 + x] = resized_word(plan, r0.q0, q1, s_xtab, b0, b1, x);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int part = 0; part < NP; ++part) {
+                const int px = part * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) w0[part][j] = (r0.real && px < P1w) ? cmp[3 * px + j] : 0u;
+            }
+        }
+        emit(r0, w0);
+        // one fence for both directions: the stores above become visible to the MMA's async-proxy reads, and the loads from
+        // the raw slot are ordered before the async-proxy refill that the release below allows
+        if (stamp) tl[256 + 4 * rows_done + 2] = clock64();
+        fence_proxy_async();
+        __syncwarp();
+        if (stamp) tl[256 + 4 * rows_done + 3] = clock64();
+        ++rows_done;
+        if (lane == 0) {
+            if (r0.real) mbar_arrive(&raw_empty[r0.slot]);
+            st_relaxed_shared(&s_rows_done[pwarp], rows_done);      // (every lane fenced its stores before the __syncwarp)
+        }
+    }
+}
+
 template <int C, bool GATHER, bool ACC16>
 __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_kernel(const Conv1Params p, const FusedSrc src) {
     using RL = F1Roles<ACC16>;
@@ -1082,118 +1225,9 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
         }
     } else if (warp >= 8 && warp < 8 + UNFOLD_WARPS) {
         // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
-        const int pwarp = warp - 8;
-        const int n_loaders = min(LOADER_WARPS, n_slots);
-        // fast path constants: tap j of pooled column px starts at byte 3*off_x + BS*(3px - 1 + j), BS = 3*step_x; a part is
-        // 32 columns = 96*BS bytes further on (a multiple of 4), so the word offset of part 0 and the byte phase serve all parts
-        const int BS = 3 * plan.gather_step_x, PB = 96 * BS;
-        int off0[5];
-        uint32_t sel[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const int b = 3 * plan.gather_off_x + BS * (3 * lane - 1 + j);
-            off0[j] = b & ~3;
-            sel[j] = 0x3210u + (uint32_t)(b & 3) * 0x1111u;
-        }
-        struct Row { int R, sub, slot; bool real; const uint8_t *q0; };
-        int R = 0, sub = pwarp, fi = 0, py = 0;              // u = 3R + sub, R = fi * RPF + py
-        while (sub >= 3) { sub -= 3; ++R; ++py; }
-        int tiles_waited = 0, rows_done = 0;
-        auto next_row = [&](Row &r, int &y_out) {            // describes the row (R, sub, fi, py) point at, waits until it may be
-            while (py >= RPF) { py -= RPF; ++fi; }           // produced (ring space, source row landed), then advances
-            const int y = 3 * py + sub;
-            r.real = y < H && (py < p.P1h || sub == 0);      // index P1h: row 3*P1h if the image has it, else zeros
-            const int n = fi * Hc + y;
-            const int use = (int)__umulhi((uint32_t)n, inv_slots);
-            r.slot = n - use * n_slots;
-            r.R = R; r.sub = sub; y_out = y;
-            r.q0 = s_raw + r.slot * slot_bytes;
-            // positions [R*P1w, (R+1)*P1w) replace those FR_CAP earlier, last read by tile (pos - FR_CAP + P1w) / 128
-            const int last_reader = ((R + 2) * P1w - 1 - FR_CAP) >> 7;      // arithmetic shift: negative = none
-            if (last_reader >= tiles_waited) {
-                mbar_wait(&tile_done[last_reader & (TILE_RING - 1)], (last_reader / TILE_RING) & 1);
-                tiles_waited = last_reader + 1;
-            }
-            if (r.real) {
-                int ld, want;                                // row n is loader n % n_loaders' (n / n_loaders + 1)-th
-                if (n_loaders == 3) { ld = n % 3; want = n / 3 + 1; }
-                else { ld = n & (n_loaders - 1); want = (n >> (n_loaders - 1)) + 1; }     // 1 or 2 loaders
-                while (ld_acquire_shared(&s_rows_issued[ld]) < want) __nanosleep(32);
-                mbar_wait(&raw_full[r.slot], use & 1);
-            }
-            sub += UNFOLD_WARPS % 3; R += UNFOLD_WARPS / 3; py += UNFOLD_WARPS / 3;
-            if (sub >= 3) { sub -= 3; ++R; ++py; }
-        };
-        auto emit = [&](const Row &r, uint32_t (&w)[NP][5]) {
-            const int pos0 = r.R * P1w + lane;
-#pragma unroll
-            for (int part = 0; part < NP; ++part) {
-                const int px = part * 32 + lane;
-                if (px < P1w) {
-                    uint4 lo, hi;
-                    chunk_from_raw<ACC16>(w[part], lo, hi);                     // zero rows: w = 0 gives the format's zeros
-                    const int pos = (pos0 + part * 32) & (FR_CAP - 1);
-                    uint8_t *dst = s_ring + r.sub * FR_SUB + pos * 16;
-                    *reinterpret_cast<uint4 *>(dst) = lo;
-                    *reinterpret_cast<uint4 *>(dst + FR_PLANE) = hi;
-                    if (pos < 128) {                                     // mirror past the end of the ring
-                        *reinterpret_cast<uint4 *>(dst + FR_CAP * 16) = lo;
-                        *reinterpret_cast<uint4 *>(dst + FR_CAP * 16 + FR_PLANE) = hi;
-                    }
-                }
-            }
-        };
-        auto gather = [&](const Row &r, uint32_t (&w)[NP][5]) {
-            // (lanes past the last column and lane 0's tap -1 read a few bytes outside the row: still this CTA's shared memory)
-#pragma unroll
-            for (int part = 0; part < NP; ++part)
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(r.q0 + part * PB + off0[j]);
-                    w[part][j] = r.real ? __byte_perm(wp[0], wp[1], sel[j]) : 0u;
-                }
-            if (lane == 0) w[0][0] = 0u;                                 // the padding column left of the image
-        };
-        // (taking two rows per step -- a second row's waits and loads in flight -- was tried: no gain, the SM's ALU pipe is the limit)
-        for (int u = pwarp; u < total_u; u += UNFOLD_WARPS) {
-            Row r0;
-            int y0;
-            const bool stamp = tl && pwarp == 0 && lane == 0 && rows_done < 96;
-            if (stamp) tl[256 + 4 * rows_done] = clock64();
-            next_row(r0, y0);
-            if (stamp) tl[256 + 4 * rows_done + 1] = clock64();
-            uint32_t w0[NP][5];
-            if (GATHER) {
-                gather(r0, w0);
-            } else {
-                // the resized row, each pixel once, into this warp's buffer; then five consecutive words per pooled column
-                uint32_t *cmp = s_cmp + pwarp * F1_CMP_STRIDE;
-                if (r0.real) {
-                    const uint8_t *q1 = r0.q0 + (src.n_src - 1) * src.row_bytes;
-                    const int b0 = s_yb[2 * y0], b1 = s_yb[2 * y0 + 1];
-                    for (int x = lane; x < plan.dst_w; x += 32) cmp[1 + x] = resized_word(plan, r0.q0, q1, s_xtab, b0, b1, x);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int part = 0; part < NP; ++part) {
-                    const int px = part * 32 + lane;
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) w0[part][j] = (r0.real && px < P1w) ? cmp[3 * px + j] : 0u;
-                }
-            }
-            emit(r0, w0);
-            // one fence for both directions: the stores above become visible to the MMA's async-proxy reads, and the loads from
-            // the raw slot are ordered before the async-proxy refill that the release below allows
-            if (stamp) tl[256 + 4 * rows_done + 2] = clock64();
-            fence_proxy_async();
-            __syncwarp();
-            if (stamp) tl[256 + 4 * rows_done + 3] = clock64();
-            ++rows_done;
-            if (lane == 0) {
-                if (r0.real) mbar_arrive(&raw_empty[r0.slot]);
-                st_relaxed_shared(&s_rows_done[pwarp], rows_done);      // (every lane fenced its stores before the __syncwarp)
-            }
-        }
+        F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
+                 RPF, Hc, total_u, n_slots, slot_bytes, min(LOADER_WARPS, n_slots), inv_slots, tl};
+        f1_unfold_role<C, GATHER, ACC16, UNFOLD_WARPS>(cx, warp - 8, lane);
     } else {
         // ------------------------------------------------------------------ epilogue
         const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
@@ -1259,6 +1293,335 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
     tc_fence_before_sync();
     __syncthreads();
     if (warp == F1_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ K1 + layer 1, one team per block row
+// conv1_fused_tc_kernel above runs ONE MMA issuer and ONE set of epilogue warps over the three block rows of a tile in turn; its
+// clock stamps (profiles/README.md, round 2) show a tile period of ~1,450 cycles against 648 cycles of MMAs: issuing a block
+// row keeps the issuer ~270 cycles (the instruction waits for the tensor pipe), an epilogue warp needs ~450 cycles per block row
+// (barrier, TMEM load, wait::ld, release), and each of the two serial chains waits for the other once per tile.
+// Here every block row dy is its own pipeline:
+//     MMA issuer dy (one warp)  -> acc_full[dy] ->  team dy (four warps, one per TMEM lane quarter) -> acc_empty[dy] -> issuer dy
+// so the three rows' chains run side by side and the tensor pipe always has the next row's MMAs queued.  A team thread reads ALL
+// the channels of its block row (3 dx x C fp16 accumulators = 3C/2 packed registers), takes the max over dx, and the 9-way max
+// is finished by passing the partial maxima DOWN the teams through spare TMEM columns (tcgen05.st / tcgen05.ld: the 80 columns
+// the accumulator leaves free; no shared memory, whose bandwidth the MMAs' operand reads already use):
+//     team 0: max over dx -> p0                team 1: max(p0, max over dx) -> p01            team 2: relu(max(p01, max over dx))
+// Rows complete in that order, so a team never waits for a later one; team 2 applies scale/shift and stores all C channels.
+// The loaders shrink to one warp that issues three rows per turn (one issuing thread sustains ~10 B/clk per row it issues, the
+// chain of waits is paid once per turn).  24 warps; registers 104 (teams) / 64 (unfold) / 40 (issuers + loader).
+struct T1Roles {
+    static constexpr int TEAM_WARPS = 12, UNFOLD_WARPS = 8, UNFOLD_WARP0 = 12, MMA_WARP0 = 20, LOAD_WARP = 23, WARPS = 24, THREADS = 32 * WARPS;
+    static constexpr int REGS_START = 80, REGS_TEAM = 104, REGS_UNFOLD = 64, REGS_LIGHT = 40;
+    static constexpr int ROWS_PER_TURN = 3;
+    static_assert(THREADS * REGS_START == 384 * REGS_TEAM + 256 * REGS_UNFOLD + 128 * REGS_LIGHT, "register pool");
+};
+
+template <int C>
+__device__ __forceinline__ void team_load_row(uint32_t taddr, uint32_t (&row)[3 * C / 2]) {
+    static_assert(C == 48 || C == 32, "channels");
+    if constexpr (C == 48) {            // 144 columns: 64 + 64 + 16 (an x64 load alone does not fit the kernel's launch-time register count)
+        tmem_ld_pack32(taddr, row);
+        tmem_ld_pack32(taddr + 64, row + 32);
+        tmem_ld_pack8(taddr + 128, row + 64);
+    } else {                            // 96 columns: 64 + 32
+        tmem_ld_pack32(taddr, row);
+        tmem_ld_pack16(taddr + 64, row + 32);
+    }
+}
+// the row's columns are ordered [channel half][dx][C/2 channels]: max over dx, channel pairs in channel order
+template <int C>
+__device__ __forceinline__ void team_max_dx(const uint32_t (&row)[3 * C / 2], uint32_t (&m)[C / 2]) {
+    constexpr int Q = C / 4;            // packed pairs per (half, dx)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) m[h * Q + j] = hmax3(row[h * 3 * Q + j], row[h * 3 * Q + Q + j], row[h * 3 * Q + 2 * Q + j]);
+}
+template <int C>
+__device__ __forceinline__ void team_xch_store(uint32_t taddr, const uint32_t (&m)[C / 2]) {
+    tmem_st_u16(taddr, m);
+    if constexpr (C == 48) tmem_st_u8(taddr + 16, m + 16);
+}
+template <int C>
+__device__ __forceinline__ void team_xch_load(uint32_t taddr, uint32_t (&v)[C / 2]) {
+    tmem_ld_u16(taddr, v);
+    if constexpr (C == 48) tmem_ld_u8(taddr + 16, v + 16);
+}
+
+template <int C, bool GATHER>
+__global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(const Conv1Params p, const FusedSrc src) {
+    using RL = T1Roles;
+    constexpr int UNFOLD_WARPS = RL::UNFOLD_WARPS;
+    using S = F1Smem<C, UNFOLD_WARPS>;
+    constexpr int CG = C / 8, NPK = C / 2, ROWPK = 3 * C / 2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *s_w = smem;
+    uint8_t *s_ring = smem + S::OFF_RING;
+    uint8_t *s_raw = smem + S::OFF_RAW;
+    int *s_rowoff = reinterpret_cast<int *>(smem + S::OFF_TAB);               // [y][2]
+    int *s_yb = s_rowoff + 2 * F_MAX_DST;                                       // [y][2]: b0, b1
+    int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);              // [x]: 3*x0, a0 | a1 << 16
+    uint32_t *s_cmp = reinterpret_cast<uint32_t *>(smem + S::OFF_CMP);          // [unfold warp][F1_CMP_STRIDE]
+    uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);       // [3]
+    uint64_t *acc_empty = acc_full + 3;                                         // [3]
+    uint64_t *raw_full = acc_empty + 3;                                         // [RAW_SLOTS_MAX]
+    uint64_t *raw_empty = raw_full + RAW_SLOTS_MAX;                             // [RAW_SLOTS_MAX]
+    uint64_t *tile_done = raw_empty + RAW_SLOTS_MAX;                            // [TILE_RING] tile t's MMAs have completed
+    uint64_t *xch_full = tile_done + TILE_RING;                                 // [2][4]: p0 / p01 of lane quarter q is in TMEM
+    uint64_t *xch_empty = xch_full + 8;                                         // [2][4]: ... has been read
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xch_empty + 8);
+    int *s_rows_done = reinterpret_cast<int *>(tmem_slot + 2);                  // [UNFOLD_WARPS] rows finished by each unfold warp
+    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;                            // [1] rows issued by the loader
+    static_assert((3 + 3 + 2 * RAW_SLOTS_MAX + TILE_RING + 16) * 8 + 8 + (UNFOLD_WARPS + 4) * 4 <= 1024, "barrier block");
+    uint32_t *s_par16 = reinterpret_cast<uint32_t *>(smem + S::OFF_PAR);        // [C/2 scale pairs | C/2 shift pairs]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ResizePlanDev &plan = src.plan;
+    const int H = p.H, P1w = p.P1w, RPF = p.P1h + 1;          // pooled rows per frame incl. the zero row
+    const int Hc = min(H, 3 * p.P1h + 1);                     // resized rows the conv reads (row 3*P1h only if it exists)
+    const int n_frames_cta = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_tiles = (n_frames_cta * RPF * P1w + 127) / 128;
+    const int total_u = 3 * n_frames_cta * RPF;               // resized rows incl. the zero rows, u = 3R + sub
+    const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;
+    const uint32_t inv_slots = 0xffffffffu / (uint32_t)n_slots + 1u;       // n / n_slots = umulhi(n, inv_slots), exact while n * n_slots < 2^32
+
+    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_perm16[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_par16[i] = p.par16[i];
+    // operand-format zeros for the row above the first frame (tile 0's view shifted by -P1w); the last half of the second
+    // plane is the constant 1.0 that multiplies the bias row
+    for (int i = threadIdx.x; i < UNFOLD_WARPS * F1_CMP_STRIDE; i += blockDim.x) s_cmp[i] = 0u;
+    for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
+        reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
+            make_uint4(0u, 0u, 0u, i >= P1w ? 0x3c000000u : 0u);
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        int r0, r1, b0 = 2048, b1 = 0;
+        if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
+        else if (plan.mode == RESIZE_COPY) { r0 = r1 = y; }
+        else if (plan.mode == RESIZE_AREA2) { r0 = 2 * y; r1 = 2 * y + 1; }
+        else { r0 = plan.y0[y]; r1 = plan.y1[y]; b0 = plan.b0[y]; b1 = plan.b1[y]; }
+        if (src.compact) { r0 = plan.row_slot[r0]; r1 = (plan.mode == RESIZE_LINEAR && b1 == 0) ? r0 : plan.row_slot[r1]; }
+        s_rowoff[2 * y] = (int)(r0 * src.row_pitch);
+        s_rowoff[2 * y + 1] = (int)(r1 * src.row_pitch);
+        s_yb[2 * y] = b0;
+        s_yb[2 * y + 1] = b1;
+    }
+    if (plan.mode == RESIZE_LINEAR && plan.gather_step_x == 0)
+        for (int x = threadIdx.x; x < plan.dst_w; x += blockDim.x) {
+            const int x0 = plan.x0[x], x1 = plan.x1[x];
+            int a0 = plan.a0[x], a1 = plan.a1[x];
+            if (x1 != x0 + 1) { a0 += a1; a1 = 0; }          // clamped at the edge: always read the six bytes of pixels x0, x0 + 1
+            s_xtab[x] = make_int4(3 * x0, a0 | (a1 << 16), 0, 0);
+        }
+    if (threadIdx.x < UNFOLD_WARPS + 1) s_rows_done[threadIdx.x] = 0;       // ... and s_rows_issued[0]
+    fence_proxy_async();
+    if (threadIdx.x == 0) {
+        for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], 4); }
+        for (int s = 0; s < RAW_SLOTS_MAX; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
+        for (int s = 0; s < TILE_RING; ++s) mbar_init(&tile_done[s], 3);
+        for (int s = 0; s < 8; ++s) { mbar_init(&xch_full[s], 1); mbar_init(&xch_empty[s], 1); }
+        fence_barrier_init();
+    }
+    if (warp == RL::MMA_WARP0) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;     // debug stamps of CTA 0 (cutdet_net_debug_timeline)
+    if (tl && threadIdx.x == 0) tl[2047] = clock64();
+    // Programmatic dependent launch: the kernel before this one -- conv2 of the previous sub-batch -- may still be READING the
+    // activation buffer this kernel writes.  Only team 2's stores and the pad zeroing touch it: they wait for that kernel to
+    // complete (grid_dep_wait), everything else starts at once.  The next kernel may be scheduled now.
+    grid_dep_launch();
+
+    // Register budgets per warpgroup (setmaxnreg.sync.aligned), set at the top of each role's branch so that ptxas sees which
+    // budget governs which code (set in a separate if-chain it allocated every role within the smallest one).
+    if (warp >= RL::MMA_WARP0) {
+      reg_dealloc<RL::REGS_LIGHT>();
+      if (warp == RL::LOAD_WARP) {
+        // ------------------------------------------------------------------ loader: source rows -> raw ring, three per turn
+        const int total_rows = n_frames_cta * Hc;
+        const uint64_t stream_once = l2_policy_evict_first();   // frames are read once: keep the L2 for the activations
+        int fi = 0, y = 0;
+        const int per_turn = min(RL::ROWS_PER_TURN, n_slots);      // never wait for a slot that this very turn has yet to fill
+        for (int n = 0; n < total_rows; n += per_turn) {
+            const int cnt = min(per_turn, total_rows - n);
+            for (int j = 0; j < cnt; ++j) {          // row n - n_slots has been read (the slot cannot be a phase further: that takes row n)
+                const int use = (int)__umulhi((uint32_t)(n + j), inv_slots), slot = n + j - use * n_slots;
+                mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
+            }
+            if (tl && lane == 0 && n < 255) tl[n] = clock64();
+            if (elect_one()) {
+                int fj = fi, yj = y;
+                for (int j = 0; j < cnt; ++j) {
+                    const int use = (int)__umulhi((uint32_t)(n + j), inv_slots), slot = n + j - use * n_slots;
+                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fj * gridDim.x) * src.frame_stride;
+                    mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
+                    for (int k = 0; k < src.n_src; ++k)
+                        bulk_load_1d_hint(s_raw + slot * slot_bytes + k * src.row_bytes, frame + s_rowoff[2 * yj + k],
+                                          (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
+                    if (++yj == Hc) { yj = 0; ++fj; }
+                }
+                st_release_shared(&s_rows_issued[0], n + cnt);      // raw_full of these slots is now in these rows' phase
+            }
+            __syncwarp();
+            y += cnt;
+            while (y >= Hc) { y -= Hc; ++fi; }
+        }
+      } else {
+        // ------------------------------------------------------------------ MMA issuer of block row dy
+        const int dy = warp - RL::MMA_WARP0;
+        const bool stamp = tl && lane == 0;
+        uint32_t acc_phase = 0;
+        const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
+        const uint32_t idesc = instr_desc_f16_acc16(128, 3 * C);
+        const uint32_t tmem_row = tmem_base + 3 * C * dy;
+        int r_hi = 127 / P1w, r_rem = 127 % P1w;      // pooled row of the tile's last position, kept without a division per tile
+        for (int t = 0; t < n_tiles; ++t) {
+            // block row dy reads input rows 3R - 1 + dy .. 3R + 1 + dy of pooled row R: resized rows up to u = 3 r_hi + 1 + dy
+            const int u_hi = min(total_u - 1, 3 * r_hi + 1 + dy);
+            r_rem += 128;                                 // 64 <= P1w: at most three rows further
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const bool c = r_rem >= P1w; r_rem -= c ? P1w : 0; r_hi += c ? 1 : 0; }
+            const int mine = lane % UNFOLD_WARPS;
+            const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
+            while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(20);
+            __syncwarp();
+            if (stamp && dy == 0 && t < 64) tl[1024 + t] = clock64();
+            uint32_t a_chunk[3];
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                const int c = dy + ks, sub = (c + 2) % 3, shift = c == 0 ? -P1w : (c == 4 ? P1w : 0);
+                a_chunk[ks] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
+            }
+            mbar_wait(&acc_empty[dy], acc_phase ^ 1);
+            tc_fence_after_sync();
+            if (stamp && t < 60) tl[1800 + 4 * t + dy] = clock64();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) {
+                    const uint64_t da = smem_desc(a_chunk[ks], FR_PLANE, 128);
+                    const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
+                    umma_16bit(tmem_row, da, db, idesc, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(&acc_full[dy]);
+                umma_commit(&tile_done[t & (TILE_RING - 1)]);     // tile t no longer reads the operand ring once all three rows have completed
+            }
+            __syncwarp();
+            acc_phase ^= 1;
+        }
+      }
+    } else if (warp >= RL::UNFOLD_WARP0) {
+        // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
+        reg_dealloc<RL::REGS_UNFOLD>();
+        F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
+                 RPF, Hc, total_u, n_slots, slot_bytes, 1, inv_slots, tl};
+        f1_unfold_role<C, GATHER, true, UNFOLD_WARPS>(cx, warp - RL::UNFOLD_WARP0, lane);
+        // ... and, once the rows are through, the entries of the output buffer that are not pixels (they belong to no GEMM row)
+        grid_dep_wait();
+        for (int fi = 0; fi < n_frames_cta; ++fi)
+            zero_pads(p.out, CG, blockIdx.x + fi * gridDim.x, blockIdx.x + fi * gridDim.x + 1, threadIdx.x - 32 * RL::UNFOLD_WARP0, 32 * UNFOLD_WARPS);
+    } else {
+        // ------------------------------------------------------------------ teams: block row `team` of every tile
+        reg_alloc<RL::REGS_TEAM>();
+        const int team = warp >> 2, q = warp & 3;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t tm_row = lane_base + 3 * C * team, tm_p0 = lane_base + 9 * C, tm_p01 = tm_p0 + NPK;
+        uint64_t *full = &acc_full[team], *empty = &acc_empty[team];
+        uint64_t *p0_full = &xch_full[q], *p0_empty = &xch_empty[q], *p01_full = &xch_full[4 + q], *p01_empty = &xch_empty[4 + q];
+        const bool stamp = tl && q == 0 && lane == 0;
+        // read this team's block row of tile t and hand it back to its issuer; returns the max over dx
+        auto read_row = [&](int t, uint32_t (&m)[NPK]) {
+            mbar_wait(full, (uint32_t)(t & 1));
+            tc_fence_after_sync();
+            if (stamp && t < 64) tl[1216 + 8 * t + 2 * team] = clock64();
+            uint32_t row[ROWPK];
+            team_load_row<C>(tm_row, row);
+            tmem_ld_wait();
+            reg_fence_u<ROWPK>(row);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty);
+            if (stamp && t < 64) tl[1216 + 8 * t + 2 * team + 1] = clock64();
+            team_max_dx<C>(row, m);
+        };
+        if (team == 0) {
+            for (int t = 0; t < n_tiles; ++t) {
+                uint32_t m[NPK];
+                read_row(t, m);
+                mbar_wait(p0_empty, (uint32_t)(t & 1) ^ 1);          // team 1 has read p0 of tile t - 1
+                tc_fence_after_sync();
+                team_xch_store<C>(tm_p0, m);
+                tmem_st_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p0_full);
+            }
+        } else if (team == 1) {
+            for (int t = 0; t < n_tiles; ++t) {
+                uint32_t m[NPK], v[NPK];
+                read_row(t, m);
+                mbar_wait(p0_full, (uint32_t)(t & 1));
+                tc_fence_after_sync();
+                team_xch_load<C>(tm_p0, v);
+                tmem_ld_wait();
+                reg_fence_u<NPK>(v);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p0_empty);
+#pragma unroll
+                for (int i = 0; i < NPK; ++i) m[i] = hmax2(m[i], v[i]);
+                mbar_wait(p01_empty, (uint32_t)(t & 1) ^ 1);         // team 2 has read p01 of tile t - 1
+                tc_fence_after_sync();
+                team_xch_store<C>(tm_p01, m);
+                tmem_st_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p01_full);
+            }
+        } else {
+            const int mrow = q * 32 + lane;
+            int X = mrow % P1w, Y = mrow / P1w, fi = 0;        // position 128 t + mrow = ((fi * RPF + Y) * P1w + X), advanced tile by tile
+            while (Y >= RPF) { Y -= RPF; ++fi; }
+            const uint4 *sc4 = reinterpret_cast<const uint4 *>(s_par16), *sh4 = reinterpret_cast<const uint4 *>(s_par16 + NPK);
+            for (int t = 0; t < n_tiles; ++t) {
+                const bool valid = fi < n_frames_cta && Y < p.P1h;
+                uint4 *dst = store_addr16<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, 0);
+                X += 128;                                      // next tile: 64 <= P1w, at most three rows further; branch-free
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const bool c = X >= P1w; X -= c ? P1w : 0; Y += c ? 1 : 0; }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const bool c = Y >= RPF; Y -= c ? RPF : 0; fi += c ? 1 : 0; }
+                uint32_t m[NPK], v[NPK];
+                read_row(t, m);
+                mbar_wait(p01_full, (uint32_t)(t & 1));
+                tc_fence_after_sync();
+                team_xch_load<C>(tm_p01, v);
+                tmem_ld_wait();
+                reg_fence_u<NPK>(v);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p01_empty);
+#pragma unroll
+                for (int i = 0; i < NPK / 4; ++i) {             // 9-way max, ReLU (the bias is inside the accumulator), scale and shift
+                    const uint4 sc = sc4[i], sh = sh4[i];
+                    m[4 * i + 0] = hfma2(hmax3(m[4 * i + 0], v[4 * i + 0], 0u), sc.x, sh.x);
+                    m[4 * i + 1] = hfma2(hmax3(m[4 * i + 1], v[4 * i + 1], 0u), sc.y, sh.y);
+                    m[4 * i + 2] = hfma2(hmax3(m[4 * i + 2], v[4 * i + 2], 0u), sc.z, sh.z);
+                    m[4 * i + 3] = hfma2(hmax3(m[4 * i + 3], v[4 * i + 3], 0u), sc.w, sh.w);
+                }
+                if (t == 0) grid_dep_wait();                   // the kernel that may still read this buffer has completed
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < CG; ++j) dst[(size_t)j * p.out.gtot] = make_uint4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
+                }
+                if (stamp && t < 64) tl[1152 + t] = clock64();
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == RL::MMA_WARP0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ input packing
@@ -1648,6 +2011,8 @@ int set_smem_limits() {
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32));
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_teams_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_teams_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, MidSmem<C>::total));
     return CUTDET_OK;
 }
@@ -1683,17 +2048,18 @@ int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
 }
 
 template <int C>
-int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream, bool pdl, bool acc32, int grid_cap) {
+int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream, bool pdl, bool acc32, int grid_cap, bool legacy) {
     // grid_cap (CUTDET_OPT_CONV1_GRID) is a test hook: several frames per CTA, as on a part with fewer SMs than a sub-batch has frames
     const int grid = std::min(std::min(p.B, sm_count()), grid_cap > 0 ? grid_cap : 1 << 30);
     static const bool regs_ok = [] {
-        const void *fns[4] = {(const void *)conv1_fused_tc_kernel<C, true, false>, (const void *)conv1_fused_tc_kernel<C, false, false>,
-                              (const void *)conv1_fused_tc_kernel<C, true, true>, (const void *)conv1_fused_tc_kernel<C, false, true>};
+        const void *fns[6] = {(const void *)conv1_fused_tc_kernel<C, true, false>, (const void *)conv1_fused_tc_kernel<C, false, false>,
+                              (const void *)conv1_fused_tc_kernel<C, true, true>, (const void *)conv1_fused_tc_kernel<C, false, true>,
+                              (const void *)conv1_fused_teams_kernel<C, true>, (const void *)conv1_fused_teams_kernel<C, false>};
         bool ok = true;
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 6; ++i) {
             cudaFuncAttributes a{};
             cudaFuncGetAttributes(&a, fns[i]);
-            const int want = i < 2 ? F1Roles<false>::REGS_START : F1Roles<true>::REGS_START;
+            const int want = i < 2 ? F1Roles<false>::REGS_START : (i < 4 ? F1Roles<true>::REGS_START : T1Roles::REGS_START);
             if (a.numRegs != want) {
                 fprintf(stderr, "cutdet: conv1_fused_tc compiled with %d registers, the setmaxnreg budget assumes %d\n", a.numRegs, want);
                 ok = false;
@@ -1708,9 +2074,11 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_
     FusedSrc src = src_in;
     src.n_slots = (int)std::min<long long>(raw_bytes(acc16 ? F1Roles<true>::UNFOLD_WARPS : F1Roles<false>::UNFOLD_WARPS) / ((long long)src.n_src * src.row_bytes),
                                            RAW_SLOTS_MAX);
+    const bool teams = acc16 && !legacy;
     // Every slot must belong to ONE loader (row n goes to loader n % n_loaders and to slot n % n_slots): a loader's wait on
     // raw_empty sees one parity bit, and only its own earlier fill of that slot keeps it from running two phases ahead.
-    src.n_slots -= src.n_slots % std::min(LOADER_WARPS, src.n_slots);
+    // (The teams kernel has a single loader.)
+    if (!teams) src.n_slots -= src.n_slots % std::min(LOADER_WARPS, src.n_slots);
     constexpr int smem32 = F1Smem<C, F1Roles<false>::UNFOLD_WARPS>::total, smem16 = F1Smem<C, F1Roles<true>::UNFOLD_WARPS>::total;
     constexpr int thr32 = F1Roles<false>::THREADS, thr16 = F1Roles<true>::THREADS;
     {
@@ -1719,7 +2087,9 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_
         const bool gather = src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0;
         // pdl: only when the kernel before this one is one of ours (conv2/conv3 of the previous sub-batch): the loaders read the
         // frames without waiting for it, so it must not be what produced them
-        if (gather && acc16) launch_pdl(pdl, conv1_fused_tc_kernel<C, true, true>, grid, thr16, smem16, stream, p, src);
+        if (teams && gather) launch_pdl(pdl, conv1_fused_teams_kernel<C, true>, grid, T1Roles::THREADS, smem16, stream, p, src);
+        else if (teams) launch_pdl(pdl, conv1_fused_teams_kernel<C, false>, grid, T1Roles::THREADS, smem16, stream, p, src);
+        else if (gather && acc16) launch_pdl(pdl, conv1_fused_tc_kernel<C, true, true>, grid, thr16, smem16, stream, p, src);
         else if (gather) launch_pdl(pdl, conv1_fused_tc_kernel<C, true, false>, grid, thr32, smem32, stream, p, src);
         else if (acc16) launch_pdl(pdl, conv1_fused_tc_kernel<C, false, true>, grid, thr16, smem16, stream, p, src);
         else launch_pdl(pdl, conv1_fused_tc_kernel<C, false, false>, grid, thr32, smem32, stream, p, src);
@@ -1813,7 +2183,7 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     if (fused) {
         FusedSrc fs = *fused;
         fs.frames += (long long)f0 * fs.frame_stride;
-        if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0 && !net->opt.no_pdl, net->opt.conv1_acc32 != 0, net->opt.conv1_grid)) return rc;
+        if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0 && !net->opt.no_pdl, net->opt.conv1_acc32 != 0, net->opt.conv1_grid, net->opt.conv1_legacy != 0)) return rc;
     } else if (int rc = launch_conv1<C>(c1, stream)) return rc;
 
     MidParams p2 = mid_params(nb, g.FP1, g.PW1, g.P2h, g.P2w);
