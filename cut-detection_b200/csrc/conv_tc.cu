@@ -1296,25 +1296,28 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
 }
 
 // ------------------------------------------------------------------------------------------------ K1 + layer 1, one team per block row
+// EXPERIMENT (net option conv1_teams; not the default -- measured 2-3 % slower on same-box A/Bs, profiles/README.md round 2).
 // conv1_fused_tc_kernel above runs ONE MMA issuer and ONE set of epilogue warps over the three block rows of a tile in turn; its
-// clock stamps (profiles/README.md, round 2) show a tile period of ~1,450 cycles against 648 cycles of MMAs: issuing a block
-// row keeps the issuer ~270 cycles (the instruction waits for the tensor pipe), an epilogue warp needs ~450 cycles per block row
-// (barrier, TMEM load, wait::ld, release), and each of the two serial chains waits for the other once per tile.
-// Here every block row dy is its own pipeline:
+// clock stamps show a tile period of ~1,450 cycles against 648 cycles of MMAs: issuing a block row keeps the issuer ~270 cycles
+// (the instruction waits for the tensor pipe), an epilogue warp needs ~450 cycles per block row (barrier, TMEM load, wait::ld,
+// release), and each of the two serial chains waits for the other once per tile.  Here every block row dy is its own pipeline:
 //     MMA issuer dy (one warp)  -> acc_full[dy] ->  team dy (four warps, one per TMEM lane quarter) -> acc_empty[dy] -> issuer dy
-// so the three rows' chains run side by side and the tensor pipe always has the next row's MMAs queued.  A team thread reads ALL
-// the channels of its block row (3 dx x C fp16 accumulators = 3C/2 packed registers), takes the max over dx, and the 9-way max
-// is finished by passing the partial maxima DOWN the teams through spare TMEM columns (tcgen05.st / tcgen05.ld: the 80 columns
-// the accumulator leaves free; no shared memory, whose bandwidth the MMAs' operand reads already use):
+// A team thread reads ALL the channels of its block row (3 dx x C fp16 accumulators = 3C/2 packed registers), takes the max over
+// dx, and the 9-way max is finished by passing the partial maxima DOWN the teams through spare TMEM columns (tcgen05.st /
+// tcgen05.ld: the 80 columns the accumulator leaves free):
 //     team 0: max over dx -> p0                team 1: max(p0, max over dx) -> p01            team 2: relu(max(p01, max over dx))
 // Rows complete in that order, so a team never waits for a later one; team 2 applies scale/shift and stores all C channels.
-// The loaders shrink to one warp that issues three rows per turn (one issuing thread sustains ~10 B/clk per row it issues, the
-// chain of waits is paid once per turn).  24 warps; registers 104 (teams) / 64 (unfold) / 40 (issuers + loader).
+// What the stamps of THIS kernel show: the rows' pipelines do decouple (a row is read and handed back ~250 cycles after its MMAs
+// complete), but a hop between teams costs ~400 cycles (st, wait::st, barrier, ld, wait::ld) and the middle team's chain --
+// read, hop in, hop out -- is ~1,400 cycles per tile, so the period stays at ~1,500; with the hops through shared memory
+// instead the teams are fast but the added LSU traffic slows the unfold warps 2-3 x and the rows starve.  TMEM holds one
+// accumulator tile (432 of 512 columns) and the register file cannot hold a second set of teams, so no two tiles can be in the
+// epilogue at once: the serial latency chain per tile is what it is.  Kept for A/B runs; results are bit-identical.
 struct T1Roles {
-    static constexpr int TEAM_WARPS = 12, UNFOLD_WARPS = 8, UNFOLD_WARP0 = 12, MMA_WARP0 = 20, LOAD_WARP = 23, WARPS = 24, THREADS = 32 * WARPS;
-    static constexpr int REGS_START = 80, REGS_TEAM = 104, REGS_UNFOLD = 64, REGS_LIGHT = 40;
-    static constexpr int ROWS_PER_TURN = 3;
-    static_assert(THREADS * REGS_START == 384 * REGS_TEAM + 256 * REGS_UNFOLD + 128 * REGS_LIGHT, "register pool");
+    // warps: 0-11 teams | 12-19 unfold | 20-22 MMA issuers, 23 idle | 24-26 loaders, 27 idle
+    static constexpr int TEAM_WARPS = 12, UNFOLD_WARPS = 8, UNFOLD_WARP0 = 12, MMA_WARP0 = 20, LOAD_WARP0 = 24, WARPS = 28, THREADS = 32 * WARPS;
+    static constexpr int REGS_START = 72, REGS_TEAM = 112, REGS_UNFOLD = 56, REGS_MMA = 32, REGS_LOAD = 24;
+    static_assert(THREADS * REGS_START == 384 * REGS_TEAM + 256 * REGS_UNFOLD + 128 * REGS_MMA + 128 * REGS_LOAD, "register pool");
 };
 
 template <int C>
@@ -1338,6 +1341,10 @@ __device__ __forceinline__ void team_max_dx(const uint32_t (&row)[3 * C / 2], ui
 #pragma unroll
         for (int j = 0; j < Q; ++j) m[h * Q + j] = hmax3(row[h * 3 * Q + j], row[h * 3 * Q + Q + j], row[h * 3 * Q + 2 * Q + j]);
 }
+// Partial maxima travel between the teams of a lane quarter through spare TMEM columns (tcgen05.st / wait::st / mbarrier /
+// tcgen05.ld / wait::ld).  Shared memory was tried for the hop as well (24 KB taken from the raw ring, 128-bit conflict-free
+// accesses): the teams' chains got short, but the extra LSU traffic slowed the unfold warps' gather 2-3 x and the rows became the
+// bottleneck (1.95 M frames/s against 2.15 M; profiles/README.md, round 2).
 template <int C>
 __device__ __forceinline__ void team_xch_store(uint32_t taddr, const uint32_t (&m)[C / 2]) {
     tmem_st_u16(taddr, m);
@@ -1372,7 +1379,7 @@ __global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(
     uint64_t *xch_empty = xch_full + 8;                                         // [2][4]: ... has been read
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xch_empty + 8);
     int *s_rows_done = reinterpret_cast<int *>(tmem_slot + 2);                  // [UNFOLD_WARPS] rows finished by each unfold warp
-    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;                            // [1] rows issued by the loader
+    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;                            // [LOADER_WARPS] rows issued by each loader
     static_assert((3 + 3 + 2 * RAW_SLOTS_MAX + TILE_RING + 16) * 8 + 8 + (UNFOLD_WARPS + 4) * 4 <= 1024, "barrier block");
     uint32_t *s_par16 = reinterpret_cast<uint32_t *>(smem + S::OFF_PAR);        // [C/2 scale pairs | C/2 shift pairs]
 
@@ -1413,7 +1420,7 @@ __global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(
             if (x1 != x0 + 1) { a0 += a1; a1 = 0; }          // clamped at the edge: always read the six bytes of pixels x0, x0 + 1
             s_xtab[x] = make_int4(3 * x0, a0 | (a1 << 16), 0, 0);
         }
-    if (threadIdx.x < UNFOLD_WARPS + 1) s_rows_done[threadIdx.x] = 0;       // ... and s_rows_issued[0]
+    if (threadIdx.x < UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;       // ... and s_rows_issued
     fence_proxy_async();
     if (threadIdx.x == 0) {
         for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], 4); }
@@ -1436,39 +1443,38 @@ __global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(
 
     // Register budgets per warpgroup (setmaxnreg.sync.aligned), set at the top of each role's branch so that ptxas sees which
     // budget governs which code (set in a separate if-chain it allocated every role within the smallest one).
-    if (warp >= RL::MMA_WARP0) {
-      reg_dealloc<RL::REGS_LIGHT>();
-      if (warp == RL::LOAD_WARP) {
-        // ------------------------------------------------------------------ loader: source rows -> raw ring, three per turn
-        const int total_rows = n_frames_cta * Hc;
-        const uint64_t stream_once = l2_policy_evict_first();   // frames are read once: keep the L2 for the activations
-        int fi = 0, y = 0;
-        const int per_turn = min(RL::ROWS_PER_TURN, n_slots);      // never wait for a slot that this very turn has yet to fill
-        for (int n = 0; n < total_rows; n += per_turn) {
-            const int cnt = min(per_turn, total_rows - n);
-            for (int j = 0; j < cnt; ++j) {          // row n - n_slots has been read (the slot cannot be a phase further: that takes row n)
-                const int use = (int)__umulhi((uint32_t)(n + j), inv_slots), slot = n + j - use * n_slots;
+    if (warp >= RL::LOAD_WARP0) {
+      reg_dealloc<RL::REGS_LOAD>();
+      if (warp < RL::LOAD_WARP0 + LOADER_WARPS) {
+        // ------------------------------------------------------------------ loaders: source rows -> raw ring
+        // row n is issued by loader n % n_loaders into slot n % n_slots (the slot count is a multiple of the loader count, so a
+        // slot is always refilled by the same loader; the wait on raw_empty is for row n - n_slots to have been read)
+        const int lw = warp - RL::LOAD_WARP0, total_rows = n_frames_cta * Hc;
+        const int n_loaders = min(LOADER_WARPS, n_slots);
+        if (lw < n_loaders) {
+            const uint64_t stream_once = l2_policy_evict_first();   // frames are read once: keep the L2 for the activations
+            int fi = 0, y = lw, issued = 0;
+            for (int n = lw; n < total_rows; n += n_loaders, y += n_loaders) {
+                while (y >= Hc) { y -= Hc; ++fi; }
+                const int use = (int)__umulhi((uint32_t)n, inv_slots), slot = n - use * n_slots;
                 mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
-            }
-            if (tl && lane == 0 && n < 255) tl[n] = clock64();
-            if (elect_one()) {
-                int fj = fi, yj = y;
-                for (int j = 0; j < cnt; ++j) {
-                    const int use = (int)__umulhi((uint32_t)(n + j), inv_slots), slot = n + j - use * n_slots;
-                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fj * gridDim.x) * src.frame_stride;
+                if (tl && lane == 0 && n < 256) tl[n] = clock64();
+                ++issued;
+                if (elect_one()) {
+                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
                     mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
-                    for (int k = 0; k < src.n_src; ++k)
-                        bulk_load_1d_hint(s_raw + slot * slot_bytes + k * src.row_bytes, frame + s_rowoff[2 * yj + k],
+                    for (int j = 0; j < src.n_src; ++j)
+                        bulk_load_1d_hint(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * y + j],
                                           (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
-                    if (++yj == Hc) { yj = 0; ++fj; }
+                    st_release_shared(&s_rows_issued[lw], issued);   // raw_full[slot] is now in row n's phase
                 }
-                st_release_shared(&s_rows_issued[0], n + cnt);      // raw_full of these slots is now in these rows' phase
+                __syncwarp();
             }
-            __syncwarp();
-            y += cnt;
-            while (y >= Hc) { y -= Hc; ++fi; }
         }
-      } else {
+      }
+    } else if (warp >= RL::MMA_WARP0) {
+      reg_dealloc<RL::REGS_MMA>();
+      if (warp < RL::MMA_WARP0 + 3) {
         // ------------------------------------------------------------------ MMA issuer of block row dy
         const int dy = warp - RL::MMA_WARP0;
         const bool stamp = tl && lane == 0;
@@ -1515,7 +1521,7 @@ __global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(
         // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
         reg_dealloc<RL::REGS_UNFOLD>();
         F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
-                 RPF, Hc, total_u, n_slots, slot_bytes, 1, inv_slots, tl};
+                 RPF, Hc, total_u, n_slots, slot_bytes, min(LOADER_WARPS, n_slots), inv_slots, tl};
         f1_unfold_role<C, GATHER, true, UNFOLD_WARPS>(cx, warp - RL::UNFOLD_WARP0, lane);
         // ... and, once the rows are through, the entries of the output buffer that are not pixels (they belong to no GEMM row)
         grid_dep_wait();
@@ -1529,12 +1535,12 @@ __global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(
         const uint32_t tm_row = lane_base + 3 * C * team, tm_p0 = lane_base + 9 * C, tm_p01 = tm_p0 + NPK;
         uint64_t *full = &acc_full[team], *empty = &acc_empty[team];
         uint64_t *p0_full = &xch_full[q], *p0_empty = &xch_empty[q], *p01_full = &xch_full[4 + q], *p01_empty = &xch_empty[4 + q];
-        const bool stamp = tl && q == 0 && lane == 0;
+        const bool stamp = tl && q == 0 && lane == 0 && team < 2;      // (team 2 has no register to spare for debug stamps)
         // read this team's block row of tile t and hand it back to its issuer; returns the max over dx
         auto read_row = [&](int t, uint32_t (&m)[NPK]) {
             mbar_wait(full, (uint32_t)(t & 1));
             tc_fence_after_sync();
-            if (stamp && t < 64) tl[1216 + 8 * t + 2 * team] = clock64();
+            if (stamp && t < 64) tl[1216 + 8 * t + 3 * team + 1] = clock64();         // the row's MMAs have completed
             uint32_t row[ROWPK];
             team_load_row<C>(tm_row, row);
             tmem_ld_wait();
@@ -1542,7 +1548,7 @@ __global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(empty);
-            if (stamp && t < 64) tl[1216 + 8 * t + 2 * team + 1] = clock64();
+            if (stamp && t < 64) tl[1216 + 8 * t + 3 * team + 2] = clock64();         // row handed back
             team_max_dx<C>(row, m);
         };
         if (team == 0) {
@@ -1585,22 +1591,15 @@ __global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(
             while (Y >= RPF) { Y -= RPF; ++fi; }
             const uint4 *sc4 = reinterpret_cast<const uint4 *>(s_par16), *sh4 = reinterpret_cast<const uint4 *>(s_par16 + NPK);
             for (int t = 0; t < n_tiles; ++t) {
-                const bool valid = fi < n_frames_cta && Y < p.P1h;
-                uint4 *dst = store_addr16<C>(p.out, blockIdx.x + fi * gridDim.x, Y, X, 0);
-                X += 128;                                      // next tile: 64 <= P1w, at most three rows further; branch-free
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { const bool c = X >= P1w; X -= c ? P1w : 0; Y += c ? 1 : 0; }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { const bool c = Y >= RPF; Y -= c ? RPF : 0; fi += c ? 1 : 0; }
+                // (no register may spill here: this CTA's shared memory leaves no L1, a spilled word costs an L2 round trip -- 18
+                // spilled words once made the tail of this loop 2,000 cycles long)
+                // p01 is complete well before this tile's block row 2 (rows finish in order): its load flies while the row is waited for
                 uint32_t m[NPK], v[NPK];
-                read_row(t, m);
                 mbar_wait(p01_full, (uint32_t)(t & 1));
                 tc_fence_after_sync();
                 team_xch_load<C>(tm_p01, v);
-                tmem_ld_wait();
+                read_row(t, m);                                 // (its wait::ld covers the load above)
                 reg_fence_u<NPK>(v);
-                tc_fence_before_sync();
-                __syncwarp();
                 if (lane == 0) mbar_arrive(p01_empty);
 #pragma unroll
                 for (int i = 0; i < NPK / 4; ++i) {             // 9-way max, ReLU (the bias is inside the accumulator), scale and shift
@@ -1611,11 +1610,20 @@ __global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(
                     m[4 * i + 3] = hfma2(hmax3(m[4 * i + 3], v[4 * i + 3], 0u), sc.w, sh.w);
                 }
                 if (t == 0) grid_dep_wait();                   // the kernel that may still read this buffer has completed
-                if (valid) {
+                // (X, Y, fi) is this tile's position: the address is worked out here, when the row's registers are free again
+                if (fi < n_frames_cta && Y < p.P1h) {
+                    // entry of the phase-split buffer (32-bit arithmetic: the buffer has fewer than 2^32 16-byte entries)
+                    const uint32_t off = (uint32_t)(((Y % 3) * 3 + X % 3) * CG) * (uint32_t)p.out.gtot +
+                                         (uint32_t)(p.out.frame0 + blockIdx.x + fi * gridDim.x) * (uint32_t)p.out.FP + (uint32_t)((Y / 3) * p.out.PW + X / 3);
+                    uint4 *dst = reinterpret_cast<uint4 *>(p.out.ptr) + off;
 #pragma unroll
                     for (int j = 0; j < CG; ++j) dst[(size_t)j * p.out.gtot] = make_uint4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
                 }
-                if (stamp && t < 64) tl[1152 + t] = clock64();
+                X += 128;                                      // next tile: 64 <= P1w, at most three rows further; branch-free
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const bool c = X >= P1w; X -= c ? P1w : 0; Y += c ? 1 : 0; }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const bool c = Y >= RPF; Y -= c ? RPF : 0; fi += c ? 1 : 0; }
             }
         }
     }
@@ -2048,7 +2056,7 @@ int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
 }
 
 template <int C>
-int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream, bool pdl, bool acc32, int grid_cap, bool legacy) {
+int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream, bool pdl, bool acc32, int grid_cap, bool use_teams) {
     // grid_cap (CUTDET_OPT_CONV1_GRID) is a test hook: several frames per CTA, as on a part with fewer SMs than a sub-batch has frames
     const int grid = std::min(std::min(p.B, sm_count()), grid_cap > 0 ? grid_cap : 1 << 30);
     static const bool regs_ok = [] {
@@ -2072,13 +2080,12 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_
     // (cutdet_net_set_option(CUTDET_OPT_CONV1_ACC32))
     const bool acc16 = !acc32 && p.w_perm16 != nullptr;
     FusedSrc src = src_in;
-    src.n_slots = (int)std::min<long long>(raw_bytes(acc16 ? F1Roles<true>::UNFOLD_WARPS : F1Roles<false>::UNFOLD_WARPS) / ((long long)src.n_src * src.row_bytes),
-                                           RAW_SLOTS_MAX);
-    const bool teams = acc16 && !legacy;
+    const bool teams = acc16 && use_teams;    // the kernel with an epilogue team and an MMA issuer per block row (experiment, see below)
+    const long long ring_bytes = raw_bytes(acc16 ? F1Roles<true>::UNFOLD_WARPS : F1Roles<false>::UNFOLD_WARPS);
+    src.n_slots = (int)std::min<long long>(ring_bytes / ((long long)src.n_src * src.row_bytes), RAW_SLOTS_MAX);
     // Every slot must belong to ONE loader (row n goes to loader n % n_loaders and to slot n % n_slots): a loader's wait on
     // raw_empty sees one parity bit, and only its own earlier fill of that slot keeps it from running two phases ahead.
-    // (The teams kernel has a single loader.)
-    if (!teams) src.n_slots -= src.n_slots % std::min(LOADER_WARPS, src.n_slots);
+    src.n_slots -= src.n_slots % std::min(LOADER_WARPS, src.n_slots);
     constexpr int smem32 = F1Smem<C, F1Roles<false>::UNFOLD_WARPS>::total, smem16 = F1Smem<C, F1Roles<true>::UNFOLD_WARPS>::total;
     constexpr int thr32 = F1Roles<false>::THREADS, thr16 = F1Roles<true>::THREADS;
     {
@@ -2183,7 +2190,7 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     if (fused) {
         FusedSrc fs = *fused;
         fs.frames += (long long)f0 * fs.frame_stride;
-        if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0 && !net->opt.no_pdl, net->opt.conv1_acc32 != 0, net->opt.conv1_grid, net->opt.conv1_legacy != 0)) return rc;
+        if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0 && !net->opt.no_pdl, net->opt.conv1_acc32 != 0, net->opt.conv1_grid, net->opt.conv1_teams != 0)) return rc;
     } else if (int rc = launch_conv1<C>(c1, stream)) return rc;
 
     MidParams p2 = mid_params(nb, g.FP1, g.PW1, g.P2h, g.P2w);

@@ -146,8 +146,8 @@ enum {
     CUTDET_OPT_GROUP_FRAMES = 3, /* frames gathered for one conv3 launch (default 0 = 1184)                             */
     CUTDET_OPT_NO_PDL = 4,       /* 1: ordinary launches instead of programmatic dependent launch                       */
     CUTDET_OPT_CONV1_GRID = 5,   /* test hook: cap on the fused conv1 grid (several frames per CTA); 0 = no cap         */
-    CUTDET_OPT_CONV1_LEGACY = 6  /* 1: the single-issuer fused conv1 kernel (round 1) instead of the one with an epilogue
-                                    team and an MMA issuer per block row; same arithmetic, kept for same-box A/B runs   */
+    CUTDET_OPT_CONV1_TEAMS = 6   /* 1: experiment -- the fused conv1 kernel with an epilogue team and an MMA issuer per block
+                                    row instead of the default one; same arithmetic, same bits, ~3 % slower (kept for A/B) */
 };
 CUTDET_API int cutdet_net_set_option(cutdet_net *net, int option, int value);
 CUTDET_API int cutdet_net_get_option(const cutdet_net *net, int option, int *value);
