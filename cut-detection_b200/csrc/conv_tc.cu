@@ -1136,8 +1136,9 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;     // debug stamps of CTA 0 (CUTDET_TIMELINE1)
+    long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;     // debug stamps of CTA 0 (cutdet_net_debug_timeline)
     if (tl && threadIdx.x == 0) tl[2047] = clock64();
+    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2048 + 2 * blockIdx.x] = g; }
     // Programmatic dependent launch (launch_conv1_fused): the kernel before this one -- conv2 of the previous sub-batch -- may
     // still be READING the activation buffer this kernel writes.  Loaders, unfold and MMAs do not touch it and start at once;
     // the epilogue warps wait for that kernel to complete before their first store.  The next kernel may be scheduled now.
@@ -1292,6 +1293,7 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2049 + 2 * blockIdx.x] = g; }
     if (warp == F1_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -1436,6 +1438,7 @@ __global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(
     const uint32_t tmem_base = *tmem_slot;
     long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;     // debug stamps of CTA 0 (cutdet_net_debug_timeline)
     if (tl && threadIdx.x == 0) tl[2047] = clock64();
+    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2048 + 2 * blockIdx.x] = g; }
     // Programmatic dependent launch: the kernel before this one -- conv2 of the previous sub-batch -- may still be READING the
     // activation buffer this kernel writes.  Only team 2's stores and the pad zeroing touch it: they wait for that kernel to
     // complete (grid_dep_wait), everything else starts at once.  The next kernel may be scheduled now.
@@ -1629,6 +1632,256 @@ __global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2049 + 2 * blockIdx.x] = g; }
+    if (warp == RL::MMA_WARP0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ K1 + layer 1, two epilogue sets
+// The fused kernel with TWO sets of epilogue warps that alternate over the tiles and an MMA issuer per block row.
+// TMEM holds one accumulator tile (432 of 512 columns), so tile t + 1's block row dy can only be computed once tile t's row dy has
+// been read -- but nothing requires the SAME warps to read consecutive tiles.  conv1_fused_tc_kernel's epilogue chain per tile
+// (three rounds of barrier / tcgen05.ld / wait::ld / hand-back, then max, affine, address, store: ~1,450 cycles by its clock
+// stamps) sets its tile period; with two sets that chain has two periods to complete, and what bounds a period is the loop of
+// one block row: MMAs (216 cycles) -> commit -> a set reads the row (~350) -> hand-back -> issue.
+// A set is FOUR warps (one per TMEM lane quarter; a thread takes all C channels of its pooled pixel: 3C/2 packed registers per
+// block row): with 16 epilogue warps of half the channels each (1,024 threads) the epilogue was as quick, but the unfold warps,
+// left with 64 registers among 32 warps, took 1,600 cycles per row and the rows became the bottleneck at the same 1,450 cycles.
+//   warps 0-3 set A | 4-7 set B | 8-15 unfold | 16-18 MMA issuers (block row dy), 19 idle | 20-22 loaders, 23 idle
+struct S2Roles {
+    static constexpr int EPI_WARPS2 = 8, UNFOLD_WARPS = 8, UNFOLD_WARP0 = 8, MMA_WARP0 = 16, LOAD_WARP0 = 20, WARPS = 24, THREADS = 32 * WARPS;
+    static constexpr int REGS_START = 80, REGS_EPI = 120, REGS_UNFOLD = 88, REGS_MMA = 32, REGS_LOAD = 32;
+    static_assert(THREADS * REGS_START == 256 * REGS_EPI + 256 * REGS_UNFOLD + 128 * REGS_MMA + 128 * REGS_LOAD, "register pool");
+};
+
+template <int C, bool GATHER>
+__global__ void __launch_bounds__(S2Roles::THREADS, 1) conv1_fused_sets_kernel(const Conv1Params p, const FusedSrc src) {
+    using RL = S2Roles;
+    constexpr int UNFOLD_WARPS = RL::UNFOLD_WARPS;
+    using S = F1Smem<C, UNFOLD_WARPS>;
+    constexpr int CG = C / 8, NPK = C / 2, ROWPK = 3 * C / 2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *s_w = smem;
+    uint8_t *s_ring = smem + S::OFF_RING;
+    uint8_t *s_raw = smem + S::OFF_RAW;
+    int *s_rowoff = reinterpret_cast<int *>(smem + S::OFF_TAB);               // [y][2]
+    int *s_yb = s_rowoff + 2 * F_MAX_DST;                                       // [y][2]: b0, b1
+    int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);              // [x]: 3*x0, a0 | a1 << 16
+    uint32_t *s_cmp = reinterpret_cast<uint32_t *>(smem + S::OFF_CMP);          // [unfold warp][F1_CMP_STRIDE]
+    uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);       // [set][3]: block row dy of the set's tile is complete
+    uint64_t *acc_rel = acc_full + 6;                                           // [set][3]: ... has been read by the set (4 warps)
+    uint64_t *raw_full = acc_rel + 6;                                           // [RAW_SLOTS_MAX]
+    uint64_t *raw_empty = raw_full + RAW_SLOTS_MAX;                             // [RAW_SLOTS_MAX]
+    uint64_t *tile_done = raw_empty + RAW_SLOTS_MAX;                            // [TILE_RING] tile t's MMAs have completed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tile_done + TILE_RING);
+    int *s_rows_done = reinterpret_cast<int *>(tmem_slot + 2);                  // [UNFOLD_WARPS] rows finished by each unfold warp
+    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;                            // [LOADER_WARPS] rows issued by each loader
+    static_assert((6 + 6 + 2 * RAW_SLOTS_MAX + TILE_RING) * 8 + 8 + (UNFOLD_WARPS + 4) * 4 <= 1024, "barrier block");
+    uint32_t *s_par16 = reinterpret_cast<uint32_t *>(smem + S::OFF_PAR);        // [C/2 scale pairs | C/2 shift pairs]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ResizePlanDev &plan = src.plan;
+    const int H = p.H, P1w = p.P1w, RPF = p.P1h + 1;          // pooled rows per frame incl. the zero row
+    const int Hc = min(H, 3 * p.P1h + 1);                     // resized rows the conv reads (row 3*P1h only if it exists)
+
+    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_perm16[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_par16[i] = p.par16[i];
+    // operand-format zeros for the row above the first frame (tile 0's view shifted by -P1w); the last half of the second
+    // plane is the constant 1.0 that multiplies the bias row
+    for (int i = threadIdx.x; i < UNFOLD_WARPS * F1_CMP_STRIDE; i += blockDim.x) s_cmp[i] = 0u;
+    for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
+        reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
+            make_uint4(0u, 0u, 0u, i >= P1w ? 0x3c000000u : 0u);
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        int r0, r1, b0 = 2048, b1 = 0;
+        if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
+        else if (plan.mode == RESIZE_COPY) { r0 = r1 = y; }
+        else if (plan.mode == RESIZE_AREA2) { r0 = 2 * y; r1 = 2 * y + 1; }
+        else { r0 = plan.y0[y]; r1 = plan.y1[y]; b0 = plan.b0[y]; b1 = plan.b1[y]; }
+        if (src.compact) { r0 = plan.row_slot[r0]; r1 = (plan.mode == RESIZE_LINEAR && b1 == 0) ? r0 : plan.row_slot[r1]; }
+        s_rowoff[2 * y] = (int)(r0 * src.row_pitch);
+        s_rowoff[2 * y + 1] = (int)(r1 * src.row_pitch);
+        s_yb[2 * y] = b0;
+        s_yb[2 * y + 1] = b1;
+    }
+    if (plan.mode == RESIZE_LINEAR && plan.gather_step_x == 0)
+        for (int x = threadIdx.x; x < plan.dst_w; x += blockDim.x) {
+            const int x0 = plan.x0[x], x1 = plan.x1[x];
+            int a0 = plan.a0[x], a1 = plan.a1[x];
+            if (x1 != x0 + 1) { a0 += a1; a1 = 0; }          // clamped at the edge: always read the six bytes of pixels x0, x0 + 1
+            s_xtab[x] = make_int4(3 * x0, a0 | (a1 << 16), 0, 0);
+        }
+    if (threadIdx.x < UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;       // ... and s_rows_issued
+    fence_proxy_async();
+    if (threadIdx.x == 0) {
+        for (int d = 0; d < 6; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_rel[d], 4); }
+        for (int s = 0; s < RAW_SLOTS_MAX; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
+        for (int s = 0; s < TILE_RING; ++s) mbar_init(&tile_done[s], 3);
+        fence_barrier_init();
+    }
+    if (warp == RL::MMA_WARP0) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    // (declared after the set-up on purpose: the kernel starts with 64 registers per thread, and values that live across the
+    // set-up were spilled there and re-read from L2 inside the roles' loops)
+    const int n_frames_cta = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_tiles = (n_frames_cta * RPF * P1w + 127) / 128;
+    const int total_u = 3 * n_frames_cta * RPF;               // resized rows incl. the zero rows, u = 3R + sub
+    const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;
+    const uint32_t inv_slots = 0xffffffffu / (uint32_t)n_slots + 1u;       // n / n_slots = umulhi(n, inv_slots), exact while n * n_slots < 2^32
+    long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;     // debug stamps of CTA 0 (cutdet_net_debug_timeline)
+    if (tl && threadIdx.x == 0) tl[2047] = clock64();
+    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2048 + 2 * blockIdx.x] = g; }
+    // Programmatic dependent launch: the kernel before this one -- conv2 of the previous sub-batch -- may still be READING the
+    // activation buffer this kernel writes.  Only the epilogue's stores and the pad zeroing touch it: they wait for that kernel
+    // to complete (grid_dep_wait), everything else starts at once.  The next kernel may be scheduled now.
+    grid_dep_launch();
+
+    // Register budgets per warpgroup (setmaxnreg.sync.aligned), set at the top of each role's branch so that ptxas sees which
+    // budget governs which code (set in a separate if-chain it allocated every role within the smallest one).
+    if (warp >= RL::LOAD_WARP0) {
+      reg_dealloc<RL::REGS_LOAD>();
+      if (warp < RL::LOAD_WARP0 + LOADER_WARPS) {
+        // ------------------------------------------------------------------ loaders: source rows -> raw ring
+        // row n is issued by loader n % n_loaders into slot n % n_slots (the slot count is a multiple of the loader count, so a
+        // slot is always refilled by the same loader; the wait on raw_empty is for row n - n_slots to have been read)
+        const int lw = warp - RL::LOAD_WARP0, total_rows = n_frames_cta * Hc;
+        const int n_loaders = min(LOADER_WARPS, n_slots);
+        if (lw < n_loaders) {
+            const uint64_t stream_once = l2_policy_evict_first();   // frames are read once: keep the L2 for the activations
+            int fi = 0, y = lw, issued = 0;
+            for (int n = lw; n < total_rows; n += n_loaders, y += n_loaders) {
+                while (y >= Hc) { y -= Hc; ++fi; }
+                const int use = (int)__umulhi((uint32_t)n, inv_slots), slot = n - use * n_slots;
+                mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
+                if (tl && lane == 0 && n < 256) tl[n] = clock64();
+                ++issued;
+                if (elect_one()) {
+                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
+                    mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
+                    for (int j = 0; j < src.n_src; ++j)
+                        bulk_load_1d_hint(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * y + j],
+                                          (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
+                    st_release_shared(&s_rows_issued[lw], issued);   // raw_full[slot] is now in row n's phase
+                }
+                __syncwarp();
+            }
+        }
+      }
+    } else if (warp >= RL::MMA_WARP0) {
+      reg_dealloc<RL::REGS_MMA>();
+      if (warp < RL::MMA_WARP0 + 3) {
+        // ------------------------------------------------------------------ MMA issuer of block row dy
+        const int dy = warp - RL::MMA_WARP0;
+        const bool stamp = tl && lane == 0;
+        const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
+        const uint32_t idesc = instr_desc_f16_acc16(128, 3 * C);
+        const uint32_t tmem_row = tmem_base + 3 * C * dy;
+        int r_hi = 127 / P1w, r_rem = 127 % P1w;      // pooled row of the tile's last position, kept without a division per tile
+        for (int t = 0; t < n_tiles; ++t) {
+            // block row dy reads input rows 3R - 1 + dy .. 3R + 1 + dy of pooled row R: resized rows up to u = 3 r_hi + 1 + dy
+            const int u_hi = min(total_u - 1, 3 * r_hi + 1 + dy);
+            r_rem += 128;                                 // 64 <= P1w: at most three rows further
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const bool c = r_rem >= P1w; r_rem -= c ? P1w : 0; r_hi += c ? 1 : 0; }
+            const int mine = lane % UNFOLD_WARPS;
+            const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
+            while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(20);
+            __syncwarp();
+            if (stamp && dy == 0 && t < 64) tl[1024 + t] = clock64();
+            uint32_t a_chunk[3];
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                const int c = dy + ks, sub = (c + 2) % 3, shift = c == 0 ? -P1w : (c == 4 ? P1w : 0);
+                a_chunk[ks] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
+            }
+            // block row dy of the accumulator was last filled for tile t - 1, which the OTHER set reads: its (t - 1) / 2-th tile
+            if (t > 0) mbar_wait(&acc_rel[3 * ((t - 1) & 1) + dy], (uint32_t)((t - 1) >> 1) & 1u);
+            tc_fence_after_sync();
+            if (stamp && t < 60) tl[1800 + 4 * t + dy] = clock64();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) {
+                    const uint64_t da = smem_desc(a_chunk[ks], FR_PLANE, 128);
+                    const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
+                    umma_16bit(tmem_row, da, db, idesc, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(&acc_full[3 * (t & 1) + dy]);
+                umma_commit(&tile_done[t & (TILE_RING - 1)]);     // tile t no longer reads the operand ring once all three rows have completed
+            }
+            __syncwarp();
+        }
+      }
+    } else if (warp >= RL::UNFOLD_WARP0) {
+        // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
+        if constexpr (RL::REGS_UNFOLD > RL::REGS_START) reg_alloc<RL::REGS_UNFOLD>();      // (waits for what the light groups give up)
+        else reg_dealloc<RL::REGS_UNFOLD>();
+        F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
+                 RPF, Hc, total_u, n_slots, slot_bytes, min(LOADER_WARPS, n_slots), inv_slots, tl};
+        f1_unfold_role<C, GATHER, true, UNFOLD_WARPS>(cx, warp - RL::UNFOLD_WARP0, lane);
+        // ... and, once the rows are through, the entries of the output buffer that are not pixels (they belong to no GEMM row)
+        grid_dep_wait();
+        for (int fi = 0; fi < n_frames_cta; ++fi)
+            zero_pads(p.out, CG, blockIdx.x + fi * gridDim.x, blockIdx.x + fi * gridDim.x + 1, threadIdx.x - 32 * RL::UNFOLD_WARP0, 32 * UNFOLD_WARPS);
+    } else {
+        // ------------------------------------------------------------------ epilogue sets: set s takes tiles s, s + 2, s + 4, ...
+        // A thread is a TMEM lane (a pooled pixel) and ALL its channels.  A set's chain per tile -- three rounds of barrier, TMEM
+        // load, wait::ld and hand-back, then ReLU/affine, address and store -- has two tile periods to complete, and block row dy
+        // of the next tile (the other set's) is issued the moment this set has handed row dy back.
+        reg_alloc<RL::REGS_EPI>();
+        const int set = warp >> 2, q = warp & 3, mrow = q * 32 + lane;
+        const uint32_t tm_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint64_t *full = &acc_full[3 * set], *rel = &acc_rel[3 * set];
+        // (no debug stamps here: the set has no register to spare, and a spilled word costs an L2 round trip per tile)
+        int X = (128 * set + mrow) % p.P1w, Y = (128 * set + mrow) / p.P1w, fi = 0;   // position 128 t + mrow = ((fi * RPF + Y) * P1w + X)
+        while (Y >= p.P1h + 1) { Y -= p.P1h + 1; ++fi; }
+        const uint4 *sc4 = reinterpret_cast<const uint4 *>(s_par16), *sh4 = reinterpret_cast<const uint4 *>(s_par16 + NPK);
+        uint32_t par = 0;
+        for (int t = set; t < n_tiles; t += 2, par ^= 1) {
+            uint32_t run[NPK];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                mbar_wait(&full[dy], par);
+                tc_fence_after_sync();
+                uint32_t row[ROWPK], m[NPK];
+                team_load_row<C>(tm_lane + 3 * C * dy, row);
+                tmem_ld_wait();
+                reg_fence_u<ROWPK>(row);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rel[dy]);                 // the next tile's MMAs of this block row may start
+                team_max_dx<C>(row, m);
+#pragma unroll
+                for (int i = 0; i < NPK; ++i) run[i] = dy == 0 ? m[i] : (dy == 1 ? hmax2(run[i], m[i]) : hmax3(run[i], m[i], 0u));   // ... and the ReLU
+            }
+#pragma unroll
+            for (int i = 0; i < NPK / 4; ++i) {                 // scale (+-2^k, exact) and BatchNorm shift
+                const uint4 sc = sc4[i], sh = sh4[i];
+                run[4 * i + 0] = hfma2(run[4 * i + 0], sc.x, sh.x);
+                run[4 * i + 1] = hfma2(run[4 * i + 1], sc.y, sh.y);
+                run[4 * i + 2] = hfma2(run[4 * i + 2], sc.z, sh.z);
+                run[4 * i + 3] = hfma2(run[4 * i + 3], sc.w, sh.w);
+            }
+            if (t == set) grid_dep_wait();                         // the kernel that may still read this buffer has completed
+            if (fi < n_frames_cta && Y < p.P1h) {
+                // entry of the phase-split buffer (32-bit arithmetic: the buffer has fewer than 2^32 16-byte entries)
+                const uint32_t off = (uint32_t)(((Y % 3) * 3 + X % 3) * CG) * (uint32_t)p.out.gtot +
+                                     (uint32_t)(p.out.frame0 + blockIdx.x + fi * gridDim.x) * (uint32_t)p.out.FP + (uint32_t)((Y / 3) * p.out.PW + X / 3);
+                uint4 *dst = reinterpret_cast<uint4 *>(p.out.ptr) + off;
+#pragma unroll
+                for (int j = 0; j < CG; ++j) dst[(size_t)j * p.out.gtot] = make_uint4(run[4 * j], run[4 * j + 1], run[4 * j + 2], run[4 * j + 3]);
+            }
+            X += 256;                                              // this set's next tile: 64 <= P1w, at most four rows further; branch-free
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) { const bool c = X >= p.P1w; X -= c ? p.P1w : 0; Y += c ? 1 : 0; }
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) { const bool c = Y > p.P1h; Y -= c ? p.P1h + 1 : 0; fi += c ? 1 : 0; }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2049 + 2 * blockIdx.x] = g; }
     if (warp == RL::MMA_WARP0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -2019,6 +2272,8 @@ int set_smem_limits() {
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32));
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_sets_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_sets_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_teams_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_teams_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, MidSmem<C>::total));
@@ -2056,18 +2311,20 @@ int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
 }
 
 template <int C>
-int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream, bool pdl, bool acc32, int grid_cap, bool use_teams) {
+int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream, bool pdl, bool acc32, int grid_cap, int variant) {
+    const bool use_teams = variant == 1, use_sets = variant == 2;
     // grid_cap (CUTDET_OPT_CONV1_GRID) is a test hook: several frames per CTA, as on a part with fewer SMs than a sub-batch has frames
     const int grid = std::min(std::min(p.B, sm_count()), grid_cap > 0 ? grid_cap : 1 << 30);
     static const bool regs_ok = [] {
-        const void *fns[6] = {(const void *)conv1_fused_tc_kernel<C, true, false>, (const void *)conv1_fused_tc_kernel<C, false, false>,
+        const void *fns[8] = {(const void *)conv1_fused_tc_kernel<C, true, false>, (const void *)conv1_fused_tc_kernel<C, false, false>,
                               (const void *)conv1_fused_tc_kernel<C, true, true>, (const void *)conv1_fused_tc_kernel<C, false, true>,
-                              (const void *)conv1_fused_teams_kernel<C, true>, (const void *)conv1_fused_teams_kernel<C, false>};
+                              (const void *)conv1_fused_teams_kernel<C, true>, (const void *)conv1_fused_teams_kernel<C, false>,
+                              (const void *)conv1_fused_sets_kernel<C, true>, (const void *)conv1_fused_sets_kernel<C, false>};
         bool ok = true;
-        for (int i = 0; i < 6; ++i) {
+        for (int i = 0; i < 8; ++i) {
             cudaFuncAttributes a{};
             cudaFuncGetAttributes(&a, fns[i]);
-            const int want = i < 2 ? F1Roles<false>::REGS_START : (i < 4 ? F1Roles<true>::REGS_START : T1Roles::REGS_START);
+            const int want = i < 2 ? F1Roles<false>::REGS_START : (i < 4 ? F1Roles<true>::REGS_START : (i < 6 ? T1Roles::REGS_START : S2Roles::REGS_START));
             if (a.numRegs != want) {
                 fprintf(stderr, "cutdet: conv1_fused_tc compiled with %d registers, the setmaxnreg budget assumes %d\n", a.numRegs, want);
                 ok = false;
@@ -2094,7 +2351,9 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_
         const bool gather = src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0;
         // pdl: only when the kernel before this one is one of ours (conv2/conv3 of the previous sub-batch): the loaders read the
         // frames without waiting for it, so it must not be what produced them
-        if (teams && gather) launch_pdl(pdl, conv1_fused_teams_kernel<C, true>, grid, T1Roles::THREADS, smem16, stream, p, src);
+        if (acc16 && use_sets && gather) launch_pdl(pdl, conv1_fused_sets_kernel<C, true>, grid, S2Roles::THREADS, smem16, stream, p, src);
+        else if (acc16 && use_sets) launch_pdl(pdl, conv1_fused_sets_kernel<C, false>, grid, S2Roles::THREADS, smem16, stream, p, src);
+        else if (teams && gather) launch_pdl(pdl, conv1_fused_teams_kernel<C, true>, grid, T1Roles::THREADS, smem16, stream, p, src);
         else if (teams) launch_pdl(pdl, conv1_fused_teams_kernel<C, false>, grid, T1Roles::THREADS, smem16, stream, p, src);
         else if (gather && acc16) launch_pdl(pdl, conv1_fused_tc_kernel<C, true, true>, grid, thr16, smem16, stream, p, src);
         else if (gather) launch_pdl(pdl, conv1_fused_tc_kernel<C, true, false>, grid, thr32, smem32, stream, p, src);
@@ -2190,7 +2449,7 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     if (fused) {
         FusedSrc fs = *fused;
         fs.frames += (long long)f0 * fs.frame_stride;
-        if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0 && !net->opt.no_pdl, net->opt.conv1_acc32 != 0, net->opt.conv1_grid, net->opt.conv1_teams != 0)) return rc;
+        if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0 && !net->opt.no_pdl, net->opt.conv1_acc32 != 0, net->opt.conv1_grid, net->opt.conv1_teams)) return rc;
     } else if (int rc = launch_conv1<C>(c1, stream)) return rc;
 
     MidParams p2 = mid_params(nb, g.FP1, g.PW1, g.P2h, g.P2w);

@@ -243,7 +243,7 @@ extern "C" int cutdet_net_set_option(cutdet_net *net, int option, int value) {
         case CUTDET_OPT_GROUP_FRAMES: net->opt.group_frames = value; break;
         case CUTDET_OPT_NO_PDL: net->opt.no_pdl = value != 0; break;
         case CUTDET_OPT_CONV1_GRID: net->opt.conv1_grid = value; break;
-        case CUTDET_OPT_CONV1_TEAMS: net->opt.conv1_teams = value != 0; break;
+        case CUTDET_OPT_CONV1_TEAMS: net->opt.conv1_teams = value; break;
         default: return fail(CUTDET_EINVAL, "net_set_option: unknown option %d", option);
     }
     return CUTDET_OK;
@@ -266,7 +266,7 @@ extern "C" int cutdet_net_get_option(const cutdet_net *net, int option, int *val
 extern "C" int cutdet_net_debug_timeline(cutdet_net *net, int kernel, long long *stamps_dev, size_t n_entries) {
     CUTDET_REQUIRE(net, "net_debug_timeline: null net");
     if (kernel == 0 || !stamps_dev) { net->opt.timeline_kernel = 0; net->opt.timeline_dev = nullptr; return CUTDET_OK; }
-    CUTDET_REQUIRE((kernel == 1 || kernel == 2) && n_entries >= 2048, "net_debug_timeline: kernel 1 or 2 and >= 2048 entries");
+    CUTDET_REQUIRE((kernel == 1 || kernel == 2) && n_entries >= 4096, "net_debug_timeline: kernel 1 or 2 and >= 4096 entries");
     net->opt.timeline_kernel = kernel;
     net->opt.timeline_dev = stamps_dev;
     return CUTDET_OK;

@@ -185,7 +185,8 @@ CUTDET_API int cutdet_net_forward_fc_layer(cutdet_net *net, int layer, const flo
                                 int relu, int bn_mode, cutdet_stream_t stream);
 
 /* Debug aid (tools/timeline.py): while armed (kernel 1 = conv1_fused_tc, 2 = conv2_tc; 0 or a null buffer disarms), CTA 0 of
- * every full sub-batch launch of that kernel writes clock stamps into the caller's device buffer of >= 2048 int64 entries.
+ * every full sub-batch launch of that kernel writes clock stamps into the caller's device buffer of >= 4096 int64 entries
+ * (conv1: entries 2048 + 2 b, 2049 + 2 b = %globaltimer at entry / exit of CTA b).
  * The library allocates, copies and synchronises nothing for it.                                                          */
 CUTDET_API int cutdet_net_debug_timeline(cutdet_net *net, int kernel, long long *stamps_dev, size_t n_entries);
 

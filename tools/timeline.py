@@ -36,8 +36,8 @@ def main():
     for _ in range(3):
         native.forward_frames(plan, frames)
     torch.cuda.synchronize()
-    stamps = torch.zeros(2048, dtype=torch.int64, device="cuda")
-    _cabi.check(_cabi.lib().cutdet_net_debug_timeline(native.handle, a.kernel, stamps.data_ptr(), 2048))
+    stamps = torch.zeros(4096, dtype=torch.int64, device="cuda")
+    _cabi.check(_cabi.lib().cutdet_net_debug_timeline(native.handle, a.kernel, stamps.data_ptr(), 4096))
     native.forward_frames(plan, frames)
     torch.cuda.synchronize()
     _cabi.check(_cabi.lib().cutdet_net_debug_timeline(native.handle, 0, None, 0))
@@ -45,9 +45,14 @@ def main():
     t0 = h[2047] if a.kernel == 1 else h[0]
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     with open(a.out, "w") as f:
-        for i, v in enumerate(h):
+        for i, v in enumerate(h[:2048]):
             if v:
                 f.write(f"{i} {v - t0}\n")
+        if a.kernel == 1:          # per-CTA entry / exit in ns since the first CTA's entry
+            g0 = min(v for v in h[2048::2] if v)
+            for b in range(148):
+                if h[2048 + 2 * b]:
+                    f.write(f"cta {b} {h[2048 + 2 * b] - g0} {h[2049 + 2 * b] - g0}\n")
     print(f"wrote {sum(1 for v in h if v)} stamps to {a.out}")
 
 
