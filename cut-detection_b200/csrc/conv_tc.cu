@@ -912,7 +912,7 @@ __device__ __forceinline__ void chunk_from_raw(const uint32_t (&w)[5], uint4 &lo
     hi.w = __byte_perm(w[4], K0, 0x7640);                       // B4, then the constant 1024 that multiplies the bias row
 }
 
-// ---- the unfold role of the fused kernels (shared by conv1_fused_tc_kernel and conv1_fused_teams_kernel) ----
+// ---- the unfold role of the fused kernels (shared by conv1_fused_tc_kernel and conv1_fused_sets_kernel) ----
 struct F1Ctx {
     const Conv1Params *p;
     const FusedSrc *src;
@@ -1297,33 +1297,9 @@ __global__ void __launch_bounds__(F1Roles<ACC16>::THREADS, 1) conv1_fused_tc_ker
     if (warp == F1_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// ------------------------------------------------------------------------------------------------ K1 + layer 1, one team per block row
-// EXPERIMENT (net option conv1_teams; not the default -- measured 2-3 % slower on same-box A/Bs, profiles/README.md round 2).
-// conv1_fused_tc_kernel above runs ONE MMA issuer and ONE set of epilogue warps over the three block rows of a tile in turn; its
-// clock stamps show a tile period of ~1,450 cycles against 648 cycles of MMAs: issuing a block row keeps the issuer ~270 cycles
-// (the instruction waits for the tensor pipe), an epilogue warp needs ~450 cycles per block row (barrier, TMEM load, wait::ld,
-// release), and each of the two serial chains waits for the other once per tile.  Here every block row dy is its own pipeline:
-//     MMA issuer dy (one warp)  -> acc_full[dy] ->  team dy (four warps, one per TMEM lane quarter) -> acc_empty[dy] -> issuer dy
-// A team thread reads ALL the channels of its block row (3 dx x C fp16 accumulators = 3C/2 packed registers), takes the max over
-// dx, and the 9-way max is finished by passing the partial maxima DOWN the teams through spare TMEM columns (tcgen05.st /
-// tcgen05.ld: the 80 columns the accumulator leaves free):
-//     team 0: max over dx -> p0                team 1: max(p0, max over dx) -> p01            team 2: relu(max(p01, max over dx))
-// Rows complete in that order, so a team never waits for a later one; team 2 applies scale/shift and stores all C channels.
-// What the stamps of THIS kernel show: the rows' pipelines do decouple (a row is read and handed back ~250 cycles after its MMAs
-// complete), but a hop between teams costs ~400 cycles (st, wait::st, barrier, ld, wait::ld) and the middle team's chain --
-// read, hop in, hop out -- is ~1,400 cycles per tile, so the period stays at ~1,500; with the hops through shared memory
-// instead the teams are fast but the added LSU traffic slows the unfold warps 2-3 x and the rows starve.  TMEM holds one
-// accumulator tile (432 of 512 columns) and the register file cannot hold a second set of teams, so no two tiles can be in the
-// epilogue at once: the serial latency chain per tile is what it is.  Kept for A/B runs; results are bit-identical.
-struct T1Roles {
-    // warps: 0-11 teams | 12-19 unfold | 20-22 MMA issuers, 23 idle | 24-26 loaders, 27 idle
-    static constexpr int TEAM_WARPS = 12, UNFOLD_WARPS = 8, UNFOLD_WARP0 = 12, MMA_WARP0 = 20, LOAD_WARP0 = 24, WARPS = 28, THREADS = 32 * WARPS;
-    static constexpr int REGS_START = 72, REGS_TEAM = 112, REGS_UNFOLD = 56, REGS_MMA = 32, REGS_LOAD = 24;
-    static_assert(THREADS * REGS_START == 384 * REGS_TEAM + 256 * REGS_UNFOLD + 128 * REGS_MMA + 128 * REGS_LOAD, "register pool");
-};
-
+// ------------------------------------------------------------------------------------------------ helpers of the two-set kernel
 template <int C>
-__device__ __forceinline__ void team_load_row(uint32_t taddr, uint32_t (&row)[3 * C / 2]) {
+__device__ __forceinline__ void row_load_all(uint32_t taddr, uint32_t (&row)[3 * C / 2]) {
     static_assert(C == 48 || C == 32, "channels");
     if constexpr (C == 48) {            // 144 columns: 64 + 64 + 16 (an x64 load alone does not fit the kernel's launch-time register count)
         tmem_ld_pack32(taddr, row);
@@ -1336,306 +1312,13 @@ __device__ __forceinline__ void team_load_row(uint32_t taddr, uint32_t (&row)[3 
 }
 // the row's columns are ordered [channel half][dx][C/2 channels]: max over dx, channel pairs in channel order
 template <int C>
-__device__ __forceinline__ void team_max_dx(const uint32_t (&row)[3 * C / 2], uint32_t (&m)[C / 2]) {
+__device__ __forceinline__ void row_max_dx(const uint32_t (&row)[3 * C / 2], uint32_t (&m)[C / 2]) {
     constexpr int Q = C / 4;            // packed pairs per (half, dx)
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int j = 0; j < Q; ++j) m[h * Q + j] = hmax3(row[h * 3 * Q + j], row[h * 3 * Q + Q + j], row[h * 3 * Q + 2 * Q + j]);
 }
-// Partial maxima travel between the teams of a lane quarter through spare TMEM columns (tcgen05.st / wait::st / mbarrier /
-// tcgen05.ld / wait::ld).  Shared memory was tried for the hop as well (24 KB taken from the raw ring, 128-bit conflict-free
-// accesses): the teams' chains got short, but the extra LSU traffic slowed the unfold warps' gather 2-3 x and the rows became the
-// bottleneck (1.95 M frames/s against 2.15 M; profiles/README.md, round 2).
-template <int C>
-__device__ __forceinline__ void team_xch_store(uint32_t taddr, const uint32_t (&m)[C / 2]) {
-    tmem_st_u16(taddr, m);
-    if constexpr (C == 48) tmem_st_u8(taddr + 16, m + 16);
-}
-template <int C>
-__device__ __forceinline__ void team_xch_load(uint32_t taddr, uint32_t (&v)[C / 2]) {
-    tmem_ld_u16(taddr, v);
-    if constexpr (C == 48) tmem_ld_u8(taddr + 16, v + 16);
-}
-
-template <int C, bool GATHER>
-__global__ void __launch_bounds__(T1Roles::THREADS, 1) conv1_fused_teams_kernel(const Conv1Params p, const FusedSrc src) {
-    using RL = T1Roles;
-    constexpr int UNFOLD_WARPS = RL::UNFOLD_WARPS;
-    using S = F1Smem<C, UNFOLD_WARPS>;
-    constexpr int CG = C / 8, NPK = C / 2, ROWPK = 3 * C / 2;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *s_w = smem;
-    uint8_t *s_ring = smem + S::OFF_RING;
-    uint8_t *s_raw = smem + S::OFF_RAW;
-    int *s_rowoff = reinterpret_cast<int *>(smem + S::OFF_TAB);               // [y][2]
-    int *s_yb = s_rowoff + 2 * F_MAX_DST;                                       // [y][2]: b0, b1
-    int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);              // [x]: 3*x0, a0 | a1 << 16
-    uint32_t *s_cmp = reinterpret_cast<uint32_t *>(smem + S::OFF_CMP);          // [unfold warp][F1_CMP_STRIDE]
-    uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);       // [3]
-    uint64_t *acc_empty = acc_full + 3;                                         // [3]
-    uint64_t *raw_full = acc_empty + 3;                                         // [RAW_SLOTS_MAX]
-    uint64_t *raw_empty = raw_full + RAW_SLOTS_MAX;                             // [RAW_SLOTS_MAX]
-    uint64_t *tile_done = raw_empty + RAW_SLOTS_MAX;                            // [TILE_RING] tile t's MMAs have completed
-    uint64_t *xch_full = tile_done + TILE_RING;                                 // [2][4]: p0 / p01 of lane quarter q is in TMEM
-    uint64_t *xch_empty = xch_full + 8;                                         // [2][4]: ... has been read
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xch_empty + 8);
-    int *s_rows_done = reinterpret_cast<int *>(tmem_slot + 2);                  // [UNFOLD_WARPS] rows finished by each unfold warp
-    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;                            // [LOADER_WARPS] rows issued by each loader
-    static_assert((3 + 3 + 2 * RAW_SLOTS_MAX + TILE_RING + 16) * 8 + 8 + (UNFOLD_WARPS + 4) * 4 <= 1024, "barrier block");
-    uint32_t *s_par16 = reinterpret_cast<uint32_t *>(smem + S::OFF_PAR);        // [C/2 scale pairs | C/2 shift pairs]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const ResizePlanDev &plan = src.plan;
-    const int H = p.H, P1w = p.P1w, RPF = p.P1h + 1;          // pooled rows per frame incl. the zero row
-    const int Hc = min(H, 3 * p.P1h + 1);                     // resized rows the conv reads (row 3*P1h only if it exists)
-    const int n_frames_cta = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int n_tiles = (n_frames_cta * RPF * P1w + 127) / 128;
-    const int total_u = 3 * n_frames_cta * RPF;               // resized rows incl. the zero rows, u = 3R + sub
-    const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;
-    const uint32_t inv_slots = 0xffffffffu / (uint32_t)n_slots + 1u;       // n / n_slots = umulhi(n, inv_slots), exact while n * n_slots < 2^32
-
-    for (int i = threadIdx.x; i < S::W_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_w)[i] = p.w_perm16[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) s_par16[i] = p.par16[i];
-    // operand-format zeros for the row above the first frame (tile 0's view shifted by -P1w); the last half of the second
-    // plane is the constant 1.0 that multiplies the bias row
-    for (int i = threadIdx.x; i < UNFOLD_WARPS * F1_CMP_STRIDE; i += blockDim.x) s_cmp[i] = 0u;
-    for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
-        reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
-            make_uint4(0u, 0u, 0u, i >= P1w ? 0x3c000000u : 0u);
-    for (int y = threadIdx.x; y < H; y += blockDim.x) {
-        int r0, r1, b0 = 2048, b1 = 0;
-        if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
-        else if (plan.mode == RESIZE_COPY) { r0 = r1 = y; }
-        else if (plan.mode == RESIZE_AREA2) { r0 = 2 * y; r1 = 2 * y + 1; }
-        else { r0 = plan.y0[y]; r1 = plan.y1[y]; b0 = plan.b0[y]; b1 = plan.b1[y]; }
-        if (src.compact) { r0 = plan.row_slot[r0]; r1 = (plan.mode == RESIZE_LINEAR && b1 == 0) ? r0 : plan.row_slot[r1]; }
-        s_rowoff[2 * y] = (int)(r0 * src.row_pitch);
-        s_rowoff[2 * y + 1] = (int)(r1 * src.row_pitch);
-        s_yb[2 * y] = b0;
-        s_yb[2 * y + 1] = b1;
-    }
-    if (plan.mode == RESIZE_LINEAR && plan.gather_step_x == 0)
-        for (int x = threadIdx.x; x < plan.dst_w; x += blockDim.x) {
-            const int x0 = plan.x0[x], x1 = plan.x1[x];
-            int a0 = plan.a0[x], a1 = plan.a1[x];
-            if (x1 != x0 + 1) { a0 += a1; a1 = 0; }          // clamped at the edge: always read the six bytes of pixels x0, x0 + 1
-            s_xtab[x] = make_int4(3 * x0, a0 | (a1 << 16), 0, 0);
-        }
-    if (threadIdx.x < UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;       // ... and s_rows_issued
-    fence_proxy_async();
-    if (threadIdx.x == 0) {
-        for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], 4); }
-        for (int s = 0; s < RAW_SLOTS_MAX; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
-        for (int s = 0; s < TILE_RING; ++s) mbar_init(&tile_done[s], 3);
-        for (int s = 0; s < 8; ++s) { mbar_init(&xch_full[s], 1); mbar_init(&xch_empty[s], 1); }
-        fence_barrier_init();
-    }
-    if (warp == RL::MMA_WARP0) tmem_alloc(tmem_slot, TMEM_COLS);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-    long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;     // debug stamps of CTA 0 (cutdet_net_debug_timeline)
-    if (tl && threadIdx.x == 0) tl[2047] = clock64();
-    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2048 + 2 * blockIdx.x] = g; }
-    // Programmatic dependent launch: the kernel before this one -- conv2 of the previous sub-batch -- may still be READING the
-    // activation buffer this kernel writes.  Only team 2's stores and the pad zeroing touch it: they wait for that kernel to
-    // complete (grid_dep_wait), everything else starts at once.  The next kernel may be scheduled now.
-    grid_dep_launch();
-
-    // Register budgets per warpgroup (setmaxnreg.sync.aligned), set at the top of each role's branch so that ptxas sees which
-    // budget governs which code (set in a separate if-chain it allocated every role within the smallest one).
-    if (warp >= RL::LOAD_WARP0) {
-      reg_dealloc<RL::REGS_LOAD>();
-      if (warp < RL::LOAD_WARP0 + LOADER_WARPS) {
-        // ------------------------------------------------------------------ loaders: source rows -> raw ring
-        // row n is issued by loader n % n_loaders into slot n % n_slots (the slot count is a multiple of the loader count, so a
-        // slot is always refilled by the same loader; the wait on raw_empty is for row n - n_slots to have been read)
-        const int lw = warp - RL::LOAD_WARP0, total_rows = n_frames_cta * Hc;
-        const int n_loaders = min(LOADER_WARPS, n_slots);
-        if (lw < n_loaders) {
-            const uint64_t stream_once = l2_policy_evict_first();   // frames are read once: keep the L2 for the activations
-            int fi = 0, y = lw, issued = 0;
-            for (int n = lw; n < total_rows; n += n_loaders, y += n_loaders) {
-                while (y >= Hc) { y -= Hc; ++fi; }
-                const int use = (int)__umulhi((uint32_t)n, inv_slots), slot = n - use * n_slots;
-                mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
-                if (tl && lane == 0 && n < 256) tl[n] = clock64();
-                ++issued;
-                if (elect_one()) {
-                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)fi * gridDim.x) * src.frame_stride;
-                    mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
-                    for (int j = 0; j < src.n_src; ++j)
-                        bulk_load_1d_hint(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * y + j],
-                                          (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
-                    st_release_shared(&s_rows_issued[lw], issued);   // raw_full[slot] is now in row n's phase
-                }
-                __syncwarp();
-            }
-        }
-      }
-    } else if (warp >= RL::MMA_WARP0) {
-      reg_dealloc<RL::REGS_MMA>();
-      if (warp < RL::MMA_WARP0 + 3) {
-        // ------------------------------------------------------------------ MMA issuer of block row dy
-        const int dy = warp - RL::MMA_WARP0;
-        const bool stamp = tl && lane == 0;
-        uint32_t acc_phase = 0;
-        const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
-        const uint32_t idesc = instr_desc_f16_acc16(128, 3 * C);
-        const uint32_t tmem_row = tmem_base + 3 * C * dy;
-        int r_hi = 127 / P1w, r_rem = 127 % P1w;      // pooled row of the tile's last position, kept without a division per tile
-        for (int t = 0; t < n_tiles; ++t) {
-            // block row dy reads input rows 3R - 1 + dy .. 3R + 1 + dy of pooled row R: resized rows up to u = 3 r_hi + 1 + dy
-            const int u_hi = min(total_u - 1, 3 * r_hi + 1 + dy);
-            r_rem += 128;                                 // 64 <= P1w: at most three rows further
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { const bool c = r_rem >= P1w; r_rem -= c ? P1w : 0; r_hi += c ? 1 : 0; }
-            const int mine = lane % UNFOLD_WARPS;
-            const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
-            while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(20);
-            __syncwarp();
-            if (stamp && dy == 0 && t < 64) tl[1024 + t] = clock64();
-            uint32_t a_chunk[3];
-#pragma unroll
-            for (int ks = 0; ks < 3; ++ks) {
-                const int c = dy + ks, sub = (c + 2) % 3, shift = c == 0 ? -P1w : (c == 4 ? P1w : 0);
-                a_chunk[ks] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
-            }
-            mbar_wait(&acc_empty[dy], acc_phase ^ 1);
-            tc_fence_after_sync();
-            if (stamp && t < 60) tl[1800 + 4 * t + dy] = clock64();
-            if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < 3; ++ks) {
-                    const uint64_t da = smem_desc(a_chunk[ks], FR_PLANE, 128);
-                    const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
-                    umma_16bit(tmem_row, da, db, idesc, ks > 0 ? 1u : 0u);
-                }
-                umma_commit(&acc_full[dy]);
-                umma_commit(&tile_done[t & (TILE_RING - 1)]);     // tile t no longer reads the operand ring once all three rows have completed
-            }
-            __syncwarp();
-            acc_phase ^= 1;
-        }
-      }
-    } else if (warp >= RL::UNFOLD_WARP0) {
-        // ------------------------------------------------------------------ unfold: raw rows -> x-unfolded fp16 ring
-        reg_dealloc<RL::REGS_UNFOLD>();
-        F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
-                 RPF, Hc, total_u, n_slots, slot_bytes, min(LOADER_WARPS, n_slots), inv_slots, tl};
-        f1_unfold_role<C, GATHER, true, UNFOLD_WARPS>(cx, warp - RL::UNFOLD_WARP0, lane);
-        // ... and, once the rows are through, the entries of the output buffer that are not pixels (they belong to no GEMM row)
-        grid_dep_wait();
-        for (int fi = 0; fi < n_frames_cta; ++fi)
-            zero_pads(p.out, CG, blockIdx.x + fi * gridDim.x, blockIdx.x + fi * gridDim.x + 1, threadIdx.x - 32 * RL::UNFOLD_WARP0, 32 * UNFOLD_WARPS);
-    } else {
-        // ------------------------------------------------------------------ teams: block row `team` of every tile
-        reg_alloc<RL::REGS_TEAM>();
-        const int team = warp >> 2, q = warp & 3;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t tm_row = lane_base + 3 * C * team, tm_p0 = lane_base + 9 * C, tm_p01 = tm_p0 + NPK;
-        uint64_t *full = &acc_full[team], *empty = &acc_empty[team];
-        uint64_t *p0_full = &xch_full[q], *p0_empty = &xch_empty[q], *p01_full = &xch_full[4 + q], *p01_empty = &xch_empty[4 + q];
-        const bool stamp = tl && q == 0 && lane == 0 && team < 2;      // (team 2 has no register to spare for debug stamps)
-        // read this team's block row of tile t and hand it back to its issuer; returns the max over dx
-        auto read_row = [&](int t, uint32_t (&m)[NPK]) {
-            mbar_wait(full, (uint32_t)(t & 1));
-            tc_fence_after_sync();
-            if (stamp && t < 64) tl[1216 + 8 * t + 3 * team + 1] = clock64();         // the row's MMAs have completed
-            uint32_t row[ROWPK];
-            team_load_row<C>(tm_row, row);
-            tmem_ld_wait();
-            reg_fence_u<ROWPK>(row);
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty);
-            if (stamp && t < 64) tl[1216 + 8 * t + 3 * team + 2] = clock64();         // row handed back
-            team_max_dx<C>(row, m);
-        };
-        if (team == 0) {
-            for (int t = 0; t < n_tiles; ++t) {
-                uint32_t m[NPK];
-                read_row(t, m);
-                mbar_wait(p0_empty, (uint32_t)(t & 1) ^ 1);          // team 1 has read p0 of tile t - 1
-                tc_fence_after_sync();
-                team_xch_store<C>(tm_p0, m);
-                tmem_st_wait();
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p0_full);
-            }
-        } else if (team == 1) {
-            for (int t = 0; t < n_tiles; ++t) {
-                uint32_t m[NPK], v[NPK];
-                read_row(t, m);
-                mbar_wait(p0_full, (uint32_t)(t & 1));
-                tc_fence_after_sync();
-                team_xch_load<C>(tm_p0, v);
-                tmem_ld_wait();
-                reg_fence_u<NPK>(v);
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p0_empty);
-#pragma unroll
-                for (int i = 0; i < NPK; ++i) m[i] = hmax2(m[i], v[i]);
-                mbar_wait(p01_empty, (uint32_t)(t & 1) ^ 1);         // team 2 has read p01 of tile t - 1
-                tc_fence_after_sync();
-                team_xch_store<C>(tm_p01, m);
-                tmem_st_wait();
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p01_full);
-            }
-        } else {
-            const int mrow = q * 32 + lane;
-            int X = mrow % P1w, Y = mrow / P1w, fi = 0;        // position 128 t + mrow = ((fi * RPF + Y) * P1w + X), advanced tile by tile
-            while (Y >= RPF) { Y -= RPF; ++fi; }
-            const uint4 *sc4 = reinterpret_cast<const uint4 *>(s_par16), *sh4 = reinterpret_cast<const uint4 *>(s_par16 + NPK);
-            for (int t = 0; t < n_tiles; ++t) {
-                // (no register may spill here: this CTA's shared memory leaves no L1, a spilled word costs an L2 round trip -- 18
-                // spilled words once made the tail of this loop 2,000 cycles long)
-                // p01 is complete well before this tile's block row 2 (rows finish in order): its load flies while the row is waited for
-                uint32_t m[NPK], v[NPK];
-                mbar_wait(p01_full, (uint32_t)(t & 1));
-                tc_fence_after_sync();
-                team_xch_load<C>(tm_p01, v);
-                read_row(t, m);                                 // (its wait::ld covers the load above)
-                reg_fence_u<NPK>(v);
-                if (lane == 0) mbar_arrive(p01_empty);
-#pragma unroll
-                for (int i = 0; i < NPK / 4; ++i) {             // 9-way max, ReLU (the bias is inside the accumulator), scale and shift
-                    const uint4 sc = sc4[i], sh = sh4[i];
-                    m[4 * i + 0] = hfma2(hmax3(m[4 * i + 0], v[4 * i + 0], 0u), sc.x, sh.x);
-                    m[4 * i + 1] = hfma2(hmax3(m[4 * i + 1], v[4 * i + 1], 0u), sc.y, sh.y);
-                    m[4 * i + 2] = hfma2(hmax3(m[4 * i + 2], v[4 * i + 2], 0u), sc.z, sh.z);
-                    m[4 * i + 3] = hfma2(hmax3(m[4 * i + 3], v[4 * i + 3], 0u), sc.w, sh.w);
-                }
-                if (t == 0) grid_dep_wait();                   // the kernel that may still read this buffer has completed
-                // (X, Y, fi) is this tile's position: the address is worked out here, when the row's registers are free again
-                if (fi < n_frames_cta && Y < p.P1h) {
-                    // entry of the phase-split buffer (32-bit arithmetic: the buffer has fewer than 2^32 16-byte entries)
-                    const uint32_t off = (uint32_t)(((Y % 3) * 3 + X % 3) * CG) * (uint32_t)p.out.gtot +
-                                         (uint32_t)(p.out.frame0 + blockIdx.x + fi * gridDim.x) * (uint32_t)p.out.FP + (uint32_t)((Y / 3) * p.out.PW + X / 3);
-                    uint4 *dst = reinterpret_cast<uint4 *>(p.out.ptr) + off;
-#pragma unroll
-                    for (int j = 0; j < CG; ++j) dst[(size_t)j * p.out.gtot] = make_uint4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]);
-                }
-                X += 128;                                      // next tile: 64 <= P1w, at most three rows further; branch-free
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { const bool c = X >= P1w; X -= c ? P1w : 0; Y += c ? 1 : 0; }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { const bool c = Y >= RPF; Y -= c ? RPF : 0; fi += c ? 1 : 0; }
-            }
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2049 + 2 * blockIdx.x] = g; }
-    if (warp == RL::MMA_WARP0) tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
 // ------------------------------------------------------------------------------------------------ K1 + layer 1, two epilogue sets
 // The fused kernel with TWO sets of epilogue warps that alternate over the tiles and an MMA issuer per block row.
 // TMEM holds one accumulator tile (432 of 512 columns), so tile t + 1's block row dy can only be computed once tile t's row dy has
@@ -1845,13 +1528,13 @@ __global__ void __launch_bounds__(S2Roles::THREADS, 1) conv1_fused_sets_kernel(c
                 mbar_wait(&full[dy], par);
                 tc_fence_after_sync();
                 uint32_t row[ROWPK], m[NPK];
-                team_load_row<C>(tm_lane + 3 * C * dy, row);
+                row_load_all<C>(tm_lane + 3 * C * dy, row);
                 tmem_ld_wait();
                 reg_fence_u<ROWPK>(row);
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rel[dy]);                 // the next tile's MMAs of this block row may start
-                team_max_dx<C>(row, m);
+                row_max_dx<C>(row, m);
 #pragma unroll
                 for (int i = 0; i < NPK; ++i) run[i] = dy == 0 ? m[i] : (dy == 1 ? hmax2(run[i], m[i]) : hmax3(run[i], m[i], 0u));   // ... and the ReLU
             }
@@ -2274,8 +1957,6 @@ int set_smem_limits() {
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_tc_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_sets_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_sets_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
-    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_teams_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
-    CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_teams_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, MidSmem<C>::total));
     return CUTDET_OK;
 }
@@ -2312,19 +1993,18 @@ int launch_conv1(const Conv1Params &p, cudaStream_t stream) {
 
 template <int C>
 int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_t stream, bool pdl, bool acc32, int grid_cap, int variant) {
-    const bool use_teams = variant == 1, use_sets = variant == 2;
+    const bool use_sets = variant == 1;        // experiment: two epilogue sets + an MMA issuer per block row (conv1_fused_sets_kernel)
     // grid_cap (CUTDET_OPT_CONV1_GRID) is a test hook: several frames per CTA, as on a part with fewer SMs than a sub-batch has frames
     const int grid = std::min(std::min(p.B, sm_count()), grid_cap > 0 ? grid_cap : 1 << 30);
     static const bool regs_ok = [] {
-        const void *fns[8] = {(const void *)conv1_fused_tc_kernel<C, true, false>, (const void *)conv1_fused_tc_kernel<C, false, false>,
+        const void *fns[6] = {(const void *)conv1_fused_tc_kernel<C, true, false>, (const void *)conv1_fused_tc_kernel<C, false, false>,
                               (const void *)conv1_fused_tc_kernel<C, true, true>, (const void *)conv1_fused_tc_kernel<C, false, true>,
-                              (const void *)conv1_fused_teams_kernel<C, true>, (const void *)conv1_fused_teams_kernel<C, false>,
                               (const void *)conv1_fused_sets_kernel<C, true>, (const void *)conv1_fused_sets_kernel<C, false>};
         bool ok = true;
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 6; ++i) {
             cudaFuncAttributes a{};
             cudaFuncGetAttributes(&a, fns[i]);
-            const int want = i < 2 ? F1Roles<false>::REGS_START : (i < 4 ? F1Roles<true>::REGS_START : (i < 6 ? T1Roles::REGS_START : S2Roles::REGS_START));
+            const int want = i < 2 ? F1Roles<false>::REGS_START : (i < 4 ? F1Roles<true>::REGS_START : S2Roles::REGS_START);
             if (a.numRegs != want) {
                 fprintf(stderr, "cutdet: conv1_fused_tc compiled with %d registers, the setmaxnreg budget assumes %d\n", a.numRegs, want);
                 ok = false;
@@ -2337,7 +2017,6 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_
     // (cutdet_net_set_option(CUTDET_OPT_CONV1_ACC32))
     const bool acc16 = !acc32 && p.w_perm16 != nullptr;
     FusedSrc src = src_in;
-    const bool teams = acc16 && use_teams;    // the kernel with an epilogue team and an MMA issuer per block row (experiment, see below)
     const long long ring_bytes = raw_bytes(acc16 ? F1Roles<true>::UNFOLD_WARPS : F1Roles<false>::UNFOLD_WARPS);
     src.n_slots = (int)std::min<long long>(ring_bytes / ((long long)src.n_src * src.row_bytes), RAW_SLOTS_MAX);
     // Every slot must belong to ONE loader (row n goes to loader n % n_loaders and to slot n % n_slots): a loader's wait on
@@ -2353,8 +2032,6 @@ int launch_conv1_fused(const Conv1Params &p, const FusedSrc &src_in, cudaStream_
         // frames without waiting for it, so it must not be what produced them
         if (acc16 && use_sets && gather) launch_pdl(pdl, conv1_fused_sets_kernel<C, true>, grid, S2Roles::THREADS, smem16, stream, p, src);
         else if (acc16 && use_sets) launch_pdl(pdl, conv1_fused_sets_kernel<C, false>, grid, S2Roles::THREADS, smem16, stream, p, src);
-        else if (teams && gather) launch_pdl(pdl, conv1_fused_teams_kernel<C, true>, grid, T1Roles::THREADS, smem16, stream, p, src);
-        else if (teams) launch_pdl(pdl, conv1_fused_teams_kernel<C, false>, grid, T1Roles::THREADS, smem16, stream, p, src);
         else if (gather && acc16) launch_pdl(pdl, conv1_fused_tc_kernel<C, true, true>, grid, thr16, smem16, stream, p, src);
         else if (gather) launch_pdl(pdl, conv1_fused_tc_kernel<C, true, false>, grid, thr32, smem32, stream, p, src);
         else if (acc16) launch_pdl(pdl, conv1_fused_tc_kernel<C, false, true>, grid, thr16, smem16, stream, p, src);
@@ -2449,7 +2126,7 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     if (fused) {
         FusedSrc fs = *fused;
         fs.frames += (long long)f0 * fs.frame_stride;
-        if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0 && !net->opt.no_pdl, net->opt.conv1_acc32 != 0, net->opt.conv1_grid, net->opt.conv1_teams)) return rc;
+        if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0 && !net->opt.no_pdl, net->opt.conv1_acc32 != 0, net->opt.conv1_grid, net->opt.conv1_variant)) return rc;
     } else if (int rc = launch_conv1<C>(c1, stream)) return rc;
 
     MidParams p2 = mid_params(nb, g.FP1, g.PW1, g.P2h, g.P2w);

@@ -243,7 +243,7 @@ extern "C" int cutdet_net_set_option(cutdet_net *net, int option, int value) {
         case CUTDET_OPT_GROUP_FRAMES: net->opt.group_frames = value; break;
         case CUTDET_OPT_NO_PDL: net->opt.no_pdl = value != 0; break;
         case CUTDET_OPT_CONV1_GRID: net->opt.conv1_grid = value; break;
-        case CUTDET_OPT_CONV1_TEAMS: net->opt.conv1_teams = value; break;
+        case CUTDET_OPT_CONV1_VARIANT: net->opt.conv1_variant = value; break;
         default: return fail(CUTDET_EINVAL, "net_set_option: unknown option %d", option);
     }
     return CUTDET_OK;
@@ -257,7 +257,7 @@ extern "C" int cutdet_net_get_option(const cutdet_net *net, int option, int *val
         case CUTDET_OPT_GROUP_FRAMES: *value = net->opt.group_frames; break;
         case CUTDET_OPT_NO_PDL: *value = net->opt.no_pdl; break;
         case CUTDET_OPT_CONV1_GRID: *value = net->opt.conv1_grid; break;
-        case CUTDET_OPT_CONV1_TEAMS: *value = net->opt.conv1_teams; break;
+        case CUTDET_OPT_CONV1_VARIANT: *value = net->opt.conv1_variant; break;
         default: return fail(CUTDET_EINVAL, "net_get_option: unknown option %d", option);
     }
     return CUTDET_OK;

@@ -131,134 +131,148 @@ __global__ void __launch_bounds__(256) preprocess_generic_kernel(ResizePlanDev p
 // gather, DP2A on byte pairs for the bilinear case), and the output row leaves through shared memory as 128-bit stores --
 // float4 per channel plane, or uint4 over the packed BGR bytes.
 constexpr int ROWS_THREADS = 128;
+constexpr int ROWS_PER_BLOCK = 2;       // output rows per block: all their source rows are in flight together (cp.async)
 
-__device__ __forceinline__ uint4 ldg_nc_128(const uint4 *p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One resized pixel (B, G, R, 0) of output row `y`, column x, from the staged source rows.
+__device__ __forceinline__ uint32_t rows_pixel(const ResizePlanDev &plan, const uint8_t *s_row0, const uint8_t *s_row1, bool two, int b0,
+                                               int b1, int x) {
+    if (plan.gather_step_x > 0 || plan.mode == RESIZE_COPY) {
+        const int o = plan.gather_step_x > 0 ? 3 * (plan.gather_off_x + x * plan.gather_step_x) : 3 * x;
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_row0 + (o & ~3));
+        return __funnelshift_r(wp[0], wp[1], (o & 3) * 8) & 0x00FFFFFFu;
+    }
+    if (plan.mode == RESIZE_AREA2) {
+        const int o = 6 * x;
+        const uint32_t *w0 = reinterpret_cast<const uint32_t *>(s_row0 + (o & ~3));
+        const uint32_t *w1 = reinterpret_cast<const uint32_t *>(s_row1 + (o & ~3));
+        const uint32_t sh = (o & 3) * 8;
+        const uint32_t lo0 = __funnelshift_r(w0[0], w0[1], sh), hi0 = __funnelshift_r(w0[1], w0[2], sh);   // bytes 0..3, 4..7
+        const uint32_t lo1 = __funnelshift_r(w1[0], w1[1], sh), hi1 = __funnelshift_r(w1[1], w1[2], sh);
+        uint32_t px = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t selc = c == 0 ? 0x7730u : (c == 1 ? 0x7741u : 0x7752u);       // (p[2x][c], p[2x+1][c]) in the low half
+            const uint32_t v = (__dp2a_lo(0x00010001u, __byte_perm(lo0, hi0, selc), 0u) +
+                                __dp2a_lo(0x00010001u, __byte_perm(lo1, hi1, selc), 0u) + 2u) >> 2;
+            px |= v << (8 * c);
+        }
+        return px;
+    }
+    const int x0 = __ldg(plan.x0 + x), x1 = __ldg(plan.x1 + x);
+    int a0 = __ldg(plan.a0 + x), a1 = __ldg(plan.a1 + x);
+    if (x1 != x0 + 1) { a0 += a1; a1 = 0; }            // clamped at the edge: both taps are the same pixel
+    const uint32_t aw = (uint32_t)a0 | ((uint32_t)a1 << 16);
+    const int o = 3 * x0;
+    const uint32_t sh = (o & 3) * 8;
+    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(s_row0 + (o & ~3));
+    const uint32_t lo0 = __funnelshift_r(w0[0], w0[1], sh), hi0 = __funnelshift_r(w0[1], w0[2], sh);
+    uint32_t lo1 = 0, hi1 = 0;
+    if (two) {
+        const uint32_t *w1 = reinterpret_cast<const uint32_t *>(s_row1 + (o & ~3));
+        lo1 = __funnelshift_r(w1[0], w1[1], sh); hi1 = __funnelshift_r(w1[1], w1[2], sh);
+    }
+    uint32_t px = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t selc = c == 0 ? 0x7730u : (c == 1 ? 0x7741u : 0x7752u);
+        const int s0 = (int)__dp2a_lo(aw, __byte_perm(lo0, hi0, selc), 0u);
+        const int s1 = two ? (int)__dp2a_lo(aw, __byte_perm(lo1, hi1, selc), 0u) : 0;
+        const int o8 = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+        px |= (uint32_t)min(max(o8, 0), 255) << (8 * c);
+    }
+    return px;
 }
 
 template <int OUT>
 __global__ void __launch_bounds__(ROWS_THREADS) preprocess_rows_kernel(ResizePlanDev plan, const uint8_t *__restrict__ frames,
                                                                       int64_t frame_stride, int64_t row_pitch, int compact,
-                                                                      void *__restrict__ out, int row_pad, int vec_out) {
+                                                                      void *__restrict__ out, int row_pad, int out_pad, int vec_out) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int y = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int y0 = blockIdx.x * ROWS_PER_BLOCK, b = blockIdx.y, tid = threadIdx.x;
     const int row_bytes = 3 * plan.src_w, n16 = (row_bytes + 15) >> 4;
-    uint8_t *s_row0 = smem, *s_row1 = smem + row_pad, *s_out = smem + 2 * row_pad;
-    int r0, r1, b0 = 2048, b1 = 0;
-    if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
-    else if (plan.mode == RESIZE_COPY) { r0 = r1 = y; }
-    else if (plan.mode == RESIZE_AREA2) { r0 = 2 * y; r1 = 2 * y + 1; b1 = 1; }
-    else { r0 = plan.y0[y]; r1 = plan.y1[y]; b0 = plan.b0[y]; b1 = plan.b1[y]; }
-    const bool two = b1 != 0;
-    if (compact) { r0 = plan.row_slot[r0]; r1 = two ? plan.row_slot[r1] : r0; }
     const uint8_t *frame = frames + (int64_t)b * frame_stride;
-    {
+    uint8_t *s_out = smem + 2 * ROWS_PER_BLOCK * row_pad;
+    int yb0[ROWS_PER_BLOCK], yb1[ROWS_PER_BLOCK];
+    // stage: every source row of the block's output rows, 16 bytes per cp.async, all in flight before the one wait
+#pragma unroll
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const int y = y0 + r;
+        yb0[r] = 2048; yb1[r] = 0;
+        if (y >= plan.dst_h) continue;
+        int r0, r1;
+        if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
+        else if (plan.mode == RESIZE_COPY) { r0 = r1 = y; }
+        else if (plan.mode == RESIZE_AREA2) { r0 = 2 * y; r1 = 2 * y + 1; yb1[r] = 1; }
+        else { r0 = plan.y0[y]; r1 = plan.y1[y]; yb0[r] = plan.b0[y]; yb1[r] = plan.b1[y]; }
+        const bool two = yb1[r] != 0;
+        if (compact) { r0 = plan.row_slot[r0]; r1 = two ? plan.row_slot[r1] : r0; }
         const uint4 *g0 = reinterpret_cast<const uint4 *>(frame + (int64_t)r0 * row_pitch);
         const uint4 *g1 = reinterpret_cast<const uint4 *>(frame + (int64_t)r1 * row_pitch);
-        uint4 *d0 = reinterpret_cast<uint4 *>(s_row0), *d1 = reinterpret_cast<uint4 *>(s_row1);
-        // every load is issued before the first store (the compiler keeps them in flight: independent addresses)
-        for (int i = tid; i < n16; i += 4 * ROWS_THREADS) {
-            uint4 a[4], c[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = i + k * ROWS_THREADS;
-                if (j < n16) { a[k] = ldg_nc_128(g0 + j); if (two) c[k] = ldg_nc_128(g1 + j); }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = i + k * ROWS_THREADS;
-                if (j < n16) { d0[j] = a[k]; if (two) d1[j] = c[k]; }
-            }
+        uint4 *d0 = reinterpret_cast<uint4 *>(smem + (2 * r) * row_pad), *d1 = reinterpret_cast<uint4 *>(smem + (2 * r + 1) * row_pad);
+        for (int i = tid; i < n16; i += ROWS_THREADS) {
+            cp_async_16(d0 + i, g0 + i);
+            if (two) cp_async_16(d1 + i, g1 + i);
         }
         if (tid == 0) {        // the taps of the last pixels read a word or two past the row
             d0[n16] = make_uint4(0, 0, 0, 0);
             d1[n16] = make_uint4(0, 0, 0, 0);
         }
     }
+    cp_async_wait_all();
     __syncthreads();
     const int dst_w = plan.dst_w;
-    for (int x = tid; x < dst_w; x += ROWS_THREADS) {
-        uint32_t px;                                           // (B, G, R, 0)
-        if (plan.gather_step_x > 0) {
-            const int o = 3 * (plan.gather_off_x + x * plan.gather_step_x);
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_row0 + (o & ~3));
-            px = __funnelshift_r(wp[0], wp[1], (o & 3) * 8) & 0x00FFFFFFu;
-        } else if (plan.mode == RESIZE_COPY) {
-            const int o = 3 * x;
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_row0 + (o & ~3));
-            px = __funnelshift_r(wp[0], wp[1], (o & 3) * 8) & 0x00FFFFFFu;
-        } else if (plan.mode == RESIZE_AREA2) {
-            const int o = 6 * x;
-            const uint32_t *w0 = reinterpret_cast<const uint32_t *>(s_row0 + (o & ~3));
-            const uint32_t *w1 = reinterpret_cast<const uint32_t *>(s_row1 + (o & ~3));
-            const uint32_t sh = (o & 3) * 8;
-            const uint32_t lo0 = __funnelshift_r(w0[0], w0[1], sh), hi0 = __funnelshift_r(w0[1], w0[2], sh);   // bytes 0..3, 4..7
-            const uint32_t lo1 = __funnelshift_r(w1[0], w1[1], sh), hi1 = __funnelshift_r(w1[1], w1[2], sh);
-            px = 0;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const uint32_t selc = c == 0 ? 0x7730u : (c == 1 ? 0x7741u : 0x7752u);       // (p[2x][c], p[2x+1][c]) in the low half
-                const uint32_t v = (__dp2a_lo(0x00010001u, __byte_perm(lo0, hi0, selc), 0u) +
-                                    __dp2a_lo(0x00010001u, __byte_perm(lo1, hi1, selc), 0u) + 2u) >> 2;
-                px |= v << (8 * c);
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        if (y0 + r >= plan.dst_h) break;
+        const uint8_t *s_row0 = smem + (2 * r) * row_pad, *s_row1 = smem + (2 * r + 1) * row_pad;
+        uint8_t *so8 = s_out + r * out_pad;
+        for (int x = tid; x < dst_w; x += ROWS_THREADS) {
+            const uint32_t px = rows_pixel(plan, s_row0, s_row1, yb1[r] != 0, yb0[r], yb1[r], x);
+            if (OUT == 0) {
+                float *so = reinterpret_cast<float *>(so8);      // [3][dst_w], RGB: output channel 0 is source channel 2
+                so[x] = __fdiv_rn((float)((px >> 16) & 0xff), 255.f);
+                so[dst_w + x] = __fdiv_rn((float)((px >> 8) & 0xff), 255.f);
+                so[2 * dst_w + x] = __fdiv_rn((float)(px & 0xff), 255.f);
+            } else {
+                so8[3 * x] = (uint8_t)px; so8[3 * x + 1] = (uint8_t)(px >> 8); so8[3 * x + 2] = (uint8_t)(px >> 16);
             }
-        } else {
-            const int x0 = __ldg(plan.x0 + x), x1 = __ldg(plan.x1 + x);
-            int a0 = __ldg(plan.a0 + x), a1 = __ldg(plan.a1 + x);
-            if (x1 != x0 + 1) { a0 += a1; a1 = 0; }            // clamped at the edge: both taps are the same pixel
-            const uint32_t aw = (uint32_t)a0 | ((uint32_t)a1 << 16);
-            const int o = 3 * x0;
-            const uint32_t sh = (o & 3) * 8;
-            const uint32_t *w0 = reinterpret_cast<const uint32_t *>(s_row0 + (o & ~3));
-            const uint32_t lo0 = __funnelshift_r(w0[0], w0[1], sh), hi0 = __funnelshift_r(w0[1], w0[2], sh);
-            uint32_t lo1 = 0, hi1 = 0;
-            if (two) {
-                const uint32_t *w1 = reinterpret_cast<const uint32_t *>(s_row1 + (o & ~3));
-                lo1 = __funnelshift_r(w1[0], w1[1], sh); hi1 = __funnelshift_r(w1[1], w1[2], sh);
-            }
-            px = 0;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const uint32_t selc = c == 0 ? 0x7730u : (c == 1 ? 0x7741u : 0x7752u);
-                const int s0 = (int)__dp2a_lo(aw, __byte_perm(lo0, hi0, selc), 0u);
-                const int s1 = two ? (int)__dp2a_lo(aw, __byte_perm(lo1, hi1, selc), 0u) : 0;
-                const int o8 = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
-                px |= (uint32_t)min(max(o8, 0), 255) << (8 * c);
-            }
-        }
-        if (OUT == 0) {
-            float *so = reinterpret_cast<float *>(s_out);       // [3][dst_w], RGB: output channel 0 is source channel 2
-            so[x] = __fdiv_rn((float)((px >> 16) & 0xff), 255.f);
-            so[dst_w + x] = __fdiv_rn((float)((px >> 8) & 0xff), 255.f);
-            so[2 * dst_w + x] = __fdiv_rn((float)(px & 0xff), 255.f);
-        } else {
-            s_out[3 * x] = (uint8_t)px; s_out[3 * x + 1] = (uint8_t)(px >> 8); s_out[3 * x + 2] = (uint8_t)(px >> 16);
         }
     }
     __syncthreads();
-    if (OUT == 0) {
-        const int64_t plane = (int64_t)plan.dst_h * dst_w;
-        float *o = reinterpret_cast<float *>(out) + (int64_t)b * 3 * plane + (int64_t)y * dst_w;
-        if (vec_out) {
-            const int q = dst_w >> 2;
-            for (int i = tid; i < 3 * q; i += ROWS_THREADS) {
-                const int c = i / q, j = i - c * q;
-                reinterpret_cast<float4 *>(o + c * plane)[j] = reinterpret_cast<const float4 *>(s_out)[c * q + j];
+#pragma unroll
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const int y = y0 + r;
+        if (y >= plan.dst_h) break;
+        const uint8_t *so8 = s_out + r * out_pad;
+        if (OUT == 0) {
+            const int64_t plane = (int64_t)plan.dst_h * dst_w;
+            float *o = reinterpret_cast<float *>(out) + (int64_t)b * 3 * plane + (int64_t)y * dst_w;
+            if (vec_out) {
+                const int q = dst_w >> 2;
+                for (int i = tid; i < 3 * q; i += ROWS_THREADS) {
+                    const int c = i / q, j = i - c * q;
+                    reinterpret_cast<float4 *>(o + c * plane)[j] = reinterpret_cast<const float4 *>(so8)[c * q + j];
+                }
+            } else {
+                for (int i = tid; i < 3 * dst_w; i += ROWS_THREADS) { const int c = i / dst_w; o[c * plane + (i - c * dst_w)] = reinterpret_cast<const float *>(so8)[i]; }
             }
         } else {
-            for (int i = tid; i < 3 * dst_w; i += ROWS_THREADS) { const int c = i / dst_w; o[c * plane + (i - c * dst_w)] = reinterpret_cast<const float *>(s_out)[i]; }
-        }
-    } else {
-        uint8_t *o = reinterpret_cast<uint8_t *>(out) + ((int64_t)b * plan.dst_h + y) * dst_w * 3;
-        if (vec_out) {
-            for (int i = tid; i < (3 * dst_w) >> 4; i += ROWS_THREADS) reinterpret_cast<uint4 *>(o)[i] = reinterpret_cast<const uint4 *>(s_out)[i];
-        } else {
-            for (int i = tid; i < 3 * dst_w; i += ROWS_THREADS) o[i] = s_out[i];
+            uint8_t *o = reinterpret_cast<uint8_t *>(out) + ((int64_t)b * plan.dst_h + y) * dst_w * 3;
+            if (vec_out) {
+                for (int i = tid; i < (3 * dst_w) >> 4; i += ROWS_THREADS) reinterpret_cast<uint4 *>(o)[i] = reinterpret_cast<const uint4 *>(so8)[i];
+            } else {
+                for (int i = tid; i < 3 * dst_w; i += ROWS_THREADS) o[i] = so8[i];
+            }
         }
     }
 }
+
+int g_k1_kernel = 0;        // cutdet_debug_k1_kernel: 0 = choose, 1 = one thread per pixel, 2 = row kernel (measurement aid)
 
 int check_frames(const cutdet_resize_plan *plan, const cutdet_frames *src) {
     CUTDET_REQUIRE(plan && src, "preprocess: null plan/frames");
@@ -282,8 +296,8 @@ static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *s
     const bool aligned = ((reinterpret_cast<uintptr_t>(src->frames_dev) | (uintptr_t)src->frame_stride | (uintptr_t)src->row_pitch) & 15) == 0;
     const int row_pad = ((3 * h.src_w + 15) / 16 + 1) * 16;
     const int out_bytes = OUT == 0 ? 3 * h.dst_w * 4 : (3 * h.dst_w + 15) / 16 * 16;
-    const size_t smem = 2 * (size_t)row_pad + out_bytes;
-    if (aligned && smem <= 200 * 1024 && h.dst_h <= 65535) {
+    const size_t smem = (size_t)ROWS_PER_BLOCK * (2 * (size_t)row_pad + out_bytes);
+    if (aligned && smem <= 200 * 1024 && h.dst_h <= 65535 && g_k1_kernel != 1) {
         static bool attr_set[2] = {false, false};
         if (smem > 48 * 1024 && !attr_set[OUT]) {
             CUTDET_CUDA(cudaFuncSetAttribute(preprocess_rows_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -297,9 +311,9 @@ static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *s
             void *o = OUT == 0 ? (void *)((float *)out + b0 * out_frame) : (void *)((uint8_t *)out + b0 * out_frame);
             {
                 KernelScope scope("preprocess_rows_kernel", as_stream(stream));
-                preprocess_rows_kernel<OUT><<<dim3((unsigned)h.dst_h, (unsigned)nb), ROWS_THREADS, smem, as_stream(stream)>>>(
+                preprocess_rows_kernel<OUT><<<dim3((unsigned)ceil_div(h.dst_h, ROWS_PER_BLOCK), (unsigned)nb), ROWS_THREADS, smem, as_stream(stream)>>>(
                     h, src->frames_dev + (int64_t)b0 * src->frame_stride, src->frame_stride, src->row_pitch, src->row_map_compact, o,
-                    row_pad, vec_out ? 1 : 0);
+                    row_pad, out_bytes, vec_out ? 1 : 0);
             }
             CUTDET_LAUNCH_CHECK("preprocess_rows_kernel");
         }
@@ -441,6 +455,12 @@ extern "C" int cutdet_upload_frames(const cutdet_resize_plan *plan, const uint8_
                                           cudaMemcpyHostToDevice, as_stream(stream)));
         }
     if (bytes_copied) *bytes_copied = (int64_t)batch * plan->n_rows * width;
+    return CUTDET_OK;
+}
+
+extern "C" int cutdet_debug_k1_kernel(int mode) {
+    CUTDET_REQUIRE(mode >= 0 && mode <= 2, "debug_k1_kernel: mode 0 (choose), 1 (one thread per pixel) or 2 (row kernel)");
+    g_k1_kernel = mode;
     return CUTDET_OK;
 }
 

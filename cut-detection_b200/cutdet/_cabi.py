@@ -18,7 +18,7 @@ LIB_OVERRIDE = None      # development aid (bench.py --lib): load this build of 
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ECAPACITY, ELONE_ORPHAN = range(6)
 ABI_VERSION = 2
-NET_OPTIONS = {"conv1_acc32": 1, "sub_batch": 2, "group_frames": 3, "no_pdl": 4, "conv1_grid": 5, "conv1_teams": 6}
+NET_OPTIONS = {"conv1_acc32": 1, "sub_batch": 2, "group_frames": 3, "no_pdl": 4, "conv1_grid": 5, "conv1_variant": 6}
 
 
 class Frames(C.Structure):
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "cutdet_resize_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "cutdet_resize_plan_destroy": (None, [_P]),
     "cutdet_resize_plan_rows": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cutdet_debug_k1_kernel": (C.c_int, [C.c_int]),
     "cutdet_preprocess_f32": (C.c_int, [_P, C.POINTER(Frames), _P, _P]),
     "cutdet_preprocess_u8": (C.c_int, [_P, C.POINTER(Frames), _P, _P]),
     "cutdet_net_create": (C.c_int, [C.POINTER(NetConfig), C.POINTER(_P)]),

@@ -99,6 +99,10 @@ CUTDET_API int cutdet_upload_frames(const cutdet_resize_plan *plan, const uint8_
  * stacked to [B,3,H2,W2] as default_collate does (segment_video.py:29).                                  */
 CUTDET_API int cutdet_preprocess_f32(const cutdet_resize_plan *plan, const cutdet_frames *src, float *out_nchw_dev,
                           cutdet_stream_t stream);
+/* Measurement aid (tools/time_k1.py): which K1 kernel the two entry points below launch.  0 = the library chooses (default),
+ * 1 = the one-thread-per-pixel kernel (any alignment), 2 = the row kernel (128-bit staged rows; 16-byte aligned frames).
+ * Process-wide; the results are bit-identical either way.                                                          */
+CUTDET_API int cutdet_debug_k1_kernel(int mode);
 /* uint8 BGR HWC -> resized uint8 BGR HWC [B,H2,W2,3]: bit-exactly cv2.resize(..., INTER_LINEAR).          */
 CUTDET_API int cutdet_preprocess_u8(const cutdet_resize_plan *plan, const cutdet_frames *src, uint8_t *out_hwc_dev,
                          cutdet_stream_t stream);
@@ -146,8 +150,9 @@ enum {
     CUTDET_OPT_GROUP_FRAMES = 3, /* frames gathered for one conv3 launch (default 0 = 1184)                             */
     CUTDET_OPT_NO_PDL = 4,       /* 1: ordinary launches instead of programmatic dependent launch                       */
     CUTDET_OPT_CONV1_GRID = 5,   /* test hook: cap on the fused conv1 grid (several frames per CTA); 0 = no cap         */
-    CUTDET_OPT_CONV1_TEAMS = 6   /* 1: experiment -- the fused conv1 kernel with an epilogue team and an MMA issuer per block
-                                    row instead of the default one; same arithmetic, same bits, ~3 % slower (kept for A/B) */
+    CUTDET_OPT_CONV1_VARIANT = 6 /* 1: experiment -- the fused conv1 kernel with two alternating epilogue sets and an MMA issuer
+                                    per block row instead of the default one; same arithmetic, same bits, same speed to within
+                                    1 % (profiles/README.md, round 2; kept for same-box A/B runs)                          */
 };
 CUTDET_API int cutdet_net_set_option(cutdet_net *net, int option, int value);
 CUTDET_API int cutdet_net_get_option(const cutdet_net *net, int option, int *value);

@@ -282,10 +282,10 @@ def test_dependent_launch_changes_nothing(prod_weights):
     from cutdet import engine
     wts, params = prod_weights
     nets = {}
-    # conv1_teams: the experimental fused conv1 kernel with an epilogue team and an MMA issuer per block row -- max is exact in fp16,
-    # so it must give the same bits as the default kernel
+    # conv1_variant 1: the experimental fused conv1 kernel with two epilogue sets and an MMA issuer per block row -- max is exact in
+    # fp16, so it must give the same bits as the default kernel
     for name, opts in (("pdl", {}), ("no_pdl", {"no_pdl": 1}), ("sub74", {"sub_batch": 74}), ("sub296", {"sub_batch": 296, "group_frames": 592}),
-                       ("teams", {"conv1_teams": 1}), ("teams_no_pdl", {"conv1_teams": 1, "no_pdl": 1}), ("sets", {"conv1_teams": 2}), ("sets_no_pdl", {"conv1_teams": 2, "no_pdl": 1})):
+                       ("sets", {"conv1_variant": 1}), ("sets_no_pdl", {"conv1_variant": 1, "no_pdl": 1})):
         nets[name] = engine.NativeNet(wts, params["avg_pool_size"])
         for k, v in opts.items():
             nets[name].set_option(k, v)

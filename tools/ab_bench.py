@@ -4,7 +4,7 @@
 Boxes differ by several per cent and the default 80-step run is power-capped (profiles/README.md, v9), so two variants are only
 comparable when they are measured on ONE box, interleaved, a few times each:
 
-    python tools/ab_bench.py --reps 2 --steps 30,80 -- "" "sub_batch=296" "conv1_teams=1" "lib=gpurun_out/libcutdet_old.so"
+    python tools/ab_bench.py --reps 2 --steps 30,80 -- "" "sub_batch=296" "conv1_variant=1" "lib=gpurun_out/libcutdet_old.so"
 
 Each variant is a space-separated list of NAME=VALUE pairs ("" = the defaults): net options (bench.py --net-opt) or
 ``lib=PATH`` (bench.py --lib: another build of libcutdet_b200.so).  Prints one line per run and a summary table

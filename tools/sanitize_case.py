@@ -27,8 +27,8 @@ def main():
     native = net.eval().to("cuda")._native()
     weights, wparams = onet.load_weights_npz(os.path.join(ROOT, "cut-detection_b200", "frameID", "prod_net", "prod_net_weights.npz"))
     rng = np.random.default_rng(0)
-    for teams in (0, 1):
-        native.set_option("conv1_teams", teams)
+    for teams in (0, 1):     # default fused conv1 kernel / the two-epilogue-set experiment
+        native.set_option("conv1_variant", teams)
         for h, w in ((720, 1280), (1080, 1920)):
             frames = rng.integers(0, 256, (frames_per_case, h, w, 3), dtype=np.uint8)
             frames[0, : h // 2] = 255
@@ -40,7 +40,7 @@ def main():
             assert err <= 0.05
             x = engine.preprocess_f32(plan, torch.from_numpy(frames).cuda())
             assert np.array_equal(x.cpu().numpy(), opre.preprocess_batch(frames, 256))
-    native.set_option("conv1_teams", 0)
+    native.set_option("conv1_variant", 0)
     n = 20_011
     lab = np.repeat(rng.integers(0, 3, n // 37 + 2), 37)[:n].astype(np.uint8)
     lab[rng.uniform(size=n) < 0.02] = 2
