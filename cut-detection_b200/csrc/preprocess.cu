@@ -297,7 +297,12 @@ static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *s
     const int row_pad = ((3 * h.src_w + 15) / 16 + 1) * 16;
     const int out_bytes = OUT == 0 ? 3 * h.dst_w * 4 : (3 * h.dst_w + 15) / 16 * 16;
     const size_t smem = (size_t)ROWS_PER_BLOCK * (2 * (size_t)row_pad + out_bytes);
-    if (aligned && smem <= 200 * 1024 && h.dst_h <= 65535 && g_k1_kernel != 1) {
+    // Which kernel (profiles/r02_k1_matrix.txt, B200, frames resident in HBM): the row kernel wins where the output is the small
+    // uint8 image (720p 73.5 % of the HBM peak against 69.2 %, 1080p 92.8 % against 83.9 %, 360p 45.6 against 41.4) except for
+    // very long rows (2160p: 78.8 % against 93.7 %); with the 4 x larger float32 output the one-thread-per-pixel kernel is
+    // ahead (720p 77.6 % against 68.5 %): its coalesced 4-byte plane stores need no second pass through shared memory.
+    const bool choose_rows = g_k1_kernel == 2 || (g_k1_kernel == 0 && OUT == 1 && 3 * h.src_w <= 6144);
+    if (aligned && smem <= 200 * 1024 && h.dst_h <= 65535 && choose_rows) {
         static bool attr_set[2] = {false, false};
         if (smem > 48 * 1024 && !attr_set[OUT]) {
             CUTDET_CUDA(cudaFuncSetAttribute(preprocess_rows_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
