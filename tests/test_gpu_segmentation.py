@@ -302,11 +302,13 @@ def _nccl_worker(rank, world, port, n, seed, out_dir):
         enc = engine.RunLengthEncoder(max(hi - lo, 1), f"cuda:{rank}")
         if hi > lo:
             enc.append(torch.from_numpy(lab[lo:hi]).cuda(), torch.from_numpy(top[lo:hi]).cuda())
-        table, total = shard.stitch_all(enc.finish(), hi - lo, 1024)
-        raw = table.to_te()
-        pipeline.smooth(table, 100, 10)
-        te = table.to_te()
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), total=int(total.item()),
+        local = enc.finish()
+        # 1,024 rows do not hold this shard's ~2,600 runs: the stitch kernel reports it and finish_checked repeats the exchange
+        # (pack, NCCL all-gather, stitch) with a capacity that fits -- on every rank alike, so the collectives stay matched
+        raw, total = shard.finish_checked(lambda cap: shard.stitch_all(local, hi - lo, cap), capacity=1024)
+        te, _ = shard.finish_checked(lambda cap: shard.stitch_all(local, hi - lo, cap), after=lambda t: pipeline.smooth(t, 100, 10),
+                                     capacity=1024)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), total=total,
                  **{"raw_" + k: v.numpy() for k, v in raw.items()}, **{k: v.numpy() for k, v in te.items()})
     finally:
         dist.destroy_process_group()
