@@ -620,10 +620,14 @@ def run_cli_measurement(rig: Rig, frames_host, cpu_path):
     for workers in (1, None):
         csv_path = os.path.join(tmp, f"out_{workers}.csv")
         argv = [path, "--output_path", csv_path, "--print-every", "0"] + (["--decode-workers", str(workers)] if workers else [])
+        ns = sv.sv_parser.parse_args(argv)
+        ns.timings = {}
         t0 = time.perf_counter()
-        sv.main(sv.sv_parser.parse_args(argv))
+        sv.main(ns)
         dt = time.perf_counter() - t0
-        results["sequential_decode" if workers else "default_workers"] = {"frames_per_s": n / dt, "seconds": dt}
+        results["sequential_decode" if workers else "default_workers"] = {
+            "frames_per_s": n / dt, "seconds": dt, "phases_s": {k: round(v, 3) for k, v in ns.timings.items()},
+            "other_s": round(dt - sum(ns.timings.values()), 3)}
         out["csv_" + ("w1" if workers else "default")] = open(csv_path, "rb").read().decode()
     from cutdet import decode
     out["decode_workers_default"] = decode.default_workers()

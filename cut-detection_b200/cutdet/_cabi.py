@@ -74,6 +74,8 @@ _SIGNATURES = {
     "cutdet_net_forward_frames": (C.c_int, [_P, _P, C.POINTER(Frames), _P, _P, C.c_size_t, _P]),
     "cutdet_contrastive_loss_workspace_bytes": (C.c_size_t, [C.c_int]),
     "cutdet_contrastive_loss": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "cutdet_cross_entropy_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "cutdet_cross_entropy_sum": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, _P, _P, C.c_size_t, C.POINTER(C.c_int), _P]),
     "cutdet_net_debug_conv_output": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "cutdet_argmax": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, _P]),
     "cutdet_rle_state_bytes": (C.c_size_t, []),

@@ -460,3 +460,28 @@ def contrastive_loss(x: torch.Tensor, temperature: float = 1.0, h_norm: bool = T
     _cabi.check(lib.cutdet_contrastive_loss(x.data_ptr(), pairs, dim, float(temperature), 1 if h_norm else 0, loss.data_ptr(),
                                             logits_ab.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
     return loss, logits_ab
+
+
+def cross_entropy_sum(logits: torch.Tensor, labels: torch.Tensor, with_counts: bool = False, check_labels: bool = True):
+    """torch.nn.CrossEntropyLoss(reduction="sum")(logits, labels) on the GPU (forward only; reference
+    training_scripts/supervised_training.py:132, 148) and, with ``with_counts``, the validation loop's per-class
+    (correct, total) counters (:188-193).  Returns loss (0-d float32 tensor) or (loss, correct int64 [C], total int64 [C])."""
+    _need_cuda(logits, "logits")
+    _need_cuda(labels, "labels")
+    if logits.dtype != torch.float32 or logits.dim() != 2 or labels.dim() != 1 or labels.shape[0] != logits.shape[0]:
+        raise ValueError(f"logits must be float32 [N, C] and labels [N], got {tuple(logits.shape)} / {tuple(labels.shape)}")
+    logits, labels = logits.contiguous(), labels.to(torch.int64).contiguous()
+    n, c = logits.shape
+    lib = _cabi.lib()
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    correct = torch.empty(c, dtype=torch.int64, device=logits.device) if with_counts else None
+    total = torch.empty(c, dtype=torch.int64, device=logits.device) if with_counts else None
+    ws = torch.empty(lib.cutdet_cross_entropy_workspace_bytes(c) // 8 + 1, dtype=torch.int64, device=logits.device)
+    bad = C.c_int(0)
+    rc = lib.cutdet_cross_entropy_sum(logits.data_ptr(), labels.data_ptr(), n, c, loss.data_ptr(),
+                                      correct.data_ptr() if with_counts else None, total.data_ptr() if with_counts else None,
+                                      ws.data_ptr(), ws.numel() * 8, C.byref(bad) if check_labels else None, _stream())
+    if rc == _cabi.EINVAL and bad.value:
+        raise IndexError("Target out of bounds")          # what torch's cross_entropy raises on the CPU
+    _cabi.check(rc)
+    return (loss, correct, total) if with_counts else loss

@@ -30,3 +30,17 @@ class ContrastiveLoss(nn.Module):
                                f"{2 * self.labels.shape[0]}")
         loss, logits_ab = _engine.contrastive_loss(x, temperature=self.temperature, h_norm=bool(self.h_norm))
         return loss, logits_ab, self.labels
+
+
+class SummedCrossEntropy(nn.Module):
+    """Addition to the reference API: what ``torch.nn.CrossEntropyLoss(reduction="sum")`` computes in the reference's supervised
+    script (training_scripts/supervised_training.py:132, 148, 186) on the native path, forward only.  ``forward(pred, labels)``
+    returns the summed loss; ``accuracy_counts(pred, labels)`` also returns the validation loop's per-class ``(correct, total)``
+    tensors (:188-193), all from one kernel."""
+
+    def forward(self, pred, labels):
+        return _engine.cross_entropy_sum(pred, labels)
+
+    @staticmethod
+    def accuracy_counts(pred, labels):
+        return _engine.cross_entropy_sum(pred, labels, with_counts=True)

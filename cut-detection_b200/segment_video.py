@@ -29,10 +29,20 @@ logging.basicConfig(
 )
 
 
-def score_video(path, net, batch_size, frame_limit=None, print_every=0, decode_workers=None, device="cuda:0"):
+def score_video(path, net, batch_size, frame_limit=None, print_every=0, decode_workers=None, device="cuda:0", timings=None):
     """Decode -> K1 -> CNN -> K4 -> K5 for a whole video: returns (DeviceRunTable of the initial runs, frames scored).
-    What the reference's batch loop plus ``Segmentation.__init__`` compute (segment_video.py:38-62), streamed."""
+    What the reference's batch loop plus ``Segmentation.__init__`` compute (segment_video.py:38-62), streamed.
+    ``timings``: a dict that receives wall-clock seconds per phase (probe, ring + workers, decode/score loop, finish)."""
+    import time
     from cutdet import decode, engine, pipeline
+    t_start = time.perf_counter()
+
+    def lap(name):
+        nonlocal t_start
+        if timings is not None:
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + now - t_start
+            t_start = now
 
     n_meta, h, w = decode.probe_video(path)
     if h == 0:
@@ -49,25 +59,33 @@ def score_video(path, net, batch_size, frame_limit=None, print_every=0, decode_w
         workers = 1
     native = net._native()
     plan = engine.ResizePlan.for_video(h, w, 256)
+    lap("probe_and_plan")
+    # the ring's slots hold at most 32 frames: the workers hand over small chunks (a short clip keeps all of them busy and the
+    # pinned ring stays small: registering it is a fixed cost), the kernels take whatever arrives, the log still counts batches
+    chunk = max(1, min(batch_size, 32))
     for attempt in range(2):
-        pool = decode.DecodePool(path, plan.rows, h, w, batch_size, workers, max(n_frames, 0), to_eof=to_eof)
+        pool = decode.DecodePool(path, plan.rows, h, w, chunk, workers, max(n_frames, 0), to_eof=to_eof, slots_per_worker=3)
         # a run table never has more rows than frames; a range that outgrows this (a container that under-reports its length)
         # is reported as an overflow by the table, not silently truncated
         capacity = max(hi - lo for lo, hi in pool.ranges) + (1 << 16)
-        pipe = pipeline.FramePipeline(native, plan, batch_size, capacity, device, n_ranges=pool.n_workers)
+        pipe = pipeline.FramePipeline(native, plan, chunk, capacity, device, n_ranges=pool.n_workers)
+        lap("ring_and_workers")
         try:
             scored = 0
             for worker, frames, first_frame, slot in pool:
                 uploaded = pipe.push_host(frames, compact=True, rng=worker)
                 pool.release(slot, uploaded)
-                scored += 1
-                if print_every > 0 and scored % print_every == 0:
-                    logging.info(f"Scored batch {scored} ({scored * batch_size} frames).")
+                batches = pipe.n_frames // batch_size
+                if print_every > 0 and batches > scored and batches % print_every == 0:
+                    logging.info(f"Scored batch {batches} ({batches * batch_size} frames).")
+                scored = batches
+            lap("decode_and_score")
             table, total = pipe.finish_ranges()
             try:
                 table.count()
             except engine.ShardOverflow as e:        # a range with more runs than the default join capacity
                 table, total = pipe.finish_ranges(capacity=1 << int(e.needed - 1).bit_length())
+            lap("finish")
             return table, pipe.n_frames
         except decode.SeekMismatch as e:
             if attempt or workers == 1:
@@ -96,7 +114,7 @@ def main(args):
 
     with torch.no_grad():
         table, n_scored = score_video(args.input_path, net, args.batch_size, args.frame_limit, args.print_every,
-                                      getattr(args, "decode_workers", None), device)
+                                      getattr(args, "decode_workers", None), device, getattr(args, "timings", None))
 
         seg = Segmentation.from_table(table)
         logging.info(f"Found {len(seg)} initial segments")

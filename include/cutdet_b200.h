@@ -210,6 +210,20 @@ CUTDET_API int cutdet_contrastive_loss(const float *x_dev, int pairs, int dim, f
                            float *logits_ab_dev, void *workspace_dev, size_t workspace_bytes, cutdet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Supervised objective (forward)    replaces torch.nn.CrossEntropyLoss(reduction="sum") and the per-class accuracy counters
+ *                                   of the validation loop, training_scripts/supervised_training.py:132, 148, 186-193
+ * ------------------------------------------------------------------------------------------------ */
+/* logits [n, n_classes] float32, labels [n] int64 -> *loss_dev = sum_i -log_softmax(logits_i)[label_i] and, if not null,
+ * correct_dev[c] = #{i: label_i = c and argmax(logits_i) = c}, total_dev[c] = #{i: label_i = c} (int64 [n_classes], first-index
+ * argmax as torch.max).  workspace_dev: cutdet_cross_entropy_workspace_bytes(n_classes) bytes, 8-byte aligned.  bad_label_host:
+ * NULL = fully asynchronous (out-of-range labels are skipped); else the call synchronises the stream and returns CUTDET_EINVAL if
+ * a label was outside [0, n_classes) (torch raises "Target out of bounds").  Forward only.                                      */
+CUTDET_API size_t cutdet_cross_entropy_workspace_bytes(int n_classes);
+CUTDET_API int cutdet_cross_entropy_sum(const float *logits_dev, const int64_t *labels_dev, int64_t n, int n_classes, float *loss_dev,
+                             int64_t *correct_dev, int64_t *total_dev, void *workspace_dev, size_t workspace_bytes,
+                             int *bad_label_host, cutdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K4  per-frame decision            replaces torch.max(scores, dim=1), frameID/segmentation.py:37
  * ------------------------------------------------------------------------------------------------ */
 /* scores [N,C] float32 -> top[N] (max logit), labels[N] (first index of the max, as torch does on CPU). */
