@@ -1942,7 +1942,12 @@ uint16_t operand_bits(float f) {      // float -> the 16-bit operand format, rou
 int upload_bytes(cutdet_net *net, const void *host, size_t bytes, void **dev) {
     CUTDET_CUDA(cudaMalloc(dev, bytes));
     net->dev_allocs.push_back(*dev);
+    // A cudaMemcpy from pageable memory may return once the data is STAGED: the DMA then completes on the legacy stream, which
+    // the caller's (non-blocking) stream does not wait for.  Uploads are rare (set-up, or once per input size): drain the device, so
+    // that a kernel launched next on any stream sees the data (found by tests/test_gpu_stress.py: a net whose first forward -- the
+    // lazily folded first FC matrix -- ran on a side stream while another net kept the GPU busy returned wrong logits).
     CUTDET_CUDA(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+    CUTDET_CUDA(cudaDeviceSynchronize());
     return CUTDET_OK;
 }
 

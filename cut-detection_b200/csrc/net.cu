@@ -18,6 +18,7 @@ int upload(cutdet_net *net, const std::vector<float> &h, float **d) {
     CUTDET_CUDA(cudaMalloc(&p, h.size() * sizeof(float)));
     net->dev_allocs.push_back(p);
     CUTDET_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUTDET_CUDA(cudaDeviceSynchronize());        // see upload_bytes (conv_tc.cu): the copy's DMA runs on the legacy stream
     *d = reinterpret_cast<float *>(p);
     return CUTDET_OK;
 }

@@ -389,6 +389,7 @@ extern "C" int cutdet_resize_plan_create(int src_h, int src_w, int dst_h, int ds
     int *hslot = put(slot, src_h);
     cudaError_t e = cudaMalloc(&plan->dev_blob, n_ints * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(plan->dev_blob, blob.data(), n_ints * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();     // the tables may be used at once on a non-blocking stream (see upload_bytes, conv_tc.cu)
     if (e != cudaSuccess) {
         if (plan->dev_blob) cudaFree(plan->dev_blob);
         delete plan;
@@ -417,6 +418,27 @@ extern "C" void cutdet_resize_plan_destroy(cutdet_resize_plan *plan) {
     if (!plan) return;
     if (plan->dev_blob) cudaFree(plan->dev_blob);
     delete plan;
+}
+
+extern "C" int cutdet_resize_rows(int src_h, int src_w, int dst_h, int dst_w, int *rows_host, int *n_rows_out) {
+    CUTDET_REQUIRE(n_rows_out, "resize_rows: null output");
+    CUTDET_REQUIRE(src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "resize_rows: bad geometry %dx%d -> %dx%d", src_w, src_h, dst_w, dst_h);
+    std::vector<char> used(src_h, 0);
+    if ((src_h == dst_h && src_w == dst_w) || (src_w == 2 * dst_w && src_h == 2 * dst_h)) {
+        for (int y = 0; y < src_h; ++y) used[y] = 1;
+    } else {
+        std::vector<int> y0, y1, b0, b1;
+        linear_taps(src_h, dst_h, false, y0, y1, b0, b1);
+        for (int y = 0; y < dst_h; ++y) {
+            used[y0[y]] = 1;
+            if (b1[y] != 0) used[y1[y]] = 1;
+        }
+    }
+    int n = 0;
+    for (int y = 0; y < src_h; ++y)
+        if (used[y]) { if (rows_host) rows_host[n] = y; ++n; }
+    *n_rows_out = n;
+    return CUTDET_OK;
 }
 
 extern "C" int cutdet_resize_plan_rows(const cutdet_resize_plan *plan, int *rows_host, int *n_rows_out) {

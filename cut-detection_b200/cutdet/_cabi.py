@@ -54,6 +54,7 @@ _SIGNATURES = {
     "cutdet_resize_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "cutdet_resize_plan_destroy": (None, [_P]),
     "cutdet_resize_plan_rows": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cutdet_resize_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cutdet_debug_k1_kernel": (C.c_int, [C.c_int]),
     "cutdet_preprocess_f32": (C.c_int, [_P, C.POINTER(Frames), _P, _P]),
     "cutdet_preprocess_u8": (C.c_int, [_P, C.POINTER(Frames), _P, _P]),

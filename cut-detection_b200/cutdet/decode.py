@@ -127,9 +127,9 @@ class DecodePool:
         self._ring_np = np.ndarray(self.ring_shape, dtype=np.uint8, buffer=self._shm.buf)
         self.ring = torch.from_numpy(self._ring_np)
         self._registered = False
-        if pin and torch.cuda.is_available():
-            err = torch.cuda.cudart().cudaHostRegister(self.ring.data_ptr(), nbytes, 0)
-            self._registered = int(err) == 0
+        self._nbytes = nbytes
+        if pin:
+            self.pin()
         # fork: the workers start at once and never touch CUDA or torch (they run _worker_main: numpy + cv2 only), which is what
         # torch's own DataLoader workers rely on; "spawn" re-imports the parent's __main__ (and torch with it) in every worker
         if start_method is None:
@@ -156,6 +156,14 @@ class DecodePool:
         self._first_crc = [None] * n_workers
         self._tail_crc = [None] * n_workers
         self._closed = False
+
+    def pin(self) -> None:
+        """Register the ring as pinned memory (once).  ``DecodePool(..., pin=False)`` + ``pin()`` later lets the workers be
+        forked BEFORE the process creates its CUDA context: forking a process that holds one costs ~70 ms per worker."""
+        import torch
+        if not self._registered and torch.cuda.is_available():
+            err = torch.cuda.cudart().cudaHostRegister(self.ring.data_ptr(), self._nbytes, 0)
+            self._registered = int(err) == 0
 
     # ------------------------------------------------------------------ slots
     def release(self, slot: int, event=None) -> None:

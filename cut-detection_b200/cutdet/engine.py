@@ -37,6 +37,17 @@ def target_size(width: int, height: int, resize: int = 256) -> tuple[int, int]:
     return nw.value, nh.value
 
 
+def resize_rows(height: int, width: int, resize: int = 256) -> np.ndarray:
+    """Source rows the resize of a height x width frame reads (what ``ResizePlan.for_video(...).rows`` lists), computed on the
+    host without any CUDA call: a frame source can start gathering rows before the process has a CUDA context."""
+    nw, nh = target_size(width, height, resize)
+    n = C.c_int()
+    _cabi.check(_cabi.lib().cutdet_resize_rows(height, width, nh, nw, None, C.byref(n)))
+    rows = (C.c_int * max(n.value, 1))()
+    _cabi.check(_cabi.lib().cutdet_resize_rows(height, width, nh, nw, rows, C.byref(n)))
+    return np.frombuffer(rows, dtype=np.int32)[:n.value].copy()
+
+
 # ----------------------------------------------------------------------------------------------- K1
 class ResizePlan:
     """Tap tables of one cv2.resize(INTER_LINEAR) geometry, resident on the current device."""

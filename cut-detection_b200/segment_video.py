@@ -17,6 +17,7 @@ from frameID.net import load_default_net
 from frameID.data import open_video
 from frameID.segmentation import Segmentation
 
+import numpy as np
 import torch
 
 import argparse
@@ -29,21 +30,13 @@ logging.basicConfig(
 )
 
 
-def score_video(path, net, batch_size, frame_limit=None, print_every=0, decode_workers=None, device="cuda:0", timings=None):
-    """Decode -> K1 -> CNN -> K4 -> K5 for a whole video: returns (DeviceRunTable of the initial runs, frames scored).
-    What the reference's batch loop plus ``Segmentation.__init__`` compute (segment_video.py:38-62), streamed.
-    ``timings``: a dict that receives wall-clock seconds per phase (probe, ring + workers, decode/score loop, finish)."""
+def open_decode(path, batch_size, frame_limit=None, decode_workers=None, timings=None):
+    """Start the decoder processes on their time ranges of the video.  No CUDA call is made here on purpose: call it BEFORE the
+    process creates its CUDA context (forking a process that holds one costs ~70 ms per worker).  Returns the state
+    ``score_video`` consumes."""
     import time
-    from cutdet import decode, engine, pipeline
-    t_start = time.perf_counter()
-
-    def lap(name):
-        nonlocal t_start
-        if timings is not None:
-            now = time.perf_counter()
-            timings[name] = timings.get(name, 0.0) + now - t_start
-            t_start = now
-
+    from cutdet import decode, engine
+    t0 = time.perf_counter()
     n_meta, h, w = decode.probe_video(path)
     if h == 0:
         raise IndexError("the video has no decodable frame")          # what Segmentation(empty scores) ends in
@@ -57,20 +50,46 @@ def score_video(path, net, batch_size, frame_limit=None, print_every=0, decode_w
     workers = decode.default_workers() if decode_workers is None else max(1, int(decode_workers))
     if n_frames <= 0:
         workers = 1
-    native = net._native()
-    plan = engine.ResizePlan.for_video(h, w, 256)
-    lap("probe_and_plan")
     # the ring's slots hold at most 32 frames: the workers hand over small chunks (a short clip keeps all of them busy and the
     # pinned ring stays small: registering it is a fixed cost), the kernels take whatever arrives, the log still counts batches
     chunk = max(1, min(batch_size, 32))
+    rows = engine.resize_rows(h, w, 256)
+    pool = decode.DecodePool(path, rows, h, w, chunk, workers, max(n_frames, 0), to_eof=to_eof, slots_per_worker=3, pin=False)
+    if timings is not None:
+        timings["probe_and_workers"] = time.perf_counter() - t0
+    return {"path": path, "pool": pool, "h": h, "w": w, "chunk": chunk, "rows": rows, "n_frames": n_frames, "to_eof": to_eof,
+            "batch_size": batch_size, "workers": workers}
+
+
+def score_video(dec, net, print_every=0, device="cuda:0", timings=None):
+    """Decode -> K1 -> CNN -> K4 -> K5 for a whole video: returns (DeviceRunTable of the initial runs, frames scored).
+    What the reference's batch loop plus ``Segmentation.__init__`` compute (segment_video.py:38-62), streamed.
+    ``dec``: the state ``open_decode`` returned.  ``timings``: a dict that receives wall-clock seconds per phase."""
+    import time
+    from cutdet import decode, engine, pipeline
+    t_start = time.perf_counter()
+
+    def lap(name):
+        nonlocal t_start
+        if timings is not None:
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + now - t_start
+            t_start = now
+
+    h, w, chunk, batch_size = dec["h"], dec["w"], dec["chunk"], dec["batch_size"]
+    native = net._native()
+    plan = engine.ResizePlan.for_video(h, w, 256)
+    assert np.array_equal(plan.rows, dec["rows"])
+    pool = dec["pool"]
     for attempt in range(2):
-        pool = decode.DecodePool(path, plan.rows, h, w, chunk, workers, max(n_frames, 0), to_eof=to_eof, slots_per_worker=3)
-        # a run table never has more rows than frames; a range that outgrows this (a container that under-reports its length)
-        # is reported as an overflow by the table, not silently truncated
-        capacity = max(hi - lo for lo, hi in pool.ranges) + (1 << 16)
-        pipe = pipeline.FramePipeline(native, plan, chunk, capacity, device, n_ranges=pool.n_workers)
-        lap("ring_and_workers")
+        retry = None
         try:
+            pool.pin()
+            # a run table never has more rows than frames; a range that outgrows this (a container that under-reports its
+            # length) is reported as an overflow by the table, not silently truncated
+            capacity = max(hi - lo for lo, hi in pool.ranges) + (1 << 16)
+            pipe = pipeline.FramePipeline(native, plan, chunk, capacity, device, n_ranges=pool.n_workers)
+            lap("plan_ring_pipeline")
             scored = 0
             for worker, frames, first_frame, slot in pool:
                 uploaded = pipe.push_host(frames, compact=True, rng=worker)
@@ -88,13 +107,15 @@ def score_video(path, net, batch_size, frame_limit=None, print_every=0, decode_w
             lap("finish")
             return table, pipe.n_frames
         except decode.SeekMismatch as e:
-            if attempt or workers == 1:
+            if attempt or pool.n_workers == 1:
                 raise
-            logging.warning(f"{e}; decoding sequentially instead")
-            workers = 1
+            retry = e
         finally:
             torch.cuda.synchronize()
             pool.close()
+        logging.warning(f"{retry}; decoding sequentially instead")
+        pool = decode.DecodePool(dec["path"], dec["rows"], h, w, chunk, 1, max(dec["n_frames"], 0), to_eof=dec["to_eof"],
+                                 slots_per_worker=3, pin=False)
 
 
 def main(args):
@@ -107,14 +128,17 @@ def main(args):
     device = "cuda:0"
     logging.info(f"Using {device}")
 
+    # the decoder processes are forked first, while this process has no CUDA context yet
+    dec = open_decode(args.input_path, args.batch_size, args.frame_limit, getattr(args, "decode_workers", None),
+                      getattr(args, "timings", None))
+
     net, params = load_default_net()
     net.eval()
     net.to(device)
     logging.info("Loaded default classifier.")
 
     with torch.no_grad():
-        table, n_scored = score_video(args.input_path, net, args.batch_size, args.frame_limit, args.print_every,
-                                      getattr(args, "decode_workers", None), device, getattr(args, "timings", None))
+        table, n_scored = score_video(dec, net, args.print_every, device, getattr(args, "timings", None))
 
         seg = Segmentation.from_table(table)
         logging.info(f"Found {len(seg)} initial segments")

@@ -76,6 +76,10 @@ CUTDET_API void cutdet_resize_plan_destroy(cutdet_resize_plan *plan);
 /* Source rows the resize actually reads (sorted, unique).  n_rows_out receives the count; rows_host may
  * be NULL to query it.  A host-side caller can copy just these rows to the device (row-compacted frames). */
 CUTDET_API int cutdet_resize_plan_rows(const cutdet_resize_plan *plan, int *rows_host, int *n_rows_out);
+/* The same list from the geometry alone: pure host arithmetic, no CUDA call (a frame source can start gathering rows --
+ * e.g. fork its decoder processes -- before the process has a CUDA context).  rows_host may be NULL to query the count
+ * (at most src_h).                                                                                                   */
+CUTDET_API int cutdet_resize_rows(int src_h, int src_w, int dst_h, int dst_w, int *rows_host, int *n_rows_out);
 
 /* Layout of a batch of source frames in device memory.  `row_map_compact` != 0 says the buffer holds only
  * the rows listed by cutdet_resize_plan_rows(), in that order (row r of the list at row_pitch * r).      */

@@ -89,3 +89,21 @@ def test_stale_library_is_not_loaded(tmp_path):
         os.path.join(ROOT, "cut-detection_b200"), str(tmp_path / "no_stamp.txt"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert "RAISED" in out.stdout and "older than the sources" in out.stdout
+
+
+@pytest.mark.parametrize("h,w", [(720, 1280), (1080, 1920), (360, 640), (288, 512), (2160, 3840), (256, 455), (144, 256),
+                                 (480, 854), (1080, 1440), (601, 333)])
+def test_host_only_row_list_equals_the_oracle_taps(h, w):
+    """cutdet_resize_rows is arithmetic on the host (the CLI calls it before the process has a CUDA context): the rows it
+    names are the vertical taps with a non-zero weight of the oracle's coefficient table."""
+    import numpy as np
+    from cutdet import engine
+    from oracle import preprocess as opre
+    nw, nh = opre.target_size(w, h, 256)
+    rows = engine.resize_rows(h, w, 256)
+    if (nh, nw) == (h, w) or (2 * nh, 2 * nw) == (h, w):
+        want = np.arange(h)
+    else:
+        i0, i1, w0, w1 = opre.linear_coeffs(h, nh, clamp_weights=False)
+        want = np.unique(np.concatenate([i0, i1[w1 != 0]]))
+    assert np.array_equal(rows, want)
