@@ -35,6 +35,7 @@ import hashlib
 import json
 import os
 import statistics
+import subprocess
 import sys
 import tempfile
 import time
@@ -615,19 +616,25 @@ def run_cli_measurement(rig: Rig, frames_host, cpu_path):
     for f in frames_host:
         vw.write(f)
     vw.release()
-    out = {"video": f"{n} frames 720p mp4v written with cv2.VideoWriter", "video_bytes": os.path.getsize(path)}
+    out = {"video": f"{n} frames 720p mp4v written with cv2.VideoWriter", "video_bytes": os.path.getsize(path),
+           "timed": "segment_video.main() in a fresh process (tools/cli_timing.py), from after the imports to the CSV on disk: "
+                    "CUDA context, weights, decoder forks, ring pinning, decode, kernels, smoothing, CSV; process_wall_s adds "
+                    "the interpreter and `import torch`, which the reference's CLI pays too"}
     results = {}
+    # each run in a fresh process, as a user's is: this process already holds a CUDA context, which would hide what the CLI pays
+    # once (context, forks, pinning) and make every fork slower than it is for a user
     for workers in (1, None):
         csv_path = os.path.join(tmp, f"out_{workers}.csv")
-        argv = [path, "--output_path", csv_path, "--print-every", "0"] + (["--decode-workers", str(workers)] if workers else [])
-        ns = sv.sv_parser.parse_args(argv)
-        ns.timings = {}
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "cli_timing.py"), path, csv_path] + ([str(workers)] if workers else [])
         t0 = time.perf_counter()
-        sv.main(ns)
-        dt = time.perf_counter() - t0
+        proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        wall = time.perf_counter() - t0
+        if proc.returncode != 0:
+            raise RuntimeError(f"the CLI failed: {proc.stderr[-2000:]}")
+        r = json.loads(proc.stdout.strip().splitlines()[-1])
         results["sequential_decode" if workers else "default_workers"] = {
-            "frames_per_s": n / dt, "seconds": dt, "phases_s": {k: round(v, 3) for k, v in ns.timings.items()},
-            "other_s": round(dt - sum(ns.timings.values()), 3)}
+            "frames_per_s": n / r["seconds"], "seconds": r["seconds"], "phases_s": r["phases_s"], "other_s": r["other_s"],
+            "process_wall_s": round(wall, 3), "python_and_torch_import_s": r["import_s"]}
         out["csv_" + ("w1" if workers else "default")] = open(csv_path, "rb").read().decode()
     from cutdet import decode
     out["decode_workers_default"] = decode.default_workers()

@@ -49,8 +49,12 @@ def _crc(a: np.ndarray) -> int:
     return zlib.crc32(memoryview(np.ascontiguousarray(a))) & 0xFFFFFFFF
 
 
-def _worker_main(worker: int, path: str, shm_name: str, ring_shape: tuple, my_slots: list, lo: int, hi: int, to_eof: bool,
-                 rows: np.ndarray, check_next: bool, free_q, ready_q):
+def _slot_view(buf, slot: int, slot_stride: int, slot_shape: tuple) -> np.ndarray:
+    return np.ndarray(slot_shape, dtype=np.uint8, buffer=buf, offset=slot * slot_stride)
+
+
+def _worker_main(worker: int, path: str, shm_name: str, slot_shape: tuple, slot_stride: int, my_slots: list, lo: int, hi: int,
+                 to_eof: bool, rows: np.ndarray, check_next: bool, free_q, ready_q):
     """Decode frames [lo, hi) (or to the end of the file when ``to_eof``) into this worker's ring slots.
     Messages to the parent: ("chunk", worker, slot, n_frames, first_frame, crc_of_first_frame_or_None),
     ("done", worker, frames_decoded, crc_of_frame_hi_or_None), ("error", worker, text)."""
@@ -63,12 +67,13 @@ def _worker_main(worker: int, path: str, shm_name: str, ring_shape: tuple, my_sl
         if lo > 0:
             cap.set(cv2.CAP_PROP_POS_FRAMES, lo)
         shm = shared_memory.SharedMemory(name=shm_name)
-        ring = np.ndarray(ring_shape, dtype=np.uint8, buffer=shm.buf)
-        chunk = ring_shape[1]
+        ring = {s: _slot_view(shm.buf, s, slot_stride, slot_shape) for s in my_slots}
+        chunk = slot_shape[0]
         done, eof, first = 0, False, True
         while not eof and (to_eof or lo + done < hi):
             slot = free_q.get()
             if slot is None:                    # the parent is shutting down
+                ring = view = None
                 return
             view, k, crc = ring[slot], 0, None
             while k < chunk and (to_eof or lo + done < hi):
@@ -91,6 +96,7 @@ def _worker_main(worker: int, path: str, shm_name: str, ring_shape: tuple, my_sl
             if ret:
                 tail = _crc(frame[rows])
         cap.release()
+        ring = view = None                      # no exported buffers left when the mapping is closed
         ready_q.put(("done", worker, done, tail))
     except Exception as e:      # pragma: no cover  (reported to the parent, which raises)
         ready_q.put(("error", worker, repr(e)))
@@ -101,7 +107,7 @@ def _worker_main(worker: int, path: str, shm_name: str, ring_shape: tuple, my_sl
 
 class DecodePool:
     """Iterate over decoded chunks: ``for worker, frames, first_frame, slot in pool`` where ``frames`` is a pinned uint8 torch
-    tensor view [n, len(rows), w, 3] of the ring (row-compacted BGR frames in decode order within the worker's range).  Call
+    tensor view [n, len(rows), w, 3] of one ring slot (row-compacted BGR frames in decode order within the worker's range).  Call
     ``pool.release(slot, event)`` once the frames have been queued for upload: the slot goes back to its worker when the CUDA
     event has completed.  ``pool.ranges`` lists each worker's [lo, hi); ``pool.frames_decoded`` the true counts afterwards."""
 
@@ -121,15 +127,14 @@ class DecodePool:
             self.ranges.append((lo, hi))
         self.to_eof = bool(to_eof)
         n_slots = n_workers * slots_per_worker
-        self.ring_shape = (n_slots, self.chunk, len(self.rows), src_w, 3)
-        nbytes = int(np.prod(self.ring_shape))
-        self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
-        self._ring_np = np.ndarray(self.ring_shape, dtype=np.uint8, buffer=self._shm.buf)
-        self.ring = torch.from_numpy(self._ring_np)
-        self._registered = False
-        self._nbytes = nbytes
-        if pin:
-            self.pin()
+        self.slot_shape = (self.chunk, len(self.rows), src_w, 3)
+        self.slot_bytes = int(np.prod(self.slot_shape))
+        self.slot_stride = -(-self.slot_bytes // 4096) * 4096        # every slot starts on a page: slots are pinned one by one
+        self._shm = shared_memory.SharedMemory(create=True, size=n_slots * self.slot_stride)
+        self._slots_np = [_slot_view(self._shm.buf, s, self.slot_stride, self.slot_shape) for s in range(n_slots)]
+        self.slots = [torch.from_numpy(a) for a in self._slots_np]
+        self._registered = set()
+        self._pin = bool(pin)
         # fork: the workers start at once and never touch CUDA or torch (they run _worker_main: numpy + cv2 only), which is what
         # torch's own DataLoader workers rely on; "spawn" re-imports the parent's __main__ (and torch with it) in every worker
         if start_method is None:
@@ -148,8 +153,8 @@ class DecodePool:
             lo, hi = self.ranges[w]
             last = w == n_workers - 1
             p = ctx.Process(target=_worker_main, daemon=True,
-                            args=(w, path, self._shm.name, self.ring_shape, slots, lo, hi, self.to_eof and last, self.rows,
-                                  not last, self._free[w], self._ready))
+                            args=(w, path, self._shm.name, self.slot_shape, self.slot_stride, slots, lo, hi,
+                                  self.to_eof and last, self.rows, not last, self._free[w], self._ready))
             p.start()
             self._procs.append(p)
         self.frames_decoded = [0] * n_workers
@@ -158,12 +163,18 @@ class DecodePool:
         self._closed = False
 
     def pin(self) -> None:
-        """Register the ring as pinned memory (once).  ``DecodePool(..., pin=False)`` + ``pin()`` later lets the workers be
-        forked BEFORE the process creates its CUDA context: forking a process that holds one costs ~70 ms per worker."""
+        """Pin the ring from now on.  A slot is registered as pinned memory the first time a worker hands it over (its pages
+        exist by then, and the other workers keep decoding meanwhile) instead of the whole ring up front, which costs ~0.3 s for
+        a 400 MB ring before the first frame is scored.  ``DecodePool(..., pin=False)`` + ``pin()`` later lets the workers be
+        forked BEFORE the process creates its CUDA context: forking a process that holds one is several times slower."""
+        self._pin = True
+
+    def _register(self, slot: int) -> None:
         import torch
-        if not self._registered and torch.cuda.is_available():
-            err = torch.cuda.cudart().cudaHostRegister(self.ring.data_ptr(), self._nbytes, 0)
-            self._registered = int(err) == 0
+        if self._pin and slot not in self._registered and torch.cuda.is_available():
+            err = torch.cuda.cudart().cudaHostRegister(self.slots[slot].data_ptr(), self.slot_bytes, 0)
+            if int(err) == 0:
+                self._registered.add(slot)
 
     # ------------------------------------------------------------------ slots
     def release(self, slot: int, event=None) -> None:
@@ -210,7 +221,8 @@ class DecodePool:
             _, w, slot, k, first_frame, crc = msg
             if crc is not None:
                 self._first_crc[w] = crc
-            yield w, self.ring[slot, :k], first_frame, slot
+            self._register(slot)
+            yield w, self.slots[slot][:k], first_frame, slot
         self._check_seams()
 
     def _check_seams(self) -> None:
@@ -240,9 +252,11 @@ class DecodePool:
         import torch
         if self._registered:
             torch.cuda.synchronize()
-            torch.cuda.cudart().cudaHostUnregister(self.ring.data_ptr())
-        self.ring = None
-        self._ring_np = None
+            for slot in sorted(self._registered):
+                torch.cuda.cudart().cudaHostUnregister(self.slots[slot].data_ptr())
+            self._registered.clear()
+        self.slots = None
+        self._slots_np = None
         try:
             self._shm.close()
             self._shm.unlink()
