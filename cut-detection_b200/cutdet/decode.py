@@ -29,6 +29,15 @@ from multiprocessing import shared_memory
 import numpy as np
 
 
+# Scheduling of the decoder processes (module defaults; DecodePool's arguments override them).  The parent needs the CPU in
+# bursts -- creating the CUDA context while the workers already decode, then one short push per chunk -- and ffmpeg starts one
+# decoding thread per core in EVERY worker, so W workers oversubscribe the box W times and the parent's bursts stretch (measured:
+# context + weights 0.9 s alone, 2.6 s next to 8 such workers).  The workers therefore run at a lower priority, and each gets
+# its share of the cores as ffmpeg threads.
+WORKER_NICE = 10
+DECODER_THREADS = "auto"          # "auto": max(1, cores // workers); an int; or None for ffmpeg's default (one per core)
+
+
 class SeekMismatch(RuntimeError):
     """The first frame a worker decoded after its seek is not the frame that follows the previous worker's range."""
 
@@ -54,12 +63,19 @@ def _slot_view(buf, slot: int, slot_stride: int, slot_shape: tuple) -> np.ndarra
 
 
 def _worker_main(worker: int, path: str, shm_name: str, slot_shape: tuple, slot_stride: int, my_slots: list, lo: int, hi: int,
-                 to_eof: bool, rows: np.ndarray, check_next: bool, free_q, ready_q):
+                 to_eof: bool, rows: np.ndarray, check_next: bool, free_q, ready_q, nice: int = 0, threads=None):
     """Decode frames [lo, hi) (or to the end of the file when ``to_eof``) into this worker's ring slots.
     Messages to the parent: ("chunk", worker, slot, n_frames, first_frame, crc_of_first_frame_or_None),
     ("done", worker, frames_decoded, crc_of_frame_hi_or_None), ("error", worker, text)."""
     shm = None
     try:
+        if nice:
+            try:
+                os.nice(int(nice))
+            except OSError:
+                pass
+        if threads:                             # read by OpenCV's ffmpeg backend when the capture is opened
+            os.environ["OPENCV_FFMPEG_CAPTURE_OPTIONS"] = f"threads;{int(threads)}"
         import cv2
         cap = cv2.VideoCapture(path)
         if not cap.isOpened():
@@ -112,7 +128,8 @@ class DecodePool:
     event has completed.  ``pool.ranges`` lists each worker's [lo, hi); ``pool.frames_decoded`` the true counts afterwards."""
 
     def __init__(self, path: str, rows: np.ndarray, src_h: int, src_w: int, chunk: int, n_workers: int, n_frames: int,
-                 to_eof: bool = True, slots_per_worker: int = 2, pin: bool = True, start_method: str | None = None):
+                 to_eof: bool = True, slots_per_worker: int = 2, pin: bool = True, start_method: str | None = None,
+                 worker_nice: int | None = None, decoder_threads="default"):
         import torch
         self.path, self.chunk = path, int(chunk)
         self.rows = np.ascontiguousarray(rows, dtype=np.int64)
@@ -140,6 +157,10 @@ class DecodePool:
         if start_method is None:
             start_method = "fork" if "fork" in mp.get_all_start_methods() else "spawn"
         ctx = mp.get_context(start_method)
+        nice = WORKER_NICE if worker_nice is None else int(worker_nice)
+        threads = DECODER_THREADS if decoder_threads == "default" else decoder_threads
+        if threads == "auto":
+            threads = max(1, (os.cpu_count() or 1) // n_workers) if n_workers > 1 else None
         self._ready = ctx.Queue()
         self._free = [ctx.Queue() for _ in range(n_workers)]
         self._procs = []
@@ -154,7 +175,7 @@ class DecodePool:
             last = w == n_workers - 1
             p = ctx.Process(target=_worker_main, daemon=True,
                             args=(w, path, self._shm.name, self.slot_shape, self.slot_stride, slots, lo, hi,
-                                  self.to_eof and last, self.rows, not last, self._free[w], self._ready))
+                                  self.to_eof and last, self.rows, not last, self._free[w], self._ready, nice, threads))
             p.start()
             self._procs.append(p)
         self.frames_decoded = [0] * n_workers

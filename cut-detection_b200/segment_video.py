@@ -113,6 +113,7 @@ def score_video(dec, net, print_every=0, device="cuda:0", timings=None):
         finally:
             torch.cuda.synchronize()
             pool.close()
+            lap("teardown")
         logging.warning(f"{retry}; decoding sequentially instead")
         pool = decode.DecodePool(dec["path"], dec["rows"], h, w, chunk, 1, max(dec["n_frames"], 0), to_eof=dec["to_eof"],
                                  slots_per_worker=3, pin=False)
@@ -123,23 +124,36 @@ def main(args):
     if not os.path.isfile(args.input_path):
         raise ValueError(f"{args.input_path} does not exist.")
 
-    if args.cpu or not torch.cuda.is_available():
+    if args.cpu:
         raise RuntimeError("this build runs on a CUDA device (sm_100a) only; there is no CPU path")
     device = "cuda:0"
+
+    # the decoder processes are forked first, before this process has touched the CUDA driver at all (not even the device
+    # query below): they inherit nothing of it, and they decode while the context is created
+    import time
+    timings = getattr(args, "timings", None)
+    dec = open_decode(args.input_path, args.batch_size, args.frame_limit, getattr(args, "decode_workers", None), timings)
+
+    t0 = time.perf_counter()
+    if not torch.cuda.is_available():
+        dec["pool"].close()
+        raise RuntimeError("this build runs on a CUDA device (sm_100a) only; there is no CPU path")
     logging.info(f"Using {device}")
-
-    # the decoder processes are forked first, while this process has no CUDA context yet
-    dec = open_decode(args.input_path, args.batch_size, args.frame_limit, getattr(args, "decode_workers", None),
-                      getattr(args, "timings", None))
-
+    if timings is not None:
+        timings["driver_init"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     net, params = load_default_net()
     net.eval()
     net.to(device)
+    net._native()                       # CUDA context, library load and weight upload happen here, while the workers decode
     logging.info("Loaded default classifier.")
+    if timings is not None:
+        timings["context_and_weights"] = time.perf_counter() - t0
 
     with torch.no_grad():
-        table, n_scored = score_video(dec, net, args.print_every, device, getattr(args, "timings", None))
+        table, n_scored = score_video(dec, net, args.print_every, device, timings)
 
+        t0 = time.perf_counter()
         seg = Segmentation.from_table(table)
         logging.info(f"Found {len(seg)} initial segments")
         seg.glue_orphans(args.base_threshold, args.blank_threshold)
@@ -154,6 +168,8 @@ def main(args):
 
         logging.info(f"Writing {len(seg)} segments to {out_path}")
         seg.write_csv(out_path)
+        if timings is not None:
+            timings["smooth_and_csv"] = time.perf_counter() - t0
 
 
 sv_parser = argparse.ArgumentParser("Segment a video into scenes.", fromfile_prefix_chars="@")

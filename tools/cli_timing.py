@@ -2,7 +2,7 @@
 bench.py's ``cli`` leg calls it as a subprocess: a process that already holds a CUDA context (bench.py itself) would hide what
 a user's run pays once -- context creation, forking the decoders, pinning the ring -- and overstate the cost of the forks.
 
-    python tools/cli_timing.py VIDEO OUT.csv [decode_workers]
+    python tools/cli_timing.py VIDEO OUT.csv [decode_workers|- [worker_nice [decoder_threads|auto|none]]]
 """
 import json
 import os
@@ -18,8 +18,13 @@ def main():
     import segment_video as sv          # imports torch
     t_imported = time.perf_counter()
     argv = [sys.argv[1], "--output_path", sys.argv[2], "--print-every", "0"]
-    if len(sys.argv) > 3:
+    if len(sys.argv) > 3 and sys.argv[3] != "-":
         argv += ["--decode-workers", sys.argv[3]]
+    if len(sys.argv) > 4:                                   # scheduling experiments (cutdet.decode's module defaults)
+        from cutdet import decode
+        decode.WORKER_NICE = int(sys.argv[4])
+        if len(sys.argv) > 5:
+            decode.DECODER_THREADS = {"auto": "auto", "none": None}.get(sys.argv[5], sys.argv[5])
     ns = sv.sv_parser.parse_args(argv)
     ns.timings = {}
     t0 = time.perf_counter()
