@@ -560,6 +560,9 @@ def kernel_table(kernels: dict, prof_steps: int, chunk: int, k1_src_bytes: int):
         # K1 fused into conv1: reads the source rows a frame needs (552,960 B at 720p), writes nothing to HBM by design (its
         # output stays in L2 for conv2); HBM time floor 0.086 us/frame > tensor floor 0.068 us/frame, so it is HBM-bound.
         "conv1_fused_tc": ("hbm", k1_src_bytes),
+        # K1 + layer 1 + layer 2 of a frame by one CTA: the tensor time floor (264.8 MFLOP at the sustained peak: 0.19 us/frame) is
+        # above the HBM floor of the source rows (0.086 us/frame), so it is tensor-bound; the HBM side is reported beside it
+        "conv12_frames": ("tensor", FLOPS["L0"] + FLOPS["L1"]),
         "conv_block_generic_L1": ("tensor", FLOPS["L1"]), "conv_block_generic_L2": ("tensor", FLOPS["L2"]),
         "conv1_tc": ("tensor", FLOPS["L0"]), "conv2_tc": ("tensor", FLOPS["L1"]), "conv3_tc": ("tensor", FLOPS["L2"]),
     }
@@ -579,6 +582,9 @@ def kernel_table(kernels: dict, prof_steps: int, chunk: int, k1_src_bytes: int):
             else:
                 row.update(bound="tensor", achieved=units / (avg_ms * 1e-3) / 1e12, unit="TFLOP/s", peak=peaks["tflops_sustained"])
             row["frac"] = row["achieved"] / row["peak"]
+            if key == "conv12_frames":           # the same launch also streams the source rows from HBM
+                row["hbm_gbs"] = k1_src_bytes * frames_per_launch / (avg_ms * 1e-3) / 1e9
+                row["hbm_frac_of_peak"] = row["hbm_gbs"] / peaks["hbm_gbs"]
             if key == "conv1_fused_tc":          # the same launch is also layer 1's MMAs
                 row["tensor_tflops"] = FLOPS["L0"] * frames_per_launch / (avg_ms * 1e-3) / 1e12
                 row["tensor_frac_of_sustained"] = row["tensor_tflops"] / peaks["tflops_sustained"]

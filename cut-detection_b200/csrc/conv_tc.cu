@@ -95,20 +95,22 @@ struct Geom {
     size_t xin_frame, act3_frame;       // bytes per frame
 };
 
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 Geom make_geom(int H, int W, int C) {
     Geom g;
     g.H = H; g.W = W; g.C = C; g.CG = C / 8;
     g.P1h = H / 3; g.P1w = W / 3;
     g.P2h = g.P1h / 3; g.P2w = g.P1w / 3;
     g.P3h = g.P2h / 3; g.P3w = g.P2w / 3;
-    g.Q1h = g.P1h / 3 + 1; g.PW1 = g.P1w / 3 + 1; g.FP1 = g.Q1h * g.PW1;
+    // layer 1's frames start on a tile boundary of layer 2's GEMM rows (128 positions): a frame is then a whole number of tiles, which
+    // is what lets one CTA run both layers of a frame back to back (conv12_frames_kernel); the rows past Q1h * PW1 are zero padding
+    g.Q1h = g.P1h / 3 + 1; g.PW1 = g.P1w / 3 + 1; g.FP1 = (int)align_up((size_t)g.Q1h * g.PW1, 128);
     g.Q2h = g.P2h / 3 + 1; g.PW2 = g.P2w / 3 + 1; g.FP2 = g.Q2h * g.PW2;
     g.xin_frame = (size_t)H * g.P1w * 32;
     g.act3_frame = (size_t)g.P3h * g.P3w * C * sizeof(float);
     return g;
 }
-
-size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // positions per (plane, channel group) of a phase-split buffer holding `frames` frames (TMA rows are 32 positions)
 int gtot_for(int frames, int FP) { return (int)align_up((size_t)frames * FP, 32); }
@@ -418,10 +420,11 @@ __device__ __forceinline__ void store_pixel16(uint4 *dst, int gtot, const uint32
 }
 
 // Zero the entries of frames [f_lo, f_hi) of a phase-split buffer that are not real pixels (the last row and/or the
-// last column of each plane): they are the zero padding the next conv's shifted views read.
+// last column of each plane, and the positions between the last row and the frame pitch): they are the zero padding the next
+// conv's shifted views read.
 __device__ __forceinline__ void zero_pads(const OutSpec &o, int CG, int f_lo, int f_hi, int tid, int nthreads) {
     if (o.mode != 0) return;
-    const int span = o.PW + o.QH, per_frame = 9 * CG * span;
+    const int gap = o.FP - o.QH * o.PW, span = o.PW + o.QH + gap, per_frame = 9 * CG * span;
     const long long total = (long long)(f_hi - f_lo) * per_frame;
     uint4 *dst = reinterpret_cast<uint4 *>(o.ptr);
     for (long long i = tid; i < total; i += nthreads) {
@@ -431,7 +434,8 @@ __device__ __forceinline__ void zero_pads(const OutSpec &o, int CG, int f_lo, in
         int Yq, Xq;
         bool pad;
         if (e < o.PW) { Yq = o.QH - 1; Xq = e; pad = 3 * Yq + py >= o.out_h; }
-        else { Yq = e - o.PW; Xq = o.PW - 1; pad = 3 * Xq + px >= o.out_w; }
+        else if (e < o.PW + o.QH) { Yq = e - o.PW; Xq = o.PW - 1; pad = 3 * Xq + px >= o.out_w; }
+        else { Yq = o.QH; Xq = e - o.PW - o.QH; pad = true; }          // position QH * PW + Xq, up to the frame pitch
         if (pad) dst[(size_t)pc * o.gtot + (size_t)(o.frame0 + f) * o.FP + Yq * o.PW + Xq] = make_uint4(0, 0, 0, 0);
     }
 }
@@ -1568,6 +1572,420 @@ __global__ void __launch_bounds__(S2Roles::THREADS, 1) conv1_fused_sets_kernel(c
     if (warp == RL::MMA_WARP0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------ K1 + layer 1 + layer 2, frame by frame
+// One persistent CTA per SM takes a frame through BOTH layers before it starts the next one: the fused K1 + layer-1 pipeline of
+// conv1_fused_tc_kernel (fp16 accumulators) writes the frame's pooled map into this CTA's slot of the phase-split buffer, then the
+// same CTA runs layer 2's tiles of that slot (conv_mid_tc_kernel's pipeline: TMA producer, MMA issuer, the eight epilogue warps)
+// and stores the frame's layer-2 map for conv3.
+// Why: as two kernels per 148-frame sub-batch the layers are joined by GRID-wide dependencies -- conv2 waits for the last conv1
+// CTA, conv1's epilogue of the next sub-batch waits for the last conv2 CTA (it overwrites what conv2 reads) -- and every launch
+// pays its ramp and drain: by the per-CTA clock stamps a sub-batch takes ~62 us of which ~46 us are the two tile loops.  A frame's
+// layer-2 rows depend on that frame's layer-1 map only (the conv padding is per frame, and with the frame pitch a multiple of 128
+// positions a frame is a whole number of layer-2 tiles), so nothing has to cross CTAs: here a phase change is a __syncthreads.
+// The slot (400 KB at 720p) is written and read back by the same SM within ~50 us; the 148 slots (59 MB) stay in the L2.
+// Shared memory is time-shared by the phases: layer 2's taps and stages overlay layer 1's taps and rings; the resize tables, all
+// mbarriers and both layers' epilogue parameters live beyond layer 2's footprint and persist.  Layer 1 starts every frame from
+// zero (its counters and barrier phases are re-initialised: the pipeline is quiescent at a phase change); layer 2's barrier
+// phases simply run on from frame to frame.
+template <int C>
+struct F12Smem {
+    using S1 = F1Smem<C, F1Roles<true>::UNFOLD_WARPS>;
+    using S2 = MidSmem<C>;
+    static constexpr int OFF_BAR2 = S1::OFF_BAR + 640;             // layer 2's 13 barriers, inside layer 1's 1 KB barrier block
+    static constexpr int OFF_PAR2 = S1::total;                     // layer 2's bias / scale / shift
+    static constexpr int total = OFF_PAR2 + 3 * C * 4;
+    static_assert(S2::W_BYTES + MID_STAGES * MID_STAGE_BYTES <= S1::OFF_TAB, "layer 2's operands must end before the tables layer 1 keeps");
+    static_assert(2 * (3 + 3 + 2 * RAW_SLOTS_MAX + TILE_RING) * 4 + 8 + (F1Roles<true>::UNFOLD_WARPS + 4) * 4 <= 640, "layer 1's barrier block");
+    static_assert(total <= 232448, "227 KB of shared memory per CTA");
+};
+
+template <int C, bool GATHER>
+__global__ void __launch_bounds__(F1Roles<true>::THREADS, 1)
+conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_constant__ CUtensorMap in_map, const MidParams p2) {
+    using RL = F1Roles<true>;
+    constexpr int UNFOLD_WARPS = RL::UNFOLD_WARPS, F1_MMA_WARP = RL::MMA_WARP0, F1_LOAD_WARP0 = RL::LOAD_WARP0;
+    static_assert(RL::MMA_WARPS == 1, "one issuer for both layers");
+    using S = F1Smem<C, UNFOLD_WARPS>;
+    using S2 = MidSmem<C>;
+    using SS = F12Smem<C>;
+    constexpr int CG = C / 8, CH = C / 2, KS = C / 16;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // ---- layer 1 (the layout of conv1_fused_tc_kernel)
+    uint8_t *s_w = smem;
+    uint8_t *s_ring = smem + S::OFF_RING;
+    uint8_t *s_raw = smem + S::OFF_RAW;
+    int *s_rowoff = reinterpret_cast<int *>(smem + S::OFF_TAB);
+    int *s_yb = s_rowoff + 2 * F_MAX_DST;
+    int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);
+    uint32_t *s_cmp = reinterpret_cast<uint32_t *>(smem + S::OFF_CMP);
+    uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);
+    uint64_t *acc_empty = acc_full + 3;
+    uint64_t *raw_full = acc_empty + 3;
+    uint64_t *raw_empty = raw_full + RAW_SLOTS_MAX;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + RAW_SLOTS_MAX);
+    int *s_rows_done = reinterpret_cast<int *>(tmem_slot + 2);
+    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;
+    uint64_t *tile_done = reinterpret_cast<uint64_t *>(s_rows_issued + 4);
+    uint32_t *s_par = reinterpret_cast<uint32_t *>(smem + S::OFF_PAR);
+    // ---- layer 2 (conv_mid_tc_kernel's operands over the same bytes; its barriers and parameters in the persistent tail)
+    uint8_t *s_w2 = smem;
+    uint8_t *s_stage = smem + S2::W_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SS::OFF_BAR2);
+    uint64_t *empty = full + MID_STAGES;
+    uint64_t *acc_full2 = empty + MID_STAGES;
+    uint64_t *acc_empty2 = acc_full2 + 3;
+    uint64_t *w_full = acc_empty2 + 3;
+    uint64_t *w1_full = w_full + 1;                                // layer 1's taps have landed (bulk copy, once per frame)
+    float *s_par2 = reinterpret_cast<float *>(smem + SS::OFF_PAR2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ResizePlanDev &plan = src.plan;
+    const int H = p.H, P1w = p.P1w, RPF = p.P1h + 1;
+    const int Hc = min(H, 3 * p.P1h + 1);
+    const int slot_idx = blockIdx.x;                              // this CTA's frame slot of the layer-1 buffer
+    const int n_frames_cta = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_tiles = (RPF * P1w + 127) / 128;                  // layer-1 tiles of ONE frame
+    const int total_u = 3 * RPF;
+    const int tiles2 = p2.FP / 128;                               // layer-2 tiles of one frame (the frame pitch is a multiple of 128)
+    const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;
+    const uint32_t inv_slots = 0xffffffffu / (uint32_t)n_slots + 1u;
+
+    // ---- once per launch: what survives the phases
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        s_par[i] = p.par16[i];
+        s_par2[i] = p2.bias[i]; s_par2[C + i] = p2.scale[i]; s_par2[2 * C + i] = p2.shift[i];
+    }
+    for (int i = threadIdx.x; i < UNFOLD_WARPS * F1_CMP_STRIDE; i += blockDim.x) s_cmp[i] = 0u;
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        int r0, r1, b0 = 2048, b1 = 0;
+        if (plan.gather_step_x > 0) { r0 = r1 = plan.gather_off_y + y * plan.gather_step_y; }
+        else if (plan.mode == RESIZE_COPY) { r0 = r1 = y; }
+        else if (plan.mode == RESIZE_AREA2) { r0 = 2 * y; r1 = 2 * y + 1; }
+        else { r0 = plan.y0[y]; r1 = plan.y1[y]; b0 = plan.b0[y]; b1 = plan.b1[y]; }
+        if (src.compact) { r0 = plan.row_slot[r0]; r1 = (plan.mode == RESIZE_LINEAR && b1 == 0) ? r0 : plan.row_slot[r1]; }
+        s_rowoff[2 * y] = (int)(r0 * src.row_pitch);
+        s_rowoff[2 * y + 1] = (int)(r1 * src.row_pitch);
+        s_yb[2 * y] = b0;
+        s_yb[2 * y + 1] = b1;
+    }
+    if (plan.mode == RESIZE_LINEAR && plan.gather_step_x == 0)
+        for (int x = threadIdx.x; x < plan.dst_w; x += blockDim.x) {
+            const int x0 = plan.x0[x], x1 = plan.x1[x];
+            int a0 = plan.a0[x], a1 = plan.a1[x];
+            if (x1 != x0 + 1) { a0 += a1; a1 = 0; }
+            s_xtab[x] = make_int4(3 * x0, a0 | (a1 << 16), 0, 0);
+        }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MID_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int d = 0; d < 3; ++d) { mbar_init(&acc_full2[d], 1); mbar_init(&acc_empty2[d], EPI_WARPS); }
+        mbar_init(w_full, 1);
+        mbar_init(w1_full, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&in_map);
+    }
+    if (warp == F1_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    long long *tl = (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr;    // debug stamps of CTA 0
+    if (tl) tl[0] = clock64();
+    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2048 + 2 * blockIdx.x] = g; }
+    grid_dep_launch();
+
+    // ---- phase changes (every thread runs all three, once per frame)
+    // Layer 1 starts from zero: its taps and the zero row above the frame go back over what layer 2 left, its counters and barriers
+    // are reset.  (All of them are quiescent: every transaction was waited for by a consumer, every generic arrival precedes the
+    // __syncthreads of frame_end, and the issuer waits for its last commit.)
+    const uint32_t Z2 = 0u, Z2K = 0x3c000000u;
+    // layer 1's barriers: acc_full[3] | acc_empty[3] | raw_full | raw_empty are consecutive, tile_done follows the counters
+    constexpr int L1_BARS = 6 + 2 * RAW_SLOTS_MAX + TILE_RING;
+    auto l1_bar = [&](int i) { return i < L1_BARS - TILE_RING ? acc_full + i : tile_done + (i - (L1_BARS - TILE_RING)); };
+    auto frame_begin = [&](int it) {
+        if (threadIdx.x == 0) {            // layer 1's taps by bulk copy (the issuer waits for them before its first MMA)
+            mbar_arrive_expect_tx(w1_full, S::W_BYTES);
+            bulk_load_1d(s_w, p.w_perm16, S::W_BYTES, w1_full);
+        }
+        for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
+            reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
+                make_uint4(Z2, Z2, Z2, i >= P1w ? Z2K : Z2);
+        if (threadIdx.x < UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;    // ... and s_rows_issued
+        {   // one barrier per thread (they were invalidated at the last phase change, see phase_switch)
+            const int i = (int)threadIdx.x - 64;
+            if (i >= 0 && i < L1_BARS) {
+                mbar_init(l1_bar(i), (i >= 3 && i < 6) ? EPI_WARPS : 1);
+                fence_barrier_init();
+            }
+        }
+        if (tl && it < 600) tl[1 + 3 * it] = clock64();
+        fence_proxy_async();
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+    };
+    // layer 1 -> layer 2: the slot is complete in global memory (the epilogue warps fenced their stores towards the async proxy)
+    auto phase_switch = [&](int it) {
+        fence_proxy_async();
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+        // Layer 1's barriers are invalidated HERE, a whole layer-2 phase before frame_begin initialises them again: mbarrier.inval
+        // (SYNCS.CCTL.IV) directly followed by mbarrier.init (SYNCS.EXCH) of the same barrier by the same thread left barriers
+        // invalid -- the kernel hung on its second frame -- while a version in which one thread invalidated all 62 and then
+        // initialised all 62 ran: the invalidation is not ordered with an exchange that follows it closely.
+        const int i = (int)threadIdx.x - 64;
+        if (i >= 0 && i < L1_BARS) mbar_inval(l1_bar(i));
+        if (tl && it < 600) tl[2 + 3 * it] = clock64();
+    };
+    auto frame_end = [&](int it) {
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+        if (tl && it < 600) tl[3 + 3 * it] = clock64();
+    };
+
+    if (warp < 8) reg_alloc<RL::REGS_EPI>();
+    else if (warp >= RL::WARPS - 4) reg_dealloc<RL::REGS_LIGHT>();
+    else reg_dealloc<RL::REGS_UNFOLD>();
+    if (warp >= F1_MMA_WARP) {
+        if (warp >= F1_LOAD_WARP0) {
+            // ------------------------------------------------------------------ loaders (layer 1); the first one is layer 2's TMA producer
+            const int lw = warp - F1_LOAD_WARP0;
+            const int n_loaders = min(LOADER_WARPS, n_slots);
+            const uint64_t stream_once = l2_policy_evict_first();
+            uint32_t stage = 0, phase = 0;
+            for (int it = 0; it < n_frames_cta; ++it) {
+                frame_begin(it);
+                if (lw < n_loaders) {
+                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)it * gridDim.x) * src.frame_stride;
+                    int issued = 0;
+                    for (int n = lw; n < Hc; n += n_loaders) {
+                        const int use = (int)__umulhi((uint32_t)n, inv_slots), slot = n - use * n_slots;
+                        mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
+                        ++issued;
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
+                            for (int j = 0; j < src.n_src; ++j)
+                                bulk_load_1d_hint(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * n + j],
+                                                  (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
+                            st_release_shared(&s_rows_issued[lw], issued);
+                        }
+                        __syncwarp();
+                    }
+                }
+                phase_switch(it);
+                if (lw == 0) {
+                    fence_proxy_async_global();
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(w_full, S2::W_BYTES);
+                        for (int ky = 0; ky < 3; ++ky)
+                            bulk_load_1d(s_w2 + ky * S2::W_KY_BYTES, reinterpret_cast<const uint8_t *>(p2.w_packed) + ky * S2::W_KY_BYTES, S2::W_KY_BYTES, w_full);
+                    }
+                    __syncwarp();
+                    for (int t2 = 0; t2 < tiles2; ++t2) {
+                        const int tile = slot_idx * tiles2 + t2;
+                        for (int ks = 0; ks < KS; ++ks) {
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&full[stage], MID_STAGE_BYTES);
+                                uint8_t *dst = s_stage + stage * MID_STAGE_BYTES;
+                                for (int pl = 0; pl < 9; ++pl)
+                                    tma_load_4d(dst + pl * (2 * MID_WIN * 16), &in_map, &full[stage], 0, 4 * tile - 1, 2 * ks, pl);
+                            }
+                            __syncwarp();
+                            if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+                frame_end(it);
+            }
+        } else {
+            // ------------------------------------------------------------------ MMA issuer of both layers
+            const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
+            const uint32_t w2_addr = smem_u32(s_w2), stage_addr = smem_u32(s_stage);
+            const uint32_t idesc1 = instr_desc_f16_acc16(128, 3 * C);
+            uint32_t stage = 0, phase = 0, acc_phase2 = 0;
+            for (int it = 0; it < n_frames_cta; ++it) {
+                frame_begin(it);
+                {
+                    uint32_t acc_phase = 0;
+                    int r_hi = 127 / P1w, r_rem = 127 % P1w;
+                    mbar_wait(w1_full, it & 1);
+                    for (int t = 0; t < n_tiles; ++t) {
+                        const int u_hi = min(total_u - 1, 3 * (r_hi + 1));
+                        r_rem += 128;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) { const bool c = r_rem >= P1w; r_rem -= c ? P1w : 0; r_hi += c ? 1 : 0; }
+                        const int mine = lane % UNFOLD_WARPS;
+                        const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
+                        while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(32);
+                        __syncwarp();
+                        tc_fence_after_sync();
+                        uint32_t a_chunk[5];
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) {
+                            const int sub = (c + 2) % 3, shift = c == 0 ? -P1w : (c == 4 ? P1w : 0);
+                            a_chunk[c] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
+                        }
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            mbar_wait(&acc_empty[dy], acc_phase ^ 1);
+                            tc_fence_after_sync();
+                            if (elect_one()) {
+#pragma unroll
+                                for (int ks = 0; ks < 3; ++ks) {
+                                    const uint64_t da = smem_desc(a_chunk[dy + ks], FR_PLANE, 128);
+                                    const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
+                                    umma_16bit(tmem_base + 3 * C * dy, da, db, idesc1, ks > 0 ? 1u : 0u);
+                                }
+                                umma_commit(&acc_full[dy]);
+                                if (dy == 2) umma_commit(&tile_done[t & (TILE_RING - 1)]);
+                            }
+                            __syncwarp();
+                        }
+                        acc_phase ^= 1;
+                    }
+                    // the last commit has arrived (and with it every earlier one) before the barriers are re-initialised
+                    mbar_wait(&tile_done[(n_tiles - 1) & (TILE_RING - 1)], ((n_tiles - 1) / TILE_RING) & 1);
+                }
+                phase_switch(it);
+                mbar_wait(w_full, it & 1);
+                for (int t2 = 0; t2 < tiles2; ++t2) {
+                    for (int ks = 0; ks < KS; ++ks) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after_sync();
+                        const uint32_t a_stage = stage_addr + stage * MID_STAGE_BYTES;
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            if (ks == 0) {
+                                mbar_wait(&acc_empty2[dy], acc_phase2 ^ 1);
+                                tc_fence_after_sync();
+                            }
+                            if (elect_one()) {
+#pragma unroll
+                                for (int ky = 0; ky < 3; ++ky) {
+                                    const int oy = dy + ky - 1;
+                                    const int py = (oy + 3) % 3, sy = oy < 0 ? -1 : (oy > 2 ? 1 : 0);
+#pragma unroll
+                                    for (int o = 0; o < 5; ++o) {
+                                        const int ox = (o == 0) ? 1 : (o == 1) ? 0 : (o == 2) ? 2 : (o == 3) ? -1 : 3;
+                                        const int px = (ox + 3) % 3, sx = ox < 0 ? -1 : (ox > 2 ? 1 : 0);
+                                        const int dx_lo = ox - 1 < 0 ? 0 : ox - 1, dx_hi = ox + 1 > 2 ? 2 : ox + 1;
+                                        const int n_dx = dx_hi - dx_lo + 1, kx_start = ox + 1 - dx_lo;
+                                        const uint32_t idesc = instr_desc_16bit(128, C * n_dx, kBf16);
+                                        const uint32_t a_view = a_stage + (py * 3 + px) * (2 * MID_WIN * 16) +
+                                                                (uint32_t)(MID_HALO + sy * p2.PW + sx) * 16;
+                                        const uint32_t b_tap = w2_addr + ky * S2::W_KY_BYTES + 2 * ks * S2::LBO_B + (2 - kx_start) * C * 16;
+                                        const uint64_t da = smem_desc(a_view, MID_WIN * 16, 128);
+                                        const uint64_t db = smem_desc(b_tap, S2::LBO_B, 128);
+                                        umma_16bit(tmem_base + C * (dy * 3 + dx_lo), da, db, idesc, (ks == 0 && ky == 0 && ox == 1) ? 0u : 1u);
+                                    }
+                                }
+                                if (ks == KS - 1) umma_commit(&acc_full2[dy]);
+                            }
+                            __syncwarp();
+                        }
+                        if (elect_one()) umma_commit(&empty[stage]);
+                        __syncwarp();
+                        if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    acc_phase2 ^= 1;
+                }
+                frame_end(it);
+            }
+        }
+    } else if (warp >= 8) {
+        // ------------------------------------------------------------------ unfold (layer 1); idle during layer 2
+        for (int it = 0; it < n_frames_cta; ++it) {
+            frame_begin(it);
+            F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
+                     RPF, Hc, total_u, n_slots, slot_bytes, min(LOADER_WARPS, n_slots), inv_slots, nullptr};
+            f1_unfold_role<C, GATHER, true, UNFOLD_WARPS>(cx, warp - 8, lane);
+            phase_switch(it);
+            if (warp == 8 && it + 1 < n_frames_cta) {
+                // these warps idle while layer 2 runs: bring the first source rows of the next frame into the L2, so that layer 1
+                // starts on L2 hits instead of a DRAM round trip per loader
+                const uint8_t *next = src.frames + (long long)(blockIdx.x + (long long)(it + 1) * gridDim.x) * src.frame_stride;
+                for (int n = lane; n < min(Hc, 2 * n_slots); n += 32)
+                    for (int j = 0; j < src.n_src; ++j) bulk_prefetch_l2(next + s_rowoff[2 * n + j], (uint32_t)src.row_bytes);
+            }
+            frame_end(it);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue of both layers
+        const int q = warp & 3, half = warp >> 2, m = q * 32 + lane, ch0 = half * CH;
+        const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + half * 3 * CH;     // layer 1: columns [dy][half][dx][CH]
+        const uint32_t tmem_thread2 = tmem_base + ((uint32_t)(q * 32) << 16) + ch0;              // layer 2: columns [dy][dx][C]
+        uint32_t acc_phase2 = 0;
+        // The kernel before this one (conv3 of the previous group, and through it the previous launch of this kernel) may still be
+        // using the buffers written from here on.
+        grid_dep_wait();
+        zero_pads(p.out, CG, slot_idx, slot_idx + 1, threadIdx.x, EPI_WARPS * 32);
+        if (slot_idx > 0) {
+            // ... and the MID_HALO positions before this slot, which tile 0's shifted views read: the tail of the previous slot's
+            // padding (never anything but zero), zeroed here as well so that this CTA does not depend on when its neighbour starts
+            uint4 *act = reinterpret_cast<uint4 *>(p.out.ptr);
+            for (int i = threadIdx.x; i < 9 * CG * MID_HALO; i += EPI_WARPS * 32)
+                act[(size_t)(i / MID_HALO) * p.out.gtot + (size_t)slot_idx * p.out.FP - MID_HALO + i % MID_HALO] = make_uint4(0, 0, 0, 0);
+        }
+        for (int it = 0; it < n_frames_cta; ++it) {
+            frame_begin(it);
+            {
+                uint32_t acc_phase = 0;
+                int X = m % P1w, Y = m / P1w;                          // position 128 t + m = Y * P1w + X of this frame
+                EpiRow16<CH> bufA, bufB;
+                mbar_wait(&acc_full[0], 0);
+                tc_fence_after_sync();
+                epi_issue_row16<C>(tmem_thread, 0, bufA);
+                auto tile = [&](int t, EpiRow16<CH> &cur, EpiRow16<CH> &nxt) {
+                    const bool valid = Y < p.P1h;
+                    uint4 *dst = store_addr16<C>(p.out, slot_idx, Y, X, ch0);
+                    X += 128;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { const bool c = X >= P1w; X -= c ? P1w : 0; Y += c ? 1 : 0; }
+                    uint32_t v[CH / 2];
+                    bool requested = epilogue_tile_pipelined16<C>(tmem_thread, acc_full, acc_empty, acc_phase, lane, t + 1 < n_tiles, cur, nxt, v);
+                    epilogue_scale_shift16<C>(s_par, ch0, v);
+                    if (!requested && mbar_test_wait(&acc_full[0], acc_phase ^ 1)) {
+                        tc_fence_after_sync();
+                        epi_issue_row16<C>(tmem_thread, 0, nxt);
+                        requested = true;
+                    }
+                    if (valid) store_pixel16<C>(dst, p.out.gtot, v);
+                    if (!requested) {
+                        mbar_wait(&acc_full[0], acc_phase ^ 1);
+                        tc_fence_after_sync();
+                        epi_issue_row16<C>(tmem_thread, 0, nxt);
+                    }
+                    acc_phase ^= 1;
+                };
+                for (int t = 0; t < n_tiles; t += 2) {
+                    tile(t, bufA, bufB);
+                    if (t + 1 < n_tiles) tile(t + 1, bufB, bufA);
+                }
+            }
+            fence_proxy_async_global();            // this thread's stores of the slot, before layer 2's TMA reads them
+            phase_switch(it);
+            {
+                const int f_out = blockIdx.x + it * gridDim.x;         // frame index inside this launch = slot of the layer-2 buffer
+                zero_pads(p2.out, CG, f_out, f_out + 1, threadIdx.x, EPI_WARPS * 32);
+                for (int t2 = 0; t2 < tiles2; ++t2) {
+                    const int pos = t2 * 128 + m;
+                    const int Y = pos / p2.PW, X = pos % p2.PW;
+                    const bool valid = Y < p2.out_h && X < p2.out_w;
+                    float v[CH];
+                    epilogue_tile<C>(tmem_thread2, acc_full2, acc_empty2, acc_phase2, lane, s_par2, ch0, v);
+                    if (valid) store_pixel<C>(p2.out, f_out, Y, X, ch0, v);
+                    acc_phase2 ^= 1;
+                }
+            }
+            frame_end(it);
+        }
+    }
+    if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2049 + 2 * blockIdx.x] = g; }
+    if (warp == F1_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // ------------------------------------------------------------------------------------------------ input packing
 // K1 for the tensor-core path: decoded frames -> x-unfolded 16-bit operands (pixel value * kPixelScale / 255, RGB order).
 // One thread per (frame, output row, pooled column): five resized pixels, 32 bytes out.
@@ -1963,6 +2381,8 @@ int set_smem_limits() {
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_sets_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv1_fused_sets_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     CUTDET_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, MidSmem<C>::total));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv12_frames_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F12Smem<C>::total));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv12_frames_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F12Smem<C>::total));
     return CUTDET_OK;
 }
 
@@ -2104,11 +2524,7 @@ int get_maps(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, std
     return CUTDET_OK;
 }
 
-// conv1 + conv2 over one sub-batch whose x-unfolded input already sits in the workspace; layer 2's maps land in the
-// group buffer at frame slot `slot0`.
-template <int C>
-int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, const CUtensorMap &map1, int nb, int slot0,
-               cudaStream_t stream, const FusedSrc *fused, int f0) {
+Conv1Params conv1_params(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int nb) {
     TcState *tc = net->tc;
     Conv1Params c1;
     memset(&c1, 0, sizeof(c1));
@@ -2125,6 +2541,23 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
     c1.w_perm16 = reinterpret_cast<const uint4 *>(tc->d_w1_perm16);
     c1.par16 = tc->d_c1_par16;
     c1.folded = tc->c1_folded ? 1 : 0;
+    return c1;
+}
+
+MidParams conv2_params(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, int nb, int slot0) {
+    MidParams p2 = mid_params(nb, g.FP1, g.PW1, g.P2h, g.P2w);
+    p2.out = OutSpec{ws + w.act2, 0, w.gtot2, g.PW2, g.FP2, g.Q2h, slot0, g.P2h, g.P2w};
+    p2.w_packed = reinterpret_cast<const uint4 *>(net->tc->d_w2);
+    p2.bias = net->conv[1].d_bias; p2.scale = net->conv[1].d_scale; p2.shift = net->conv[1].d_shift;
+    return p2;
+}
+
+// conv1 + conv2 over one sub-batch whose x-unfolded input already sits in the workspace; layer 2's maps land in the
+// group buffer at frame slot `slot0`.
+template <int C>
+int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, const CUtensorMap &map1, int nb, int slot0,
+               cudaStream_t stream, const FusedSrc *fused, int f0) {
+    Conv1Params c1 = conv1_params(net, g, w, ws, nb);
     // debug stamps (cutdet_net_debug_timeline): the armed buffer is caller-owned device memory; nothing is allocated, copied or
     // synchronised here
     if (net->opt.timeline_kernel == 1 && nb >= SUB_BATCH) c1.timeline = net->opt.timeline_dev;
@@ -2134,12 +2567,48 @@ int run_conv12(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, c
         if (int rc = launch_conv1_fused<C>(c1, fs, stream, f0 > 0 && !net->opt.no_pdl, net->opt.conv1_acc32 != 0, net->opt.conv1_grid, net->opt.conv1_variant)) return rc;
     } else if (int rc = launch_conv1<C>(c1, stream)) return rc;
 
-    MidParams p2 = mid_params(nb, g.FP1, g.PW1, g.P2h, g.P2w);
-    p2.out = OutSpec{ws + w.act2, 0, w.gtot2, g.PW2, g.FP2, g.Q2h, slot0, g.P2h, g.P2w};
-    p2.w_packed = reinterpret_cast<const uint4 *>(tc->d_w2);
-    p2.bias = net->conv[1].d_bias; p2.scale = net->conv[1].d_scale; p2.shift = net->conv[1].d_shift;
+    MidParams p2 = conv2_params(net, g, w, ws, nb, slot0);
     if (net->opt.timeline_kernel == 2 && nb >= SUB_BATCH) p2.timeline = net->opt.timeline_dev;
     return launch_mid<C>(map1, p2, "conv2_tc", stream, !net->opt.no_pdl);
+}
+
+// K1 + conv1 + conv2 of frames [f0, f0 + n) in ONE launch, a frame at a time per CTA (conv12_frames_kernel); layer 2's maps land in
+// frame slots [0, n) of the group buffer.  The layer-1 buffer serves as one scratch slot per CTA.
+template <int C>
+int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, const CUtensorMap &map1, int n, cudaStream_t stream,
+                      const FusedSrc &fused, int f0) {
+    Conv1Params c1 = conv1_params(net, g, w, ws, n);
+    if (net->opt.timeline_kernel == 3 && n >= SUB_BATCH) c1.timeline = net->opt.timeline_dev;
+    const MidParams p2 = conv2_params(net, g, w, ws, n, 0);
+    FusedSrc src = fused;
+    src.frames += (long long)f0 * src.frame_stride;
+    const int grid_cap = net->opt.conv1_grid > 0 ? net->opt.conv1_grid : 1 << 30;
+    const int grid = std::min(std::min(std::min(n, sm_count()), w.sub), grid_cap);      // one layer-1 slot per CTA
+    static const bool regs_ok = [] {
+        const void *fns[2] = {(const void *)conv12_frames_kernel<C, true>, (const void *)conv12_frames_kernel<C, false>};
+        bool ok = true;
+        for (int i = 0; i < 2; ++i) {
+            cudaFuncAttributes a{};
+            cudaFuncGetAttributes(&a, fns[i]);
+            if (a.numRegs != F1Roles<true>::REGS_START) {
+                fprintf(stderr, "cutdet: conv12_frames compiled with %d registers, the setmaxnreg budget assumes %d\n", a.numRegs, F1Roles<true>::REGS_START);
+                ok = false;
+            }
+        }
+        return ok;
+    }();
+    if (!regs_ok) return CUTDET_EUNSUPPORTED;
+    src.n_slots = (int)std::min<long long>(raw_bytes(F1Roles<true>::UNFOLD_WARPS) / ((long long)src.n_src * src.row_bytes), RAW_SLOTS_MAX);
+    src.n_slots -= src.n_slots % std::min(LOADER_WARPS, src.n_slots);
+    {
+        KernelScope scope("conv12_frames", stream);
+        const bool gather = src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0;
+        const bool pdl = f0 > 0 && !net->opt.no_pdl;        // the loaders read the frames at once: only behind a kernel of ours
+        if (gather) launch_pdl(pdl, conv12_frames_kernel<C, true>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2);
+        else launch_pdl(pdl, conv12_frames_kernel<C, false>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2);
+    }
+    CUTDET_LAUNCH_CHECK("conv12_frames_kernel");
+    return CUTDET_OK;
 }
 
 // conv3 over the `n` frames gathered in the group buffer; their layer-3 maps go to frames [frame0, frame0 + n) of act3.
@@ -2232,6 +2701,16 @@ int run_batch(cutdet_net *net, const Geom &g, const TcWorkspace &w, char *ws, in
               Pack pack, const FusedSrc *fused = nullptr) {
     std::pair<CUtensorMap, CUtensorMap> *maps = nullptr;
     if (int rc = get_maps(net, g, w, ws, &maps)) return rc;
+    // CUTDET_OPT_CONV1_VARIANT: 0 = automatic, 2 = the same choice stated; 1 and 3 keep the two-kernel path (3 with the default conv1)
+    if (fused && (net->opt.conv1_variant == 0 || net->opt.conv1_variant == 2) && !net->opt.conv1_acc32 && net->tc->d_w1_perm16) {
+        // both layers of a frame by one CTA, a whole group per launch, then conv3 of the group
+        for (int f0 = 0; f0 < batch; f0 += w.group_frames) {
+            const int n = std::min(batch - f0, w.group_frames);
+            if (int rc = run_conv12_frames<C>(net, g, w, ws, maps->first, n, stream, *fused, f0)) return rc;
+            if (int rc = run_conv3<C>(net, g, w, ws, maps->second, n, f0, stream)) return rc;
+        }
+        return run_head(net, g, w, ws, batch, logits, stream);
+    }
     int group_start = 0, in_group = 0;
     for (int f0 = 0; f0 < batch; f0 += w.sub) {
         const int nb = batch - f0 < w.sub ? batch - f0 : w.sub;

@@ -267,7 +267,7 @@ extern "C" int cutdet_net_get_option(const cutdet_net *net, int option, int *val
 extern "C" int cutdet_net_debug_timeline(cutdet_net *net, int kernel, long long *stamps_dev, size_t n_entries) {
     CUTDET_REQUIRE(net, "net_debug_timeline: null net");
     if (kernel == 0 || !stamps_dev) { net->opt.timeline_kernel = 0; net->opt.timeline_dev = nullptr; return CUTDET_OK; }
-    CUTDET_REQUIRE((kernel == 1 || kernel == 2) && n_entries >= 4096, "net_debug_timeline: kernel 1 or 2 and >= 4096 entries");
+    CUTDET_REQUIRE(kernel >= 1 && kernel <= 3 && n_entries >= 4096, "net_debug_timeline: kernel 1, 2 or 3 and >= 4096 entries");
     net->opt.timeline_kernel = kernel;
     net->opt.timeline_dev = stamps_dev;
     return CUTDET_OK;

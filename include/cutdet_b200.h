@@ -154,9 +154,12 @@ enum {
     CUTDET_OPT_GROUP_FRAMES = 3, /* frames gathered for one conv3 launch (default 0 = 1184)                             */
     CUTDET_OPT_NO_PDL = 4,       /* 1: ordinary launches instead of programmatic dependent launch                       */
     CUTDET_OPT_CONV1_GRID = 5,   /* test hook: cap on the fused conv1 grid (several frames per CTA); 0 = no cap         */
-    CUTDET_OPT_CONV1_VARIANT = 6 /* 1: experiment -- the fused conv1 kernel with two alternating epilogue sets and an MMA issuer
-                                    per block row instead of the default one; same arithmetic, same bits, same speed to within
-                                    1 % (profiles/README.md, round 2; kept for same-box A/B runs)                          */
+    CUTDET_OPT_CONV1_VARIANT = 6 /* which kernels run layers 1 and 2 of the fused frames path; all give the same bits.
+                                    0 (default) and 2: ONE kernel takes a frame through K1 + layer 1 + layer 2 per CTA
+                                    (conv12_frames_kernel; where it does not apply -- fp32 accumulators requested -- the
+                                    two-kernel path runs); 3: the two-kernel path (conv1_fused_tc + conv2_tc per 148-frame
+                                    sub-batch); 1: the two-kernel path with the experimental conv1 kernel of two alternating
+                                    epilogue sets (profiles/README.md, round 2; kept for same-box A/B runs)                 */
 };
 CUTDET_API int cutdet_net_set_option(cutdet_net *net, int option, int value);
 CUTDET_API int cutdet_net_get_option(const cutdet_net *net, int option, int *value);

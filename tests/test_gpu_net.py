@@ -264,13 +264,15 @@ def test_fused_kernel_with_several_frames_per_cta(prod_weights):
     net = engine.NativeNet(wts, params["avg_pool_size"])
     net.set_option("conv1_grid", 37)
     worst = 0.0
-    for (h, w, batch) in ((720, 1280, 301), (1080, 1920, 75), (360, 640, 140)):
-        rng = np.random.default_rng(h + batch)
-        frames = torch.from_numpy(rng.integers(0, 256, (batch, h, w, 3), dtype=np.uint8)).cuda()
-        plan = engine.ResizePlan.for_video(h, w, 256)
-        want = net.forward_f32(engine.preprocess_f32(plan, frames)).cpu().numpy()
-        got = net.forward_frames(plan, frames).cpu().numpy()
-        worst = max(worst, float(np.abs(got - want).max()))
+    for variant in (3, 2):          # the two-kernel path, and one CTA per frame through both layers (the default)
+        net.set_option("conv1_variant", variant)
+        for (h, w, batch) in ((720, 1280, 301), (1080, 1920, 75), (360, 640, 140)):
+            rng = np.random.default_rng(h + batch)
+            frames = torch.from_numpy(rng.integers(0, 256, (batch, h, w, 3), dtype=np.uint8)).cuda()
+            plan = engine.ResizePlan.for_video(h, w, 256)
+            want = net.forward_f32(engine.preprocess_f32(plan, frames)).cpu().numpy()
+            got = net.forward_frames(plan, frames).cpu().numpy()
+            worst = max(worst, float(np.abs(got - want).max()))
     assert worst <= FUSED_TOL, worst
 
 
@@ -285,7 +287,13 @@ def test_dependent_launch_changes_nothing(prod_weights):
     # conv1_variant 1: the experimental fused conv1 kernel with two epilogue sets and an MMA issuer per block row -- max is exact in
     # fp16, so it must give the same bits as the default kernel
     for name, opts in (("pdl", {}), ("no_pdl", {"no_pdl": 1}), ("sub74", {"sub_batch": 74}), ("sub296", {"sub_batch": 296, "group_frames": 592}),
-                       ("sets", {"conv1_variant": 1}), ("sets_no_pdl", {"conv1_variant": 1, "no_pdl": 1})):
+                       ("two_kernels_sub74", {"conv1_variant": 3, "sub_batch": 74}), ("two_kernels_sub296", {"conv1_variant": 3, "sub_batch": 296, "group_frames": 592}),
+                       ("sets", {"conv1_variant": 1}), ("sets_no_pdl", {"conv1_variant": 1, "no_pdl": 1}),
+                       # conv1_variant 2: K1 + conv1 + conv2 of a frame by one CTA (conv12_frames_kernel): every position's
+                       # arithmetic is the same as in the two-kernel path, whatever the tiling
+                       ("two_kernels", {"conv1_variant": 3}), ("two_kernels_no_pdl", {"conv1_variant": 3, "no_pdl": 1}),
+                       ("frames", {"conv1_variant": 2}), ("frames_no_pdl", {"conv1_variant": 2, "no_pdl": 1}),
+                       ("frames_grid37", {"conv1_variant": 2, "conv1_grid": 37}), ("frames_group300", {"conv1_variant": 2, "group_frames": 300})):
         nets[name] = engine.NativeNet(wts, params["avg_pool_size"])
         for k, v in opts.items():
             nets[name].set_option(k, v)

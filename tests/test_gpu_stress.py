@@ -12,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 def test_forward_frames_is_reproducible(prod_weights, variant):
     from cutdet import engine
     wts, params = prod_weights

@@ -22,12 +22,13 @@ def main():
     ap.add_argument("--kernel", type=int, default=1)
     ap.add_argument("--height", type=int, default=720)
     ap.add_argument("--width", type=int, default=1280)
-    ap.add_argument("--frames", type=int, default=444)
+    ap.add_argument("--frames", type=int, default=444, help="for --kernel 3 use a multiple of 148, e.g. 1184")
     ap.add_argument("--out", default="gpurun_out/timeline.txt")
     ap.add_argument("--net-opt", action="append", default=[])
     a = ap.parse_args()
     net, _ = load_default_net()
     native = net.eval().to("cuda")._native()
+    native.set_option("conv1_variant", 2 if a.kernel == 3 else 3)       # kernels 1 and 2 belong to the two-kernel path
     for kv in a.net_opt:
         k, _, v = kv.partition("=")
         native.set_option(k, int(v))
@@ -43,6 +44,24 @@ def main():
     _cabi.check(_cabi.lib().cutdet_net_debug_timeline(native.handle, 0, None, 0))
     h = stamps.cpu().tolist()
     t0 = h[2047] if a.kernel == 1 else h[0]
+    if a.kernel == 3:
+        # conv12_frames_kernel, CTA 0: [0] start, then per frame [1 + 3 it] layer 1 set up, [2 + 3 it] layer 1 done, [3 + 3 it] layer 2 done
+        os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+        with open(a.out, "w") as f:
+            f.write("# frame: setup_done layer1_done layer2_done (cycles since CTA 0's start) | layer1 layer2 cycles\n")
+            it = 0
+            prev = 0
+            while 3 + 3 * it < 2048 and h[3 + 3 * it]:
+                b, m, e = (h[1 + 3 * it] - t0, h[2 + 3 * it] - t0, h[3 + 3 * it] - t0)
+                f.write(f"{it}: {b} {m} {e} | setup {b - prev} layer1 {m - b} layer2 {e - m}\n")
+                prev = e
+                it += 1
+            g0 = min(v for v in h[2048::2] if v)
+            for b in range(148):
+                if h[2048 + 2 * b]:
+                    f.write(f"cta {b} {h[2048 + 2 * b] - g0} {h[2049 + 2 * b] - g0}\n")
+        print(f"wrote {it} frames to {a.out}")
+        return
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     with open(a.out, "w") as f:
         for i, v in enumerate(h[:2048]):
