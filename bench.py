@@ -592,7 +592,10 @@ def kernel_table(kernels: dict, prof_steps: int, chunk: int, k1_src_bytes: int):
     dominant = max((n for n in table if "frac" in table[n]), key=lambda n: table[n]["share"], default=None)
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dominant, {}).get("dram_bytes_per_launch")
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dominant, {})
+        traffic = t.get("dram_bytes_per_launch")
+        if traffic is None and "dram_bytes_per_frame" in t:         # kernels whose launches cover any number of frames
+            traffic = t["dram_bytes_per_frame"] * table[dominant]["frames_per_launch"]
     except Exception:
         pass
     roofline = None

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """One short run of every kernel the round's ncu captures look at (profiles/README.md): the standalone K1 kernels (both of
 them, 720p and 1080p, float32 and uint8 outputs), K4/K5 over a full game's worth of frames (324,000), K6, and two full
-sub-batches of the fused frames path (conv1_fused_tc -> conv2_tc -> conv3_tc -> head).
+sub-batches of the fused frames path, by the two-kernel path (conv1_fused_tc -> conv2_tc -> conv3_tc -> head) and by the default
+one (conv12_frames -> conv3_tc -> head).
 
     python tools/ncu_case.py && ncu --set full -k regex:... python tools/ncu_case.py"""
 import os
@@ -29,8 +30,10 @@ def main():
                 engine.preprocess_f32(plan, frames)
                 engine.preprocess_u8(plan, frames)
         _cabi.check(lib.cutdet_debug_k1_kernel(0))
-        for _ in range(2):
-            native.forward_frames(plan, frames[:296])
+        for variant in (3, 0):              # the two-kernel path, then conv12_frames (two frames per CTA)
+            native.set_option("conv1_variant", variant)
+            for _ in range(2):
+                native.forward_frames(plan, frames[:296])
         torch.cuda.synchronize()
         del frames
     n = 324_000
