@@ -461,10 +461,14 @@ struct MidSmem {
     static constexpr int total = W_BYTES + MID_STAGES * MID_STAGE_BYTES + 256 /* barriers */ + 3 * C * 4;
 };
 
-// 320 threads: warps 0..7 = epilogue (TMEM lane quarter = warp % 4, channel half = warp / 4), warp 8 = TMA producer,
-// warp 9 = MMA issuer (+ TMEM alloc).  Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...
+// 384 threads: warps 0..7 = epilogue (TMEM lane quarter = warp % 4, channel half = warp / 4), warp 8 = TMA producer,
+// warps 9..11 = MMA issuers, one per block row dy (warp 9 also allocates TMEM).  Persistent: each CTA walks tiles blockIdx.x,
+// +gridDim.x, ...  Three issuers because a block row's 15 MMAs per k-step sit behind ~300 instructions of descriptor set-up, which
+// ONE warp issues about as fast as the tensor pipe retires the MMAs (3,100 cycles per k-step measured, 2,450 of MMA time): the
+// rows write disjoint TMEM columns, each issuer commits its own row's barrier, and a stage is free once all three committed it.
+constexpr int MID_THREADS = 384;
 template <int C>
-__global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_constant__ CUtensorMap in_map, const MidParams p) {
+__global__ void __launch_bounds__(MID_THREADS, 1) conv_mid_tc_kernel(const __grid_constant__ CUtensorMap in_map, const MidParams p) {
     using S = MidSmem<C>;
     constexpr int CG = C / 8, KS = C / 16, CH = C / 2;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
     // pipeline fills while they are in flight (copying them with LDG/STS before the first TMA cost ~2 us per launch).
     for (int i = threadIdx.x; i < C; i += blockDim.x) { s_par[i] = p.bias[i]; s_par[C + i] = p.scale[i]; s_par[2 * C + i] = p.shift[i]; }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < MID_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < MID_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 3); }
         for (int d = 0; d < 3; ++d) { mbar_init(&acc_full[d], 1); mbar_init(&acc_empty[d], EPI_WARPS); }
         mbar_init(w_full, 1);
         fence_barrier_init();
@@ -525,31 +529,28 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
                 if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 9) {
-        // ------------------------------------------------------------------ MMA issuer
-        uint32_t stage = 0, phase = 0, acc_phase = 0;
+    } else if (warp >= 9) {
+        // ------------------------------------------------------------------ MMA issuers: warp 9 + dy takes block row dy
         const uint32_t w_addr = smem_u32(s_w), stage_addr = smem_u32(s_stage);
-        long long *tl = (p.timeline && blockIdx.x == 0) ? p.timeline : nullptr;
-        int tli = 1;
-        if (tl && lane == 0) tl[tli] = clock64();
-        ++tli;
-        bool first_stamp = true;
-        mbar_wait(w_full, 0);
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            for (int ks = 0; ks < KS; ++ks) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after_sync();
-                if (tl && lane == 0) tl[tli] = clock64();      // stage data present
-                ++tli;
-                if (p.timeline && first_stamp && lane == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[128 + 4 * blockIdx.x + 2] = g; }
-                first_stamp = false;
-                const uint32_t a_stage = stage_addr + stage * MID_STAGE_BYTES;
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    if (ks == 0) {                          // first touch of block row dy in this tile: the epilogue must be done with it
-                        mbar_wait(&acc_empty[dy], acc_phase ^ 1);
-                        tc_fence_after_sync();
-                    }
+        long long *tl = (p.timeline && blockIdx.x == 0 && warp == 9) ? p.timeline : nullptr;
+        auto issue = [&](auto dyc) {
+            constexpr int dy = decltype(dyc)::value;
+            uint32_t stage = 0, phase = 0, acc_phase = 0;
+            int tli = 1;
+            if (tl && lane == 0) tl[tli] = clock64();
+            ++tli;
+            bool first_stamp = true;
+            mbar_wait(w_full, 0);
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int ks = 0; ks < KS; ++ks) {
+                    mbar_wait(&full[stage], phase);
+                    if (ks == 0) mbar_wait(&acc_empty[dy], acc_phase ^ 1);   // the epilogue must be done with this row of the previous tile
+                    tc_fence_after_sync();
+                    if (tl && lane == 0) tl[tli] = clock64();      // stage data present
+                    ++tli;
+                    if (dy == 0 && p.timeline && first_stamp && lane == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[128 + 4 * blockIdx.x + 2] = g; }
+                    first_stamp = false;
+                    const uint32_t a_stage = stage_addr + stage * MID_STAGE_BYTES;
                     if (elect_one()) {
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky) {
@@ -571,17 +572,19 @@ __global__ void __launch_bounds__(320, 1) conv_mid_tc_kernel(const __grid_consta
                             }
                         }
                         if (ks == KS - 1) umma_commit(&acc_full[dy]);
+                        umma_commit(&empty[stage]);                // one of the three arrivals that free the stage
                     }
                     __syncwarp();
+                    if (tl && lane == 0) tl[tli] = clock64();      // stage issued
+                    ++tli;
+                    if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (elect_one()) umma_commit(&empty[stage]);  // frees the stage once these MMAs have read it
-                __syncwarp();
-                if (tl && lane == 0) tl[tli] = clock64();      // stage issued
-                ++tli;
-                if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
+                acc_phase ^= 1;
             }
-            acc_phase ^= 1;
-        }
+        };
+        if (warp == 9) issue(std::integral_constant<int, 0>{});
+        else if (warp == 10) issue(std::integral_constant<int, 1>{});
+        else issue(std::integral_constant<int, 2>{});
     } else {
         // ------------------------------------------------------------------ epilogue
         // pads of the output buffer first (they belong to no GEMM row)
@@ -1676,7 +1679,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
             s_xtab[x] = make_int4(3 * x0, a0 | (a1 << 16), 0, 0);
         }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < MID_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < MID_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 3); }      // three issuers free a stage
         for (int d = 0; d < 3; ++d) { mbar_init(&acc_full2[d], 1); mbar_init(&acc_empty2[d], EPI_WARPS); }
         mbar_init(w_full, 1);
         mbar_init(w1_full, 1);
@@ -1744,6 +1747,49 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         if (tl && it < 600) tl[3 + 3 * it] = clock64();
     };
 
+    // Layer 2's MMAs of ONE block row dy over a frame's tiles.  Three warps issue, one per block row (the layer-1 issuer and the two
+    // loaders that layer 2 does not need): a block row is 15 MMAs per k-step behind ~300 instructions of descriptor set-up, which
+    // one warp issues about as fast as the tensor pipe retires them; three in parallel keep its queue full.  The rows write
+    // disjoint TMEM columns, each issuer commits its own row's barrier, and a stage is free once all three have committed it.
+    const uint32_t w2_addr = smem_u32(s_w2), stage_addr = smem_u32(s_stage);
+    auto layer2_issue = [&](auto dyc, int it, uint32_t &stage, uint32_t &phase, uint32_t &acc_phase2) {
+        constexpr int dy = decltype(dyc)::value;
+        mbar_wait(w_full, it & 1);
+        for (int t2 = 0; t2 < tiles2; ++t2) {
+            for (int ks = 0; ks < KS; ++ks) {
+                mbar_wait(&full[stage], phase);
+                if (ks == 0) mbar_wait(&acc_empty2[dy], acc_phase2 ^ 1);     // the epilogue is done with this row of the previous tile
+                tc_fence_after_sync();
+                const uint32_t a_stage = stage_addr + stage * MID_STAGE_BYTES;
+                if (elect_one()) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int oy = dy + ky - 1;
+                        const int py = (oy + 3) % 3, sy = oy < 0 ? -1 : (oy > 2 ? 1 : 0);
+#pragma unroll
+                        for (int o = 0; o < 5; ++o) {
+                            const int ox = (o == 0) ? 1 : (o == 1) ? 0 : (o == 2) ? 2 : (o == 3) ? -1 : 3;   // centre first
+                            const int px = (ox + 3) % 3, sx = ox < 0 ? -1 : (ox > 2 ? 1 : 0);
+                            const int dx_lo = ox - 1 < 0 ? 0 : ox - 1, dx_hi = ox + 1 > 2 ? 2 : ox + 1;
+                            const int n_dx = dx_hi - dx_lo + 1, kx_start = ox + 1 - dx_lo;
+                            const uint32_t idesc = instr_desc_16bit(128, C * n_dx, kBf16);
+                            const uint32_t a_view = a_stage + (py * 3 + px) * (2 * MID_WIN * 16) + (uint32_t)(MID_HALO + sy * p2.PW + sx) * 16;
+                            const uint32_t b_tap = w2_addr + ky * S2::W_KY_BYTES + 2 * ks * S2::LBO_B + (2 - kx_start) * C * 16;
+                            const uint64_t da = smem_desc(a_view, MID_WIN * 16, 128);
+                            const uint64_t db = smem_desc(b_tap, S2::LBO_B, 128);
+                            umma_16bit(tmem_base + C * (dy * 3 + dx_lo), da, db, idesc, (ks == 0 && ky == 0 && ox == 1) ? 0u : 1u);
+                        }
+                    }
+                    if (ks == KS - 1) umma_commit(&acc_full2[dy]);
+                    umma_commit(&empty[stage]);        // one of the three arrivals that free the stage
+                }
+                __syncwarp();
+                if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
+            }
+            acc_phase2 ^= 1;
+        }
+    };
+
     if (warp < 8) reg_alloc<RL::REGS_EPI>();
     else if (warp >= RL::WARPS - 4) reg_dealloc<RL::REGS_LIGHT>();
     else reg_dealloc<RL::REGS_UNFOLD>();
@@ -1753,7 +1799,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
             const int lw = warp - F1_LOAD_WARP0;
             const int n_loaders = min(LOADER_WARPS, n_slots);
             const uint64_t stream_once = l2_policy_evict_first();
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, acc_phase2 = 0;
             for (int it = 0; it < n_frames_cta; ++it) {
                 frame_begin(it);
                 if (lw < n_loaders) {
@@ -1796,13 +1842,16 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                             if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
+                } else if (lw == 1) {
+                    layer2_issue(std::integral_constant<int, 1>{}, it, stage, phase, acc_phase2);
+                } else {
+                    layer2_issue(std::integral_constant<int, 2>{}, it, stage, phase, acc_phase2);
                 }
                 frame_end(it);
             }
         } else {
-            // ------------------------------------------------------------------ MMA issuer of both layers
+            // ------------------------------------------------------------------ MMA issuer of layer 1 and of layer 2's block row 0
             const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
-            const uint32_t w2_addr = smem_u32(s_w2), stage_addr = smem_u32(s_stage);
             const uint32_t idesc1 = instr_desc_f16_acc16(128, 3 * C);
             uint32_t stage = 0, phase = 0, acc_phase2 = 0;
             for (int it = 0; it < n_frames_cta; ++it) {
@@ -1849,48 +1898,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                     mbar_wait(&tile_done[(n_tiles - 1) & (TILE_RING - 1)], ((n_tiles - 1) / TILE_RING) & 1);
                 }
                 phase_switch(it);
-                mbar_wait(w_full, it & 1);
-                for (int t2 = 0; t2 < tiles2; ++t2) {
-                    for (int ks = 0; ks < KS; ++ks) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after_sync();
-                        const uint32_t a_stage = stage_addr + stage * MID_STAGE_BYTES;
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
-                            if (ks == 0) {
-                                mbar_wait(&acc_empty2[dy], acc_phase2 ^ 1);
-                                tc_fence_after_sync();
-                            }
-                            if (elect_one()) {
-#pragma unroll
-                                for (int ky = 0; ky < 3; ++ky) {
-                                    const int oy = dy + ky - 1;
-                                    const int py = (oy + 3) % 3, sy = oy < 0 ? -1 : (oy > 2 ? 1 : 0);
-#pragma unroll
-                                    for (int o = 0; o < 5; ++o) {
-                                        const int ox = (o == 0) ? 1 : (o == 1) ? 0 : (o == 2) ? 2 : (o == 3) ? -1 : 3;
-                                        const int px = (ox + 3) % 3, sx = ox < 0 ? -1 : (ox > 2 ? 1 : 0);
-                                        const int dx_lo = ox - 1 < 0 ? 0 : ox - 1, dx_hi = ox + 1 > 2 ? 2 : ox + 1;
-                                        const int n_dx = dx_hi - dx_lo + 1, kx_start = ox + 1 - dx_lo;
-                                        const uint32_t idesc = instr_desc_16bit(128, C * n_dx, kBf16);
-                                        const uint32_t a_view = a_stage + (py * 3 + px) * (2 * MID_WIN * 16) +
-                                                                (uint32_t)(MID_HALO + sy * p2.PW + sx) * 16;
-                                        const uint32_t b_tap = w2_addr + ky * S2::W_KY_BYTES + 2 * ks * S2::LBO_B + (2 - kx_start) * C * 16;
-                                        const uint64_t da = smem_desc(a_view, MID_WIN * 16, 128);
-                                        const uint64_t db = smem_desc(b_tap, S2::LBO_B, 128);
-                                        umma_16bit(tmem_base + C * (dy * 3 + dx_lo), da, db, idesc, (ks == 0 && ky == 0 && ox == 1) ? 0u : 1u);
-                                    }
-                                }
-                                if (ks == KS - 1) umma_commit(&acc_full2[dy]);
-                            }
-                            __syncwarp();
-                        }
-                        if (elect_one()) umma_commit(&empty[stage]);
-                        __syncwarp();
-                        if (++stage == MID_STAGES) { stage = 0; phase ^= 1; }
-                    }
-                    acc_phase2 ^= 1;
-                }
+                layer2_issue(std::integral_constant<int, 0>{}, it, stage, phase, acc_phase2);
                 frame_end(it);
             }
         }
@@ -2495,7 +2503,7 @@ int launch_mid(const CUtensorMap &map, const MidParams &p, const char *name, cud
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
     {
         KernelScope scope(name, stream);
-        launch_pdl(pdl, conv_mid_tc_kernel<C>, grid, 320, MidSmem<C>::total, stream, map, p);
+        launch_pdl(pdl, conv_mid_tc_kernel<C>, grid, MID_THREADS, MidSmem<C>::total, stream, map, p);
     }
     CUTDET_LAUNCH_CHECK("conv_mid_tc_kernel");
     return CUTDET_OK;
