@@ -478,6 +478,8 @@ def run_game(rig: Rig):
     _cabi.check(lib.cutdet_profile_end(cbuf, 65536))
     kernels = json.loads(cbuf.value.decode())
     table, roofline = kernel_table(kernels, prof_steps, chunk, K1_SRC_BYTES_720P)
+    if roofline and roofline["kernel"] == "conv12_frames" and not rig.net_opts:
+        roofline["phases"] = frame_phases(rig, plan, pool[0])
 
     # ---------------- CPU baseline + whole-clip parity + the CLI on a file (rank 0, N = 1)
     cpu_baseline, cli = None, None
@@ -534,6 +536,55 @@ def run_game(rig: Rig):
             "cpu_baseline": cpu_baseline, "strong": strong, "cli": cli, "kernels": table, "parity": parity,
         }
         _emit(line)
+
+
+def frame_phases(rig: Rig, plan, frames):
+    """conv12_frames runs a frame's two layers as two disjoint phases per SM, so each phase has its own roofline.  One extra
+    call (outside every timed region) with the kernel's clock stamps armed (cutdet_net_debug_timeline, a caller-owned buffer):
+    CTA 0 stamps the phase changes with clock64 and every CTA its start and end with %globaltimer, which also gives the SM
+    clock the stamps were taken at.  8 frames per CTA (one 1,184-frame group)."""
+    import torch
+    from cutdet import _cabi
+    peaks = measured_peaks()
+    lib, native = rig.lib, rig.native
+    n = 8 * 148
+    stamps = torch.zeros(4096, dtype=torch.int64, device=rig.dev)
+    for _ in range(2):
+        native.forward_frames(plan, frames[:n])
+    torch.cuda.synchronize()
+    _cabi.check(lib.cutdet_net_debug_timeline(native.handle, 3, stamps.data_ptr(), 4096))
+    native.forward_frames(plan, frames[:n])
+    torch.cuda.synchronize()
+    _cabi.check(lib.cutdet_net_debug_timeline(native.handle, 0, None, 0))
+    h = stamps.cpu().tolist()
+    l1, l2, gap, it, prev = [], [], [], 0, h[0]
+    while 3 + 3 * it < 2048 and h[3 + 3 * it]:
+        b, m, e = h[1 + 3 * it], h[2 + 3 * it], h[3 + 3 * it]
+        if it > 0:                                  # the first frame's set-up includes the launch's one-time work
+            gap.append(b - prev)
+            l1.append(m - b)
+            l2.append(e - m)
+        prev = e
+        it += 1
+    if not l1:
+        return None
+    cycles = h[3 + 3 * (it - 1)] - h[0]
+    ns = h[2049] - h[2048]                          # CTA 0, %globaltimer
+    ghz = cycles / max(ns, 1)
+    avg = lambda v: sum(v) / len(v)
+    us1, us2 = avg(l1) / ghz / 1e3, avg(l2) / ghz / 1e3
+    sms = 148
+    return {"frames_per_cta": it, "sm_clock_ghz": round(ghz, 3),
+            "cycles_per_frame": {"phase_change": round(avg(gap)), "layer1": round(avg(l1)), "layer2": round(avg(l2))},
+            "layer1": {"us_per_frame_per_sm": round(us1, 2), "bound": "hbm",
+                       "achieved": K1_SRC_BYTES_720P * sms / (us1 * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": K1_SRC_BYTES_720P * sms / (us1 * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                       "tensor_tflops": FLOPS["L0"] * sms / (us1 * 1e-6) / 1e12},
+            "layer2": {"us_per_frame_per_sm": round(us2, 2), "bound": "tensor",
+                       "achieved": FLOPS["L1"] * sms / (us2 * 1e-6) / 1e12, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                       "frac": FLOPS["L1"] * sms / (us2 * 1e-6) / 1e12 / peaks["tflops_sustained"]},
+            "note": "every SM alternates between the phases, so a phase's rate is its per-frame work x 148 SMs / its time; "
+                    "layer 1 streams the source rows (HBM side), layer 2 is MMAs from the L2-resident slot"}
 
 
 def clip_runs(n: int):

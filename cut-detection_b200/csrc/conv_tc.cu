@@ -76,7 +76,11 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) { return kBf16 ? p
 // overrides it for such experiments.
 constexpr int SUB_BATCH = 148;
 constexpr int BATCHSTATS_MAX = 148;     // training-mode BatchNorm on the tensor-core path: one frame per CTA, everything resident
-constexpr int GROUP_FRAMES = 1184;      // frames whose layer-2 maps are gathered for ONE conv3 launch (fills the SMs)
+// Frames whose layer-2 maps are gathered for ONE launch of conv12_frames and ONE of conv3: 28 frames per CTA.  A 4,050-frame chunk is
+// then one launch of each instead of four (the same 28 rounds, but conv3's four ramps and drains become one: 0.116 -> 0.077 ms per
+// chunk, 2.53-2.55 -> 2.62-2.67 M frames/s in same-box 40-step runs); the layer-2 maps (52 KB per frame) go through HBM instead of
+// staying in the L2, which conv3 does not notice.
+constexpr int GROUP_FRAMES = 4144;
 constexpr int TMEM_COLS = 512;
 constexpr int MID_STAGES = 3;
 constexpr int MID_WIN = 192;            // positions per (plane, channel group) in a stage: 32 halo + 128 + 32 halo

@@ -151,7 +151,7 @@ CUTDET_API int cutdet_net_uses_tensor_cores(const cutdet_net *net, int height, i
 enum {
     CUTDET_OPT_CONV1_ACC32 = 1,  /* fused frames kernel: fp32 accumulators in layer 1 (default 0: fp16 accumulators)    */
     CUTDET_OPT_SUB_BATCH = 2,    /* frames per conv1/conv2 pass (default 0 = one frame per SM of a B200: 148)           */
-    CUTDET_OPT_GROUP_FRAMES = 3, /* frames gathered for one conv3 launch (default 0 = 1184)                             */
+    CUTDET_OPT_GROUP_FRAMES = 3, /* frames per conv12_frames / conv3 launch (default 0 = 4144 = 28 per SM)                    */
     CUTDET_OPT_NO_PDL = 4,       /* 1: ordinary launches instead of programmatic dependent launch                       */
     CUTDET_OPT_CONV1_GRID = 5,   /* test hook: cap on the fused conv1 grid (several frames per CTA); 0 = no cap         */
     CUTDET_OPT_CONV1_VARIANT = 6 /* which kernels run layers 1 and 2 of the fused frames path; all give the same bits.
