@@ -422,6 +422,11 @@ __device__ __forceinline__ void store_pixel16(uint4 *dst, int gtot, const uint32
 #pragma unroll
     for (int j = 0; j < C / 16; ++j) dst[(size_t)j * gtot] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
+template <int C>
+__device__ __forceinline__ void store_pixel16_hint(uint4 *dst, int gtot, const uint32_t (&v)[C / 4], uint64_t policy) {
+#pragma unroll
+    for (int j = 0; j < C / 16; ++j) st_global_v4_hint(dst + (size_t)j * gtot, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], policy);
+}
 
 // Zero the entries of frames [f_lo, f_hi) of a phase-split buffer that are not real pixels (the last row and/or the
 // last column of each plane, and the positions between the last row and the frame pitch): they are the zero padding the next
@@ -1929,6 +1934,8 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         const uint32_t tmem_thread = tmem_base + ((uint32_t)(q * 32) << 16) + half * 3 * CH;     // layer 1: columns [dy][half][dx][CH]
         const uint32_t tmem_thread2 = tmem_base + ((uint32_t)(q * 32) << 16) + ch0;              // layer 2: columns [dy][dx][C]
         uint32_t acc_phase2 = 0;
+        // the slot is read back by this CTA ~25 us after it is written: ask the L2 to keep it (the frames stream with evict_first)
+        const uint64_t keep_in_l2 = l2_policy_evict_last();
         // The kernel before this one (conv3 of the previous group, and through it the previous launch of this kernel) may still be
         // using the buffers written from here on.
         grid_dep_wait();
@@ -1963,7 +1970,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                         epi_issue_row16<C>(tmem_thread, 0, nxt);
                         requested = true;
                     }
-                    if (valid) store_pixel16<C>(dst, p.out.gtot, v);
+                    if (valid) store_pixel16_hint<C>(dst, p.out.gtot, v, keep_in_l2);
                     if (!requested) {
                         mbar_wait(&acc_full[0], acc_phase ^ 1);
                         tc_fence_after_sync();
