@@ -1656,8 +1656,12 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
     const int Hc = min(H, 3 * p.P1h + 1);
     const int slot_idx = blockIdx.x;                              // this CTA's frame slot of the layer-1 buffer
     const int n_frames_cta = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int n_tiles = (RPF * P1w + 127) / 128;                  // layer-1 tiles of ONE frame
-    const int total_u = 3 * RPF;
+    // Layer-1 tiles of ONE frame: its P1h pooled rows only.  (The continuous stream of conv1_fused_tc also walks the zero row between
+    // frames; here a frame stands alone, so the stream ends with the last real pooled row -- 32 tiles instead of 33 at 720p -- and
+    // the unfold stops after the one zero row below the image that this row's views read.  Positions past it in the operand ring
+    // hold stale data, which only reaches accumulator rows that are never stored.)
+    const int n_tiles = (p.P1h * P1w + 127) / 128;
+    const int total_u = 3 * p.P1h + 1;
     const int tiles2 = p2.FP / 128;                               // layer-2 tiles of one frame (the frame pitch is a multiple of 128)
     const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;
     const uint32_t inv_slots = 0xffffffffu / (uint32_t)n_slots + 1u;
