@@ -1599,6 +1599,14 @@ __global__ void __launch_bounds__(S2Roles::THREADS, 1) conv1_fused_sets_kernel(c
 // mbarriers and both layers' epilogue parameters live beyond layer 2's footprint and persist.  Layer 1 starts every frame from
 // zero (its counters and barrier phases are re-initialised: the pipeline is quiescent at a phase change); layer 2's barrier
 // phases simply run on from frame to frame.
+// Layer-1 issuers of conv12_frames: 1 = the issuer warp takes all three block rows and three warps load; 2 = the third loader
+// issues block row 2 instead (two loaders nominally sustain the frame stream: 2 x 10 B/clk against 12 B/clk needed at 720p).
+// Measured (-DCUTDET_F12_L1_ISSUERS=2, same box, 4,050 frames): 1.581 ms against 1.476 ms with 1 -- layer 1 loses more from the
+// slower row supply than it gains from the second issuer, so 1 it stays.
+#ifndef CUTDET_F12_L1_ISSUERS
+#define CUTDET_F12_L1_ISSUERS 1
+#endif
+constexpr int F12_L1_ISSUERS = CUTDET_F12_L1_ISSUERS, F12_L1_LOADERS = LOADER_WARPS - (F12_L1_ISSUERS - 1);
 template <int C>
 struct F12Smem {
     using S1 = F1Smem<C, F1Roles<true>::UNFOLD_WARPS>;
@@ -1729,7 +1737,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         {   // one barrier per thread (they were invalidated at the last phase change, see phase_switch)
             const int i = (int)threadIdx.x - 64;
             if (i >= 0 && i < L1_BARS) {
-                mbar_init(l1_bar(i), (i >= 3 && i < 6) ? EPI_WARPS : 1);
+                mbar_init(l1_bar(i), (i >= 3 && i < 6) ? EPI_WARPS : (i >= L1_BARS - TILE_RING ? F12_L1_ISSUERS : 1));
                 fence_barrier_init();
             }
         }
@@ -1758,6 +1766,53 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         __syncthreads();
         tc_fence_after_sync();
         if (tl && it < 600) tl[3 + 3 * it] = clock64();
+    };
+
+    // Layer 1's MMAs of block rows [DY_LO, DY_HI] over a frame's tiles (conv1_fused_tc_kernel's issuer loop).
+    auto layer1_issue = [&](auto lo_c, auto hi_c, int it) {
+        constexpr int DY_LO = decltype(lo_c)::value, DY_HI = decltype(hi_c)::value;
+        const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
+        const uint32_t idesc1 = instr_desc_f16_acc16(128, 3 * C);
+        uint32_t acc_phase = 0;
+        int r_hi = 127 / P1w, r_rem = 127 % P1w;
+        mbar_wait(w1_full, it & 1);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int u_hi = min(total_u - 1, 3 * (r_hi + 1));
+            r_rem += 128;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const bool c = r_rem >= P1w; r_rem -= c ? P1w : 0; r_hi += c ? 1 : 0; }
+            const int mine = lane % UNFOLD_WARPS;
+            const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
+            while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(32);
+            __syncwarp();
+            tc_fence_after_sync();
+            uint32_t a_chunk[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const int sub = (c + 2) % 3, shift = c == 0 ? -P1w : (c == 4 ? P1w : 0);
+                a_chunk[c] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
+            }
+#pragma unroll
+            for (int dy = DY_LO; dy <= DY_HI; ++dy) {
+                mbar_wait(&acc_empty[dy], acc_phase ^ 1);
+                tc_fence_after_sync();
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) {
+                        const uint64_t da = smem_desc(a_chunk[dy + ks], FR_PLANE, 128);
+                        const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
+                        umma_16bit(tmem_base + 3 * C * dy, da, db, idesc1, ks > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&acc_full[dy]);
+                    // tile t no longer reads the operand ring once every issuer's MMAs of it have completed
+                    if (dy == DY_HI) umma_commit(&tile_done[t & (TILE_RING - 1)]);
+                }
+                __syncwarp();
+            }
+            acc_phase ^= 1;
+        }
+        // the last commit has arrived (and with it every earlier one) before the barriers are invalidated
+        mbar_wait(&tile_done[(n_tiles - 1) & (TILE_RING - 1)], ((n_tiles - 1) / TILE_RING) & 1);
     };
 
     // Layer 2's MMAs of ONE block row dy over a frame's tiles.  Three warps issue, one per block row (the layer-1 issuer and the two
@@ -1810,12 +1865,14 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         if (warp >= F1_LOAD_WARP0) {
             // ------------------------------------------------------------------ loaders (layer 1); the first one is layer 2's TMA producer
             const int lw = warp - F1_LOAD_WARP0;
-            const int n_loaders = min(LOADER_WARPS, n_slots);
+            const int n_loaders = min(F12_L1_LOADERS, n_slots);
             const uint64_t stream_once = l2_policy_evict_first();
             uint32_t stage = 0, phase = 0, acc_phase2 = 0;
             for (int it = 0; it < n_frames_cta; ++it) {
                 frame_begin(it);
-                if (lw < n_loaders) {
+                if (F12_L1_ISSUERS == 2 && lw == 2) {
+                    layer1_issue(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}, it);
+                } else if (lw < n_loaders) {
                     const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)it * gridDim.x) * src.frame_stride;
                     int issued = 0;
                     for (int n = lw; n < Hc; n += n_loaders) {
@@ -1864,52 +1921,10 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
             }
         } else {
             // ------------------------------------------------------------------ MMA issuer of layer 1 and of layer 2's block row 0
-            const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
-            const uint32_t idesc1 = instr_desc_f16_acc16(128, 3 * C);
             uint32_t stage = 0, phase = 0, acc_phase2 = 0;
             for (int it = 0; it < n_frames_cta; ++it) {
                 frame_begin(it);
-                {
-                    uint32_t acc_phase = 0;
-                    int r_hi = 127 / P1w, r_rem = 127 % P1w;
-                    mbar_wait(w1_full, it & 1);
-                    for (int t = 0; t < n_tiles; ++t) {
-                        const int u_hi = min(total_u - 1, 3 * (r_hi + 1));
-                        r_rem += 128;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) { const bool c = r_rem >= P1w; r_rem -= c ? P1w : 0; r_hi += c ? 1 : 0; }
-                        const int mine = lane % UNFOLD_WARPS;
-                        const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
-                        while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(32);
-                        __syncwarp();
-                        tc_fence_after_sync();
-                        uint32_t a_chunk[5];
-#pragma unroll
-                        for (int c = 0; c < 5; ++c) {
-                            const int sub = (c + 2) % 3, shift = c == 0 ? -P1w : (c == 4 ? P1w : 0);
-                            a_chunk[c] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
-                        }
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
-                            mbar_wait(&acc_empty[dy], acc_phase ^ 1);
-                            tc_fence_after_sync();
-                            if (elect_one()) {
-#pragma unroll
-                                for (int ks = 0; ks < 3; ++ks) {
-                                    const uint64_t da = smem_desc(a_chunk[dy + ks], FR_PLANE, 128);
-                                    const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
-                                    umma_16bit(tmem_base + 3 * C * dy, da, db, idesc1, ks > 0 ? 1u : 0u);
-                                }
-                                umma_commit(&acc_full[dy]);
-                                if (dy == 2) umma_commit(&tile_done[t & (TILE_RING - 1)]);
-                            }
-                            __syncwarp();
-                        }
-                        acc_phase ^= 1;
-                    }
-                    // the last commit has arrived (and with it every earlier one) before the barriers are re-initialised
-                    mbar_wait(&tile_done[(n_tiles - 1) & (TILE_RING - 1)], ((n_tiles - 1) / TILE_RING) & 1);
-                }
+                layer1_issue(std::integral_constant<int, 0>{}, std::integral_constant<int, F12_L1_ISSUERS == 1 ? 2 : 1>{}, it);
                 phase_switch(it);
                 layer2_issue(std::integral_constant<int, 0>{}, it, stage, phase, acc_phase2);
                 frame_end(it);
@@ -1920,7 +1935,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         for (int it = 0; it < n_frames_cta; ++it) {
             frame_begin(it);
             F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
-                     RPF, Hc, total_u, n_slots, slot_bytes, min(LOADER_WARPS, n_slots), inv_slots, nullptr};
+                     RPF, Hc, total_u, n_slots, slot_bytes, min(F12_L1_LOADERS, n_slots), inv_slots, nullptr};
             f1_unfold_role<C, GATHER, true, UNFOLD_WARPS>(cx, warp - 8, lane);
             phase_switch(it);
             if (warp == 8 && it + 1 < n_frames_cta) {
@@ -2622,7 +2637,7 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
     }();
     if (!regs_ok) return CUTDET_EUNSUPPORTED;
     src.n_slots = (int)std::min<long long>(raw_bytes(F1Roles<true>::UNFOLD_WARPS) / ((long long)src.n_src * src.row_bytes), RAW_SLOTS_MAX);
-    src.n_slots -= src.n_slots % std::min(LOADER_WARPS, src.n_slots);
+    src.n_slots -= src.n_slots % std::min(F12_L1_LOADERS, src.n_slots);
     {
         KernelScope scope("conv12_frames", stream);
         const bool gather = src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0;
