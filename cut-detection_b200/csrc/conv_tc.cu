@@ -796,6 +796,7 @@ struct FusedSrc {
     int n_src;        // raw rows per resized row
     int row_bytes;    // 3 * src_w, a multiple of 16
     int n_slots;      // raw ring slots of n_src * row_bytes each (2 .. RAW_SLOTS_MAX)
+    int tma_shift;    // conv12_frames with a tensor map of the source rows: a slot holds 2^tma_shift rows, fetched by ONE TMA box; -1 = bulk copies
 };
 
 template <int C, int UW>
@@ -941,6 +942,7 @@ struct F1Ctx {
     int RPF, Hc, total_u, n_slots, slot_bytes, n_loaders;
     uint32_t inv_slots;
     long long *tl;
+    int rps_shift = 0;   // a raw slot holds 2^rps_shift rows (the loaders fetch and the barriers count whole slots)
 };
 
 template <int C, bool GATHER, bool ACC16, int UNFOLD_WARPS>
@@ -978,11 +980,11 @@ __device__ __forceinline__ void f1_unfold_role(const F1Ctx &cx, const int pwarp,
         while (py >= RPF) { py -= RPF; ++fi; }           // produced (ring space, source row landed), then advances
         const int y = 3 * py + sub;
         r.real = y < H && (py < p.P1h || sub == 0);      // index P1h: row 3*P1h if the image has it, else zeros
-        const int n = fi * Hc + y;
-        const int use = (int)__umulhi((uint32_t)n, inv_slots);
-        r.slot = n - use * n_slots;
+        const int n = fi * Hc + y, g = n >> cx.rps_shift;         // row, and the slot-sized group of rows it arrives with
+        const int use = (int)__umulhi((uint32_t)g, inv_slots);
+        r.slot = g - use * n_slots;
         r.R = R; r.sub = sub; y_out = y;
-        r.q0 = s_raw + r.slot * slot_bytes;
+        r.q0 = s_raw + ((r.slot << cx.rps_shift) + (n & ((1 << cx.rps_shift) - 1))) * slot_bytes;
         // positions [R*P1w, (R+1)*P1w) replace those FR_CAP earlier, last read by tile (pos - FR_CAP + P1w) / 128
         const int last_reader = ((R + 2) * P1w - 1 - FR_CAP) >> 7;      // arithmetic shift: negative = none
         if (last_reader >= tiles_waited) {
@@ -990,9 +992,10 @@ __device__ __forceinline__ void f1_unfold_role(const F1Ctx &cx, const int pwarp,
             tiles_waited = last_reader + 1;
         }
         if (r.real) {
-            int ld, want;                                // row n is loader n % n_loaders' (n / n_loaders + 1)-th
-            if (n_loaders == 3) { ld = n % 3; want = n / 3 + 1; }
-            else { ld = n & (n_loaders - 1); want = (n >> (n_loaders - 1)) + 1; }     // 1 or 2 loaders
+            int ld, want;                                // group g is loader g % n_loaders' (g / n_loaders + 1)-th
+            if (n_loaders == 3) { ld = g % 3; want = g / 3 + 1; }
+            else if (n_loaders <= 2) { ld = g & (n_loaders - 1); want = (g >> (n_loaders - 1)) + 1; }     // 1 or 2 loaders
+            else { ld = g % n_loaders; want = g / n_loaders + 1; }                    // several row streams per loader warp
             while (ld_acquire_shared(&s_rows_issued[ld]) < want) __nanosleep(32);
             mbar_wait(&raw_full[r.slot], use & 1);
         }
@@ -1606,7 +1609,37 @@ __global__ void __launch_bounds__(S2Roles::THREADS, 1) conv1_fused_sets_kernel(c
 #ifndef CUTDET_F12_L1_ISSUERS
 #define CUTDET_F12_L1_ISSUERS 1
 #endif
-constexpr int F12_L1_ISSUERS = CUTDET_F12_L1_ISSUERS, F12_L1_LOADERS = LOADER_WARPS - (F12_L1_ISSUERS - 1);
+// 3 = one issuer per block row: the issuer warp takes row 0, the last two of the eight unfold warps take rows 1 and 2 (six unfold
+// warps left; all three loaders stay).
+constexpr int F12_L1_ISSUERS = CUTDET_F12_L1_ISSUERS, F12_L1_LOADERS = F12_L1_ISSUERS == 2 ? LOADER_WARPS - 1 : LOADER_WARPS;
+// Row streams per loader warp: lanes 0 .. k-1 of a loader warp each issue their own rows (row n belongs to stream n % (3 k), which
+// is lane s / 3 of loader warp s % 3).  One lane per warp sustains a row per ~500 cycles at best and ~850 in steady state (wait,
+// expect_tx, bulk copy, release of the issue counter), which is exactly the pace layer 1 then runs at: the unfold warps consume
+// each row the moment it lands, ~2,300 cycles after its issue (profiles/r02_timeline_frames_detail.txt).
+#ifndef CUTDET_F12_STREAMS
+#define CUTDET_F12_STREAMS 1
+#endif
+constexpr int F12_STREAMS = CUTDET_F12_STREAMS, F12_MAX_STREAMS = 12;
+// Rows a loader issues per release of its issue counter (the release is a MEMBAR: the dearest instruction of the loop)
+#ifndef CUTDET_F12_LOAD_BATCH
+#define CUTDET_F12_LOAD_BATCH 1
+#endif
+constexpr int F12_LOAD_BATCH = CUTDET_F12_LOAD_BATCH;
+// Source rows of integer-scale gathers by TMA boxes of two rows instead of one bulk copy per row (0 = off, for A/B builds)
+#ifndef CUTDET_F12_SRC_TMA
+#define CUTDET_F12_SRC_TMA 1
+#endif
+constexpr bool F12_SRC_TMA = CUTDET_F12_SRC_TMA != 0;
+constexpr int F12_UNFOLD = F12_L1_ISSUERS == 3 ? F1Roles<true>::UNFOLD_WARPS - 2 : F1Roles<true>::UNFOLD_WARPS;
+// Layer-1 epilogue of conv12_frames: 0 = all eight warps read every tile (a warp = a TMEM lane quarter x a channel half); 1 = two
+// SETS of four warps (a thread takes all channels of its pixel) that alternate over the tiles, as in conv1_fused_sets_kernel: a
+// set's chain of TMEM reads, max, affine and store has two tile periods to complete, and block row dy of the next tile is issued
+// the moment the other set has handed row dy back.
+#ifndef CUTDET_F12_SETS
+#define CUTDET_F12_SETS 0
+#endif
+constexpr bool F12_SETS = CUTDET_F12_SETS != 0;
+constexpr int F12_NACC = F12_SETS ? 6 : 3;        // accumulator barriers per direction: [set][block row]
 template <int C>
 struct F12Smem {
     using S1 = F1Smem<C, F1Roles<true>::UNFOLD_WARPS>;
@@ -1615,13 +1648,14 @@ struct F12Smem {
     static constexpr int OFF_PAR2 = S1::total;                     // layer 2's bias / scale / shift
     static constexpr int total = OFF_PAR2 + 3 * C * 4;
     static_assert(S2::W_BYTES + MID_STAGES * MID_STAGE_BYTES <= S1::OFF_TAB, "layer 2's operands must end before the tables layer 1 keeps");
-    static_assert(2 * (3 + 3 + 2 * RAW_SLOTS_MAX + TILE_RING) * 4 + 8 + (F1Roles<true>::UNFOLD_WARPS + 4) * 4 <= 640, "layer 1's barrier block");
+    static_assert(2 * (2 * F12_NACC + 2 * RAW_SLOTS_MAX + TILE_RING) * 4 + 8 + (F1Roles<true>::UNFOLD_WARPS + F12_MAX_STREAMS) * 4 <= 640, "layer 1's barrier block");
     static_assert(total <= 232448, "227 KB of shared memory per CTA");
 };
 
 template <int C, bool GATHER>
 __global__ void __launch_bounds__(F1Roles<true>::THREADS, 1)
-conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_constant__ CUtensorMap in_map, const MidParams p2) {
+conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_constant__ CUtensorMap in_map, const MidParams p2,
+                     const __grid_constant__ CUtensorMap src_map) {
     using RL = F1Roles<true>;
     constexpr int UNFOLD_WARPS = RL::UNFOLD_WARPS, F1_MMA_WARP = RL::MMA_WARP0, F1_LOAD_WARP0 = RL::LOAD_WARP0;
     static_assert(RL::MMA_WARPS == 1, "one issuer for both layers");
@@ -1638,14 +1672,14 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
     int *s_yb = s_rowoff + 2 * F_MAX_DST;
     int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);
     uint32_t *s_cmp = reinterpret_cast<uint32_t *>(smem + S::OFF_CMP);
-    uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);
-    uint64_t *acc_empty = acc_full + 3;
-    uint64_t *raw_full = acc_empty + 3;
+    uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);      // [F12_NACC]
+    uint64_t *acc_empty = acc_full + F12_NACC;                                  // [F12_NACC]
+    uint64_t *raw_full = acc_empty + F12_NACC;
     uint64_t *raw_empty = raw_full + RAW_SLOTS_MAX;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + RAW_SLOTS_MAX);
     int *s_rows_done = reinterpret_cast<int *>(tmem_slot + 2);
-    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;
-    uint64_t *tile_done = reinterpret_cast<uint64_t *>(s_rows_issued + 4);
+    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;                           // [F12_MAX_STREAMS] rows issued by each row stream
+    uint64_t *tile_done = reinterpret_cast<uint64_t *>(s_rows_issued + F12_MAX_STREAMS);
     uint32_t *s_par = reinterpret_cast<uint32_t *>(smem + S::OFF_PAR);
     // ---- layer 2 (conv_mid_tc_kernel's operands over the same bytes; its barriers and parameters in the persistent tail)
     uint8_t *s_w2 = smem;
@@ -1671,8 +1705,15 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
     const int n_tiles = (p.P1h * P1w + 127) / 128;
     const int total_u = 3 * p.P1h + 1;
     const int tiles2 = p2.FP / 128;                               // layer-2 tiles of one frame (the frame pitch is a multiple of 128)
-    const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;
+    const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;    // (slot_bytes: one ROW's bytes in the ring)
     const uint32_t inv_slots = 0xffffffffu / (uint32_t)n_slots + 1u;
+    // Source rows by TMA (src.tma_shift >= 0; integer-scale gathers, whose rows are evenly spaced): a slot of the raw ring holds
+    // 2^tma_shift rows fetched by ONE box of src_map.  Why: a thread gets a bulk copy accepted every ~500 cycles and no faster
+    // (300 cycles for the instruction alone on an idle SM, profiles/r02_timeline_frames_detail.txt), so three loaders issuing one
+    // row each delivered 4.5 rows per ~1,400 cycles -- precisely the tile period of layer 1, whose unfold warps were seen to pick
+    // every row up the moment it landed.  With two rows per instruction the row supply has a factor 2 in hand.
+    const bool use_tma = src.tma_shift >= 0;
+    const int rps_shift = use_tma ? src.tma_shift : 0;
 
     // ---- once per launch: what survives the phases
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -1706,6 +1747,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         mbar_init(w1_full, 1);
         fence_barrier_init();
         tma_prefetch_desc(&in_map);
+        if (use_tma) tma_prefetch_desc(&src_map);
     }
     if (warp == F1_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before_sync();
@@ -1713,6 +1755,9 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     long long *tl = (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr;    // debug stamps of CTA 0
+    // ... and of its other roles during its THIRD frame (lane 0 of a warp): loaders [40 + row], unfold warp 0 [256 + 4 row ..],
+    // issuer [700 + 2 tile: rows there, + 1: issued], epilogue [800 + tile: stored]
+    long long *tlw = (p.timeline && blockIdx.x == 0 && lane == 0) ? p.timeline : nullptr;
     if (tl) tl[0] = clock64();
     if (p.timeline && threadIdx.x == 0) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); p.timeline[2048 + 2 * blockIdx.x] = g; }
     grid_dep_launch();
@@ -1723,7 +1768,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
     // __syncthreads of frame_end, and the issuer waits for its last commit.)
     const uint32_t Z2 = 0u, Z2K = 0x3c000000u;
     // layer 1's barriers: acc_full[3] | acc_empty[3] | raw_full | raw_empty are consecutive, tile_done follows the counters
-    constexpr int L1_BARS = 6 + 2 * RAW_SLOTS_MAX + TILE_RING;
+    constexpr int L1_BARS = 2 * F12_NACC + 2 * RAW_SLOTS_MAX + TILE_RING;
     auto l1_bar = [&](int i) { return i < L1_BARS - TILE_RING ? acc_full + i : tile_done + (i - (L1_BARS - TILE_RING)); };
     auto frame_begin = [&](int it) {
         if (threadIdx.x == 0) {            // layer 1's taps by bulk copy (the issuer waits for them before its first MMA)
@@ -1733,11 +1778,13 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
             reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
                 make_uint4(Z2, Z2, Z2, i >= P1w ? Z2K : Z2);
-        if (threadIdx.x < UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;    // ... and s_rows_issued
+        if (threadIdx.x < UNFOLD_WARPS + F12_MAX_STREAMS) s_rows_done[threadIdx.x] = 0;    // ... and s_rows_issued
         {   // one barrier per thread (they were invalidated at the last phase change, see phase_switch)
             const int i = (int)threadIdx.x - 64;
             if (i >= 0 && i < L1_BARS) {
-                mbar_init(l1_bar(i), (i >= 3 && i < 6) ? EPI_WARPS : (i >= L1_BARS - TILE_RING ? F12_L1_ISSUERS : 1));
+                const bool is_raw_empty = i >= 2 * F12_NACC + RAW_SLOTS_MAX && i < 2 * F12_NACC + 2 * RAW_SLOTS_MAX;
+                mbar_init(l1_bar(i), (i >= F12_NACC && i < 2 * F12_NACC) ? (F12_SETS ? 4 : EPI_WARPS)
+                                     : (i >= L1_BARS - TILE_RING ? F12_L1_ISSUERS : (is_raw_empty ? 1 << rps_shift : 1)));
                 fence_barrier_init();
             }
         }
@@ -1777,15 +1824,17 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         int r_hi = 127 / P1w, r_rem = 127 % P1w;
         mbar_wait(w1_full, it & 1);
         for (int t = 0; t < n_tiles; ++t) {
-            const int u_hi = min(total_u - 1, 3 * (r_hi + 1));
+            // block row dy reads input rows 3R - 1 + dy .. 3R + 1 + dy of pooled row R: resized rows up to u = 3 r_hi + 1 + dy
+            const int u_hi = min(total_u - 1, 3 * r_hi + 1 + DY_HI);
             r_rem += 128;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { const bool c = r_rem >= P1w; r_rem -= c ? P1w : 0; r_hi += c ? 1 : 0; }
-            const int mine = lane % UNFOLD_WARPS;
-            const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
+            const int mine = lane % F12_UNFOLD;
+            const int need = u_hi >= mine ? (u_hi - mine) / F12_UNFOLD + 1 : 0;
             while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(32);
             __syncwarp();
             tc_fence_after_sync();
+            if (tlw && it == 2 && DY_LO == 0 && t < 40) tlw[700 + 2 * t] = clock64();
             uint32_t a_chunk[5];
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
@@ -1794,7 +1843,12 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
             }
 #pragma unroll
             for (int dy = DY_LO; dy <= DY_HI; ++dy) {
-                mbar_wait(&acc_empty[dy], acc_phase ^ 1);
+                if constexpr (F12_SETS) {
+                    // block row dy was last filled for tile t - 1, which the OTHER set reads: its (t - 1) / 2-th tile
+                    if (t > 0) mbar_wait(&acc_empty[3 * ((t - 1) & 1) + dy], (uint32_t)((t - 1) >> 1) & 1u);
+                } else {
+                    mbar_wait(&acc_empty[dy], acc_phase ^ 1);
+                }
                 tc_fence_after_sync();
                 if (elect_one()) {
 #pragma unroll
@@ -1803,12 +1857,13 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                         const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
                         umma_16bit(tmem_base + 3 * C * dy, da, db, idesc1, ks > 0 ? 1u : 0u);
                     }
-                    umma_commit(&acc_full[dy]);
+                    umma_commit(&acc_full[F12_SETS ? 3 * (t & 1) + dy : dy]);
                     // tile t no longer reads the operand ring once every issuer's MMAs of it have completed
                     if (dy == DY_HI) umma_commit(&tile_done[t & (TILE_RING - 1)]);
                 }
                 __syncwarp();
             }
+            if (tlw && it == 2 && DY_LO == 0 && t < 40) tlw[701 + 2 * t] = clock64();
             acc_phase ^= 1;
         }
         // the last commit has arrived (and with it every earlier one) before the barriers are invalidated
@@ -1865,26 +1920,83 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         if (warp >= F1_LOAD_WARP0) {
             // ------------------------------------------------------------------ loaders (layer 1); the first one is layer 2's TMA producer
             const int lw = warp - F1_LOAD_WARP0;
-            const int n_loaders = min(F12_L1_LOADERS, n_slots);
+            const int n_loaders = min(F12_L1_LOADERS * F12_STREAMS, n_slots);         // row streams
             const uint64_t stream_once = l2_policy_evict_first();
             uint32_t stage = 0, phase = 0, acc_phase2 = 0;
             for (int it = 0; it < n_frames_cta; ++it) {
                 frame_begin(it);
                 if (F12_L1_ISSUERS == 2 && lw == 2) {
                     layer1_issue(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}, it);
-                } else if (lw < n_loaders) {
-                    const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)it * gridDim.x) * src.frame_stride;
-                    int issued = 0;
-                    for (int n = lw; n < Hc; n += n_loaders) {
-                        const int use = (int)__umulhi((uint32_t)n, inv_slots), slot = n - use * n_slots;
-                        mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
-                        ++issued;
-                        if (elect_one()) {
-                            mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
-                            for (int j = 0; j < src.n_src; ++j)
-                                bulk_load_1d_hint(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * n + j],
-                                                  (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
-                            st_release_shared(&s_rows_issued[lw], issued);
+                } else {
+                    if (use_tma) {
+                        // group g = rows [g << rps_shift, (g + 1) << rps_shift) of the frame: one TMA box, one slot, one barrier phase
+                        if (lw < n_loaders) {
+                            const int n_groups = (Hc + (1 << rps_shift) - 1) >> rps_shift, f_idx = blockIdx.x + it * gridDim.x;
+                            int issued = 0;
+                            for (int g = lw; g < n_groups; g += n_loaders) {
+                                const int use = (int)__umulhi((uint32_t)g, inv_slots), slot = g - use * n_slots;
+                                mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
+                                ++issued;
+                                if (tlw && it == 2 && (g << rps_shift) < 200) tlw[40 + (g << rps_shift)] = clock64();
+                                if (elect_one()) {
+                                    mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)(slot_bytes << rps_shift));
+                                    tma_load_4d_hint(s_raw + (slot << rps_shift) * slot_bytes, &src_map, &raw_full[slot], 0, 0, g << rps_shift, f_idx,
+                                                     stream_once);
+                                    st_release_shared(&s_rows_issued[lw], issued);
+                                }
+                                __syncwarp();
+                            }
+                        }
+                    } else if (F12_STREAMS == 1) {
+                        // one row stream per loader warp, issued by its elected lane; F12_LOAD_BATCH rows share one release of the counter
+                        if (lw < n_loaders) {
+                            const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)it * gridDim.x) * src.frame_stride;
+                            int issued = 0;
+                            for (int n = lw; n < Hc; n += F12_LOAD_BATCH * n_loaders) {
+#pragma unroll
+                                for (int b = 0; b < F12_LOAD_BATCH; ++b) {
+                                    const int nn = n + b * n_loaders;
+                                    if (nn < Hc) {
+                                        const int use = (int)__umulhi((uint32_t)nn, inv_slots), slot = nn - use * n_slots;
+                                        const bool st = tlw && it == 2 && lw == 0 && nn < 144;
+                                        if (st) tlw[1000 + nn] = clock64();                      // loader 0: before the slot wait
+                                        mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
+                                        ++issued;
+                                        if (tlw && it == 2 && nn < 200) tlw[40 + nn] = clock64();   // slot free
+                                        if (elect_one()) {
+                                            mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
+                                            for (int j = 0; j < src.n_src; ++j)
+                                                bulk_load_1d_hint(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * nn + j],
+                                                                  (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
+                                            if (st) tlw[1001 + nn] = clock64();                  // copy issued
+                                            if (F12_LOAD_BATCH == 1) st_release_shared(&s_rows_issued[lw], issued);
+                                            if (st) tlw[1002 + nn] = clock64();                  // counter released
+                                        }
+                                        __syncwarp();
+                                    }
+                                }
+                                if (F12_LOAD_BATCH > 1) {
+                                    if (elect_one()) st_release_shared(&s_rows_issued[lw], issued);
+                                    __syncwarp();
+                                }
+                            }
+                        }
+                    } else {
+                        // lane l of loader warp lw is row stream lw + 3 l
+                        const int stream = lw + F12_L1_LOADERS * lane;
+                        if (lane < F12_STREAMS && stream < n_loaders) {
+                            const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)it * gridDim.x) * src.frame_stride;
+                            int issued = 0;
+                            for (int n = stream; n < Hc; n += n_loaders) {
+                                const int use = (int)__umulhi((uint32_t)n, inv_slots), slot = n - use * n_slots;
+                                mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
+                                ++issued;
+                                mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
+                                for (int j = 0; j < src.n_src; ++j)
+                                    bulk_load_1d_hint(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * n + j],
+                                                      (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
+                                st_release_shared(&s_rows_issued[stream], issued);
+                            }
                         }
                         __syncwarp();
                     }
@@ -1924,7 +2036,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
             uint32_t stage = 0, phase = 0, acc_phase2 = 0;
             for (int it = 0; it < n_frames_cta; ++it) {
                 frame_begin(it);
-                layer1_issue(std::integral_constant<int, 0>{}, std::integral_constant<int, F12_L1_ISSUERS == 1 ? 2 : 1>{}, it);
+                layer1_issue(std::integral_constant<int, 0>{}, std::integral_constant<int, F12_L1_ISSUERS == 1 ? 2 : (F12_L1_ISSUERS == 2 ? 1 : 0)>{}, it);
                 phase_switch(it);
                 layer2_issue(std::integral_constant<int, 0>{}, it, stage, phase, acc_phase2);
                 frame_end(it);
@@ -1934,9 +2046,15 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         // ------------------------------------------------------------------ unfold (layer 1); idle during layer 2
         for (int it = 0; it < n_frames_cta; ++it) {
             frame_begin(it);
-            F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
-                     RPF, Hc, total_u, n_slots, slot_bytes, min(F12_L1_LOADERS, n_slots), inv_slots, nullptr};
-            f1_unfold_role<C, GATHER, true, UNFOLD_WARPS>(cx, warp - 8, lane);
+            if (F12_L1_ISSUERS == 3 && warp - 8 >= F12_UNFOLD) {
+                if (warp - 8 == F12_UNFOLD) layer1_issue(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{}, it);
+                else layer1_issue(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}, it);
+            } else {
+                F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
+                         RPF, Hc, total_u, n_slots, slot_bytes, min(F12_L1_LOADERS * F12_STREAMS, n_slots), inv_slots,
+                         (it == 2 && p.timeline && blockIdx.x == 0) ? p.timeline : nullptr, rps_shift};
+                f1_unfold_role<C, GATHER, true, F12_UNFOLD>(cx, warp - 8, lane);
+            }
             phase_switch(it);
             if (warp == 8 && it + 1 < n_frames_cta) {
                 // these warps idle while layer 2 runs: bring the first source rows of the next frame into the L2, so that layer 1
@@ -1968,7 +2086,53 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         }
         for (int it = 0; it < n_frames_cta; ++it) {
             frame_begin(it);
-            {
+            if constexpr (F12_SETS) {
+                // set s (warps 4s .. 4s + 3) takes tiles s, s + 2, ...; a thread is a TMEM lane (a pooled pixel) and ALL its channels
+                constexpr int NPK = C / 2, ROWPK = 3 * C / 2;
+                const int set = warp >> 2;
+                const uint32_t tm_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+                uint64_t *full1 = &acc_full[3 * set], *rel1 = &acc_empty[3 * set];
+                int X = (128 * set + m) % P1w, Y = (128 * set + m) / P1w;
+                const uint4 *sc4 = reinterpret_cast<const uint4 *>(s_par), *sh4 = reinterpret_cast<const uint4 *>(s_par + NPK);
+                uint32_t par = 0;
+                for (int t = set; t < n_tiles; t += 2, par ^= 1) {
+                    uint32_t run[NPK];
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        mbar_wait(&full1[dy], par);
+                        tc_fence_after_sync();
+                        uint32_t row[ROWPK], mx[NPK];
+                        row_load_all<C>(tm_lane + 3 * C * dy, row);
+                        tmem_ld_wait();
+                        reg_fence_u<ROWPK>(row);
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&rel1[dy]);                 // the next tile's MMAs of this block row may start
+                        row_max_dx<C>(row, mx);
+#pragma unroll
+                        for (int i = 0; i < NPK; ++i) run[i] = dy == 0 ? mx[i] : (dy == 1 ? hmax2(run[i], mx[i]) : hmax3(run[i], mx[i], 0u));   // ... and the ReLU
+                    }
+#pragma unroll
+                    for (int i = 0; i < NPK / 4; ++i) {                 // scale (+-2^k, exact) and BatchNorm shift
+                        const uint4 sc = sc4[i], sh = sh4[i];
+                        run[4 * i + 0] = hfma2(run[4 * i + 0], sc.x, sh.x);
+                        run[4 * i + 1] = hfma2(run[4 * i + 1], sc.y, sh.y);
+                        run[4 * i + 2] = hfma2(run[4 * i + 2], sc.z, sh.z);
+                        run[4 * i + 3] = hfma2(run[4 * i + 3], sc.w, sh.w);
+                    }
+                    if (Y < p.P1h) {
+                        const uint32_t off = (uint32_t)(((Y % 3) * 3 + X % 3) * CG) * (uint32_t)p.out.gtot +
+                                             (uint32_t)slot_idx * (uint32_t)p.out.FP + (uint32_t)((Y / 3) * p.out.PW + X / 3);
+                        uint4 *dst = reinterpret_cast<uint4 *>(p.out.ptr) + off;
+#pragma unroll
+                        for (int j = 0; j < CG; ++j)
+                            st_global_v4_hint(dst + (size_t)j * p.out.gtot, run[4 * j], run[4 * j + 1], run[4 * j + 2], run[4 * j + 3], keep_in_l2);
+                    }
+                    X += 256;                                              // this set's next tile: 64 <= P1w, at most four rows further
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) { const bool c = X >= P1w; X -= c ? P1w : 0; Y += c ? 1 : 0; }
+                }
+            } else {
                 uint32_t acc_phase = 0;
                 int X = m % P1w, Y = m / P1w;                          // position 128 t + m = Y * P1w + X of this frame
                 EpiRow16<CH> bufA, bufB;
@@ -1995,6 +2159,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                         tc_fence_after_sync();
                         epi_issue_row16<C>(tmem_thread, 0, nxt);
                     }
+                    if (tl && it == 2 && t < 40) tl[800 + t] = clock64();
                     acc_phase ^= 1;
                 };
                 for (int t = 0; t < n_tiles; t += 2) {
@@ -2316,6 +2481,25 @@ EncodeTiledFn encode_fn() {
 
 // A phase-split activation buffer as a 4-D tensor: (32 positions x 8 channels = 256 halves, block of 32 positions,
 // channel group, phase plane); the box is one plane's window of a tile: 6 blocks x 2 channel groups.
+// The source rows of `n_frames` frames as a 4-D tensor for conv12_frames' loaders: [frame][row][row_bytes / d0][d0 bytes], where the
+// rows are the evenly spaced ones an integer-scale gather reads; a box is `rows_per_box` whole rows, contiguous in shared memory.
+int make_src_map(CUtensorMap *map, const uint8_t *base, int row_bytes, long long row_stride, long long frame_stride, int n_rows,
+                 int n_frames, int rows_per_box) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(CUTDET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    int d0 = 256;
+    while (d0 > 16 && row_bytes % d0) d0 >>= 1;
+    if (row_bytes % d0 || row_bytes / d0 > 256) return CUTDET_EUNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)(row_bytes / d0), (cuuint64_t)n_rows, (cuuint64_t)n_frames};
+    cuuint64_t strides[3] = {(cuuint64_t)d0, (cuuint64_t)row_stride, (cuuint64_t)frame_stride};
+    cuuint32_t box[4] = {(cuuint32_t)d0, (cuuint32_t)(row_bytes / d0), (cuuint32_t)rows_per_box, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return CUTDET_EUNSUPPORTED;      // a shape the encoder refuses: the caller stays on bulk copies
+    return CUTDET_OK;
+}
+
 int make_act_map(CUtensorMap *map, void *base, int CG, int gtot) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(CUTDET_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -2525,6 +2709,7 @@ bool fused_source(const cutdet_resize_plan *plan, const cutdet_frames *frames, c
     out->n_src = n_src;
     out->row_bytes = (int)row_bytes;
     out->n_slots = (int)n_slots;
+    out->tma_shift = -1;
     return true;
 }
 
@@ -2637,13 +2822,30 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
     }();
     if (!regs_ok) return CUTDET_EUNSUPPORTED;
     src.n_slots = (int)std::min<long long>(raw_bytes(F1Roles<true>::UNFOLD_WARPS) / ((long long)src.n_src * src.row_bytes), RAW_SLOTS_MAX);
-    src.n_slots -= src.n_slots % std::min(F12_L1_LOADERS, src.n_slots);
+    src.n_slots -= src.n_slots % std::min(F12_L1_LOADERS * F12_STREAMS, src.n_slots);
+    const bool gather = src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0;
+    // Integer-scale gathers read evenly spaced source rows (row off_y + y * step_y; consecutive slots in compact frames): the
+    // loaders then fetch two rows per TMA instruction through a tensor map of this launch's frames (see the kernel).
+    CUtensorMap src_map;
+    memset(&src_map, 0, sizeof(src_map));
+    src.tma_shift = -1;
+    if (F12_SRC_TMA && gather && src.n_src == 1 && F12_STREAMS == 1 && F12_L1_ISSUERS != 2) {
+        const int shift = 1, rows_per_slot = 1 << shift;
+        int groups = (int)std::min<long long>(raw_bytes(F1Roles<true>::UNFOLD_WARPS) / ((long long)rows_per_slot * src.row_bytes), RAW_SLOTS_MAX);
+        groups -= groups % LOADER_WARPS;
+        const long long row_stride = src.compact ? src.row_pitch : (long long)src.plan.gather_step_y * src.row_pitch;
+        const uint8_t *base = src.frames + (src.compact ? 0 : (long long)src.plan.gather_off_y * src.row_pitch);
+        if (groups >= LOADER_WARPS && c1.H % rows_per_slot == 0 &&
+            make_src_map(&src_map, base, src.row_bytes, row_stride, src.frame_stride, c1.H, n, rows_per_slot) == CUTDET_OK) {
+            src.tma_shift = shift;
+            src.n_slots = groups;
+        }
+    }
     {
         KernelScope scope("conv12_frames", stream);
-        const bool gather = src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0;
         const bool pdl = f0 > 0 && !net->opt.no_pdl;        // the loaders read the frames at once: only behind a kernel of ours
-        if (gather) launch_pdl(pdl, conv12_frames_kernel<C, true>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2);
-        else launch_pdl(pdl, conv12_frames_kernel<C, false>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2);
+        if (gather) launch_pdl(pdl, conv12_frames_kernel<C, true>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2, src_map);
+        else launch_pdl(pdl, conv12_frames_kernel<C, false>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2, src_map);
     }
     CUTDET_LAUNCH_CHECK("conv12_frames_kernel");
     return CUTDET_OK;

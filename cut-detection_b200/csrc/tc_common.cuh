@@ -113,6 +113,15 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         "r"(c3)
         : "memory");
 }
+// ... with an L2 eviction policy
+__device__ __forceinline__ void tma_load_4d_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                                 int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "l"(policy)
+        : "memory");
+}
 // 1-D bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16), completion on an mbarrier.
 __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -56,6 +56,29 @@ def main():
                 f.write(f"{it}: {b} {m} {e} | setup {b - prev} layer1 {m - b} layer2 {e - m}\n")
                 prev = e
                 it += 1
+            if it > 2 and h[700]:
+                # the third frame in detail (cycles since its layer 1 was set up)
+                f0 = h[1 + 3 * 2]
+                f.write("# third frame, layer 1: tile: rows_there issued stored | period\n")
+                t = 0
+                while t < 40 and h[700 + 2 * t]:
+                    f.write(f"tile {t}: {h[700 + 2 * t] - f0} {h[701 + 2 * t] - f0} {h[800 + t] - f0} | {h[700 + 2 * t] - h[700 + 2 * (t - 1)] if t else 0}\n")
+                    t += 1
+                f.write("# loaders: row: issued (after its slot was free)\n")
+                f.write(" ".join(f"{n}:{h[40 + n] - f0}" for n in range(0, 200) if h[40 + n]) + "\n")
+                f.write("# loader 0, its rows: row: before_wait (+wait) (+issue) (+release) | period\n")
+                prev = None
+                for n in range(0, 144, 3):
+                    if h[1000 + n]:
+                        a0 = h[1000 + n]
+                        f.write(f"lrow {n}: {a0 - f0} +{h[40 + n] - a0} +{h[1001 + n] - h[40 + n]} +{h[1002 + n] - h[1001 + n]} | {a0 - prev if prev else 0}\n")
+                        prev = a0
+                f.write("# unfold warp 0: its k-th row: start, wait for ring space and source row, work, fence\n")
+                k = 0
+                while k < 30 and h[256 + 4 * k]:
+                    a0, b0, c0, d0 = (h[256 + 4 * k + j] for j in range(4))
+                    f.write(f"urow {k}: start {a0 - f0} wait {b0 - a0} work {c0 - b0} fence {d0 - c0}\n")
+                    k += 1
             g0 = min(v for v in h[2048::2] if v)
             for b in range(148):
                 if h[2048 + 2 * b]:
