@@ -994,8 +994,7 @@ __device__ __forceinline__ void f1_unfold_role(const F1Ctx &cx, const int pwarp,
         if (r.real) {
             int ld, want;                                // group g is loader g % n_loaders' (g / n_loaders + 1)-th
             if (n_loaders == 3) { ld = g % 3; want = g / 3 + 1; }
-            else if (n_loaders <= 2) { ld = g & (n_loaders - 1); want = (g >> (n_loaders - 1)) + 1; }     // 1 or 2 loaders
-            else { ld = g % n_loaders; want = g / n_loaders + 1; }                    // several row streams per loader warp
+            else { ld = g & (n_loaders - 1); want = (g >> (n_loaders - 1)) + 1; }     // 1 or 2 loaders
             while (ld_acquire_shared(&s_rows_issued[ld]) < want) __nanosleep(32);
             mbar_wait(&raw_full[r.slot], use & 1);
         }
@@ -1602,44 +1601,18 @@ __global__ void __launch_bounds__(S2Roles::THREADS, 1) conv1_fused_sets_kernel(c
 // mbarriers and both layers' epilogue parameters live beyond layer 2's footprint and persist.  Layer 1 starts every frame from
 // zero (its counters and barrier phases are re-initialised: the pipeline is quiescent at a phase change); layer 2's barrier
 // phases simply run on from frame to frame.
-// Layer-1 issuers of conv12_frames: 1 = the issuer warp takes all three block rows and three warps load; 2 = the third loader
-// issues block row 2 instead (two loaders nominally sustain the frame stream: 2 x 10 B/clk against 12 B/clk needed at 720p).
-// Measured (-DCUTDET_F12_L1_ISSUERS=2, same box, 4,050 frames): 1.581 ms against 1.476 ms with 1 -- layer 1 loses more from the
-// slower row supply than it gains from the second issuer, so 1 it stays.
-#ifndef CUTDET_F12_L1_ISSUERS
-#define CUTDET_F12_L1_ISSUERS 1
-#endif
-// 3 = one issuer per block row: the issuer warp takes row 0, the last two of the eight unfold warps take rows 1 and 2 (six unfold
-// warps left; all three loaders stay).
-constexpr int F12_L1_ISSUERS = CUTDET_F12_L1_ISSUERS, F12_L1_LOADERS = F12_L1_ISSUERS == 2 ? LOADER_WARPS - 1 : LOADER_WARPS;
-// Row streams per loader warp: lanes 0 .. k-1 of a loader warp each issue their own rows (row n belongs to stream n % (3 k), which
-// is lane s / 3 of loader warp s % 3).  One lane per warp sustains a row per ~500 cycles at best and ~850 in steady state (wait,
-// expect_tx, bulk copy, release of the issue counter), which is exactly the pace layer 1 then runs at: the unfold warps consume
-// each row the moment it lands, ~2,300 cycles after its issue (profiles/r02_timeline_frames_detail.txt).
-#ifndef CUTDET_F12_STREAMS
-#define CUTDET_F12_STREAMS 1
-#endif
-constexpr int F12_STREAMS = CUTDET_F12_STREAMS, F12_MAX_STREAMS = 12;
-// Rows a loader issues per release of its issue counter (the release is a MEMBAR: the dearest instruction of the loop)
-#ifndef CUTDET_F12_LOAD_BATCH
-#define CUTDET_F12_LOAD_BATCH 1
-#endif
-constexpr int F12_LOAD_BATCH = CUTDET_F12_LOAD_BATCH;
-// Source rows of integer-scale gathers by TMA boxes of two rows instead of one bulk copy per row (0 = off, for A/B builds)
-#ifndef CUTDET_F12_SRC_TMA
-#define CUTDET_F12_SRC_TMA 1
-#endif
-constexpr bool F12_SRC_TMA = CUTDET_F12_SRC_TMA != 0;
-constexpr int F12_UNFOLD = F12_L1_ISSUERS == 3 ? F1Roles<true>::UNFOLD_WARPS - 2 : F1Roles<true>::UNFOLD_WARPS;
-// Layer-1 epilogue of conv12_frames: 0 = all eight warps read every tile (a warp = a TMEM lane quarter x a channel half); 1 = two
-// SETS of four warps (a thread takes all channels of its pixel) that alternate over the tiles, as in conv1_fused_sets_kernel: a
-// set's chain of TMEM reads, max, affine and store has two tile periods to complete, and block row dy of the next tile is issued
-// the moment the other set has handed row dy back.
-#ifndef CUTDET_F12_SETS
-#define CUTDET_F12_SETS 0
-#endif
-constexpr bool F12_SETS = CUTDET_F12_SETS != 0;
-constexpr int F12_NACC = F12_SETS ? 6 : 3;        // accumulator barriers per direction: [set][block row]
+// What was tried on layer 1 of conv12_frames and measured on one box (4,050 frames 720p, ms per call; all variants bit-equal;
+// profiles/README.md, round 2), before and after the loaders moved to TMA boxes of two rows:
+//   one issuer, eight epilogue warps on every tile, three loaders, one row per bulk copy ............ 1.449 -> 1.418 with TMA rows
+//   the third loader issues block row 2 instead (two loaders) ...................................... 1.581
+//   two epilogue SETS of four warps alternating over the tiles (as conv1_fused_sets_kernel) ........ 1.457 -> 1.427 with TMA rows
+//   an issuer per block row (two of the eight unfold warps issue) .................................. 1.462 -> 1.506 with TMA rows
+//   both ............................................................................................ 1.475 -> 1.508 with TMA rows
+//   two / three row streams per loader warp (lanes issuing their own rows) ......................... 1.522 / 1.521 (base 1.556 in that build)
+//   two / four rows per release of a loader's issue counter ........................................ 1.484 / 1.494 (base 1.457)
+// Only the row supply moved the number: a thread gets a bulk copy accepted every ~500 cycles, so three loaders with one row per copy
+// delivered 4.5 rows per ~1,400 cycles, exactly the tile period; with that lifted the stages are balanced again (fewer unfold
+// warps or fewer loaders cost time, more issuers or epilogue sets gain none).
 template <int C>
 struct F12Smem {
     using S1 = F1Smem<C, F1Roles<true>::UNFOLD_WARPS>;
@@ -1648,7 +1621,7 @@ struct F12Smem {
     static constexpr int OFF_PAR2 = S1::total;                     // layer 2's bias / scale / shift
     static constexpr int total = OFF_PAR2 + 3 * C * 4;
     static_assert(S2::W_BYTES + MID_STAGES * MID_STAGE_BYTES <= S1::OFF_TAB, "layer 2's operands must end before the tables layer 1 keeps");
-    static_assert(2 * (2 * F12_NACC + 2 * RAW_SLOTS_MAX + TILE_RING) * 4 + 8 + (F1Roles<true>::UNFOLD_WARPS + F12_MAX_STREAMS) * 4 <= 640, "layer 1's barrier block");
+    static_assert(2 * (6 + 2 * RAW_SLOTS_MAX + TILE_RING) * 4 + 8 + (F1Roles<true>::UNFOLD_WARPS + 4) * 4 <= 640, "layer 1's barrier block");
     static_assert(total <= 232448, "227 KB of shared memory per CTA");
 };
 
@@ -1672,14 +1645,14 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
     int *s_yb = s_rowoff + 2 * F_MAX_DST;
     int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);
     uint32_t *s_cmp = reinterpret_cast<uint32_t *>(smem + S::OFF_CMP);
-    uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);      // [F12_NACC]
-    uint64_t *acc_empty = acc_full + F12_NACC;                                  // [F12_NACC]
-    uint64_t *raw_full = acc_empty + F12_NACC;
+    uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem + S::OFF_BAR);
+    uint64_t *acc_empty = acc_full + 3;
+    uint64_t *raw_full = acc_empty + 3;
     uint64_t *raw_empty = raw_full + RAW_SLOTS_MAX;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + RAW_SLOTS_MAX);
     int *s_rows_done = reinterpret_cast<int *>(tmem_slot + 2);
-    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;                           // [F12_MAX_STREAMS] rows issued by each row stream
-    uint64_t *tile_done = reinterpret_cast<uint64_t *>(s_rows_issued + F12_MAX_STREAMS);
+    int *s_rows_issued = s_rows_done + UNFOLD_WARPS;                           // [LOADER_WARPS] slots issued by each loader
+    uint64_t *tile_done = reinterpret_cast<uint64_t *>(s_rows_issued + 4);
     uint32_t *s_par = reinterpret_cast<uint32_t *>(smem + S::OFF_PAR);
     // ---- layer 2 (conv_mid_tc_kernel's operands over the same bytes; its barriers and parameters in the persistent tail)
     uint8_t *s_w2 = smem;
@@ -1768,7 +1741,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
     // __syncthreads of frame_end, and the issuer waits for its last commit.)
     const uint32_t Z2 = 0u, Z2K = 0x3c000000u;
     // layer 1's barriers: acc_full[3] | acc_empty[3] | raw_full | raw_empty are consecutive, tile_done follows the counters
-    constexpr int L1_BARS = 2 * F12_NACC + 2 * RAW_SLOTS_MAX + TILE_RING;
+    constexpr int L1_BARS = 6 + 2 * RAW_SLOTS_MAX + TILE_RING;
     auto l1_bar = [&](int i) { return i < L1_BARS - TILE_RING ? acc_full + i : tile_done + (i - (L1_BARS - TILE_RING)); };
     auto frame_begin = [&](int it) {
         if (threadIdx.x == 0) {            // layer 1's taps by bulk copy (the issuer waits for them before its first MMA)
@@ -1778,13 +1751,12 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
             reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
                 make_uint4(Z2, Z2, Z2, i >= P1w ? Z2K : Z2);
-        if (threadIdx.x < UNFOLD_WARPS + F12_MAX_STREAMS) s_rows_done[threadIdx.x] = 0;    // ... and s_rows_issued
+        if (threadIdx.x < UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;    // ... and s_rows_issued
         {   // one barrier per thread (they were invalidated at the last phase change, see phase_switch)
             const int i = (int)threadIdx.x - 64;
             if (i >= 0 && i < L1_BARS) {
-                const bool is_raw_empty = i >= 2 * F12_NACC + RAW_SLOTS_MAX && i < 2 * F12_NACC + 2 * RAW_SLOTS_MAX;
-                mbar_init(l1_bar(i), (i >= F12_NACC && i < 2 * F12_NACC) ? (F12_SETS ? 4 : EPI_WARPS)
-                                     : (i >= L1_BARS - TILE_RING ? F12_L1_ISSUERS : (is_raw_empty ? 1 << rps_shift : 1)));
+                const bool is_raw_empty = i >= 6 + RAW_SLOTS_MAX && i < 6 + 2 * RAW_SLOTS_MAX;
+                mbar_init(l1_bar(i), (i >= 3 && i < 6) ? EPI_WARPS : (is_raw_empty ? 1 << rps_shift : 1));
                 fence_barrier_init();
             }
         }
@@ -1815,26 +1787,25 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         if (tl && it < 600) tl[3 + 3 * it] = clock64();
     };
 
-    // Layer 1's MMAs of block rows [DY_LO, DY_HI] over a frame's tiles (conv1_fused_tc_kernel's issuer loop).
-    auto layer1_issue = [&](auto lo_c, auto hi_c, int it) {
-        constexpr int DY_LO = decltype(lo_c)::value, DY_HI = decltype(hi_c)::value;
+    // Layer 1's MMAs over a frame's tiles (conv1_fused_tc_kernel's issuer loop).
+    auto layer1_issue = [&](int it) {
         const uint32_t w_addr = smem_u32(s_w), ring_addr = smem_u32(s_ring);
         const uint32_t idesc1 = instr_desc_f16_acc16(128, 3 * C);
         uint32_t acc_phase = 0;
         int r_hi = 127 / P1w, r_rem = 127 % P1w;
         mbar_wait(w1_full, it & 1);
         for (int t = 0; t < n_tiles; ++t) {
-            // block row dy reads input rows 3R - 1 + dy .. 3R + 1 + dy of pooled row R: resized rows up to u = 3 r_hi + 1 + dy
-            const int u_hi = min(total_u - 1, 3 * r_hi + 1 + DY_HI);
+            // rows of sub-rings 1 and 2 up to pooled row (128 t + 127) / P1w, of sub-ring 0 one pooled row further
+            const int u_hi = min(total_u - 1, 3 * (r_hi + 1));
             r_rem += 128;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { const bool c = r_rem >= P1w; r_rem -= c ? P1w : 0; r_hi += c ? 1 : 0; }
-            const int mine = lane % F12_UNFOLD;
-            const int need = u_hi >= mine ? (u_hi - mine) / F12_UNFOLD + 1 : 0;
+            const int mine = lane % UNFOLD_WARPS;
+            const int need = u_hi >= mine ? (u_hi - mine) / UNFOLD_WARPS + 1 : 0;
             while (!__all_sync(0xffffffffu, ld_acquire_shared(&s_rows_done[mine]) >= need)) __nanosleep(32);
             __syncwarp();
             tc_fence_after_sync();
-            if (tlw && it == 2 && DY_LO == 0 && t < 40) tlw[700 + 2 * t] = clock64();
+            if (tlw && it == 2 && t < 40) tlw[700 + 2 * t] = clock64();
             uint32_t a_chunk[5];
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
@@ -1842,13 +1813,8 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                 a_chunk[c] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
             }
 #pragma unroll
-            for (int dy = DY_LO; dy <= DY_HI; ++dy) {
-                if constexpr (F12_SETS) {
-                    // block row dy was last filled for tile t - 1, which the OTHER set reads: its (t - 1) / 2-th tile
-                    if (t > 0) mbar_wait(&acc_empty[3 * ((t - 1) & 1) + dy], (uint32_t)((t - 1) >> 1) & 1u);
-                } else {
-                    mbar_wait(&acc_empty[dy], acc_phase ^ 1);
-                }
+            for (int dy = 0; dy < 3; ++dy) {
+                mbar_wait(&acc_empty[dy], acc_phase ^ 1);
                 tc_fence_after_sync();
                 if (elect_one()) {
 #pragma unroll
@@ -1857,13 +1823,12 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                         const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
                         umma_16bit(tmem_base + 3 * C * dy, da, db, idesc1, ks > 0 ? 1u : 0u);
                     }
-                    umma_commit(&acc_full[F12_SETS ? 3 * (t & 1) + dy : dy]);
-                    // tile t no longer reads the operand ring once every issuer's MMAs of it have completed
-                    if (dy == DY_HI) umma_commit(&tile_done[t & (TILE_RING - 1)]);
+                    umma_commit(&acc_full[dy]);
+                    if (dy == 2) umma_commit(&tile_done[t & (TILE_RING - 1)]);   // tile t no longer reads the operand ring
                 }
                 __syncwarp();
             }
-            if (tlw && it == 2 && DY_LO == 0 && t < 40) tlw[701 + 2 * t] = clock64();
+            if (tlw && it == 2 && t < 40) tlw[701 + 2 * t] = clock64();
             acc_phase ^= 1;
         }
         // the last commit has arrived (and with it every earlier one) before the barriers are invalidated
@@ -1920,85 +1885,47 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         if (warp >= F1_LOAD_WARP0) {
             // ------------------------------------------------------------------ loaders (layer 1); the first one is layer 2's TMA producer
             const int lw = warp - F1_LOAD_WARP0;
-            const int n_loaders = min(F12_L1_LOADERS * F12_STREAMS, n_slots);         // row streams
+            const int n_loaders = min(LOADER_WARPS, n_slots);
             const uint64_t stream_once = l2_policy_evict_first();
             uint32_t stage = 0, phase = 0, acc_phase2 = 0;
             for (int it = 0; it < n_frames_cta; ++it) {
                 frame_begin(it);
-                if (F12_L1_ISSUERS == 2 && lw == 2) {
-                    layer1_issue(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}, it);
-                } else {
+                if (lw < n_loaders) {
                     if (use_tma) {
                         // group g = rows [g << rps_shift, (g + 1) << rps_shift) of the frame: one TMA box, one slot, one barrier phase
-                        if (lw < n_loaders) {
-                            const int n_groups = (Hc + (1 << rps_shift) - 1) >> rps_shift, f_idx = blockIdx.x + it * gridDim.x;
-                            int issued = 0;
-                            for (int g = lw; g < n_groups; g += n_loaders) {
-                                const int use = (int)__umulhi((uint32_t)g, inv_slots), slot = g - use * n_slots;
-                                mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
-                                ++issued;
-                                if (tlw && it == 2 && (g << rps_shift) < 200) tlw[40 + (g << rps_shift)] = clock64();
-                                if (elect_one()) {
-                                    mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)(slot_bytes << rps_shift));
-                                    tma_load_4d_hint(s_raw + (slot << rps_shift) * slot_bytes, &src_map, &raw_full[slot], 0, 0, g << rps_shift, f_idx,
-                                                     stream_once);
-                                    st_release_shared(&s_rows_issued[lw], issued);
-                                }
-                                __syncwarp();
+                        const int n_groups = (Hc + (1 << rps_shift) - 1) >> rps_shift, f_idx = blockIdx.x + it * gridDim.x;
+                        int issued = 0;
+                        for (int g = lw; g < n_groups; g += n_loaders) {
+                            const int use = (int)__umulhi((uint32_t)g, inv_slots), slot = g - use * n_slots;
+                            mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
+                            ++issued;
+                            if (tlw && it == 2 && (g << rps_shift) < 200) tlw[40 + (g << rps_shift)] = clock64();
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)(slot_bytes << rps_shift));
+                                tma_load_4d_hint(s_raw + (slot << rps_shift) * slot_bytes, &src_map, &raw_full[slot], 0, 0, g << rps_shift, f_idx,
+                                                 stream_once);
+                                st_release_shared(&s_rows_issued[lw], issued);   // raw_full[slot] is now in group g's phase
                             }
-                        }
-                    } else if (F12_STREAMS == 1) {
-                        // one row stream per loader warp, issued by its elected lane; F12_LOAD_BATCH rows share one release of the counter
-                        if (lw < n_loaders) {
-                            const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)it * gridDim.x) * src.frame_stride;
-                            int issued = 0;
-                            for (int n = lw; n < Hc; n += F12_LOAD_BATCH * n_loaders) {
-#pragma unroll
-                                for (int b = 0; b < F12_LOAD_BATCH; ++b) {
-                                    const int nn = n + b * n_loaders;
-                                    if (nn < Hc) {
-                                        const int use = (int)__umulhi((uint32_t)nn, inv_slots), slot = nn - use * n_slots;
-                                        const bool st = tlw && it == 2 && lw == 0 && nn < 144;
-                                        if (st) tlw[1000 + nn] = clock64();                      // loader 0: before the slot wait
-                                        mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
-                                        ++issued;
-                                        if (tlw && it == 2 && nn < 200) tlw[40 + nn] = clock64();   // slot free
-                                        if (elect_one()) {
-                                            mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
-                                            for (int j = 0; j < src.n_src; ++j)
-                                                bulk_load_1d_hint(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * nn + j],
-                                                                  (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
-                                            if (st) tlw[1001 + nn] = clock64();                  // copy issued
-                                            if (F12_LOAD_BATCH == 1) st_release_shared(&s_rows_issued[lw], issued);
-                                            if (st) tlw[1002 + nn] = clock64();                  // counter released
-                                        }
-                                        __syncwarp();
-                                    }
-                                }
-                                if (F12_LOAD_BATCH > 1) {
-                                    if (elect_one()) st_release_shared(&s_rows_issued[lw], issued);
-                                    __syncwarp();
-                                }
-                            }
+                            __syncwarp();
                         }
                     } else {
-                        // lane l of loader warp lw is row stream lw + 3 l
-                        const int stream = lw + F12_L1_LOADERS * lane;
-                        if (lane < F12_STREAMS && stream < n_loaders) {
-                            const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)it * gridDim.x) * src.frame_stride;
-                            int issued = 0;
-                            for (int n = stream; n < Hc; n += n_loaders) {
-                                const int use = (int)__umulhi((uint32_t)n, inv_slots), slot = n - use * n_slots;
-                                mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
-                                ++issued;
+                        // one bulk copy per source row (two for a bilinear resize), row n issued by loader n % n_loaders
+                        const uint8_t *frame = src.frames + (long long)(blockIdx.x + (long long)it * gridDim.x) * src.frame_stride;
+                        int issued = 0;
+                        for (int n = lw; n < Hc; n += n_loaders) {
+                            const int use = (int)__umulhi((uint32_t)n, inv_slots), slot = n - use * n_slots;
+                            mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
+                            ++issued;
+                            if (tlw && it == 2 && n < 200) tlw[40 + n] = clock64();
+                            if (elect_one()) {
                                 mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)slot_bytes);
                                 for (int j = 0; j < src.n_src; ++j)
                                     bulk_load_1d_hint(s_raw + slot * slot_bytes + j * src.row_bytes, frame + s_rowoff[2 * n + j],
                                                       (uint32_t)src.row_bytes, &raw_full[slot], stream_once);
-                                st_release_shared(&s_rows_issued[stream], issued);
+                                st_release_shared(&s_rows_issued[lw], issued);
                             }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                 }
                 phase_switch(it);
@@ -2036,7 +1963,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
             uint32_t stage = 0, phase = 0, acc_phase2 = 0;
             for (int it = 0; it < n_frames_cta; ++it) {
                 frame_begin(it);
-                layer1_issue(std::integral_constant<int, 0>{}, std::integral_constant<int, F12_L1_ISSUERS == 1 ? 2 : (F12_L1_ISSUERS == 2 ? 1 : 0)>{}, it);
+                layer1_issue(it);
                 phase_switch(it);
                 layer2_issue(std::integral_constant<int, 0>{}, it, stage, phase, acc_phase2);
                 frame_end(it);
@@ -2046,14 +1973,11 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         // ------------------------------------------------------------------ unfold (layer 1); idle during layer 2
         for (int it = 0; it < n_frames_cta; ++it) {
             frame_begin(it);
-            if (F12_L1_ISSUERS == 3 && warp - 8 >= F12_UNFOLD) {
-                if (warp - 8 == F12_UNFOLD) layer1_issue(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{}, it);
-                else layer1_issue(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}, it);
-            } else {
+            {
                 F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
-                         RPF, Hc, total_u, n_slots, slot_bytes, min(F12_L1_LOADERS * F12_STREAMS, n_slots), inv_slots,
+                         RPF, Hc, total_u, n_slots, slot_bytes, min(LOADER_WARPS, n_slots), inv_slots,
                          (it == 2 && p.timeline && blockIdx.x == 0) ? p.timeline : nullptr, rps_shift};
-                f1_unfold_role<C, GATHER, true, F12_UNFOLD>(cx, warp - 8, lane);
+                f1_unfold_role<C, GATHER, true, UNFOLD_WARPS>(cx, warp - 8, lane);
             }
             phase_switch(it);
             if (warp == 8 && it + 1 < n_frames_cta) {
@@ -2086,53 +2010,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         }
         for (int it = 0; it < n_frames_cta; ++it) {
             frame_begin(it);
-            if constexpr (F12_SETS) {
-                // set s (warps 4s .. 4s + 3) takes tiles s, s + 2, ...; a thread is a TMEM lane (a pooled pixel) and ALL its channels
-                constexpr int NPK = C / 2, ROWPK = 3 * C / 2;
-                const int set = warp >> 2;
-                const uint32_t tm_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-                uint64_t *full1 = &acc_full[3 * set], *rel1 = &acc_empty[3 * set];
-                int X = (128 * set + m) % P1w, Y = (128 * set + m) / P1w;
-                const uint4 *sc4 = reinterpret_cast<const uint4 *>(s_par), *sh4 = reinterpret_cast<const uint4 *>(s_par + NPK);
-                uint32_t par = 0;
-                for (int t = set; t < n_tiles; t += 2, par ^= 1) {
-                    uint32_t run[NPK];
-#pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        mbar_wait(&full1[dy], par);
-                        tc_fence_after_sync();
-                        uint32_t row[ROWPK], mx[NPK];
-                        row_load_all<C>(tm_lane + 3 * C * dy, row);
-                        tmem_ld_wait();
-                        reg_fence_u<ROWPK>(row);
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&rel1[dy]);                 // the next tile's MMAs of this block row may start
-                        row_max_dx<C>(row, mx);
-#pragma unroll
-                        for (int i = 0; i < NPK; ++i) run[i] = dy == 0 ? mx[i] : (dy == 1 ? hmax2(run[i], mx[i]) : hmax3(run[i], mx[i], 0u));   // ... and the ReLU
-                    }
-#pragma unroll
-                    for (int i = 0; i < NPK / 4; ++i) {                 // scale (+-2^k, exact) and BatchNorm shift
-                        const uint4 sc = sc4[i], sh = sh4[i];
-                        run[4 * i + 0] = hfma2(run[4 * i + 0], sc.x, sh.x);
-                        run[4 * i + 1] = hfma2(run[4 * i + 1], sc.y, sh.y);
-                        run[4 * i + 2] = hfma2(run[4 * i + 2], sc.z, sh.z);
-                        run[4 * i + 3] = hfma2(run[4 * i + 3], sc.w, sh.w);
-                    }
-                    if (Y < p.P1h) {
-                        const uint32_t off = (uint32_t)(((Y % 3) * 3 + X % 3) * CG) * (uint32_t)p.out.gtot +
-                                             (uint32_t)slot_idx * (uint32_t)p.out.FP + (uint32_t)((Y / 3) * p.out.PW + X / 3);
-                        uint4 *dst = reinterpret_cast<uint4 *>(p.out.ptr) + off;
-#pragma unroll
-                        for (int j = 0; j < CG; ++j)
-                            st_global_v4_hint(dst + (size_t)j * p.out.gtot, run[4 * j], run[4 * j + 1], run[4 * j + 2], run[4 * j + 3], keep_in_l2);
-                    }
-                    X += 256;                                              // this set's next tile: 64 <= P1w, at most four rows further
-#pragma unroll
-                    for (int k2 = 0; k2 < 4; ++k2) { const bool c = X >= P1w; X -= c ? P1w : 0; Y += c ? 1 : 0; }
-                }
-            } else {
+            {
                 uint32_t acc_phase = 0;
                 int X = m % P1w, Y = m / P1w;                          // position 128 t + m = Y * P1w + X of this frame
                 EpiRow16<CH> bufA, bufB;
@@ -2822,14 +2700,14 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
     }();
     if (!regs_ok) return CUTDET_EUNSUPPORTED;
     src.n_slots = (int)std::min<long long>(raw_bytes(F1Roles<true>::UNFOLD_WARPS) / ((long long)src.n_src * src.row_bytes), RAW_SLOTS_MAX);
-    src.n_slots -= src.n_slots % std::min(F12_L1_LOADERS * F12_STREAMS, src.n_slots);
+    src.n_slots -= src.n_slots % std::min(LOADER_WARPS, src.n_slots);
     const bool gather = src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0;
     // Integer-scale gathers read evenly spaced source rows (row off_y + y * step_y; consecutive slots in compact frames): the
     // loaders then fetch two rows per TMA instruction through a tensor map of this launch's frames (see the kernel).
     CUtensorMap src_map;
     memset(&src_map, 0, sizeof(src_map));
     src.tma_shift = -1;
-    if (F12_SRC_TMA && gather && src.n_src == 1 && F12_STREAMS == 1 && F12_L1_ISSUERS != 2) {
+    if (gather && src.n_src == 1) {
         const int shift = 1, rows_per_slot = 1 << shift;
         int groups = (int)std::min<long long>(raw_bytes(F1Roles<true>::UNFOLD_WARPS) / ((long long)rows_per_slot * src.row_bytes), RAW_SLOTS_MAX);
         groups -= groups % LOADER_WARPS;

@@ -66,13 +66,6 @@ def main():
                     t += 1
                 f.write("# loaders: row: issued (after its slot was free)\n")
                 f.write(" ".join(f"{n}:{h[40 + n] - f0}" for n in range(0, 200) if h[40 + n]) + "\n")
-                f.write("# loader 0, its rows: row: before_wait (+wait) (+issue) (+release) | period\n")
-                prev = None
-                for n in range(0, 144, 3):
-                    if h[1000 + n]:
-                        a0 = h[1000 + n]
-                        f.write(f"lrow {n}: {a0 - f0} +{h[40 + n] - a0} +{h[1001 + n] - h[40 + n]} +{h[1002 + n] - h[1001 + n]} | {a0 - prev if prev else 0}\n")
-                        prev = a0
                 f.write("# unfold warp 0: its k-th row: start, wait for ring space and source row, work, fence\n")
                 k = 0
                 while k < 30 and h[256 + 4 * k]:
