@@ -797,6 +797,8 @@ struct FusedSrc {
     int row_bytes;    // 3 * src_w, a multiple of 16
     int n_slots;      // raw ring slots of n_src * row_bytes each (2 .. RAW_SLOTS_MAX)
     int tma_shift;    // conv12_frames with a tensor map of the source rows: a slot holds 2^tma_shift rows, fetched by ONE TMA box; -1 = bulk copies
+    int pair_rows;    // a resized row's two source rows are adjacent in the buffer (one two-row box serves n_src = 2)
+    int buf_rows;     // rows per frame in the buffer (all source rows, or the compact ones)
 };
 
 template <int C, int UW>
@@ -1680,8 +1682,9 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
     const int tiles2 = p2.FP / 128;                               // layer-2 tiles of one frame (the frame pitch is a multiple of 128)
     const int n_slots = src.n_slots, slot_bytes = src.n_src * src.row_bytes;    // (slot_bytes: one ROW's bytes in the ring)
     const uint32_t inv_slots = 0xffffffffu / (uint32_t)n_slots + 1u;
-    // Source rows by TMA (src.tma_shift >= 0; integer-scale gathers, whose rows are evenly spaced): a slot of the raw ring holds
-    // 2^tma_shift rows fetched by ONE box of src_map.  Why: a thread gets a bulk copy accepted every ~500 cycles and no faster
+    // Source rows by TMA (src.tma_shift >= 0): a slot of the raw ring is fetched by ONE box of src_map -- 2^tma_shift rows of an
+    // integer-scale gather or a plain copy (their rows are evenly spaced: the map's row axis walks them), or the two adjacent rows a
+    // bilinear / 2x2 resize reads per output row (n_src = 2, tma_shift = 0: the map's row axis is the buffer's).  Why: a thread gets a bulk copy accepted every ~500 cycles and no faster
     // (300 cycles for the instruction alone on an idle SM, profiles/r02_timeline_frames_detail.txt), so three loaders issuing one
     // row each delivered 4.5 rows per ~1,400 cycles -- precisely the tile period of layer 1, whose unfold warps were seen to pick
     // every row up the moment it landed.  With two rows per instruction the row supply has a factor 2 in hand.
@@ -1702,7 +1705,8 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
         else { r0 = plan.y0[y]; r1 = plan.y1[y]; b0 = plan.b0[y]; b1 = plan.b1[y]; }
         if (src.compact) { r0 = plan.row_slot[r0]; r1 = (plan.mode == RESIZE_LINEAR && b1 == 0) ? r0 : plan.row_slot[r1]; }
         s_rowoff[2 * y] = (int)(r0 * src.row_pitch);
-        s_rowoff[2 * y + 1] = (int)(r1 * src.row_pitch);
+        // (with two-row TMA boxes the second row needs no offset of its own: the slot keeps the first row's INDEX in the buffer)
+        s_rowoff[2 * y + 1] = (use_tma && src.n_src == 2) ? r0 : (int)(r1 * src.row_pitch);
         s_yb[2 * y] = b0;
         s_yb[2 * y + 1] = b1;
     }
@@ -1902,8 +1906,8 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                             if (tlw && it == 2 && (g << rps_shift) < 200) tlw[40 + (g << rps_shift)] = clock64();
                             if (elect_one()) {
                                 mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)(slot_bytes << rps_shift));
-                                tma_load_4d_hint(s_raw + (slot << rps_shift) * slot_bytes, &src_map, &raw_full[slot], 0, 0, g << rps_shift, f_idx,
-                                                 stream_once);
+                                tma_load_4d_hint(s_raw + (slot << rps_shift) * slot_bytes, &src_map, &raw_full[slot], 0, 0,
+                                                 src.n_src == 2 ? s_rowoff[2 * g + 1] : g << rps_shift, f_idx, stream_once);
                                 st_release_shared(&s_rows_issued[lw], issued);   // raw_full[slot] is now in group g's phase
                             }
                             __syncwarp();
@@ -1984,8 +1988,8 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                 // these warps idle while layer 2 runs: bring the first source rows of the next frame into the L2, so that layer 1
                 // starts on L2 hits instead of a DRAM round trip per loader
                 const uint8_t *next = src.frames + (long long)(blockIdx.x + (long long)(it + 1) * gridDim.x) * src.frame_stride;
-                for (int n = lane; n < min(Hc, 2 * n_slots); n += 32)
-                    for (int j = 0; j < src.n_src; ++j) bulk_prefetch_l2(next + s_rowoff[2 * n + j], (uint32_t)src.row_bytes);
+                for (int n = lane; n < min(Hc, 2 * n_slots); n += 32)      // (n_src = 2: the second row follows the first)
+                    bulk_prefetch_l2(next + s_rowoff[2 * n], (uint32_t)(src.n_src * src.row_bytes));
             }
             frame_end(it);
         }
@@ -2588,6 +2592,8 @@ bool fused_source(const cutdet_resize_plan *plan, const cutdet_frames *frames, c
     out->row_bytes = (int)row_bytes;
     out->n_slots = (int)n_slots;
     out->tma_shift = -1;
+    out->pair_rows = plan->pair_rows ? 1 : 0;
+    out->buf_rows = rows;
     return true;
 }
 
@@ -2707,12 +2713,18 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
     CUtensorMap src_map;
     memset(&src_map, 0, sizeof(src_map));
     src.tma_shift = -1;
-    if (gather && src.n_src == 1) {
+    const bool even_rows = (gather || src.plan.mode == RESIZE_COPY) && src.n_src == 1;
+    if (!even_rows && src.n_src == 2 && src.pair_rows && !src.plan.gather_step_x) {
+        // the two source rows of an output row as one two-row box at the first one's index in the buffer
+        if (make_src_map(&src_map, src.frames, src.row_bytes, src.row_pitch, src.frame_stride, src.buf_rows, n, 2) == CUTDET_OK) src.tma_shift = 0;
+    }
+    if (even_rows) {
         const int shift = 1, rows_per_slot = 1 << shift;
         int groups = (int)std::min<long long>(raw_bytes(F1Roles<true>::UNFOLD_WARPS) / ((long long)rows_per_slot * src.row_bytes), RAW_SLOTS_MAX);
         groups -= groups % LOADER_WARPS;
-        const long long row_stride = src.compact ? src.row_pitch : (long long)src.plan.gather_step_y * src.row_pitch;
-        const uint8_t *base = src.frames + (src.compact ? 0 : (long long)src.plan.gather_off_y * src.row_pitch);
+        const bool plain = src.plan.mode == RESIZE_COPY && !gather;
+        const long long row_stride = (src.compact || plain) ? src.row_pitch : (long long)src.plan.gather_step_y * src.row_pitch;
+        const uint8_t *base = src.frames + ((src.compact || plain) ? 0 : (long long)src.plan.gather_off_y * src.row_pitch);
         if (groups >= LOADER_WARPS && c1.H % rows_per_slot == 0 &&
             make_src_map(&src_map, base, src.row_bytes, row_stride, src.frame_stride, c1.H, n, rows_per_slot) == CUTDET_OK) {
             src.tma_shift = shift;

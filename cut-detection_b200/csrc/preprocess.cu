@@ -375,6 +375,12 @@ extern "C" int cutdet_resize_plan_create(int src_h, int src_w, int dst_h, int ds
     std::vector<int> slot(src_h, -1);
     for (int y = 0; y < src_h; ++y)
         if (used[y]) { slot[y] = (int)plan->rows.size(); plan->rows.push_back(y); }
+    if (h.mode == RESIZE_AREA2) plan->pair_rows = true;
+    if (h.mode == RESIZE_LINEAR) {
+        plan->pair_rows = true;
+        for (int y = 0; y < dst_h && plan->pair_rows; ++y)
+            if (b1[y] != 0 && (y1[y] != y0[y] + 1 || slot[y1[y]] != slot[y0[y]] + 1)) plan->pair_rows = false;
+    }
     // rows never read still need a defined slot (never dereferenced)
     for (int y = 0; y < src_h; ++y) if (slot[y] < 0) slot[y] = 0;
     plan->n_rows = (int)plan->rows.size();

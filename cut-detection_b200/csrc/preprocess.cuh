@@ -30,4 +30,7 @@ struct cutdet_resize_plan {
     void *dev_blob = nullptr;
     std::vector<int> rows;   // source rows the resize reads
     int n_rows = 0;
+    // every output row reads source row y0 and (with a non-zero weight) only the row right after it, which is also the next
+    // compact slot: the two rows can then be fetched as ONE two-row box (conv12_frames' TMA loaders)
+    bool pair_rows = false;
 };
