@@ -2494,6 +2494,10 @@ int set_smem_limits() {
 // grid_dep_launch / grid_dep_wait in tc_common.cuh; every kernel launched this way orders its dependent accesses itself).
 // Grids are at most one CTA per SM, so a waiting successor can never keep a predecessor's CTA from being scheduled.
 // cutdet_net_set_option(CUTDET_OPT_NO_PDL) falls back to ordinary launches (pdl = false everywhere).
+// An optional window of global memory whose lines the kernel's accesses mark as PERSISTING in the L2 (cudaLaunchAttributeAccessPolicyWindow)
+struct L2Window { void *base = nullptr; size_t bytes = 0; };
+thread_local L2Window g_launch_window;       // set by a caller for its next launch_pdl, cleared by it
+
 template <typename... KArgs, typename... Args>
 void launch_pdl(bool pdl, void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t stream, Args &&...args) {
     cudaLaunchConfig_t cfg{};
@@ -2501,11 +2505,25 @@ void launch_pdl(bool pdl, void (*kernel)(KArgs...), int grid, int threads, size_
     cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (g_launch_window.base) {
+        attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[n].val.accessPolicyWindow.base_ptr = g_launch_window.base;
+        attr[n].val.accessPolicyWindow.num_bytes = g_launch_window.bytes;
+        attr[n].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++n;
+        g_launch_window = L2Window{};
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = n;
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -2730,6 +2748,20 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
             src.tma_shift = shift;
             src.n_slots = groups;
         }
+    }
+    if (net->opt.l2_persist) {
+        // experiment (CUTDET_OPT_L2_PERSIST): the layer-1 slots as a persisting window of the L2, so that the frame stream cannot push
+        // dirty slot lines out to DRAM between their write and their read-back.  The carve-out is a limit of the CUDA context.
+        static const size_t carve = [] {
+            int dev = 0, max_persist = 0, max_window = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            return (size_t)std::min(max_persist, max_window);
+        }();
+        const size_t bytes = std::min(carve, act_bytes(g.CG, w.gtot1));
+        if (bytes) g_launch_window = L2Window{ws + w.act1, bytes};
     }
     {
         KernelScope scope("conv12_frames", stream);

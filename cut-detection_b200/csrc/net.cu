@@ -245,6 +245,7 @@ extern "C" int cutdet_net_set_option(cutdet_net *net, int option, int value) {
         case CUTDET_OPT_NO_PDL: net->opt.no_pdl = value != 0; break;
         case CUTDET_OPT_CONV1_GRID: net->opt.conv1_grid = value; break;
         case CUTDET_OPT_CONV1_VARIANT: net->opt.conv1_variant = value; break;
+        case CUTDET_OPT_L2_PERSIST: net->opt.l2_persist = value; break;
         default: return fail(CUTDET_EINVAL, "net_set_option: unknown option %d", option);
     }
     return CUTDET_OK;
@@ -259,6 +260,7 @@ extern "C" int cutdet_net_get_option(const cutdet_net *net, int option, int *val
         case CUTDET_OPT_NO_PDL: *value = net->opt.no_pdl; break;
         case CUTDET_OPT_CONV1_GRID: *value = net->opt.conv1_grid; break;
         case CUTDET_OPT_CONV1_VARIANT: *value = net->opt.conv1_variant; break;
+        case CUTDET_OPT_L2_PERSIST: *value = net->opt.l2_persist; break;
         default: return fail(CUTDET_EINVAL, "net_get_option: unknown option %d", option);
     }
     return CUTDET_OK;

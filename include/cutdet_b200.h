@@ -154,6 +154,8 @@ enum {
     CUTDET_OPT_GROUP_FRAMES = 3, /* frames per conv12_frames / conv3 launch (default 0 = 4144 = 28 per SM)                    */
     CUTDET_OPT_NO_PDL = 4,       /* 1: ordinary launches instead of programmatic dependent launch                       */
     CUTDET_OPT_CONV1_GRID = 5,   /* test hook: cap on the fused conv1 grid (several frames per CTA); 0 = no cap         */
+    CUTDET_OPT_L2_PERSIST = 7,   /* experiment: 1 = conv12_frames marks its layer-1 slots as a persisting window of the L2 (sets the
+                                    context's cudaLimitPersistingL2CacheSize to the device maximum on first use)               */
     CUTDET_OPT_CONV1_VARIANT = 6 /* which kernels run layers 1 and 2 of the fused frames path; all give the same bits.
                                     0 (default) and 2: ONE kernel takes a frame through K1 + layer 1 + layer 2 per CTA
                                     (conv12_frames_kernel; where it does not apply -- fp32 accumulators requested -- the

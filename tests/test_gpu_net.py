@@ -293,7 +293,9 @@ def test_dependent_launch_changes_nothing(prod_weights):
                        # arithmetic is the same as in the two-kernel path, whatever the tiling
                        ("two_kernels", {"conv1_variant": 3}), ("two_kernels_no_pdl", {"conv1_variant": 3, "no_pdl": 1}),
                        ("frames", {"conv1_variant": 2}), ("frames_no_pdl", {"conv1_variant": 2, "no_pdl": 1}),
-                       ("frames_grid37", {"conv1_variant": 2, "conv1_grid": 37}), ("frames_group300", {"conv1_variant": 2, "group_frames": 300})):
+                       ("frames_grid37", {"conv1_variant": 2, "conv1_grid": 37}), ("frames_group300", {"conv1_variant": 2, "group_frames": 300}),
+                       # l2_persist: the layer-1 slots as a persisting window of the L2 (a cache policy, never a numerical switch)
+                       ("frames_l2_persist", {"l2_persist": 1})):
         nets[name] = engine.NativeNet(wts, params["avg_pool_size"])
         for k, v in opts.items():
             nets[name].set_option(k, v)
