@@ -1591,8 +1591,9 @@ __global__ void __launch_bounds__(S2Roles::THREADS, 1) conv1_fused_sets_kernel(c
 // ------------------------------------------------------------------------------------------------ K1 + layer 1 + layer 2, frame by frame
 // One persistent CTA per SM takes a frame through BOTH layers before it starts the next one: the fused K1 + layer-1 pipeline of
 // conv1_fused_tc_kernel (fp16 accumulators) writes the frame's pooled map into this CTA's slot of the phase-split buffer, then the
-// same CTA runs layer 2's tiles of that slot (conv_mid_tc_kernel's pipeline: TMA producer, MMA issuer, the eight epilogue warps)
-// and stores the frame's layer-2 map for conv3.
+// same CTA runs layer 2's tiles of that slot (conv_mid_tc_kernel's pipeline: the first loader becomes the TMA producer, the issuer
+// and the two other loaders issue one block row each, the eight epilogue warps serve both layers) and stores the frame's layer-2
+// map for conv3.
 // Why: as two kernels per 148-frame sub-batch the layers are joined by GRID-wide dependencies -- conv2 waits for the last conv1
 // CTA, conv1's epilogue of the next sub-batch waits for the last conv2 CTA (it overwrites what conv2 reads) -- and every launch
 // pays its ramp and drain: by the per-CTA clock stamps a sub-batch takes ~62 us of which ~46 us are the two tile loops.  A frame's
@@ -1619,7 +1620,7 @@ template <int C>
 struct F12Smem {
     using S1 = F1Smem<C, F1Roles<true>::UNFOLD_WARPS>;
     using S2 = MidSmem<C>;
-    static constexpr int OFF_BAR2 = S1::OFF_BAR + 640;             // layer 2's 13 barriers, inside layer 1's 1 KB barrier block
+    static constexpr int OFF_BAR2 = S1::OFF_BAR + 640;             // layer 2's 14 barriers, inside layer 1's 1 KB barrier block
     static constexpr int OFF_PAR2 = S1::total;                     // layer 2's bias / scale / shift
     static constexpr int total = OFF_PAR2 + 3 * C * 4;
     static_assert(S2::W_BYTES + MID_STAGES * MID_STAGE_BYTES <= S1::OFF_TAB, "layer 2's operands must end before the tables layer 1 keeps");
@@ -1633,7 +1634,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                      const __grid_constant__ CUtensorMap src_map) {
     using RL = F1Roles<true>;
     constexpr int UNFOLD_WARPS = RL::UNFOLD_WARPS, F1_MMA_WARP = RL::MMA_WARP0, F1_LOAD_WARP0 = RL::LOAD_WARP0;
-    static_assert(RL::MMA_WARPS == 1, "one issuer for both layers");
+    static_assert(RL::MMA_WARPS == 1, "one issuer warp in layer 1 (layer 2 adds two of the loaders)");
     using S = F1Smem<C, UNFOLD_WARPS>;
     using S2 = MidSmem<C>;
     using SS = F12Smem<C>;
