@@ -2497,10 +2497,10 @@ int set_smem_limits() {
 // cutdet_net_set_option(CUTDET_OPT_NO_PDL) falls back to ordinary launches (pdl = false everywhere).
 // An optional window of global memory whose lines the kernel's accesses mark as PERSISTING in the L2 (cudaLaunchAttributeAccessPolicyWindow)
 struct L2Window { void *base = nullptr; size_t bytes = 0; };
-thread_local L2Window g_launch_window;       // set by a caller for its next launch_pdl, cleared by it
 
 template <typename... KArgs, typename... Args>
-void launch_pdl(bool pdl, void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t stream, Args &&...args) {
+void launch_pdl_window(bool pdl, const L2Window &window, void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t stream,
+                       Args &&...args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)threads);
@@ -2513,19 +2513,23 @@ void launch_pdl(bool pdl, void (*kernel)(KArgs...), int grid, int threads, size_
         attr[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
     }
-    if (g_launch_window.base) {
+    if (window.base && window.bytes) {
         attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[n].val.accessPolicyWindow.base_ptr = g_launch_window.base;
-        attr[n].val.accessPolicyWindow.num_bytes = g_launch_window.bytes;
+        attr[n].val.accessPolicyWindow.base_ptr = window.base;
+        attr[n].val.accessPolicyWindow.num_bytes = window.bytes;
         attr[n].val.accessPolicyWindow.hitRatio = 1.0f;
         attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         ++n;
-        g_launch_window = L2Window{};
     }
     cfg.attrs = attr;
     cfg.numAttrs = n;
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+void launch_pdl(bool pdl, void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t stream, Args &&...args) {
+    launch_pdl_window(pdl, L2Window{}, kernel, grid, threads, smem, stream, std::forward<Args>(args)...);
 }
 
 template <int C>
@@ -2750,6 +2754,7 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
             src.n_slots = groups;
         }
     }
+    L2Window window;
     if (net->opt.l2_persist) {
         // experiment (CUTDET_OPT_L2_PERSIST): the layer-1 slots as a persisting window of the L2, so that the frame stream cannot push
         // dirty slot lines out to DRAM between their write and their read-back.  The carve-out is a limit of the CUDA context.
@@ -2761,14 +2766,13 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
             if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
             return (size_t)std::min(max_persist, max_window);
         }();
-        const size_t bytes = std::min(carve, act_bytes(g.CG, w.gtot1));
-        if (bytes) g_launch_window = L2Window{ws + w.act1, bytes};
+        window = L2Window{ws + w.act1, std::min(carve, act_bytes(g.CG, w.gtot1))};
     }
     {
         KernelScope scope("conv12_frames", stream);
         const bool pdl = f0 > 0 && !net->opt.no_pdl;        // the loaders read the frames at once: only behind a kernel of ours
-        if (gather) launch_pdl(pdl, conv12_frames_kernel<C, true>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2, src_map);
-        else launch_pdl(pdl, conv12_frames_kernel<C, false>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2, src_map);
+        if (gather) launch_pdl_window(pdl, window, conv12_frames_kernel<C, true>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2, src_map);
+        else launch_pdl_window(pdl, window, conv12_frames_kernel<C, false>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2, src_map);
     }
     CUTDET_LAUNCH_CHECK("conv12_frames_kernel");
     return CUTDET_OK;
