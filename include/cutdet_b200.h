@@ -198,9 +198,11 @@ CUTDET_API int cutdet_net_forward_conv_layer(cutdet_net *net, int layer, const f
 CUTDET_API int cutdet_net_forward_fc_layer(cutdet_net *net, int layer, const float *x_dev, int batch, float *out_dev,
                                 int relu, int bn_mode, cutdet_stream_t stream);
 
-/* Debug aid (tools/timeline.py): while armed (kernel 1 = conv1_fused_tc, 2 = conv2_tc; 0 or a null buffer disarms), CTA 0 of
- * every full sub-batch launch of that kernel writes clock stamps into the caller's device buffer of >= 4096 int64 entries
- * (conv1: entries 2048 + 2 b, 2049 + 2 b = %globaltimer at entry / exit of CTA b).
+/* Debug aid (tools/timeline.py, bench.py's roofline.phases): while armed (kernel 1 = conv1_fused_tc, 2 = conv2_tc, 3 =
+ * conv12_frames; 0 or a null buffer disarms), CTA 0 of every launch of that kernel over at least 148 frames writes clock stamps
+ * into the caller's device buffer of >= 4096 int64 entries (kernels 1 and 3: entries 2048 + 2 b, 2049 + 2 b = %globaltimer at
+ * entry / exit of CTA b; kernel 3: [0] = clock64 at its start, [1 + 3 i], [2 + 3 i], [3 + 3 i] = layer 1 set up / layer 1 done /
+ * layer 2 done of CTA 0's i-th frame, and per-role stamps of its third frame, see csrc/conv_tc.cu).
  * The library allocates, copies and synchronises nothing for it.                                                          */
 CUTDET_API int cutdet_net_debug_timeline(cutdet_net *net, int kernel, long long *stamps_dev, size_t n_entries);
 
