@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=4050, help="frames per step")
     ap.add_argument("--pool", type=int, default=4, help="distinct chunks kept resident in HBM")
     ap.add_argument("--cpu-sample", type=int, default=1800, help="frames of the CPU baseline sample (configs[0])")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="FramePipeline lanes: consecutive chunks scored on alternating streams (1 = everything on one stream)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true")
@@ -379,11 +381,11 @@ def run_game(rig: Rig):
         return np.concatenate([rank_clip.labels[(s % cycle) * chunk:(s % cycle + 1) * chunk] for s in range(steps)])
 
     capacity = K * chunk                          # a run table can never have more rows than frames
-    pipe = pipeline.FramePipeline(native, plan, chunk, capacity, dev)
+    pipe = pipeline.FramePipeline(native, plan, chunk, capacity, dev, lanes=args.lanes)
     step_results = torch.empty((chunk, 5), dtype=torch.uint8).pin_memory()     # (label u8, max logit f32) per frame
     host_pool = []
 
-    def finalize(frames_local):
+    def finalize(frames_local, pipe=pipe):
         """close the table, exchange (N > 1), raw copy, K6, final copy: all queued without a host synchronisation until the
         first device->host copy.  Returns (raw te, smoothed te, total frames)."""
         table = pipe.finish()
@@ -395,7 +397,7 @@ def run_game(rig: Rig):
         te = table.to_te()
         return raw, te, (int(total.item()) if total is not None else frames_local)
 
-    def job(source, steps):
+    def job(source, steps, pipe=pipe):
         pipe.reset()
         for s in range(steps):
             if source == "device":
@@ -403,9 +405,10 @@ def run_game(rig: Rig):
             else:
                 pipe.push_host(host_pool[s % len(host_pool)])
                 n = chunk
+                pipe.wait_results()
                 step_results[:n, 0].copy_(pipe.labels[:n], non_blocking=True)
                 step_results[:n, 1:].copy_(pipe.top[:n].view(torch.uint8).view(n, 4), non_blocking=True)
-        return finalize(steps * chunk)
+        return finalize(steps * chunk, pipe)
 
     def check_parity(raw, te, total, cycle, steps):
         """rank 0: the gathered, stitched table against the global plan (every rank's clip is a function of seed + rank), K6
@@ -469,10 +472,12 @@ def run_game(rig: Rig):
 
     # ---------------- roofline: per-kernel CUDA-event timings of the same job (separate pass)
     prof_steps = min(K, 8)
-    job("device", min(W, 2) or 1)
+    # one lane: a kernel's events then bracket its own run, not its wait for the SMs the other lane's kernels hold
+    pipe1 = pipe if args.lanes <= 1 else pipeline.FramePipeline(native, plan, chunk, capacity, dev, lanes=1)
+    job("device", min(W, 2) or 1, pipe1)
     torch.cuda.synchronize()
     lib.cutdet_profile_begin()
-    job("device", prof_steps)
+    job("device", prof_steps, pipe1)
     import ctypes
     cbuf = ctypes.create_string_buffer(65536)
     _cabi.check(lib.cutdet_profile_end(cbuf, 65536))
@@ -528,6 +533,7 @@ def run_game(rig: Rig):
                                    f"({K} steps x {chunk} frames per GPU; decode excluded)",
                        "resolution": [WIDTH, HEIGHT], "chunk_frames": chunk, "frames_per_gpu": K * chunk,
                        "total_frames": world * K * chunk, "pool_chunks": pool_n,
+                       "lanes": args.lanes,
                        "l2_policy": "inputs larger than L2: each step reads a distinct 11.2 GB chunk",
                        "weights": "shipped prod_net", "conv_path": "tcgen05" if uses_tc else "generic-cuda-core",
                        "net_options": rig.net_opts,

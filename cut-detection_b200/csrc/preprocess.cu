@@ -272,7 +272,102 @@ __global__ void __launch_bounds__(ROWS_THREADS) preprocess_rows_kernel(ResizePla
     }
 }
 
-int g_k1_kernel = 0;        // cutdet_debug_k1_kernel: 0 = choose, 1 = one thread per pixel, 2 = row kernel (measurement aid)
+// Two-tap (bilinear) resizes again, for the geometries where the arithmetic -- not the memory -- paces the kernels above
+// (640x360 -> 256x144 reads 15 source bytes per output pixel where 1080p reads 45): FOUR ADJACENT output pixels per thread.
+// The source rows of four output rows are staged as in the row kernel; a thread fetches the packed taps of its four columns once
+// (two 16-byte loads of plan.xpack) and uses them for two output rows; the vertical pass needs no clamp (the weights of a pair are
+// non-negative and sum to 2048, so the result is at most 255); and the outputs leave straight from registers -- a float4 per
+// channel plane (the division by 255 is a 256-entry table of correctly rounded quotients in shared memory) or the twelve packed
+// BGR bytes as three words -- with no second pass through shared memory.
+constexpr int QUAD_ROWS = 4;
+constexpr int QUAD_THREADS = 128;
+
+template <int OUT>
+__global__ void __launch_bounds__(QUAD_THREADS, 10) preprocess_quads_kernel(ResizePlanDev plan, const uint8_t *__restrict__ frames,
+                                                                       int64_t frame_stride, int64_t row_pitch, int compact,
+                                                                       void *__restrict__ out, int row_pad) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *s_lut = reinterpret_cast<float *>(smem + 2 * QUAD_ROWS * row_pad);
+    const int y_first = blockIdx.x * QUAD_ROWS, b = blockIdx.y, tid = threadIdx.x;
+    const int n16 = (3 * plan.src_w + 15) >> 4;
+    const uint8_t *frame = frames + (int64_t)b * frame_stride;
+#pragma unroll
+    for (int r = 0; r < QUAD_ROWS; ++r) {
+        const int y = y_first + r;
+        if (y >= plan.dst_h) break;
+        int r0 = __ldg(plan.y0 + y), r1 = __ldg(plan.y1 + y);
+        const bool two = __ldg(plan.b1 + y) != 0;
+        if (compact) { r0 = __ldg(plan.row_slot + r0); r1 = two ? __ldg(plan.row_slot + r1) : r0; }
+        const uint4 *g0 = reinterpret_cast<const uint4 *>(frame + (int64_t)r0 * row_pitch);
+        const uint4 *g1 = reinterpret_cast<const uint4 *>(frame + (int64_t)r1 * row_pitch);
+        uint4 *d0 = reinterpret_cast<uint4 *>(smem + (2 * r) * row_pad), *d1 = reinterpret_cast<uint4 *>(smem + (2 * r + 1) * row_pad);
+        for (int i = tid; i < n16; i += QUAD_THREADS) {
+            cp_async_16(d0 + i, g0 + i);
+            if (two) cp_async_16(d1 + i, g1 + i);
+        }
+        if (tid == 0) {        // the taps of the last pixels read a word or two past the row
+            d0[n16] = make_uint4(0, 0, 0, 0);
+            d1[n16] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    if (OUT == 0)
+        for (int i = tid; i < 256; i += QUAD_THREADS) s_lut[i] = __fdiv_rn((float)i, 255.f);      // true float32 division, as the reference does
+    cp_async_wait_all();
+    __syncthreads();
+    const int quads = plan.dst_w >> 2;
+    for (int item = tid; item < 2 * quads; item += QUAD_THREADS) {
+        const int half = item >= quads ? 1 : 0, j = item - half * quads;
+        const int4 ta = __ldg(reinterpret_cast<const int4 *>(plan.xpack) + 2 * j), tb = __ldg(reinterpret_cast<const int4 *>(plan.xpack) + 2 * j + 1);
+        const int off[4] = {ta.x, ta.z, tb.x, tb.z};
+        const uint32_t aw[4] = {(uint32_t)ta.y, (uint32_t)ta.w, (uint32_t)tb.y, (uint32_t)tb.w};
+#pragma unroll
+        for (int rr = 0; rr < QUAD_ROWS; rr += 2) {
+            const int r = rr + half, y = y_first + r;
+            if (y >= plan.dst_h) break;
+            const int yb0 = __ldg(plan.b0 + y), yb1 = __ldg(plan.b1 + y);
+            const uint8_t *s_row0 = smem + (2 * r) * row_pad;
+            const uint8_t *s_row1 = yb1 != 0 ? s_row0 + row_pad : s_row0;         // weight 0: any staged row will do
+            uint32_t px[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t sh = (uint32_t)(off[k] & 3) * 8;
+                const uint32_t *w0 = reinterpret_cast<const uint32_t *>(s_row0 + (off[k] & ~3));
+                const uint32_t *w1 = reinterpret_cast<const uint32_t *>(s_row1 + (off[k] & ~3));
+                const uint32_t lo0 = __funnelshift_r(w0[0], w0[1], sh), hi0 = __funnelshift_r(w0[1], w0[2], sh);   // bytes 0..3, 4..7 of the pair
+                const uint32_t lo1 = __funnelshift_r(w1[0], w1[1], sh), hi1 = __funnelshift_r(w1[1], w1[2], sh);
+                uint32_t p = 0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const uint32_t selc = c == 0 ? 0x7730u : (c == 1 ? 0x7741u : 0x7752u);          // (p[x0][c], p[x0+1][c]) in the low half
+                    const int s0 = (int)__dp2a_lo(aw[k], __byte_perm(lo0, hi0, selc), 0u);
+                    const int s1 = (int)__dp2a_lo(aw[k], __byte_perm(lo1, hi1, selc), 0u);
+                    // ((b0 (S0 >> 4)) >> 16) + ((b1 (S1 >> 4)) >> 16) + 2: the rounding 2 rides in the first product as 2 << 16 (it cannot
+                    // disturb the bits below); <= 255 by construction
+                    const int v = (((yb0 * (s0 >> 4) + 0x20000) >> 16) + ((yb1 * (s1 >> 4)) >> 16)) >> 2;
+                    p |= (uint32_t)v << (8 * c);
+                }
+                px[k] = p;
+            }
+            if (OUT == 0) {
+                const int64_t plane = (int64_t)plan.dst_h * plan.dst_w;
+                float *o = reinterpret_cast<float *>(out) + (int64_t)b * 3 * plane + (int64_t)y * plan.dst_w + 4 * j;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {        // RGB planes: output channel 0 is source byte 2
+                    const int shift = 8 * (2 - c);
+                    reinterpret_cast<float4 *>(o + c * plane)[0] = make_float4(s_lut[(px[0] >> shift) & 0xff], s_lut[(px[1] >> shift) & 0xff],
+                                                                              s_lut[(px[2] >> shift) & 0xff], s_lut[(px[3] >> shift) & 0xff]);
+                }
+            } else {
+                uint32_t *o = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(out) + (((int64_t)b * plan.dst_h + y) * plan.dst_w + 4 * j) * 3);
+                o[0] = px[0] | (px[1] << 24);
+                o[1] = (px[1] >> 8) | (px[2] << 16);
+                o[2] = (px[2] >> 16) | (px[3] << 8);
+            }
+        }
+    }
+}
+
+int g_k1_kernel = 0;        // cutdet_debug_k1_kernel: 0 = choose, 1 = one thread per pixel, 2 = row kernel, 3 = quad kernel (measurement aid)
 
 int check_frames(const cutdet_resize_plan *plan, const cutdet_frames *src) {
     CUTDET_REQUIRE(plan && src, "preprocess: null plan/frames");
@@ -285,6 +380,9 @@ int check_frames(const cutdet_resize_plan *plan, const cutdet_frames *src) {
                    "preprocess: frame_stride too small");
     return CUTDET_OK;
 }
+
+// The quad kernel by default where the source row is short (profiles/r02_k1_matrix.txt): few source bytes per output pixel.
+#define QUADS_BY_DEFAULT(h) (3 * (h).src_w <= 2048)
 
 template <int OUT>
 static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *src, void *out, cutdet_stream_t stream) {
@@ -302,6 +400,30 @@ static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *s
     // very long rows (2160p: 78.8 % against 93.7 %); with the 4 x larger float32 output the one-thread-per-pixel kernel is
     // ahead (720p 77.6 % against 68.5 %): its coalesced 4-byte plane stores need no second pass through shared memory.
     const bool choose_rows = g_k1_kernel == 2 || (g_k1_kernel == 0 && OUT == 1 && 3 * h.src_w <= 6144);
+    // two-tap resizes with few source bytes per output pixel (360p): the quad kernel (see above)
+    const size_t smem_quads = 2 * (size_t)QUAD_ROWS * row_pad + (OUT == 0 ? 1024 : 0);
+    const bool quads_ok = h.mode == RESIZE_LINEAR && h.gather_step_x == 0 && h.dst_w % 4 == 0 && aligned && h.dst_h <= 4 * 65535 &&
+                          smem_quads <= 200 * 1024 && reinterpret_cast<uintptr_t>(out) % (OUT == 0 ? 16 : 4) == 0;
+    const bool choose_quads = quads_ok && (g_k1_kernel == 3 || (g_k1_kernel == 0 && QUADS_BY_DEFAULT(h)));
+    if (choose_quads) {
+        static bool attr_set[2] = {false, false};
+        if (smem_quads > 48 * 1024 && !attr_set[OUT]) {
+            CUTDET_CUDA(cudaFuncSetAttribute(preprocess_quads_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[OUT] = true;
+        }
+        const int64_t out_frame = (int64_t)h.dst_h * h.dst_w * 3;
+        for (int b0 = 0; b0 < src->batch; b0 += 65535) {
+            const int nb = src->batch - b0 < 65535 ? src->batch - b0 : 65535;
+            void *o = OUT == 0 ? (void *)((float *)out + b0 * out_frame) : (void *)((uint8_t *)out + b0 * out_frame);
+            {
+                KernelScope scope("preprocess_quads_kernel", as_stream(stream));
+                preprocess_quads_kernel<OUT><<<dim3((unsigned)ceil_div(h.dst_h, QUAD_ROWS), (unsigned)nb), QUAD_THREADS, smem_quads, as_stream(stream)>>>(
+                    h, src->frames_dev + (int64_t)b0 * src->frame_stride, src->frame_stride, src->row_pitch, src->row_map_compact, o, row_pad);
+            }
+            CUTDET_LAUNCH_CHECK("preprocess_quads_kernel");
+        }
+        return CUTDET_OK;
+    }
     if (aligned && smem <= 200 * 1024 && h.dst_h <= 65535 && choose_rows) {
         static bool attr_set[2] = {false, false};
         if (smem > 48 * 1024 && !attr_set[OUT]) {
@@ -386,10 +508,19 @@ extern "C" int cutdet_resize_plan_create(int src_h, int src_w, int dst_h, int ds
     plan->n_rows = (int)plan->rows.size();
 
     // one device allocation for all tables
-    const size_t n_ints = 4 * (size_t)dst_w + 4 * (size_t)dst_h + (size_t)src_h;
+    const size_t n_xpack = ((2 * (size_t)dst_w + 3) / 4) * 4;       // first in the blob: read with 16-byte loads
+    const size_t n_ints = n_xpack + 4 * (size_t)dst_w + 4 * (size_t)dst_h + (size_t)src_h;
     std::vector<int> blob(n_ints, 0);
     int *p = blob.data();
     auto put = [&](const std::vector<int> &v, size_t n) { if (!v.empty()) memcpy(p, v.data(), n * sizeof(int)); int *r = p; p += n; return r; };
+    if (h.mode == RESIZE_LINEAR)
+        for (int x = 0; x < dst_w; ++x) {
+            int wa = a0[x], wb = a1[x];
+            if (x1[x] != x0[x] + 1) { wa += wb; wb = 0; }          // clamped at the edge: both taps are the same pixel
+            blob[2 * x] = 3 * x0[x];
+            blob[2 * x + 1] = (int)((uint32_t)wa | ((uint32_t)wb << 16));
+        }
+    p += n_xpack;
     int *hx0 = put(x0, dst_w), *hx1 = put(x1, dst_w), *ha0 = put(a0, dst_w), *ha1 = put(a1, dst_w);
     int *hy0 = put(y0, dst_h), *hy1 = put(y1, dst_h), *hb0 = put(b0, dst_h), *hb1 = put(b1, dst_h);
     int *hslot = put(slot, src_h);
@@ -407,6 +538,7 @@ extern "C" int cutdet_resize_plan_create(int src_h, int src_w, int dst_h, int ds
     h.y0 = d + (hy0 - blob.data()); h.y1 = d + (hy1 - blob.data());
     h.b0 = d + (hb0 - blob.data()); h.b1 = d + (hb1 - blob.data());
     h.row_slot = d + (hslot - blob.data());
+    h.xpack = reinterpret_cast<const int2 *>(d);
     // integer-scale gather fast path: every second tap has zero weight and taps are evenly spaced
     h.gather_step_x = 0; h.gather_step_y = 0; h.gather_off_x = 0; h.gather_off_y = 0;
     if (h.mode == RESIZE_LINEAR && h.all_a1_zero && h.all_b1_zero && dst_w > 1 && dst_h > 1) {
@@ -492,7 +624,7 @@ extern "C" int cutdet_upload_frames(const cutdet_resize_plan *plan, const uint8_
 }
 
 extern "C" int cutdet_debug_k1_kernel(int mode) {
-    CUTDET_REQUIRE(mode >= 0 && mode <= 2, "debug_k1_kernel: mode 0 (choose), 1 (one thread per pixel) or 2 (row kernel)");
+    CUTDET_REQUIRE(mode >= 0 && mode <= 3, "debug_k1_kernel: mode 0 (choose), 1 (one thread per pixel), 2 (row kernel) or 3 (quad kernel)");
     g_k1_kernel = mode;
     return CUTDET_OK;
 }

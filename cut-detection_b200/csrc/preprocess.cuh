@@ -19,6 +19,7 @@ struct ResizePlanDev {
     const int *x0, *x1, *a0, *a1;   // [dst_w]
     const int *y0, *y1, *b0, *b1;   // [dst_h]
     const int *row_slot;            // [src_h] source row -> slot in a row-compacted frame
+    const int2 *xpack;              // [dst_w] two-tap resizes: {3 * x0, a0 | a1 << 16}, a clamped edge folded into a0 (16-byte aligned)
 };
 
 int check_frames(const struct ::cutdet_resize_plan *plan, const cutdet_frames *src);

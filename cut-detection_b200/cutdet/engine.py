@@ -270,14 +270,21 @@ class NativeNet:
                                                                   ws.data_ptr(), ws.numel(), 1 if tensor_cores else 0, _stream()))
         return out
 
+    def workspace_bytes(self, batch: int, height: int, width: int) -> int:
+        need = C.c_size_t()
+        _cabi.check(_cabi.lib().cutdet_net_workspace_bytes(self.handle, batch, height, width, C.byref(need)))
+        return need.value
+
     def forward_frames(self, plan: ResizePlan, frames: torch.Tensor, compact: bool = False,
-                       out: torch.Tensor | None = None) -> torch.Tensor:
-        """Decoded uint8 BGR HWC frames -> logits, K1 fused in front of the conv stack."""
+                       out: torch.Tensor | None = None, ws: torch.Tensor | None = None) -> torch.Tensor:
+        """Decoded uint8 BGR HWC frames -> logits, K1 fused in front of the conv stack.  ``ws``: a workspace of the caller's
+        (``workspace_bytes``) instead of the net's own -- calls that run side by side on different streams each need one."""
         fs, keep = _frames_struct(plan, frames, compact)
         b = frames.shape[0]
         if out is None:
             out = torch.empty((b, self.out_features), dtype=torch.float32, device=frames.device)
-        ws = self.workspace(b, plan.dst_h, plan.dst_w, frames.device)
+        if ws is None:
+            ws = self.workspace(b, plan.dst_h, plan.dst_w, frames.device)
         _cabi.check(_cabi.lib().cutdet_net_forward_frames(self.handle, plan.handle, C.byref(fs), out.data_ptr(),
                                                           ws.data_ptr(), ws.numel(), _stream()))
         return out

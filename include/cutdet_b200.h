@@ -104,7 +104,8 @@ CUTDET_API int cutdet_upload_frames(const cutdet_resize_plan *plan, const uint8_
 CUTDET_API int cutdet_preprocess_f32(const cutdet_resize_plan *plan, const cutdet_frames *src, float *out_nchw_dev,
                           cutdet_stream_t stream);
 /* Measurement aid (tools/time_k1.py): which K1 kernel the two entry points below launch.  0 = the library chooses (default),
- * 1 = the one-thread-per-pixel kernel (any alignment), 2 = the row kernel (128-bit staged rows; 16-byte aligned frames).
+ * 1 = the one-thread-per-pixel kernel (any alignment), 2 = the row kernel (128-bit staged rows; 16-byte aligned frames),
+ * 3 = the quad kernel (two-tap resizes, four adjacent output pixels per thread; falls back where it does not apply).
  * Process-wide; the results are bit-identical either way.                                                          */
 CUTDET_API int cutdet_debug_k1_kernel(int mode);
 /* uint8 BGR HWC -> resized uint8 BGR HWC [B,H2,W2,3]: bit-exactly cv2.resize(..., INTER_LINEAR).          */

@@ -263,3 +263,48 @@ def test_push_host_ownership_contract():
         results.append(pipe.finish().to_te())
     for te in results:
         assert te["frame_types"].tolist() == [0, 2, 1] and te["run_lengths"].tolist() == [70, 30, 100]
+
+
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_pipeline_lanes_change_nothing(lanes):
+    """FramePipeline(lanes > 1) scores consecutive chunks on alternating streams with their own workspaces; the shared
+    run-length encoder takes them in order.  Same table, bit for bit, as one lane -- from device frames and from pinned host
+    frames, over several repetitions (reset in between) and with ragged chunk sizes; per-chunk results read behind
+    wait_results() are the chunk's own."""
+    from cutdet import engine, pipeline, synth
+    from frameID.net import load_default_net
+    net, _ = load_default_net()
+    native = net.eval().to("cuda")._native()
+    h, w, n, chunk = 720, 1280, 1500, 300
+    runs = [(0, 310), (2, 7), (1, 290), (2, 40), (0, 153), (1, 300), (2, 3), (1, 97), (0, 300)]
+    clip = synth.SyntheticClip(h, w, n, seed=21, runs=runs)
+    frames = clip.frames_torch(0, n, device="cuda")
+    host = frames.cpu().pin_memory()
+    plan = engine.ResizePlan.for_video(h, w, 256)
+    sizes = [300, 300, 148, 300, 2, 300, 150]
+    assert sum(sizes) == n
+
+    def run(pipe, source):
+        pipe.reset()
+        per_chunk, f0 = [], 0
+        for sz in sizes:
+            if source == "device":
+                pipe.push_device(frames[f0:f0 + sz])
+            else:
+                pipe.push_host(host[f0:f0 + sz])
+            pipe.wait_results()
+            per_chunk.append(pipe.labels[:sz].clone())
+            f0 += sz
+        te = pipe.finish().to_te()
+        return te, torch.cat(per_chunk).cpu()
+
+    one = pipeline.FramePipeline(native, plan, chunk, n, "cuda")
+    want, want_labels = run(one, "device")
+    assert want["frame_types"].tolist() == [r[0] for r in runs] and want["run_lengths"].tolist() == [r[1] for r in runs]
+    many = pipeline.FramePipeline(native, plan, chunk, n, "cuda", lanes=lanes)
+    for rep in range(3):
+        for source in ("device", "host"):
+            te, labels = run(many, source)
+            assert torch.equal(labels, want_labels), (rep, source)
+            for k in ("end_frames", "frame_types", "run_lengths", "start_frames", "score_means"):
+                assert torch.equal(te[k], want[k]), (rep, source, k)

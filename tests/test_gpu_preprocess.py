@@ -86,3 +86,33 @@ def test_no_resize_is_identity_layout():
     plan = engine.ResizePlan(144, 256, 144, 256)
     got = engine.preprocess_f32(plan, torch.from_numpy(f).cuda()).cpu().numpy()
     assert np.array_equal(got, opre.preprocess_batch(f, None))
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_every_k1_kernel_bit_exact(kernel):
+    """The library picks one of three K1 kernels per geometry and output type (one thread per pixel, staged rows, four
+    adjacent pixels per thread for two-tap resizes); cutdet_debug_k1_kernel forces each of them in turn.  Every one must give
+    the oracle's bytes for both outputs, from whole and from row-compacted frames, also where a frame's last block of output
+    rows is ragged (70 and 562 source rows) and where the selected kernel does not apply and the library falls back."""
+    from cutdet import _cabi, engine
+    lib = _cabi.lib()
+    _cabi.check(lib.cutdet_debug_k1_kernel(kernel))
+    try:
+        for w, h in GEOMETRIES:
+            if w * h > 1920 * 1080:
+                continue
+            f = _frames(w, h, 3, seed=11 + kernel)
+            plan = engine.ResizePlan.for_video(h, w, 256)
+            dev = torch.from_numpy(f).cuda()
+            nw, nh = opre.target_size(w, h)
+            want_u8 = np.stack([opre.resize_bilinear_u8(x, nw, nh) for x in f])
+            want_f32 = opre.preprocess_batch(f, 256)
+            assert np.array_equal(engine.preprocess_u8(plan, dev).cpu().numpy(), want_u8), (kernel, w, h, "u8")
+            assert np.array_equal(engine.preprocess_f32(plan, dev).cpu().numpy(), want_f32), (kernel, w, h, "f32")
+            compact = torch.from_numpy(np.ascontiguousarray(f[:, plan.rows])).cuda()
+            assert np.array_equal(engine.preprocess_u8(plan, compact, compact=True).cpu().numpy(), want_u8), (kernel, w, h, "compact u8")
+            assert np.array_equal(engine.preprocess_f32(plan, compact, compact=True).cpu().numpy(), want_f32), (kernel, w, h, "compact f32")
+            # a view that starts one frame in: frame pointers that are 16-byte aligned only when a frame's size is
+            assert np.array_equal(engine.preprocess_u8(plan, dev[1:]).cpu().numpy(), want_u8[1:]), (kernel, w, h, "offset")
+    finally:
+        _cabi.check(lib.cutdet_debug_k1_kernel(0))
