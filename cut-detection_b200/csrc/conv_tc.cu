@@ -782,6 +782,23 @@ __global__ void __launch_bounds__(416, 1) conv1_tc_kernel(const Conv1Params p) {
 constexpr int FR_CAP = 1024;                 // positions per sub-ring (a power of two)
 constexpr int FR_PLANE = (FR_CAP + 128) * 16;            // bytes of one k-half plane incl. the mirror
 constexpr int FR_SUB = 2 * FR_PLANE;
+// conv12_frames can run with a SMALLER operand ring (CAP positions, not necessarily a power of two) and hand the difference to the
+// raw-row ring: where a resized row needs two long source rows (1080p: 11.5 KB per slot) the raw ring, not the operand ring, is
+// what the unfold warps wait for.  A tile's views span 128 + 2 P1w <= 300 positions and the unfold warps work on eight rows at a
+// time, so CAP >= 3 P1w + 126 + 8/3 P1w (deadlock-free, all eight warps busy): 768 is the smallest multiple of 256 that fits.
+constexpr int FR_CAP_TWO_ROWS = 768;
+template <int CAP>
+struct FrRing {
+    static constexpr int PLANE = (CAP + 128) * 16, SUB = 2 * PLANE;
+    static constexpr int EXTRA_RAW = 3 * (FR_SUB - SUB);                  // bytes handed to the raw ring
+    static constexpr uint32_t MAGIC = (uint32_t)(0x100000000ull / CAP) + 1u;
+    static_assert(CAP % 128 == 0 && CAP <= FR_CAP && CAP >= 3 * ((256 + 2) / 3) + 126, "operand ring capacity");
+    // x mod CAP for 0 <= x < 2^22 (positions of one launch stay far below)
+    static __device__ __forceinline__ int wrap(int x) {
+        if ((CAP & (CAP - 1)) == 0) return x & (CAP - 1);
+        return x - CAP * (int)__umulhi((uint32_t)x, MAGIC);
+    }
+};
 // raw-row ring: what is left of the 227 KB (24 rows of 720p, 8 row pairs of 1080p with four unfold warps; 22 / 7 with eight)
 constexpr int raw_bytes(int unfold_warps) { return 92160 - (unfold_warps - 4) * 1056; }
 constexpr int RAW_SLOTS_MAX = 24;
@@ -947,8 +964,9 @@ struct F1Ctx {
     int rps_shift = 0;   // a raw slot holds 2^rps_shift rows (the loaders fetch and the barriers count whole slots)
 };
 
-template <int C, bool GATHER, bool ACC16, int UNFOLD_WARPS>
+template <int C, bool GATHER, bool ACC16, int UNFOLD_WARPS, int CAP = FR_CAP>
 __device__ __forceinline__ void f1_unfold_role(const F1Ctx &cx, const int pwarp, const int lane) {
+    using RG = FrRing<CAP>;
     constexpr int NP = (F_MAX_DST / 3 + 31) / 32;
     const Conv1Params &p = *cx.p;
     const FusedSrc &src = *cx.src;
@@ -987,8 +1005,8 @@ __device__ __forceinline__ void f1_unfold_role(const F1Ctx &cx, const int pwarp,
         r.slot = g - use * n_slots;
         r.R = R; r.sub = sub; y_out = y;
         r.q0 = s_raw + ((r.slot << cx.rps_shift) + (n & ((1 << cx.rps_shift) - 1))) * slot_bytes;
-        // positions [R*P1w, (R+1)*P1w) replace those FR_CAP earlier, last read by tile (pos - FR_CAP + P1w) / 128
-        const int last_reader = ((R + 2) * P1w - 1 - FR_CAP) >> 7;      // arithmetic shift: negative = none
+        // positions [R*P1w, (R+1)*P1w) replace those CAP earlier, last read by tile (pos - CAP + P1w) / 128
+        const int last_reader = ((R + 2) * P1w - 1 - CAP) >> 7;      // arithmetic shift: negative = none
         if (last_reader >= tiles_waited) {
             mbar_wait(&tile_done[last_reader & (TILE_RING - 1)], (last_reader / TILE_RING) & 1);
             tiles_waited = last_reader + 1;
@@ -1011,13 +1029,13 @@ __device__ __forceinline__ void f1_unfold_role(const F1Ctx &cx, const int pwarp,
             if (px < P1w) {
                 uint4 lo, hi;
                 chunk_from_raw<ACC16>(w[part], lo, hi);                     // zero rows: w = 0 gives the format's zeros
-                const int pos = (pos0 + part * 32) & (FR_CAP - 1);
-                uint8_t *dst = s_ring + r.sub * FR_SUB + pos * 16;
+                const int pos = RG::wrap(pos0 + part * 32);
+                uint8_t *dst = s_ring + r.sub * RG::SUB + pos * 16;
                 *reinterpret_cast<uint4 *>(dst) = lo;
-                *reinterpret_cast<uint4 *>(dst + FR_PLANE) = hi;
+                *reinterpret_cast<uint4 *>(dst + RG::PLANE) = hi;
                 if (pos < 128) {                                     // mirror past the end of the ring
-                    *reinterpret_cast<uint4 *>(dst + FR_CAP * 16) = lo;
-                    *reinterpret_cast<uint4 *>(dst + FR_CAP * 16 + FR_PLANE) = hi;
+                    *reinterpret_cast<uint4 *>(dst + CAP * 16) = lo;
+                    *reinterpret_cast<uint4 *>(dst + CAP * 16 + RG::PLANE) = hi;
                 }
             }
         }
@@ -1628,11 +1646,12 @@ struct F12Smem {
     static_assert(total <= 232448, "227 KB of shared memory per CTA");
 };
 
-template <int C, bool GATHER>
+template <int C, bool GATHER, int CAP = FR_CAP>
 __global__ void __launch_bounds__(F1Roles<true>::THREADS, 1)
 conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_constant__ CUtensorMap in_map, const MidParams p2,
                      const __grid_constant__ CUtensorMap src_map) {
     using RL = F1Roles<true>;
+    using RG = FrRing<CAP>;              // layer 1's operand ring; what it does not use of the FR_CAP layout belongs to the raw ring
     constexpr int UNFOLD_WARPS = RL::UNFOLD_WARPS, F1_MMA_WARP = RL::MMA_WARP0, F1_LOAD_WARP0 = RL::LOAD_WARP0;
     static_assert(RL::MMA_WARPS == 1, "one issuer warp in layer 1 (layer 2 adds two of the loaders)");
     using S = F1Smem<C, UNFOLD_WARPS>;
@@ -1643,7 +1662,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
     // ---- layer 1 (the layout of conv1_fused_tc_kernel)
     uint8_t *s_w = smem;
     uint8_t *s_ring = smem + S::OFF_RING;
-    uint8_t *s_raw = smem + S::OFF_RAW;
+    uint8_t *s_raw = smem + S::OFF_RAW - RG::EXTRA_RAW;
     int *s_rowoff = reinterpret_cast<int *>(smem + S::OFF_TAB);
     int *s_yb = s_rowoff + 2 * F_MAX_DST;
     int4 *s_xtab = reinterpret_cast<int4 *>(s_yb + 2 * F_MAX_DST);
@@ -1754,7 +1773,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
             bulk_load_1d(s_w, p.w_perm16, S::W_BYTES, w1_full);
         }
         for (int i = threadIdx.x; i < 2 * P1w; i += blockDim.x)
-            reinterpret_cast<uint4 *>(s_ring + 2 * FR_SUB + (i >= P1w ? FR_PLANE : 0))[FR_CAP - P1w + (i >= P1w ? i - P1w : i)] =
+            reinterpret_cast<uint4 *>(s_ring + 2 * RG::SUB + (i >= P1w ? RG::PLANE : 0))[CAP - P1w + (i >= P1w ? i - P1w : i)] =
                 make_uint4(Z2, Z2, Z2, i >= P1w ? Z2K : Z2);
         if (threadIdx.x < UNFOLD_WARPS + LOADER_WARPS) s_rows_done[threadIdx.x] = 0;    // ... and s_rows_issued
         {   // one barrier per thread (they were invalidated at the last phase change, see phase_switch)
@@ -1815,7 +1834,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
                 const int sub = (c + 2) % 3, shift = c == 0 ? -P1w : (c == 4 ? P1w : 0);
-                a_chunk[c] = ring_addr + sub * FR_SUB + (uint32_t)((t * 128 + shift) & (FR_CAP - 1)) * 16;
+                a_chunk[c] = ring_addr + sub * RG::SUB + (uint32_t)RG::wrap(t * 128 + shift + CAP) * 16;
             }
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
@@ -1824,7 +1843,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                 if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 3; ++ks) {
-                        const uint64_t da = smem_desc(a_chunk[dy + ks], FR_PLANE, 128);
+                        const uint64_t da = smem_desc(a_chunk[dy + ks], RG::PLANE, 128);
                         const uint64_t db = smem_desc(w_addr + 2 * ks * S::LBO_B, S::LBO_B, 128);
                         umma_16bit(tmem_base + 3 * C * dy, da, db, idesc1, ks > 0 ? 1u : 0u);
                     }
@@ -1982,7 +2001,7 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                 F1Ctx cx{&p, &src, s_ring, s_raw, s_cmp, s_yb, s_xtab, raw_full, raw_empty, tile_done, s_rows_done, s_rows_issued,
                          RPF, Hc, total_u, n_slots, slot_bytes, min(LOADER_WARPS, n_slots), inv_slots,
                          (it == 2 && p.timeline && blockIdx.x == 0) ? p.timeline : nullptr, rps_shift};
-                f1_unfold_role<C, GATHER, true, UNFOLD_WARPS>(cx, warp - 8, lane);
+                f1_unfold_role<C, GATHER, true, UNFOLD_WARPS, CAP>(cx, warp - 8, lane);
             }
             phase_switch(it);
             if (warp == 8 && it + 1 < n_frames_cta) {
@@ -2488,6 +2507,7 @@ int set_smem_limits() {
     CUTDET_CUDA(cudaFuncSetAttribute(conv_mid_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, MidSmem<C>::total));
     CUTDET_CUDA(cudaFuncSetAttribute(conv12_frames_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F12Smem<C>::total));
     CUTDET_CUDA(cudaFuncSetAttribute(conv12_frames_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F12Smem<C>::total));
+    CUTDET_CUDA(cudaFuncSetAttribute(conv12_frames_kernel<C, false, FR_CAP_TWO_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, F12Smem<C>::total));
     return CUTDET_OK;
 }
 
@@ -2715,9 +2735,10 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
     const int grid_cap = net->opt.conv1_grid > 0 ? net->opt.conv1_grid : 1 << 30;
     const int grid = std::min(std::min(std::min(n, sm_count()), w.sub), grid_cap);      // one layer-1 slot per CTA
     static const bool regs_ok = [] {
-        const void *fns[2] = {(const void *)conv12_frames_kernel<C, true>, (const void *)conv12_frames_kernel<C, false>};
+        const void *fns[3] = {(const void *)conv12_frames_kernel<C, true>, (const void *)conv12_frames_kernel<C, false>,
+                              (const void *)conv12_frames_kernel<C, false, FR_CAP_TWO_ROWS>};
         bool ok = true;
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 3; ++i) {
             cudaFuncAttributes a{};
             cudaFuncGetAttributes(&a, fns[i]);
             if (a.numRegs != F1Roles<true>::REGS_START) {
@@ -2728,9 +2749,16 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
         return ok;
     }();
     if (!regs_ok) return CUTDET_EUNSUPPORTED;
-    src.n_slots = (int)std::min<long long>(raw_bytes(F1Roles<true>::UNFOLD_WARPS) / ((long long)src.n_src * src.row_bytes), RAW_SLOTS_MAX);
-    src.n_slots -= src.n_slots % std::min(LOADER_WARPS, src.n_slots);
     const bool gather = src.plan.gather_step_x > 0 && src.plan.dst_w % 3 != 0;
+    // Two source rows per resized row (bilinear, 2x2): the raw ring's slots are what the unfold warps wait for (six 11.5 KB slots for
+    // eight warps at 1080p), so the operand ring gives up a quarter (net option ring_cap: 1 = keep the full operand ring)
+    // -- only where slots are scarce: 1080p 0.825 -> 0.706 ms per 1,184 frames with nine slots instead of six, 640x360 (21 slots
+    // anyway) 1 % slower with the smaller operand ring (tools/ab_ring.py, profiles/r02_ab_ring.txt)
+    const long long full_slots = raw_bytes(F1Roles<true>::UNFOLD_WARPS) / ((long long)src.n_src * src.row_bytes);
+    const bool small_ring = !gather && src.n_src == 2 && (net->opt.ring_cap == 2 || (net->opt.ring_cap == 0 && full_slots < 2 * F1Roles<true>::UNFOLD_WARPS));
+    const long long raw_ring = raw_bytes(F1Roles<true>::UNFOLD_WARPS) + (small_ring ? FrRing<FR_CAP_TWO_ROWS>::EXTRA_RAW : 0);
+    src.n_slots = (int)std::min<long long>(raw_ring / ((long long)src.n_src * src.row_bytes), RAW_SLOTS_MAX);
+    src.n_slots -= src.n_slots % std::min(LOADER_WARPS, src.n_slots);
     // Integer-scale gathers read evenly spaced source rows (row off_y + y * step_y; consecutive slots in compact frames): the
     // loaders then fetch two rows per TMA instruction through a tensor map of this launch's frames (see the kernel).
     CUtensorMap src_map;
@@ -2772,6 +2800,7 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
         KernelScope scope("conv12_frames", stream);
         const bool pdl = f0 > 0 && !net->opt.no_pdl;        // the loaders read the frames at once: only behind a kernel of ours
         if (gather) launch_pdl_window(pdl, window, conv12_frames_kernel<C, true>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2, src_map);
+        else if (small_ring) launch_pdl_window(pdl, window, conv12_frames_kernel<C, false, FR_CAP_TWO_ROWS>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2, src_map);
         else launch_pdl_window(pdl, window, conv12_frames_kernel<C, false>, grid, F1Roles<true>::THREADS, (size_t)F12Smem<C>::total, stream, c1, src, map1, p2, src_map);
     }
     CUTDET_LAUNCH_CHECK("conv12_frames_kernel");

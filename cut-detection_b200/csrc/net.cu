@@ -246,6 +246,7 @@ extern "C" int cutdet_net_set_option(cutdet_net *net, int option, int value) {
         case CUTDET_OPT_CONV1_GRID: net->opt.conv1_grid = value; break;
         case CUTDET_OPT_CONV1_VARIANT: net->opt.conv1_variant = value; break;
         case CUTDET_OPT_L2_PERSIST: net->opt.l2_persist = value; break;
+        case CUTDET_OPT_RING_CAP: net->opt.ring_cap = value; break;
         default: return fail(CUTDET_EINVAL, "net_set_option: unknown option %d", option);
     }
     return CUTDET_OK;
@@ -261,6 +262,7 @@ extern "C" int cutdet_net_get_option(const cutdet_net *net, int option, int *val
         case CUTDET_OPT_CONV1_GRID: *value = net->opt.conv1_grid; break;
         case CUTDET_OPT_CONV1_VARIANT: *value = net->opt.conv1_variant; break;
         case CUTDET_OPT_L2_PERSIST: *value = net->opt.l2_persist; break;
+        case CUTDET_OPT_RING_CAP: *value = net->opt.ring_cap; break;
         default: return fail(CUTDET_EINVAL, "net_get_option: unknown option %d", option);
     }
     return CUTDET_OK;

@@ -272,42 +272,78 @@ __global__ void __launch_bounds__(ROWS_THREADS) preprocess_rows_kernel(ResizePla
     }
 }
 
-// Two-tap (bilinear) resizes again, for the geometries where the arithmetic -- not the memory -- paces the kernels above
-// (640x360 -> 256x144 reads 15 source bytes per output pixel where 1080p reads 45): FOUR ADJACENT output pixels per thread.
-// The source rows of four output rows are staged as in the row kernel; a thread fetches the packed taps of its four columns once
-// (two 16-byte loads of plan.xpack) and uses them for two output rows; the vertical pass needs no clamp (the weights of a pair are
-// non-negative and sum to 2048, so the result is at most 255); and the outputs leave straight from registers -- a float4 per
-// channel plane (the division by 255 is a 256-entry table of correctly rounded quotients in shared memory) or the twelve packed
-// BGR bytes as three words -- with no second pass through shared memory.
+// Two-tap resizes again (bilinear, and the exact 2x2 mean), for the geometries where the arithmetic -- not the memory -- paces
+// the kernels above (640x360 -> 256x144 reads 15 source bytes per output pixel where 1080p reads 45): FOUR ADJACENT output
+// pixels per thread.  The source rows of four output rows are staged as in the row kernel; a thread fetches the packed taps of
+// its four columns once (two 16-byte loads of plan.xpack) and uses them for two output rows; the vertical pass needs no clamp
+// (the weights of a pair are non-negative and sum to 2048, so the result is at most 255); and the outputs leave straight from
+// registers -- a float4 per channel plane (the division by 255 is a 256-entry table of correctly rounded quotients in shared
+// memory) or the twelve packed BGR bytes as three words -- with no second pass through shared memory.
+// Rows need not be 16-byte aligned (854-pixel rows are 2,562 bytes): a row is staged at its own offset within a 16-byte chunk,
+// whole chunks by cp.async, the partial chunks at its two ends byte by byte, so nothing outside the row is ever read.
 constexpr int QUAD_ROWS = 4;
 constexpr int QUAD_THREADS = 128;
 
-template <int OUT>
+// Stage `bytes` bytes from g to slot + (g & 15) (slot 16-byte aligned); zero the 16 bytes behind them (the taps of the last
+// pixels read a word or two past the row).  All threads of the block take part.
+__device__ __forceinline__ void quads_stage_row(uint8_t *slot, const uint8_t *g, int bytes, int tid) {
+    const int lead = (int)(reinterpret_cast<uintptr_t>(g) & 15);
+    const uint8_t *a = g - lead;                                     // 16-byte aligned
+    const int c0 = lead ? 1 : 0, c1 = (lead + bytes) >> 4;           // whole chunks [c0, c1) lie inside the row
+    for (int k = c0 + tid; k < c1; k += QUAD_THREADS) cp_async_16(slot + 16 * k, a + 16 * k);
+    const int head = lead ? min(16 - lead, bytes) : 0;               // row bytes [0, head) share chunk 0 with what lies before the row
+    const int tail0 = max(16 * c1 - lead, head);                     // row bytes [tail0, bytes): the last, partial chunk
+    if (tid < head) slot[lead + tid] = __ldg(g + tid);
+    const int t = tid - 32;                                          // the second warp: tail bytes, then the zeros behind the row
+    if (t >= 0 && t < 32) {
+        if (tail0 + t < bytes) slot[lead + tail0 + t] = __ldg(g + tail0 + t);
+        if (t < 16) slot[lead + bytes + t] = 0;
+    }
+}
+
+// AREA: the exact 2x2 mean instead of the bilinear taps.  ALIGNED: every row starts on a 16-byte boundary (then a row sits at the
+// start of its slot and both rows of a pair share the tap offsets).  Compile-time, because the kernel runs within a few per cent
+// of the memory roofline only while its instruction count stays where it is: with both as run-time switches 640x360 fell from 90 %
+// of the HBM peak to 72 % (profiles/r02_k1_matrix_quads.txt).
+template <int OUT, bool AREA, bool ALIGNED>
 __global__ void __launch_bounds__(QUAD_THREADS, 10) preprocess_quads_kernel(ResizePlanDev plan, const uint8_t *__restrict__ frames,
-                                                                       int64_t frame_stride, int64_t row_pitch, int compact,
-                                                                       void *__restrict__ out, int row_pad) {
+                                                                           int64_t frame_stride, int64_t row_pitch, int compact,
+                                                                           void *__restrict__ out, int row_pad) {
     extern __shared__ __align__(16) uint8_t smem[];
     float *s_lut = reinterpret_cast<float *>(smem + 2 * QUAD_ROWS * row_pad);
+    int *s_lead = reinterpret_cast<int *>(smem + 2 * QUAD_ROWS * row_pad + 1024);       // [2 * QUAD_ROWS] where each row starts in its slot
     const int y_first = blockIdx.x * QUAD_ROWS, b = blockIdx.y, tid = threadIdx.x;
-    const int n16 = (3 * plan.src_w + 15) >> 4;
+    const int row_bytes = 3 * plan.src_w;
+    constexpr bool area = AREA;
+    const int n16 = (row_bytes + 15) >> 4;
     const uint8_t *frame = frames + (int64_t)b * frame_stride;
 #pragma unroll
     for (int r = 0; r < QUAD_ROWS; ++r) {
         const int y = y_first + r;
         if (y >= plan.dst_h) break;
-        int r0 = __ldg(plan.y0 + y), r1 = __ldg(plan.y1 + y);
-        const bool two = __ldg(plan.b1 + y) != 0;
+        int r0, r1;
+        bool two;
+        if (area) { r0 = 2 * y; r1 = 2 * y + 1; two = true; }
+        else { r0 = __ldg(plan.y0 + y); r1 = __ldg(plan.y1 + y); two = __ldg(plan.b1 + y) != 0; }
         if (compact) { r0 = __ldg(plan.row_slot + r0); r1 = two ? __ldg(plan.row_slot + r1) : r0; }
-        const uint4 *g0 = reinterpret_cast<const uint4 *>(frame + (int64_t)r0 * row_pitch);
-        const uint4 *g1 = reinterpret_cast<const uint4 *>(frame + (int64_t)r1 * row_pitch);
-        uint4 *d0 = reinterpret_cast<uint4 *>(smem + (2 * r) * row_pad), *d1 = reinterpret_cast<uint4 *>(smem + (2 * r + 1) * row_pad);
-        for (int i = tid; i < n16; i += QUAD_THREADS) {
-            cp_async_16(d0 + i, g0 + i);
-            if (two) cp_async_16(d1 + i, g1 + i);
-        }
-        if (tid == 0) {        // the taps of the last pixels read a word or two past the row
-            d0[n16] = make_uint4(0, 0, 0, 0);
-            d1[n16] = make_uint4(0, 0, 0, 0);
+        const uint8_t *g0 = frame + (int64_t)r0 * row_pitch, *g1 = frame + (int64_t)r1 * row_pitch;
+        if (ALIGNED) {
+            uint4 *d0 = reinterpret_cast<uint4 *>(smem + (2 * r) * row_pad), *d1 = reinterpret_cast<uint4 *>(smem + (2 * r + 1) * row_pad);
+            for (int i = tid; i < n16; i += QUAD_THREADS) {
+                cp_async_16(d0 + i, reinterpret_cast<const uint4 *>(g0) + i);
+                if (two) cp_async_16(d1 + i, reinterpret_cast<const uint4 *>(g1) + i);
+            }
+            if (tid == 0) {        // the taps of the last pixels read a word or two past the row
+                d0[n16] = make_uint4(0, 0, 0, 0);
+                d1[n16] = make_uint4(0, 0, 0, 0);
+            }
+        } else {
+            quads_stage_row(smem + (2 * r) * row_pad, g0, row_bytes, tid);
+            if (two) quads_stage_row(smem + (2 * r + 1) * row_pad, g1, row_bytes, tid);
+            if (tid == 0) {
+                s_lead[2 * r] = (int)(reinterpret_cast<uintptr_t>(g0) & 15);
+                s_lead[2 * r + 1] = two ? row_pad + (int)(reinterpret_cast<uintptr_t>(g1) & 15) : s_lead[2 * r];   // weight 0: any staged row will do
+            }
         }
     }
     if (OUT == 0)
@@ -324,26 +360,30 @@ __global__ void __launch_bounds__(QUAD_THREADS, 10) preprocess_quads_kernel(Resi
         for (int rr = 0; rr < QUAD_ROWS; rr += 2) {
             const int r = rr + half, y = y_first + r;
             if (y >= plan.dst_h) break;
-            const int yb0 = __ldg(plan.b0 + y), yb1 = __ldg(plan.b1 + y);
-            const uint8_t *s_row0 = smem + (2 * r) * row_pad;
-            const uint8_t *s_row1 = yb1 != 0 ? s_row0 + row_pad : s_row0;         // weight 0: any staged row will do
+            int yb0 = 0, yb1 = 0;
+            if (!area) { yb0 = __ldg(plan.b0 + y); yb1 = __ldg(plan.b1 + y); }
+            const uint8_t *s_slot = smem + (2 * r) * row_pad;
+            // ALIGNED: the rows sit at the start of their slots (row 1 in the next slot; with weight 0 any staged row will do)
+            const int lead0 = ALIGNED ? 0 : s_lead[2 * r], lead1 = ALIGNED ? ((area || yb1 != 0) ? row_pad : 0) : s_lead[2 * r + 1];
             uint32_t px[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t sh = (uint32_t)(off[k] & 3) * 8;
-                const uint32_t *w0 = reinterpret_cast<const uint32_t *>(s_row0 + (off[k] & ~3));
-                const uint32_t *w1 = reinterpret_cast<const uint32_t *>(s_row1 + (off[k] & ~3));
-                const uint32_t lo0 = __funnelshift_r(w0[0], w0[1], sh), hi0 = __funnelshift_r(w0[1], w0[2], sh);   // bytes 0..3, 4..7 of the pair
-                const uint32_t lo1 = __funnelshift_r(w1[0], w1[1], sh), hi1 = __funnelshift_r(w1[1], w1[2], sh);
+                const int o0 = lead0 + off[k], o1 = lead1 + off[k];
+                const uint32_t sh0 = (uint32_t)(o0 & 3) * 8, sh1 = ALIGNED ? sh0 : (uint32_t)(o1 & 3) * 8;     // (slots are 16 bytes apart)
+                const uint32_t *w0 = reinterpret_cast<const uint32_t *>(s_slot + (o0 & ~3));
+                const uint32_t *w1 = ALIGNED ? reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(w0) + lead1)
+                                             : reinterpret_cast<const uint32_t *>(s_slot + (o1 & ~3));
+                const uint32_t lo0 = __funnelshift_r(w0[0], w0[1], sh0), hi0 = __funnelshift_r(w0[1], w0[2], sh0);   // bytes 0..3, 4..7 of the pair
+                const uint32_t lo1 = __funnelshift_r(w1[0], w1[1], sh1), hi1 = __funnelshift_r(w1[1], w1[2], sh1);
                 uint32_t p = 0;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const uint32_t selc = c == 0 ? 0x7730u : (c == 1 ? 0x7741u : 0x7752u);          // (p[x0][c], p[x0+1][c]) in the low half
                     const int s0 = (int)__dp2a_lo(aw[k], __byte_perm(lo0, hi0, selc), 0u);
                     const int s1 = (int)__dp2a_lo(aw[k], __byte_perm(lo1, hi1, selc), 0u);
-                    // ((b0 (S0 >> 4)) >> 16) + ((b1 (S1 >> 4)) >> 16) + 2: the rounding 2 rides in the first product as 2 << 16 (it cannot
-                    // disturb the bits below); <= 255 by construction
-                    const int v = (((yb0 * (s0 >> 4) + 0x20000) >> 16) + ((yb1 * (s1 >> 4)) >> 16)) >> 2;
+                    // bilinear: ((b0 (S0 >> 4)) >> 16) + ((b1 (S1 >> 4)) >> 16) + 2: the rounding 2 rides in the first product as 2 << 16
+                    // (it cannot disturb the bits below); <= 255 by construction.  2x2 mean: the taps are (1, 1), S0 + S1 is the sum of four
+                    const int v = area ? (s0 + s1 + 2) >> 2 : (((yb0 * (s0 >> 4) + 0x20000) >> 16) + ((yb1 * (s1 >> 4)) >> 16)) >> 2;
                     p |= (uint32_t)v << (8 * c);
                 }
                 px[k] = p;
@@ -381,9 +421,6 @@ int check_frames(const cutdet_resize_plan *plan, const cutdet_frames *src) {
     return CUTDET_OK;
 }
 
-// The quad kernel by default where the source row is short (profiles/r02_k1_matrix.txt): few source bytes per output pixel.
-#define QUADS_BY_DEFAULT(h) (3 * (h).src_w <= 2048)
-
 template <int OUT>
 static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *src, void *out, cutdet_stream_t stream) {
     if (int rc = check_frames(plan, src)) return rc;
@@ -400,16 +437,21 @@ static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *s
     // very long rows (2160p: 78.8 % against 93.7 %); with the 4 x larger float32 output the one-thread-per-pixel kernel is
     // ahead (720p 77.6 % against 68.5 %): its coalesced 4-byte plane stores need no second pass through shared memory.
     const bool choose_rows = g_k1_kernel == 2 || (g_k1_kernel == 0 && OUT == 1 && 3 * h.src_w <= 6144);
-    // two-tap resizes with few source bytes per output pixel (360p): the quad kernel (see above)
-    const size_t smem_quads = 2 * (size_t)QUAD_ROWS * row_pad + (OUT == 0 ? 1024 : 0);
-    const bool quads_ok = h.mode == RESIZE_LINEAR && h.gather_step_x == 0 && h.dst_w % 4 == 0 && aligned && h.dst_h <= 4 * 65535 &&
+    // two-tap resizes (bilinear that is not a plain gather, the 2x2 mean): the quad kernel, whatever the alignment of the rows
+    // (profiles/r02_k1_matrix_quads.txt: 640x360 53 -> 90 % of the HBM peak, 1080p 87 -> 96 %)
+    const int quad_pad = row_pad + 16;                   // a row starts up to 15 bytes into its slot
+    const size_t smem_quads = 2 * (size_t)QUAD_ROWS * quad_pad + 1024 + 2 * QUAD_ROWS * sizeof(int);
+    const bool quads_ok = ((h.mode == RESIZE_LINEAR && h.gather_step_x == 0) || h.mode == RESIZE_AREA2) && h.dst_w % 4 == 0 &&
                           smem_quads <= 200 * 1024 && reinterpret_cast<uintptr_t>(out) % (OUT == 0 ? 16 : 4) == 0;
-    const bool choose_quads = quads_ok && (g_k1_kernel == 3 || (g_k1_kernel == 0 && QUADS_BY_DEFAULT(h)));
+    const bool choose_quads = quads_ok && (g_k1_kernel == 3 || g_k1_kernel == 0);
     if (choose_quads) {
-        static bool attr_set[2] = {false, false};
-        if (smem_quads > 48 * 1024 && !attr_set[OUT]) {
-            CUTDET_CUDA(cudaFuncSetAttribute(preprocess_quads_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set[OUT] = true;
+        const bool is_area = h.mode == RESIZE_AREA2;
+        auto quads_fn = is_area ? (aligned ? preprocess_quads_kernel<OUT, true, true> : preprocess_quads_kernel<OUT, true, false>)
+                                : (aligned ? preprocess_quads_kernel<OUT, false, true> : preprocess_quads_kernel<OUT, false, false>);
+        static bool attr_set[2][2][2] = {};
+        if (smem_quads > 48 * 1024 && !attr_set[OUT][is_area][aligned]) {
+            CUTDET_CUDA(cudaFuncSetAttribute(quads_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[OUT][is_area][aligned] = true;
         }
         const int64_t out_frame = (int64_t)h.dst_h * h.dst_w * 3;
         for (int b0 = 0; b0 < src->batch; b0 += 65535) {
@@ -417,8 +459,8 @@ static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *s
             void *o = OUT == 0 ? (void *)((float *)out + b0 * out_frame) : (void *)((uint8_t *)out + b0 * out_frame);
             {
                 KernelScope scope("preprocess_quads_kernel", as_stream(stream));
-                preprocess_quads_kernel<OUT><<<dim3((unsigned)ceil_div(h.dst_h, QUAD_ROWS), (unsigned)nb), QUAD_THREADS, smem_quads, as_stream(stream)>>>(
-                    h, src->frames_dev + (int64_t)b0 * src->frame_stride, src->frame_stride, src->row_pitch, src->row_map_compact, o, row_pad);
+                quads_fn<<<dim3((unsigned)ceil_div(h.dst_h, QUAD_ROWS), (unsigned)nb), QUAD_THREADS, smem_quads, as_stream(stream)>>>(
+                    h, src->frames_dev + (int64_t)b0 * src->frame_stride, src->frame_stride, src->row_pitch, src->row_map_compact, o, quad_pad);
             }
             CUTDET_LAUNCH_CHECK("preprocess_quads_kernel");
         }
@@ -520,6 +562,8 @@ extern "C" int cutdet_resize_plan_create(int src_h, int src_w, int dst_h, int ds
             blob[2 * x] = 3 * x0[x];
             blob[2 * x + 1] = (int)((uint32_t)wa | ((uint32_t)wb << 16));
         }
+    if (h.mode == RESIZE_AREA2)
+        for (int x = 0; x < dst_w; ++x) { blob[2 * x] = 6 * x; blob[2 * x + 1] = 0x00010001; }      // pixels 2x and 2x + 1, weights (1, 1)
     p += n_xpack;
     int *hx0 = put(x0, dst_w), *hx1 = put(x1, dst_w), *ha0 = put(a0, dst_w), *ha1 = put(a1, dst_w);
     int *hy0 = put(y0, dst_h), *hy1 = put(y1, dst_h), *hb0 = put(b0, dst_h), *hb1 = put(b1, dst_h);

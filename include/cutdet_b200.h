@@ -155,6 +155,10 @@ enum {
     CUTDET_OPT_GROUP_FRAMES = 3, /* frames per conv12_frames / conv3 launch (default 0 = 4144 = 28 per SM)                    */
     CUTDET_OPT_NO_PDL = 4,       /* 1: ordinary launches instead of programmatic dependent launch                       */
     CUTDET_OPT_CONV1_GRID = 5,   /* test hook: cap on the fused conv1 grid (several frames per CTA); 0 = no cap         */
+    CUTDET_OPT_RING_CAP = 8,     /* conv12_frames, resizes that read two source rows per output row (bilinear, 2x2): 0 (default) = a
+                                    768-position operand ring where the raw-row ring would otherwise hold fewer than 16 slots, the
+                                    freed 24 KB go to the raw-row ring (nine 11.5 KB slots at 1080p instead of six); 1 = always the
+                                    full 1,024-position operand ring; 2 = always the smaller one.  Same bits either way.       */
     CUTDET_OPT_L2_PERSIST = 7,   /* experiment: 1 = conv12_frames marks its layer-1 slots as a persisting window of the L2 (sets the
                                     context's cudaLimitPersistingL2CacheSize to the device maximum on first use)               */
     CUTDET_OPT_CONV1_VARIANT = 6 /* which kernels run layers 1 and 2 of the fused frames path; all give the same bits.

@@ -295,7 +295,10 @@ def test_dependent_launch_changes_nothing(prod_weights):
                        ("frames", {"conv1_variant": 2}), ("frames_no_pdl", {"conv1_variant": 2, "no_pdl": 1}),
                        ("frames_grid37", {"conv1_variant": 2, "conv1_grid": 37}), ("frames_group300", {"conv1_variant": 2, "group_frames": 300}),
                        # l2_persist: the layer-1 slots as a persisting window of the L2 (a cache policy, never a numerical switch)
-                       ("frames_l2_persist", {"l2_persist": 1})):
+                       ("frames_l2_persist", {"l2_persist": 1}),
+                       # ring_cap 1: the full operand ring where two source rows per output row (1080p, 360p) default to the smaller one
+                       # with more raw-row slots; also with a small grid (several frames per CTA: the ring is re-primed per frame)
+                       ("frames_full_ring", {"ring_cap": 1}), ("frames_small_ring", {"ring_cap": 2}), ("frames_small_ring_grid37", {"ring_cap": 2, "conv1_grid": 37})):
         nets[name] = engine.NativeNet(wts, params["avg_pool_size"])
         for k, v in opts.items():
             nets[name].set_option(k, v)
