@@ -816,6 +816,7 @@ struct FusedSrc {
     int tma_shift;    // conv12_frames with a tensor map of the source rows: a slot holds 2^tma_shift rows, fetched by ONE TMA box; -1 = bulk copies
     int pair_rows;    // a resized row's two source rows are adjacent in the buffer (one two-row box serves n_src = 2)
     int buf_rows;     // rows per frame in the buffer (all source rows, or the compact ones)
+    int l2_prefetch;  // conv12_frames' TMA loaders bring a slot's box into the L2 BEFORE they wait for the slot to come free
 };
 
 template <int C, int UW>
@@ -1921,13 +1922,17 @@ conv12_frames_kernel(const Conv1Params p, const FusedSrc src, const __grid_const
                         int issued = 0;
                         for (int g = lw; g < n_groups; g += n_loaders) {
                             const int use = (int)__umulhi((uint32_t)g, inv_slots), slot = g - use * n_slots;
+                            const int row_coord = src.n_src == 2 ? s_rowoff[2 * g + 1] : g << rps_shift;
+                            // (experiment) Where slots are scarce the loader waits here for thousands of cycles, and the box then takes a DRAM
+                            // round trip (~2,300 cycles from issue to landing): ask for it NOW, so that the load below finds it in the L2.
+                            if (src.l2_prefetch && elect_one()) tma_prefetch_4d_hint(&src_map, 0, 0, row_coord, f_idx, stream_once);
                             mbar_wait(&raw_empty[slot], (use & 1) ^ 1);
                             ++issued;
                             if (tlw && it == 2 && (g << rps_shift) < 200) tlw[40 + (g << rps_shift)] = clock64();
                             if (elect_one()) {
                                 mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)(slot_bytes << rps_shift));
                                 tma_load_4d_hint(s_raw + (slot << rps_shift) * slot_bytes, &src_map, &raw_full[slot], 0, 0,
-                                                 src.n_src == 2 ? s_rowoff[2 * g + 1] : g << rps_shift, f_idx, stream_once);
+                                                 row_coord, f_idx, stream_once);
                                 st_release_shared(&s_rows_issued[lw], issued);   // raw_full[slot] is now in group g's phase
                             }
                             __syncwarp();
@@ -2635,6 +2640,7 @@ bool fused_source(const cutdet_resize_plan *plan, const cutdet_frames *frames, c
     out->row_bytes = (int)row_bytes;
     out->n_slots = (int)n_slots;
     out->tma_shift = -1;
+    out->l2_prefetch = 0;
     out->pair_rows = plan->pair_rows ? 1 : 0;
     out->buf_rows = rows;
     return true;
@@ -2782,6 +2788,11 @@ int run_conv12_frames(cutdet_net *net, const Geom &g, const TcWorkspace &w, char
             src.n_slots = groups;
         }
     }
+    // CUTDET_OPT_SRC_PREFETCH (experiment, off by default): 1 = where a resized row reads two source rows (few, large slots: the
+    // loaders wait for slots), 2 = with every tensor map of the source rows.  Measured (profiles/r02_ab_ring_prefetch.txt): 1080p with
+    // SIX slots 0.822 -> 0.788 ms per 1,184 frames, with the nine slots of the smaller operand ring 0.706 -> 0.705 (the unfold warps'
+    // resize arithmetic is the limit by then); 640x360 and 720p 0.3-1 % slower (one more instruction per box for the loaders).
+    src.l2_prefetch = src.tma_shift >= 0 && (net->opt.src_prefetch == 2 || (net->opt.src_prefetch == 1 && src.n_src == 2)) ? 1 : 0;
     L2Window window;
     if (net->opt.l2_persist) {
         // experiment (CUTDET_OPT_L2_PERSIST): the layer-1 slots as a persisting window of the L2, so that the frame stream cannot push

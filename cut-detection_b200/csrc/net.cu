@@ -247,6 +247,7 @@ extern "C" int cutdet_net_set_option(cutdet_net *net, int option, int value) {
         case CUTDET_OPT_CONV1_VARIANT: net->opt.conv1_variant = value; break;
         case CUTDET_OPT_L2_PERSIST: net->opt.l2_persist = value; break;
         case CUTDET_OPT_RING_CAP: net->opt.ring_cap = value; break;
+        case CUTDET_OPT_SRC_PREFETCH: net->opt.src_prefetch = value; break;
         default: return fail(CUTDET_EINVAL, "net_set_option: unknown option %d", option);
     }
     return CUTDET_OK;
@@ -263,6 +264,7 @@ extern "C" int cutdet_net_get_option(const cutdet_net *net, int option, int *val
         case CUTDET_OPT_CONV1_VARIANT: *value = net->opt.conv1_variant; break;
         case CUTDET_OPT_L2_PERSIST: *value = net->opt.l2_persist; break;
         case CUTDET_OPT_RING_CAP: *value = net->opt.ring_cap; break;
+        case CUTDET_OPT_SRC_PREFETCH: *value = net->opt.src_prefetch; break;
         default: return fail(CUTDET_EINVAL, "net_get_option: unknown option %d", option);
     }
     return CUTDET_OK;

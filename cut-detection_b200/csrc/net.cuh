@@ -56,6 +56,7 @@ struct cutdet_net_options {
     int no_pdl = 0;           // ordinary launches instead of programmatic dependent launch
     int conv1_grid = 0;       // cap on the fused conv1 grid (test hook: several frames per CTA)
     int ring_cap = 0;         // conv12_frames with two source rows per output row: 1 = keep the full operand ring (see CUTDET_OPT_RING_CAP)
+    int src_prefetch = 0;     // experiment: conv12_frames' loaders prefetch source rows into the L2 (see CUTDET_OPT_SRC_PREFETCH)
     int l2_persist = 0;       // experiment: conv12_frames' layer-1 slots as a persisting L2 window
     int conv1_variant = 0;    // 1 = experiment: the fused conv1 kernel with two epilogue sets and an MMA issuer per block row (A/B runs)
     int timeline_kernel = 0;  // cutdet_net_debug_timeline: 1 = conv1_fused_tc, 2 = conv2_tc

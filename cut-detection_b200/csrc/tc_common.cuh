@@ -122,6 +122,12 @@ __device__ __forceinline__ void tma_load_4d_hint(void *smem_dst, const CUtensorM
         "r"(c3), "l"(policy)
         : "memory");
 }
+// ... and the same box brought into the L2 only (no shared-memory destination, no barrier): a hint, issued ahead of the load
+__device__ __forceinline__ void tma_prefetch_4d_hint(const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile.L2::cache_hint [%0, {%1, %2, %3, %4}], %5;"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+                 : "memory");
+}
 // 1-D bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16), completion on an mbarrier.
 __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

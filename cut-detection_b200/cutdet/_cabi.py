@@ -18,7 +18,7 @@ LIB_OVERRIDE = None      # development aid (bench.py --lib): load this build of 
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ECAPACITY, ELONE_ORPHAN = range(6)
 ABI_VERSION = 2
-NET_OPTIONS = {"conv1_acc32": 1, "sub_batch": 2, "group_frames": 3, "no_pdl": 4, "conv1_grid": 5, "conv1_variant": 6, "l2_persist": 7, "ring_cap": 8}
+NET_OPTIONS = {"conv1_acc32": 1, "sub_batch": 2, "group_frames": 3, "no_pdl": 4, "conv1_grid": 5, "conv1_variant": 6, "l2_persist": 7, "ring_cap": 8, "src_prefetch": 9}
 
 
 class Frames(C.Structure):

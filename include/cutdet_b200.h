@@ -159,6 +159,10 @@ enum {
                                     768-position operand ring where the raw-row ring would otherwise hold fewer than 16 slots, the
                                     freed 24 KB go to the raw-row ring (nine 11.5 KB slots at 1080p instead of six); 1 = always the
                                     full 1,024-position operand ring; 2 = always the smaller one.  Same bits either way.       */
+    CUTDET_OPT_SRC_PREFETCH = 9, /* experiment: conv12_frames' TMA loaders ask for a slot's source rows in the L2
+                                    (cp.async.bulk.prefetch.tensor) before they wait for the slot: 0 (default) = never, 1 = for resizes
+                                    with two source rows per output row, 2 = with every tensor map of the source rows.  A cache
+                                    hint: same bits; measured neutral once the raw ring has nine slots (profiles/README.md).      */
     CUTDET_OPT_L2_PERSIST = 7,   /* experiment: 1 = conv12_frames marks its layer-1 slots as a persisting window of the L2 (sets the
                                     context's cudaLimitPersistingL2CacheSize to the device maximum on first use)               */
     CUTDET_OPT_CONV1_VARIANT = 6 /* which kernels run layers 1 and 2 of the fused frames path; all give the same bits.

@@ -298,7 +298,9 @@ def test_dependent_launch_changes_nothing(prod_weights):
                        ("frames_l2_persist", {"l2_persist": 1}),
                        # ring_cap 1: the full operand ring where two source rows per output row (1080p, 360p) default to the smaller one
                        # with more raw-row slots; also with a small grid (several frames per CTA: the ring is re-primed per frame)
-                       ("frames_full_ring", {"ring_cap": 1}), ("frames_small_ring", {"ring_cap": 2}), ("frames_small_ring_grid37", {"ring_cap": 2, "conv1_grid": 37})):
+                       ("frames_full_ring", {"ring_cap": 1}), ("frames_small_ring", {"ring_cap": 2}), ("frames_small_ring_grid37", {"ring_cap": 2, "conv1_grid": 37}),
+                       # src_prefetch: the loaders' L2 prefetch of the source rows (a cache hint), off and for every geometry
+                       ("frames_prefetch_two_rows", {"src_prefetch": 1}), ("frames_prefetch_all", {"src_prefetch": 2})):
         nets[name] = engine.NativeNet(wts, params["avg_pool_size"])
         for k, v in opts.items():
             nets[name].set_option(k, v)

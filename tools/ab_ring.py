@@ -1,5 +1,7 @@
-"""Same-process A/B of conv12_frames' operand-ring capacity where a resized row reads two source rows (net option ring_cap:
-2 = 768 positions and a larger raw-row ring, 1 = the full 1,024; 0 = the library's choice): ms per forward_frames call, interleaved, and bit-equality.
+"""Same-process A/B of conv12_frames' row-supply options: the operand-ring capacity where a resized row reads two source rows
+(net option ring_cap: 2 = 768 positions and a larger raw-row ring, 1 = the full 1,024; 0 = the library's choice) and the loaders'
+L2 prefetch of the source rows (src_prefetch: 0 = never, 1 = two-row geometries, 2 = every tensor map): ms per forward_frames
+call, interleaved, and bit-equality.
     python tools/ab_ring.py"""
 import os, sys
 import torch
@@ -9,10 +11,13 @@ from cutdet import engine, synth
 from frameID.net import load_default_net
 
 nets = {}
-for name, cap in (("small_ring", 2), ("full_ring", 1)):
+VARIANTS = (("default", {}), ("prefetch_two_rows", {"src_prefetch": 1}), ("prefetch_all", {"src_prefetch": 2}), ("full_ring", {"ring_cap": 1}),
+            ("full_ring_prefetch", {"ring_cap": 1, "src_prefetch": 1}))
+for name, opts in VARIANTS:
     net, _ = load_default_net()
     nets[name] = net.eval().to("cuda")._native()
-    nets[name].set_option("ring_cap", cap)
+    for k, v in opts.items():
+        nets[name].set_option(k, v)
 for h, w, n in ((1080, 1920, 1184), (360, 640, 2368), (720, 1280, 1184)):
     frames = synth.SyntheticClip(h, w, n, seed=3).frames_torch(0, n, device="cuda")
     plan = engine.ResizePlan.for_video(h, w, 256)
@@ -21,7 +26,7 @@ for h, w, n in ((1080, 1920, 1184), (360, 640, 2368), (720, 1280, 1184)):
         for _ in range(2):
             outs[name] = net.forward_frames(plan, frames)
     torch.cuda.synchronize()
-    print(f"{w}x{h} x{n}: logits bit-equal: {bool(torch.equal(outs['small_ring'], outs['full_ring']))}", flush=True)
+    print(f"{w}x{h} x{n}: logits bit-equal: {all(bool(torch.equal(outs['default'], o)) for o in outs.values())}", flush=True)
     for rep in range(3):
         for name, net in nets.items():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,6 +36,6 @@ for h, w, n in ((1080, 1920, 1184), (360, 640, 2368), (720, 1280, 1184)):
             b.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / 10
-            print(f"  rep {rep} {name:10s} {ms:.3f} ms per {n} frames = {n / ms * 1e3:,.0f} frames/s", flush=True)
+            print(f"  rep {rep} {name:22s} {ms:.3f} ms per {n} frames = {n / ms * 1e3:,.0f} frames/s", flush=True)
     del frames
     torch.cuda.empty_cache()
