@@ -868,6 +868,26 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
     return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16);
 }
 
+// The bilinear case alone (no dispatch on the plan inside): the unfold warps keep FOUR of these in flight per lane.
+__device__ __forceinline__ uint32_t bilinear_word(const uint8_t *q0, const uint8_t *q1, const int4 *s_xtab, int b0, int b1, int x) {
+    const int4 xt = s_xtab[x];
+    const uint32_t sh = (uint32_t)(xt.x & 3) * 8, aw = (uint32_t)xt.y;
+    const uint32_t *r0 = reinterpret_cast<const uint32_t *>(q0 + (xt.x & ~3));
+    const uint32_t *r1 = reinterpret_cast<const uint32_t *>(q1 + (xt.x & ~3));
+    const uint32_t lo0 = __funnelshift_r(r0[0], r0[1], sh), hi0 = __funnelshift_r(r0[1], r0[2], sh);
+    const uint32_t lo1 = __funnelshift_r(r1[0], r1[1], sh), hi1 = __funnelshift_r(r1[1], r1[2], sh);
+    uint32_t word = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t selc = c == 0 ? 0x7730u : (c == 1 ? 0x7741u : 0x7752u);
+        const int s0 = (int)__dp2a_lo(aw, __byte_perm(lo0, hi0, selc), 0u);
+        const int s1 = (int)__dp2a_lo(aw, __byte_perm(lo1, hi1, selc), 0u);
+        // ((b0 (S0 >> 4)) >> 16) + ((b1 (S1 >> 4)) >> 16) + 2, the 2 riding in the first product as 2 << 16; <= 255 by construction
+        word |= (uint32_t)((((b0 * (s0 >> 4) + 0x20000) >> 16) + ((b1 * (s1 >> 4)) >> 16)) >> 2) << (8 * c);
+    }
+    return word;
+}
+
 // Warps 0..7 = epilogue, then the unfold warps, the MMA issuer (+ TMEM alloc) and three loaders (F1Roles below: 640 threads with
 // fp16 accumulators, 512 with fp32 ones).
 //
@@ -1069,7 +1089,23 @@ __device__ __forceinline__ void f1_unfold_role(const F1Ctx &cx, const int pwarp,
             if (r0.real) {
                 const uint8_t *q1 = r0.q0 + (src.n_src - 1) * src.row_bytes;
                 const int b0 = s_yb[2 * y0], b1 = s_yb[2 * y0 + 1];
-                for (int x = lane; x < plan.dst_w; x += 32) cmp[1 + x] = resized_word(plan, r0.q0, q1, s_xtab, b0, b1, x);
+                if (plan.mode == RESIZE_LINEAR && plan.gather_step_x == 0) {
+                    // Four pixels per lane at a time, results held in registers until all four are done: one pixel is a chain of
+                    // ~12 dependent steps behind two rounds of shared-memory loads, and a store to cmp between two pixels would
+                    // order the next pixel's loads behind it (q0 is a byte pointer: it may alias anything).  One pixel at a time
+                    // with the dispatch on the plan inside the loop took ~3,600 cycles per 1080p row and warp.
+                    const int last = plan.dst_w - 1;
+                    for (int xb = lane; xb < plan.dst_w; xb += 128) {
+                        uint32_t v[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[k] = bilinear_word(r0.q0, q1, s_xtab, b0, b1, min(xb + 32 * k, last));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (xb + 32 * k <= last) cmp[1 + xb + 32 * k] = v[k];
+                    }
+                } else {
+                    for (int x = lane; x < plan.dst_w; x += 32) cmp[1 + x] = resized_word(plan, r0.q0, q1, s_xtab, b0, b1, x);
+                }
             }
             __syncwarp();
 #pragma unroll
