@@ -868,7 +868,10 @@ __device__ __forceinline__ uint32_t resized_word(const ResizePlanDev &plan, cons
     return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16);
 }
 
-// The bilinear case alone (no dispatch on the plan inside): the unfold warps keep FOUR of these in flight per lane.
+// The bilinear case alone (no dispatch on the plan inside): the unfold warps keep F1_RESIZE_ILP of these in flight per lane.
+#ifndef F1_RESIZE_ILP
+#define F1_RESIZE_ILP 4
+#endif
 __device__ __forceinline__ uint32_t bilinear_word(const uint8_t *q0, const uint8_t *q1, const int4 *s_xtab, int b0, int b1, int x) {
     const int4 xt = s_xtab[x];
     const uint32_t sh = (uint32_t)(xt.x & 3) * 8, aw = (uint32_t)xt.y;
@@ -1095,12 +1098,12 @@ __device__ __forceinline__ void f1_unfold_role(const F1Ctx &cx, const int pwarp,
                     // order the next pixel's loads behind it (q0 is a byte pointer: it may alias anything).  One pixel at a time
                     // with the dispatch on the plan inside the loop took ~3,600 cycles per 1080p row and warp.
                     const int last = plan.dst_w - 1;
-                    for (int xb = lane; xb < plan.dst_w; xb += 128) {
-                        uint32_t v[4];
+                    for (int xb = lane; xb < plan.dst_w; xb += 32 * F1_RESIZE_ILP) {
+                        uint32_t v[F1_RESIZE_ILP];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) v[k] = bilinear_word(r0.q0, q1, s_xtab, b0, b1, min(xb + 32 * k, last));
+                        for (int k = 0; k < F1_RESIZE_ILP; ++k) v[k] = bilinear_word(r0.q0, q1, s_xtab, b0, b1, min(xb + 32 * k, last));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        for (int k = 0; k < F1_RESIZE_ILP; ++k)
                             if (xb + 32 * k <= last) cmp[1 + xb + 32 * k] = v[k];
                     }
                 } else {

@@ -2,11 +2,15 @@
 (net option ring_cap: 2 = 768 positions and a larger raw-row ring, 1 = the full 1,024; 0 = the library's choice) and the loaders'
 L2 prefetch of the source rows (src_prefetch: 0 = never, 1 = two-row geometries, 2 = every tensor map): ms per forward_frames
 call, interleaved, and bit-equality.
-    python tools/ab_ring.py"""
+    python tools/ab_ring.py [libcutdet_b200.so of another build]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "cut-detection_b200")]
+from cutdet import _cabi
+if len(sys.argv) > 1:                 # another build of the library (e.g. compiled with -DF1_RESIZE_ILP=8)
+    _cabi.LIB_OVERRIDE = os.path.abspath(sys.argv[1])
+    print("library:", sys.argv[1])
 from cutdet import engine, synth
 from frameID.net import load_default_net
 
