@@ -286,7 +286,7 @@ constexpr int QUAD_THREADS = 128;
 
 // Stage `bytes` bytes from g to slot + (g & 15) (slot 16-byte aligned); zero the 16 bytes behind them (the taps of the last
 // pixels read a word or two past the row).  All threads of the block take part.
-__device__ __forceinline__ void quads_stage_row(uint8_t *slot, const uint8_t *g, int bytes, int tid) {
+__device__ __noinline__ void quads_stage_row(uint8_t *slot, const uint8_t *g, int bytes, int tid) {
     const int lead = (int)(reinterpret_cast<uintptr_t>(g) & 15);
     const uint8_t *a = g - lead;                                     // 16-byte aligned
     const int c0 = lead ? 1 : 0, c1 = (lead + bytes) >> 4;           // whole chunks [c0, c1) lie inside the row
@@ -301,20 +301,23 @@ __device__ __forceinline__ void quads_stage_row(uint8_t *slot, const uint8_t *g,
     }
 }
 
-// AREA: the exact 2x2 mean instead of the bilinear taps.  ALIGNED: every row starts on a 16-byte boundary (then a row sits at the
+// MODE: 0 = bilinear taps, 1 = the exact 2x2 mean, 2 = one source pixel per output pixel (integer-scale gathers such as 720p ->
+// 256x144, plain copies: one source row per output row, no arithmetic).  ALIGNED: every row starts on a 16-byte boundary (then a row sits at the
 // start of its slot and both rows of a pair share the tap offsets).  Compile-time, because the kernel runs within a few per cent
 // of the memory roofline only while its instruction count stays where it is: with both as run-time switches 640x360 fell from 90 %
 // of the HBM peak to 72 % (profiles/r02_k1_matrix_quads.txt).
-template <int OUT, bool AREA, bool ALIGNED>
+template <int OUT, int MODE, bool ALIGNED>
 __global__ void __launch_bounds__(QUAD_THREADS, 10) preprocess_quads_kernel(ResizePlanDev plan, const uint8_t *__restrict__ frames,
                                                                            int64_t frame_stride, int64_t row_pitch, int compact,
-                                                                           void *__restrict__ out, int row_pad) {
+                                                                           void *__restrict__ out, int row_pad,
+                                                                           const uint8_t *safe_lo, const uint8_t *safe_hi) {
     extern __shared__ __align__(16) uint8_t smem[];
-    float *s_lut = reinterpret_cast<float *>(smem + 2 * QUAD_ROWS * row_pad);
-    int *s_lead = reinterpret_cast<int *>(smem + 2 * QUAD_ROWS * row_pad + 1024);       // [2 * QUAD_ROWS] where each row starts in its slot
+    constexpr int SPR = MODE == 2 ? 1 : 2;          // slots (source rows) per output row
+    float *s_lut = reinterpret_cast<float *>(smem + SPR * QUAD_ROWS * row_pad);
+    int *s_lead = reinterpret_cast<int *>(smem + SPR * QUAD_ROWS * row_pad + 1024);       // [2 * QUAD_ROWS] where each row starts in its slot
     const int y_first = blockIdx.x * QUAD_ROWS, b = blockIdx.y, tid = threadIdx.x;
     const int row_bytes = 3 * plan.src_w;
-    constexpr bool area = AREA;
+    constexpr bool area = MODE == 1, pick = MODE == 2;
     const int n16 = (row_bytes + 15) >> 4;
     const uint8_t *frame = frames + (int64_t)b * frame_stride;
 #pragma unroll
@@ -324,22 +327,39 @@ __global__ void __launch_bounds__(QUAD_THREADS, 10) preprocess_quads_kernel(Resi
         int r0, r1;
         bool two;
         if (area) { r0 = 2 * y; r1 = 2 * y + 1; two = true; }
+        else if (pick) { r0 = r1 = plan.gather_step_y > 0 ? plan.gather_off_y + y * plan.gather_step_y : y; two = false; }
         else { r0 = __ldg(plan.y0 + y); r1 = __ldg(plan.y1 + y); two = __ldg(plan.b1 + y) != 0; }
         if (compact) { r0 = __ldg(plan.row_slot + r0); r1 = two ? __ldg(plan.row_slot + r1) : r0; }
         const uint8_t *g0 = frame + (int64_t)r0 * row_pitch, *g1 = frame + (int64_t)r1 * row_pitch;
         if (ALIGNED) {
-            uint4 *d0 = reinterpret_cast<uint4 *>(smem + (2 * r) * row_pad), *d1 = reinterpret_cast<uint4 *>(smem + (2 * r + 1) * row_pad);
+            uint4 *d0 = reinterpret_cast<uint4 *>(smem + (SPR * r) * row_pad), *d1 = reinterpret_cast<uint4 *>(smem + (SPR * r + 1) * row_pad);
             for (int i = tid; i < n16; i += QUAD_THREADS) {
                 cp_async_16(d0 + i, reinterpret_cast<const uint4 *>(g0) + i);
-                if (two) cp_async_16(d1 + i, reinterpret_cast<const uint4 *>(g1) + i);
+                if (!pick && two) cp_async_16(d1 + i, reinterpret_cast<const uint4 *>(g1) + i);
             }
             if (tid == 0) {        // the taps of the last pixels read a word or two past the row
                 d0[n16] = make_uint4(0, 0, 0, 0);
-                d1[n16] = make_uint4(0, 0, 0, 0);
+                if (!pick) d1[n16] = make_uint4(0, 0, 0, 0);
             }
         } else {
-            quads_stage_row(smem + (2 * r) * row_pad, g0, row_bytes, tid);
-            if (two) quads_stage_row(smem + (2 * r + 1) * row_pad, g1, row_bytes, tid);
+            // Unaligned rows: whole 16-byte chunks from the aligned address below the row to the one above its end, i.e. up to 15
+            // bytes of the NEIGHBOURING rows on either side -- allowed wherever that stays inside [safe_lo, safe_hi), the bytes of
+            // this launch's frames (bytes past a row only ever meet zero weights); the first and last rows of the batch, where it
+            // would not, are staged exactly.
+            auto stage = [&](uint8_t *slot, const uint8_t *g) {
+                const int lead = (int)(reinterpret_cast<uintptr_t>(g) & 15), nch = (lead + row_bytes + 15) >> 4;
+                const uint8_t *a = g - lead;
+                if (a >= safe_lo && a + 16 * nch <= safe_hi) {
+                    for (int i = tid; i <= nch; i += QUAD_THREADS) {
+                        if (i < nch) cp_async_16(slot + 16 * i, a + 16 * i);
+                        else *reinterpret_cast<uint4 *>(slot + 16 * i) = make_uint4(0, 0, 0, 0);
+                    }
+                } else {
+                    quads_stage_row(slot, g, row_bytes, tid);
+                }
+            };
+            stage(smem + (SPR * r) * row_pad, g0);
+            if (!pick && two) stage(smem + (SPR * r + 1) * row_pad, g1);
             if (tid == 0) {
                 s_lead[2 * r] = (int)(reinterpret_cast<uintptr_t>(g0) & 15);
                 s_lead[2 * r + 1] = two ? row_pad + (int)(reinterpret_cast<uintptr_t>(g1) & 15) : s_lead[2 * r];   // weight 0: any staged row will do
@@ -361,8 +381,8 @@ __global__ void __launch_bounds__(QUAD_THREADS, 10) preprocess_quads_kernel(Resi
             const int r = rr + half, y = y_first + r;
             if (y >= plan.dst_h) break;
             int yb0 = 0, yb1 = 0;
-            if (!area) { yb0 = __ldg(plan.b0 + y); yb1 = __ldg(plan.b1 + y); }
-            const uint8_t *s_slot = smem + (2 * r) * row_pad;
+            if (MODE == 0) { yb0 = __ldg(plan.b0 + y); yb1 = __ldg(plan.b1 + y); }
+            const uint8_t *s_slot = smem + (SPR * r) * row_pad;
             // ALIGNED: the rows sit at the start of their slots (row 1 in the next slot; with weight 0 any staged row will do)
             const int lead0 = ALIGNED ? 0 : s_lead[2 * r], lead1 = ALIGNED ? ((area || yb1 != 0) ? row_pad : 0) : s_lead[2 * r + 1];
             uint32_t px[4];
@@ -373,6 +393,10 @@ __global__ void __launch_bounds__(QUAD_THREADS, 10) preprocess_quads_kernel(Resi
                 const uint32_t *w0 = reinterpret_cast<const uint32_t *>(s_slot + (o0 & ~3));
                 const uint32_t *w1 = ALIGNED ? reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(w0) + lead1)
                                              : reinterpret_cast<const uint32_t *>(s_slot + (o1 & ~3));
+                if (pick) {                // the pixel itself: three bytes out of two words
+                    px[k] = __funnelshift_r(w0[0], w0[1], sh0) & 0x00FFFFFFu;
+                    continue;
+                }
                 const uint32_t lo0 = __funnelshift_r(w0[0], w0[1], sh0), hi0 = __funnelshift_r(w0[1], w0[2], sh0);   // bytes 0..3, 4..7 of the pair
                 const uint32_t lo1 = __funnelshift_r(w1[0], w1[1], sh1), hi1 = __funnelshift_r(w1[1], w1[2], sh1);
                 uint32_t p = 0;
@@ -421,6 +445,9 @@ int check_frames(const cutdet_resize_plan *plan, const cutdet_frames *src) {
     return CUTDET_OK;
 }
 
+// Where the quad kernel is the default: every two-tap resize; gathers and copies per measurement (profiles/r02_k1_matrix_final.txt)
+#define QUADS_BY_DEFAULT(one_pixel, out, row_bytes) (!(one_pixel) || (row_bytes) <= 6144)
+
 template <int OUT>
 static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *src, void *out, cutdet_stream_t stream) {
     if (int rc = check_frames(plan, src)) return rc;
@@ -432,35 +459,39 @@ static int launch_generic(const cutdet_resize_plan *plan, const cutdet_frames *s
     const int row_pad = ((3 * h.src_w + 15) / 16 + 1) * 16;
     const int out_bytes = OUT == 0 ? 3 * h.dst_w * 4 : (3 * h.dst_w + 15) / 16 * 16;
     const size_t smem = (size_t)ROWS_PER_BLOCK * (2 * (size_t)row_pad + out_bytes);
-    // Which kernel (profiles/r02_k1_matrix.txt, B200, frames resident in HBM): the row kernel wins where the output is the small
-    // uint8 image (720p 73.5 % of the HBM peak against 69.2 %, 1080p 92.8 % against 83.9 %, 360p 45.6 against 41.4) except for
-    // very long rows (2160p: 78.8 % against 93.7 %); with the 4 x larger float32 output the one-thread-per-pixel kernel is
-    // ahead (720p 77.6 % against 68.5 %): its coalesced 4-byte plane stores need no second pass through shared memory.
+    // Which kernel (profiles/r02_k1_matrix_final.txt, B200, frames resident in HBM): the quad kernel wherever it applies, except for
+    // gathers from rows longer than 6 KB (2160p: 88 % of the HBM peak against 95 % for one thread per pixel).  Where it does not
+    // apply (an output width that is not a multiple of four, a misaligned output) the row kernel takes the uint8 output of aligned
+    // frames with rows up to 6 KB and the one-thread-per-pixel kernel the rest, as before the quad kernel existed.
     const bool choose_rows = g_k1_kernel == 2 || (g_k1_kernel == 0 && OUT == 1 && 3 * h.src_w <= 6144);
-    // two-tap resizes (bilinear that is not a plain gather, the 2x2 mean): the quad kernel, whatever the alignment of the rows
-    // (profiles/r02_k1_matrix_quads.txt: 640x360 53 -> 90 % of the HBM peak, 1080p 87 -> 96 %)
-    const int quad_pad = row_pad + 16;                   // a row starts up to 15 bytes into its slot
-    const size_t smem_quads = 2 * (size_t)QUAD_ROWS * quad_pad + 1024 + 2 * QUAD_ROWS * sizeof(int);
-    const bool quads_ok = ((h.mode == RESIZE_LINEAR && h.gather_step_x == 0) || h.mode == RESIZE_AREA2) && h.dst_w % 4 == 0 &&
-                          smem_quads <= 200 * 1024 && reinterpret_cast<uintptr_t>(out) % (OUT == 0 ? 16 : 4) == 0;
-    const bool choose_quads = quads_ok && (g_k1_kernel == 3 || g_k1_kernel == 0);
+    const int quad_pad = row_pad + 32;                   // a row starts up to 15 bytes into its slot; one chunk of zeros behind it
+    const bool one_pixel = h.gather_step_x > 0 || h.mode == RESIZE_COPY;        // a gather or a copy: no arithmetic
+    const int quad_mode = one_pixel ? 2 : (h.mode == RESIZE_AREA2 ? 1 : 0);
+    const size_t smem_quads = (one_pixel ? 1 : 2) * (size_t)QUAD_ROWS * quad_pad + 1024 + 2 * QUAD_ROWS * sizeof(int);
+    const bool quads_ok = h.dst_w % 4 == 0 && smem_quads <= 200 * 1024 && reinterpret_cast<uintptr_t>(out) % (OUT == 0 ? 16 : 4) == 0;
+    const bool choose_quads = quads_ok && (g_k1_kernel == 3 || (g_k1_kernel == 0 && QUADS_BY_DEFAULT(one_pixel, OUT, 3 * h.src_w)));
     if (choose_quads) {
-        const bool is_area = h.mode == RESIZE_AREA2;
-        auto quads_fn = is_area ? (aligned ? preprocess_quads_kernel<OUT, true, true> : preprocess_quads_kernel<OUT, true, false>)
-                                : (aligned ? preprocess_quads_kernel<OUT, false, true> : preprocess_quads_kernel<OUT, false, false>);
-        static bool attr_set[2][2][2] = {};
-        if (smem_quads > 48 * 1024 && !attr_set[OUT][is_area][aligned]) {
+        using QuadsFn = void (*)(ResizePlanDev, const uint8_t *, int64_t, int64_t, int, void *, int, const uint8_t *, const uint8_t *);
+        static const QuadsFn fns[3][2] = {{preprocess_quads_kernel<OUT, 0, false>, preprocess_quads_kernel<OUT, 0, true>},
+                                          {preprocess_quads_kernel<OUT, 1, false>, preprocess_quads_kernel<OUT, 1, true>},
+                                          {preprocess_quads_kernel<OUT, 2, false>, preprocess_quads_kernel<OUT, 2, true>}};
+        const QuadsFn quads_fn = fns[quad_mode][aligned];
+        static bool attr_set[2][3][2] = {};
+        if (smem_quads > 48 * 1024 && !attr_set[OUT][quad_mode][aligned]) {
             CUTDET_CUDA(cudaFuncSetAttribute(quads_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set[OUT][is_area][aligned] = true;
+            attr_set[OUT][quad_mode][aligned] = true;
         }
         const int64_t out_frame = (int64_t)h.dst_h * h.dst_w * 3;
         for (int b0 = 0; b0 < src->batch; b0 += 65535) {
             const int nb = src->batch - b0 < 65535 ? src->batch - b0 : 65535;
             void *o = OUT == 0 ? (void *)((float *)out + b0 * out_frame) : (void *)((uint8_t *)out + b0 * out_frame);
+            const uint8_t *first = src->frames_dev + (int64_t)b0 * src->frame_stride;
+            const int buf_rows = src->row_map_compact ? plan->n_rows : h.src_h;
+            const uint8_t *past = first + (int64_t)(nb - 1) * src->frame_stride + (int64_t)(buf_rows - 1) * src->row_pitch + 3 * (int64_t)h.src_w;
             {
                 KernelScope scope("preprocess_quads_kernel", as_stream(stream));
                 quads_fn<<<dim3((unsigned)ceil_div(h.dst_h, QUAD_ROWS), (unsigned)nb), QUAD_THREADS, smem_quads, as_stream(stream)>>>(
-                    h, src->frames_dev + (int64_t)b0 * src->frame_stride, src->frame_stride, src->row_pitch, src->row_map_compact, o, quad_pad);
+                    h, first, src->frame_stride, src->row_pitch, src->row_map_compact, o, quad_pad, first, past);
             }
             CUTDET_LAUNCH_CHECK("preprocess_quads_kernel");
         }
@@ -564,6 +595,8 @@ extern "C" int cutdet_resize_plan_create(int src_h, int src_w, int dst_h, int ds
         }
     if (h.mode == RESIZE_AREA2)
         for (int x = 0; x < dst_w; ++x) { blob[2 * x] = 6 * x; blob[2 * x + 1] = 0x00010001; }      // pixels 2x and 2x + 1, weights (1, 1)
+    if (h.mode == RESIZE_COPY)
+        for (int x = 0; x < dst_w; ++x) { blob[2 * x] = 3 * x; blob[2 * x + 1] = 2048; }
     p += n_xpack;
     int *hx0 = put(x0, dst_w), *hx1 = put(x1, dst_w), *ha0 = put(a0, dst_w), *ha1 = put(a1, dst_w);
     int *hy0 = put(y0, dst_h), *hy1 = put(y1, dst_h), *hb0 = put(b0, dst_h), *hb1 = put(b1, dst_h);
