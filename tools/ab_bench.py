@@ -7,7 +7,7 @@ comparable when they are measured on ONE box, interleaved, a few times each:
     python tools/ab_bench.py --reps 2 --steps 30,80 -- "" "sub_batch=296" "conv1_variant=1" "lib=gpurun_out/libcutdet_old.so"
 
 Each variant is a space-separated list of NAME=VALUE pairs ("" = the defaults): net options (bench.py --net-opt) or
-``lib=PATH`` (bench.py --lib: another build of libcutdet_b200.so) or ``lanes=N`` (bench.py --lanes).  Prints one line per run and a summary table
+``lib=PATH`` (bench.py --lib: another build of libcutdet_b200.so) or ``lanes=N`` / ``chunk=N`` (bench.py --lanes / --chunk).  Prints one line per run and a summary table
 (mean / min / max frames per second per variant and step count); with --out also writes them to a text file for profiles/."""
 import argparse
 import json
@@ -36,7 +36,7 @@ def main():
                 cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(st), "--no-e2e", "--no-cpu-baseline"]
                 for kv in v.split():
                     k, _, val = kv.partition("=")
-                    cmd += ["--lib", val] if k == "lib" else ["--lanes", val] if k == "lanes" else ["--net-opt", kv]
+                    cmd += ["--lib", val] if k == "lib" else [f"--{k}", val] if k in ("lanes", "chunk") else ["--net-opt", kv]
                 try:
                     r = subprocess.run(cmd, capture_output=True, text=True, timeout=a.timeout)
                     d = json.loads(r.stdout.strip().splitlines()[-1])
