@@ -308,3 +308,35 @@ def test_pipeline_lanes_change_nothing(lanes):
             assert torch.equal(labels, want_labels), (rep, source)
             for k in ("end_frames", "frame_types", "run_lengths", "start_frames", "score_means"):
                 assert torch.equal(te[k], want[k]), (rep, source, k)
+
+
+def test_forward_frames_in_a_cuda_graph():
+    """After its first call for a geometry the library allocates and synchronises nothing, so its launches -- programmatic
+    dependent launches and tensor maps included -- can be captured into a CUDA graph as they are.  A replayed
+    graph must give the eager call's logits bit for bit, also after the input buffer's contents change."""
+    from cutdet import engine, synth
+    from frameID.net import load_default_net
+    net, _ = load_default_net()
+    native = net.eval().to("cuda")._native()
+    h, w, n = 720, 1280, 300
+    clip = synth.SyntheticClip(h, w, 2 * n, seed=5)
+    a, b = clip.frames_torch(0, n, device="cuda"), clip.frames_torch(n, n, device="cuda")
+    plan = engine.ResizePlan.for_video(h, w, 256)
+    want_a, want_b = native.forward_frames(plan, a).clone(), native.forward_frames(plan, b).clone()
+    static_in = a.clone()
+    out = torch.empty_like(want_a)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        native.forward_frames(plan, static_in, out=out)          # warm on the capture stream
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            native.forward_frames(plan, static_in, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    for frames, want in ((a, want_a), (b, want_b), (a, want_a)):
+        static_in.copy_(frames)
+        out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want)
