@@ -885,7 +885,8 @@ __device__ __forceinline__ uint32_t bilinear_word(const uint8_t *q0, const uint8
         const uint32_t selc = c == 0 ? 0x7730u : (c == 1 ? 0x7741u : 0x7752u);
         const int s0 = (int)__dp2a_lo(aw, __byte_perm(lo0, hi0, selc), 0u);
         const int s1 = (int)__dp2a_lo(aw, __byte_perm(lo1, hi1, selc), 0u);
-        // ((b0 (S0 >> 4)) >> 16) + ((b1 (S1 >> 4)) >> 16) + 2, the 2 riding in the first product as 2 << 16; <= 255 by construction
+        // ((b0 (S0 >> 4)) >> 16) + ((b1 (S1 >> 4)) >> 16) + 2, the 2 riding in the first product as 2 << 16; <= 255 for weight pairs
+        // that sum to 2049 at most, which OpenCV's always do (tests/test_kernel_invariants.py)
         word |= (uint32_t)((((b0 * (s0 >> 4) + 0x20000) >> 16) + ((b1 * (s1 >> 4)) >> 16)) >> 2) << (8 * c);
     }
     return word;

@@ -276,7 +276,8 @@ __global__ void __launch_bounds__(ROWS_THREADS) preprocess_rows_kernel(ResizePla
 // the kernels above (640x360 -> 256x144 reads 15 source bytes per output pixel where 1080p reads 45): FOUR ADJACENT output
 // pixels per thread.  The source rows of four output rows are staged as in the row kernel; a thread fetches the packed taps of
 // its four columns once (two 16-byte loads of plan.xpack) and uses them for two output rows; the vertical pass needs no clamp
-// (the weights of a pair are non-negative and sum to 2048, so the result is at most 255); and the outputs leave straight from
+// (the weights of a pair are non-negative and sum to 2048 -- 2049 at most, for a pathological fraction -- and up to that sum in
+// both passes the result is at most 255: tests/test_kernel_invariants.py); and the outputs leave straight from
 // registers -- a float4 per channel plane (the division by 255 is a 256-entry table of correctly rounded quotients in shared
 // memory) or the twelve packed BGR bytes as three words -- with no second pass through shared memory.
 // Rows need not be 16-byte aligned (854-pixel rows are 2,562 bytes): a row is staged at its own offset within a 16-byte chunk,
