@@ -51,3 +51,35 @@ gb = n * rows * w * 3 / 1e9
 for name, fn in (("contiguous", contiguous), ("strided 2-D (cutdet_upload_frames)", strided), ("strided, two streams", two_streams)):
     ms = timed(fn)
     print(f"{name:38s} {ms:8.2f} ms  {gb / ms * 1e3:6.2f} GB/s", flush=True)
+
+# ---- the same uploads with the kernels of the previous chunk running beside them (FramePipeline.push_host), per step
+from cutdet import pipeline
+from frameID.net import load_default_net
+net, _ = load_default_net()
+native = net.eval().to("cuda")._native()
+del dev, flat
+for lanes in (1, 2):
+    pipe = pipeline.FramePipeline(native, plan, n, 16 * n, "cuda", lanes=lanes)
+    for _ in range(2):
+        pipe.push_host(host)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(8):
+        pipe.push_host(host)
+    pipe.finish()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 8
+    print(f"push_host pipeline, lanes={lanes}:          {ms:8.2f} ms per chunk  {gb / ms * 1e3:6.2f} GB/s", flush=True)
+    del pipe
+# uploads alone through the pipeline's copy stream and staging buffers, no kernels
+stage = [torch.empty((n, rows, w, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+cs = torch.cuda.Stream()
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record(cs)
+for i in range(8):
+    strided(host, stage[i & 1], cs)
+b.record(cs); torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 8
+print(f"uploads alone, two staging buffers:        {ms:8.2f} ms per chunk  {gb / ms * 1e3:6.2f} GB/s", flush=True)
