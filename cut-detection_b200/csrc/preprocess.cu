@@ -272,16 +272,17 @@ __global__ void __launch_bounds__(ROWS_THREADS) preprocess_rows_kernel(ResizePla
     }
 }
 
-// Two-tap resizes again (bilinear, and the exact 2x2 mean), for the geometries where the arithmetic -- not the memory -- paces
-// the kernels above (640x360 -> 256x144 reads 15 source bytes per output pixel where 1080p reads 45): FOUR ADJACENT output
-// pixels per thread.  The source rows of four output rows are staged as in the row kernel; a thread fetches the packed taps of
+// The resize once more, for all the geometries where instructions -- not the memory -- pace the kernels above (640x360 -> 256x144
+// reads 15 source bytes per output pixel where 1080p reads 45; even the 720p gather, which computes nothing, was short of issue
+// slots at 78 % of the HBM rate): FOUR ADJACENT output pixels per thread.  The source rows of four output rows are staged as in the row kernel; a thread fetches the packed taps of
 // its four columns once (two 16-byte loads of plan.xpack) and uses them for two output rows; the vertical pass needs no clamp
 // (the weights of a pair are non-negative and sum to 2048 -- 2049 at most, for a pathological fraction -- and up to that sum in
 // both passes the result is at most 255: tests/test_kernel_invariants.py); and the outputs leave straight from
 // registers -- a float4 per channel plane (the division by 255 is a 256-entry table of correctly rounded quotients in shared
 // memory) or the twelve packed BGR bytes as three words -- with no second pass through shared memory.
-// Rows need not be 16-byte aligned (854-pixel rows are 2,562 bytes): a row is staged at its own offset within a 16-byte chunk,
-// whole chunks by cp.async, the partial chunks at its two ends byte by byte, so nothing outside the row is ever read.
+// Rows need not be 16-byte aligned (854-pixel rows are 2,562 bytes): a row is staged at its own offset within a 16-byte chunk, as
+// whole chunks from the aligned address below it -- up to 15 bytes of its neighbours come along, inside this launch's frames -- and
+// only the first and last rows of a batch byte by byte at their ends, so nothing outside the caller's buffer is ever read.
 constexpr int QUAD_ROWS = 4;
 constexpr int QUAD_THREADS = 128;
 
@@ -303,10 +304,10 @@ __device__ __noinline__ void quads_stage_row(uint8_t *slot, const uint8_t *g, in
 }
 
 // MODE: 0 = bilinear taps, 1 = the exact 2x2 mean, 2 = one source pixel per output pixel (integer-scale gathers such as 720p ->
-// 256x144, plain copies: one source row per output row, no arithmetic).  ALIGNED: every row starts on a 16-byte boundary (then a row sits at the
-// start of its slot and both rows of a pair share the tap offsets).  Compile-time, because the kernel runs within a few per cent
-// of the memory roofline only while its instruction count stays where it is: with both as run-time switches 640x360 fell from 90 %
-// of the HBM peak to 72 % (profiles/r02_k1_matrix_quads.txt).
+// 256x144, plain copies: one source row per output row, no arithmetic).  ALIGNED: every row starts on a 16-byte boundary (then a
+// row sits at the start of its slot and both rows of a pair share the tap offsets).  Compile-time, because the kernel runs within a
+// few per cent of the memory roofline only while its instruction count stays where it is: with the 2x2 mean and the alignment as
+// run-time switches 640x360 fell from 90 % of the HBM peak to 72 % (profiles/r02_k1_matrix_quads_runtime_switches.txt).
 template <int OUT, int MODE, bool ALIGNED>
 __global__ void __launch_bounds__(QUAD_THREADS, 10) preprocess_quads_kernel(ResizePlanDev plan, const uint8_t *__restrict__ frames,
                                                                            int64_t frame_stride, int64_t row_pitch, int compact,
